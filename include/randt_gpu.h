@@ -1,0 +1,184 @@
+/* randt_gpu.h — C-ABI of the B200-native NDT scan-matching hot path.
+ *
+ * Drop-in boundary for IGMR-RWTH/RaNDT-SLAM's ndt_representation voxelisation and ndt_registration
+ * cost/Jacobian evaluation.  The reference has no FFI/plugin mechanism; its seam is the
+ * C++ surface of the catkin libraries `ndt_representation` / `ndt_registration` plus the Ceres
+ * `CostFunction::Evaluate` interface.  Each entry point below names the reference interface it replaces
+ * (R/ = ros/ndt_radar_slam/ in the reference tree).  The host-side C++ mirror of the reference classes
+ * (randt_slam_b200/host/) and the Python test/bench bindings are thin layers over exactly these symbols.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no C++/torch types.  All functions return 0 on success, <0 on error
+ *    (RANDT_E_*); they never throw.  randt_last_error(ctx) returns a description of the last failure on ctx.
+ *  - a randt_ctx owns one CUDA stream (or borrows the caller's); contexts are independent and may be used
+ *    from different host threads concurrently (one thread per context at a time).  No global mutable state.
+ *  - "cell" = 12 float32: mean (x, y, intensity) then row-major 3x3 covariance — the values
+ *    Cell::new_mean_ / new_cov_ hold (R/include/ndt_representation/ndt_cell.h:167-168).
+ *  - "pose" = 4 float64 in Sophus::SE2d::data() order [cos, sin, tx, ty] (R/src/ndt_registration/ndt_matcher.cpp:233,292)
+ *    for the SE2 variants, or 3 float64 [x, y, theta] for the vector variants.
+ *  - *_dev entry points take device pointers, enqueue on the context stream and do not synchronise.
+ */
+#ifndef RANDT_GPU_H
+#define RANDT_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RANDT_API __attribute__((visibility("default")))
+
+enum {
+  RANDT_OK = 0,
+  RANDT_E_INVALID = -1,     /* bad argument */
+  RANDT_E_CUDA = -2,        /* CUDA runtime error (see randt_last_error) */
+  RANDT_E_CAPACITY = -3,    /* input exceeds a kernel capacity (e.g. label span, scan too large) */
+  RANDT_E_NONFINITE = -4,   /* evaluation produced non-finite output (singular covariance sum, ...) */
+  RANDT_E_NOMEM = -5
+};
+
+/* residual functor variants — R/include/ndt_registration/ceres_residuals.h */
+enum {
+  RANDT_VAR_SE2_INTENSITY = 0,  /* NDTFrameToMapIntensityFactorResidualSE2  :520-552  (live in every shipped config) */
+  RANDT_VAR_SE2_XY = 1,         /* NDTFrameToMapFactorResidualSE2           :454-484 */
+  RANDT_VAR_VEC_INTENSITY = 2,  /* NDTFrameToMapIntensityFactorResidual     :486-518  params [x, y | theta] */
+  RANDT_VAR_VEC_XY = 3          /* NDTFrameToMapFactorResidual              :421-451  params [x, y | theta] */
+};
+
+/* robust loss — R/include/ndt_registration/ceres_loss_functions.h:9-48, wrapped in ceres::ScaledLoss(loss, weight)
+ * as R/src/ndt_registration/ndt_matcher.cpp:392,479 does. */
+enum { RANDT_LOSS_NONE = 0, RANDT_LOSS_BARRON = 1, RANDT_LOSS_WELSCH = 2 };
+typedef struct randt_loss {
+  int32_t kind;
+  double scale;      /* a      : loss_function_scale */
+  double alpha;      /* alpha  : loss_function_convexity (Barron) */
+  double mu;         /* GNC control parameter (>= 1 in the reference's schedule) */
+  double weight;     /* ScaledLoss factor, e.g. ndt_weight / (n_cells * k) */
+} randt_loss;
+
+/* nearest-neighbour metric of Map::getClosestCells — R/src/ndt_representation/ndt_map.cpp:101-151 */
+enum { RANDT_LOOKUP_MAHALANOBIS_INTENSITY = 0, RANDT_LOOKUP_EUCLID_XY = 1 };
+
+/* voxel grid + map geometry: RadarPreprocessorParameters / NDTMapParameters after NDTSlam::readParameters
+ * (R/include/ndt_slam/ndt_slam_parameters.h:17-50, R/src/ndt_slam/ndt_slam.cpp:653-654,691) */
+typedef struct randt_grid_params {
+  float max_range;        /* radar_preprocessor/max_range (float, as ClusterGenerator::max_sensor_range_) */
+  int32_t n_clusters;     /* int((2*max_range/resolution)^2) */
+  int32_t min_points;     /* ndt_map/min_points_per_cell; a cell needs n > min_points */
+  int32_t size_x, size_y; /* map size in cells (after the int /= resolution truncation) */
+  double resolution;      /* ndt_map/resolution */
+  double max_linf;        /* ndt_map/max_neighbor_linf_distance */
+} randt_grid_params;
+
+/* one fused evaluation result per segment (= per pose): 24 float64 */
+enum {
+  RANDT_FUSED_H = 0,       /* [16] row-major 4x4  sum J~^T J~  (ambient parameters; 3x3 in the top-left for VEC variants) */
+  RANDT_FUSED_G = 16,      /* [4]  sum J~^T r~ */
+  RANDT_FUSED_COST = 20,   /* sum 0.5 * rho(r^2)  (what ceres reports as cost for these blocks) */
+  RANDT_FUSED_MAXR = 21,   /* max raw residual (GNC mu seed, ndt_matcher.cpp:387) */
+  RANDT_FUSED_SUMSQ = 22,  /* sum raw r^2 */
+  RANDT_FUSED_N = 23,      /* residual blocks in the segment */
+  RANDT_FUSED_STRIDE = 24
+};
+
+typedef struct randt_ctx randt_ctx;
+typedef struct randt_map randt_map;          /* a batch of B NDT maps resident on the device */
+typedef struct randt_problem randt_problem;  /* cell tables + frozen pair list (construction-time state of addNDTFactor) */
+
+/* ---- context ------------------------------------------------------------------------------------------ */
+RANDT_API int randt_version(void);
+/* stream: a cudaStream_t to borrow (e.g. the caller's current stream), or NULL to create an owned non-blocking stream. */
+RANDT_API int randt_ctx_create(int device, void* stream, randt_ctx** out);
+RANDT_API void randt_ctx_destroy(randt_ctx* ctx);
+RANDT_API const char* randt_last_error(const randt_ctx* ctx);
+RANDT_API void* randt_ctx_stream(const randt_ctx* ctx);
+RANDT_API int randt_ctx_sync(randt_ctx* ctx);
+/* number of kernels this context has launched since creation (bench "gpu_launches") */
+RANDT_API uint64_t randt_ctx_launch_count(const randt_ctx* ctx);
+
+/* returns (and clears) the number of degenerate pairs K3 has met on this context: pairs whose d^T B^-1 d is negative or
+ * non-finite (singular covariance sum).  They are excluded from the fused sums and emitted as NaN by randt_eval_emit. */
+RANDT_API int randt_ctx_take_bad_pairs(randt_ctx* ctx, uint64_t* count);
+/* pinned host / device buffers and stream-ordered copies for callers that stage their own data (bench, host adapters) */
+RANDT_API void* randt_host_alloc(size_t bytes);
+RANDT_API void randt_host_free(void* p);
+RANDT_API void* randt_dev_alloc(size_t bytes);
+RANDT_API void randt_dev_free(void* p);
+RANDT_API int randt_memcpy_h2d(randt_ctx* ctx, void* dst, const void* src, size_t bytes);
+RANDT_API int randt_memcpy_d2h(randt_ctx* ctx, void* dst, const void* src, size_t bytes);
+
+/* ---- K1: voxelisation ---------------------------------------------------------------------------------
+ * Replaces Grid::cluster (R/src/radar_preprocessing/grid.cpp:7-14), ClusterGenerator::labelClouds
+ * (R/src/radar_preprocessing/radar_preprocessor.cpp:151-169), Map::insertCluster (R/src/ndt_representation/ndt_map.cpp:238-245)
+ * and Cell::addPointCloud/updateCell (R/src/ndt_representation/ndt_cell.cpp:25-114) — i.e. what
+ * HierarchicalMap::addClusters does per scan (R/src/local_fuser/local_fuser.cpp:102-105).
+ * pts4: float32 [n_pts_total][4] = (x, y, z-unused, intensity); scan b owns points [scan_off[b], scan_off[b+1]).
+ * pts_on_device != 0: pts4 is a device pointer (scan_off is always a host pointer). */
+RANDT_API int randt_voxelize(randt_ctx* ctx, const float* pts4, const uint32_t* scan_off, uint32_t n_scans,
+                             const randt_grid_params* params, int pts_on_device, randt_map** out);
+
+/* ---- maps ---------------------------------------------------------------------------------------------- */
+/* Upload B maps built elsewhere.  cell_off[B+1]; npts may be NULL (treated as 0); slot may be NULL, in which case the
+ * dense lookup table grid_indizes_ is rebuilt from the cell means in cell order (later cell wins, as insertCluster does). */
+RANDT_API int randt_map_upload(randt_ctx* ctx, const float* cells, const uint32_t* npts, const uint32_t* cell_off, uint32_t n_maps,
+                               const int32_t* slot, const randt_grid_params* params, randt_map** out);
+RANDT_API int randt_map_info(const randt_map* map, uint32_t* n_maps, uint32_t* n_cells_total, uint32_t* n_slots);
+/* any output pointer may be NULL.  cells [n_cells_total][12], npts [n_cells_total], labels [n_cells_total] (voxelised maps only),
+ * cell_off [n_maps+1], slot [n_maps][n_slots] */
+RANDT_API int randt_map_download(randt_ctx* ctx, const randt_map* map, float* cells, uint32_t* npts, int32_t* labels,
+                                 uint32_t* cell_off, int32_t* slot);
+/* Map::transformMap / Cell::transformCell (R/src/ndt_representation/ndt_map.cpp:177-182, ndt_cell.cpp:117-123).
+ * trans: float32 [n_maps][4] = (cos, sin, tx, ty) on the host.  The slot table is NOT updated (neither is the reference's). */
+RANDT_API int randt_map_transform(randt_ctx* ctx, randt_map* map, const float* trans);
+/* Map::mergeMapCell + Cell::operator+= (R/src/ndt_representation/ndt_map.cpp:191-207, ndt_cell.h:133-142): merge moving map b
+ * into fixed map b for every b.  `fixed` is rebuilt in place (cell order: existing cells, then appended cells in moving order). */
+RANDT_API int randt_map_merge(randt_ctx* ctx, randt_map* fixed, const randt_map* moving);
+RANDT_API void randt_map_destroy(randt_map* map);
+
+/* ---- K2: association ----------------------------------------------------------------------------------
+ * Replaces the association half of Matcher::addNDTFactor (R/src/ndt_registration/ndt_matcher.cpp:200-217,249-253):
+ * transform each moving cell by the initial guess (float32), Map::getClosestCells (ndt_map.cpp:101-151,163-175) with the
+ * expanding window, Mahalanobis (ndt_cell.cpp:172-176) or Euclidean metric, first k by (distance, index).
+ * Problem b pairs moving map b with fixed map b at pose0[b] (float64 [n_maps][4], host).  The resulting problem has one
+ * segment per map; pairs are stored in the reference's residual-block order. */
+RANDT_API int randt_associate(randt_ctx* ctx, const randt_map* fixed, const randt_map* moving, const double* pose0, int k, int metric,
+                              randt_problem** out);
+
+/* ---- problems -------------------------------------------------------------------------------------------
+ * A problem snapshots the cell tables (like the functors copy their cells, ceres_residuals.h:528-535) and a frozen pair list.
+ * pair_m / pair_f index rows of cells_m / cells_f; segment s owns pairs [seg_off[s], seg_off[s+1]) and is evaluated at pose s. */
+RANDT_API int randt_problem_create(randt_ctx* ctx, const float* cells_m, uint32_t n_m, const float* cells_f, uint32_t n_f,
+                                   const uint32_t* pair_m, const uint32_t* pair_f, uint32_t n_pairs, const uint32_t* seg_off,
+                                   uint32_t n_segments, randt_problem** out);
+RANDT_API int randt_problem_info(const randt_problem* p, uint32_t* n_segments, uint32_t* n_pairs, uint32_t* n_m, uint32_t* n_f);
+/* any pointer may be NULL */
+RANDT_API int randt_problem_download(randt_ctx* ctx, const randt_problem* p, uint32_t* pair_m, uint32_t* pair_f, uint32_t* seg_off);
+/* the snapshotted cell tables: cells_m [n_m][12], cells_f [n_f][12]; either may be NULL */
+RANDT_API int randt_problem_download_cells(randt_ctx* ctx, const randt_problem* p, float* cells_m, float* cells_f);
+RANDT_API void randt_problem_destroy(randt_problem* p);
+
+/* ---- K3: residual / Jacobian evaluation ---------------------------------------------------------------
+ * Replaces ceres::AutoDiffCostFunction<NDTFrameToMap*Residual*, 1, ...>::Evaluate over every residual block of the problem
+ * (hot loop C), the per-block robust-loss Corrector, and the normal-equation accumulation.
+ *
+ * EMIT: r[n_pairs] and J[n_pairs][np] (np = 4 SE2 variants, 3 VEC variants), raw (no loss) — exactly what Evaluate returns per
+ * block.  J == NULL gives the residual-only pass used for the GNC seed (ndt_matcher.cpp:382-387). */
+RANDT_API int randt_eval_emit(randt_ctx* ctx, const randt_problem* p, int variant, const double* poses, double* r, double* J);
+RANDT_API int randt_eval_emit_dev(randt_ctx* ctx, const randt_problem* p, int variant, const double* d_poses, double* d_r, double* d_J);
+/* FUSED: per segment, loss-corrected J~^T J~, J~^T r~, cost, max raw residual (layout RANDT_FUSED_*).  mu_per_seg (may be NULL)
+ * overrides loss->mu per segment.  want_jac == 0 computes cost/max/sumsq only (trust-region candidate evaluation, BnB sweep). */
+RANDT_API int randt_eval_fused(randt_ctx* ctx, const randt_problem* p, int variant, const double* poses, const randt_loss* loss,
+                               const double* mu_per_seg, int want_jac, double* out);
+RANDT_API int randt_eval_fused_dev(randt_ctx* ctx, const randt_problem* p, int variant, const double* d_poses, const randt_loss* loss,
+                                   const double* d_mu_per_seg, int want_jac, double* d_out);
+/* Cost of ONE segment's pair list at many candidate poses (the inner loop of Matcher::estimateTransformGlobalBNB,
+ * ndt_matcher.cpp:560-576): cost[i] = sum over the pairs of segment `seg` of 0.5 * rho(r^2) at poses[i]. */
+RANDT_API int randt_sweep_costs(randt_ctx* ctx, const randt_problem* p, uint32_t seg, int variant, const double* poses, uint32_t n_poses,
+                                const randt_loss* loss, double* cost);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RANDT_GPU_H */

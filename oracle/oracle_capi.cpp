@@ -1,0 +1,216 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see ndt_oracle.h header).  PARITY UNPINNED.
+// Flat-array C exports of the CPU restatement so the Python tests / bench baseline can drive it via ctypes.
+#include <chrono>
+#include <cstdio>
+#include <thread>
+
+#include <atomic>
+
+#include "lm_oracle.h"
+
+using namespace orc;
+
+namespace {
+NdtMap view_map(const float* cells, const uint32_t* npts, int n, const int32_t* slot, int size_x, int size_y, double res, double max_linf) {
+  NdtMap m;
+  MapGeom g; g.set(size_x, size_y, res, max_linf);
+  m.geom = g;
+  m.cells.resize(n);
+  if (n) std::memcpy(m.cells.data(), cells, sizeof(Cell12) * n);
+  m.npts.assign(n, 0);
+  if (npts) for (int i = 0; i < n; ++i) m.npts[i] = npts[i];
+  if (slot) m.slot.assign(slot, slot + g.n_slots()); else m.slot.assign(g.n_slots(), -1);
+  return m;
+}
+Loss make_loss(int kind, double a, double alpha, double mu, double weight) {
+  Loss l; l.kind = kind; l.a = a; l.alpha = alpha; l.mu = mu; l.weight = weight; return l;
+}
+}  // namespace
+
+extern "C" {
+
+int orc_n_clusters(double max_range, double resolution) { return n_clusters_from_params(max_range, resolution); }
+int orc_grid_row_size(size_t n_clusters) { return grid_row_size(n_clusters); }
+
+void orc_grid_labels(const float* pts4, size_t n, size_t n_clusters, float max_range, int32_t* labels) {
+  grid_labels(reinterpret_cast<const Pt4*>(pts4), n, n_clusters, max_range, labels);
+}
+
+uint32_t orc_coord_to_index(int size_x, int size_y, double res, float x, float y) {
+  MapGeom g; g.set(size_x, size_y, res, 0.0);
+  return coord_to_index(g, x, y);
+}
+
+void orc_sym2_eigen(float a00, float a10, float a11, float* ev2, float* V4) {
+  float V[2][2];
+  sym2_eigen_f(a00, a10, a11, ev2, V);
+  V4[0] = V[0][0]; V4[1] = V[0][1]; V4[2] = V[1][0]; V4[3] = V[1][1];
+}
+
+int orc_cell_from_points(const float* pts4, size_t n, int min_points, float* cell12) {
+  Cell12 c;
+  if (!cell_from_points(reinterpret_cast<const Pt4*>(pts4), nullptr, n, min_points, c)) return 0;
+  std::memcpy(cell12, &c, sizeof(c));
+  return 1;
+}
+
+// returns number of cells (<= cap); slot_out has size_x*size_y entries
+int orc_voxelize(const float* pts4, size_t n, size_t n_clusters, float max_range, int min_points, int size_x, int size_y,
+                 double res, double max_linf, float* cells_out, uint32_t* npts_out, int32_t* labels_out, int32_t* slot_out,
+                 int cap, int* dropped) {
+  MapGeom g; g.set(size_x, size_y, res, max_linf);
+  NdtMap m;
+  std::vector<int32_t> labels;
+  voxelize(reinterpret_cast<const Pt4*>(pts4), n, n_clusters, max_range, min_points, g, m, &labels);
+  const int nc = (int)m.cells.size();
+  if (nc > cap) return -nc;
+  if (nc) std::memcpy(cells_out, m.cells.data(), sizeof(Cell12) * nc);
+  for (int i = 0; i < nc; ++i) { if (npts_out) npts_out[i] = m.npts[i]; if (labels_out) labels_out[i] = labels[i]; }
+  if (slot_out) std::memcpy(slot_out, m.slot.data(), sizeof(int32_t) * m.slot.size());
+  if (dropped) *dropped = m.dropped_out_of_map;
+  return nc;
+}
+
+void orc_transform_cells(float* cells, size_t n, float c, float s, float tx, float ty) {
+  Cell12* cc = reinterpret_cast<Cell12*>(cells);
+  for (size_t i = 0; i < n; ++i) transform_cell(cc[i], c, s, tx, ty);
+}
+
+// in-place merge of a moving map into a fixed map (arrays have capacity cap_f); returns new fixed cell count or -needed
+int orc_merge_map_cell(float* f_cells, uint32_t* f_npts, int n_f, int cap_f, int32_t* f_slot, int size_x, int size_y, double res,
+                       const float* m_cells, const uint32_t* m_npts, int n_m) {
+  NdtMap F = view_map(f_cells, f_npts, n_f, f_slot, size_x, size_y, res, 0.0);
+  NdtMap M = view_map(m_cells, m_npts, n_m, nullptr, size_x, size_y, res, 0.0);
+  merge_map_cell(F, M);
+  const int nf = (int)F.cells.size();
+  if (nf > cap_f) return -nf;
+  std::memcpy(f_cells, F.cells.data(), sizeof(Cell12) * nf);
+  for (int i = 0; i < nf; ++i) f_npts[i] = F.npts[i];
+  std::memcpy(f_slot, F.slot.data(), sizeof(int32_t) * F.slot.size());
+  return nf;
+}
+
+// returns P (number of pairs) or -needed when cap is too small
+int orc_associate(const float* f_cells, int n_f, const int32_t* f_slot, int size_x, int size_y, double res, double max_linf,
+                  const float* m_cells, int n_m, const double* pose4, int k, int metric, uint32_t* im_out, uint32_t* jf_out, int cap) {
+  NdtMap F = view_map(f_cells, nullptr, n_f, f_slot, size_x, size_y, res, max_linf);
+  NdtMap M = view_map(m_cells, nullptr, n_m, nullptr, size_x, size_y, res, max_linf);
+  PairList pl;
+  associate(F, M, pose4, k, metric, pl);
+  const int P = (int)pl.im.size();
+  if (P > cap) return -P;
+  for (int i = 0; i < P; ++i) { im_out[i] = pl.im[i]; jf_out[i] = pl.jf[i]; }
+  return P;
+}
+
+// mode: 0 = autodiff (Jet), 1 = closed form (VAR_SE2_INTENSITY only), 2 = value only
+void orc_eval_pairs(int variant, int mode, const float* cells_m, const float* cells_f, const uint32_t* im, const uint32_t* jf,
+                    size_t P, const double* params, double* r_out, double* J_out) {
+  const Cell12* cm = reinterpret_cast<const Cell12*>(cells_m);
+  const Cell12* cf = reinterpret_cast<const Cell12*>(cells_f);
+  const int np = variant_num_params(variant);
+  for (size_t p = 0; p < P; ++p) {
+    double r, J[4];
+    if (mode == 0) eval_pair_autodiff(variant, params, cm[im[p]], cf[jf[p]], &r, J);
+    else if (mode == 1) eval_pair_closed_form(params, cm[im[p]], cf[jf[p]], &r, J);
+    else { r = eval_pair_value(variant, params, cm[im[p]], cf[jf[p]]); }
+    r_out[p] = r;
+    if (J_out && mode != 2) for (int a = 0; a < np; ++a) J_out[p * np + a] = J[a];
+  }
+}
+
+void orc_loss_eval(int kind, double a, double alpha, double mu, double weight, double s, double* rho3) {
+  make_loss(kind, a, alpha, mu, weight).evaluate(s, rho3);
+}
+
+void orc_corrector(double sq_norm, const double* rho3, double* out3) {
+  Corrector c(sq_norm, rho3);
+  out3[0] = c.sqrt_rho1; out3[1] = c.residual_scaling; out3[2] = c.alpha_sq_norm;
+}
+
+double orc_gnc_initial_mu(double max_residual, double loss_scale, double divisor, int steps) {
+  return gnc_initial_mu(max_residual, loss_scale, divisor, steps);
+}
+
+// out24 = H[16], g[4], cost, max_r, sum_sq, n
+static void pack_fused(const FusedOut& f, double* out24) {
+  for (int i = 0; i < 16; ++i) out24[i] = f.H[i];
+  for (int i = 0; i < 4; ++i) out24[16 + i] = f.g[i];
+  out24[20] = f.cost; out24[21] = f.max_r; out24[22] = f.sum_sq; out24[23] = (double)f.n;
+}
+
+void orc_fused(int variant, const float* cells_m, const float* cells_f, const uint32_t* im, const uint32_t* jf, size_t P,
+               const double* params, int loss_kind, double a, double alpha, double mu, double weight, int want_jac, double* out24) {
+  FusedOut f;
+  accumulate_pairs(variant, params, reinterpret_cast<const Cell12*>(cells_m), reinterpret_cast<const Cell12*>(cells_f), im, jf, P,
+                   make_loss(loss_kind, a, alpha, mu, weight), want_jac != 0, f);
+  pack_fused(f, out24);
+}
+
+int orc_hw_threads() { return (int)std::thread::hardware_concurrency(); }
+
+// Batched: S segments; pairs of segment s are [seg_off[s], seg_off[s+1]); im/jf index the concatenated tables.
+// pose stride = 4 (SE2 variants) or 3.  mu may be per segment (mu_per_seg != NULL) else scalar `mu`.
+// Returns wall seconds for `repeats` passes.  closed_form = 1 uses the closed form instead of the Jet path (informational).
+double orc_fused_batch(int variant, const float* cells_m, const float* cells_f, const uint32_t* im, const uint32_t* jf,
+                       const uint32_t* seg_off, int S, const double* poses, int loss_kind, double a, double alpha, double mu,
+                       double weight, const double* mu_per_seg, int want_jac, double* out24, int n_threads, int repeats) {
+  const Cell12* cm = reinterpret_cast<const Cell12*>(cells_m);
+  const Cell12* cf = reinterpret_cast<const Cell12*>(cells_f);
+  const int np = variant_num_params(variant);
+  const auto t0 = std::chrono::steady_clock::now();
+  const int T = n_threads > 0 ? n_threads : 1;
+  for (int rep = 0; rep < repeats; ++rep) {
+    std::atomic<int> next(0);
+    auto worker = [&]() {
+      for (;;) {
+        const int s0 = next.fetch_add(4);
+        if (s0 >= S) break;
+        for (int s = s0; s < std::min(S, s0 + 4); ++s) {
+          FusedOut f;
+          const Loss loss = make_loss(loss_kind, a, alpha, mu_per_seg ? mu_per_seg[s] : mu, weight);
+          accumulate_pairs(variant, poses + (size_t)s * np, cm, cf, im + seg_off[s], jf + seg_off[s], seg_off[s + 1] - seg_off[s],
+                           loss, want_jac != 0, f);
+          pack_fused(f, out24 + (size_t)s * 24);
+        }
+      }
+    };
+    if (T == 1) { worker(); }
+    else {
+      std::vector<std::thread> pool;
+      for (int t = 0; t < T; ++t) pool.emplace_back(worker);
+      for (auto& th : pool) th.join();
+    }
+  }
+  const auto t1 = std::chrono::steady_clock::now();
+  return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// Matcher::estimateLoopConstraint restated.  out = pose[4], score, gnc_solves, total_iterations, total_evals, mu_first ; returns status
+int orc_loop_constraint(const float* f_cells, int n_f, const int32_t* f_slot, int size_x, int size_y, double res, double max_linf,
+                        const float* m_cells, int n_m, const double* pose4, int k, int metric, int variant,
+                        double matcher_loss_scale, double loop_scale, double alpha, double divisor, int max_gnc_steps,
+                        int max_iterations, int on_manifold, double loss_weight, const uint32_t* im_in, const uint32_t* jf_in, int P_in,
+                        double* out9) {
+  NdtMap F = view_map(f_cells, nullptr, n_f, f_slot, size_x, size_y, res, max_linf);
+  NdtMap M = view_map(m_cells, nullptr, n_m, nullptr, size_x, size_y, res, max_linf);
+  LmOptions opt; opt.max_num_iterations = max_iterations;
+  PairList pl;
+  if (im_in && P_in > 0) { pl.im.assign(im_in, im_in + P_in); pl.jf.assign(jf_in, jf_in + P_in); }
+  LoopConstraintResult R = loop_constraint(F, M, pose4, k, metric, variant, matcher_loss_scale, loop_scale, alpha, divisor,
+                                           max_gnc_steps, opt, on_manifold != 0, loss_weight, (im_in && P_in > 0) ? &pl : nullptr);
+  for (int i = 0; i < 4; ++i) out9[i] = R.pose[i];
+  out9[4] = R.score; out9[5] = R.gnc_solves; out9[6] = R.total_iterations; out9[7] = R.total_evals; out9[8] = R.gnc_mu_first;
+  return R.status;
+}
+
+void orc_sweep_costs(int variant, const float* cells_m, const float* cells_f, const uint32_t* im, const uint32_t* jf, size_t P,
+                     int loss_kind, double a, double alpha, double mu, double weight, const double* poses, size_t S, double* cost_out) {
+  sweep_costs(variant, reinterpret_cast<const Cell12*>(cells_m), reinterpret_cast<const Cell12*>(cells_f), im, jf, P,
+              make_loss(loss_kind, a, alpha, mu, weight), poses, S, cost_out);
+}
+
+void orc_se2_plus(const double* T4, const double* d3, double* out4) { se2_plus(T4, d3, out4); }
+void orc_se2_plus_jacobian(const double* T4, double* J12) { se2_plus_jacobian(T4, J12); }
+
+}  // extern "C"

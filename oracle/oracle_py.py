@@ -1,0 +1,252 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  ctypes view of oracle/_build/liboracle.so.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this
+module.  PARITY UNPINNED: see oracle/ndt_oracle.h.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
+
+VAR_SE2_INTENSITY, VAR_SE2_XY, VAR_VEC_INTENSITY, VAR_VEC_XY = 0, 1, 2, 3
+LOSS_NONE, LOSS_BARRON, LOSS_WELSCH = 0, 1, 2
+LOOKUP_MAHALANOBIS, LOOKUP_EUCLID = 0, 1
+
+
+def build(force=False):
+    """Compile the C++ restatement (g++, seconds).  Safe to call repeatedly."""
+    srcs = [os.path.join(_HERE, f) for f in ("oracle_capi.cpp", "ndt_oracle.h", "lm_oracle.h", "jet.h", "Makefile")]
+    if (not force) and os.path.exists(_LIB_PATH) and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in srcs):
+        return _LIB_PATH
+    subprocess.run(["make", "-C", _HERE, "-s"], check=True)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB_PATH)
+        _sig(_lib)
+    return _lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _sig(L):
+    f, d, i, u, sz = C.c_float, C.c_double, C.c_int, C.c_uint32, C.c_size_t
+    pf, pd, pi, pu = C.POINTER(f), C.POINTER(d), C.POINTER(C.c_int32), C.POINTER(u)
+    L.orc_n_clusters.restype = i; L.orc_n_clusters.argtypes = [d, d]
+    L.orc_grid_row_size.restype = i; L.orc_grid_row_size.argtypes = [sz]
+    L.orc_grid_labels.restype = None; L.orc_grid_labels.argtypes = [pf, sz, sz, f, pi]
+    L.orc_coord_to_index.restype = u; L.orc_coord_to_index.argtypes = [i, i, d, f, f]
+    L.orc_sym2_eigen.restype = None; L.orc_sym2_eigen.argtypes = [f, f, f, pf, pf]
+    L.orc_cell_from_points.restype = i; L.orc_cell_from_points.argtypes = [pf, sz, i, pf]
+    L.orc_voxelize.restype = i
+    L.orc_voxelize.argtypes = [pf, sz, sz, f, i, i, i, d, d, pf, pu, pi, pi, i, C.POINTER(i)]
+    L.orc_transform_cells.restype = None; L.orc_transform_cells.argtypes = [pf, sz, f, f, f, f]
+    L.orc_merge_map_cell.restype = i; L.orc_merge_map_cell.argtypes = [pf, pu, i, i, pi, i, i, d, pf, pu, i]
+    L.orc_associate.restype = i; L.orc_associate.argtypes = [pf, i, pi, i, i, d, d, pf, i, pd, i, i, pu, pu, i]
+    L.orc_eval_pairs.restype = None; L.orc_eval_pairs.argtypes = [i, i, pf, pf, pu, pu, sz, pd, pd, pd]
+    L.orc_loss_eval.restype = None; L.orc_loss_eval.argtypes = [i, d, d, d, d, d, pd]
+    L.orc_corrector.restype = None; L.orc_corrector.argtypes = [d, pd, pd]
+    L.orc_gnc_initial_mu.restype = d; L.orc_gnc_initial_mu.argtypes = [d, d, d, i]
+    L.orc_fused.restype = None; L.orc_fused.argtypes = [i, pf, pf, pu, pu, sz, pd, i, d, d, d, d, i, pd]
+    L.orc_hw_threads.restype = i; L.orc_hw_threads.argtypes = []
+    L.orc_fused_batch.restype = d
+    L.orc_fused_batch.argtypes = [i, pf, pf, pu, pu, pu, i, pd, i, d, d, d, d, pd, i, pd, i, i]
+    L.orc_loop_constraint.restype = i
+    L.orc_loop_constraint.argtypes = [pf, i, pi, i, i, d, d, pf, i, pd, i, i, i, d, d, d, d, i, i, i, d, pu, pu, i, pd]
+    L.orc_sweep_costs.restype = None; L.orc_sweep_costs.argtypes = [i, pf, pf, pu, pu, sz, i, d, d, d, d, pd, sz, pd]
+    L.orc_se2_plus.restype = None; L.orc_se2_plus.argtypes = [pd, pd, pd]
+    L.orc_se2_plus_jacobian.restype = None; L.orc_se2_plus_jacobian.argtypes = [pd, pd]
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _u32(a):
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def n_clusters(max_range, resolution):
+    return lib().orc_n_clusters(float(max_range), float(resolution))
+
+
+def grid_labels(pts, n_clusters_, max_range):
+    pts = _f32(pts).reshape(-1, 4)
+    out = np.empty(len(pts), np.int32)
+    lib().orc_grid_labels(_p(pts, C.c_float), len(pts), int(n_clusters_), float(max_range), _p(out, C.c_int32))
+    return out
+
+
+def coord_to_index(size_x, size_y, res, x, y):
+    return lib().orc_coord_to_index(size_x, size_y, float(res), float(x), float(y))
+
+
+def sym2_eigen(a00, a10, a11):
+    ev = np.empty(2, np.float32); V = np.empty(4, np.float32)
+    lib().orc_sym2_eigen(float(a00), float(a10), float(a11), _p(ev, C.c_float), _p(V, C.c_float))
+    return ev, V.reshape(2, 2)
+
+
+def cell_from_points(pts, min_points):
+    pts = _f32(pts).reshape(-1, 4)
+    out = np.empty(12, np.float32)
+    ok = lib().orc_cell_from_points(_p(pts, C.c_float), len(pts), int(min_points), _p(out, C.c_float))
+    return out if ok else None
+
+
+def voxelize(pts, n_clusters_, max_range, min_points, size_x, size_y, res, max_linf=0.0):
+    """-> dict(cells [N,12] f32, npts [N] u32, labels [N] i32, slot [size_x*size_y] i32, dropped)"""
+    pts = _f32(pts).reshape(-1, 4)
+    cap = max(16, len(pts))
+    cells = np.zeros((cap, 12), np.float32); npts = np.zeros(cap, np.uint32); labels = np.zeros(cap, np.int32)
+    slot = np.full(size_x * size_y, -1, np.int32); dropped = C.c_int(0)
+    n = lib().orc_voxelize(_p(pts, C.c_float), len(pts), int(n_clusters_), float(max_range), int(min_points), size_x, size_y,
+                           float(res), float(max_linf), _p(cells, C.c_float), _p(npts, C.c_uint32), _p(labels, C.c_int32),
+                           _p(slot, C.c_int32), cap, C.byref(dropped))
+    assert n >= 0
+    return dict(cells=cells[:n].copy(), npts=npts[:n].copy(), labels=labels[:n].copy(), slot=slot, dropped=dropped.value)
+
+
+def transform_cells(cells, c, s, tx, ty):
+    out = _f32(cells).reshape(-1, 12).copy()
+    lib().orc_transform_cells(_p(out, C.c_float), len(out), float(c), float(s), float(tx), float(ty))
+    return out
+
+
+def merge_map_cell(f_cells, f_npts, f_slot, size_x, size_y, res, m_cells, m_npts):
+    n_f, n_m = len(f_cells), len(m_cells)
+    cap = n_f + n_m + 1
+    fc = np.zeros((cap, 12), np.float32); fc[:n_f] = f_cells
+    fn = np.zeros(cap, np.uint32); fn[:n_f] = f_npts
+    fs = _i32(f_slot).copy()
+    mc = _f32(m_cells).reshape(-1, 12); mn = _u32(m_npts)
+    n = lib().orc_merge_map_cell(_p(fc, C.c_float), _p(fn, C.c_uint32), n_f, cap, _p(fs, C.c_int32), size_x, size_y, float(res),
+                                 _p(mc, C.c_float), _p(mn, C.c_uint32), n_m)
+    assert n >= 0
+    return fc[:n].copy(), fn[:n].copy(), fs
+
+
+def associate(f_cells, f_slot, size_x, size_y, res, max_linf, m_cells, pose, k, metric=LOOKUP_MAHALANOBIS):
+    fc = _f32(f_cells).reshape(-1, 12); mc = _f32(m_cells).reshape(-1, 12); fs = _i32(f_slot); pose = _f64(pose)
+    cap = max(1, len(mc) * max(k, 1))
+    im = np.zeros(cap, np.uint32); jf = np.zeros(cap, np.uint32)
+    P = lib().orc_associate(_p(fc, C.c_float), len(fc), _p(fs, C.c_int32), size_x, size_y, float(res), float(max_linf),
+                            _p(mc, C.c_float), len(mc), _p(pose, C.c_double), int(k), int(metric), _p(im, C.c_uint32),
+                            _p(jf, C.c_uint32), cap)
+    assert P >= 0
+    return im[:P].copy(), jf[:P].copy()
+
+
+def eval_pairs(variant, cells_m, cells_f, im, jf, params, mode=0):
+    """mode 0 autodiff (Jet, = what ceres executes), 1 closed form, 2 value only -> r [P], J [P, np]"""
+    cm = _f32(cells_m).reshape(-1, 12); cf = _f32(cells_f).reshape(-1, 12); im = _u32(im); jf = _u32(jf); params = _f64(params)
+    npar = 4 if variant in (VAR_SE2_INTENSITY, VAR_SE2_XY) else 3
+    r = np.zeros(len(im), np.float64); J = np.zeros((len(im), npar), np.float64)
+    lib().orc_eval_pairs(variant, mode, _p(cm, C.c_float), _p(cf, C.c_float), _p(im, C.c_uint32), _p(jf, C.c_uint32), len(im),
+                         _p(params, C.c_double), _p(r, C.c_double), _p(J, C.c_double))
+    return r, J
+
+
+def loss_eval(kind, a, alpha, mu, weight, s):
+    rho = np.zeros(3, np.float64)
+    lib().orc_loss_eval(kind, float(a), float(alpha), float(mu), float(weight), float(s), _p(rho, C.c_double))
+    return rho
+
+
+def corrector(sq_norm, rho):
+    rho = _f64(rho); out = np.zeros(3, np.float64)
+    lib().orc_corrector(float(sq_norm), _p(rho, C.c_double), _p(out, C.c_double))
+    return out
+
+
+def gnc_initial_mu(max_residual, loss_scale, divisor, steps):
+    return lib().orc_gnc_initial_mu(float(max_residual), float(loss_scale), float(divisor), int(steps))
+
+
+def _unpack_fused(o):
+    return dict(H=o[..., :16].reshape(o.shape[:-1] + (4, 4)).copy(), g=o[..., 16:20].copy(), cost=o[..., 20].copy(),
+                max_r=o[..., 21].copy(), sum_sq=o[..., 22].copy(), n=o[..., 23].copy())
+
+
+def fused(variant, cells_m, cells_f, im, jf, params, loss=(LOSS_NONE, 1.0, -2.0, 1.0, 1.0), want_jac=True):
+    cm = _f32(cells_m).reshape(-1, 12); cf = _f32(cells_f).reshape(-1, 12); im = _u32(im); jf = _u32(jf); params = _f64(params)
+    out = np.zeros(24, np.float64)
+    lib().orc_fused(variant, _p(cm, C.c_float), _p(cf, C.c_float), _p(im, C.c_uint32), _p(jf, C.c_uint32), len(im),
+                    _p(params, C.c_double), int(loss[0]), float(loss[1]), float(loss[2]), float(loss[3]), float(loss[4]),
+                    int(want_jac), _p(out, C.c_double))
+    return _unpack_fused(out)
+
+
+def hw_threads():
+    return lib().orc_hw_threads()
+
+
+def fused_batch(variant, cells_m, cells_f, im, jf, seg_off, poses, loss=(LOSS_NONE, 1.0, -2.0, 1.0, 1.0), mu_per_seg=None,
+                want_jac=True, n_threads=1, repeats=1):
+    """-> (dict of per-segment arrays, wall seconds for `repeats` passes)"""
+    cm = _f32(cells_m).reshape(-1, 12); cf = _f32(cells_f).reshape(-1, 12); im = _u32(im); jf = _u32(jf)
+    seg_off = _u32(seg_off); poses = _f64(poses)
+    S = len(seg_off) - 1
+    out = np.zeros((S, 24), np.float64)
+    mu_p = None
+    if mu_per_seg is not None:
+        mu_arr = _f64(mu_per_seg); mu_p = _p(mu_arr, C.c_double)
+    t = lib().orc_fused_batch(variant, _p(cm, C.c_float), _p(cf, C.c_float), _p(im, C.c_uint32), _p(jf, C.c_uint32),
+                              _p(seg_off, C.c_uint32), S, _p(poses, C.c_double), int(loss[0]), float(loss[1]), float(loss[2]),
+                              float(loss[3]), float(loss[4]), mu_p, int(want_jac), _p(out, C.c_double), int(n_threads), int(repeats))
+    return _unpack_fused(out), t
+
+
+def loop_constraint(f_cells, f_slot, size_x, size_y, res, max_linf, m_cells, pose, k, metric=LOOKUP_MAHALANOBIS,
+                    variant=VAR_SE2_INTENSITY, matcher_loss_scale=1.0, loop_scale=1.0, alpha=-2.0, divisor=1.1, max_gnc_steps=2,
+                    max_iterations=200, on_manifold=False, loss_weight=1.0, pairs=None):
+    fc = _f32(f_cells).reshape(-1, 12); mc = _f32(m_cells).reshape(-1, 12); fs = _i32(f_slot); pose = _f64(pose)
+    out = np.zeros(9, np.float64)
+    if pairs is not None:
+        im, jf = _u32(pairs[0]), _u32(pairs[1]); pim, pjf, P = _p(im, C.c_uint32), _p(jf, C.c_uint32), len(im)
+    else:
+        pim, pjf, P = None, None, 0
+    st = lib().orc_loop_constraint(_p(fc, C.c_float), len(fc), _p(fs, C.c_int32), size_x, size_y, float(res), float(max_linf),
+                                   _p(mc, C.c_float), len(mc), _p(pose, C.c_double), int(k), int(metric), int(variant),
+                                   float(matcher_loss_scale), float(loop_scale), float(alpha), float(divisor), int(max_gnc_steps),
+                                   int(max_iterations), int(on_manifold), float(loss_weight), pim, pjf, P, _p(out, C.c_double))
+    return dict(pose=out[:4].copy(), score=out[4], gnc_solves=int(out[5]), iterations=int(out[6]), evals=int(out[7]),
+                mu_first=out[8], status=st)
+
+
+def sweep_costs(variant, cells_m, cells_f, im, jf, loss, poses):
+    cm = _f32(cells_m).reshape(-1, 12); cf = _f32(cells_f).reshape(-1, 12); im = _u32(im); jf = _u32(jf); poses = _f64(poses)
+    npar = 4 if variant in (VAR_SE2_INTENSITY, VAR_SE2_XY) else 3
+    S = poses.size // npar
+    out = np.zeros(S, np.float64)
+    lib().orc_sweep_costs(variant, _p(cm, C.c_float), _p(cf, C.c_float), _p(im, C.c_uint32), _p(jf, C.c_uint32), len(im),
+                          int(loss[0]), float(loss[1]), float(loss[2]), float(loss[3]), float(loss[4]), _p(poses, C.c_double), S,
+                          _p(out, C.c_double))
+    return out
+
+
+def se2_plus(T, d):
+    T = _f64(T); d = _f64(d); out = np.zeros(4)
+    lib().orc_se2_plus(_p(T, C.c_double), _p(d, C.c_double), _p(out, C.c_double))
+    return out

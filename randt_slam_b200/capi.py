@@ -1,0 +1,303 @@
+"""ctypes bindings over the C-ABI in include/randt_gpu.h (librandt_gpu.so, built in-tree by build.py).
+
+This is plumbing for the tests and bench.py: every call goes straight to an exported `randt_*` symbol.  There is no CPU
+fallback: if the shared library is missing or a call fails, a RandtError is raised.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librandt_gpu.so")
+
+VAR_SE2_INTENSITY, VAR_SE2_XY, VAR_VEC_INTENSITY, VAR_VEC_XY = 0, 1, 2, 3
+LOSS_NONE, LOSS_BARRON, LOSS_WELSCH = 0, 1, 2
+LOOKUP_MAHALANOBIS, LOOKUP_EUCLID = 0, 1
+FUSED_STRIDE = 24
+E_INVALID, E_CUDA, E_CAPACITY, E_NONFINITE, E_NOMEM = -1, -2, -3, -4, -5
+
+
+class RandtError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("randt error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Loss(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("scale", C.c_double), ("alpha", C.c_double), ("mu", C.c_double), ("weight", C.c_double)]
+
+
+class GridParams(C.Structure):
+    _fields_ = [("max_range", C.c_float), ("n_clusters", C.c_int32), ("min_points", C.c_int32), ("size_x", C.c_int32),
+                ("size_y", C.c_int32), ("resolution", C.c_double), ("max_linf", C.c_double)]
+
+
+def grid_params(p):
+    """from a randt_slam_b200.params.NdtParams"""
+    return GridParams(float(p.max_range), int(p.n_clusters), int(p.min_points_per_cell), int(p.size_x), int(p.size_y),
+                      float(p.resolution), float(p.max_neighbor_linf_distance))
+
+
+_lib = None
+
+# every symbol include/randt_gpu.h declares (kept in sync by tests/test_abi.py)
+_vp, _u32, _u64, _i, _d = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int, C.c_double
+_SIGS = {
+    "randt_version": (_i, []),
+    "randt_ctx_create": (_i, [_i, _vp, C.POINTER(_vp)]),
+    "randt_ctx_destroy": (None, [_vp]),
+    "randt_last_error": (C.c_char_p, [_vp]),
+    "randt_ctx_stream": (_vp, [_vp]),
+    "randt_ctx_sync": (_i, [_vp]),
+    "randt_ctx_launch_count": (_u64, [_vp]),
+    "randt_ctx_take_bad_pairs": (_i, [_vp, C.POINTER(_u64)]),
+    "randt_host_alloc": (_vp, [C.c_size_t]),
+    "randt_host_free": (None, [_vp]),
+    "randt_dev_alloc": (_vp, [C.c_size_t]),
+    "randt_dev_free": (None, [_vp]),
+    "randt_memcpy_h2d": (_i, [_vp, _vp, _vp, C.c_size_t]),
+    "randt_memcpy_d2h": (_i, [_vp, _vp, _vp, C.c_size_t]),
+    "randt_voxelize": (_i, [_vp, _vp, _vp, _u32, C.POINTER(GridParams), _i, C.POINTER(_vp)]),
+    "randt_map_upload": (_i, [_vp, _vp, _vp, _vp, _u32, _vp, C.POINTER(GridParams), C.POINTER(_vp)]),
+    "randt_map_info": (_i, [_vp, C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_u32)]),
+    "randt_map_download": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "randt_map_transform": (_i, [_vp, _vp, _vp]),
+    "randt_map_merge": (_i, [_vp, _vp, _vp]),
+    "randt_map_destroy": (None, [_vp]),
+    "randt_associate": (_i, [_vp, _vp, _vp, _vp, _i, _i, C.POINTER(_vp)]),
+    "randt_problem_create": (_i, [_vp, _vp, _u32, _vp, _u32, _vp, _vp, _u32, _vp, _u32, C.POINTER(_vp)]),
+    "randt_problem_info": (_i, [_vp, C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_u32)]),
+    "randt_problem_download": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "randt_problem_download_cells": (_i, [_vp, _vp, _vp, _vp]),
+    "randt_problem_destroy": (None, [_vp]),
+    "randt_eval_emit": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
+    "randt_eval_emit_dev": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
+    "randt_eval_fused": (_i, [_vp, _vp, _i, _vp, C.POINTER(Loss), _vp, _i, _vp]),
+    "randt_eval_fused_dev": (_i, [_vp, _vp, _i, _vp, C.POINTER(Loss), _vp, _i, _vp]),
+    "randt_sweep_costs": (_i, [_vp, _vp, _u32, _i, _vp, _u32, C.POINTER(Loss), _vp]),
+}
+
+
+def lib():
+    """Load librandt_gpu.so.  Raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RandtError(E_INVALID, "CUDA extension %s is missing: run `python -m randt_slam_b200.build` "
+                                        "(or __graft_entry__.build())" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            f = getattr(L, name)
+            f.restype = res
+            f.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return C.c_void_p(a.ctypes.data)
+
+
+def _f32(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a if shape is None else a.reshape(shape)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _u32a(a):
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+def make_loss(kind=LOSS_NONE, scale=1.0, alpha=-2.0, mu=1.0, weight=1.0):
+    return Loss(int(kind), float(scale), float(alpha), float(mu), float(weight))
+
+
+class Context:
+    """One randt_ctx (one CUDA stream).  stream: an int cudaStream_t to borrow, or None for an owned stream."""
+
+    def __init__(self, device=0, stream=None):
+        self._h = C.c_void_p()
+        rc = lib().randt_ctx_create(int(device), C.c_void_p(stream) if stream else None, C.byref(self._h))
+        if rc != 0:
+            raise RandtError(rc, "randt_ctx_create failed (no CUDA device %d?)" % device)
+        self.device = device
+
+    def close(self):
+        if self._h:
+            lib().randt_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RandtError(rc, lib().randt_last_error(self._h).decode())
+
+    @property
+    def stream(self):
+        return lib().randt_ctx_stream(self._h)
+
+    def sync(self):
+        self._check(lib().randt_ctx_sync(self._h))
+
+    @property
+    def launch_count(self):
+        return int(lib().randt_ctx_launch_count(self._h))
+
+    def take_bad_pairs(self):
+        n = C.c_uint64(0)
+        self._check(lib().randt_ctx_take_bad_pairs(self._h, C.byref(n)))
+        return int(n.value)
+
+    # ---- K1 ----
+    def voxelize(self, pts, scan_off, gp, pts_on_device=False):
+        """pts: float32 [N,4] host array (or int device pointer); scan_off: uint32 [B+1] -> Map"""
+        scan_off = _u32a(scan_off)
+        if not pts_on_device:
+            pts = _f32(pts, (-1, 4))
+        out = C.c_void_p()
+        self._check(lib().randt_voxelize(self._h, _ptr(pts), _ptr(scan_off), len(scan_off) - 1, C.byref(gp), int(pts_on_device),
+                                         C.byref(out)))
+        return Map(self, out, gp)
+
+    def map_upload(self, cells, cell_off, gp, npts=None, slot=None):
+        cells = _f32(cells, (-1, 12)); cell_off = _u32a(cell_off)
+        npts_a = _u32a(npts) if npts is not None else None
+        slot_a = np.ascontiguousarray(slot, dtype=np.int32) if slot is not None else None
+        out = C.c_void_p()
+        self._check(lib().randt_map_upload(self._h, _ptr(cells), _ptr(npts_a), _ptr(cell_off), len(cell_off) - 1, _ptr(slot_a),
+                                           C.byref(gp), C.byref(out)))
+        return Map(self, out, gp)
+
+    # ---- K2 ----
+    def associate(self, fixed, moving, pose0, k, metric=LOOKUP_MAHALANOBIS):
+        pose0 = _f64(pose0)
+        out = C.c_void_p()
+        self._check(lib().randt_associate(self._h, fixed._h, moving._h, _ptr(pose0), int(k), int(metric), C.byref(out)))
+        return Problem(self, out)
+
+    def problem_create(self, cells_m, cells_f, pair_m, pair_f, seg_off):
+        cells_m = _f32(cells_m, (-1, 12)); cells_f = _f32(cells_f, (-1, 12))
+        pair_m = _u32a(pair_m); pair_f = _u32a(pair_f); seg_off = _u32a(seg_off)
+        out = C.c_void_p()
+        self._check(lib().randt_problem_create(self._h, _ptr(cells_m), len(cells_m), _ptr(cells_f), len(cells_f), _ptr(pair_m),
+                                               _ptr(pair_f), len(pair_m), _ptr(seg_off), len(seg_off) - 1, C.byref(out)))
+        return Problem(self, out)
+
+
+class Map:
+    def __init__(self, ctx, handle, gp):
+        self.ctx, self._h, self.gp = ctx, handle, gp
+
+    def close(self):
+        if self._h:
+            lib().randt_map_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self):
+        b, n, s = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        lib().randt_map_info(self._h, C.byref(b), C.byref(n), C.byref(s))
+        return b.value, n.value, s.value
+
+    def download(self, want_labels=False, want_slot=True):
+        B, n, ns = self.info()
+        cells = np.zeros((n, 12), np.float32); npts = np.zeros(n, np.uint32); off = np.zeros(B + 1, np.uint32)
+        labels = np.zeros(n, np.int32) if want_labels else None
+        slot = np.zeros((B, ns), np.int32) if want_slot else None
+        self.ctx._check(lib().randt_map_download(self.ctx._h, self._h, _ptr(cells), _ptr(npts), _ptr(labels), _ptr(off), _ptr(slot)))
+        return dict(cells=cells, npts=npts, labels=labels, cell_off=off, slot=slot)
+
+    def transform(self, trans):
+        trans = _f32(trans, (-1, 4))
+        assert len(trans) == self.info()[0]
+        self.ctx._check(lib().randt_map_transform(self.ctx._h, self._h, _ptr(trans)))
+
+    def merge(self, moving):
+        self.ctx._check(lib().randt_map_merge(self.ctx._h, self._h, moving._h))
+
+
+class Problem:
+    def __init__(self, ctx, handle):
+        self.ctx, self._h = ctx, handle
+        s, p, m, f = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+        lib().randt_problem_info(handle, C.byref(s), C.byref(p), C.byref(m), C.byref(f))
+        self.n_segments, self.n_pairs, self.n_m, self.n_f = s.value, p.value, m.value, f.value
+
+    def close(self):
+        if self._h:
+            lib().randt_problem_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def download(self):
+        pm = np.zeros(self.n_pairs, np.uint32); pf = np.zeros(self.n_pairs, np.uint32); off = np.zeros(self.n_segments + 1, np.uint32)
+        self.ctx._check(lib().randt_problem_download(self.ctx._h, self._h, _ptr(pm), _ptr(pf), _ptr(off)))
+        return pm, pf, off
+
+    def download_cells(self):
+        cm = np.zeros((self.n_m, 12), np.float32); cf = np.zeros((self.n_f, 12), np.float32)
+        self.ctx._check(lib().randt_problem_download_cells(self.ctx._h, self._h, _ptr(cm), _ptr(cf)))
+        return cm, cf
+
+    def eval_emit(self, poses, variant=VAR_SE2_INTENSITY, want_jac=True):
+        npar = 4 if variant <= 1 else 3
+        poses = _f64(poses).reshape(self.n_segments, npar)
+        r = np.zeros(self.n_pairs, np.float64)
+        J = np.zeros((self.n_pairs, npar), np.float64) if want_jac else None
+        self.ctx._check(lib().randt_eval_emit(self.ctx._h, self._h, int(variant), _ptr(poses), _ptr(r), _ptr(J)))
+        return r, J
+
+    def eval_fused(self, poses, loss=None, mu_per_seg=None, want_jac=True, variant=VAR_SE2_INTENSITY, out=None):
+        npar = 4 if variant <= 1 else 3
+        poses = _f64(poses).reshape(self.n_segments, npar)
+        if out is None:
+            out = np.zeros((self.n_segments, FUSED_STRIDE), np.float64)
+        mu = _f64(mu_per_seg) if mu_per_seg is not None else None
+        lp = C.byref(loss) if loss is not None else None
+        self.ctx._check(lib().randt_eval_fused(self.ctx._h, self._h, int(variant), _ptr(poses), lp, _ptr(mu), int(want_jac), _ptr(out)))
+        return out
+
+    def eval_fused_dev(self, d_poses, d_out, loss=None, d_mu=None, want_jac=True, variant=VAR_SE2_INTENSITY):
+        lp = C.byref(loss) if loss is not None else None
+        self.ctx._check(lib().randt_eval_fused_dev(self.ctx._h, self._h, int(variant), _ptr(d_poses), lp, _ptr(d_mu), int(want_jac),
+                                                   _ptr(d_out)))
+
+    def eval_emit_dev(self, d_poses, d_r, d_J, variant=VAR_SE2_INTENSITY):
+        self.ctx._check(lib().randt_eval_emit_dev(self.ctx._h, self._h, int(variant), _ptr(d_poses), _ptr(d_r), _ptr(d_J)))
+
+    def sweep_costs(self, seg, poses, loss=None, variant=VAR_SE2_INTENSITY):
+        npar = 4 if variant <= 1 else 3
+        poses = _f64(poses).reshape(-1, npar)
+        cost = np.zeros(len(poses), np.float64)
+        lp = C.byref(loss) if loss is not None else None
+        self.ctx._check(lib().randt_sweep_costs(self.ctx._h, self._h, int(seg), int(variant), _ptr(poses), len(poses), lp, _ptr(cost)))
+        return cost
+
+
+def unpack_fused(o):
+    o = np.asarray(o)
+    return dict(H=o[..., :16].reshape(o.shape[:-1] + (4, 4)), g=o[..., 16:20], cost=o[..., 20], max_r=o[..., 21], sum_sq=o[..., 22],
+                n=o[..., 23])

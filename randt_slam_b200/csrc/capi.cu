@@ -1,0 +1,583 @@
+// C-ABI layer: contexts, device-resident maps and problems, and the extern "C" entry points declared in include/randt_gpu.h.
+// Host code only orchestrates (allocation, small prefix sums over per-map counts, tile lists); all per-point / per-cell /
+// per-pair work runs in the kernels of k1_voxelize.cu, k2_associate.cu and k3_pair_eval.cu.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+
+#include "common.cuh"
+
+using namespace randt;
+
+struct randt_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  uint64_t launches = 0;
+  unsigned long long* d_bad = nullptr;   // count of degenerate pairs seen by K3
+};
+
+struct randt_map {
+  int device = 0;
+  randt_grid_params gp{};
+  MapGeomDev geom{};
+  uint32_t B = 0, n_cells = 0, max_per_map = 0;
+  float4* cells = nullptr;       // [n_cells][3]
+  uint32_t* npts = nullptr;      // [n_cells]
+  int32_t* labels = nullptr;     // [n_cells] voxel labels (voxelised maps only)
+  uint32_t* cell_off = nullptr;  // [B+1] device
+  int32_t* slot = nullptr;       // [B][n_slots]
+  std::vector<uint32_t> h_cell_off;
+};
+
+struct randt_problem {
+  int device = 0;
+  uint32_t S = 0, P = 0, n_m = 0, n_f = 0;
+  float4 *cells_m = nullptr, *cells_f = nullptr;
+  uint2* pairs = nullptr;
+  Tile* tiles = nullptr; uint32_t n_tiles = 0;
+  uint32_t* seg_first_tile = nullptr;
+  uint32_t* seg_off = nullptr;
+  double* partials = nullptr;
+  uint32_t* seg_counters = nullptr;
+  std::vector<uint32_t> h_seg_off;
+  bool has_empty_segment = false;
+  // scratch for the host-pointer entry points
+  double *d_poses = nullptr, *d_out = nullptr, *d_mu = nullptr, *d_r = nullptr, *d_J = nullptr;
+  double* d_sweep = nullptr; size_t sweep_cap = 0;
+};
+
+namespace {
+
+int fail(randt_ctx* ctx, int code, const char* what, cudaError_t e = cudaSuccess) {
+  if (ctx) {
+    char buf[512];
+    if (e != cudaSuccess) snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
+    else snprintf(buf, sizeof(buf), "%s", what);
+    ctx->err = buf;
+  }
+  return code;
+}
+
+#define CK(call)                                                                 \
+  do {                                                                           \
+    cudaError_t e__ = (call);                                                    \
+    if (e__ != cudaSuccess) return fail(ctx, RANDT_E_CUDA, #call, e__);          \
+  } while (0)
+
+template <typename T>
+cudaError_t dev_alloc(T** p, size_t n) { *p = nullptr; if (n == 0) n = 1; return cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)); }
+
+bool same_geom(const randt_grid_params& a, const randt_grid_params& b) {
+  return a.size_x == b.size_x && a.size_y == b.size_y && a.resolution == b.resolution;
+}
+
+void free_map(randt_map* m) {
+  if (!m) return;
+  cudaFree(m->cells); cudaFree(m->npts); cudaFree(m->labels); cudaFree(m->cell_off); cudaFree(m->slot);
+  delete m;
+}
+void free_problem(randt_problem* p) {
+  if (!p) return;
+  cudaFree(p->cells_m); cudaFree(p->cells_f); cudaFree(p->pairs); cudaFree(p->tiles); cudaFree(p->seg_first_tile); cudaFree(p->seg_off);
+  cudaFree(p->partials); cudaFree(p->seg_counters); cudaFree(p->d_poses); cudaFree(p->d_out); cudaFree(p->d_mu); cudaFree(p->d_r);
+  cudaFree(p->d_J); cudaFree(p->d_sweep);
+  delete p;
+}
+
+// tile list + per-segment bookkeeping from a host seg_off; uploads everything a DeviceProblem needs
+int finish_problem(randt_ctx* ctx, randt_problem* p) {
+  std::vector<Tile> tiles;
+  std::vector<uint32_t> first(p->S + 1, 0);
+  for (uint32_t s = 0; s < p->S; ++s) {
+    first[s] = (uint32_t)tiles.size();
+    uint32_t part = 0;
+    for (uint32_t b = p->h_seg_off[s]; b < p->h_seg_off[s + 1]; b += kTilePairs) {
+      Tile t; t.seg = s; t.begin = b; t.end = std::min(p->h_seg_off[s + 1], b + (uint32_t)kTilePairs); t.part = part++;
+      tiles.push_back(t);
+    }
+  }
+  first[p->S] = (uint32_t)tiles.size();
+  for (uint32_t s = 0; s < p->S; ++s) if (p->h_seg_off[s + 1] == p->h_seg_off[s]) p->has_empty_segment = true;
+  p->n_tiles = (uint32_t)tiles.size();
+  CK(dev_alloc(&p->tiles, tiles.size()));
+  CK(dev_alloc(&p->seg_first_tile, first.size()));
+  CK(dev_alloc(&p->seg_off, p->h_seg_off.size()));
+  CK(dev_alloc(&p->partials, (size_t)tiles.size() * kMaxAcc));
+  CK(dev_alloc(&p->seg_counters, p->S));
+  CK(dev_alloc(&p->d_poses, (size_t)p->S * 4));
+  CK(dev_alloc(&p->d_out, (size_t)p->S * RANDT_FUSED_STRIDE));
+  CK(dev_alloc(&p->d_mu, p->S));
+  if (!tiles.empty()) CK(cudaMemcpyAsync(p->tiles, tiles.data(), tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(p->seg_first_tile, first.data(), first.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(p->seg_off, p->h_seg_off.data(), p->h_seg_off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(p->seg_counters, 0, std::max<size_t>(1, p->S) * sizeof(uint32_t), ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));   // the host vectors above go out of scope
+  return RANDT_OK;
+}
+
+DeviceProblem view(const randt_problem* p) {
+  DeviceProblem d;
+  d.cells_m = p->cells_m; d.cells_f = p->cells_f; d.pairs = p->pairs; d.tiles = p->tiles; d.n_tiles = p->n_tiles;
+  d.seg_first_tile = p->seg_first_tile; d.n_segments = p->S; d.n_pairs = p->P; d.partials = p->partials; d.seg_counters = p->seg_counters;
+  return d;
+}
+
+int make_loss(randt_ctx* ctx, const randt_loss* l, LossParams* out) {
+  LossParams lp; lp.kind = RANDT_LOSS_NONE; lp.a2 = 1.0; lp.alpha = 2.0; lp.weight = 1.0; lp.mu = 1.0;
+  if (l) {
+    if (l->kind < RANDT_LOSS_NONE || l->kind > RANDT_LOSS_WELSCH) return fail(ctx, RANDT_E_INVALID, "unknown loss kind");
+    lp.kind = l->kind; lp.a2 = l->scale * l->scale; lp.alpha = l->alpha; lp.weight = l->weight; lp.mu = l->mu;
+    if (l->kind != RANDT_LOSS_NONE && !(l->scale > 0.0 && l->mu > 0.0)) return fail(ctx, RANDT_E_INVALID, "loss scale and mu must be > 0");
+    if (l->kind == RANDT_LOSS_BARRON && l->alpha == 0.0) { /* handled by the |alpha| <= 0.05 branch */ }
+  }
+  *out = lp;
+  return RANDT_OK;
+}
+
+int check_variant(randt_ctx* ctx, int v) { return (v < 0 || v > 3) ? fail(ctx, RANDT_E_INVALID, "variant must be 0..3") : RANDT_OK; }
+int np_of(int variant) { return variant <= 1 ? 4 : 3; }
+
+}  // namespace
+
+extern "C" {
+
+int randt_version(void) { return 100; }
+
+int randt_ctx_create(int device, void* stream, randt_ctx** out) {
+  if (!out) return RANDT_E_INVALID;
+  *out = nullptr;
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || device < 0 || device >= n_dev) return RANDT_E_CUDA;
+  randt_ctx* ctx = new (std::nothrow) randt_ctx();
+  if (!ctx) return RANDT_E_NOMEM;
+  ctx->device = device;
+  cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) {
+    if (stream) { ctx->stream = (cudaStream_t)stream; ctx->own_stream = false; }
+    else { e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking); ctx->own_stream = true; }
+  }
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_bad), sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_bad, 0, sizeof(unsigned long long), ctx->stream);
+  if (e != cudaSuccess) { delete ctx; return RANDT_E_CUDA; }
+  *out = ctx;
+  return RANDT_OK;
+}
+
+void randt_ctx_destroy(randt_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(ctx->d_bad);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* randt_last_error(const randt_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+void* randt_ctx_stream(const randt_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int randt_ctx_sync(randt_ctx* ctx) { if (!ctx) return RANDT_E_INVALID; CK(cudaStreamSynchronize(ctx->stream)); return RANDT_OK; }
+uint64_t randt_ctx_launch_count(const randt_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+void* randt_host_alloc(size_t bytes) { void* p = nullptr; return cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess ? p : nullptr; }
+void randt_host_free(void* p) { if (p) cudaFreeHost(p); }
+void* randt_dev_alloc(size_t bytes) { void* p = nullptr; return cudaMalloc(&p, bytes ? bytes : 1) == cudaSuccess ? p : nullptr; }
+void randt_dev_free(void* p) { if (p) cudaFree(p); }
+int randt_memcpy_h2d(randt_ctx* ctx, void* dst, const void* src, size_t bytes) { if (!ctx) return RANDT_E_INVALID; CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream)); return RANDT_OK; }
+int randt_memcpy_d2h(randt_ctx* ctx, void* dst, const void* src, size_t bytes) { if (!ctx) return RANDT_E_INVALID; CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream)); return RANDT_OK; }
+
+// returns (and clears) the number of degenerate pairs (non-finite or negative d^T B^-1 d) K3 has seen on this context
+int randt_ctx_take_bad_pairs(randt_ctx* ctx, uint64_t* count) {
+  if (!ctx || !count) return RANDT_E_INVALID;
+  unsigned long long h = 0;
+  CK(cudaMemcpyAsync(&h, ctx->d_bad, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemsetAsync(ctx->d_bad, 0, sizeof(h), ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *count = h;
+  return RANDT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K1
+// ---------------------------------------------------------------------------------------------------------------
+int randt_voxelize(randt_ctx* ctx, const float* pts4, const uint32_t* scan_off, uint32_t n_scans, const randt_grid_params* gp,
+                   int pts_on_device, randt_map** out) {
+  if (!ctx || !out || !gp || !scan_off || (!pts4 && n_scans && scan_off[n_scans] > 0)) return fail(ctx, RANDT_E_INVALID, "randt_voxelize: null argument");
+  *out = nullptr;
+  if (gp->n_clusters <= 0 || gp->size_x <= 0 || gp->size_y <= 0 || !(gp->resolution > 0) || !(gp->max_range > 0))
+    return fail(ctx, RANDT_E_INVALID, "randt_voxelize: bad grid parameters");
+  CK(cudaSetDevice(ctx->device));
+  const uint32_t B = n_scans;
+  if (scan_off[0] != 0) return fail(ctx, RANDT_E_INVALID, "randt_voxelize: scan_off[0] must be 0");
+  const uint32_t n_pts = scan_off[B];
+  uint32_t max_pts = 0;
+  for (uint32_t b = 0; b < B; ++b) { if (scan_off[b + 1] < scan_off[b]) return fail(ctx, RANDT_E_INVALID, "scan_off not monotone"); max_pts = std::max(max_pts, scan_off[b + 1] - scan_off[b]); }
+  const uint32_t div = (uint32_t)std::max(gp->min_points, 0) + 1u;
+  const uint32_t cell_cap = std::max<uint32_t>(1, max_pts / div);   // a kept cell has > min_points points
+  randt_map* m = new (std::nothrow) randt_map();
+  if (!m) return RANDT_E_NOMEM;
+  m->device = ctx->device; m->gp = *gp; m->geom = make_geom(*gp); m->B = B;
+  float4* d_pts = nullptr; bool own_pts = false;
+  uint32_t *d_scan_off = nullptr, *d_cnt = nullptr, *d_order = nullptr, *d_npts_p = nullptr;
+  int32_t *d_labels_scratch = nullptr, *d_labels_p = nullptr; float4* d_cells_p = nullptr; int* d_status = nullptr;
+  int rc = RANDT_OK;
+  auto cleanup = [&]() {
+    if (own_pts) cudaFree(d_pts);
+    cudaFree(d_scan_off); cudaFree(d_cnt); cudaFree(d_order); cudaFree(d_npts_p); cudaFree(d_labels_scratch); cudaFree(d_labels_p);
+    cudaFree(d_cells_p); cudaFree(d_status);
+  };
+#define CKV(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rc = fail(ctx, RANDT_E_CUDA, #call, e__); cleanup(); free_map(m); return rc; } } while (0)
+  if (pts_on_device) d_pts = const_cast<float4*>(reinterpret_cast<const float4*>(pts4));
+  else { CKV(dev_alloc(&d_pts, n_pts)); own_pts = true; if (n_pts) CKV(cudaMemcpyAsync(d_pts, pts4, (size_t)n_pts * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream)); }
+  CKV(dev_alloc(&d_scan_off, B + 1));
+  CKV(cudaMemcpyAsync(d_scan_off, scan_off, (size_t)(B + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  CKV(dev_alloc(&d_cnt, B)); CKV(dev_alloc(&d_order, n_pts)); CKV(dev_alloc(&d_labels_scratch, n_pts));
+  CKV(dev_alloc(&d_cells_p, (size_t)B * cell_cap * 3)); CKV(dev_alloc(&d_npts_p, (size_t)B * cell_cap)); CKV(dev_alloc(&d_labels_p, (size_t)B * cell_cap));
+  CKV(dev_alloc(&d_status, B));
+  CKV(dev_alloc(&m->slot, (size_t)B * m->geom.n_slots));
+  int nl = 0;
+  CKV(launch_voxelize(d_pts, d_scan_off, B, max_pts, *gp, m->geom, cell_cap, d_cells_p, d_npts_p, d_labels_p, d_cnt, m->slot, d_labels_scratch,
+                      d_order, d_status, ctx->stream, &nl));
+  std::vector<uint32_t> h_cnt(B); std::vector<int> h_status(B);
+  if (B) { CKV(cudaMemcpyAsync(h_cnt.data(), d_cnt, B * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+           CKV(cudaMemcpyAsync(h_status.data(), d_status, B * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream)); }
+  CKV(cudaStreamSynchronize(ctx->stream));
+  for (uint32_t b = 0; b < B; ++b) {
+    if (h_status[b] == VOX_SPAN || h_status[b] == VOX_CELL_CAP) {
+      cleanup(); free_map(m);
+      return fail(ctx, RANDT_E_CAPACITY, "randt_voxelize: label span / cell capacity exceeded (points far outside +-max_range?)");
+    }
+    if (h_status[b] == VOX_OUT_OF_MAP) {
+      cleanup(); free_map(m);
+      return fail(ctx, RANDT_E_INVALID, "randt_voxelize: a cell mean falls outside the map (the reference throws std::out_of_range here)");
+    }
+  }
+  m->h_cell_off.assign(B + 1, 0);
+  for (uint32_t b = 0; b < B; ++b) { m->h_cell_off[b + 1] = m->h_cell_off[b] + h_cnt[b]; m->max_per_map = std::max(m->max_per_map, h_cnt[b]); }
+  m->n_cells = m->h_cell_off[B];
+  CKV(dev_alloc(&m->cell_off, B + 1));
+  CKV(cudaMemcpyAsync(m->cell_off, m->h_cell_off.data(), (size_t)(B + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  CKV(dev_alloc(&m->cells, (size_t)m->n_cells * 3)); CKV(dev_alloc(&m->npts, m->n_cells)); CKV(dev_alloc(&m->labels, m->n_cells));
+  CKV(launch_compact_cells(d_cells_p, d_npts_p, d_labels_p, m->cell_off, B, cell_cap, m->max_per_map, m->cells, m->npts, m->labels, ctx->stream, &nl));
+  CKV(cudaStreamSynchronize(ctx->stream));
+#undef CKV
+  ctx->launches += nl;
+  cleanup();
+  *out = m;
+  return RANDT_OK;
+}
+
+int randt_map_upload(randt_ctx* ctx, const float* cells, const uint32_t* npts, const uint32_t* cell_off, uint32_t n_maps, const int32_t* slot,
+                     const randt_grid_params* gp, randt_map** out) {
+  if (!ctx || !out || !gp || !cell_off) return fail(ctx, RANDT_E_INVALID, "randt_map_upload: null argument");
+  *out = nullptr;
+  if (gp->size_x <= 0 || gp->size_y <= 0 || !(gp->resolution > 0)) return fail(ctx, RANDT_E_INVALID, "randt_map_upload: bad map geometry");
+  CK(cudaSetDevice(ctx->device));
+  randt_map* m = new (std::nothrow) randt_map();
+  if (!m) return RANDT_E_NOMEM;
+  m->device = ctx->device; m->gp = *gp; m->geom = make_geom(*gp); m->B = n_maps;
+  m->h_cell_off.assign(cell_off, cell_off + n_maps + 1);
+  for (uint32_t b = 0; b < n_maps; ++b) {
+    if (cell_off[b + 1] < cell_off[b]) { free_map(m); return fail(ctx, RANDT_E_INVALID, "cell_off not monotone"); }
+    m->max_per_map = std::max(m->max_per_map, cell_off[b + 1] - cell_off[b]);
+  }
+  m->n_cells = cell_off[n_maps];
+  if (m->n_cells && !cells) { free_map(m); return fail(ctx, RANDT_E_INVALID, "randt_map_upload: cells == NULL"); }
+  int rc = RANDT_OK; int nl = 0;
+#define CKM(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rc = fail(ctx, RANDT_E_CUDA, #call, e__); free_map(m); return rc; } } while (0)
+  CKM(dev_alloc(&m->cells, (size_t)m->n_cells * 3)); CKM(dev_alloc(&m->npts, m->n_cells)); CKM(dev_alloc(&m->cell_off, n_maps + 1));
+  CKM(dev_alloc(&m->slot, (size_t)n_maps * m->geom.n_slots));
+  if (m->n_cells) CKM(cudaMemcpyAsync(m->cells, cells, (size_t)m->n_cells * 48, cudaMemcpyHostToDevice, ctx->stream));
+  if (npts && m->n_cells) CKM(cudaMemcpyAsync(m->npts, npts, (size_t)m->n_cells * 4, cudaMemcpyHostToDevice, ctx->stream));
+  else CKM(cudaMemsetAsync(m->npts, 0, std::max<size_t>(1, m->n_cells) * 4, ctx->stream));
+  CKM(cudaMemcpyAsync(m->cell_off, cell_off, (size_t)(n_maps + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  if (slot) CKM(cudaMemcpyAsync(m->slot, slot, (size_t)n_maps * m->geom.n_slots * 4, cudaMemcpyHostToDevice, ctx->stream));
+  else {
+    CKM(cudaMemsetAsync(m->slot, 0xFF, std::max<size_t>(1, (size_t)n_maps * m->geom.n_slots) * 4, ctx->stream));
+    CKM(launch_build_slots(m->cells, m->cell_off, n_maps, m->max_per_map, m->geom, m->slot, ctx->stream, &nl));
+  }
+  CKM(cudaStreamSynchronize(ctx->stream));
+#undef CKM
+  ctx->launches += nl;
+  *out = m;
+  return RANDT_OK;
+}
+
+int randt_map_info(const randt_map* m, uint32_t* n_maps, uint32_t* n_cells_total, uint32_t* n_slots) {
+  if (!m) return RANDT_E_INVALID;
+  if (n_maps) *n_maps = m->B;
+  if (n_cells_total) *n_cells_total = m->n_cells;
+  if (n_slots) *n_slots = m->geom.n_slots;
+  return RANDT_OK;
+}
+
+int randt_map_download(randt_ctx* ctx, const randt_map* m, float* cells, uint32_t* npts, int32_t* labels, uint32_t* cell_off, int32_t* slot) {
+  if (!ctx || !m) return fail(ctx, RANDT_E_INVALID, "randt_map_download: null argument");
+  CK(cudaSetDevice(ctx->device));
+  if (cells && m->n_cells) CK(cudaMemcpyAsync(cells, m->cells, (size_t)m->n_cells * 48, cudaMemcpyDeviceToHost, ctx->stream));
+  if (npts && m->n_cells) CK(cudaMemcpyAsync(npts, m->npts, (size_t)m->n_cells * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (labels) {
+    if (!m->labels) return fail(ctx, RANDT_E_INVALID, "randt_map_download: this map has no voxel labels");
+    if (m->n_cells) CK(cudaMemcpyAsync(labels, m->labels, (size_t)m->n_cells * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (cell_off) memcpy(cell_off, m->h_cell_off.data(), m->h_cell_off.size() * 4);
+  if (slot) CK(cudaMemcpyAsync(slot, m->slot, (size_t)m->B * m->geom.n_slots * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return RANDT_OK;
+}
+
+int randt_map_transform(randt_ctx* ctx, randt_map* m, const float* trans) {
+  if (!ctx || !m || !trans) return fail(ctx, RANDT_E_INVALID, "randt_map_transform: null argument");
+  CK(cudaSetDevice(ctx->device));
+  float4* d_t = nullptr;
+  CK(dev_alloc(&d_t, m->B));
+  int nl = 0;
+  cudaError_t e = cudaMemcpyAsync(d_t, trans, (size_t)m->B * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = launch_transform_cells(m->cells, m->cell_off, m->B, m->max_per_map, d_t, ctx->stream, &nl);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_t);
+  if (e != cudaSuccess) return fail(ctx, RANDT_E_CUDA, "randt_map_transform", e);
+  ctx->launches += nl;
+  return RANDT_OK;
+}
+
+int randt_map_merge(randt_ctx* ctx, randt_map* F, const randt_map* M) {
+  if (!ctx || !F || !M) return fail(ctx, RANDT_E_INVALID, "randt_map_merge: null argument");
+  if (F->B != M->B || !same_geom(F->gp, M->gp)) return fail(ctx, RANDT_E_INVALID, "randt_map_merge: batch size / geometry mismatch");
+  CK(cudaSetDevice(ctx->device));
+  const uint32_t B = F->B;
+  uint32_t cap = 1;
+  for (uint32_t b = 0; b < B; ++b) cap = std::max(cap, (F->h_cell_off[b + 1] - F->h_cell_off[b]) + (M->h_cell_off[b + 1] - M->h_cell_off[b]));
+  std::vector<uint32_t> h_ooff(B + 1);
+  for (uint32_t b = 0; b <= B; ++b) h_ooff[b] = b * cap;
+  float4 *o_cells = nullptr, *n_cells = nullptr; uint32_t *o_npts = nullptr, *o_cnt = nullptr, *d_ooff = nullptr, *n_npts = nullptr, *n_off = nullptr;
+  int nl = 0; int rc = RANDT_OK;
+  auto cleanup = [&]() { cudaFree(o_cells); cudaFree(o_npts); cudaFree(o_cnt); cudaFree(d_ooff); };
+#define CKG(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rc = fail(ctx, RANDT_E_CUDA, #call, e__); cleanup(); cudaFree(n_cells); cudaFree(n_npts); cudaFree(n_off); return rc; } } while (0)
+  CKG(dev_alloc(&o_cells, (size_t)B * cap * 3)); CKG(dev_alloc(&o_npts, (size_t)B * cap)); CKG(dev_alloc(&o_cnt, B)); CKG(dev_alloc(&d_ooff, B + 1));
+  CKG(cudaMemcpyAsync(d_ooff, h_ooff.data(), (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CKG(launch_merge_maps(F->cells, F->npts, F->cell_off, F->slot, M->cells, M->npts, M->cell_off, B, F->geom, d_ooff, o_cells, o_npts, o_cnt, ctx->stream, &nl));
+  std::vector<uint32_t> h_cnt(B);
+  if (B) CKG(cudaMemcpyAsync(h_cnt.data(), o_cnt, (size_t)B * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CKG(cudaStreamSynchronize(ctx->stream));
+  std::vector<uint32_t> new_off(B + 1, 0); uint32_t max_per = 0;
+  for (uint32_t b = 0; b < B; ++b) { new_off[b + 1] = new_off[b] + h_cnt[b]; max_per = std::max(max_per, h_cnt[b]); }
+  CKG(dev_alloc(&n_cells, (size_t)new_off[B] * 3)); CKG(dev_alloc(&n_npts, new_off[B])); CKG(dev_alloc(&n_off, B + 1));
+  CKG(cudaMemcpyAsync(n_off, new_off.data(), (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CKG(launch_compact_cells(o_cells, o_npts, nullptr, n_off, B, cap, max_per, n_cells, n_npts, nullptr, ctx->stream, &nl));
+  CKG(cudaStreamSynchronize(ctx->stream));
+#undef CKG
+  cleanup();
+  cudaFree(F->cells); cudaFree(F->npts); cudaFree(F->cell_off); cudaFree(F->labels);
+  F->cells = n_cells; F->npts = n_npts; F->cell_off = n_off; F->labels = nullptr;
+  F->h_cell_off = new_off; F->n_cells = new_off[B]; F->max_per_map = max_per;
+  ctx->launches += nl;
+  return RANDT_OK;
+}
+
+void randt_map_destroy(randt_map* m) { if (m) { cudaSetDevice(m->device); free_map(m); } }
+
+// ---------------------------------------------------------------------------------------------------------------
+// K2
+// ---------------------------------------------------------------------------------------------------------------
+int randt_associate(randt_ctx* ctx, const randt_map* F, const randt_map* M, const double* pose0, int k, int metric, randt_problem** out) {
+  if (!ctx || !F || !M || !pose0 || !out) return fail(ctx, RANDT_E_INVALID, "randt_associate: null argument");
+  *out = nullptr;
+  if (F->B != M->B) return fail(ctx, RANDT_E_INVALID, "randt_associate: fixed and moving batches differ in size");
+  if (k < 1 || k > kMaxNeighbours) return fail(ctx, RANDT_E_INVALID, "randt_associate: k must be in 1..8");
+  if (metric != RANDT_LOOKUP_MAHALANOBIS_INTENSITY && metric != RANDT_LOOKUP_EUCLID_XY) return fail(ctx, RANDT_E_INVALID, "randt_associate: bad metric");
+  MapGeomDev geom = F->geom;
+  geom.r_stop = static_cast<int>(F->gp.max_linf / F->gp.resolution);
+  if (2 * (geom.r_stop > 0 ? geom.r_stop - 1 : 0) + 1 > geom.size_x)
+    return fail(ctx, RANDT_E_CAPACITY, "randt_associate: search window wider than the map (duplicate window slots are not supported)");
+  CK(cudaSetDevice(ctx->device));
+  const uint32_t B = F->B, n_m = M->n_cells;
+  randt_problem* p = new (std::nothrow) randt_problem();
+  if (!p) return RANDT_E_NOMEM;
+  p->device = ctx->device; p->S = B; p->n_m = n_m; p->n_f = F->n_cells;
+  float4* d_pose = nullptr; uint32_t *d_nn = nullptr, *d_cnt = nullptr, *d_scan = nullptr, *d_bs = nullptr;
+  int rc = RANDT_OK; int nl = 0;
+  auto cleanup = [&]() { cudaFree(d_pose); cudaFree(d_nn); cudaFree(d_cnt); cudaFree(d_scan); cudaFree(d_bs); };
+#define CKA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rc = fail(ctx, RANDT_E_CUDA, #call, e__); cleanup(); free_problem(p); return rc; } } while (0)
+  std::vector<float4> h_pose(B);
+  for (uint32_t b = 0; b < B; ++b) h_pose[b] = make_float4((float)pose0[4 * b], (float)pose0[4 * b + 1], (float)pose0[4 * b + 2], (float)pose0[4 * b + 3]);
+  CKA(dev_alloc(&d_pose, B));
+  if (B) CKA(cudaMemcpyAsync(d_pose, h_pose.data(), (size_t)B * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+  CKA(dev_alloc(&d_nn, (size_t)n_m * k)); CKA(dev_alloc(&d_cnt, n_m)); CKA(dev_alloc(&d_scan, (size_t)n_m + 1)); CKA(dev_alloc(&d_bs, n_m / 1024 + 2));
+  CKA(launch_associate(F->cells, F->cell_off, F->slot, M->cells, M->cell_off, B, n_m, M->max_per_map, geom, d_pose, k, metric, d_nn, d_cnt, ctx->stream, &nl));
+  CKA(launch_exclusive_scan_u32(d_cnt, d_scan, n_m, d_bs, ctx->stream, &nl));
+  std::vector<uint32_t> h_scan((size_t)n_m + 1);
+  CKA(cudaMemcpyAsync(h_scan.data(), d_scan, ((size_t)n_m + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CKA(cudaStreamSynchronize(ctx->stream));
+  p->P = h_scan[n_m];
+  p->h_seg_off.resize(B + 1);
+  for (uint32_t b = 0; b <= B; ++b) p->h_seg_off[b] = h_scan[M->h_cell_off[b]];
+  CKA(dev_alloc(&p->pairs, p->P));
+  CKA(launch_compact_pairs(d_nn, d_cnt, d_scan, M->cell_off, F->cell_off, B, n_m, M->max_per_map, k, p->pairs, ctx->stream, &nl));
+  // snapshot the cell tables (the reference's functors copy their cells; maps may be merged/transformed afterwards)
+  CKA(dev_alloc(&p->cells_m, (size_t)n_m * 3)); CKA(dev_alloc(&p->cells_f, (size_t)F->n_cells * 3));
+  if (n_m) CKA(cudaMemcpyAsync(p->cells_m, M->cells, (size_t)n_m * 48, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (F->n_cells) CKA(cudaMemcpyAsync(p->cells_f, F->cells, (size_t)F->n_cells * 48, cudaMemcpyDeviceToDevice, ctx->stream));
+  CKA(cudaStreamSynchronize(ctx->stream));
+#undef CKA
+  cleanup();
+  ctx->launches += nl;
+  rc = finish_problem(ctx, p);
+  if (rc != RANDT_OK) { free_problem(p); return rc; }
+  *out = p;
+  return RANDT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// problems
+// ---------------------------------------------------------------------------------------------------------------
+int randt_problem_create(randt_ctx* ctx, const float* cells_m, uint32_t n_m, const float* cells_f, uint32_t n_f, const uint32_t* pair_m,
+                         const uint32_t* pair_f, uint32_t n_pairs, const uint32_t* seg_off, uint32_t n_segments, randt_problem** out) {
+  if (!ctx || !out || !seg_off || (n_pairs && (!pair_m || !pair_f)) || (n_m && !cells_m) || (n_f && !cells_f))
+    return fail(ctx, RANDT_E_INVALID, "randt_problem_create: null argument");
+  *out = nullptr;
+  if (seg_off[0] != 0 || seg_off[n_segments] != n_pairs) return fail(ctx, RANDT_E_INVALID, "randt_problem_create: seg_off must span [0, n_pairs]");
+  for (uint32_t s = 0; s < n_segments; ++s) if (seg_off[s + 1] < seg_off[s]) return fail(ctx, RANDT_E_INVALID, "randt_problem_create: seg_off not monotone");
+  for (uint32_t i = 0; i < n_pairs; ++i) if (pair_m[i] >= n_m || pair_f[i] >= n_f) return fail(ctx, RANDT_E_INVALID, "randt_problem_create: pair index out of range");
+  CK(cudaSetDevice(ctx->device));
+  randt_problem* p = new (std::nothrow) randt_problem();
+  if (!p) return RANDT_E_NOMEM;
+  p->device = ctx->device; p->S = n_segments; p->P = n_pairs; p->n_m = n_m; p->n_f = n_f;
+  p->h_seg_off.assign(seg_off, seg_off + n_segments + 1);
+  std::vector<uint2> h_pairs(n_pairs);
+  for (uint32_t i = 0; i < n_pairs; ++i) h_pairs[i] = make_uint2(pair_m[i], pair_f[i]);
+  int rc = RANDT_OK;
+#define CKP(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rc = fail(ctx, RANDT_E_CUDA, #call, e__); free_problem(p); return rc; } } while (0)
+  CKP(dev_alloc(&p->cells_m, (size_t)n_m * 3)); CKP(dev_alloc(&p->cells_f, (size_t)n_f * 3)); CKP(dev_alloc(&p->pairs, n_pairs));
+  if (n_m) CKP(cudaMemcpyAsync(p->cells_m, cells_m, (size_t)n_m * 48, cudaMemcpyHostToDevice, ctx->stream));
+  if (n_f) CKP(cudaMemcpyAsync(p->cells_f, cells_f, (size_t)n_f * 48, cudaMemcpyHostToDevice, ctx->stream));
+  if (n_pairs) CKP(cudaMemcpyAsync(p->pairs, h_pairs.data(), (size_t)n_pairs * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
+  CKP(cudaStreamSynchronize(ctx->stream));
+#undef CKP
+  rc = finish_problem(ctx, p);
+  if (rc != RANDT_OK) { free_problem(p); return rc; }
+  *out = p;
+  return RANDT_OK;
+}
+
+int randt_problem_info(const randt_problem* p, uint32_t* n_segments, uint32_t* n_pairs, uint32_t* n_m, uint32_t* n_f) {
+  if (!p) return RANDT_E_INVALID;
+  if (n_segments) *n_segments = p->S;
+  if (n_pairs) *n_pairs = p->P;
+  if (n_m) *n_m = p->n_m;
+  if (n_f) *n_f = p->n_f;
+  return RANDT_OK;
+}
+
+int randt_problem_download(randt_ctx* ctx, const randt_problem* p, uint32_t* pair_m, uint32_t* pair_f, uint32_t* seg_off) {
+  if (!ctx || !p) return fail(ctx, RANDT_E_INVALID, "randt_problem_download: null argument");
+  CK(cudaSetDevice(ctx->device));
+  if ((pair_m || pair_f) && p->P) {
+    std::vector<uint2> h(p->P);
+    CK(cudaMemcpyAsync(h.data(), p->pairs, (size_t)p->P * sizeof(uint2), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (uint32_t i = 0; i < p->P; ++i) { if (pair_m) pair_m[i] = h[i].x; if (pair_f) pair_f[i] = h[i].y; }
+  }
+  if (seg_off) memcpy(seg_off, p->h_seg_off.data(), p->h_seg_off.size() * 4);
+  return RANDT_OK;
+}
+
+// download the snapshotted cell tables (tests)
+int randt_problem_download_cells(randt_ctx* ctx, const randt_problem* p, float* cells_m, float* cells_f) {
+  if (!ctx || !p) return fail(ctx, RANDT_E_INVALID, "randt_problem_download_cells: null argument");
+  CK(cudaSetDevice(ctx->device));
+  if (cells_m && p->n_m) CK(cudaMemcpyAsync(cells_m, p->cells_m, (size_t)p->n_m * 48, cudaMemcpyDeviceToHost, ctx->stream));
+  if (cells_f && p->n_f) CK(cudaMemcpyAsync(cells_f, p->cells_f, (size_t)p->n_f * 48, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return RANDT_OK;
+}
+
+void randt_problem_destroy(randt_problem* p) { if (p) { cudaSetDevice(p->device); free_problem(p); } }
+
+// ---------------------------------------------------------------------------------------------------------------
+// K3
+// ---------------------------------------------------------------------------------------------------------------
+int randt_eval_emit_dev(randt_ctx* ctx, const randt_problem* p, int variant, const double* d_poses, double* d_r, double* d_J) {
+  if (!ctx || !p || !d_poses || !d_r) return fail(ctx, RANDT_E_INVALID, "randt_eval_emit_dev: null argument");
+  if (check_variant(ctx, variant)) return RANDT_E_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  int nl = 0;
+  CK(launch_eval_emit(view(p), variant, d_poses, d_r, d_J, ctx->d_bad, ctx->stream, &nl));
+  ctx->launches += nl;
+  return RANDT_OK;
+}
+
+int randt_eval_emit(randt_ctx* ctx, const randt_problem* cp, int variant, const double* poses, double* r, double* J) {
+  if (!ctx || !cp || !poses || !r) return fail(ctx, RANDT_E_INVALID, "randt_eval_emit: null argument");
+  if (check_variant(ctx, variant)) return RANDT_E_INVALID;
+  randt_problem* p = const_cast<randt_problem*>(cp);
+  CK(cudaSetDevice(ctx->device));
+  const int np = np_of(variant);
+  if (!p->d_r) CK(dev_alloc(&p->d_r, p->P));
+  if (J && !p->d_J) CK(dev_alloc(&p->d_J, (size_t)p->P * 4));
+  CK(cudaMemcpyAsync(p->d_poses, poses, (size_t)p->S * np * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  int rc = randt_eval_emit_dev(ctx, p, variant, p->d_poses, p->d_r, J ? p->d_J : nullptr);
+  if (rc) return rc;
+  if (p->P) CK(cudaMemcpyAsync(r, p->d_r, (size_t)p->P * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (J && p->P) CK(cudaMemcpyAsync(J, p->d_J, (size_t)p->P * np * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return RANDT_OK;
+}
+
+int randt_eval_fused_dev(randt_ctx* ctx, const randt_problem* p, int variant, const double* d_poses, const randt_loss* loss,
+                         const double* d_mu_per_seg, int want_jac, double* d_out) {
+  if (!ctx || !p || !d_poses || !d_out) return fail(ctx, RANDT_E_INVALID, "randt_eval_fused_dev: null argument");
+  if (check_variant(ctx, variant)) return RANDT_E_INVALID;
+  LossParams lp;
+  if (int rc = make_loss(ctx, loss, &lp)) return rc;
+  CK(cudaSetDevice(ctx->device));
+  // segments without pairs produce no tile: clear their records up front
+  if (p->has_empty_segment) CK(cudaMemsetAsync(d_out, 0, (size_t)p->S * RANDT_FUSED_STRIDE * sizeof(double), ctx->stream));
+  int nl = 0;
+  CK(launch_eval_fused(view(p), variant, d_poses, lp, d_mu_per_seg, want_jac != 0, d_out, ctx->d_bad, ctx->stream, &nl));
+  ctx->launches += nl;
+  return RANDT_OK;
+}
+
+int randt_eval_fused(randt_ctx* ctx, const randt_problem* cp, int variant, const double* poses, const randt_loss* loss,
+                     const double* mu_per_seg, int want_jac, double* out) {
+  if (!ctx || !cp || !poses || !out) return fail(ctx, RANDT_E_INVALID, "randt_eval_fused: null argument");
+  if (check_variant(ctx, variant)) return RANDT_E_INVALID;
+  randt_problem* p = const_cast<randt_problem*>(cp);
+  CK(cudaSetDevice(ctx->device));
+  const int np = np_of(variant);
+  CK(cudaMemcpyAsync(p->d_poses, poses, (size_t)p->S * np * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (mu_per_seg) CK(cudaMemcpyAsync(p->d_mu, mu_per_seg, (size_t)p->S * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  int rc = randt_eval_fused_dev(ctx, p, variant, p->d_poses, loss, mu_per_seg ? p->d_mu : nullptr, want_jac, p->d_out);
+  if (rc) return rc;
+  if (p->S) CK(cudaMemcpyAsync(out, p->d_out, (size_t)p->S * RANDT_FUSED_STRIDE * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return RANDT_OK;
+}
+
+int randt_sweep_costs(randt_ctx* ctx, const randt_problem* cp, uint32_t seg, int variant, const double* poses, uint32_t n_poses,
+                      const randt_loss* loss, double* cost) {
+  if (!ctx || !cp || !poses || !cost) return fail(ctx, RANDT_E_INVALID, "randt_sweep_costs: null argument");
+  if (check_variant(ctx, variant)) return RANDT_E_INVALID;
+  randt_problem* p = const_cast<randt_problem*>(cp);
+  if (seg >= p->S) return fail(ctx, RANDT_E_INVALID, "randt_sweep_costs: segment out of range");
+  LossParams lp;
+  if (int rc = make_loss(ctx, loss, &lp)) return rc;
+  CK(cudaSetDevice(ctx->device));
+  const int np = np_of(variant);
+  const size_t need = (size_t)n_poses * (np + 1);
+  if (p->sweep_cap < need) { cudaFree(p->d_sweep); p->d_sweep = nullptr; p->sweep_cap = 0; CK(dev_alloc(&p->d_sweep, need)); p->sweep_cap = need; }
+  double* d_p = p->d_sweep; double* d_c = p->d_sweep + (size_t)n_poses * np;
+  if (n_poses) CK(cudaMemcpyAsync(d_p, poses, (size_t)n_poses * np * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  int nl = 0;
+  CK(launch_sweep_costs(view(p), p->h_seg_off[seg], p->h_seg_off[seg + 1], variant, d_p, n_poses, lp, d_c, ctx->stream, &nl));
+  ctx->launches += nl;
+  if (n_poses) CK(cudaMemcpyAsync(cost, d_c, (size_t)n_poses * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return RANDT_OK;
+}
+
+}  // extern "C"

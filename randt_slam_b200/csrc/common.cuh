@@ -1,0 +1,108 @@
+// Internal declarations shared by the CUDA translation units (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/randt_gpu.h"
+
+namespace randt {
+
+constexpr int kSmCount = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+
+struct LossParams {  // host-evaluated constants of the loss that do not depend on mu
+  int kind;
+  double a2;      // scale^2           (b = mu * a2)
+  double alpha;
+  double weight;
+  double mu;      // used when no per-segment mu is given
+};
+
+// A work tile: pairs [begin, end) of segment `seg`; `part` = index of the tile inside its segment.
+struct Tile { uint32_t seg, begin, end, part; };
+
+struct DeviceProblem {
+  const float4* cells_m;   // 3 x float4 per cell
+  const float4* cells_f;
+  const uint2* pairs;      // (im, jf)
+  const Tile* tiles;
+  uint32_t n_tiles;
+  const uint32_t* seg_first_tile;  // [S+1]
+  uint32_t n_segments;
+  uint32_t n_pairs;
+  double* partials;        // [n_tiles][kMaxAcc]
+  uint32_t* seg_counters;  // [S] zero between launches
+};
+
+constexpr int kTilePairs = 512;   // pairs per tile
+constexpr int kK3Threads = 128;   // threads per CTA in the pair-evaluation kernels
+constexpr int kMaxAcc = 20;       // accumulators per tile partial (<= 10 H + 4 g + cost + max + sumsq + nonfinite)
+
+// launchers (k3_pair_eval.cu)
+cudaError_t launch_eval_fused(const DeviceProblem& p, int variant, const double* d_poses, const LossParams& lp, const double* d_mu,
+                              bool want_jac, double* d_out, unsigned long long* d_bad, cudaStream_t s, int* n_launches);
+cudaError_t launch_eval_emit(const DeviceProblem& p, int variant, const double* d_poses, double* d_r, double* d_J,
+                             unsigned long long* d_bad, cudaStream_t s, int* n_launches);
+cudaError_t launch_sweep_costs(const DeviceProblem& p, uint32_t pair_begin, uint32_t pair_end, int variant, const double* d_poses,
+                               uint32_t n_poses, const LossParams& lp, double* d_cost, cudaStream_t s, int* n_launches);
+
+// map geometry as the kernels need it
+struct MapGeomDev {
+  int size_x, size_y;
+  uint32_t n_slots;
+  double res, off_x, off_y;
+  int r_stop;  // int(max_linf / res)
+};
+inline MapGeomDev make_geom(const randt_grid_params& g) {
+  MapGeomDev m;
+  m.size_x = g.size_x; m.size_y = g.size_y; m.n_slots = (uint32_t)g.size_x * (uint32_t)g.size_y;
+  m.res = g.resolution;
+  m.off_x = -static_cast<double>((unsigned)g.size_x) / 2.0 * g.resolution;
+  m.off_y = -static_cast<double>((unsigned)g.size_y) / 2.0 * g.resolution;
+  m.r_stop = static_cast<int>(g.max_linf / g.resolution);
+  return m;
+}
+
+// k2_associate.cu
+constexpr int kMaxNeighbours = 8;
+cudaError_t launch_associate(const float4* cells_f, const uint32_t* cell_off_f, const int32_t* slot_f, const float4* cells_m,
+                             const uint32_t* cell_off_m, uint32_t n_maps, uint32_t n_m_total, uint32_t max_m_per_map,
+                             const MapGeomDev& geom, const float4* d_pose_f /*[B] (c,s,tx,ty)*/, int k, int metric,
+                             uint32_t* d_nn /*[n_m_total*k]*/, uint32_t* d_cnt /*[n_m_total]*/, cudaStream_t s, int* n_launches);
+cudaError_t launch_compact_pairs(const uint32_t* d_nn, const uint32_t* d_cnt, const uint32_t* d_scan /*exclusive scan of cnt*/,
+                                 const uint32_t* cell_off_m, const uint32_t* cell_off_f, uint32_t n_maps, uint32_t n_m_total,
+                                 uint32_t max_m_per_map, int k, uint2* d_pairs, cudaStream_t s, int* n_launches);
+cudaError_t launch_exclusive_scan_u32(const uint32_t* d_in, uint32_t* d_out /*[n+1]*/, uint32_t n, uint32_t* d_block_sums, cudaStream_t s,
+                                      int* n_launches);
+
+// k1_voxelize.cu
+enum { VOX_OK = 0, VOX_SPAN = 1, VOX_CELL_CAP = 2, VOX_OUT_OF_MAP = 3 };
+cudaError_t launch_voxelize(const float4* d_pts, const uint32_t* d_scan_off, uint32_t n_scans, uint32_t max_pts_per_scan,
+                            const randt_grid_params& gp, const MapGeomDev& geom, uint32_t cell_cap_per_scan, float4* d_cells_p,
+                            uint32_t* d_npts_p, int32_t* d_labels_p, uint32_t* d_cell_count, int32_t* d_slot, int32_t* d_labels_scratch,
+                            uint32_t* d_order, int* d_status, cudaStream_t s, int* n_launches);
+cudaError_t launch_compact_cells(const float4* d_cells_p, const uint32_t* d_npts_p, const int32_t* d_labels_p, const uint32_t* d_cell_off,
+                                 uint32_t n_scans, uint32_t cell_cap_per_scan, uint32_t max_cells_per_scan, float4* d_cells,
+                                 uint32_t* d_npts, int32_t* d_labels, cudaStream_t s, int* n_launches);
+cudaError_t launch_build_slots(const float4* d_cells, const uint32_t* d_cell_off, uint32_t n_maps, uint32_t max_per_map,
+                               const MapGeomDev& geom, int32_t* d_slot, cudaStream_t s, int* n_launches);
+cudaError_t launch_transform_cells(float4* d_cells, const uint32_t* d_cell_off, uint32_t n_maps, uint32_t max_per_map, const float4* d_trans,
+                                   cudaStream_t s, int* n_launches);
+cudaError_t launch_merge_maps(const float4* f_cells, const uint32_t* f_npts, const uint32_t* f_off, int32_t* f_slot, const float4* m_cells,
+                              const uint32_t* m_npts, const uint32_t* m_off, uint32_t n_maps, const MapGeomDev& geom, const uint32_t* o_off,
+                              float4* o_cells, uint32_t* o_npts, uint32_t* o_count, cudaStream_t s, int* n_launches);
+
+// static_cast<unsigned>(double) as x86-64 gcc defines it for negative inputs: truncate to int64, keep the low 32 bits
+__host__ __device__ inline uint32_t to_u32_trunc(double v) {
+  if (!(v > -9.2e18 && v < 9.2e18)) return 0u;
+  return (uint32_t)(long long)v;
+}
+__host__ __device__ inline uint32_t coord_to_index(const MapGeomDev& g, float x, float y) {
+  const uint32_t mx = to_u32_trunc(((double)x - g.off_x) / g.res);
+  const uint32_t my = to_u32_trunc(((double)y - g.off_y) / g.res);
+  return my * (uint32_t)g.size_x + mx;
+}
+
+}  // namespace randt

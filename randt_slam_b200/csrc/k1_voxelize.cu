@@ -1,0 +1,452 @@
+// K1 — radar point cloud -> NDT cells (sm_100a).  Compiled with -fmad=false (see k2_associate.cu): the reference's cell
+// statistics are sequential float32 sums in point order, and this kernel reproduces that order and rounding exactly.
+//
+// Replaces, per scan:
+//   Grid::cluster                    R/src/radar_preprocessing/grid.cpp:7-14            label = int(x/res) + row*int(y/res)
+//   ClusterGenerator::labelClouds    R/src/radar_preprocessing/radar_preprocessor.cpp:151-169   clusters in ascending-label order
+//   Map::insertCluster               R/src/ndt_representation/ndt_map.cpp:238-245       keep n > min_points; slot table, later wins
+//   Cell::addPointCloud/updateCell   R/src/ndt_representation/ndt_cell.cpp:25-114       mean, population covariance, regularisation
+//
+// One CTA per scan.  Points are read with coalesced float4 loads; labels are binned with a STABLE parallel counting sort
+// (each warp owns a contiguous slice of the scan, per-warp histograms in shared memory, warp-level __match_any_sync ranking)
+// so that every cell sees its points in original order; one thread per occupied label then accumulates the two passes
+// sequentially in float32.  Kept cells are written in ascending-label order into a per-scan padded region and compacted
+// across the batch by a second kernel.
+#include <float.h>
+
+#include "common.cuh"
+
+namespace randt {
+namespace {
+
+constexpr int kVoxThreads = 256;
+constexpr int kVoxWarps = kVoxThreads / 32;
+
+__device__ __forceinline__ uint32_t block_scan_excl(uint32_t v, uint32_t* warp_sums, uint32_t* total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+  if (lane == 31) warp_sums[w] = x;
+  __syncthreads();
+  if (w == 0) {
+    uint32_t s = (lane < kVoxWarps) ? warp_sums[lane] : 0u;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
+    warp_sums[lane] = s;
+  }
+  __syncthreads();
+  const uint32_t base = (w > 0) ? warp_sums[w - 1] : 0u;
+  *total = warp_sums[kVoxWarps - 1];
+  __syncthreads();
+  return base + x - v;
+}
+
+// ---- Eigen 3.3.7 SelfAdjointEigenSolver<Matrix2f> (constructor -> compute(): scale, trivial 2x2 tridiagonalisation, implicit
+// QR with Wilkinson shift, ascending sort), as used by Cell::updateCell's regularisation (ndt_cell.cpp:104-110) ----
+__device__ __forceinline__ float hypot_eigen(float x, float y) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  float p, qp;
+  if (ax > ay) { p = ax; qp = ay / p; } else { p = ay; qp = ax / p; }
+  if (p == 0.0f) return 0.0f;
+  return p * sqrtf(1.0f + qp * qp);
+}
+__device__ __forceinline__ void make_givens(float p, float q, float& c, float& s) {
+  if (q == 0.0f) { c = p < 0.0f ? -1.0f : 1.0f; s = 0.0f; }
+  else if (p == 0.0f) { c = 0.0f; s = q < 0.0f ? 1.0f : -1.0f; }
+  else if (fabsf(p) > fabsf(q)) {
+    const float t = q / p; float u = sqrtf(1.0f + t * t); if (p < 0.0f) u = -u;
+    c = 1.0f / u; s = -t * c;
+  } else {
+    const float t = p / q; float u = sqrtf(1.0f + t * t); if (q < 0.0f) u = -u;
+    s = -1.0f / u; c = -t * s;
+  }
+}
+__device__ void selfadjoint_eig2(float a00, float a10, float a11, float& l0, float& l1, float& v00, float& v01, float& v10, float& v11) {
+  float scale = fmaxf(fmaxf(fabsf(a00), fabsf(a10)), fabsf(a11));
+  if (scale == 0.0f) scale = 1.0f;
+  float d0 = a00 / scale, d1 = a11 / scale, e = a10 / scale;
+  v00 = 1.0f; v01 = 0.0f; v10 = 0.0f; v11 = 1.0f;
+  const float prec = 2.0f * FLT_EPSILON;
+  for (int iter = 0;;) {
+    if (fabsf(e) <= (fabsf(d0) + fabsf(d1)) * prec || fabsf(e) <= FLT_MIN) e = 0.0f;
+    if (e == 0.0f) break;
+    if (++iter > 60) break;
+    const float td = (d0 - d1) * 0.5f;
+    float mu = d1;
+    if (td == 0.0f) mu -= fabsf(e);
+    else {
+      const float e2 = e * e;
+      const float h = hypot_eigen(td, e);
+      if (e2 == 0.0f) mu -= (e / (td + (td > 0.0f ? 1.0f : -1.0f))) * (e / h);
+      else            mu -= e2 / (td + (td > 0.0f ? h : -h));
+    }
+    float c, s;
+    make_givens(d0 - mu, e, c, s);
+    const float sdk = s * d0 + c * e;
+    const float dkp1 = s * e + c * d1;
+    const float nd0 = c * (c * d0 - s * e) - s * (c * e - s * d1);
+    const float nd1 = s * sdk + c * dkp1;
+    const float ne = c * sdk - s * dkp1;
+    d0 = nd0; d1 = nd1; e = ne;
+    if (!(c == 1.0f && s == 0.0f)) {
+      const float ns = -s;
+      float xi = v00, yi = v01; v00 = c * xi + ns * yi; v01 = s * xi + c * yi;
+      xi = v10; yi = v11;       v10 = c * xi + ns * yi; v11 = s * xi + c * yi;
+    }
+  }
+  if (d1 < d0) { float t = d0; d0 = d1; d1 = t; t = v00; v00 = v01; v01 = t; t = v10; v10 = v11; v11 = t; }
+  l0 = d0 * scale; l1 = d1 * scale;
+}
+
+struct CellOut { float mu[3]; float cov[9]; };
+
+// Cell::updateCell for a fresh cell: two sequential float32 passes over the cell's points (ndt_cell.cpp:43-65), then the
+// xy eigenvalue floor and the +1e-6 on the intensity variance (ndt_cell.cpp:102-112).
+__device__ void cell_stats(const float4* __restrict__ pts, const uint32_t* __restrict__ order, uint32_t n, CellOut& o) {
+  float sx = 0.f, sy = 0.f, si = 0.f;
+  for (uint32_t k = 0; k < n; ++k) { const float4 p = __ldg(pts + order[k]); sx += p.x; sy += p.y; si += p.w; }
+  const float nf = (float)n;
+  const float mx = sx / nf, my = sy / nf, mz = si / nf;
+  float c00 = 0.f, c11 = 0.f, c22 = 0.f, c01 = 0.f, c02 = 0.f, c12 = 0.f;
+  for (uint32_t k = 0; k < n; ++k) {
+    const float4 p = __ldg(pts + order[k]);
+    const float dx = p.x - mx, dy = p.y - my, di = p.w - mz;
+    c00 += dx * dx; c11 += dy * dy; c22 += di * di;
+    c01 += dx * dy; c02 += dx * di; c12 += dy * di;
+  }
+  o.mu[0] = mx; o.mu[1] = my; o.mu[2] = mz;
+  o.cov[0] = c00 / nf; o.cov[1] = c01 / nf; o.cov[2] = c02 / nf;
+  o.cov[3] = c01 / nf; o.cov[4] = c11 / nf; o.cov[5] = c12 / nf;
+  o.cov[6] = c02 / nf; o.cov[7] = c12 / nf; o.cov[8] = c22 / nf;
+  float l0, l1, v00, v01, v10, v11;
+  selfadjoint_eig2(o.cov[0], o.cov[3], o.cov[4], l0, l1, v00, v01, v10, v11);
+  l0 = fmaxf(l0, 0.001f * l1);
+  // V * diag(l) * V^-1, left to right (the explicit zeros of the diagonal matrix take part in the sums)
+  const float t00 = v00 * l0 + v01 * 0.0f, t01 = v00 * 0.0f + v01 * l1;
+  const float t10 = v10 * l0 + v11 * 0.0f, t11 = v10 * 0.0f + v11 * l1;
+  const float det = v00 * v11 - v10 * v01;
+  const float invdet = 1.0f / det;
+  const float i00 = v11 * invdet, i10 = -v10 * invdet, i01 = -v01 * invdet, i11 = v00 * invdet;
+  o.cov[0] = t00 * i00 + t01 * i10; o.cov[1] = t00 * i01 + t01 * i11;
+  o.cov[3] = t10 * i00 + t11 * i10; o.cov[4] = t10 * i01 + t11 * i11;
+  o.cov[8] = (float)((double)o.cov[8] + 0.000001);
+}
+
+// per-scan status codes: VOX_* in common.cuh
+
+// dynamic shared memory: uint32 bin_start[span_cap] | uint32 bin_rank[span_cap] | uint16 whist[n_cnt_warps][span_cap]
+__global__ void __launch_bounds__(kVoxThreads) k1_voxelize_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ scan_off,
+                                                                 int row, float label_res, int min_points, MapGeomDev geom,
+                                                                 uint32_t span_cap, int n_cnt_warps, uint32_t cell_cap, float4* __restrict__ cells_out,
+                                                                 uint32_t* __restrict__ npts_out, int32_t* __restrict__ labels_out,
+                                                                 uint32_t* __restrict__ cell_count, int32_t* __restrict__ slot_out,
+                                                                 int32_t* __restrict__ labels_scratch, uint32_t* __restrict__ order, int* __restrict__ status) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t* bin_start = reinterpret_cast<uint32_t*>(smem_raw);
+  uint32_t* bin_rank = bin_start + span_cap;
+  unsigned short* whist = reinterpret_cast<unsigned short*>(bin_rank + span_cap);
+  __shared__ uint32_t warp_sums[32];
+  __shared__ int s_min[kVoxWarps], s_max[kVoxWarps];
+  __shared__ int s_lab_min, s_lab_max;
+
+  const uint32_t b = blockIdx.x;
+  const uint32_t p0 = scan_off[b], p1 = scan_off[b + 1];
+  const uint32_t n = p1 - p0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int32_t* __restrict__ slot = slot_out + (size_t)b * geom.n_slots;
+  for (uint32_t e = tid; e < geom.n_slots; e += kVoxThreads) slot[e] = -1;
+  if (tid == 0) { cell_count[b] = 0; status[b] = VOX_OK; }
+  if (n == 0) return;
+
+  // ---- phase 0: labels (Grid::cluster), min/max label ----
+  int lmin = INT_MAX, lmax = INT_MIN;
+  for (uint32_t e = tid; e < n; e += kVoxThreads) {
+    const float4 p = __ldg(pts + p0 + e);
+    const int lab = (int)(p.x / label_res) + row * (int)(p.y / label_res);   // C++ float->int conversion truncates toward zero
+    labels_scratch[p0 + e] = lab;
+    lmin = min(lmin, lab); lmax = max(lmax, lab);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, o)); lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o)); }
+  if (lane == 0) { s_min[warp] = lmin; s_max[warp] = lmax; }
+  __syncthreads();
+  if (tid == 0) {
+    int a = s_min[0], z = s_max[0];
+    for (int w = 1; w < kVoxWarps; ++w) { a = min(a, s_min[w]); z = max(z, s_max[w]); }
+    s_lab_min = a; s_lab_max = z;
+  }
+  __syncthreads();
+  const int lab_min = s_lab_min;
+  const long long span_ll = (long long)s_lab_max - (long long)lab_min + 1;
+  if (span_ll > (long long)span_cap) { if (tid == 0) status[b] = VOX_SPAN; return; }
+  const uint32_t span = (uint32_t)span_ll;
+
+  // ---- phase 1: per-warp histograms over contiguous slices (stable counting sort, pass 1) ----
+  const uint32_t slice = (n + n_cnt_warps - 1) / n_cnt_warps;
+  if (slice > 65535u) { if (tid == 0) status[b] = VOX_SPAN; return; }
+  for (uint32_t e = tid; e < (uint32_t)n_cnt_warps * span_cap; e += kVoxThreads) whist[e] = 0;
+  __syncthreads();
+  if (warp < n_cnt_warps) {
+    const uint32_t s0 = warp * slice, s1 = min(n, s0 + slice);
+    unsigned short* h = whist + (size_t)warp * span_cap;
+    for (uint32_t base = s0; base < s1; base += 32) {
+      const uint32_t e = base + lane;
+      const bool act = e < s1;
+      const uint32_t bin = act ? (uint32_t)(labels_scratch[p0 + e] - lab_min) : 0xffffffffu;
+      const unsigned peers = __match_any_sync(0xffffffffu, bin);
+      if (act && (__ffs(peers) - 1) == lane) h[bin] = (unsigned short)(h[bin] + __popc(peers));
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: totals per bin -> exclusive scan (bin_start) and rank of occupied bins (ascending label = cluster id) ----
+  uint32_t carry_pts = 0, carry_occ = 0;
+  for (uint32_t base = 0; base < span; base += kVoxThreads) {
+    const uint32_t bin = base + tid;
+    uint32_t tot = 0;
+    if (bin < span) for (int w = 0; w < n_cnt_warps; ++w) tot += whist[(size_t)w * span_cap + bin];
+    uint32_t t_pts, t_occ;
+    const uint32_t ex_pts = block_scan_excl(tot, warp_sums, &t_pts);
+    const uint32_t ex_occ = block_scan_excl(tot > 0 ? 1u : 0u, warp_sums, &t_occ);
+    if (bin < span) {
+      bin_start[bin] = carry_pts + ex_pts;
+      bin_rank[bin] = carry_occ + ex_occ;
+      // turn per-warp counts into per-warp offsets inside the bin
+      uint32_t run = 0;
+      for (int w = 0; w < n_cnt_warps; ++w) {
+        const uint32_t c = whist[(size_t)w * span_cap + bin];
+        whist[(size_t)w * span_cap + bin] = (unsigned short)run;
+        run += c;
+      }
+      if (run > 65535u) status[b] = VOX_SPAN;   // a single cell with > 65535 points does not fit the 16-bit offsets
+    }
+    carry_pts += t_pts; carry_occ += t_occ;
+  }
+  __syncthreads();
+
+  // ---- phase 3: stable scatter of point indices ----
+  if (warp < n_cnt_warps) {
+    const uint32_t s0 = warp * slice, s1 = min(n, s0 + slice);
+    unsigned short* h = whist + (size_t)warp * span_cap;
+    for (uint32_t base = s0; base < s1; base += 32) {
+      const uint32_t e = base + lane;
+      const bool act = e < s1;
+      const uint32_t bin = act ? (uint32_t)(labels_scratch[p0 + e] - lab_min) : 0xffffffffu;
+      const unsigned peers = __match_any_sync(0xffffffffu, bin);
+      const int leader = __ffs(peers) - 1;
+      uint32_t off = 0;
+      if (act && leader == lane) { off = h[bin]; h[bin] = (unsigned short)(off + __popc(peers)); }
+      off = __shfl_sync(0xffffffffu, off, leader);
+      if (act) order[p0 + bin_start[bin] + off + __popc(peers & ((1u << lane) - 1u))] = p0 + e;
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 4: one thread per occupied label: keep test, sequential float32 statistics ----
+  // cluster c (rank among occupied bins) is kept iff count > min_points; kept clusters are numbered in ascending label order.
+  uint32_t carry_keep = 0;
+  for (uint32_t base = 0; base < span; base += kVoxThreads) {
+    const uint32_t bin = base + tid;
+    uint32_t cnt = 0;
+    if (bin < span) cnt = ((bin + 1 < span) ? bin_start[bin + 1] : n) - bin_start[bin];
+    const bool keep = (bin < span) && cnt > 0 && ((long long)cnt > (long long)min_points);
+    uint32_t t_keep;
+    const uint32_t ex = block_scan_excl(keep ? 1u : 0u, warp_sums, &t_keep);
+    if (keep) {
+      const uint32_t ci = carry_keep + ex;
+      if (ci < cell_cap) {
+        CellOut o;
+        cell_stats(pts, order + p0 + bin_start[bin], cnt, o);
+        const uint32_t s = coord_to_index(geom, o.mu[0], o.mu[1]);
+        float4* dst = cells_out + 3 * ((size_t)b * cell_cap + ci);
+        dst[0] = make_float4(o.mu[0], o.mu[1], o.mu[2], o.cov[0]);
+        dst[1] = make_float4(o.cov[1], o.cov[2], o.cov[3], o.cov[4]);
+        dst[2] = make_float4(o.cov[5], o.cov[6], o.cov[7], o.cov[8]);
+        npts_out[(size_t)b * cell_cap + ci] = cnt;
+        labels_out[(size_t)b * cell_cap + ci] = (int32_t)bin + lab_min;
+        // the reference would throw (vector::at) for a mean outside the map; flagged instead, cell kept without a slot
+        if (s < geom.n_slots) atomicMax(&slot[s], (int32_t)ci);   // "later cluster wins" == largest kept index
+        else status[b] = VOX_OUT_OF_MAP;
+      } else {
+        status[b] = VOX_CELL_CAP;
+      }
+    }
+    carry_keep += t_keep;
+  }
+  if (tid == 0) cell_count[b] = min(carry_keep, cell_cap);
+}
+
+__global__ void k1_compact_cells_kernel(const float4* __restrict__ cells_p, const uint32_t* __restrict__ npts_p, const int32_t* __restrict__ labels_p,
+                                        const uint32_t* __restrict__ cell_off, uint32_t cell_cap, float4* __restrict__ cells,
+                                        uint32_t* __restrict__ npts, int32_t* __restrict__ labels) {
+  const uint32_t b = blockIdx.y;
+  const uint32_t c0 = cell_off[b], nc = cell_off[b + 1] - c0;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nc) return;
+  const size_t src = (size_t)b * cell_cap + i;
+#pragma unroll
+  for (int e = 0; e < 3; ++e) cells[3 * (size_t)(c0 + i) + e] = cells_p[3 * src + e];
+  npts[c0 + i] = npts_p[src];
+  if (labels) labels[c0 + i] = labels_p[src];
+}
+
+// grid_indizes_ rebuilt from cell means, cell order, later cell wins (Map::insertCluster semantics)
+__global__ void build_slots_kernel(const float4* __restrict__ cells, const uint32_t* __restrict__ cell_off, MapGeomDev geom, int32_t* __restrict__ slot_out) {
+  const uint32_t b = blockIdx.y;
+  const uint32_t c0 = cell_off[b], nc = cell_off[b + 1] - c0;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nc) return;
+  const float4 a = cells[3 * (size_t)(c0 + i)];
+  const uint32_t s = coord_to_index(geom, a.x, a.y);
+  if (s < geom.n_slots) atomicMax(&slot_out[(size_t)b * geom.n_slots + s], (int32_t)i);
+}
+
+// Map::transformMap: every cell of map b by trans[b] = (c, s, tx, ty), float32 (Cell::transformCell, ndt_cell.cpp:117-123)
+__global__ void transform_cells_kernel(float4* __restrict__ cells, const uint32_t* __restrict__ cell_off, const float4* __restrict__ trans) {
+  const uint32_t b = blockIdx.y;
+  const uint32_t c0 = cell_off[b], nc = cell_off[b + 1] - c0;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nc) return;
+  const float4 T = trans[b];
+  const float c = T.x, s = T.y, ns = -T.y;
+  float4* p = cells + 3 * (size_t)(c0 + i);
+  const float4 A = p[0], B = p[1], C = p[2];
+  const float cov[9] = {A.w, B.x, B.y, B.z, B.w, C.x, C.y, C.z, C.w};
+  const float mx = T.z + (c * A.x + ns * A.y);
+  const float my = T.w + (s * A.x + c * A.y);
+  float Tm[3][3], O[9];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) { Tm[0][j] = c * cov[j] + ns * cov[3 + j]; Tm[1][j] = s * cov[j] + c * cov[3 + j]; Tm[2][j] = cov[6 + j]; }
+#pragma unroll
+  for (int r = 0; r < 3; ++r) { O[r * 3 + 0] = Tm[r][0] * c + Tm[r][1] * ns; O[r * 3 + 1] = Tm[r][0] * s + Tm[r][1] * c; O[r * 3 + 2] = Tm[r][2]; }
+  p[0] = make_float4(mx, my, A.z, O[0]);
+  p[1] = make_float4(O[1], O[2], O[3], O[4]);
+  p[2] = make_float4(O[5], O[6], O[7], O[8]);
+}
+
+// Map::mergeMapCell + Cell::operator+=.  One warp per map; lane 0 walks the moving cells in order (the recursion is
+// sequential by construction: a mover may create the cell the next mover merges into).  Output region of map b has room for
+// n_f(b) + n_m(b) cells; the fixed slot table is updated in place.
+__global__ void merge_maps_kernel(const float4* __restrict__ f_cells, const uint32_t* __restrict__ f_npts, const uint32_t* __restrict__ f_off,
+                                  int32_t* __restrict__ f_slot, const float4* __restrict__ m_cells, const uint32_t* __restrict__ m_npts,
+                                  const uint32_t* __restrict__ m_off, MapGeomDev geom, const uint32_t* __restrict__ o_off, float4* __restrict__ o_cells,
+                                  uint32_t* __restrict__ o_npts, uint32_t* __restrict__ o_count) {
+  const uint32_t b = blockIdx.x;
+  const uint32_t f0 = f_off[b], nf = f_off[b + 1] - f0, m0 = m_off[b], nm = m_off[b + 1] - m0, o0 = o_off[b];
+  // copy the existing fixed cells (all lanes)
+  for (uint32_t e = threadIdx.x; e < nf * 3; e += blockDim.x) o_cells[3 * (size_t)o0 + e] = f_cells[3 * (size_t)f0 + e];
+  for (uint32_t e = threadIdx.x; e < nf; e += blockDim.x) o_npts[o0 + e] = f_npts[f0 + e];
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  int32_t* slot = f_slot + (size_t)b * geom.n_slots;
+  uint32_t count = nf;
+  for (uint32_t i = 0; i < nm; ++i) {
+    const float4 A = m_cells[3 * (size_t)(m0 + i)], Bq = m_cells[3 * (size_t)(m0 + i) + 1], Cq = m_cells[3 * (size_t)(m0 + i) + 2];
+    const uint32_t s = coord_to_index(geom, A.x, A.y);
+    if (s >= geom.n_slots) continue;
+    const int32_t idx = slot[s];
+    if (idx < 0) {
+      float4* dst = o_cells + 3 * (size_t)(o0 + count);
+      dst[0] = A; dst[1] = Bq; dst[2] = Cq;
+      o_npts[o0 + count] = m_npts[m0 + i];
+      slot[s] = (int32_t)count;
+      ++count;
+    } else {
+      float4* dst = o_cells + 3 * (size_t)(o0 + idx);
+      const float4 FA = dst[0], FB = dst[1], FC = dst[2];
+      float amu[3] = {FA.x, FA.y, FA.z};
+      float acov[9] = {FA.w, FB.x, FB.y, FB.z, FB.w, FC.x, FC.y, FC.z, FC.w};
+      const float bmu[3] = {A.x, A.y, A.z};
+      const float bcov[9] = {A.w, Bq.x, Bq.y, Bq.z, Bq.w, Cq.x, Cq.y, Cq.z, Cq.w};
+      const uint32_t na = o_npts[o0 + idx], nb = m_npts[m0 + i];
+      // operator+= (ndt_cell.h:133-142): unsigned / size_t weights converted to float, (na*nb)/(na+nb) is integer division
+      const float w1 = (float)(na - 1u);
+      const float w2 = (float)((unsigned long long)nb - 1ull);
+      const float w3 = (float)(((unsigned long long)na * (unsigned long long)nb) / ((unsigned long long)na + (unsigned long long)nb));
+      const float d[3] = {amu[0] - bmu[0], amu[1] - bmu[1], amu[2] - bmu[2]};
+      for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) acov[r * 3 + c] = (w1 * acov[r * 3 + c] + w2 * bcov[r * 3 + c]) + w3 * (d[r] * d[c]);
+      const float n1 = (float)na, n2 = (float)(unsigned long long)nb, nn = (float)((unsigned long long)na + (unsigned long long)nb);
+      for (int r = 0; r < 3; ++r) amu[r] = ((amu[r] * n1) + (bmu[r] * n2)) / nn;
+      const uint32_t nsum = na + nb;
+      const float dn = (float)(nsum - 1u);
+      for (int e = 0; e < 9; ++e) acov[e] /= dn;
+      dst[0] = make_float4(amu[0], amu[1], amu[2], acov[0]);
+      dst[1] = make_float4(acov[1], acov[2], acov[3], acov[4]);
+      dst[2] = make_float4(acov[5], acov[6], acov[7], acov[8]);
+      o_npts[o0 + idx] = nsum;
+    }
+  }
+  o_count[b] = count;
+}
+
+}  // namespace
+
+cudaError_t launch_voxelize(const float4* d_pts, const uint32_t* d_scan_off, uint32_t n_scans, uint32_t max_pts_per_scan,
+                            const randt_grid_params& gp, const MapGeomDev& geom, uint32_t cell_cap_per_scan, float4* d_cells_p,
+                            uint32_t* d_npts_p, int32_t* d_labels_p, uint32_t* d_cell_count, int32_t* d_slot, int32_t* d_labels_scratch,
+                            uint32_t* d_order, int* d_status, cudaStream_t s, int* n_launches) {
+  if (n_scans == 0) return cudaSuccess;
+  const int row = static_cast<int>(sqrt((double)(size_t)gp.n_clusters));
+  if (row <= 0) return cudaErrorInvalidValue;
+  const float label_res = gp.max_range * 2 / row;
+  // label span bound for points within +-max_range (plus margin); a scan whose labels span more reports VOX_SPAN
+  const long long bound = (long long)(row + 4) * (long long)(row + 4);
+  uint32_t span_cap = (uint32_t)((bound + 255) / 256 * 256);
+  const size_t smem_max = 220 * 1024;
+  if ((size_t)span_cap * (8 + 2) > smem_max) span_cap = (uint32_t)(smem_max / 10 / 256 * 256);
+  int n_cnt_warps = (int)((smem_max - (size_t)span_cap * 8) / ((size_t)span_cap * 2));
+  if (n_cnt_warps > kVoxWarps) n_cnt_warps = kVoxWarps;
+  if (n_cnt_warps < 1) n_cnt_warps = 1;
+  // small scans do not need all counting warps (fewer histograms to clear and fold)
+  while (n_cnt_warps > 1 && (max_pts_per_scan + n_cnt_warps - 1) / n_cnt_warps < 256) n_cnt_warps >>= 1;
+  const size_t smem = (size_t)span_cap * 8 + (size_t)n_cnt_warps * span_cap * 2;
+  cudaError_t e = cudaFuncSetAttribute(k1_voxelize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k1_voxelize_kernel<<<n_scans, kVoxThreads, smem, s>>>(d_pts, d_scan_off, row, label_res, gp.min_points, geom, span_cap, n_cnt_warps,
+                                                        cell_cap_per_scan, d_cells_p, d_npts_p, d_labels_p, d_cell_count, d_slot,
+                                                        d_labels_scratch, d_order, d_status);
+  if (n_launches) *n_launches += 1;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_compact_cells(const float4* d_cells_p, const uint32_t* d_npts_p, const int32_t* d_labels_p, const uint32_t* d_cell_off,
+                                 uint32_t n_scans, uint32_t cell_cap_per_scan, uint32_t max_cells_per_scan, float4* d_cells,
+                                 uint32_t* d_npts, int32_t* d_labels, cudaStream_t s, int* n_launches) {
+  if (n_scans == 0 || max_cells_per_scan == 0) return cudaSuccess;
+  dim3 grid((max_cells_per_scan + 127) / 128, n_scans);
+  k1_compact_cells_kernel<<<grid, 128, 0, s>>>(d_cells_p, d_npts_p, d_labels_p, d_cell_off, cell_cap_per_scan, d_cells, d_npts, d_labels);
+  if (n_launches) *n_launches += 1;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_build_slots(const float4* d_cells, const uint32_t* d_cell_off, uint32_t n_maps, uint32_t max_per_map,
+                               const MapGeomDev& geom, int32_t* d_slot, cudaStream_t s, int* n_launches) {
+  if (n_maps == 0 || max_per_map == 0) return cudaSuccess;
+  dim3 grid((max_per_map + 127) / 128, n_maps);
+  build_slots_kernel<<<grid, 128, 0, s>>>(d_cells, d_cell_off, geom, d_slot);
+  if (n_launches) *n_launches += 1;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_transform_cells(float4* d_cells, const uint32_t* d_cell_off, uint32_t n_maps, uint32_t max_per_map, const float4* d_trans,
+                                   cudaStream_t s, int* n_launches) {
+  if (n_maps == 0 || max_per_map == 0) return cudaSuccess;
+  dim3 grid((max_per_map + 127) / 128, n_maps);
+  transform_cells_kernel<<<grid, 128, 0, s>>>(d_cells, d_cell_off, d_trans);
+  if (n_launches) *n_launches += 1;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_merge_maps(const float4* f_cells, const uint32_t* f_npts, const uint32_t* f_off, int32_t* f_slot, const float4* m_cells,
+                              const uint32_t* m_npts, const uint32_t* m_off, uint32_t n_maps, const MapGeomDev& geom, const uint32_t* o_off,
+                              float4* o_cells, uint32_t* o_npts, uint32_t* o_count, cudaStream_t s, int* n_launches) {
+  if (n_maps == 0) return cudaSuccess;
+  merge_maps_kernel<<<n_maps, 64, 0, s>>>(f_cells, f_npts, f_off, f_slot, m_cells, m_npts, m_off, geom, o_off, o_cells, o_npts, o_count);
+  if (n_launches) *n_launches += 1;
+  return cudaGetLastError();
+}
+
+}  // namespace randt

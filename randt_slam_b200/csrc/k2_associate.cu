@@ -1,0 +1,249 @@
+// K2 — moving-cell -> fixed-cell association (sm_100a).  Compiled with -fmad=false: every float32 operation below is a
+// separate IEEE multiply/add in the order the reference's Eigen expressions evaluate them, so distances (and therefore
+// the chosen neighbour sets) are reproducible bit for bit.
+//
+// Replaces, per moving cell, the association half of Matcher::addNDTFactor
+//   R/src/ndt_registration/ndt_matcher.cpp:200-217 (Mahalanobis lookup) / :249-253 (Euclidean lookup)
+// = Cell::transformCell (R/src/ndt_representation/ndt_cell.cpp:117-123) by the initial guess cast to float,
+//   Map::getClosestCells (R/src/ndt_representation/ndt_map.cpp:101-151) with Map::getAdjacentIndizes (:163-175) windows and
+//   Cell::mahalanobisSquaredIntensity (ndt_cell.cpp:172-176), first k by (distance, index).
+// One thread per moving cell; the fixed map's dense slot table and cells are read through the read-only path.
+#include "common.cuh"
+
+namespace randt {
+namespace {
+
+struct CellF { float mu[3]; float cov[9]; };
+
+__device__ __forceinline__ CellF load_cell_f(const float4* __restrict__ tab, uint32_t idx) {
+  const float4 a = __ldg(tab + 3 * (size_t)idx), b = __ldg(tab + 3 * (size_t)idx + 1), c = __ldg(tab + 3 * (size_t)idx + 2);
+  CellF o;
+  o.mu[0] = a.x; o.mu[1] = a.y; o.mu[2] = a.z;
+  o.cov[0] = a.w; o.cov[1] = b.x; o.cov[2] = b.y; o.cov[3] = b.z; o.cov[4] = b.w; o.cov[5] = c.x; o.cov[6] = c.y; o.cov[7] = c.z; o.cov[8] = c.w;
+  return o;
+}
+
+// Cell::transformCell with trans = [[c,-s,tx],[s,c,ty]] (float)
+__device__ __forceinline__ void transform_cell_f(CellF& q, float c, float s, float tx, float ty) {
+  const float ns = -s;
+  const float x = q.mu[0], y = q.mu[1];
+  q.mu[0] = tx + (c * x + ns * y);
+  q.mu[1] = ty + (s * x + c * y);
+  float T[3][3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    T[0][j] = c * q.cov[j] + ns * q.cov[3 + j];
+    T[1][j] = s * q.cov[j] + c * q.cov[3 + j];
+    T[2][j] = q.cov[6 + j];
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    q.cov[i * 3 + 0] = T[i][0] * c + T[i][1] * ns;
+    q.cov[i * 3 + 1] = T[i][0] * s + T[i][1] * c;
+    q.cov[i * 3 + 2] = T[i][2];
+  }
+}
+
+// (v^T inv(m)) v with Eigen's cofactor inverse evaluation order (float)
+__device__ __forceinline__ float inv3_quadform_f(const float m[9], const float v[3]) {
+#define M_(r, c) m[(r) * 3 + (c)]
+#define COF_(i, j) (M_(((i) + 1) % 3, ((j) + 1) % 3) * M_(((i) + 2) % 3, ((j) + 2) % 3) - M_(((i) + 1) % 3, ((j) + 2) % 3) * M_(((i) + 2) % 3, ((j) + 1) % 3))
+  const float c0 = COF_(0, 0), c1 = COF_(1, 0), c2 = COF_(2, 0);
+  const float det = c0 * M_(0, 0) + (c1 * M_(1, 0) + c2 * M_(2, 0));
+  const float invdet = 1.0f / det;
+  float inv[3][3];
+  inv[0][0] = c0 * invdet; inv[0][1] = c1 * invdet; inv[0][2] = c2 * invdet;
+  inv[1][0] = COF_(0, 1) * invdet; inv[1][1] = COF_(1, 1) * invdet; inv[1][2] = COF_(2, 1) * invdet;
+  inv[2][0] = COF_(0, 2) * invdet; inv[2][1] = COF_(1, 2) * invdet; inv[2][2] = COF_(2, 2) * invdet;
+#undef COF_
+#undef M_
+  float t[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) t[j] = v[0] * inv[0][j] + (v[1] * inv[1][j] + v[2] * inv[2][j]);
+  return t[0] * v[0] + (t[1] * v[1] + t[2] * v[2]);
+}
+
+__device__ __forceinline__ bool closer(double d, uint32_t i, double bd, uint32_t bi) {
+  // std::sort on pair<double, size_t>: ascending distance, ties by index.  NaN never precedes anything.
+  return (d < bd) || (d == bd && i < bi);
+}
+
+__global__ void __launch_bounds__(128) k2_associate_kernel(const float4* __restrict__ cells_f, const uint32_t* __restrict__ cell_off_f,
+                                                          const int32_t* __restrict__ slot_f, const float4* __restrict__ cells_m,
+                                                          const uint32_t* __restrict__ cell_off_m, MapGeomDev geom,
+                                                          const float4* __restrict__ pose_f, int k, int metric, uint32_t* __restrict__ nn,
+                                                          uint32_t* __restrict__ cnt) {
+  const uint32_t b = blockIdx.y;
+  const uint32_t m0 = cell_off_m[b], m1 = cell_off_m[b + 1];
+  const uint32_t i = m0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m1) return;
+  const float4 T = __ldg(pose_f + b);   // (c, s, tx, ty)
+  CellF q = load_cell_f(cells_m, i);
+  if (metric == RANDT_LOOKUP_MAHALANOBIS_INTENSITY) {
+    transform_cell_f(q, T.x, T.y, T.z, T.w);
+  } else {
+    const float x = q.mu[0], y = q.mu[1];
+    q.mu[0] = (T.x * x - T.y * y) + T.z;
+    q.mu[1] = (T.y * x + T.x * y) + T.w;
+  }
+  const uint32_t f0 = cell_off_f[b];
+  const int32_t* __restrict__ slot = slot_f + (size_t)b * geom.n_slots;
+  const uint32_t center = coord_to_index(geom, q.mu[0], q.mu[1]);
+
+  double best_d[kMaxNeighbours];
+  uint32_t best_i[kMaxNeighbours];
+  int n_best = 0;
+  uint32_t total = 0;
+  int r = 0;
+  while (total < (uint32_t)(k > 0 ? k : 0)) {
+    // ring r of the window (all (i,j) with max(|i|,|j|) == r); earlier rings were visited in earlier iterations, which is
+    // equivalent to the reference re-collecting the whole (2r+1)^2 window because the final candidate set is sorted.
+    for (int di = -r; di <= r; ++di) {
+      const int step = (di == -r || di == r) ? 1 : 2 * r;   // full column at the ring's ends, else only top & bottom
+      for (int dj = -r; dj <= r; dj += (step > 0 ? step : 1)) {
+        const uint32_t ni = center + (uint32_t)di + (uint32_t)dj * (uint32_t)geom.size_x;
+        if (ni < geom.n_slots) {
+          const int32_t ci = __ldg(slot + ni);
+          if (ci >= 0) {
+            const CellF f = load_cell_f(cells_f, f0 + (uint32_t)ci);
+            double dist;
+            if (metric == RANDT_LOOKUP_MAHALANOBIS_INTENSITY) {
+              float S[9], d[3];
+#pragma unroll
+              for (int e = 0; e < 9; ++e) S[e] = f.cov[e] + q.cov[e];
+#pragma unroll
+              for (int e = 0; e < 3; ++e) d[e] = f.mu[e] - q.mu[e];
+              dist = (double)inv3_quadform_f(S, d);
+            } else {
+              const float dx = q.mu[0] - f.mu[0], dy = q.mu[1] - f.mu[1];
+              dist = (double)sqrtf(dx * dx + dy * dy);
+            }
+            ++total;
+            // insert into the sorted top-k list
+            int pos = n_best;
+            if (n_best == k && !closer(dist, (uint32_t)ci, best_d[k - 1], best_i[k - 1])) pos = -1;
+            if (pos >= 0) {
+              if (n_best < k) ++n_best;
+              int p = n_best - 1;
+              while (p > 0 && closer(dist, (uint32_t)ci, best_d[p - 1], best_i[p - 1])) {
+                best_d[p] = best_d[p - 1]; best_i[p] = best_i[p - 1]; --p;
+              }
+              best_d[p] = dist; best_i[p] = (uint32_t)ci;
+            }
+          }
+        }
+        if (r == 0) break;
+      }
+    }
+    ++r;
+    if (r >= geom.r_stop) break;
+  }
+  cnt[i] = (uint32_t)n_best;
+  for (int t = 0; t < n_best; ++t) nn[(size_t)i * k + t] = best_i[t];
+}
+
+__global__ void k2_compact_pairs_kernel(const uint32_t* __restrict__ nn, const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ scan,
+                                        const uint32_t* __restrict__ cell_off_m, const uint32_t* __restrict__ cell_off_f, int k,
+                                        uint2* __restrict__ pairs) {
+  const uint32_t b = blockIdx.y;
+  const uint32_t m0 = cell_off_m[b], m1 = cell_off_m[b + 1];
+  const uint32_t i = m0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m1) return;
+  const uint32_t f0 = cell_off_f[b];
+  const uint32_t base = scan[i], n = cnt[i];
+  for (uint32_t t = 0; t < n; ++t) pairs[base + t] = make_uint2(i, f0 + nn[(size_t)i * k + t]);
+}
+
+// ---- exclusive scan of u32 (three small kernels; construction-time only) -------------------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 4;
+constexpr int kScanBlock = kScanThreads * kScanItems;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total) {
+  __shared__ uint32_t warp_sums[32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+  if (lane == 31) warp_sums[w] = x;
+  __syncthreads();
+  if (w == 0) {
+    uint32_t s = (lane < (int)(blockDim.x >> 5)) ? warp_sums[lane] : 0u;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
+    warp_sums[lane] = s;
+  }
+  __syncthreads();
+  const uint32_t base = (w > 0) ? warp_sums[w - 1] : 0u;
+  if (total) *total = warp_sums[(blockDim.x >> 5) - 1];
+  __syncthreads();
+  return base + x - v;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_local_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n,
+                                                                  uint32_t* __restrict__ block_sums) {
+  const uint32_t base = blockIdx.x * kScanBlock + threadIdx.x * kScanItems;
+  uint32_t v[kScanItems], s = 0;
+#pragma unroll
+  for (int e = 0; e < kScanItems; ++e) { v[e] = (base + e < n) ? in[base + e] : 0u; s += v[e]; }
+  uint32_t total;
+  uint32_t ex = block_exclusive_scan(s, &total);
+#pragma unroll
+  for (int e = 0; e < kScanItems; ++e) { if (base + e < n) out[base + e] = ex; ex += v[e]; }
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(kScanThreads) scan_sums_kernel(uint32_t* __restrict__ block_sums, uint32_t n_blocks, uint32_t* __restrict__ total_out) {
+  uint32_t carry = 0;
+  for (uint32_t base = 0; base < n_blocks; base += kScanThreads) {
+    const uint32_t idx = base + threadIdx.x;
+    const uint32_t v = idx < n_blocks ? block_sums[idx] : 0u;
+    uint32_t total;
+    const uint32_t ex = block_exclusive_scan(v, &total);
+    if (idx < n_blocks) block_sums[idx] = carry + ex;
+    carry += total;
+  }
+  if (threadIdx.x == 0) *total_out = carry;
+}
+__global__ void __launch_bounds__(kScanThreads) scan_add_kernel(uint32_t* __restrict__ out, uint32_t n, const uint32_t* __restrict__ block_sums) {
+  const uint32_t base = blockIdx.x * kScanBlock + threadIdx.x * kScanItems;
+  const uint32_t add = block_sums[blockIdx.x];
+#pragma unroll
+  for (int e = 0; e < kScanItems; ++e) if (base + e < n) out[base + e] += add;
+}
+
+}  // namespace
+
+cudaError_t launch_associate(const float4* cells_f, const uint32_t* cell_off_f, const int32_t* slot_f, const float4* cells_m,
+                             const uint32_t* cell_off_m, uint32_t n_maps, uint32_t n_m_total, uint32_t max_m_per_map,
+                             const MapGeomDev& geom, const float4* d_pose_f, int k, int metric, uint32_t* d_nn, uint32_t* d_cnt,
+                             cudaStream_t s, int* n_launches) {
+  if (n_maps == 0 || max_m_per_map == 0) return cudaSuccess;
+  dim3 grid((max_m_per_map + 127) / 128, n_maps);
+  k2_associate_kernel<<<grid, 128, 0, s>>>(cells_f, cell_off_f, slot_f, cells_m, cell_off_m, geom, d_pose_f, k, metric, d_nn, d_cnt);
+  if (n_launches) *n_launches += 1;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_compact_pairs(const uint32_t* d_nn, const uint32_t* d_cnt, const uint32_t* d_scan, const uint32_t* cell_off_m,
+                                 const uint32_t* cell_off_f, uint32_t n_maps, uint32_t n_m_total, uint32_t max_m_per_map, int k,
+                                 uint2* d_pairs, cudaStream_t s, int* n_launches) {
+  if (n_maps == 0 || max_m_per_map == 0) return cudaSuccess;
+  dim3 grid((max_m_per_map + 127) / 128, n_maps);
+  k2_compact_pairs_kernel<<<grid, 128, 0, s>>>(d_nn, d_cnt, d_scan, cell_off_m, cell_off_f, k, d_pairs);
+  if (n_launches) *n_launches += 1;
+  return cudaGetLastError();
+}
+
+// d_out has n+1 entries: exclusive scan plus the grand total at d_out[n].  d_block_sums: >= ceil(n/1024) entries.
+cudaError_t launch_exclusive_scan_u32(const uint32_t* d_in, uint32_t* d_out, uint32_t n, uint32_t* d_block_sums, cudaStream_t s,
+                                      int* n_launches) {
+  if (n == 0) return cudaMemsetAsync(d_out, 0, sizeof(uint32_t), s);
+  const uint32_t n_blocks = (n + kScanBlock - 1) / kScanBlock;
+  scan_local_kernel<<<n_blocks, kScanThreads, 0, s>>>(d_in, d_out, n, d_block_sums);
+  scan_sums_kernel<<<1, kScanThreads, 0, s>>>(d_block_sums, n_blocks, d_out + n);
+  scan_add_kernel<<<n_blocks, kScanThreads, 0, s>>>(d_out, n, d_block_sums);
+  if (n_launches) *n_launches += 3;
+  return cudaGetLastError();
+}
+
+}  // namespace randt

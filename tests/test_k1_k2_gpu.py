@@ -1,0 +1,146 @@
+"""K1 (voxelise), K2 (associate) and map maintenance parity: GPU through the C-ABI vs the CPU oracle.
+
+Index work (labels, point counts, slot tables, neighbour lists, pair order) must be identical.  Cell statistics are float32 in
+both paths with the same operation order (K1/K2 are built with -fmad=false), so they are asserted bit-identical as well;
+the documented tolerance for the float path is 1e-5 relative (north_star), the observed difference is 0 ulp.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from randt_slam_b200 import capi, params as P, synth
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+PRESETS = {"oxford": P.OXFORD, "c1": P.C1, "indoor": P.INDOOR, "outdoor": P.OUTDOOR}
+
+
+def batch_scans(p, seeds):
+    scans = [H.make_scan(p, s, (0.3 * i, -0.2 * i, 0.01 * i), 50 + s) for i, s in enumerate(seeds)]
+    scans.insert(1, np.zeros((0, 4), np.float32))                       # empty scan
+    scans.insert(3, scans[0][: p.min_points_per_cell].copy())          # too few points for any cell
+    off = np.zeros(len(scans) + 1, np.uint32)
+    off[1:] = np.cumsum([len(s) for s in scans])
+    return scans, off, np.concatenate(scans, 0)
+
+
+@pytest.mark.parametrize("preset", list(PRESETS))
+def test_voxelize_matches_oracle(oracle, gpu_ctx, preset):
+    p = PRESETS[preset]
+    scans, off, pts = batch_scans(p, [1, 2, 3])
+    m = gpu_ctx.voxelize(pts, off, capi.grid_params(p))
+    d = m.download(want_labels=True)
+    assert len(d["cell_off"]) == len(scans) + 1
+    total = 0
+    for b, sc in enumerate(scans):
+        v = oracle.voxelize(sc, *H.vox_args(p))
+        a, z = d["cell_off"][b], d["cell_off"][b + 1]
+        assert z - a == len(v["cells"]), "cell count differs for scan %d" % b
+        assert np.array_equal(d["labels"][a:z], v["labels"])
+        assert np.array_equal(d["npts"][a:z], v["npts"])
+        assert np.array_equal(d["slot"][b], v["slot"])
+        if z > a:
+            assert H.rel_err(d["cells"][a:z, :3], v["cells"][:, :3]) < 1e-5
+            assert np.array_equal(d["cells"][a:z].view(np.uint32), v["cells"].view(np.uint32)), "cell statistics not bit-identical"
+        total += z - a
+    assert total > 100
+
+
+def test_voxelize_device_pointer_and_large_batch(oracle, gpu_ctx):
+    p = P.OXFORD
+    base = [H.make_scan(p, 4, (0.1 * i, 0.0, 0.0), 300 + i) for i in range(4)]
+    scans = [base[i % 4] for i in range(64)]
+    off = np.zeros(65, np.uint32); off[1:] = np.cumsum([len(s) for s in scans])
+    pts = np.concatenate(scans, 0)
+    m = gpu_ctx.voxelize(pts, off, capi.grid_params(p))
+    d = m.download()
+    ref = [oracle.voxelize(s, *H.vox_args(p)) for s in base]
+    for b in range(64):
+        a, z = d["cell_off"][b], d["cell_off"][b + 1]
+        assert np.array_equal(d["cells"][a:z].view(np.uint32), ref[b % 4]["cells"].view(np.uint32))
+
+
+def test_voxelize_rejects_far_points(gpu_ctx):
+    p = P.OXFORD
+    pts = np.zeros((50, 4), np.float32); pts[:, 0] = 1e6; pts[:, 3] = 90
+    pts[:25, 0] = -1e6
+    with pytest.raises(capi.RandtError) as e:
+        gpu_ctx.voxelize(pts, [0, 50], capi.grid_params(p))
+    assert e.value.code in (capi.E_CAPACITY, capi.E_INVALID)
+
+
+@pytest.mark.parametrize("preset", ["oxford", "c1", "indoor"])
+@pytest.mark.parametrize("metric", [capi.LOOKUP_MAHALANOBIS, capi.LOOKUP_EUCLID])
+def test_associate_matches_oracle(oracle, gpu_ctx, preset, metric):
+    p = PRESETS[preset]
+    B = 3
+    fixed, moving, poses = [], [], []
+    for b in range(B):
+        f = H.build_submap(oracle, p, 20 + b, n_scans=3)
+        pts = H.make_scan(p, 20 + b, (0.5, -0.3, 0.02), 700 + b)
+        mv = oracle.voxelize(pts, *H.vox_args(p))
+        fixed.append(f); moving.append(mv)
+        poses.append(synth.pose_to_se2(0.45 + 0.1 * b, -0.25, 0.015 * (b + 1)))
+    gp = capi.grid_params(p)
+    f_off = np.concatenate([[0], np.cumsum([len(f["cells"]) for f in fixed])]).astype(np.uint32)
+    m_off = np.concatenate([[0], np.cumsum([len(m["cells"]) for m in moving])]).astype(np.uint32)
+    fm = gpu_ctx.map_upload(np.concatenate([f["cells"] for f in fixed]), f_off, gp, npts=np.concatenate([f["npts"] for f in fixed]),
+                            slot=np.stack([f["slot"] for f in fixed]))
+    mm = gpu_ctx.map_upload(np.concatenate([m["cells"] for m in moving]), m_off, gp)
+    prob = gpu_ctx.associate(fm, mm, np.stack(poses), p.n_results_nn_lookup, metric)
+    pm, pf, seg = prob.download()
+    assert prob.n_segments == B
+    for b in range(B):
+        im, jf = oracle.associate(fixed[b]["cells"], fixed[b]["slot"], p.size_x, p.size_y, p.resolution, p.max_neighbor_linf_distance,
+                                  moving[b]["cells"], poses[b], p.n_results_nn_lookup, metric)
+        a, z = seg[b], seg[b + 1]
+        assert z - a == len(im), "pair count differs in problem %d" % b
+        assert np.array_equal(pm[a:z] - m_off[b], im)
+        assert np.array_equal(pf[a:z] - f_off[b], jf)
+        assert len(im) > 20
+    # the problem snapshots its cell tables
+    cm, cf = prob.download_cells()
+    assert np.array_equal(cm, np.concatenate([m["cells"] for m in moving]))
+
+
+def test_slot_table_rebuild_matches_insert_order(oracle, gpu_ctx):
+    p = P.OXFORD
+    v = oracle.voxelize(H.make_scan(p, 9, (0, 0, 0), 9), *H.vox_args(p))
+    m = gpu_ctx.map_upload(v["cells"], [0, len(v["cells"])], capi.grid_params(p))   # slot=None -> rebuilt on device
+    assert np.array_equal(m.download()["slot"][0], v["slot"])
+
+
+def test_transform_and_merge_match_oracle(oracle, gpu_ctx):
+    p = P.OXFORD
+    gp = capi.grid_params(p)
+    B = 2
+    subs = [dict(cells=np.zeros((0, 12), np.float32), npts=np.zeros(0, np.uint32), slot=np.full(p.size_x * p.size_y, -1, np.int32)) for _ in range(B)]
+    gm = gpu_ctx.map_upload(np.zeros((0, 12), np.float32), np.zeros(B + 1, np.uint32), gp)
+    for step in range(4):
+        scans, trans = [], []
+        for b in range(B):
+            pose = (0.5 * step, 0.1 * b * step, 0.01 * step)
+            scans.append(H.make_scan(p, 30 + b, pose, 40 + 10 * b + step))
+            trans.append([math.cos(pose[2]), math.sin(pose[2]), pose[0], pose[1]])
+        off = np.concatenate([[0], np.cumsum([len(s) for s in scans])]).astype(np.uint32)
+        mv = gpu_ctx.voxelize(np.concatenate(scans), off, gp)
+        mv.transform(np.array(trans, np.float32))
+        dmv = mv.download()
+        gm.merge(mv)
+        d = gm.download()
+        for b in range(B):
+            v = oracle.voxelize(scans[b], *H.vox_args(p))
+            t = np.array(trans[b], np.float32)
+            mc = oracle.transform_cells(v["cells"], *t)
+            a, z = dmv["cell_off"][b], dmv["cell_off"][b + 1]
+            assert np.array_equal(dmv["cells"][a:z].view(np.uint32), mc.view(np.uint32)), "transformCell differs"
+            c, n, s = oracle.merge_map_cell(subs[b]["cells"], subs[b]["npts"], subs[b]["slot"], p.size_x, p.size_y, p.resolution, mc, v["npts"])
+            subs[b] = dict(cells=c, npts=n, slot=s)
+            a, z = d["cell_off"][b], d["cell_off"][b + 1]
+            assert z - a == len(c)
+            assert np.array_equal(d["npts"][a:z], n)
+            assert np.array_equal(d["slot"][b], s)
+            assert np.array_equal(d["cells"][a:z].view(np.uint32), c.view(np.uint32)), "mergeMapCell differs at step %d" % step
+    assert len(subs[0]["cells"]) > 150
