@@ -532,7 +532,10 @@ inline int variant_num_params(int variant) { return (variant == VAR_SE2_INTENSIT
 
 // What ceres::AutoDiffCostFunction<F,1,...>::Evaluate returns for one residual block:
 // residual value and the 1 x n_params row (ambient parameters).  Autodiff = Jet path.
+inline double eval_pair_value(int variant, const double* params, const Cell12& m, const Cell12& f);
 inline void eval_pair_autodiff(int variant, const double* params, const Cell12& m, const Cell12& f, double* r, double* J) {
+  // ceres::AutoDiffCostFunction::Evaluate calls the functor with plain doubles when no Jacobian is requested
+  if (!J) { *r = eval_pair_value(variant, params, m, f); return; }
   const PairConst3 k(m, f);
   if (variant == VAR_SE2_INTENSITY || variant == VAR_SE2_XY) {
     Jet<4> p[4];

@@ -17,12 +17,32 @@ LOSS_NONE, LOSS_BARRON, LOSS_WELSCH = 0, 1, 2
 LOOKUP_MAHALANOBIS, LOOKUP_EUCLID = 0, 1
 
 
+def _host_sig():
+    """-march=native ties the binary to the CPU it was built on; rebuild when the snapshot lands on another host."""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    import zlib; return "%08x" % zlib.crc32(line.strip().encode())
+    except OSError:
+        pass
+    return "unknown"
+
+
 def build(force=False):
     """Compile the C++ restatement (g++, seconds).  Safe to call repeatedly."""
     srcs = [os.path.join(_HERE, f) for f in ("oracle_capi.cpp", "ndt_oracle.h", "lm_oracle.h", "jet.h", "Makefile")]
-    if (not force) and os.path.exists(_LIB_PATH) and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in srcs):
+    sig_path = os.path.join(_HERE, "_build", "host_sig.txt")
+    sig = _host_sig()
+    try:
+        same_host = open(sig_path).read() == sig
+    except OSError:
+        same_host = False
+    if (not force) and same_host and os.path.exists(_LIB_PATH) and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in srcs):
         return _LIB_PATH
-    subprocess.run(["make", "-C", _HERE, "-s"], check=True)
+    subprocess.run(["make", "-C", _HERE, "-s", "-B"], check=True)
+    with open(sig_path, "w") as f:
+        f.write(sig)
     return _LIB_PATH
 
 

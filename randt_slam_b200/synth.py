@@ -13,7 +13,7 @@ import numpy as np
 
 
 class Scene:
-    def __init__(self, seed, half_width, n_walls=60, n_reflectors=80, wall_len=(0.08, 0.45)):
+    def __init__(self, seed, half_width, n_walls=60, n_reflectors=80, wall_len=(0.08, 0.45), boundary=0.85):
         rng = np.random.default_rng(seed)
         hw = half_width
         c = rng.uniform(-hw, hw, size=(n_walls, 2))
@@ -27,6 +27,14 @@ class Scene:
         r = 0.004 * hw
         self.a = np.concatenate([self.a, refl - [r, 0]], 0)
         self.b = np.concatenate([self.b, refl + [r, 0]], 0)
+        if boundary:
+            # a jagged closed outline (street canyon / room) so that most beams return something
+            k = 24
+            ang = np.sort(rng.uniform(0, 2 * math.pi, k))
+            rad = boundary * hw * rng.uniform(0.55, 1.0, k)
+            v = np.stack([rad * np.cos(ang), rad * np.sin(ang)], 1)
+            self.a = np.concatenate([self.a, v], 0)
+            self.b = np.concatenate([self.b, np.roll(v, -1, 0)], 0)
         self.half_width = hw
 
 

@@ -143,4 +143,4 @@ def test_transform_and_merge_match_oracle(oracle, gpu_ctx):
             assert np.array_equal(d["npts"][a:z], n)
             assert np.array_equal(d["slot"][b], s)
             assert np.array_equal(d["cells"][a:z].view(np.uint32), c.view(np.uint32)), "mergeMapCell differs at step %d" % step
-    assert len(subs[0]["cells"]) > 150
+    assert len(subs[0]["cells"]) > 60

@@ -165,6 +165,6 @@ def test_invalid_arguments(gpu_ctx):
         gpu_ctx.problem_create(cm, cm, [0], [0], [0, 2])        # seg_off does not span the pairs
     prob = gpu_ctx.problem_create(cm, cm, [0], [0], [0, 1])
     with pytest.raises(capi.RandtError):
-        prob.eval_emit(np.zeros(4), variant=7)
+        prob.eval_emit(np.zeros(3), variant=7)
     with pytest.raises(capi.RandtError):
         prob.eval_fused(np.array([1.0, 0, 0, 0]), capi.make_loss(capi.LOSS_BARRON, scale=-1.0))
