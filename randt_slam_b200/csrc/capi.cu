@@ -93,11 +93,15 @@ void free_problem(randt_problem* p) {
 int finish_problem(randt_ctx* ctx, randt_problem* p) {
   std::vector<Tile> tiles;
   std::vector<uint32_t> first(p->S + 1, 0);
+  // one warp owns a tile.  Big batches: tiles of up to kTilePairs pairs (a whole ~200-pair registration per warp, no partials);
+  // small problems: shorter tiles so that the pairs still spread over the SMs (each extra tile costs one partial record).
+  uint32_t tile_pairs = (p->P / (uint32_t)(kSmCount * 4) + 31u) / 32u * 32u;
+  tile_pairs = std::max<uint32_t>(kMinTilePairs, std::min<uint32_t>(tile_pairs, kTilePairs));
   for (uint32_t s = 0; s < p->S; ++s) {
     first[s] = (uint32_t)tiles.size();
     uint32_t part = 0;
-    for (uint32_t b = p->h_seg_off[s]; b < p->h_seg_off[s + 1]; b += kTilePairs) {
-      Tile t; t.seg = s; t.begin = b; t.end = std::min(p->h_seg_off[s + 1], b + (uint32_t)kTilePairs); t.part = part++;
+    for (uint32_t b = p->h_seg_off[s]; b < p->h_seg_off[s + 1]; b += tile_pairs) {
+      Tile t; t.seg = s; t.begin = b; t.end = std::min(p->h_seg_off[s + 1], b + tile_pairs); t.part = part++;
       tiles.push_back(t);
     }
   }

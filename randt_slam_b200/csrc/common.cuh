@@ -36,7 +36,8 @@ struct DeviceProblem {
   uint32_t* seg_counters;  // [S] zero between launches
 };
 
-constexpr int kTilePairs = 512;   // pairs per tile
+constexpr int kTilePairs = 512;   // most pairs per tile (one warp owns a tile)
+constexpr int kMinTilePairs = 64; // tile length for small problems
 constexpr int kK3Threads = 128;   // threads per CTA in the pair-evaluation kernels
 constexpr int kMaxAcc = 20;       // accumulators per tile partial (<= 10 H + 4 g + cost + max + sumsq + nonfinite)
 

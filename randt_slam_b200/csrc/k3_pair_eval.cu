@@ -7,16 +7,23 @@
 // followed by the robust-loss Corrector (BarronLoss, R/src/ndt_registration/ceres_loss_functions.cpp:19-39, inside
 // ceres::ScaledLoss, R/src/ndt_registration/ndt_matcher.cpp:392) and ceres' accumulation of J^T J / J^T r.
 //
-// The reference differentiates with 4-wide dual numbers; this kernel evaluates the closed form
-//   r = sqrt(d^T B^-1 d),  d = R mu_m + t - mu_f,  B = R S_m R^T + S_f,
-//   dr = [ (q+p)^T dd - p^T dB q ] / (2 r),   q = B^-1 d,  p = B^-T d     (B is not assumed symmetric: the reference's
-// regularised covariances are asymmetric at float-ulp level, R/src/ndt_representation/ndt_cell.cpp:110)
-// in fp64 registers: inputs are float32-born but cond(B) reaches ~1e5, so fp32 cannot hold the 1e-5 parity bound.
+// Math.  The reference differentiates r = sqrt(d^T B^-1 d), d = R mu_m + t - mu_f, B = R S_m R^T + S_f with 4-wide dual
+// numbers.  This kernel evaluates the closed form in fp64 registers (inputs are float32-born but cond(B) reaches ~1e5, so
+// fp32 cannot hold the 1e-5 parity bound).  Only the symmetric part of B enters d^T B^-1 d and its derivative up to
+// O((eps*cond)^2) (the reference's regularised covariances are asymmetric at float-ulp level, ndt_cell.cpp:110; the first-
+// order term of the antisymmetric part cancels in the quadratic form), so B is symmetrised on load and the kernel works with
+//   q = B^-1 d (symmetric cofactor inverse),  dd = d.q,  N = r dr/dp = (1/2) d(dd)/dp :
+//   N_x = q0, N_y = q1, N_theta = q1 (xr - (Mq)0) - q0 (yr - (Mq)1),  M = R S_m R^T, (xr, yr) = R mu_m.
+// FUSED mode never forms r or J: with w = weight*rho'(dd), H += (w/dd) N N^T, g += w N, cost += weight*rho(dd)/2, and for
+// the shipped alpha = -2 loss w/dd and rho come from ONE reciprocal.  fp64 pipe: ~110 instructions per pair (was 193).
 //
-// Work decomposition: the frozen pair list is cut into tiles of <= 512 pairs that never straddle a segment (= pose).
-// One 128-thread CTA per tile; threads stride the tile (coalesced uint2 pair loads, 3 x float4 gathers per cell, the
-// k pairs of one moving cell sit in adjacent lanes).  FUSED mode keeps 13/18 fp64 accumulators per thread, reduces
-// them through shared memory in a fixed order (deterministic), and the last CTA of a segment folds the tile partials.
+// Work decomposition (B200: 148 SMs, fp64 64 lanes/clk/SM — the co-limiter next to HBM).  The frozen pair list is cut into
+// tiles that never straddle a segment (= pose); ONE WARP owns a tile: lanes stride the tile's pairs (coalesced uint2 pair
+// loads, 3 x float4 gathers per cell), partial sums stay in registers, a butterfly (transposing) shuffle reduction folds
+// them in a fixed order (deterministic), lane 0 writes the 24-double record.  No shared memory, no block barrier.  Each warp
+// walks its tiles as one software-pipelined stream of 32-pair chunks — pair indices are fetched two chunks ahead, the
+// cell gathers and the next tile's pose one chunk ahead — so HBM latency overlaps the fp64 work of the current chunk.
+// Segments longer than one tile are folded by the last warp to finish (ticket counter), in tile order.
 #include <math.h>
 
 #include "common.cuh"
@@ -27,102 +34,45 @@ namespace {
 
 enum { L_NONE = 0, L_BARRON = 1, L_WELSCH = 2, L_BARRON_M2 = 3, L_BARRON_M1 = 4 };
 
-struct SegConst {   // per-tile constants, computed by one thread, broadcast through shared memory
-  double c, s, tx, ty;      // rotation entries actually used by the variant (normalised for 0/2/3, raw for 1)
-  double ja, jb;            // variant 0: dtheta/dc, dtheta/ds
-  // loss
-  double lb, lc, pre, ts, e, weight;
+constexpr unsigned kFull = 0xffffffffu;
+
+struct PoseConst {
+  double c, s, tx, ty;     // rotation entries used by the variant (normalised for 0/2/3, raw for 1)
+  double cc, ss, cs, hd;   // c^2, s^2, c*s, (c^2 - s^2)/2
+  double ch, sh;           // c/2, s/2
+  double n2;               // c^2 + s^2 (1 unless variant 1)
+  double ja, jb;           // variant 0: dtheta/dc, dtheta/ds
 };
 
-__device__ __forceinline__ void load_cell(const float4* __restrict__ tab, uint32_t idx, double mu[3], double cov[9]) {
-  const float4 a = __ldg(tab + 3 * (size_t)idx), b = __ldg(tab + 3 * (size_t)idx + 1), c = __ldg(tab + 3 * (size_t)idx + 2);
-  mu[0] = a.x; mu[1] = a.y; mu[2] = a.z;
-  cov[0] = a.w; cov[1] = b.x; cov[2] = b.y; cov[3] = b.z; cov[4] = b.w; cov[5] = c.x; cov[6] = c.y; cov[7] = c.z; cov[8] = c.w;
-}
+struct LossConst {
+  double lb, lc, pre, ts, e, weight;
+  double preW;             // pre * weight / 2      (Barron)
+  double K;                // pre * e * ts * weight (Barron: weight * rho' = K * u^(e-1))
+};
 
-// ---- 3-D core (x, y, intensity); rotation about the intensity axis --------------------------------------------
-// returns dd = d^T B^-1 d; if WANT_JAC: un-normalised derivative numerators (multiply by 1/(2r)): nt (theta), nx, ny
-template <bool WANT_JAC>
-__device__ __forceinline__ double core3(double ct, double st, double tx, double ty, const double mm[3], const double S[9],
-                                        const double fm[3], const double F[9], double& nt, double& nx, double& ny) {
-  const double xr = ct * mm[0] - st * mm[1];
-  const double yr = st * mm[0] + ct * mm[1];
-  const double d0 = xr + tx - fm[0], d1 = yr + ty - fm[1], d2 = mm[2] - fm[2];
-  const double T00 = ct * S[0] - st * S[3], T01 = ct * S[1] - st * S[4];
-  const double T10 = st * S[0] + ct * S[3], T11 = st * S[1] + ct * S[4];
-  const double M00 = T00 * ct - T01 * st, M01 = T00 * st + T01 * ct;
-  const double M10 = T10 * ct - T11 * st, M11 = T10 * st + T11 * ct;
-  const double M02 = ct * S[2] - st * S[5], M12 = st * S[2] + ct * S[5];
-  const double M20 = S[6] * ct - S[7] * st, M21 = S[6] * st + S[7] * ct, M22 = S[8];
-  const double B00 = M00 + F[0], B01 = M01 + F[1], B02 = M02 + F[2];
-  const double B10 = M10 + F[3], B11 = M11 + F[4], B12 = M12 + F[5];
-  const double B20 = M20 + F[6], B21 = M21 + F[7], B22 = M22 + F[8];
-  const double C00 = B11 * B22 - B12 * B21, C01 = B12 * B20 - B10 * B22, C02 = B10 * B21 - B11 * B20;
-  const double C10 = B21 * B02 - B22 * B01, C11 = B22 * B00 - B20 * B02, C12 = B20 * B01 - B21 * B00;
-  const double C20 = B01 * B12 - B02 * B11, C21 = B02 * B10 - B00 * B12, C22 = B00 * B11 - B01 * B10;
-  const double det = C00 * B00 + C10 * B10 + C20 * B20;
-  const double idet = 1.0 / det;
-  // q = B^-1 d : inv[i][j] = C[j][i] / det ;  p = B^-T d
-  const double q0 = (C00 * d0 + C10 * d1 + C20 * d2) * idet;
-  const double q1 = (C01 * d0 + C11 * d1 + C21 * d2) * idet;
-  const double q2 = (C02 * d0 + C12 * d1 + C22 * d2) * idet;
-  const double dd = d0 * q0 + d1 * q1 + d2 * q2;
-  if (WANT_JAC) {
-    const double p0 = (C00 * d0 + C01 * d1 + C02 * d2) * idet;
-    const double p1 = (C10 * d0 + C11 * d1 + C12 * d2) * idet;
-    const double p2 = (C20 * d0 + C21 * d1 + C22 * d2) * idet;
-    const double u0 = q0 + p0, u1 = q1 + p1;
-    const double Mq0 = M00 * q0 + M01 * q1 + M02 * q2, Mq1 = M10 * q0 + M11 * q1 + M12 * q2;
-    const double Mtp0 = M00 * p0 + M10 * p1 + M20 * p2, Mtp1 = M01 * p0 + M11 * p1 + M21 * p2;
-    const double pSMq = (p1 * Mq0 - p0 * Mq1) + (Mtp0 * q1 - Mtp1 * q0);
-    nt = u1 * xr - u0 * yr - pSMq;
-    nx = u0; ny = u1;
-  }
-  return dd;
-}
+struct RawCell { float4 a, b, c; };   // mean (x, y, i) + row-major 3x3 covariance, as stored (12 floats)
 
-// ---- 2-D core (x, y) ---------------------------------------------------------------------------------------------
-// RAW = true : R = [c -s; s c] with the stored, un-normalised complex (Sophus SE2 * point / rotationMatrix()); derivative
-//              numerators w.r.t. c and s are independent (nc, ns).
-// RAW = false: proper rotation by theta; nc carries the theta numerator.
-template <bool WANT_JAC, bool RAW>
-__device__ __forceinline__ double core2(double c, double s, double tx, double ty, const double mm[3], const double S[9],
-                                        const double fm[3], const double F[9], double& nc, double& ns, double& nx, double& ny) {
-  const double xr = c * mm[0] - s * mm[1];
-  const double yr = s * mm[0] + c * mm[1];
-  const double d0 = xr + tx - fm[0], d1 = yr + ty - fm[1];
-  const double T00 = c * S[0] - s * S[3], T01 = c * S[1] - s * S[4];
-  const double T10 = s * S[0] + c * S[3], T11 = s * S[1] + c * S[4];
-  const double M00 = T00 * c - T01 * s, M01 = T00 * s + T01 * c;
-  const double M10 = T10 * c - T11 * s, M11 = T10 * s + T11 * c;
-  const double B00 = M00 + F[0], B01 = M01 + F[1], B10 = M10 + F[3], B11 = M11 + F[4];
-  const double det = B00 * B11 - B10 * B01;
-  const double idet = 1.0 / det;
-  const double q0 = (B11 * d0 - B01 * d1) * idet, q1 = (-B10 * d0 + B00 * d1) * idet;
-  const double dd = d0 * q0 + d1 * q1;
-  if (WANT_JAC) {
-    const double p0 = (B11 * d0 - B10 * d1) * idet, p1 = (-B01 * d0 + B00 * d1) * idet;
-    const double u0 = q0 + p0, u1 = q1 + p1;
-    nx = u0; ny = u1;
-    if (RAW) {
-      // dB/dc = K + T,  K = A R^T ;  dB/ds = S2 K + T S2^T
-      const double K00 = S[0] * c - S[1] * s, K01 = S[0] * s + S[1] * c;
-      const double K10 = S[3] * c - S[4] * s, K11 = S[3] * s + S[4] * c;
-      const double Dc00 = K00 + T00, Dc01 = K01 + T01, Dc10 = K10 + T10, Dc11 = K11 + T11;
-      const double Ds00 = -K10 - T01, Ds01 = -K11 + T00, Ds10 = K00 - T11, Ds11 = K01 + T10;
-      const double pDcq = p0 * (Dc00 * q0 + Dc01 * q1) + p1 * (Dc10 * q0 + Dc11 * q1);
-      const double pDsq = p0 * (Ds00 * q0 + Ds01 * q1) + p1 * (Ds10 * q0 + Ds11 * q1);
-      nc = u0 * mm[0] + u1 * mm[1] - pDcq;
-      ns = -u0 * mm[1] + u1 * mm[0] - pDsq;
-    } else {
-      const double Mq0 = M00 * q0 + M01 * q1, Mq1 = M10 * q0 + M11 * q1;
-      const double Mtp0 = M00 * p0 + M10 * p1, Mtp1 = M01 * p0 + M11 * p1;
-      const double pSMq = (p1 * Mq0 - p0 * Mq1) + (Mtp0 * q1 - Mtp1 * q0);
-      nc = u1 * xr - u0 * yr - pSMq;
-      ns = 0.0;
-    }
-  }
-  return dd;
+// 1/x for a normal, finite, non-zero x: MUFU.RCP64H seed (2^-23) + two Newton steps.  No slow path: callers guarantee or
+// tolerate garbage-in-garbage-out (degenerate pairs are caught by the validity test on dd).
+__device__ __forceinline__ double rcp_fast(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  return y;
+}
+// 1/sqrt(x), x normal and positive: MUFU.RSQ64H seed + two Newton steps
+__device__ __forceinline__ double rsqrt_fast(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double hx = 0.5 * x;
+  double e = fma(-hx * y, y, 0.5);
+  y = fma(y, e, y);
+  e = fma(-hx * y, y, 0.5);
+  y = fma(y, e, y);
+  return y;
 }
 
 template <int VARIANT> struct VarTraits;
@@ -131,300 +81,572 @@ template <> struct VarTraits<1> { static constexpr int NB = 4, NP = 4; };  // ba
 template <> struct VarTraits<2> { static constexpr int NB = 3, NP = 3; };  // basis (x, y, theta)
 template <> struct VarTraits<3> { static constexpr int NB = 3, NP = 3; };
 
-// residual + basis Jacobian for one pair.  Returns false when the pair is degenerate (non-finite or negative dd).
+// ---- per-pair core ------------------------------------------------------------------------------------------------
+// dd = d^T B^-1 d and (WANT_JAC) the basis numerators N[] = r * dr/d(basis), in the basis order of VarTraits.
 template <int VARIANT, bool WANT_JAC>
-__device__ __forceinline__ bool eval_pair(const SegConst& k, const float4* __restrict__ cm, const float4* __restrict__ cf, uint2 pr,
-                                          double& r, double& dd, double* jb) {
-  double mm[3], S[9], fm[3], F[9];
-  load_cell(cm, pr.x, mm, S);
-  load_cell(cf, pr.y, fm, F);
-  double n0 = 0, n1 = 0, n2 = 0, n3 = 0;
-  if (VARIANT == 0 || VARIANT == 2) dd = core3<WANT_JAC>(k.c, k.s, k.tx, k.ty, mm, S, fm, F, n0, n1, n2);
-  else if (VARIANT == 1) dd = core2<WANT_JAC, true>(k.c, k.s, k.tx, k.ty, mm, S, fm, F, n0, n1, n2, n3);
-  else dd = core2<WANT_JAC, false>(k.c, k.s, k.tx, k.ty, mm, S, fm, F, n0, n1, n2, n3);
-  const bool ok = (dd >= 0.0) && (dd < 1.0e300);   // false for NaN, inf, negative
-  if (!ok) { r = 0.0; dd = 0.0; if (WANT_JAC) { for (int i = 0; i < VarTraits<VARIANT>::NB; ++i) jb[i] = 0.0; } return false; }
-  if (dd == 0.0) {  // r = 0: the reference's dual-number sqrt yields 0/0 here; defined as J = 0
-    r = 0.0;
-    if (WANT_JAC) for (int i = 0; i < VarTraits<VARIANT>::NB; ++i) jb[i] = 0.0;
-    return true;
+__device__ __forceinline__ double pair_core(const PoseConst& k, const RawCell& m, const RawCell& f, double* __restrict__ N) {
+  const double mx = m.a.x, my = m.a.y;
+  const double S00 = m.a.w, S11 = m.b.w;
+  const double b2 = (double)m.b.x + (double)m.b.z;              // 2 * sym(S01)
+  // rotated moving covariance (symmetric): M = R S R^T
+  const double M00 = fma(k.cc, S00, fma(k.ss, S11, -k.cs * b2));
+  const double M11 = fma(k.n2, S00 + S11, -M00);
+  const double M01 = fma(k.cs, S00 - S11, k.hd * b2);
+  const double xr = fma(k.c, mx, -k.s * my);
+  const double yr = fma(k.s, mx, k.c * my);
+  const double d0 = (xr + k.tx) - (double)f.a.x;
+  const double d1 = (yr + k.ty) - (double)f.a.y;
+  const double B00 = M00 + (double)f.a.w;
+  const double B11 = M11 + (double)f.b.w;
+  const double B01 = fma(0.5, (double)f.b.x + (double)f.b.z, M01);
+  double q0, q1, q2 = 0.0, dd, M02 = 0.0, M12 = 0.0;
+  if (VARIANT == 0 || VARIANT == 2) {
+    const double e2 = (double)m.b.y + (double)m.c.y;            // 2 * sym(S02)
+    const double f2 = (double)m.c.x + (double)m.c.z;            // 2 * sym(S12)
+    M02 = fma(k.ch, e2, -k.sh * f2);
+    M12 = fma(k.sh, e2, k.ch * f2);
+    const double d2 = (double)m.a.z - (double)f.a.z;
+    const double B22 = (double)m.c.w + (double)f.c.w;
+    const double B02 = fma(0.5, (double)f.b.y + (double)f.c.y, M02);
+    const double B12 = fma(0.5, (double)f.c.x + (double)f.c.z, M12);
+    const double C00 = fma(B11, B22, -B12 * B12);
+    const double C01 = fma(B02, B12, -B01 * B22);
+    const double C02 = fma(B01, B12, -B02 * B11);
+    const double C11 = fma(B00, B22, -B02 * B02);
+    const double C12 = fma(B01, B02, -B00 * B12);
+    const double C22 = fma(B00, B11, -B01 * B01);
+    const double det = fma(B00, C00, fma(B01, C01, B02 * C02));
+    const double idet = rcp_fast(det);
+    q0 = fma(C00, d0, fma(C01, d1, C02 * d2)) * idet;
+    q1 = fma(C01, d0, fma(C11, d1, C12 * d2)) * idet;
+    q2 = fma(C02, d0, fma(C12, d1, C22 * d2)) * idet;
+    dd = fma(d0, q0, fma(d1, q1, d2 * q2));
+  } else {
+    const double det = fma(B00, B11, -B01 * B01);
+    const double idet = rcp_fast(det);
+    q0 = fma(B11, d0, -B01 * d1) * idet;
+    q1 = fma(B00, d1, -B01 * d0) * idet;
+    dd = fma(d0, q0, d1 * q1);
   }
-  const double rs = rsqrt(dd);
-  r = dd * rs;
   if (WANT_JAC) {
-    const double h = 0.5 * rs;
-    if (VARIANT == 0) { jb[0] = n0 * h; jb[1] = n1 * h; jb[2] = n2 * h; }                 // (theta, x, y)
-    else if (VARIANT == 2) { jb[0] = n1 * h; jb[1] = n2 * h; jb[2] = n0 * h; }            // (x, y, theta)
-    else if (VARIANT == 1) { jb[0] = n0 * h; jb[1] = n1 * h; jb[2] = n2 * h; jb[3] = n3 * h; }  // (c, s, x, y)
-    else { jb[0] = n2 * h; jb[1] = n3 * h; jb[2] = n0 * h; }                              // (x, y, theta)
-  }
-  return true;
-}
-
-// ---- loss: rho(s) and rho'(s), both already multiplied by the ScaledLoss weight -------------------------------
-template <int LOSS>
-__device__ __forceinline__ void loss_eval(double s, const SegConst& k, double& rho, double& rho1) {
-  if (LOSS == L_NONE) { rho = s * k.weight; rho1 = k.weight; }
-  else if (LOSS == L_WELSCH) {
-    const double ex = exp(s * k.lc);           // lc = -1/b
-    rho = k.lb * (1.0 - ex) * k.weight; rho1 = ex * k.weight;
-  } else if (LOSS == L_BARRON_M2) {            // alpha = -2  -> exponent -1
-    const double inv = 1.0 / (s * k.ts + 1.0);
-    rho = k.pre * (inv - 1.0) * k.weight;
-    rho1 = k.pre * k.e * (inv * inv) * k.ts * k.weight;
-  } else if (LOSS == L_BARRON_M1) {            // alpha = -1  -> exponent -1/2
-    const double rs = rsqrt(s * k.ts + 1.0);
-    rho = k.pre * (rs - 1.0) * k.weight;
-    rho1 = k.pre * k.e * (rs * rs * rs) * k.ts * k.weight;
-  } else {                                     // generic Barron, same branches as BarronLoss::Evaluate
-    const double alpha = 2.0 * k.e;
-    if (alpha >= 2.0) { rho = s * k.weight; rho1 = k.weight; }
-    else if (fabs(alpha) <= 0.05) {
-      const double sum = 1.0 + s * k.lc, inv = 1.0 / sum;
-      rho = k.lb * log(sum) * k.weight;
-      rho1 = fmax(2.2250738585072014e-308, inv) * k.weight;
+    if (VARIANT == 1) {
+      // R = [c -s; s c] un-normalised, c and s independent parameters:
+      //   N_c = q.(mx, my) - g^T S q,   N_s = q.(-my, mx) - (q1 (S g)0 - q0 (S g)1),   g = R^T q
+      const double bh = 0.5 * b2;
+      const double g0 = fma(k.c, q0, k.s * q1), g1 = fma(k.c, q1, -k.s * q0);
+      const double Sq0 = fma(S00, q0, bh * q1), Sq1 = fma(bh, q0, S11 * q1);
+      const double Sg0 = fma(S00, g0, bh * g1), Sg1 = fma(bh, g0, S11 * g1);
+      N[0] = fma(q0, mx, q1 * my) - fma(g0, Sq0, g1 * Sq1);
+      N[1] = fma(q1, mx, -q0 * my) - fma(q1, Sg0, -q0 * Sg1);
+      N[2] = q0; N[3] = q1;
     } else {
-      const double to_exp = s * k.ts + 1.0;
-      const double p1 = pow(to_exp, k.e - 1.0);
-      rho = k.pre * (p1 * to_exp - 1.0) * k.weight;
-      rho1 = k.pre * k.e * p1 * k.ts * k.weight;
+      const double a0 = xr - fma(M00, q0, fma(M01, q1, M02 * q2));
+      const double a1 = yr - fma(M01, q0, fma(M11, q1, M12 * q2));
+      const double nt = fma(q1, a0, -q0 * a1);
+      if (VARIANT == 0) { N[0] = nt; N[1] = q0; N[2] = q1; }      // (theta, x, y)
+      else              { N[0] = q0; N[1] = q1; N[2] = nt; }      // (x, y, theta)
     }
   }
+  return dd;
+}
+
+__device__ __forceinline__ bool dd_valid(double dd) { return (dd >= 0.0) && (dd < 1.0e300); }   // false for NaN, inf, negative
+
+// ---- loss: w = weight*rho'(s), hrho = weight*rho(s)/2, wd = w/s (finite garbage when s == 0: it only multiplies N = 0) ----
+template <int LOSS>
+__device__ __forceinline__ void loss_eval(double s, const LossConst& k, double& w, double& hrho, double& wd) {
+  const bool pos = s > 0.0;
+  if (LOSS == L_BARRON_M2) {                    // alpha = -2: rho = pre (1/u - 1), rho' = pre e ts / u^2, u = s ts + 1
+    const double u = fma(s, k.ts, 1.0);
+    const double v = (u * u) * s;
+    const double iv = rcp_fast(pos ? v : 1.0);  // 1 / (u^2 s)
+    wd = k.K * iv;
+    w = wd * s;
+    const double iu = pos ? (iv * s) * u : 1.0;
+    hrho = fma(k.preW, iu, -k.preW);
+    return;
+  }
+  if (LOSS == L_NONE) { w = k.weight; hrho = 0.5 * k.weight * s; }
+  else if (LOSS == L_WELSCH) {
+    const double ex = exp(s * k.lc);            // lc = -1/b
+    hrho = 0.5 * k.lb * (1.0 - ex) * k.weight; w = ex * k.weight;
+  } else if (LOSS == L_BARRON_M1) {             // alpha = -1  -> exponent -1/2
+    const double rs = rsqrt_fast(fma(s, k.ts, 1.0));
+    hrho = fma(k.preW, rs, -k.preW);
+    w = k.K * (rs * rs * rs);
+  } else {                                      // generic Barron, same branches as BarronLoss::Evaluate
+    const double alpha = 2.0 * k.e;
+    if (alpha >= 2.0) { w = k.weight; hrho = 0.5 * k.weight * s; }
+    else if (fabs(alpha) <= 0.05) {
+      const double sum = 1.0 + s * k.lc, inv = 1.0 / sum;
+      hrho = 0.5 * k.lb * log(sum) * k.weight;
+      w = fmax(2.2250738585072014e-308, inv) * k.weight;
+    } else {
+      const double to_exp = fma(s, k.ts, 1.0);
+      const double p1 = pow(to_exp, k.e - 1.0);
+      hrho = k.preW * (p1 * to_exp - 1.0);
+      w = k.K * p1;
+    }
+  }
+  wd = w * rcp_fast(pos ? s : 1.0);
 }
 
 template <int VARIANT>
-__device__ __forceinline__ void make_pose_const(const double* __restrict__ pose, SegConst& k) {
+__device__ __forceinline__ void make_pose_const(const double* __restrict__ pose, PoseConst& k) {
+  k.n2 = 1.0; k.ja = 0.0; k.jb = 0.0;
   if (VARIANT == 0) {
     const double c = pose[0], s = pose[1];
     const double n2 = c * c + s * s, n = sqrt(n2);
     k.c = c / n; k.s = s / n; k.tx = pose[2]; k.ty = pose[3];
     k.ja = -s / n2; k.jb = c / n2;
   } else if (VARIANT == 1) {
-    k.c = pose[0]; k.s = pose[1]; k.tx = pose[2]; k.ty = pose[3]; k.ja = 0; k.jb = 0;
+    k.c = pose[0]; k.s = pose[1]; k.tx = pose[2]; k.ty = pose[3];
+    k.n2 = k.c * k.c + k.s * k.s;
   } else {
     // NormalizeAngle (R/include/ndt_registration/state_manifold.h:17-23) then cos/sin
     const double two_pi = 2.0 * 3.14159265358979323846;
     const double th = pose[2] - two_pi * floor((pose[2] + 3.14159265358979323846) / two_pi);
     double sn, cs;
     sincos(th, &sn, &cs);
-    k.c = cs; k.s = sn; k.tx = pose[0]; k.ty = pose[1]; k.ja = 0; k.jb = 0;
+    k.c = cs; k.s = sn; k.tx = pose[0]; k.ty = pose[1];
   }
+  k.cc = k.c * k.c; k.ss = k.s * k.s; k.cs = k.c * k.s; k.hd = 0.5 * (k.cc - k.ss);
+  k.ch = 0.5 * k.c; k.sh = 0.5 * k.s;
 }
 
-__device__ __forceinline__ void make_loss_const(const LossParams& lp, double mu, SegConst& k) {
+__device__ __forceinline__ void make_loss_const(const LossParams& lp, double mu, LossConst& k) {
   k.weight = lp.weight;
   const double b = mu * lp.a2;
-  k.lb = b;
+  k.lb = b; k.preW = 0.0; k.K = 0.0;
   if (lp.kind == RANDT_LOSS_WELSCH) { k.lc = -1.0 / b; k.pre = 0; k.ts = 0; k.e = 0; return; }
   const double c = 1.0 / b, factor = fabs(lp.alpha - 2.0);
   k.lc = c; k.e = 0.5 * lp.alpha; k.pre = b * factor / lp.alpha; k.ts = 2.0 * c / factor;
+  k.preW = 0.5 * k.pre * k.weight;
+  k.K = k.pre * k.e * k.ts * k.weight;
+}
+
+// ---- warp butterfly reduction ----------------------------------------------------------------------------------------
+// N per-lane partial sums -> every lane ends up with the 32-lane total of ONE slot; ceil(N/2) + ceil(N/4) + ... shuffles
+// instead of 5 N.  Fixed exchange pattern => bitwise reproducible.
+template <int N, int XOR>
+__device__ __forceinline__ void bfly_reduce(double* a, int lane) {
+  if constexpr (XOR >= 1) {
+    if constexpr (N > 1) {
+      constexpr int H = (N + 1) / 2;
+      const bool up = (lane & XOR) != 0;
+#pragma unroll
+      for (int i = 0; i < H; ++i) {
+        const double lo = a[i];
+        const double hi = (i + H < N) ? a[i + H] : 0.0;
+        const double send = up ? lo : hi;
+        const double keep = up ? hi : lo;
+        a[i] = keep + __shfl_xor_sync(kFull, send, XOR);
+      }
+      bfly_reduce<H, XOR / 2>(a, lane);
+    } else {
+      a[0] += __shfl_xor_sync(kFull, a[0], XOR);
+      bfly_reduce<1, XOR / 2>(a, lane);
+    }
+  }
+}
+// the lane (with bit 0 clear) that holds slot `slot` after bfly_reduce<N, 16>
+template <int N>
+__host__ __device__ constexpr int bfly_lane_of_slot(int slot) {
+  int lane = 0, n = N, s = slot;
+  for (int x = 16; x >= 2; x >>= 1) {
+    if (n > 1) {
+      const int h = (n + 1) / 2;
+      if (s >= h) { lane |= x; s -= h; }
+      n = h;
+    }
+  }
+  return lane;
+}
+// totals of all N slots in every lane
+template <int N>
+__device__ __forceinline__ void warp_sum_all(double* a, int lane) {
+  bfly_reduce<N, 16>(a, lane);
+  const double mine = a[0];
+#pragma unroll
+  for (int s = 0; s < N; ++s) a[s] = __shfl_sync(kFull, mine, bfly_lane_of_slot<N>(s));
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(kFull, v, o));
+  return v;
 }
 
 // expand the basis normal equations of one segment into the 24-double output record
+// tot: [NH upper triangle (i <= j, row-major)] [NB gradient] [cost] [sum dd]; max_dd separately
 template <int VARIANT>
-__device__ void write_segment_out(const double* __restrict__ tot, const SegConst& k, uint32_t n_pairs, double* __restrict__ out) {
+__device__ void write_segment_out(const double* __restrict__ tot, double max_dd, const PoseConst& k, uint32_t n_pairs, double* __restrict__ out) {
   constexpr int NB = VarTraits<VARIANT>::NB;
   constexpr int NH = NB * (NB + 1) / 2;
   double H[16], g[4];
+#pragma unroll
   for (int i = 0; i < 16; ++i) H[i] = 0.0;
+#pragma unroll
   for (int i = 0; i < 4; ++i) g[i] = 0.0;
-  // unpack upper triangle in (i <= j) row-major order
-  double Hb[4][4]; double gb[4];
-  int t = 0;
-  for (int i = 0; i < NB; ++i) for (int j = i; j < NB; ++j) { Hb[i][j] = tot[t]; Hb[j][i] = tot[t]; ++t; }
-  for (int i = 0; i < NB; ++i) gb[i] = tot[NH + i];
   if (VARIANT == 0) {
     // ambient (c, s, tx, ty) = E^T (theta, x, y),  E rows: theta -> (ja, jb, 0, 0), x -> (0,0,1,0), y -> (0,0,0,1)
-    const double E[3][4] = {{k.ja, k.jb, 0, 0}, {0, 0, 1, 0}, {0, 0, 0, 1}};
-    for (int a = 0; a < 4; ++a) {
-      for (int i = 0; i < 3; ++i) g[a] += E[i][a] * gb[i];
-      for (int b2 = 0; b2 < 4; ++b2) {
-        double s = 0; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) s += E[i][a] * Hb[i][j] * E[j][b2];
-        H[a * 4 + b2] = s;
-      }
-    }
+    const double Htt = tot[0], Htx = tot[1], Hty = tot[2], Hxx = tot[3], Hxy = tot[4], Hyy = tot[5];
+    H[0] = k.ja * k.ja * Htt; H[1] = k.ja * k.jb * Htt; H[2] = k.ja * Htx; H[3] = k.ja * Hty;
+    H[4] = H[1];              H[5] = k.jb * k.jb * Htt; H[6] = k.jb * Htx; H[7] = k.jb * Hty;
+    H[8] = H[2];  H[9] = H[6];  H[10] = Hxx; H[11] = Hxy;
+    H[12] = H[3]; H[13] = H[7]; H[14] = Hxy; H[15] = Hyy;
+    g[0] = k.ja * tot[NH]; g[1] = k.jb * tot[NH]; g[2] = tot[NH + 1]; g[3] = tot[NH + 2];
   } else {
-    for (int a = 0; a < NB; ++a) { g[a] = gb[a]; for (int b2 = 0; b2 < NB; ++b2) H[a * 4 + b2] = Hb[a][b2]; }
+    int t = 0;
+#pragma unroll
+    for (int i = 0; i < NB; ++i)
+#pragma unroll
+      for (int j = i; j < NB; ++j) { H[i * 4 + j] = tot[t]; H[j * 4 + i] = tot[t]; ++t; }
+#pragma unroll
+    for (int i = 0; i < NB; ++i) g[i] = tot[NH + i];
   }
-  for (int i = 0; i < 16; ++i) out[RANDT_FUSED_H + i] = H[i];
-  for (int i = 0; i < 4; ++i) out[RANDT_FUSED_G + i] = g[i];
-  out[RANDT_FUSED_COST] = tot[NH + NB + 0];
-  out[RANDT_FUSED_MAXR] = tot[NH + NB + 1];
-  out[RANDT_FUSED_SUMSQ] = tot[NH + NB + 2];
-  out[RANDT_FUSED_N] = (double)n_pairs;
+  double2* o2 = reinterpret_cast<double2*>(out);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o2[i] = make_double2(H[2 * i], H[2 * i + 1]);
+  o2[8] = make_double2(g[0], g[1]); o2[9] = make_double2(g[2], g[3]);
+  o2[10] = make_double2(tot[NH + NB], sqrt(max_dd));       // cost, max raw residual
+  o2[11] = make_double2(tot[NH + NB + 1], (double)n_pairs);  // sum raw r^2, residual blocks
+}
+
+// ---- the software-pipelined tile stream of one warp ------------------------------------------------------------------
+// Every warp walks tiles w, w + n_warps, ... as a stream of 32-pair chunks.  A chunk's inputs are staged in shared memory by
+// cp.async (LDGSTS): 6 x 16 B per lane for the two cells, plus (first chunk of a tile, lane 0) the pose and mu of the tile's
+// segment and the chunk's descriptor.  kStages chunks are in flight per warp, so registers hold nothing but the accumulators
+// while HBM latency is covered; each lane reads back only what it copied itself (no cross-lane hazard on the cell slots).
+constexpr int kWarpsPerCta = kK3Threads / 32;
+constexpr int kStages = 3;
+
+struct __align__(16) ChunkMeta { uint32_t t, i, end, seg; };   // tile index (0xffffffff: past the end), first pair, tile end, segment
+struct __align__(16) StageBuf {
+  float4 cell[6][32];      // [component][lane]: moving a, b, c, fixed a, b, c
+  double pose[4];
+  double mu;
+  uint32_t first;          // 1: first chunk of its tile (pose/mu valid)
+  uint32_t pad_;
+  ChunkMeta meta;
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+struct TileStream {   // generator (warp-uniform): tiles t0, t0 + stride, ... chunk by chunk; the following tile's descriptor is prefetched
+  const Tile* __restrict__ tiles;
+  uint32_t n_tiles, stride;
+  uint32_t t, i, end, seg, begin;
+  Tile la;            // descriptor of tile t + stride (valid when that index < n_tiles)
+  __device__ __forceinline__ void init(const Tile* tl, uint32_t n, uint32_t t0, uint32_t st) {
+    tiles = tl; n_tiles = n; stride = st;
+    t = t0; i = 0; end = 0; seg = 0; begin = 0;
+    la.seg = 0; la.begin = 0; la.end = 0; la.part = 0;
+    if (t0 < n) { const Tile c = tl[t0]; i = c.begin; begin = c.begin; end = c.end; seg = c.seg; }
+    if (t0 < n && t0 + st < n) la = tl[t0 + st];
+  }
+  __device__ __forceinline__ bool valid() const { return t < n_tiles; }
+  __device__ __forceinline__ void advance() {
+    if (t >= n_tiles) return;
+    i += 32;
+    if (i >= end) {
+      t += stride;
+      i = la.begin; begin = la.begin; end = la.end; seg = la.seg;
+      if (t < n_tiles && t + stride < n_tiles) la = tiles[t + stride];
+    }
+  }
+};
+
+// issue the asynchronous copies of the generator's current chunk into `sb` (pair index `pr` was fetched one iteration earlier)
+template <int NP>
+__device__ __forceinline__ void stage_issue(const DeviceProblem& P, const TileStream& g, uint2 pr, int lane, StageBuf* sb,
+                                            const double* __restrict__ poses, const double* __restrict__ mu_per_seg) {
+  if (g.valid()) {
+    if (g.i + lane < g.end) {
+      const float4* pm = P.cells_m + 3 * (size_t)pr.x;
+      const float4* pf = P.cells_f + 3 * (size_t)pr.y;
+      cp_async16(&sb->cell[0][lane], pm); cp_async16(&sb->cell[1][lane], pm + 1); cp_async16(&sb->cell[2][lane], pm + 2);
+      cp_async16(&sb->cell[3][lane], pf); cp_async16(&sb->cell[4][lane], pf + 1); cp_async16(&sb->cell[5][lane], pf + 2);
+    }
+    if (lane == 0) {
+      const bool first = g.i == g.begin;
+      if (first) {
+        const double* ps = poses + (size_t)g.seg * NP;
+        if (NP == 4) { cp_async16(&sb->pose[0], ps); cp_async16(&sb->pose[2], ps + 2); }
+        else { cp_async8(&sb->pose[0], ps); cp_async8(&sb->pose[1], ps + 1); cp_async8(&sb->pose[2], ps + 2); }
+        if (mu_per_seg) cp_async8(&sb->mu, mu_per_seg + g.seg);
+      }
+      sb->first = first ? 1u : 0u;
+      sb->meta.t = g.t; sb->meta.i = g.i; sb->meta.end = g.end; sb->meta.seg = g.seg;
+    }
+  } else if (lane == 0) {
+    sb->meta.t = 0xffffffffu;
+  }
+  cp_async_commit();
 }
 
 template <int VARIANT, int LOSS, bool WANT_JAC>
-__global__ void __launch_bounds__(kK3Threads) k3_fused_kernel(DeviceProblem P, const double* __restrict__ poses, LossParams lp,
-                                                             const double* __restrict__ mu_per_seg, double* __restrict__ out,
-                                                             unsigned long long* __restrict__ bad_counter) {
+__global__ void __launch_bounds__(kK3Threads, 4) k3_fused_kernel(DeviceProblem P, const double* __restrict__ poses, LossParams lp,
+                                                                const double* __restrict__ mu_per_seg, double* __restrict__ out,
+                                                                unsigned long long* __restrict__ bad_counter) {
   constexpr int NB = VarTraits<VARIANT>::NB;
   constexpr int NP = VarTraits<VARIANT>::NP;
   constexpr int NH = NB * (NB + 1) / 2;
-  constexpr int NACC = NH + NB + 4;              // H, g, cost, max_r, sum_sq, bad
-  constexpr int IDX_MAX = NH + NB + 1;
-  __shared__ SegConst kc;
-  __shared__ double red[NACC][kK3Threads];
-  __shared__ double tot[NACC];
-  __shared__ uint32_t ticket;
-  const int tid = threadIdx.x;
+  constexpr int NJ = WANT_JAC ? NH + NB : 0;     // additive slots: H, g, then cost, sum dd
+  constexpr int NS = NJ + 2;
+  __shared__ StageBuf stage_all[kWarpsPerCta][kStages];
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0);
+  const uint32_t n_warps = gridDim.x * kWarpsPerCta;
+  const uint32_t w = blockIdx.x * kWarpsPerCta + warp;
+  if (w >= P.n_tiles) return;
+  StageBuf* stage = stage_all[warp];
 
-  for (uint32_t t = blockIdx.x; t < P.n_tiles; t += gridDim.x) {
-    const Tile tile = P.tiles[t];
-    if (tid == 0) {
-      make_pose_const<VARIANT>(poses + (size_t)tile.seg * NP, kc);
-      make_loss_const(lp, mu_per_seg ? mu_per_seg[tile.seg] : lp.mu, kc);
-    }
-    __syncthreads();
-    double acc[NACC];
+  TileStream gen;
+  gen.init(P.tiles, P.n_tiles, w, n_warps);
+  // prologue: chunks 0 .. kStages-2 in flight, pair indices of chunk kStages-1 in registers
+  uint2 pr = make_uint2(0, 0);
+  if (gen.valid() && gen.i + lane < gen.end) pr = P.pairs[gen.i + lane];
 #pragma unroll
-    for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
-    for (uint32_t i = tile.begin + tid; i < tile.end; i += kK3Threads) {
-      const uint2 pr = P.pairs[i];
-      double r, dd, jb[4];
-      const bool ok = eval_pair<VARIANT, WANT_JAC>(kc, P.cells_m, P.cells_f, pr, r, dd, jb);
-      if (!ok) { acc[NACC - 1] += 1.0; continue; }
-      double rho, rho1;
-      loss_eval<LOSS>(dd, kc, rho, rho1);
-      if (WANT_JAC) {
-        int q = 0;
-#pragma unroll
-        for (int a = 0; a < NB; ++a) {
-          const double wa = rho1 * jb[a];
-#pragma unroll
-          for (int b2 = a; b2 < NB; ++b2) { acc[q] += wa * jb[b2]; ++q; }
-          acc[NH + a] += wa * r;
-        }
-      }
-      acc[NH + NB + 0] += 0.5 * rho;
-      acc[IDX_MAX] = fmax(acc[IDX_MAX], r);
-      acc[NH + NB + 2] += dd;
-    }
-    // ---- block reduction through shared memory, fixed order ----
-#pragma unroll
-    for (int i = 0; i < NACC; ++i) red[i][tid] = acc[i];
-    __syncthreads();
-    if (tid < NACC * 4) {
-      // 4 lanes per quantity (NACC*4 <= 72 <= 128): each sums 32 strided entries, then 2 shuffle steps
-      const int qn = tid >> 2, j = tid & 3;
-      double v = red[qn][j];
-      if (qn == IDX_MAX) { for (int e = j + 4; e < kK3Threads; e += 4) v = fmax(v, red[qn][e]); }
-      else               { for (int e = j + 4; e < kK3Threads; e += 4) v += red[qn][e]; }
-      const unsigned mask = __activemask();
-      double o = __shfl_xor_sync(mask, v, 2); v = (qn == IDX_MAX) ? fmax(v, o) : v + o;
-      o = __shfl_xor_sync(mask, v, 1);        v = (qn == IDX_MAX) ? fmax(v, o) : v + o;
-      if (j == 0) tot[qn] = v;
-    }
-    __syncthreads();
-    const uint32_t seg_tiles = P.seg_first_tile[tile.seg + 1] - P.seg_first_tile[tile.seg];
-    if (seg_tiles == 1) {
-      if (tid == 0) {
-        write_segment_out<VARIANT>(tot, kc, tile.end - tile.begin, out + (size_t)tile.seg * RANDT_FUSED_STRIDE);
-        if (tot[NACC - 1] != 0.0) atomicAdd(bad_counter, (unsigned long long)tot[NACC - 1]);
-      }
-    } else {
-      if (tid < NACC) P.partials[(size_t)t * kMaxAcc + tid] = tot[tid];
-      __threadfence();
-      __syncthreads();
-      if (tid == 0) ticket = atomicAdd(&P.seg_counters[tile.seg], 1u);
-      __syncthreads();
-      if (ticket == seg_tiles - 1) {   // last tile of this segment to finish: fold partials in tile order
-        __threadfence();
-        const uint32_t t0 = P.seg_first_tile[tile.seg];
-        if (tid < NACC) {
-          double v = 0.0;
-          for (uint32_t u = 0; u < seg_tiles; ++u) {
-            const double x = __ldcg(&P.partials[(size_t)(t0 + u) * kMaxAcc + tid]);
-            v = (tid == IDX_MAX) ? fmax(v, x) : v + x;
-          }
-          tot[tid] = v;
-        }
-        __syncthreads();
-        if (tid == 0) {
-          const uint32_t pb = P.tiles[t0].begin, pe = P.tiles[t0 + seg_tiles - 1].end;
-          write_segment_out<VARIANT>(tot, kc, pe - pb, out + (size_t)tile.seg * RANDT_FUSED_STRIDE);
-          if (tot[NACC - 1] != 0.0) atomicAdd(bad_counter, (unsigned long long)tot[NACC - 1]);
-          P.seg_counters[tile.seg] = 0u;   // re-arm for the next launch
-        }
-      }
-    }
-    __syncthreads();
+  for (int s = 0; s < kStages - 1; ++s) {
+    stage_issue<NP>(P, gen, pr, lane, &stage[s], poses, mu_per_seg);
+    gen.advance();
+    pr = make_uint2(0, 0);
+    if (gen.valid() && gen.i + lane < gen.end) pr = P.pairs[gen.i + lane];
   }
+
+  PoseConst kc; LossConst lc;
+  double acc[NS]; double max_dd = 0.0; uint32_t n_bad = 0;
+#pragma unroll
+  for (int e = 0; e < NS; ++e) acc[e] = 0.0;
+  int slot = 0;
+  while (true) {
+    // ---- stage chunk j + kStages - 1, fetch the pair indices of chunk j + kStages ----
+    int islot = slot + kStages - 1; if (islot >= kStages) islot -= kStages;
+    stage_issue<NP>(P, gen, pr, lane, &stage[islot], poses, mu_per_seg);
+    gen.advance();
+    pr = make_uint2(0, 0);
+    if (gen.valid() && gen.i + lane < gen.end) pr = P.pairs[gen.i + lane];
+    // ---- chunk j has landed ----
+    cp_async_wait<kStages - 1>();
+    __syncwarp();
+    const StageBuf* sb = &stage[slot];
+    const ChunkMeta cm = sb->meta;
+    if (cm.t == 0xffffffffu) break;
+    if (sb->first) {
+      make_pose_const<VARIANT>(sb->pose, kc);
+      make_loss_const(lp, mu_per_seg ? sb->mu : lp.mu, lc);
+    }
+    if (cm.i + lane < cm.end) {
+      RawCell m, f;
+      m.a = sb->cell[0][lane]; m.b = sb->cell[1][lane]; m.c = sb->cell[2][lane];
+      f.a = sb->cell[3][lane]; f.b = sb->cell[4][lane]; f.c = sb->cell[5][lane];
+      double N[4];
+      const double dd = pair_core<VARIANT, WANT_JAC>(kc, m, f, N);
+      if (dd_valid(dd)) {
+        double wgt, hrho, wd;
+        loss_eval<LOSS>(dd, lc, wgt, hrho, wd);
+        if (WANT_JAC) {
+          int q = 0;
+#pragma unroll
+          for (int a = 0; a < NB; ++a) {
+            const double wa = wd * N[a];
+#pragma unroll
+            for (int b2 = a; b2 < NB; ++b2) { acc[q] = fma(wa, N[b2], acc[q]); ++q; }
+            acc[NH + a] = fma(wgt, N[a], acc[NH + a]);
+          }
+        }
+        acc[NJ] += hrho;
+        acc[NJ + 1] += dd;
+        max_dd = fmax(max_dd, dd);
+      } else {
+        ++n_bad;
+      }
+    }
+    // ---- tile finished: reduce across the warp and emit ----
+    if (cm.i + 32 >= cm.end) {
+      warp_sum_all<NS>(acc, lane);
+      const double mx = warp_max(max_dd);
+      const uint32_t bad = __reduce_add_sync(kFull, n_bad);
+      const uint32_t seg = cm.seg, t = cm.t;
+      const uint32_t first = P.seg_first_tile[seg], seg_tiles = P.seg_first_tile[seg + 1] - first;
+      if (seg_tiles == 1) {
+        if (lane == 0) {
+          double rec[NH + NB + 2];
+#pragma unroll
+          for (int e = 0; e < NH + NB; ++e) rec[e] = WANT_JAC ? acc[e < NS ? e : 0] : 0.0;
+          rec[NH + NB] = acc[NJ]; rec[NH + NB + 1] = acc[NJ + 1];
+          write_segment_out<VARIANT>(rec, mx, kc, cm.end - P.tiles[t].begin, out + (size_t)seg * RANDT_FUSED_STRIDE);
+          if (bad) atomicAdd(bad_counter, (unsigned long long)bad);
+        }
+      } else {
+        // partial record of this tile: [NS sums][max dd][bad]
+        double* part = P.partials + (size_t)t * kMaxAcc;
+        uint32_t ticket = 0;
+        if (lane == 0) {
+#pragma unroll
+          for (int e = 0; e < NS; ++e) part[e] = acc[e];
+          part[NS] = mx; part[NS + 1] = (double)bad;
+          __threadfence();
+          ticket = atomicAdd(&P.seg_counters[seg], 1u);
+        }
+        ticket = __shfl_sync(kFull, ticket, 0);
+        if (ticket == seg_tiles - 1) {   // last tile of this segment to finish: fold the partials in tile order
+          __threadfence();
+          double v = 0.0;
+          if (lane < NS + 2) {
+            for (uint32_t u = 0; u < seg_tiles; ++u) {
+              const double x = __ldcg(P.partials + (size_t)(first + u) * kMaxAcc + lane);
+              v = (lane == NS) ? fmax(v, x) : v + x;
+            }
+          }
+          double tot[NS];
+#pragma unroll
+          for (int e = 0; e < NS; ++e) tot[e] = __shfl_sync(kFull, v, e);
+          const double mx_all = __shfl_sync(kFull, v, NS);
+          const double bad_all = __shfl_sync(kFull, v, NS + 1);
+          if (lane == 0) {
+            const uint32_t pb = P.tiles[first].begin, pe = P.tiles[first + seg_tiles - 1].end;
+            double rec[NH + NB + 2];
+#pragma unroll
+            for (int e = 0; e < NH + NB; ++e) rec[e] = WANT_JAC ? tot[e < NS ? e : 0] : 0.0;
+            rec[NH + NB] = tot[NJ]; rec[NH + NB + 1] = tot[NJ + 1];
+            write_segment_out<VARIANT>(rec, mx_all, kc, pe - pb, out + (size_t)seg * RANDT_FUSED_STRIDE);
+            if (bad_all != 0.0) atomicAdd(bad_counter, (unsigned long long)bad_all);
+            P.seg_counters[seg] = 0u;   // re-arm for the next launch
+          }
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < NS; ++e) acc[e] = 0.0;
+      max_dd = 0.0; n_bad = 0;
+    }
+    __syncwarp();   // every lane is done with this slot's descriptor/pose before lane 0 restages it
+    if (++slot == kStages) slot = 0;
+  }
+  cp_async_wait<0>();
 }
 
-// EMIT: raw residual and ambient Jacobian row per pair (what Evaluate returns for each block)
+// EMIT: raw residual and ambient Jacobian row per pair (what Evaluate returns for each block); same tile stream, no reduction
 template <int VARIANT, bool WANT_JAC>
-__global__ void __launch_bounds__(kK3Threads) k3_emit_kernel(DeviceProblem P, const double* __restrict__ poses, double* __restrict__ r_out,
-                                                            double* __restrict__ J_out, unsigned long long* __restrict__ bad_counter) {
+__global__ void __launch_bounds__(kK3Threads, 4) k3_emit_kernel(DeviceProblem P, const double* __restrict__ poses, double* __restrict__ r_out,
+                                                               double* __restrict__ J_out, unsigned long long* __restrict__ bad_counter) {
   constexpr int NP = VarTraits<VARIANT>::NP;
-  __shared__ SegConst kc;
-  const int tid = threadIdx.x;
-  for (uint32_t t = blockIdx.x; t < P.n_tiles; t += gridDim.x) {
-    const Tile tile = P.tiles[t];
-    if (tid == 0) make_pose_const<VARIANT>(poses + (size_t)tile.seg * NP, kc);
-    __syncthreads();
-    for (uint32_t i = tile.begin + tid; i < tile.end; i += kK3Threads) {
-      const uint2 pr = P.pairs[i];
-      double r, dd, jb[4];
-      const bool ok = eval_pair<VARIANT, WANT_JAC>(kc, P.cells_m, P.cells_f, pr, r, dd, jb);
-      if (!ok) atomicAdd(bad_counter, 1ull);
-      r_out[i] = ok ? r : __longlong_as_double(0x7ff8000000000000ll);
+  __shared__ StageBuf stage_all[kWarpsPerCta][kStages];
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0);
+  const uint32_t n_warps = gridDim.x * kWarpsPerCta;
+  const uint32_t w = blockIdx.x * kWarpsPerCta + warp;
+  if (w >= P.n_tiles) return;
+  StageBuf* stage = stage_all[warp];
+  TileStream gen;
+  gen.init(P.tiles, P.n_tiles, w, n_warps);
+  uint2 pr = make_uint2(0, 0);
+  if (gen.valid() && gen.i + lane < gen.end) pr = P.pairs[gen.i + lane];
+#pragma unroll
+  for (int s = 0; s < kStages - 1; ++s) {
+    stage_issue<NP>(P, gen, pr, lane, &stage[s], poses, nullptr);
+    gen.advance();
+    pr = make_uint2(0, 0);
+    if (gen.valid() && gen.i + lane < gen.end) pr = P.pairs[gen.i + lane];
+  }
+  PoseConst kc;
+  uint32_t n_bad = 0;
+  int slot = 0;
+  while (true) {
+    int islot = slot + kStages - 1; if (islot >= kStages) islot -= kStages;
+    stage_issue<NP>(P, gen, pr, lane, &stage[islot], poses, nullptr);
+    gen.advance();
+    pr = make_uint2(0, 0);
+    if (gen.valid() && gen.i + lane < gen.end) pr = P.pairs[gen.i + lane];
+    cp_async_wait<kStages - 1>();
+    __syncwarp();
+    const StageBuf* sb = &stage[slot];
+    const ChunkMeta cm = sb->meta;
+    if (cm.t == 0xffffffffu) break;
+    if (sb->first) make_pose_const<VARIANT>(sb->pose, kc);
+    const uint32_t i = cm.i + lane;
+    if (i < cm.end) {
+      RawCell m, f;
+      m.a = sb->cell[0][lane]; m.b = sb->cell[1][lane]; m.c = sb->cell[2][lane];
+      f.a = sb->cell[3][lane]; f.b = sb->cell[4][lane]; f.c = sb->cell[5][lane];
+      double N[4] = {0.0, 0.0, 0.0, 0.0};
+      const double dd = pair_core<VARIANT, WANT_JAC>(kc, m, f, N);
+      const bool ok = dd_valid(dd);
+      double r = 0.0, rs = 0.0;   // r = 0: the reference's dual-number sqrt yields 0/0 here; defined as J = 0
+      if (ok && dd > 0.0) { rs = rsqrt_fast(dd); r = dd * rs; }
+      if (!ok) { ++n_bad; r = __longlong_as_double(0x7ff8000000000000ll); }
+      r_out[i] = r;
       if (WANT_JAC) {
         if (VARIANT == 0) {
           double2* dst = reinterpret_cast<double2*>(J_out + (size_t)i * 4);
-          dst[0] = make_double2(jb[0] * kc.ja, jb[0] * kc.jb);
-          dst[1] = make_double2(jb[1], jb[2]);
+          const double jt = N[0] * rs;
+          dst[0] = make_double2(jt * kc.ja, jt * kc.jb);
+          dst[1] = make_double2(N[1] * rs, N[2] * rs);
         } else if (VARIANT == 1) {
           double2* dst = reinterpret_cast<double2*>(J_out + (size_t)i * 4);
-          dst[0] = make_double2(jb[0], jb[1]);
-          dst[1] = make_double2(jb[2], jb[3]);
+          dst[0] = make_double2(N[0] * rs, N[1] * rs);
+          dst[1] = make_double2(N[2] * rs, N[3] * rs);
         } else {
-          J_out[(size_t)i * 3 + 0] = jb[0]; J_out[(size_t)i * 3 + 1] = jb[1]; J_out[(size_t)i * 3 + 2] = jb[2];
+          J_out[(size_t)i * 3 + 0] = N[0] * rs; J_out[(size_t)i * 3 + 1] = N[1] * rs; J_out[(size_t)i * 3 + 2] = N[2] * rs;
         }
       }
     }
-    __syncthreads();
+    __syncwarp();
+    if (++slot == kStages) slot = 0;
   }
+  cp_async_wait<0>();
+  const uint32_t bad = __reduce_add_sync(kFull, n_bad);
+  if (lane == 0 && bad) atomicAdd(bad_counter, (unsigned long long)bad);
 }
 
 // SWEEP: one thread per candidate pose, pairs of one segment staged through shared memory in chunks (broadcast reads).
 constexpr int kSweepThreads = 128;
-constexpr int kSweepChunk = 64;   // pairs staged per iteration: 64 * 24 doubles = 12 KB
+constexpr int kSweepChunk = 128;   // pairs staged per iteration: 128 * 2 cells * 48 B = 12 KB
 template <int VARIANT, int LOSS>
 __global__ void __launch_bounds__(kSweepThreads) k3_sweep_kernel(DeviceProblem P, uint32_t pair_begin, uint32_t pair_end,
                                                                 const double* __restrict__ poses, uint32_t n_poses, LossParams lp,
                                                                 double* __restrict__ cost_out) {
   constexpr int NP = VarTraits<VARIANT>::NP;
-  __shared__ double sm_m[kSweepChunk][12];
-  __shared__ double sm_f[kSweepChunk][12];
+  __shared__ float4 sm_m[kSweepChunk][3];
+  __shared__ float4 sm_f[kSweepChunk][3];
   const uint32_t pi = blockIdx.x * kSweepThreads + threadIdx.x;
-  SegConst k;
+  PoseConst k; LossConst lc;
   const bool active = pi < n_poses;
   if (active) make_pose_const<VARIANT>(poses + (size_t)pi * NP, k);
   else { const double idp[4] = {1, 0, 0, 0}; make_pose_const<VARIANT>(idp, k); }
-  make_loss_const(lp, lp.mu, k);
+  make_loss_const(lp, lp.mu, lc);
   double cost = 0.0;
   for (uint32_t base = pair_begin; base < pair_end; base += kSweepChunk) {
     const uint32_t n = min((uint32_t)kSweepChunk, pair_end - base);
     __syncthreads();
-    for (uint32_t e = threadIdx.x; e < n * 24; e += kSweepThreads) {
-      const uint32_t pp = e / 24, w = e % 24;
+    for (uint32_t e = threadIdx.x; e < n * 6; e += kSweepThreads) {
+      const uint32_t pp = e / 6, w = e % 6;
       const uint2 pr = P.pairs[base + pp];
-      const float* src = (w < 12) ? reinterpret_cast<const float*>(P.cells_m) + (size_t)pr.x * 12 + w
-                                  : reinterpret_cast<const float*>(P.cells_f) + (size_t)pr.y * 12 + (w - 12);
-      if (w < 12) sm_m[pp][w] = (double)__ldg(src); else sm_f[pp][w - 12] = (double)__ldg(src);
+      if (w < 3) sm_m[pp][w] = __ldg(P.cells_m + 3 * (size_t)pr.x + w);
+      else       sm_f[pp][w - 3] = __ldg(P.cells_f + 3 * (size_t)pr.y + (w - 3));
     }
     __syncthreads();
     if (active) {
       for (uint32_t pp = 0; pp < n; ++pp) {
-        double n0, n1, n2, n3, dd;
-        if (VARIANT == 0 || VARIANT == 2) dd = core3<false>(k.c, k.s, k.tx, k.ty, &sm_m[pp][0], &sm_m[pp][3], &sm_f[pp][0], &sm_f[pp][3], n0, n1, n2);
-        else if (VARIANT == 1) dd = core2<false, true>(k.c, k.s, k.tx, k.ty, &sm_m[pp][0], &sm_m[pp][3], &sm_f[pp][0], &sm_f[pp][3], n0, n1, n2, n3);
-        else dd = core2<false, false>(k.c, k.s, k.tx, k.ty, &sm_m[pp][0], &sm_m[pp][3], &sm_f[pp][0], &sm_f[pp][3], n0, n1, n2, n3);
-        if (!((dd >= 0.0) && (dd < 1.0e300))) continue;
-        double rho, rho1;
-        loss_eval<LOSS>(dd, k, rho, rho1);
-        cost += 0.5 * rho;
+        RawCell m, f;
+        m.a = sm_m[pp][0]; m.b = sm_m[pp][1]; m.c = sm_m[pp][2];
+        f.a = sm_f[pp][0]; f.b = sm_f[pp][1]; f.c = sm_f[pp][2];
+        double N[4];
+        const double dd = pair_core<VARIANT, false>(k, m, f, N);
+        if (!dd_valid(dd)) continue;
+        double wgt, hrho, wd;
+        loss_eval<LOSS>(dd, lc, wgt, hrho, wd);
+        cost += hrho;
       }
     }
   }
@@ -439,10 +661,16 @@ int loss_code(const LossParams& lp) {
   return L_BARRON;
 }
 
+inline int stream_grid(uint32_t n_tiles) {
+  const uint32_t full = (uint32_t)kSmCount * 4u;   // 4 CTAs of 4 warps per SM (128 registers per thread)
+  const uint32_t need = (n_tiles + kWarpsPerCta - 1) / kWarpsPerCta;
+  return (int)(need < full ? need : full);
+}
+
 template <int VARIANT, int LOSS>
 cudaError_t launch_fused_vl(const DeviceProblem& p, const double* d_poses, const LossParams& lp, const double* d_mu, bool want_jac,
                             double* d_out, unsigned long long* bad, cudaStream_t s) {
-  const int grid = (int)min((uint32_t)(kSmCount * 16), p.n_tiles);
+  const int grid = stream_grid(p.n_tiles);
   if (want_jac) k3_fused_kernel<VARIANT, LOSS, true><<<grid, kK3Threads, 0, s>>>(p, d_poses, lp, d_mu, d_out, bad);
   else          k3_fused_kernel<VARIANT, LOSS, false><<<grid, kK3Threads, 0, s>>>(p, d_poses, lp, d_mu, d_out, bad);
   return cudaGetLastError();
@@ -493,7 +721,7 @@ cudaError_t launch_eval_fused(const DeviceProblem& p, int variant, const double*
 cudaError_t launch_eval_emit(const DeviceProblem& p, int variant, const double* d_poses, double* d_r, double* d_J,
                              unsigned long long* d_bad, cudaStream_t s, int* n_launches) {
   if (p.n_tiles == 0) return cudaSuccess;
-  const int grid = (int)min((uint32_t)(kSmCount * 16), p.n_tiles);
+  const int grid = stream_grid(p.n_tiles);
 #define RANDT_EMIT(V)                                                                                              \
   if (d_J) k3_emit_kernel<V, true><<<grid, kK3Threads, 0, s>>>(p, d_poses, d_r, d_J, d_bad);             \
   else     k3_emit_kernel<V, false><<<grid, kK3Threads, 0, s>>>(p, d_poses, d_r, d_J, d_bad);
