@@ -14,7 +14,8 @@ OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "librandt_gpu.so")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
+EXTRA = os.environ.get("RANDT_NVCC_FLAGS", "").split()
+COMMON = EXTRA + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 UNITS = {
     "k3_pair_eval.cu": [],
     "k2_associate.cu": ["-fmad=false"],

@@ -39,6 +39,8 @@ struct randt_problem {
   uint32_t S = 0, P = 0, n_m = 0, n_f = 0;
   float4 *cells_m = nullptr, *cells_f = nullptr;
   uint2* pairs = nullptr;
+  Duo* duos = nullptr; uint32_t n_duos = 0;
+  std::vector<uint32_t> h_duo_off;   // [S+1] duo offsets per segment
   Tile* tiles = nullptr; uint32_t n_tiles = 0;
   uint32_t* seg_first_tile = nullptr;
   uint32_t* seg_off = nullptr;
@@ -83,7 +85,7 @@ void free_map(randt_map* m) {
 }
 void free_problem(randt_problem* p) {
   if (!p) return;
-  cudaFree(p->cells_m); cudaFree(p->cells_f); cudaFree(p->pairs); cudaFree(p->tiles); cudaFree(p->seg_first_tile); cudaFree(p->seg_off);
+  cudaFree(p->cells_m); cudaFree(p->cells_f); cudaFree(p->pairs); cudaFree(p->duos); cudaFree(p->tiles); cudaFree(p->seg_first_tile); cudaFree(p->seg_off);
   cudaFree(p->partials); cudaFree(p->seg_counters); cudaFree(p->d_poses); cudaFree(p->d_out); cudaFree(p->d_mu); cudaFree(p->d_r);
   cudaFree(p->d_J); cudaFree(p->d_sweep);
   delete p;
@@ -93,15 +95,15 @@ void free_problem(randt_problem* p) {
 int finish_problem(randt_ctx* ctx, randt_problem* p) {
   std::vector<Tile> tiles;
   std::vector<uint32_t> first(p->S + 1, 0);
-  // one warp owns a tile.  Big batches: tiles of up to kTilePairs pairs (a whole ~200-pair registration per warp, no partials);
+  // one warp owns a tile.  Big batches: tiles of up to kTileDuos duos (a whole ~200-pair registration per warp, no partials);
   // small problems: shorter tiles so that the pairs still spread over the SMs (each extra tile costs one partial record).
-  uint32_t tile_pairs = (p->P / (uint32_t)(kSmCount * 4) + 31u) / 32u * 32u;
-  tile_pairs = std::max<uint32_t>(kMinTilePairs, std::min<uint32_t>(tile_pairs, kTilePairs));
+  uint32_t tile_duos = (p->n_duos / (uint32_t)(kSmCount * 4) + 31u) / 32u * 32u;
+  tile_duos = std::max<uint32_t>(kMinTileDuos, std::min<uint32_t>(tile_duos, kTileDuos));
   for (uint32_t s = 0; s < p->S; ++s) {
     first[s] = (uint32_t)tiles.size();
     uint32_t part = 0;
-    for (uint32_t b = p->h_seg_off[s]; b < p->h_seg_off[s + 1]; b += tile_pairs) {
-      Tile t; t.seg = s; t.begin = b; t.end = std::min(p->h_seg_off[s + 1], b + tile_pairs); t.part = part++;
+    for (uint32_t b = p->h_duo_off[s]; b < p->h_duo_off[s + 1]; b += tile_duos) {
+      Tile t; t.seg = s; t.begin = b; t.end = std::min(p->h_duo_off[s + 1], b + tile_duos); t.part = part++;
       tiles.push_back(t);
     }
   }
@@ -126,18 +128,23 @@ int finish_problem(randt_ctx* ctx, randt_problem* p) {
 
 DeviceProblem view(const randt_problem* p) {
   DeviceProblem d;
-  d.cells_m = p->cells_m; d.cells_f = p->cells_f; d.pairs = p->pairs; d.tiles = p->tiles; d.n_tiles = p->n_tiles;
+  d.cells_m = p->cells_m; d.cells_f = p->cells_f; d.pairs = p->pairs; d.duos = p->duos; d.seg_off = p->seg_off; d.tiles = p->tiles; d.n_tiles = p->n_tiles;
   d.seg_first_tile = p->seg_first_tile; d.n_segments = p->S; d.n_pairs = p->P; d.partials = p->partials; d.seg_counters = p->seg_counters;
   return d;
 }
 
 int make_loss(randt_ctx* ctx, const randt_loss* l, LossParams* out) {
-  LossParams lp; lp.kind = RANDT_LOSS_NONE; lp.a2 = 1.0; lp.alpha = 2.0; lp.weight = 1.0; lp.mu = 1.0;
+  LossParams lp; lp.kind = RANDT_LOSS_NONE; lp.a2 = 1.0; lp.alpha = 2.0; lp.weight = 1.0; lp.mu = 1.0; lp.fa = 0.0; lp.tf = 0.0;
   if (l) {
     if (l->kind < RANDT_LOSS_NONE || l->kind > RANDT_LOSS_WELSCH) return fail(ctx, RANDT_E_INVALID, "unknown loss kind");
     lp.kind = l->kind; lp.a2 = l->scale * l->scale; lp.alpha = l->alpha; lp.weight = l->weight; lp.mu = l->mu;
     if (l->kind != RANDT_LOSS_NONE && !(l->scale > 0.0 && l->mu > 0.0)) return fail(ctx, RANDT_E_INVALID, "loss scale and mu must be > 0");
     if (l->kind == RANDT_LOSS_BARRON && l->alpha == 0.0) { /* handled by the |alpha| <= 0.05 branch */ }
+  }
+  if (lp.kind == RANDT_LOSS_BARRON) {
+    const double factor = fabs(lp.alpha - 2.0);
+    lp.fa = factor / lp.alpha;     // inf for alpha == 0: that case takes the log branch and never reads it
+    lp.tf = 2.0 / factor;
   }
   *out = lp;
   return RANDT_OK;
@@ -402,9 +409,9 @@ int randt_associate(randt_ctx* ctx, const randt_map* F, const randt_map* M, cons
   randt_problem* p = new (std::nothrow) randt_problem();
   if (!p) return RANDT_E_NOMEM;
   p->device = ctx->device; p->S = B; p->n_m = n_m; p->n_f = F->n_cells;
-  float4* d_pose = nullptr; uint32_t *d_nn = nullptr, *d_cnt = nullptr, *d_scan = nullptr, *d_bs = nullptr;
+  float4* d_pose = nullptr; uint32_t *d_nn = nullptr, *d_cnt = nullptr, *d_scan = nullptr, *d_bs = nullptr, *d_cnt2 = nullptr, *d_scan2 = nullptr;
   int rc = RANDT_OK; int nl = 0;
-  auto cleanup = [&]() { cudaFree(d_pose); cudaFree(d_nn); cudaFree(d_cnt); cudaFree(d_scan); cudaFree(d_bs); };
+  auto cleanup = [&]() { cudaFree(d_pose); cudaFree(d_nn); cudaFree(d_cnt); cudaFree(d_scan); cudaFree(d_bs); cudaFree(d_cnt2); cudaFree(d_scan2); };
 #define CKA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rc = fail(ctx, RANDT_E_CUDA, #call, e__); cleanup(); free_problem(p); return rc; } } while (0)
   std::vector<float4> h_pose(B);
   for (uint32_t b = 0; b < B; ++b) h_pose[b] = make_float4((float)pose0[4 * b], (float)pose0[4 * b + 1], (float)pose0[4 * b + 2], (float)pose0[4 * b + 3]);
@@ -421,6 +428,17 @@ int randt_associate(randt_ctx* ctx, const randt_map* F, const randt_map* M, cons
   for (uint32_t b = 0; b <= B; ++b) p->h_seg_off[b] = h_scan[M->h_cell_off[b]];
   CKA(dev_alloc(&p->pairs, p->P));
   CKA(launch_compact_pairs(d_nn, d_cnt, d_scan, M->cell_off, F->cell_off, B, n_m, M->max_per_map, k, p->pairs, ctx->stream, &nl));
+  // duos (K3's grouping): ceil(cnt / 2) per moving cell
+  CKA(dev_alloc(&d_cnt2, n_m)); CKA(dev_alloc(&d_scan2, (size_t)n_m + 1));
+  CKA(launch_duo_counts(d_cnt, n_m, d_cnt2, ctx->stream, &nl));
+  CKA(launch_exclusive_scan_u32(d_cnt2, d_scan2, n_m, d_bs, ctx->stream, &nl));
+  CKA(cudaMemcpyAsync(h_scan.data(), d_scan2, ((size_t)n_m + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CKA(cudaStreamSynchronize(ctx->stream));
+  p->n_duos = h_scan[n_m];
+  p->h_duo_off.resize(B + 1);
+  for (uint32_t b = 0; b <= B; ++b) p->h_duo_off[b] = h_scan[M->h_cell_off[b]];
+  CKA(dev_alloc(&p->duos, p->n_duos));
+  CKA(launch_compact_duos(d_nn, d_cnt, d_scan, d_scan2, M->cell_off, F->cell_off, B, n_m, M->max_per_map, k, p->duos, ctx->stream, &nl));
   // snapshot the cell tables (the reference's functors copy their cells; maps may be merged/transformed afterwards)
   CKA(dev_alloc(&p->cells_m, (size_t)n_m * 3)); CKA(dev_alloc(&p->cells_f, (size_t)F->n_cells * 3));
   if (n_m) CKA(cudaMemcpyAsync(p->cells_m, M->cells, (size_t)n_m * 48, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -455,7 +473,21 @@ int randt_problem_create(randt_ctx* ctx, const float* cells_m, uint32_t n_m, con
   for (uint32_t i = 0; i < n_pairs; ++i) h_pairs[i] = make_uint2(pair_m[i], pair_f[i]);
   int rc = RANDT_OK;
 #define CKP(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rc = fail(ctx, RANDT_E_CUDA, #call, e__); free_problem(p); return rc; } } while (0)
+  // duos: consecutive pairs of one segment that share their moving cell, two by two
+  std::vector<Duo> h_duos; h_duos.reserve(n_pairs / 2 + n_segments + 1);
+  p->h_duo_off.assign(n_segments + 1, 0);
+  for (uint32_t sg = 0; sg < n_segments; ++sg) {
+    for (uint32_t i = seg_off[sg]; i < seg_off[sg + 1];) {
+      Duo d; d.im = pair_m[i]; d.jf0 = pair_f[i]; d.jf1 = kNoCell; d.p0 = i;
+      if (i + 1 < seg_off[sg + 1] && pair_m[i + 1] == pair_m[i]) { d.jf1 = pair_f[i + 1]; i += 2; } else { i += 1; }
+      h_duos.push_back(d);
+    }
+    p->h_duo_off[sg + 1] = (uint32_t)h_duos.size();
+  }
+  p->n_duos = (uint32_t)h_duos.size();
   CKP(dev_alloc(&p->cells_m, (size_t)n_m * 3)); CKP(dev_alloc(&p->cells_f, (size_t)n_f * 3)); CKP(dev_alloc(&p->pairs, n_pairs));
+  CKP(dev_alloc(&p->duos, p->n_duos));
+  if (p->n_duos) CKP(cudaMemcpyAsync(p->duos, h_duos.data(), (size_t)p->n_duos * sizeof(Duo), cudaMemcpyHostToDevice, ctx->stream));
   if (n_m) CKP(cudaMemcpyAsync(p->cells_m, cells_m, (size_t)n_m * 48, cudaMemcpyHostToDevice, ctx->stream));
   if (n_f) CKP(cudaMemcpyAsync(p->cells_f, cells_f, (size_t)n_f * 48, cudaMemcpyHostToDevice, ctx->stream));
   if (n_pairs) CKP(cudaMemcpyAsync(p->pairs, h_pairs.data(), (size_t)n_pairs * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));

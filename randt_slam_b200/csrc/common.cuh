@@ -18,15 +18,24 @@ struct LossParams {  // host-evaluated constants of the loss that do not depend 
   double alpha;
   double weight;
   double mu;      // used when no per-segment mu is given
+  double fa, tf;  // Barron: |alpha - 2| / alpha and 2 / |alpha - 2|  (pre_factor = b * fa, times_s = tf / b)
 };
 
-// A work tile: pairs [begin, end) of segment `seg`; `part` = index of the tile inside its segment.
+// K3 evaluates "duos": one or two consecutive pairs that share their moving cell (the k neighbours of a moving cell are
+// adjacent in the reference's residual-block order, R/src/ndt_registration/ndt_matcher.cpp:217-246).  One lane owns a duo, so
+// the moving cell is loaded, converted and rotated once for both pairs.
+struct Duo { uint32_t im, jf0, jf1, p0; };   // moving cell, fixed cell of pair p0, fixed cell of pair p0 + 1 (kNoCell: none), first pair
+constexpr uint32_t kNoCell = 0xffffffffu;
+
+// A work tile: duos [begin, end) of segment `seg`; `part` = index of the tile inside its segment.
 struct Tile { uint32_t seg, begin, end, part; };
 
 struct DeviceProblem {
   const float4* cells_m;   // 3 x float4 per cell
   const float4* cells_f;
-  const uint2* pairs;      // (im, jf)
+  const uint2* pairs;      // (im, jf), reference residual-block order
+  const Duo* duos;         // the same pairs grouped for K3
+  const uint32_t* seg_off; // [S+1] pair offsets per segment
   const Tile* tiles;
   uint32_t n_tiles;
   const uint32_t* seg_first_tile;  // [S+1]
@@ -36,8 +45,8 @@ struct DeviceProblem {
   uint32_t* seg_counters;  // [S] zero between launches
 };
 
-constexpr int kTilePairs = 512;   // most pairs per tile (one warp owns a tile)
-constexpr int kMinTilePairs = 64; // tile length for small problems
+constexpr int kTileDuos = 256;    // most duos per tile (one warp owns a tile)
+constexpr int kMinTileDuos = 32;  // tile length for small problems
 constexpr int kK3Threads = 128;   // threads per CTA in the pair-evaluation kernels
 constexpr int kMaxAcc = 20;       // accumulators per tile partial (<= 10 H + 4 g + cost + max + sumsq + nonfinite)
 
@@ -75,6 +84,10 @@ cudaError_t launch_associate(const float4* cells_f, const uint32_t* cell_off_f, 
 cudaError_t launch_compact_pairs(const uint32_t* d_nn, const uint32_t* d_cnt, const uint32_t* d_scan /*exclusive scan of cnt*/,
                                  const uint32_t* cell_off_m, const uint32_t* cell_off_f, uint32_t n_maps, uint32_t n_m_total,
                                  uint32_t max_m_per_map, int k, uint2* d_pairs, cudaStream_t s, int* n_launches);
+cudaError_t launch_compact_duos(const uint32_t* d_nn, const uint32_t* d_cnt, const uint32_t* d_scan /*pairs*/, const uint32_t* d_scan2 /*duos*/,
+                                const uint32_t* cell_off_m, const uint32_t* cell_off_f, uint32_t n_maps, uint32_t n_m_total,
+                                uint32_t max_m_per_map, int k, Duo* d_duos, cudaStream_t s, int* n_launches);
+cudaError_t launch_duo_counts(const uint32_t* d_cnt, uint32_t n, uint32_t* d_cnt2, cudaStream_t s, int* n_launches);
 cudaError_t launch_exclusive_scan_u32(const uint32_t* d_in, uint32_t* d_out /*[n+1]*/, uint32_t n, uint32_t* d_block_sums, cudaStream_t s,
                                       int* n_launches);
 

@@ -154,6 +154,29 @@ __global__ void k2_compact_pairs_kernel(const uint32_t* __restrict__ nn, const u
   for (uint32_t t = 0; t < n; ++t) pairs[base + t] = make_uint2(i, f0 + nn[(size_t)i * k + t]);
 }
 
+// duos of moving cell i: its neighbours two by two (the grouping K3 evaluates, see common.cuh)
+__global__ void k2_duo_counts_kernel(const uint32_t* __restrict__ cnt, uint32_t n, uint32_t* __restrict__ cnt2) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) cnt2[i] = (cnt[i] + 1u) >> 1;
+}
+__global__ void k2_compact_duos_kernel(const uint32_t* __restrict__ nn, const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ scan,
+                                       const uint32_t* __restrict__ scan2, const uint32_t* __restrict__ cell_off_m,
+                                       const uint32_t* __restrict__ cell_off_f, int k, Duo* __restrict__ duos) {
+  const uint32_t b = blockIdx.y;
+  const uint32_t m0 = cell_off_m[b], m1 = cell_off_m[b + 1];
+  const uint32_t i = m0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m1) return;
+  const uint32_t f0 = cell_off_f[b];
+  const uint32_t base = scan[i], n = cnt[i], dbase = scan2[i];
+  for (uint32_t t = 0; t < n; t += 2) {
+    Duo d;
+    d.im = i; d.jf0 = f0 + nn[(size_t)i * k + t];
+    d.jf1 = (t + 1 < n) ? f0 + nn[(size_t)i * k + t + 1] : kNoCell;
+    d.p0 = base + t;
+    duos[dbase + (t >> 1)] = d;
+  }
+}
+
 // ---- exclusive scan of u32 (three small kernels; construction-time only) -------------------------------------
 constexpr int kScanThreads = 256;
 constexpr int kScanItems = 4;
@@ -230,6 +253,23 @@ cudaError_t launch_compact_pairs(const uint32_t* d_nn, const uint32_t* d_cnt, co
   if (n_maps == 0 || max_m_per_map == 0) return cudaSuccess;
   dim3 grid((max_m_per_map + 127) / 128, n_maps);
   k2_compact_pairs_kernel<<<grid, 128, 0, s>>>(d_nn, d_cnt, d_scan, cell_off_m, cell_off_f, k, d_pairs);
+  if (n_launches) *n_launches += 1;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_duo_counts(const uint32_t* d_cnt, uint32_t n, uint32_t* d_cnt2, cudaStream_t s, int* n_launches) {
+  if (n == 0) return cudaSuccess;
+  k2_duo_counts_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_cnt, n, d_cnt2);
+  if (n_launches) *n_launches += 1;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_compact_duos(const uint32_t* d_nn, const uint32_t* d_cnt, const uint32_t* d_scan, const uint32_t* d_scan2,
+                                const uint32_t* cell_off_m, const uint32_t* cell_off_f, uint32_t n_maps, uint32_t n_m_total,
+                                uint32_t max_m_per_map, int k, Duo* d_duos, cudaStream_t s, int* n_launches) {
+  if (n_maps == 0 || max_m_per_map == 0) return cudaSuccess;
+  dim3 grid((max_m_per_map + 127) / 128, n_maps);
+  k2_compact_duos_kernel<<<grid, 128, 0, s>>>(d_nn, d_cnt, d_scan, d_scan2, cell_off_m, cell_off_f, k, d_duos);
   if (n_launches) *n_launches += 1;
   return cudaGetLastError();
 }

@@ -82,33 +82,46 @@ template <> struct VarTraits<2> { static constexpr int NB = 3, NP = 3; };  // ba
 template <> struct VarTraits<3> { static constexpr int NB = 3, NP = 3; };
 
 // ---- per-pair core ------------------------------------------------------------------------------------------------
-// dd = d^T B^-1 d and (WANT_JAC) the basis numerators N[] = r * dr/d(basis), in the basis order of VarTraits.
-template <int VARIANT, bool WANT_JAC>
-__device__ __forceinline__ double pair_core(const PoseConst& k, const RawCell& m, const RawCell& f, double* __restrict__ N) {
-  const double mx = m.a.x, my = m.a.y;
-  const double S00 = m.a.w, S11 = m.b.w;
+// Everything that depends on the moving cell and the pose only (shared by the pairs of a duo).
+struct Moving {
+  double mx, my, mi, S00, S11, bh, S22;   // bh = sym(S01)
+  double M00, M01, M11, M02, M12;         // R S R^T (symmetric; M22 = S22)
+  double xr, yr;                          // R mu_m (no translation)
+};
+template <int VARIANT>
+__device__ __forceinline__ void moving_part(const PoseConst& k, const RawCell& m, Moving& o) {
+  o.mx = m.a.x; o.my = m.a.y; o.S00 = m.a.w; o.S11 = m.b.w;
   const double b2 = (double)m.b.x + (double)m.b.z;              // 2 * sym(S01)
-  // rotated moving covariance (symmetric): M = R S R^T
-  const double M00 = fma(k.cc, S00, fma(k.ss, S11, -k.cs * b2));
-  const double M11 = fma(k.n2, S00 + S11, -M00);
-  const double M01 = fma(k.cs, S00 - S11, k.hd * b2);
-  const double xr = fma(k.c, mx, -k.s * my);
-  const double yr = fma(k.s, mx, k.c * my);
-  const double d0 = (xr + k.tx) - (double)f.a.x;
-  const double d1 = (yr + k.ty) - (double)f.a.y;
-  const double B00 = M00 + (double)f.a.w;
-  const double B11 = M11 + (double)f.b.w;
-  const double B01 = fma(0.5, (double)f.b.x + (double)f.b.z, M01);
-  double q0, q1, q2 = 0.0, dd, M02 = 0.0, M12 = 0.0;
+  o.bh = 0.5 * b2;
+  o.M00 = fma(k.cc, o.S00, fma(k.ss, o.S11, -k.cs * b2));
+  o.M11 = fma(k.n2, o.S00 + o.S11, -o.M00);
+  o.M01 = fma(k.cs, o.S00 - o.S11, k.hd * b2);
+  o.xr = fma(k.c, o.mx, -k.s * o.my);
+  o.yr = fma(k.s, o.mx, k.c * o.my);
   if (VARIANT == 0 || VARIANT == 2) {
     const double e2 = (double)m.b.y + (double)m.c.y;            // 2 * sym(S02)
     const double f2 = (double)m.c.x + (double)m.c.z;            // 2 * sym(S12)
-    M02 = fma(k.ch, e2, -k.sh * f2);
-    M12 = fma(k.sh, e2, k.ch * f2);
-    const double d2 = (double)m.a.z - (double)f.a.z;
-    const double B22 = (double)m.c.w + (double)f.c.w;
-    const double B02 = fma(0.5, (double)f.b.y + (double)f.c.y, M02);
-    const double B12 = fma(0.5, (double)f.c.x + (double)f.c.z, M12);
+    o.M02 = fma(k.ch, e2, -k.sh * f2);
+    o.M12 = fma(k.sh, e2, k.ch * f2);
+    o.mi = m.a.z; o.S22 = m.c.w;
+  } else {
+    o.M02 = 0.0; o.M12 = 0.0; o.mi = 0.0; o.S22 = 0.0;
+  }
+}
+// dd = d^T B^-1 d and (WANT_JAC) the basis numerators N[] = r * dr/d(basis), in the basis order of VarTraits.
+template <int VARIANT, bool WANT_JAC>
+__device__ __forceinline__ double fixed_part(const PoseConst& k, const Moving& mv, const RawCell& f, double* __restrict__ N) {
+  const double d0 = (mv.xr + k.tx) - (double)f.a.x;
+  const double d1 = (mv.yr + k.ty) - (double)f.a.y;
+  const double B00 = mv.M00 + (double)f.a.w;
+  const double B11 = mv.M11 + (double)f.b.w;
+  const double B01 = fma(0.5, (double)f.b.x + (double)f.b.z, mv.M01);
+  double q0, q1, q2 = 0.0, dd;
+  if (VARIANT == 0 || VARIANT == 2) {
+    const double d2 = mv.mi - (double)f.a.z;
+    const double B22 = mv.S22 + (double)f.c.w;
+    const double B02 = fma(0.5, (double)f.b.y + (double)f.c.y, mv.M02);
+    const double B12 = fma(0.5, (double)f.c.x + (double)f.c.z, mv.M12);
     const double C00 = fma(B11, B22, -B12 * B12);
     const double C01 = fma(B02, B12, -B01 * B22);
     const double C02 = fma(B01, B12, -B02 * B11);
@@ -132,22 +145,27 @@ __device__ __forceinline__ double pair_core(const PoseConst& k, const RawCell& m
     if (VARIANT == 1) {
       // R = [c -s; s c] un-normalised, c and s independent parameters:
       //   N_c = q.(mx, my) - g^T S q,   N_s = q.(-my, mx) - (q1 (S g)0 - q0 (S g)1),   g = R^T q
-      const double bh = 0.5 * b2;
       const double g0 = fma(k.c, q0, k.s * q1), g1 = fma(k.c, q1, -k.s * q0);
-      const double Sq0 = fma(S00, q0, bh * q1), Sq1 = fma(bh, q0, S11 * q1);
-      const double Sg0 = fma(S00, g0, bh * g1), Sg1 = fma(bh, g0, S11 * g1);
-      N[0] = fma(q0, mx, q1 * my) - fma(g0, Sq0, g1 * Sq1);
-      N[1] = fma(q1, mx, -q0 * my) - fma(q1, Sg0, -q0 * Sg1);
+      const double Sq0 = fma(mv.S00, q0, mv.bh * q1), Sq1 = fma(mv.bh, q0, mv.S11 * q1);
+      const double Sg0 = fma(mv.S00, g0, mv.bh * g1), Sg1 = fma(mv.bh, g0, mv.S11 * g1);
+      N[0] = fma(q0, mv.mx, q1 * mv.my) - fma(g0, Sq0, g1 * Sq1);
+      N[1] = fma(q1, mv.mx, -q0 * mv.my) - fma(q1, Sg0, -q0 * Sg1);
       N[2] = q0; N[3] = q1;
     } else {
-      const double a0 = xr - fma(M00, q0, fma(M01, q1, M02 * q2));
-      const double a1 = yr - fma(M01, q0, fma(M11, q1, M12 * q2));
+      const double a0 = mv.xr - fma(mv.M00, q0, fma(mv.M01, q1, mv.M02 * q2));
+      const double a1 = mv.yr - fma(mv.M01, q0, fma(mv.M11, q1, mv.M12 * q2));
       const double nt = fma(q1, a0, -q0 * a1);
       if (VARIANT == 0) { N[0] = nt; N[1] = q0; N[2] = q1; }      // (theta, x, y)
       else              { N[0] = q0; N[1] = q1; N[2] = nt; }      // (x, y, theta)
     }
   }
   return dd;
+}
+template <int VARIANT, bool WANT_JAC>
+__device__ __forceinline__ double pair_core(const PoseConst& k, const RawCell& m, const RawCell& f, double* __restrict__ N) {
+  Moving mv;
+  moving_part<VARIANT>(k, m, mv);
+  return fixed_part<VARIANT, WANT_JAC>(k, mv, f, N);
 }
 
 __device__ __forceinline__ bool dd_valid(double dd) { return (dd >= 0.0) && (dd < 1.0e300); }   // false for NaN, inf, negative
@@ -195,10 +213,12 @@ template <int VARIANT>
 __device__ __forceinline__ void make_pose_const(const double* __restrict__ pose, PoseConst& k) {
   k.n2 = 1.0; k.ja = 0.0; k.jb = 0.0;
   if (VARIANT == 0) {
+    // theta = atan2(s, c): rotate by the normalised complex; dtheta/dc = -s/|z|^2, dtheta/ds = c/|z|^2
     const double c = pose[0], s = pose[1];
-    const double n2 = c * c + s * s, n = sqrt(n2);
-    k.c = c / n; k.s = s / n; k.tx = pose[2]; k.ty = pose[3];
-    k.ja = -s / n2; k.jb = c / n2;
+    const double n2 = fma(c, c, s * s);
+    const double rn = rsqrt_fast(n2), in2 = rn * rn;
+    k.c = c * rn; k.s = s * rn; k.tx = pose[2]; k.ty = pose[3];
+    k.ja = -s * in2; k.jb = c * in2;
   } else if (VARIANT == 1) {
     k.c = pose[0]; k.s = pose[1]; k.tx = pose[2]; k.ty = pose[3];
     k.n2 = k.c * k.c + k.s * k.s;
@@ -214,13 +234,14 @@ __device__ __forceinline__ void make_pose_const(const double* __restrict__ pose,
   k.ch = 0.5 * k.c; k.sh = 0.5 * k.s;
 }
 
+// loss constants for one mu.  lp carries the mu-independent factors (host-computed, LossParams in common.cuh)
 __device__ __forceinline__ void make_loss_const(const LossParams& lp, double mu, LossConst& k) {
   k.weight = lp.weight;
   const double b = mu * lp.a2;
-  k.lb = b; k.preW = 0.0; k.K = 0.0;
-  if (lp.kind == RANDT_LOSS_WELSCH) { k.lc = -1.0 / b; k.pre = 0; k.ts = 0; k.e = 0; return; }
-  const double c = 1.0 / b, factor = fabs(lp.alpha - 2.0);
-  k.lc = c; k.e = 0.5 * lp.alpha; k.pre = b * factor / lp.alpha; k.ts = 2.0 * c / factor;
+  const double c = rcp_fast(b);
+  k.lb = b; k.e = 0.5 * lp.alpha;
+  if (lp.kind == RANDT_LOSS_WELSCH) { k.lc = -c; k.pre = 0; k.ts = 0; k.preW = 0; k.K = 0; return; }
+  k.lc = c; k.pre = b * lp.fa; k.ts = c * lp.tf;
   k.preW = 0.5 * k.pre * k.weight;
   k.K = k.pre * k.e * k.ts * k.weight;
 }
@@ -313,16 +334,26 @@ __device__ void write_segment_out(const double* __restrict__ tot, double max_dd,
 }
 
 // ---- the software-pipelined tile stream of one warp ------------------------------------------------------------------
-// Every warp walks tiles w, w + n_warps, ... as a stream of 32-pair chunks.  A chunk's inputs are staged in shared memory by
-// cp.async (LDGSTS): 6 x 16 B per lane for the two cells, plus (first chunk of a tile, lane 0) the pose and mu of the tile's
-// segment and the chunk's descriptor.  kStages chunks are in flight per warp, so registers hold nothing but the accumulators
-// while HBM latency is covered; each lane reads back only what it copied itself (no cross-lane hazard on the cell slots).
+// Every warp walks tiles w, w + n_warps, ... as a stream of 32-duo chunks (a lane owns one duo = up to two pairs that share
+// their moving cell).  A chunk's inputs are staged in shared memory by cp.async (LDGSTS): 9 x 16 B per lane for the three
+// cells, plus (first chunk of a tile, lane 0) the pose and mu of the tile's segment and the chunk's descriptor.  kStages
+// chunks are in flight per warp, so registers hold nothing but the accumulators while HBM latency is covered; each lane reads
+// back only what it copied itself (no cross-lane hazard on the cell slots).  The two pairs of a duo are evaluated as two
+// independent instruction streams (ILP for the half-rate fp64 pipe).
 constexpr int kWarpsPerCta = kK3Threads / 32;
-constexpr int kStages = 3;
+#ifndef RANDT_K3_STAGES
+#define RANDT_K3_STAGES 2
+#endif
+#ifndef RANDT_K3_MIN_CTAS
+#define RANDT_K3_MIN_CTAS 4
+#endif
+constexpr int kStages = RANDT_K3_STAGES;
+constexpr int kMinCtas = RANDT_K3_MIN_CTAS;   // CTAs per SM the register allocation is bounded for
 
-struct __align__(16) ChunkMeta { uint32_t t, i, end, seg; };   // tile index (0xffffffff: past the end), first pair, tile end, segment
+struct __align__(16) ChunkMeta { uint32_t t, i, end, seg; };   // tile index (0xffffffff: past the end), first duo, tile end, segment
 struct __align__(16) StageBuf {
-  float4 cell[6][32];      // [component][lane]: moving a, b, c, fixed a, b, c
+  float4 cell[9][32];      // [component][lane]: moving a, b, c, fixed0 a, b, c, fixed1 a, b, c
+  uint4 duo[32];           // the lane's duo record (im, jf0, jf1, p0)
   double pose[4];
   double mu;
   uint32_t first;          // 1: first chunk of its tile (pose/mu valid)
@@ -364,18 +395,28 @@ struct TileStream {   // generator (warp-uniform): tiles t0, t0 + stride, ... ch
       if (t < n_tiles && t + stride < n_tiles) la = tiles[t + stride];
     }
   }
+  __device__ __forceinline__ uint4 fetch_duo(const Duo* __restrict__ duos, int lane) const {
+    uint4 d = make_uint4(0, 0, kNoCell, 0);
+    if (t < n_tiles && i + lane < end) d = __ldg(reinterpret_cast<const uint4*>(duos) + i + lane);
+    return d;
+  }
 };
 
-// issue the asynchronous copies of the generator's current chunk into `sb` (pair index `pr` was fetched one iteration earlier)
+// issue the asynchronous copies of the generator's current chunk into `sb` (duo record `du` was fetched one iteration earlier)
 template <int NP>
-__device__ __forceinline__ void stage_issue(const DeviceProblem& P, const TileStream& g, uint2 pr, int lane, StageBuf* sb,
+__device__ __forceinline__ void stage_issue(const DeviceProblem& P, const TileStream& g, uint4 du, int lane, StageBuf* sb,
                                             const double* __restrict__ poses, const double* __restrict__ mu_per_seg) {
   if (g.valid()) {
     if (g.i + lane < g.end) {
-      const float4* pm = P.cells_m + 3 * (size_t)pr.x;
-      const float4* pf = P.cells_f + 3 * (size_t)pr.y;
+      const float4* pm = P.cells_m + 3 * (size_t)du.x;
+      const float4* pf = P.cells_f + 3 * (size_t)du.y;
       cp_async16(&sb->cell[0][lane], pm); cp_async16(&sb->cell[1][lane], pm + 1); cp_async16(&sb->cell[2][lane], pm + 2);
       cp_async16(&sb->cell[3][lane], pf); cp_async16(&sb->cell[4][lane], pf + 1); cp_async16(&sb->cell[5][lane], pf + 2);
+      if (du.z != kNoCell) {
+        const float4* pg = P.cells_f + 3 * (size_t)du.z;
+        cp_async16(&sb->cell[6][lane], pg); cp_async16(&sb->cell[7][lane], pg + 1); cp_async16(&sb->cell[8][lane], pg + 2);
+      }
+      sb->duo[lane] = du;
     }
     if (lane == 0) {
       const bool first = g.i == g.begin;
@@ -395,9 +436,9 @@ __device__ __forceinline__ void stage_issue(const DeviceProblem& P, const TileSt
 }
 
 template <int VARIANT, int LOSS, bool WANT_JAC>
-__global__ void __launch_bounds__(kK3Threads, 4) k3_fused_kernel(DeviceProblem P, const double* __restrict__ poses, LossParams lp,
-                                                                const double* __restrict__ mu_per_seg, double* __restrict__ out,
-                                                                unsigned long long* __restrict__ bad_counter) {
+__global__ void __launch_bounds__(kK3Threads, kMinCtas) k3_fused_kernel(DeviceProblem P, const double* __restrict__ poses, LossParams lp,
+                                                                       const double* __restrict__ mu_per_seg, double* __restrict__ out,
+                                                                       unsigned long long* __restrict__ bad_counter) {
   constexpr int NB = VarTraits<VARIANT>::NB;
   constexpr int NP = VarTraits<VARIANT>::NP;
   constexpr int NH = NB * (NB + 1) / 2;
@@ -413,15 +454,13 @@ __global__ void __launch_bounds__(kK3Threads, 4) k3_fused_kernel(DeviceProblem P
 
   TileStream gen;
   gen.init(P.tiles, P.n_tiles, w, n_warps);
-  // prologue: chunks 0 .. kStages-2 in flight, pair indices of chunk kStages-1 in registers
-  uint2 pr = make_uint2(0, 0);
-  if (gen.valid() && gen.i + lane < gen.end) pr = P.pairs[gen.i + lane];
+  // prologue: chunks 0 .. kStages-2 in flight, duo records of chunk kStages-1 in registers
+  uint4 du = gen.fetch_duo(P.duos, lane);
 #pragma unroll
   for (int s = 0; s < kStages - 1; ++s) {
-    stage_issue<NP>(P, gen, pr, lane, &stage[s], poses, mu_per_seg);
+    stage_issue<NP>(P, gen, du, lane, &stage[s], poses, mu_per_seg);
     gen.advance();
-    pr = make_uint2(0, 0);
-    if (gen.valid() && gen.i + lane < gen.end) pr = P.pairs[gen.i + lane];
+    du = gen.fetch_duo(P.duos, lane);
   }
 
   PoseConst kc; LossConst lc;
@@ -430,12 +469,11 @@ __global__ void __launch_bounds__(kK3Threads, 4) k3_fused_kernel(DeviceProblem P
   for (int e = 0; e < NS; ++e) acc[e] = 0.0;
   int slot = 0;
   while (true) {
-    // ---- stage chunk j + kStages - 1, fetch the pair indices of chunk j + kStages ----
+    // ---- stage chunk j + kStages - 1, fetch the duo records of chunk j + kStages ----
     int islot = slot + kStages - 1; if (islot >= kStages) islot -= kStages;
-    stage_issue<NP>(P, gen, pr, lane, &stage[islot], poses, mu_per_seg);
+    stage_issue<NP>(P, gen, du, lane, &stage[islot], poses, mu_per_seg);
     gen.advance();
-    pr = make_uint2(0, 0);
-    if (gen.valid() && gen.i + lane < gen.end) pr = P.pairs[gen.i + lane];
+    du = gen.fetch_duo(P.duos, lane);
     // ---- chunk j has landed ----
     cp_async_wait<kStages - 1>();
     __syncwarp();
@@ -447,29 +485,41 @@ __global__ void __launch_bounds__(kK3Threads, 4) k3_fused_kernel(DeviceProblem P
       make_loss_const(lp, mu_per_seg ? sb->mu : lp.mu, lc);
     }
     if (cm.i + lane < cm.end) {
-      RawCell m, f;
+      RawCell m, f[2];
       m.a = sb->cell[0][lane]; m.b = sb->cell[1][lane]; m.c = sb->cell[2][lane];
-      f.a = sb->cell[3][lane]; f.b = sb->cell[4][lane]; f.c = sb->cell[5][lane];
-      double N[4];
-      const double dd = pair_core<VARIANT, WANT_JAC>(kc, m, f, N);
-      if (dd_valid(dd)) {
-        double wgt, hrho, wd;
-        loss_eval<LOSS>(dd, lc, wgt, hrho, wd);
-        if (WANT_JAC) {
-          int q = 0;
+      f[0].a = sb->cell[3][lane]; f[0].b = sb->cell[4][lane]; f[0].c = sb->cell[5][lane];
+      f[1].a = sb->cell[6][lane]; f[1].b = sb->cell[7][lane]; f[1].c = sb->cell[8][lane];
+      const bool two = sb->duo[lane].z != kNoCell;
+      Moving mv;
+      moving_part<VARIANT>(kc, m, mv);
+      double dd[2], N[2][4], wgt[2], hrho[2], wd[2];
+      bool ok[2];
 #pragma unroll
-          for (int a = 0; a < NB; ++a) {
-            const double wa = wd * N[a];
+      for (int j = 0; j < 2; ++j) dd[j] = fixed_part<VARIANT, WANT_JAC>(kc, mv, f[j], N[j]);
 #pragma unroll
-            for (int b2 = a; b2 < NB; ++b2) { acc[q] = fma(wa, N[b2], acc[q]); ++q; }
-            acc[NH + a] = fma(wgt, N[a], acc[NH + a]);
+      for (int j = 0; j < 2; ++j) {
+        ok[j] = dd_valid(dd[j]);
+        loss_eval<LOSS>(dd[j], lc, wgt[j], hrho[j], wd[j]);
+      }
+      const bool use1 = two && ok[1];
+      n_bad += (ok[0] ? 0u : 1u) + ((two && !ok[1]) ? 1u : 0u);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        if (j == 0 ? ok[0] : use1) {
+          if (WANT_JAC) {
+            int q = 0;
+#pragma unroll
+            for (int a = 0; a < NB; ++a) {
+              const double wa = wd[j] * N[j][a];
+#pragma unroll
+              for (int b2 = a; b2 < NB; ++b2) { acc[q] = fma(wa, N[j][b2], acc[q]); ++q; }
+              acc[NH + a] = fma(wgt[j], N[j][a], acc[NH + a]);
+            }
           }
+          acc[NJ] += hrho[j];
+          acc[NJ + 1] += dd[j];
+          max_dd = fmax(max_dd, dd[j]);
         }
-        acc[NJ] += hrho;
-        acc[NJ + 1] += dd;
-        max_dd = fmax(max_dd, dd);
-      } else {
-        ++n_bad;
       }
     }
     // ---- tile finished: reduce across the warp and emit ----
@@ -485,7 +535,7 @@ __global__ void __launch_bounds__(kK3Threads, 4) k3_fused_kernel(DeviceProblem P
 #pragma unroll
           for (int e = 0; e < NH + NB; ++e) rec[e] = WANT_JAC ? acc[e < NS ? e : 0] : 0.0;
           rec[NH + NB] = acc[NJ]; rec[NH + NB + 1] = acc[NJ + 1];
-          write_segment_out<VARIANT>(rec, mx, kc, cm.end - P.tiles[t].begin, out + (size_t)seg * RANDT_FUSED_STRIDE);
+          write_segment_out<VARIANT>(rec, mx, kc, P.seg_off[seg + 1] - P.seg_off[seg], out + (size_t)seg * RANDT_FUSED_STRIDE);
           if (bad) atomicAdd(bad_counter, (unsigned long long)bad);
         }
       } else {
@@ -515,12 +565,11 @@ __global__ void __launch_bounds__(kK3Threads, 4) k3_fused_kernel(DeviceProblem P
           const double mx_all = __shfl_sync(kFull, v, NS);
           const double bad_all = __shfl_sync(kFull, v, NS + 1);
           if (lane == 0) {
-            const uint32_t pb = P.tiles[first].begin, pe = P.tiles[first + seg_tiles - 1].end;
             double rec[NH + NB + 2];
 #pragma unroll
             for (int e = 0; e < NH + NB; ++e) rec[e] = WANT_JAC ? tot[e < NS ? e : 0] : 0.0;
             rec[NH + NB] = tot[NJ]; rec[NH + NB + 1] = tot[NJ + 1];
-            write_segment_out<VARIANT>(rec, mx_all, kc, pe - pb, out + (size_t)seg * RANDT_FUSED_STRIDE);
+            write_segment_out<VARIANT>(rec, mx_all, kc, P.seg_off[seg + 1] - P.seg_off[seg], out + (size_t)seg * RANDT_FUSED_STRIDE);
             if (bad_all != 0.0) atomicAdd(bad_counter, (unsigned long long)bad_all);
             P.seg_counters[seg] = 0u;   // re-arm for the next launch
           }
@@ -538,8 +587,32 @@ __global__ void __launch_bounds__(kK3Threads, 4) k3_fused_kernel(DeviceProblem P
 
 // EMIT: raw residual and ambient Jacobian row per pair (what Evaluate returns for each block); same tile stream, no reduction
 template <int VARIANT, bool WANT_JAC>
-__global__ void __launch_bounds__(kK3Threads, 4) k3_emit_kernel(DeviceProblem P, const double* __restrict__ poses, double* __restrict__ r_out,
-                                                               double* __restrict__ J_out, unsigned long long* __restrict__ bad_counter) {
+__device__ __forceinline__ void emit_one(const PoseConst& kc, uint32_t i, double dd, const double* N, double* __restrict__ r_out,
+                                         double* __restrict__ J_out, uint32_t& n_bad) {
+  const bool ok = dd_valid(dd);
+  double r = 0.0, rs = 0.0;   // r = 0: the reference's dual-number sqrt yields 0/0 here; defined as J = 0
+  if (ok && dd > 0.0) { rs = rsqrt_fast(dd); r = dd * rs; }
+  if (!ok) { ++n_bad; r = __longlong_as_double(0x7ff8000000000000ll); }
+  r_out[i] = r;
+  if (WANT_JAC) {
+    if (VARIANT == 0) {
+      double2* dst = reinterpret_cast<double2*>(J_out + (size_t)i * 4);
+      const double jt = N[0] * rs;
+      dst[0] = make_double2(jt * kc.ja, jt * kc.jb);
+      dst[1] = make_double2(N[1] * rs, N[2] * rs);
+    } else if (VARIANT == 1) {
+      double2* dst = reinterpret_cast<double2*>(J_out + (size_t)i * 4);
+      dst[0] = make_double2(N[0] * rs, N[1] * rs);
+      dst[1] = make_double2(N[2] * rs, N[3] * rs);
+    } else {
+      J_out[(size_t)i * 3 + 0] = N[0] * rs; J_out[(size_t)i * 3 + 1] = N[1] * rs; J_out[(size_t)i * 3 + 2] = N[2] * rs;
+    }
+  }
+}
+
+template <int VARIANT, bool WANT_JAC>
+__global__ void __launch_bounds__(kK3Threads, kMinCtas) k3_emit_kernel(DeviceProblem P, const double* __restrict__ poses, double* __restrict__ r_out,
+                                                                      double* __restrict__ J_out, unsigned long long* __restrict__ bad_counter) {
   constexpr int NP = VarTraits<VARIANT>::NP;
   __shared__ StageBuf stage_all[kWarpsPerCta][kStages];
   const int lane = threadIdx.x & 31;
@@ -550,55 +623,41 @@ __global__ void __launch_bounds__(kK3Threads, 4) k3_emit_kernel(DeviceProblem P,
   StageBuf* stage = stage_all[warp];
   TileStream gen;
   gen.init(P.tiles, P.n_tiles, w, n_warps);
-  uint2 pr = make_uint2(0, 0);
-  if (gen.valid() && gen.i + lane < gen.end) pr = P.pairs[gen.i + lane];
+  uint4 du = gen.fetch_duo(P.duos, lane);
 #pragma unroll
   for (int s = 0; s < kStages - 1; ++s) {
-    stage_issue<NP>(P, gen, pr, lane, &stage[s], poses, nullptr);
+    stage_issue<NP>(P, gen, du, lane, &stage[s], poses, nullptr);
     gen.advance();
-    pr = make_uint2(0, 0);
-    if (gen.valid() && gen.i + lane < gen.end) pr = P.pairs[gen.i + lane];
+    du = gen.fetch_duo(P.duos, lane);
   }
   PoseConst kc;
   uint32_t n_bad = 0;
   int slot = 0;
   while (true) {
     int islot = slot + kStages - 1; if (islot >= kStages) islot -= kStages;
-    stage_issue<NP>(P, gen, pr, lane, &stage[islot], poses, nullptr);
+    stage_issue<NP>(P, gen, du, lane, &stage[islot], poses, nullptr);
     gen.advance();
-    pr = make_uint2(0, 0);
-    if (gen.valid() && gen.i + lane < gen.end) pr = P.pairs[gen.i + lane];
+    du = gen.fetch_duo(P.duos, lane);
     cp_async_wait<kStages - 1>();
     __syncwarp();
     const StageBuf* sb = &stage[slot];
     const ChunkMeta cm = sb->meta;
     if (cm.t == 0xffffffffu) break;
     if (sb->first) make_pose_const<VARIANT>(sb->pose, kc);
-    const uint32_t i = cm.i + lane;
-    if (i < cm.end) {
-      RawCell m, f;
+    if (cm.i + lane < cm.end) {
+      RawCell m, f0, f1;
       m.a = sb->cell[0][lane]; m.b = sb->cell[1][lane]; m.c = sb->cell[2][lane];
-      f.a = sb->cell[3][lane]; f.b = sb->cell[4][lane]; f.c = sb->cell[5][lane];
+      f0.a = sb->cell[3][lane]; f0.b = sb->cell[4][lane]; f0.c = sb->cell[5][lane];
+      const uint4 d = sb->duo[lane];
+      Moving mv;
+      moving_part<VARIANT>(kc, m, mv);
       double N[4] = {0.0, 0.0, 0.0, 0.0};
-      const double dd = pair_core<VARIANT, WANT_JAC>(kc, m, f, N);
-      const bool ok = dd_valid(dd);
-      double r = 0.0, rs = 0.0;   // r = 0: the reference's dual-number sqrt yields 0/0 here; defined as J = 0
-      if (ok && dd > 0.0) { rs = rsqrt_fast(dd); r = dd * rs; }
-      if (!ok) { ++n_bad; r = __longlong_as_double(0x7ff8000000000000ll); }
-      r_out[i] = r;
-      if (WANT_JAC) {
-        if (VARIANT == 0) {
-          double2* dst = reinterpret_cast<double2*>(J_out + (size_t)i * 4);
-          const double jt = N[0] * rs;
-          dst[0] = make_double2(jt * kc.ja, jt * kc.jb);
-          dst[1] = make_double2(N[1] * rs, N[2] * rs);
-        } else if (VARIANT == 1) {
-          double2* dst = reinterpret_cast<double2*>(J_out + (size_t)i * 4);
-          dst[0] = make_double2(N[0] * rs, N[1] * rs);
-          dst[1] = make_double2(N[2] * rs, N[3] * rs);
-        } else {
-          J_out[(size_t)i * 3 + 0] = N[0] * rs; J_out[(size_t)i * 3 + 1] = N[1] * rs; J_out[(size_t)i * 3 + 2] = N[2] * rs;
-        }
+      const double dd0 = fixed_part<VARIANT, WANT_JAC>(kc, mv, f0, N);
+      emit_one<VARIANT, WANT_JAC>(kc, d.w, dd0, N, r_out, J_out, n_bad);
+      if (d.z != kNoCell) {
+        f1.a = sb->cell[6][lane]; f1.b = sb->cell[7][lane]; f1.c = sb->cell[8][lane];
+        const double dd1 = fixed_part<VARIANT, WANT_JAC>(kc, mv, f1, N);
+        emit_one<VARIANT, WANT_JAC>(kc, d.w + 1u, dd1, N, r_out, J_out, n_bad);
       }
     }
     __syncwarp();
@@ -662,7 +721,7 @@ int loss_code(const LossParams& lp) {
 }
 
 inline int stream_grid(uint32_t n_tiles) {
-  const uint32_t full = (uint32_t)kSmCount * 4u;   // 4 CTAs of 4 warps per SM (128 registers per thread)
+  const uint32_t full = (uint32_t)kSmCount * (uint32_t)kMinCtas;   // resident CTAs (4 warps each) the register bound allows
   const uint32_t need = (n_tiles + kWarpsPerCta - 1) / kWarpsPerCta;
   return (int)(need < full ? need : full);
 }
