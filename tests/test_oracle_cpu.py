@@ -1,0 +1,266 @@
+"""CPU tests of the oracle (oracle/): pins the restatement before it is trusted as the checker of the CUDA path.
+
+ 1. against the committed golden vectors (tests/golden/ndt_golden.json: 50-digit mpmath evaluation of the reference's
+    definitions, generator beside it) — residuals/Jacobians of all four functor variants, Barron/Welsch rho/rho'/rho'', voxel
+    labels, cell statistics, cell merge;
+ 2. three-way self-consistency: dual-number (what ceres executes) == closed form == central finite differences;
+ 3. the reference quirks of SURVEY.md Appendix B that the path must reproduce;
+ 4. the restated ceres LM / GNC driver recovers a known pose.
+The reference ships no tests or fixtures for this path, so these are the only pins ("parity unpinned").
+"""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from randt_slam_b200 import params as P, synth
+from tests import helpers as H
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ndt_golden.json")
+
+
+@pytest.fixture(scope="module")
+def golden():
+    with open(GOLDEN) as f:
+        return json.load(f)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 1. golden vectors
+# ---------------------------------------------------------------------------------------------------------------------
+def test_golden_residuals_and_jacobians(oracle, golden):
+    """tolerance: north_star's 1e-5 relative; asserted 1e-9 (the oracle evaluates in fp64 like the reference)"""
+    assert len(golden["pairs"]) >= 24
+    for c in golden["pairs"]:
+        cm = np.array(c["cell_m"], np.float32)[None]; cf = np.array(c["cell_f"], np.float32)[None]
+        for mode in ((0, 1) if c["variant"] == 0 else (0,)):      # 0 = dual numbers, 1 = closed form (variant 0 only)
+            r, J = oracle.eval_pairs(c["variant"], cm, cf, [0], [0], np.array(c["params"]), mode)
+            assert abs(r[0] - c["r"]) <= 1e-9 * c["r"], (c["variant"], mode)
+            scale = max(abs(v) for v in c["J"])
+            assert np.max(np.abs(J[0] - np.array(c["J"]))) <= 1e-9 * scale, (c["variant"], mode)
+        r2, _ = oracle.eval_pairs(c["variant"], cm, cf, [0], [0], np.array(c["params"]), 2)   # plain-double functor call
+        assert abs(r2[0] - c["r"]) <= 1e-9 * c["r"]
+
+
+def test_golden_losses(oracle, golden):
+    for c in golden["losses"]:
+        kind = oracle.LOSS_BARRON if c["kind"] == "barron" else oracle.LOSS_WELSCH
+        rho = oracle.loss_eval(kind, c["a"], c["alpha"], c["mu"], 1.0, c["s"])
+        # rho = pre * (u^e - 1) cancels for small s (in the reference too): absolute floor of a few ulps of pre_factor
+        floor = 1e-15 * 4.0 * c["mu"] * c["a"] ** 2
+        for got, want in zip(rho, c["rho"]):
+            assert abs(got - want) <= 1e-12 * abs(want) + floor, c
+        # ScaledLoss multiplies all three
+        rho_w = oracle.loss_eval(kind, c["a"], c["alpha"], c["mu"], 0.37, c["s"])
+        assert np.allclose(rho_w, 0.37 * rho, rtol=1e-15, atol=0)
+
+
+def test_golden_labels(oracle, golden):
+    for c in golden["labels"]:
+        assert oracle.n_clusters(c["max_range"], c["resolution"]) == c["n_clusters"]
+        pts = np.zeros((len(c["xy"]), 4), np.float32); pts[:, :2] = np.array(c["xy"], np.float32)
+        lab = oracle.grid_labels(pts, c["n_clusters"], c["max_range"])
+        assert lab.tolist() == c["labels"]
+
+
+def test_golden_cell_statistics(oracle, golden):
+    """float32 sequential accumulation vs exact arithmetic: 1e-5 relative to the matrix scale (north_star tolerance)"""
+    for c in golden["cell_stats"]:
+        pts = np.array(c["points"], np.float32)
+        cell = oracle.cell_from_points(pts, 5)
+        assert cell is not None
+        assert np.max(np.abs(cell[:3] - np.array(c["mean"])) / np.abs(np.array(c["mean"]))) < 1e-5
+        cov = cell[3:].reshape(3, 3).astype(np.float64); want = np.array(c["cov"])
+        tol = 1e-5 if not c["floor_active"] else 2e-3   # thin clusters: float32 cancellation in the minor eigen-direction
+        assert np.max(np.abs(cov[:2, :2] - want[:2, :2])) <= tol * np.max(np.abs(want[:2, :2]))
+        assert np.max(np.abs(cov[2] - want[2])) <= 1e-5 * np.max(np.abs(want[2]))
+        ev = np.linalg.eigvalsh(0.5 * (cov[:2, :2] + cov[:2, :2].T))
+        assert ev[0] >= 0.999e-3 * ev[1]        # the eigenvalue floor (ndt_cell.cpp:107)
+
+
+def test_golden_cell_merge(oracle, golden):
+    for c in golden["merges"]:
+        a = np.array(c["a"], np.float32)[None]; b = np.array(c["b"], np.float32)[None]
+        slot = np.full(4, -1, np.int32)
+        # put both cells in slot 0 of a tiny 2x2 map around the origin
+        a0 = a.copy(); b0 = b.copy()
+        shift = a0[0, :2].copy()
+        a0[0, :2] -= shift; b0[0, :2] -= shift
+        a0[0, :2] = [0.2, 0.2]; b0[0, :2] = a0[0, :2] + (b[0, :2] - a[0, :2])
+        if not (0 <= b0[0, 0] < 1 and 0 <= b0[0, 1] < 1):
+            b0[0, :2] = [0.3, 0.4]
+        size, res = 2, 1.0
+        cells, npts, slot = oracle.merge_map_cell(np.zeros((0, 12), np.float32), np.zeros(0, np.uint32), slot, size, size, res, a0, [c["n1"]])
+        cells, npts, slot = oracle.merge_map_cell(cells, npts, slot, size, size, res, b0, [c["n2"]])
+        assert len(cells) == 1 and npts[0] == c["n1"] + c["n2"]
+        # exact value of the reference's formula on these (shifted) inputs
+        n1, n2 = c["n1"], c["n2"]
+        A = a0[0].astype(np.float64); B = b0[0].astype(np.float64)
+        w3 = (n1 * n2) // (n1 + n2)                                          # unsigned integer division (quirk B.4)
+        d = A[:3] - B[:3]
+        cov = ((n1 - 1) * A[3:].reshape(3, 3) + (n2 - 1) * B[3:].reshape(3, 3) + w3 * np.outer(d, d)) / (n1 + n2 - 1)
+        mu = (A[:3] * n1 + B[:3] * n2) / (n1 + n2)
+        assert np.max(np.abs(cells[0, :3] - mu)) <= 1e-5 * np.max(np.abs(mu))
+        assert np.max(np.abs(cells[0, 3:].reshape(3, 3) - cov)) <= 1e-5 * np.max(np.abs(cov))
+        # and the real-division variant differs measurably, i.e. the quirk is observable
+        w3r = n1 * n2 / (n1 + n2)
+        if abs(w3r - w3) > 0.3 and np.max(np.abs(np.outer(d, d))) > 1e-3:
+            cov_r = ((n1 - 1) * A[3:].reshape(3, 3) + (n2 - 1) * B[3:].reshape(3, 3) + w3r * np.outer(d, d)) / (n1 + n2 - 1)
+            assert np.max(np.abs(cells[0, 3:].reshape(3, 3) - cov_r)) > 1e-7 * np.max(np.abs(cov))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 2. three-way agreement on scan-derived pairs
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("preset", ["oxford", "c1"])
+def test_dual_closed_form_finite_difference_agree(oracle, preset):
+    p = {"oxford": P.OXFORD, "c1": P.C1}[preset]
+    case = H.make_registration_case(oracle, p, seed=3)
+    cm, cf, im, jf = case["moving"]["cells"], case["fixed"]["cells"], case["im"], case["jf"]
+    assert len(im) > 50
+    pose = case["pose0"].copy(); pose[:2] *= 1.0004
+    r0, J0 = oracle.eval_pairs(0, cm, cf, im, jf, pose, 0)
+    r1, J1 = oracle.eval_pairs(0, cm, cf, im, jf, pose, 1)
+    assert np.max(np.abs(r0 - r1) / r0) < 1e-11
+    scale = np.max(np.abs(J0), axis=1, keepdims=True)
+    assert np.max(np.abs(J0 - J1) / scale) < 1e-9
+    for i in range(4):
+        h = 1e-6
+        pp, pm = pose.copy(), pose.copy(); pp[i] += h; pm[i] -= h
+        rp, _ = oracle.eval_pairs(0, cm, cf, im, jf, pp, 2); rm, _ = oracle.eval_pairs(0, cm, cf, im, jf, pm, 2)
+        fd = (rp - rm) / (2 * h)
+        assert np.max(np.abs(fd - J0[:, i]) / scale[:, 0]) < 1e-6
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3])
+def test_other_variants_match_finite_differences(oracle, variant):
+    rng = np.random.default_rng(variant)
+    cm = H.random_cells(rng, 50, extent=4.0); cf = H.random_cells(rng, 50, extent=4.0)
+    im = np.arange(50, dtype=np.uint32); jf = rng.permutation(50).astype(np.uint32)
+    params = np.array([0.98, 0.21, 0.3, -0.2]) if variant == 1 else np.array([0.3, -0.2, 0.21])
+    r0, J0 = oracle.eval_pairs(variant, cm, cf, im, jf, params, 0)
+    scale = np.max(np.abs(J0), axis=1)
+    for i in range(len(params)):
+        h = 1e-6
+        pp, pm = params.copy(), params.copy(); pp[i] += h; pm[i] -= h
+        rp, _ = oracle.eval_pairs(variant, cm, cf, im, jf, pp, 2); rm, _ = oracle.eval_pairs(variant, cm, cf, im, jf, pm, 2)
+        assert np.max(np.abs((rp - rm) / (2 * h) - J0[:, i]) / scale) < 1e-6
+
+
+def test_invariances(oracle):
+    """d is invariant under a common rigid motion of both distributions; intensity is not transformed (ceres_residuals.h:541-547)"""
+    rng = np.random.default_rng(5)
+    cm = H.random_cells(rng, 40, extent=5.0); cf = H.random_cells(rng, 40, extent=5.0)
+    idx = np.arange(40, dtype=np.uint32)
+    pose = synth.pose_to_se2(0.3, -0.1, 0.2)
+    r, _ = oracle.eval_pairs(0, cm, cf, idx, idx, pose, 2)
+    # moving the fixed cells by G and composing the pose with G leaves r unchanged (up to the float32 rounding of the moved cells)
+    g = (1.5, -0.7, 0.4)
+    cfg = oracle.transform_cells(cf, math.cos(g[2]), math.sin(g[2]), g[0], g[1])
+    c, s = math.cos(g[2]), math.sin(g[2])
+    th = 0.2 + g[2]
+    tx = c * 0.3 - s * (-0.1) + g[0]; ty = s * 0.3 + c * (-0.1) + g[1]
+    r2, _ = oracle.eval_pairs(0, cm, cfg, idx, idx, synth.pose_to_se2(tx, ty, th), 2)
+    assert np.max(np.abs(r - r2) / r) < 5e-4
+    assert np.all(r >= 0)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 3. reference quirks
+# ---------------------------------------------------------------------------------------------------------------------
+def test_label_truncation_toward_zero_and_negative_labels(oracle):
+    p = P.C1   # 32 x 32 grid, res 1.0
+    pts = np.zeros((4, 4), np.float32)
+    pts[:, :2] = [[0.4, 0.4], [-0.4, 0.4], [-0.4, -0.4], [-1.5, -2.5]]
+    lab = oracle.grid_labels(pts, p.n_clusters, p.max_range)
+    assert lab[0] == lab[1] == lab[2] == 0          # B.1: the cells straddling the axes are double-width
+    assert lab[3] == -1 + 32 * -2                   # negative labels exist
+
+
+def test_min_points_is_strict_and_population_covariance(oracle):
+    rng = np.random.default_rng(0)
+    pts = np.zeros((6, 4), np.float32); pts[:, :2] = rng.normal(0, 1, (6, 2)); pts[:, 3] = rng.uniform(70, 200, 6)
+    assert oracle.cell_from_points(pts[:5], 5) is None          # B.2: needs n > min_points
+    cell = oracle.cell_from_points(pts, 5)
+    assert cell is not None
+    xy = pts[:, :2].astype(np.float64)
+    pop = np.cov(xy.T, bias=True)                              # B.3: /n
+    assert abs(cell[3 + 8] - (np.var(pts[:, 3].astype(np.float64)) + 1e-6)) < 1e-3
+    assert np.allclose(cell[3:].reshape(3, 3)[:2, :2], pop, rtol=1e-4, atol=1e-6)
+
+
+def test_later_cluster_overwrites_slot_but_both_cells_stay(oracle):
+    """B.7: two clusters whose means share a map slot (cluster grid and map grid are different lattices)"""
+    p = P.OXFORD
+    rng = np.random.default_rng(3)
+    grid_res = 2 * p.max_range / p.grid_row_size     # 3.5088 vs map res 3.5
+    # clusters in label cells 1 and 2 along x, means pushed towards their common boundary so both fall in one 3.5 m map slot
+    a = np.zeros((12, 4), np.float32); b = np.zeros((12, 4), np.float32)
+    a[:, 0] = 2 * grid_res - rng.uniform(0.01, 0.2, 12); a[:, 1] = rng.uniform(0.2, 1.0, 12); a[:, 3] = 90
+    b[:, 0] = 2 * grid_res + rng.uniform(0.001, 0.005, 12); b[:, 1] = rng.uniform(0.2, 1.0, 12); b[:, 3] = 95
+    v = oracle.voxelize(np.concatenate([a, b]), *H.vox_args(p))
+    assert len(v["cells"]) == 2
+    s0 = oracle.coord_to_index(p.size_x, p.size_y, p.resolution, v["cells"][0, 0], v["cells"][0, 1])
+    s1 = oracle.coord_to_index(p.size_x, p.size_y, p.resolution, v["cells"][1, 0], v["cells"][1, 1])
+    if s0 == s1:
+        assert v["slot"][s0] == 1
+    assert int(np.sum(v["slot"] >= 0)) == (1 if s0 == s1 else 2)
+
+
+def test_association_window_schedule(oracle):
+    """B.9: the radius grows until >= k candidates or r + 1 >= int(max_linf / res); all occupied slots of the final window count"""
+    p = P.OXFORD   # r_stop = int(10 / 3.5) = 2 -> radii 0 and 1 only
+    assert p.r_stop == 2
+    size = p.size_x
+    slot = np.full(size * size, -1, np.int32)
+    cells = np.zeros((3, 12), np.float32)
+    for i, (dx, dy) in enumerate([(0, 0), (1, 0), (2, 0)]):
+        cells[i, :3] = [1.75 + 3.5 * dx, 1.75 + 3.5 * dy, 100.0]; cells[i, 3:] = np.diag([1.0, 1.0, 100.0]).reshape(9)
+        slot[oracle.coord_to_index(size, size, p.resolution, cells[i, 0], cells[i, 1])] = i
+    q = cells[:1].copy()
+    pose = synth.pose_to_se2(0, 0, 0)
+    im, jf = oracle.associate(cells, slot, size, size, p.resolution, p.max_neighbor_linf_distance, q, pose, 2)
+    assert jf.tolist() == [0, 1]            # the cell two slots away is never reached (r stops at 1)
+    im, jf = oracle.associate(cells, slot, size, size, p.resolution, p.max_neighbor_linf_distance, q, pose, 3)
+    assert jf.tolist() == [0, 1]
+
+
+def test_gnc_schedule(oracle):
+    """ndt_matcher.cpp:386-397: mu0 = min(2 max_r^2 / a^2, div^(steps-1)); do { mu = max(mu,1); solve; mu /= div } while (mu > 1/sqrt(div))"""
+    assert oracle.gnc_initial_mu(3.0, 1.0, 1.1, 2) == pytest.approx(1.1)
+    assert oracle.gnc_initial_mu(0.1, 1.0, 1.3, 3) == pytest.approx(0.02)
+    mu = oracle.gnc_initial_mu(3.0, 1.0, 1.1, 2); solves = 0
+    while True:
+        mu = max(mu, 1.0); solves += 1; mu /= 1.1
+        if not mu > 1.0 / math.sqrt(1.1):
+            break
+    assert solves == 2
+
+
+def test_corrector_concave_loss_reduces_to_sqrt_rho1(oracle):
+    rho = oracle.loss_eval(oracle.LOSS_BARRON, 1.0, -2.0, 1.0, 1.0, 4.0)
+    assert rho[2] <= 0                                   # Barron alpha < 2 is concave
+    c = oracle.corrector(4.0, rho)
+    assert c[0] == pytest.approx(math.sqrt(rho[1])) and c[1] == pytest.approx(math.sqrt(rho[1])) and c[2] == 0.0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 4. LM / GNC driver
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("on_manifold", [False, True])
+def test_loop_constraint_recovers_pose(oracle, on_manifold):
+    p = P.OXFORD
+    true = (0.6, -0.4, 0.03)
+    case = H.make_registration_case(oracle, p, seed=8, n_fixed_scans=5, true_pose=true, guess=(0.2, -0.1, 0.01))
+    f = case["fixed"]
+    res = oracle.loop_constraint(f["cells"], f["slot"], p.size_x, p.size_y, p.resolution, p.max_neighbor_linf_distance,
+                                 case["moving"]["cells"], case["pose0"], p.n_results_nn_lookup, matcher_loss_scale=p.loss_function_scale,
+                                 loop_scale=p.loop_closure_scale, alpha=p.loss_function_convexity, divisor=p.gnc_control_parameter_divisor,
+                                 max_gnc_steps=p.loop_closure_gnc_steps, on_manifold=on_manifold)
+    assert res["status"] == 0 and res["gnc_solves"] >= 1
+    th = math.atan2(res["pose"][1], res["pose"][0])
+    assert abs(res["pose"][2] - true[0]) < 0.15 and abs(res["pose"][3] - true[1]) < 0.15 and abs(th - true[2]) < 0.01
+    if on_manifold:
+        assert abs(math.hypot(res["pose"][0], res["pose"][1]) - 1.0) < 1e-12
