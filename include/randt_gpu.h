@@ -178,6 +178,54 @@ RANDT_API int randt_eval_fused_dev(randt_ctx* ctx, const randt_problem* p, int v
 RANDT_API int randt_sweep_costs(randt_ctx* ctx, const randt_problem* p, uint32_t seg, int variant, const double* poses, uint32_t n_poses,
                                 const randt_loss* loss, double* cost);
 
+/* ---- K4: batched GNC + Levenberg-Marquardt registration ------------------------------------------------
+ * Replaces, for every segment (= one registration) of the problem at once, the solve half of Matcher::estimateLoopConstraint
+ * (R/src/ndt_registration/ndt_matcher.cpp:457-492; the same loop closes Matcher::estimateTransformCeres, :372-397): raw residual
+ * maximum -> mu0 = min(2 max_r^2 / gnc_loss_scale^2, gnc_divisor^(gnc_max_steps-1)); do { mu = max(mu, 1); ceres::Solve (trust
+ * region, LEVENBERG_MARQUARDT, dense) with loss ScaledLoss(Barron(loss->scale, loss->alpha, mu), loss->weight); mu /= gnc_divisor }
+ * while (mu > 1/sqrt(gnc_divisor)).  Defaults of the solver fields are ceres 2.1.0's Solver::Options defaults plus the
+ * reference's max_num_iterations (ndt_radar_slam_base_parameters.yaml: max_iteration). */
+typedef struct randt_solver_options {
+  int32_t max_num_iterations;                 /* 200 */
+  int32_t use_manifold;                       /* 1: Sophus::Manifold<SE2> on the 4-parameter pose (estimateTransformCeres, ndt_matcher.cpp:334);
+                                                 0: raw ambient parameters — what estimateLoopConstraint ends up optimising */
+  int32_t max_num_consecutive_invalid_steps;  /* 5 */
+  int32_t jacobi_scaling;                     /* 1 */
+  double function_tolerance;                  /* 1e-6 */
+  double gradient_tolerance;                  /* 1e-10 */
+  double parameter_tolerance;                 /* 1e-8 */
+  double initial_trust_region_radius;         /* 1e4 */
+  double max_trust_region_radius;             /* 1e16 */
+  double min_trust_region_radius;             /* 1e-32 */
+  double min_lm_diagonal, max_lm_diagonal;    /* 1e-6, 1e32 */
+  double min_relative_decrease;               /* 1e-3 */
+  double gnc_loss_scale;                      /* ndt_matcher/loss_function_scale (the scale in mu0, ndt_matcher.cpp:386,473) */
+  double gnc_divisor;                         /* ndt_matcher/gnc_control_parameter_divisor */
+  int32_t gnc_max_steps;                      /* gnc_steps / loop_closure gnc steps */
+  int32_t poll_interval;                      /* LM iterations between host polls of the active-segment counter (0: default) */
+} randt_solver_options;
+RANDT_API void randt_solver_options_default(randt_solver_options* o);
+
+/* per-segment result record of randt_register_batch: 8 float64 */
+enum {
+  RANDT_REG_SCORE = 0,        /* summary.final_cost / num_residual_blocks of the last solve (return value of estimateLoopConstraint, :492) */
+  RANDT_REG_FINAL_COST = 1,
+  RANDT_REG_GNC_SOLVES = 2,   /* ceres::Solve calls */
+  RANDT_REG_ITERATIONS = 3,   /* minimiser iterations over all solves (iteration 0 of each solve included) */
+  RANDT_REG_EVALS = 4,        /* cost + Jacobian evaluations ceres would have made */
+  RANDT_REG_MU_FIRST = 5,     /* mu0 before the max(mu, 1) clamp */
+  RANDT_REG_STATUS = 6,       /* 0 ok, 1 the segment has no residual blocks ("NO RESIDUALS ADDED", :454-456): pose returned unchanged */
+  RANDT_REG_TERMINATION = 7,  /* last solve: 0 convergence, 1 iteration limit, 2 failure */
+  RANDT_REG_STRIDE = 8
+};
+/* poses: [n_segments][np] initial guesses in, refined poses out; result: [n_segments][RANDT_REG_STRIDE].  loss->mu is ignored (the GNC
+ * schedule sets it per segment).  The whole batch advances in lock step: one K3 launch + one K4 launch per LM iteration over the
+ * segments still active; nothing but an active counter crosses PCIe until every segment has finished.  *_dev: device pointers. */
+RANDT_API int randt_register_batch(randt_ctx* ctx, const randt_problem* p, int variant, double* poses, const randt_loss* loss,
+                                   const randt_solver_options* opt, double* result);
+RANDT_API int randt_register_batch_dev(randt_ctx* ctx, const randt_problem* p, int variant, double* d_poses, const randt_loss* loss,
+                                       const randt_solver_options* opt, double* d_result);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,6 +18,7 @@ EXTRA = os.environ.get("RANDT_NVCC_FLAGS", "").split()
 COMMON = EXTRA + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 UNITS = {
     "k3_pair_eval.cu": [],
+    "k4_lm_step.cu": [],
     "k2_associate.cu": ["-fmad=false"],
     "k1_voxelize.cu": ["-fmad=false"],
     "capi.cu": [],

@@ -33,6 +33,29 @@ class GridParams(C.Structure):
                 ("size_y", C.c_int32), ("resolution", C.c_double), ("max_linf", C.c_double)]
 
 
+class SolverOptions(C.Structure):
+    _fields_ = [("max_num_iterations", C.c_int32), ("use_manifold", C.c_int32), ("max_num_consecutive_invalid_steps", C.c_int32),
+                ("jacobi_scaling", C.c_int32), ("function_tolerance", C.c_double), ("gradient_tolerance", C.c_double),
+                ("parameter_tolerance", C.c_double), ("initial_trust_region_radius", C.c_double), ("max_trust_region_radius", C.c_double),
+                ("min_trust_region_radius", C.c_double), ("min_lm_diagonal", C.c_double), ("max_lm_diagonal", C.c_double),
+                ("min_relative_decrease", C.c_double), ("gnc_loss_scale", C.c_double), ("gnc_divisor", C.c_double),
+                ("gnc_max_steps", C.c_int32), ("poll_interval", C.c_int32)]
+
+
+REG_SCORE, REG_FINAL_COST, REG_GNC_SOLVES, REG_ITERATIONS, REG_EVALS, REG_MU_FIRST, REG_STATUS, REG_TERMINATION, REG_STRIDE = range(9)
+
+
+def solver_options(**kw):
+    """ceres / reference defaults (randt_solver_options_default), overridden by keyword"""
+    o = SolverOptions()
+    lib().randt_solver_options_default(C.byref(o))
+    for k, v in kw.items():
+        if not hasattr(o, k):
+            raise AttributeError(k)
+        setattr(o, k, v)
+    return o
+
+
 def grid_params(p):
     """from a randt_slam_b200.params.NdtParams"""
     return GridParams(float(p.max_range), int(p.n_clusters), int(p.min_points_per_cell), int(p.size_x), int(p.size_y),
@@ -76,6 +99,9 @@ _SIGS = {
     "randt_eval_fused": (_i, [_vp, _vp, _i, _vp, C.POINTER(Loss), _vp, _i, _vp]),
     "randt_eval_fused_dev": (_i, [_vp, _vp, _i, _vp, C.POINTER(Loss), _vp, _i, _vp]),
     "randt_sweep_costs": (_i, [_vp, _vp, _u32, _i, _vp, _u32, C.POINTER(Loss), _vp]),
+    "randt_solver_options_default": (None, [_vp]),
+    "randt_register_batch": (_i, [_vp, _vp, _i, _vp, C.POINTER(Loss), _vp, _vp]),
+    "randt_register_batch_dev": (_i, [_vp, _vp, _i, _vp, C.POINTER(Loss), _vp, _vp]),
 }
 
 
@@ -287,6 +313,19 @@ class Problem:
 
     def eval_emit_dev(self, d_poses, d_r, d_J, variant=VAR_SE2_INTENSITY):
         self.ctx._check(lib().randt_eval_emit_dev(self.ctx._h, self._h, int(variant), _ptr(d_poses), _ptr(d_r), _ptr(d_J)))
+
+    def register_batch(self, poses, loss, opt, variant=VAR_SE2_INTENSITY):
+        """GNC + LM for every segment at once -> (poses [S, np], result [S, REG_STRIDE])"""
+        npar = 4 if variant <= 1 else 3
+        poses = _f64(poses).reshape(self.n_segments, npar).copy()
+        result = np.zeros((self.n_segments, REG_STRIDE), np.float64)
+        lp = C.byref(loss) if loss is not None else None
+        self.ctx._check(lib().randt_register_batch(self.ctx._h, self._h, int(variant), _ptr(poses), lp, C.byref(opt), _ptr(result)))
+        return poses, result
+
+    def register_batch_dev(self, d_poses, d_result, loss, opt, variant=VAR_SE2_INTENSITY):
+        lp = C.byref(loss) if loss is not None else None
+        self.ctx._check(lib().randt_register_batch_dev(self.ctx._h, self._h, int(variant), _ptr(d_poses), lp, C.byref(opt), _ptr(d_result)))
 
     def sweep_costs(self, seg, poses, loss=None, variant=VAR_SE2_INTENSITY):
         npar = 4 if variant <= 1 else 3

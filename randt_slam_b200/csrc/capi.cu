@@ -7,6 +7,8 @@
 
 #include <algorithm>
 #include <new>
+#include <queue>
+#include <utility>
 
 #include "common.cuh"
 
@@ -42,6 +44,7 @@ struct randt_problem {
   Duo* duos = nullptr; uint32_t n_duos = 0;
   std::vector<uint32_t> h_duo_off;   // [S+1] duo offsets per segment
   Tile* tiles = nullptr; uint32_t n_tiles = 0;
+  uint32_t* warp_off = nullptr; uint32_t n_warps = 0;
   uint32_t* seg_first_tile = nullptr;
   uint32_t* seg_off = nullptr;
   double* partials = nullptr;
@@ -51,6 +54,10 @@ struct randt_problem {
   // scratch for the host-pointer entry points
   double *d_poses = nullptr, *d_out = nullptr, *d_mu = nullptr, *d_r = nullptr, *d_J = nullptr;
   double* d_sweep = nullptr; size_t sweep_cap = 0;
+  // workspace of the batched solver (randt_register_batch), allocated on first use
+  LmState* lm_state = nullptr; double *lm_eval_pose = nullptr, *lm_mu = nullptr, *lm_rec = nullptr, *lm_poses = nullptr, *lm_result = nullptr;
+  uint32_t *lm_active = nullptr, *lm_n_active = nullptr;
+  uint32_t* h_n_active = nullptr;   // pinned
 };
 
 namespace {
@@ -85,9 +92,12 @@ void free_map(randt_map* m) {
 }
 void free_problem(randt_problem* p) {
   if (!p) return;
-  cudaFree(p->cells_m); cudaFree(p->cells_f); cudaFree(p->pairs); cudaFree(p->duos); cudaFree(p->tiles); cudaFree(p->seg_first_tile); cudaFree(p->seg_off);
+  cudaFree(p->cells_m); cudaFree(p->cells_f); cudaFree(p->pairs); cudaFree(p->duos); cudaFree(p->tiles); cudaFree(p->warp_off); cudaFree(p->seg_first_tile); cudaFree(p->seg_off);
   cudaFree(p->partials); cudaFree(p->seg_counters); cudaFree(p->d_poses); cudaFree(p->d_out); cudaFree(p->d_mu); cudaFree(p->d_r);
   cudaFree(p->d_J); cudaFree(p->d_sweep);
+  cudaFree(p->lm_state); cudaFree(p->lm_eval_pose); cudaFree(p->lm_mu); cudaFree(p->lm_rec); cudaFree(p->lm_poses); cudaFree(p->lm_result);
+  cudaFree(p->lm_active); cudaFree(p->lm_n_active);
+  if (p->h_n_active) cudaFreeHost(p->h_n_active);
   delete p;
 }
 
@@ -108,6 +118,39 @@ int finish_problem(randt_ctx* ctx, randt_problem* p) {
     }
   }
   first[p->S] = (uint32_t)tiles.size();
+  // Balanced static schedule: longest-processing-time assignment of tiles to the resident warps of the persistent grid (a tile
+  // costs its chunks of 32 duos plus a fixed reduce/emit overhead), then the tile list is stored warp after warp.  Registration
+  // problems differ in size, and one warp walks only ~7 of them per launch at the bench size, so round-robin striding leaves
+  // warps (and whole SMs) idle at the tail.
+  {
+    const uint32_t n_warps = std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)kK3MaxWarps, (uint32_t)tiles.size()));
+    std::vector<uint32_t> order(tiles.size());
+    for (uint32_t t = 0; t < tiles.size(); ++t) order[t] = t;
+    auto cost = [&](uint32_t t) { return ((tiles[t].end - tiles[t].begin + 31u) / 32u) * 32u + 6u; };
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return cost(a) > cost(b); });
+    typedef std::pair<uint64_t, uint32_t> Load;   // (assigned cost, warp)
+    std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
+    for (uint32_t w = 0; w < n_warps; ++w) heap.push(Load(0, w));
+    std::vector<std::vector<uint32_t>> mine(n_warps);
+    for (uint32_t t : order) {
+      Load l = heap.top(); heap.pop();
+      mine[l.second].push_back(t);
+      l.first += cost(t);
+      heap.push(l);
+    }
+    std::vector<Tile> sorted; sorted.reserve(tiles.size());
+    std::vector<uint32_t> woff(n_warps + 1, 0);
+    for (uint32_t w = 0; w < n_warps; ++w) {
+      std::sort(mine[w].begin(), mine[w].end());
+      for (uint32_t t : mine[w]) sorted.push_back(tiles[t]);
+      woff[w + 1] = (uint32_t)sorted.size();
+    }
+    tiles.swap(sorted);
+    p->n_warps = n_warps;
+    CK(dev_alloc(&p->warp_off, woff.size()));
+    CK(cudaMemcpyAsync(p->warp_off, woff.data(), woff.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
   for (uint32_t s = 0; s < p->S; ++s) if (p->h_seg_off[s + 1] == p->h_seg_off[s]) p->has_empty_segment = true;
   p->n_tiles = (uint32_t)tiles.size();
   CK(dev_alloc(&p->tiles, tiles.size()));
@@ -128,8 +171,9 @@ int finish_problem(randt_ctx* ctx, randt_problem* p) {
 
 DeviceProblem view(const randt_problem* p) {
   DeviceProblem d;
-  d.cells_m = p->cells_m; d.cells_f = p->cells_f; d.pairs = p->pairs; d.duos = p->duos; d.seg_off = p->seg_off; d.tiles = p->tiles; d.n_tiles = p->n_tiles;
+  d.cells_m = p->cells_m; d.cells_f = p->cells_f; d.pairs = p->pairs; d.duos = p->duos; d.seg_off = p->seg_off; d.tiles = p->tiles; d.n_tiles = p->n_tiles; d.warp_off = p->warp_off; d.n_warps = p->n_warps;
   d.seg_first_tile = p->seg_first_tile; d.n_segments = p->S; d.n_pairs = p->P; d.partials = p->partials; d.seg_counters = p->seg_counters;
+  d.seg_active = nullptr;
   return d;
 }
 
@@ -612,6 +656,82 @@ int randt_sweep_costs(randt_ctx* ctx, const randt_problem* cp, uint32_t seg, int
   CK(launch_sweep_costs(view(p), p->h_seg_off[seg], p->h_seg_off[seg + 1], variant, d_p, n_poses, lp, d_c, ctx->stream, &nl));
   ctx->launches += nl;
   if (n_poses) CK(cudaMemcpyAsync(cost, d_c, (size_t)n_poses * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return RANDT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K4: batched registration
+// ---------------------------------------------------------------------------------------------------------------
+void randt_solver_options_default(randt_solver_options* o) {
+  if (!o) return;
+  memset(o, 0, sizeof(*o));
+  o->max_num_iterations = 200; o->use_manifold = 0; o->max_num_consecutive_invalid_steps = 5; o->jacobi_scaling = 1;
+  o->function_tolerance = 1e-6; o->gradient_tolerance = 1e-10; o->parameter_tolerance = 1e-8;
+  o->initial_trust_region_radius = 1e4; o->max_trust_region_radius = 1e16; o->min_trust_region_radius = 1e-32;
+  o->min_lm_diagonal = 1e-6; o->max_lm_diagonal = 1e32; o->min_relative_decrease = 1e-3;
+  o->gnc_loss_scale = 1.0; o->gnc_divisor = 1.1; o->gnc_max_steps = 2; o->poll_interval = 0;
+}
+
+int randt_register_batch_dev(randt_ctx* ctx, const randt_problem* cp, int variant, double* d_poses, const randt_loss* loss,
+                             const randt_solver_options* opt, double* d_result) {
+  if (!ctx || !cp || !d_poses || !opt || !d_result) return fail(ctx, RANDT_E_INVALID, "randt_register_batch: null argument");
+  if (check_variant(ctx, variant)) return RANDT_E_INVALID;
+  if (!(opt->gnc_divisor > 1.0) || !(opt->gnc_loss_scale > 0.0) || opt->gnc_max_steps < 1 || opt->max_num_iterations < 0 ||
+      opt->max_num_consecutive_invalid_steps < 1 || !(opt->initial_trust_region_radius > 0.0))
+    return fail(ctx, RANDT_E_INVALID, "randt_register_batch: bad solver options (gnc_divisor must be > 1, scales > 0, steps >= 1)");
+  randt_loss l0; l0.kind = RANDT_LOSS_NONE; l0.scale = 1.0; l0.alpha = 2.0; l0.mu = 1.0; l0.weight = 1.0;
+  if (loss) { l0 = *loss; l0.mu = 1.0; }
+  LossParams lp;
+  if (int rc = make_loss(ctx, &l0, &lp)) return rc;
+  randt_problem* p = const_cast<randt_problem*>(cp);
+  CK(cudaSetDevice(ctx->device));
+  const uint32_t S = p->S;
+  const int np = np_of(variant);
+  if (S == 0) return RANDT_OK;
+  if (!p->lm_state) {
+    CK(dev_alloc(&p->lm_state, S)); CK(dev_alloc(&p->lm_eval_pose, (size_t)S * 4)); CK(dev_alloc(&p->lm_mu, S));
+    CK(dev_alloc(&p->lm_rec, (size_t)S * RANDT_FUSED_STRIDE)); CK(dev_alloc(&p->lm_active, S)); CK(dev_alloc(&p->lm_n_active, 1));
+    CK(cudaHostAlloc(reinterpret_cast<void**>(&p->h_n_active), sizeof(uint32_t), cudaHostAllocDefault));
+  }
+  int nl = 0;
+  CK(launch_lm_init(S, np, d_poses, p->lm_state, p->lm_eval_pose, p->lm_mu, p->lm_active, p->lm_rec, p->lm_n_active, ctx->stream, &nl));
+  DeviceProblem v = view(p);
+  v.seg_active = p->lm_active;
+  const int poll = opt->poll_interval > 0 ? opt->poll_interval : 4;
+  // every solve needs at most max_num_iterations candidate evaluations + its start evaluation; one more launch seeds the GNC
+  const long long cap = 2 + (long long)(opt->gnc_max_steps + 1) * ((long long)opt->max_num_iterations + 2);
+  bool done = false;
+  for (long long it = 0; it < cap && !done; ++it) {
+    CK(launch_eval_fused(v, variant, p->lm_eval_pose, lp, p->lm_mu, true, p->lm_rec, ctx->d_bad, ctx->stream, &nl));
+    CK(launch_lm_step(S, np, opt->use_manifold, *opt, p->lm_rec, p->lm_state, p->lm_eval_pose, p->lm_mu, p->lm_active, p->lm_n_active, d_poses,
+                      d_result, ctx->stream, &nl));
+    if ((it + 1) % poll == 0 || it + 1 == cap) {
+      CK(cudaMemcpyAsync(p->h_n_active, p->lm_n_active, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      done = *p->h_n_active == 0u;
+    }
+  }
+  ctx->launches += nl;
+  if (!done) return fail(ctx, RANDT_E_NONFINITE, "randt_register_batch: iteration cap reached with active segments (non-finite evaluations?)");
+  return RANDT_OK;
+}
+
+int randt_register_batch(randt_ctx* ctx, const randt_problem* cp, int variant, double* poses, const randt_loss* loss,
+                         const randt_solver_options* opt, double* result) {
+  if (!ctx || !cp || !poses || !opt || !result) return fail(ctx, RANDT_E_INVALID, "randt_register_batch: null argument");
+  if (check_variant(ctx, variant)) return RANDT_E_INVALID;
+  randt_problem* p = const_cast<randt_problem*>(cp);
+  CK(cudaSetDevice(ctx->device));
+  const uint32_t S = p->S;
+  const int np = np_of(variant);
+  if (S == 0) return RANDT_OK;
+  if (!p->lm_poses) { CK(dev_alloc(&p->lm_poses, (size_t)S * 4)); CK(dev_alloc(&p->lm_result, (size_t)S * RANDT_REG_STRIDE)); }
+  CK(cudaMemcpyAsync(p->lm_poses, poses, (size_t)S * np * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  int rc = randt_register_batch_dev(ctx, p, variant, p->lm_poses, loss, opt, p->lm_result);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(poses, p->lm_poses, (size_t)S * np * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(result, p->lm_result, (size_t)S * RANDT_REG_STRIDE * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return RANDT_OK;
 }

@@ -36,18 +36,25 @@ struct DeviceProblem {
   const uint2* pairs;      // (im, jf), reference residual-block order
   const Duo* duos;         // the same pairs grouped for K3
   const uint32_t* seg_off; // [S+1] pair offsets per segment
-  const Tile* tiles;
+  const Tile* tiles;       // in the balanced order: warp w owns tiles [warp_off[w], warp_off[w+1])
   uint32_t n_tiles;
+  const uint32_t* warp_off;  // [n_warps+1]
+  uint32_t n_warps;
   const uint32_t* seg_first_tile;  // [S+1]
   uint32_t n_segments;
   uint32_t n_pairs;
   double* partials;        // [n_tiles][kMaxAcc]
   uint32_t* seg_counters;  // [S] zero between launches
+  const uint32_t* seg_active;  // [S] or NULL: segments with a zero flag are skipped by the fused kernel (batched solver)
 };
 
 constexpr int kTileDuos = 256;    // most duos per tile (one warp owns a tile)
 constexpr int kMinTileDuos = 32;  // tile length for small problems
 constexpr int kK3Threads = 128;   // threads per CTA in the pair-evaluation kernels
+#ifndef RANDT_K3_MIN_CTAS
+#define RANDT_K3_MIN_CTAS 4       // CTAs per SM the K3 register allocation is bounded for
+#endif
+constexpr int kK3MaxWarps = kSmCount * RANDT_K3_MIN_CTAS * (kK3Threads / 32);   // resident warps of the persistent grid
 constexpr int kMaxAcc = 20;       // accumulators per tile partial (<= 10 H + 4 g + cost + max + sumsq + nonfinite)
 
 // launchers (k3_pair_eval.cu)
@@ -107,6 +114,23 @@ cudaError_t launch_transform_cells(float4* d_cells, const uint32_t* d_cell_off, 
 cudaError_t launch_merge_maps(const float4* f_cells, const uint32_t* f_npts, const uint32_t* f_off, int32_t* f_slot, const float4* m_cells,
                               const uint32_t* m_npts, const uint32_t* m_off, uint32_t n_maps, const MapGeomDev& geom, const uint32_t* o_off,
                               float4* o_cells, uint32_t* o_npts, uint32_t* o_count, cudaStream_t s, int* n_launches);
+
+// k4_lm_step.cu — per-segment state of the batched GNC + LM solver
+struct LmState {
+  double x[4], cand[4];          // accepted point, candidate point
+  double cost, g[4], H[16];      // at x: cost, tangent gradient, tangent J^T J (leading dimension 4)
+  double scale[4], diag[4];      // Jacobi column scaling (fixed per solve), LM diagonal
+  double radius, decrease_factor, x_norm, model_cost_change, gmax, min_cost;
+  double mu, mu_first, final_cost;
+  int32_t phase, iteration, solve_iterations, consecutive_invalid, last_successful, reuse_diagonal;
+  int32_t gnc_solves, total_iterations, n_cost_evals, n_jac_evals, status, termination;
+  uint32_t n_blocks, pad_;
+};
+cudaError_t launch_lm_init(uint32_t S, int np, const double* d_poses0, LmState* state, double* eval_pose, double* mu, uint32_t* active,
+                           double* rec, uint32_t* n_active, cudaStream_t s, int* n_launches);
+cudaError_t launch_lm_step(uint32_t S, int np, int use_manifold, const randt_solver_options& o, const double* rec, LmState* state,
+                           double* eval_pose, double* mu, uint32_t* active, uint32_t* n_active, double* poses_out, double* result,
+                           cudaStream_t s, int* n_launches);
 
 // static_cast<unsigned>(double) as x86-64 gcc defines it for negative inputs: truncate to int64, keep the low 32 bits
 __host__ __device__ inline uint32_t to_u32_trunc(double v) {

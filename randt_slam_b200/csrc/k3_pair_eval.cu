@@ -344,13 +344,10 @@ constexpr int kWarpsPerCta = kK3Threads / 32;
 #ifndef RANDT_K3_STAGES
 #define RANDT_K3_STAGES 2
 #endif
-#ifndef RANDT_K3_MIN_CTAS
-#define RANDT_K3_MIN_CTAS 4
-#endif
 constexpr int kStages = RANDT_K3_STAGES;
 constexpr int kMinCtas = RANDT_K3_MIN_CTAS;   // CTAs per SM the register allocation is bounded for
 
-struct __align__(16) ChunkMeta { uint32_t t, i, end, seg; };   // tile index (0xffffffff: past the end), first duo, tile end, segment
+struct __align__(16) ChunkMeta { uint32_t k, i, end, seg; };   // position in the tile order, first duo, tile end, segment (0xffffffff: past the end)
 struct __align__(16) StageBuf {
   float4 cell[9][32];      // [component][lane]: moving a, b, c, fixed0 a, b, c, fixed1 a, b, c
   uint4 duo[32];           // the lane's duo record (im, jf0, jf1, p0)
@@ -373,31 +370,43 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-struct TileStream {   // generator (warp-uniform): tiles t0, t0 + stride, ... chunk by chunk; the following tile's descriptor is prefetched
-  const Tile* __restrict__ tiles;
-  uint32_t n_tiles, stride;
-  uint32_t t, i, end, seg, begin;
-  Tile la;            // descriptor of tile t + stride (valid when that index < n_tiles)
-  __device__ __forceinline__ void init(const Tile* tl, uint32_t n, uint32_t t0, uint32_t st) {
-    tiles = tl; n_tiles = n; stride = st;
-    t = t0; i = 0; end = 0; seg = 0; begin = 0;
-    la.seg = 0; la.begin = 0; la.end = 0; la.part = 0;
-    if (t0 < n) { const Tile c = tl[t0]; i = c.begin; begin = c.begin; end = c.end; seg = c.seg; }
-    if (t0 < n && t0 + st < n) la = tl[t0 + st];
-  }
-  __device__ __forceinline__ bool valid() const { return t < n_tiles; }
-  __device__ __forceinline__ void advance() {
-    if (t >= n_tiles) return;
-    i += 32;
-    if (i >= end) {
-      t += stride;
-      i = la.begin; begin = la.begin; end = la.end; seg = la.seg;
-      if (t < n_tiles && t + stride < n_tiles) la = tiles[t + stride];
+struct TileStream {   // generator (warp-uniform): the warp's range [k, k_end) of the balanced tile order, chunk by chunk; the following
+  // tile's descriptor is prefetched.  The tile list and the per-segment active flags are read through the kernel parameters
+  // (constant bank), not kept in registers.  Tiles of inactive segments (P.seg_active[seg] == 0) are emitted as one empty chunk
+  // (end == begin) that the consumer drops.
+  uint32_t k, k_end;
+  uint32_t i, end, seg, begin;
+  uint32_t la_seg, la_begin, la_end;   // descriptor of tile k + 1 (valid when k + 1 < k_end)
+  __device__ __forceinline__ void fetch_next(const DeviceProblem& P) {
+    if (k + 1 < k_end) {
+      const Tile n = P.tiles[k + 1];
+      la_seg = n.seg; la_begin = n.begin; la_end = n.end;
+      if (P.seg_active && P.seg_active[n.seg] == 0u) la_end = n.begin;
     }
   }
-  __device__ __forceinline__ uint4 fetch_duo(const Duo* __restrict__ duos, int lane) const {
+  __device__ __forceinline__ void init(const DeviceProblem& P, uint32_t w) {
+    k = P.warp_off[w]; k_end = P.warp_off[w + 1];
+    i = 0; end = 0; seg = 0; begin = 0;
+    la_seg = 0; la_begin = 0; la_end = 0;
+    if (k < k_end) {
+      const Tile c = P.tiles[k]; i = c.begin; begin = c.begin; end = c.end; seg = c.seg;
+      if (P.seg_active && P.seg_active[c.seg] == 0u) end = begin;
+    }
+    fetch_next(P);
+  }
+  __device__ __forceinline__ bool valid() const { return k < k_end; }
+  __device__ __forceinline__ void advance(const DeviceProblem& P) {
+    if (k >= k_end) return;
+    i += 32;
+    if (i >= end) {
+      ++k;
+      i = la_begin; begin = la_begin; end = la_end; seg = la_seg;
+      fetch_next(P);
+    }
+  }
+  __device__ __forceinline__ uint4 fetch_duo(const DeviceProblem& P, int lane) const {
     uint4 d = make_uint4(0, 0, kNoCell, 0);
-    if (t < n_tiles && i + lane < end) d = __ldg(reinterpret_cast<const uint4*>(duos) + i + lane);
+    if (k < k_end && i + lane < end) d = __ldg(reinterpret_cast<const uint4*>(P.duos) + i + lane);
     return d;
   }
 };
@@ -420,17 +429,17 @@ __device__ __forceinline__ void stage_issue(const DeviceProblem& P, const TileSt
     }
     if (lane == 0) {
       const bool first = g.i == g.begin;
-      if (first) {
+      if (first && g.i < g.end) {
         const double* ps = poses + (size_t)g.seg * NP;
         if (NP == 4) { cp_async16(&sb->pose[0], ps); cp_async16(&sb->pose[2], ps + 2); }
         else { cp_async8(&sb->pose[0], ps); cp_async8(&sb->pose[1], ps + 1); cp_async8(&sb->pose[2], ps + 2); }
         if (mu_per_seg) cp_async8(&sb->mu, mu_per_seg + g.seg);
       }
       sb->first = first ? 1u : 0u;
-      sb->meta.t = g.t; sb->meta.i = g.i; sb->meta.end = g.end; sb->meta.seg = g.seg;
+      sb->meta.k = g.k; sb->meta.i = g.i; sb->meta.end = g.end; sb->meta.seg = g.seg;
     }
   } else if (lane == 0) {
-    sb->meta.t = 0xffffffffu;
+    sb->meta.seg = 0xffffffffu;
   }
   cp_async_commit();
 }
@@ -447,20 +456,19 @@ __global__ void __launch_bounds__(kK3Threads, kMinCtas) k3_fused_kernel(DevicePr
   __shared__ StageBuf stage_all[kWarpsPerCta][kStages];
   const int lane = threadIdx.x & 31;
   const int warp = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0);
-  const uint32_t n_warps = gridDim.x * kWarpsPerCta;
   const uint32_t w = blockIdx.x * kWarpsPerCta + warp;
-  if (w >= P.n_tiles) return;
+  if (w >= P.n_warps) return;
   StageBuf* stage = stage_all[warp];
 
   TileStream gen;
-  gen.init(P.tiles, P.n_tiles, w, n_warps);
+  gen.init(P, w);
   // prologue: chunks 0 .. kStages-2 in flight, duo records of chunk kStages-1 in registers
-  uint4 du = gen.fetch_duo(P.duos, lane);
+  uint4 du = gen.fetch_duo(P, lane);
 #pragma unroll
   for (int s = 0; s < kStages - 1; ++s) {
     stage_issue<NP>(P, gen, du, lane, &stage[s], poses, mu_per_seg);
-    gen.advance();
-    du = gen.fetch_duo(P.duos, lane);
+    gen.advance(P);
+    du = gen.fetch_duo(P, lane);
   }
 
   PoseConst kc; LossConst lc;
@@ -472,15 +480,16 @@ __global__ void __launch_bounds__(kK3Threads, kMinCtas) k3_fused_kernel(DevicePr
     // ---- stage chunk j + kStages - 1, fetch the duo records of chunk j + kStages ----
     int islot = slot + kStages - 1; if (islot >= kStages) islot -= kStages;
     stage_issue<NP>(P, gen, du, lane, &stage[islot], poses, mu_per_seg);
-    gen.advance();
-    du = gen.fetch_duo(P.duos, lane);
+    gen.advance(P);
+    du = gen.fetch_duo(P, lane);
     // ---- chunk j has landed ----
     cp_async_wait<kStages - 1>();
     __syncwarp();
     const StageBuf* sb = &stage[slot];
     const ChunkMeta cm = sb->meta;
-    if (cm.t == 0xffffffffu) break;
-    if (sb->first) {
+    if (cm.seg == 0xffffffffu) break;
+    const bool live = cm.i < cm.end;          // false: tile of an inactive segment (dropped)
+    if (sb->first && live) {
       make_pose_const<VARIANT>(sb->pose, kc);
       make_loss_const(lp, mu_per_seg ? sb->mu : lp.mu, lc);
     }
@@ -523,12 +532,13 @@ __global__ void __launch_bounds__(kK3Threads, kMinCtas) k3_fused_kernel(DevicePr
       }
     }
     // ---- tile finished: reduce across the warp and emit ----
-    if (cm.i + 32 >= cm.end) {
+    if (live && cm.i + 32 >= cm.end) {
       warp_sum_all<NS>(acc, lane);
       const double mx = warp_max(max_dd);
       const uint32_t bad = __reduce_add_sync(kFull, n_bad);
-      const uint32_t seg = cm.seg, t = cm.t;
+      const uint32_t seg = cm.seg;
       const uint32_t first = P.seg_first_tile[seg], seg_tiles = P.seg_first_tile[seg + 1] - first;
+
       if (seg_tiles == 1) {
         if (lane == 0) {
           double rec[NH + NB + 2];
@@ -540,6 +550,7 @@ __global__ void __launch_bounds__(kK3Threads, kMinCtas) k3_fused_kernel(DevicePr
         }
       } else {
         // partial record of this tile: [NS sums][max dd][bad]
+        const uint32_t t = first + P.tiles[cm.k].part;
         double* part = P.partials + (size_t)t * kMaxAcc;
         uint32_t ticket = 0;
         if (lane == 0) {
@@ -617,18 +628,17 @@ __global__ void __launch_bounds__(kK3Threads, kMinCtas) k3_emit_kernel(DevicePro
   __shared__ StageBuf stage_all[kWarpsPerCta][kStages];
   const int lane = threadIdx.x & 31;
   const int warp = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0);
-  const uint32_t n_warps = gridDim.x * kWarpsPerCta;
   const uint32_t w = blockIdx.x * kWarpsPerCta + warp;
-  if (w >= P.n_tiles) return;
+  if (w >= P.n_warps) return;
   StageBuf* stage = stage_all[warp];
   TileStream gen;
-  gen.init(P.tiles, P.n_tiles, w, n_warps);
-  uint4 du = gen.fetch_duo(P.duos, lane);
+  gen.init(P, w);
+  uint4 du = gen.fetch_duo(P, lane);
 #pragma unroll
   for (int s = 0; s < kStages - 1; ++s) {
     stage_issue<NP>(P, gen, du, lane, &stage[s], poses, nullptr);
-    gen.advance();
-    du = gen.fetch_duo(P.duos, lane);
+    gen.advance(P);
+    du = gen.fetch_duo(P, lane);
   }
   PoseConst kc;
   uint32_t n_bad = 0;
@@ -636,14 +646,14 @@ __global__ void __launch_bounds__(kK3Threads, kMinCtas) k3_emit_kernel(DevicePro
   while (true) {
     int islot = slot + kStages - 1; if (islot >= kStages) islot -= kStages;
     stage_issue<NP>(P, gen, du, lane, &stage[islot], poses, nullptr);
-    gen.advance();
-    du = gen.fetch_duo(P.duos, lane);
+    gen.advance(P);
+    du = gen.fetch_duo(P, lane);
     cp_async_wait<kStages - 1>();
     __syncwarp();
     const StageBuf* sb = &stage[slot];
     const ChunkMeta cm = sb->meta;
-    if (cm.t == 0xffffffffu) break;
-    if (sb->first) make_pose_const<VARIANT>(sb->pose, kc);
+    if (cm.seg == 0xffffffffu) break;
+    if (sb->first && cm.i < cm.end) make_pose_const<VARIANT>(sb->pose, kc);
     if (cm.i + lane < cm.end) {
       RawCell m, f0, f1;
       m.a = sb->cell[0][lane]; m.b = sb->cell[1][lane]; m.c = sb->cell[2][lane];
@@ -720,16 +730,12 @@ int loss_code(const LossParams& lp) {
   return L_BARRON;
 }
 
-inline int stream_grid(uint32_t n_tiles) {
-  const uint32_t full = (uint32_t)kSmCount * (uint32_t)kMinCtas;   // resident CTAs (4 warps each) the register bound allows
-  const uint32_t need = (n_tiles + kWarpsPerCta - 1) / kWarpsPerCta;
-  return (int)(need < full ? need : full);
-}
+inline int stream_grid(uint32_t n_warps) { return (int)((n_warps + kWarpsPerCta - 1) / kWarpsPerCta); }
 
 template <int VARIANT, int LOSS>
 cudaError_t launch_fused_vl(const DeviceProblem& p, const double* d_poses, const LossParams& lp, const double* d_mu, bool want_jac,
                             double* d_out, unsigned long long* bad, cudaStream_t s) {
-  const int grid = stream_grid(p.n_tiles);
+  const int grid = stream_grid(p.n_warps);
   if (want_jac) k3_fused_kernel<VARIANT, LOSS, true><<<grid, kK3Threads, 0, s>>>(p, d_poses, lp, d_mu, d_out, bad);
   else          k3_fused_kernel<VARIANT, LOSS, false><<<grid, kK3Threads, 0, s>>>(p, d_poses, lp, d_mu, d_out, bad);
   return cudaGetLastError();
@@ -780,7 +786,7 @@ cudaError_t launch_eval_fused(const DeviceProblem& p, int variant, const double*
 cudaError_t launch_eval_emit(const DeviceProblem& p, int variant, const double* d_poses, double* d_r, double* d_J,
                              unsigned long long* d_bad, cudaStream_t s, int* n_launches) {
   if (p.n_tiles == 0) return cudaSuccess;
-  const int grid = stream_grid(p.n_tiles);
+  const int grid = stream_grid(p.n_warps);
 #define RANDT_EMIT(V)                                                                                              \
   if (d_J) k3_emit_kernel<V, true><<<grid, kK3Threads, 0, s>>>(p, d_poses, d_r, d_J, d_bad);             \
   else     k3_emit_kernel<V, false><<<grid, kK3Threads, 0, s>>>(p, d_poses, d_r, d_J, d_bad);
