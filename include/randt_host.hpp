@@ -1,0 +1,217 @@
+// randt_host.hpp — C++17 host-side mirror of the RaNDT-SLAM surface for the NDT hot path, over the C-ABI in randt_gpu.h.
+//
+// The reference (R/ = ros/ndt_radar_slam/) is compiled C++, so the host side above the C-ABI is C++ with the reference's class
+// and method names, argument meaning and error behaviour for this path:
+//
+//   randt::Map              <- ndt_representation::Map / HierarchicalMap      R/include/ndt_representation/ndt_map.h:14-199,
+//                                                                             ndt_hierarchical_map.h:34-69 (addClusters, transformMap, mergeMapCell)
+//   randt::Matcher          <- ndt_registration::Matcher                      R/include/ndt_registration/ndt_matcher.h:46-87
+//   randt::NdtCostFunction  <- the N x AutoDiffCostFunction<NDTFrameToMap...Residual..., 1, 4> blocks Matcher::addNDTFactor adds
+//                              (R/src/ndt_registration/ndt_matcher.cpp:183-288), as ONE ceres::CostFunction
+//   randt::SE2d             <- Sophus::SE2d (storage order [cos, sin, tx, ty], group product, exp / log of the rotation)
+//
+// No Eigen / Sophus / Ceres / PCL / ROS types appear here (none exist in this image); INTEGRATION.md shows the few lines that
+// adapt them in the reference tree.  Every method throws randt::Error (std::runtime_error) on a C-ABI failure — there is no CPU
+// fallback.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "randt_gpu.h"
+
+#if __has_include(<ceres/cost_function.h>)
+#include <ceres/cost_function.h>
+#else
+// Stand-in with the exact interface of ceres::CostFunction (Ceres 2.1.0 include/ceres/cost_function.h) so that NdtCostFunction
+// compiles here and drops into a real ceres::Problem unchanged where Ceres is installed.
+namespace ceres {
+class CostFunction {
+ public:
+  CostFunction() : num_residuals_(0) {}
+  CostFunction(const CostFunction&) = delete;
+  void operator=(const CostFunction&) = delete;
+  virtual ~CostFunction() {}
+  virtual bool Evaluate(double const* const* parameters, double* residuals, double** jacobians) const = 0;
+  const std::vector<int32_t>& parameter_block_sizes() const { return parameter_block_sizes_; }
+  int num_residuals() const { return num_residuals_; }
+
+ protected:
+  std::vector<int32_t>* mutable_parameter_block_sizes() { return &parameter_block_sizes_; }
+  void set_num_residuals(int n) { num_residuals_ = n; }
+
+ private:
+  std::vector<int32_t> parameter_block_sizes_;
+  int num_residuals_;
+};
+}  // namespace ceres
+#endif
+
+namespace randt {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& what) : std::runtime_error(what), code(c) {}
+};
+
+// Sophus::SE2d stand-in: unit complex number + translation, data() in Sophus' storage order.
+struct SE2d {
+  double v[4] = {1.0, 0.0, 0.0, 0.0};   // cos, sin, tx, ty
+  SE2d() {}
+  SE2d(double theta, double tx, double ty);
+  double* data() { return v; }
+  const double* data() const { return v; }
+  double angle() const;                  // so2().log()
+  SE2d operator*(const SE2d& o) const;   // group product with Sophus' conditional renormalisation of the complex number
+  void matrix3f(float out[9]) const;     // column-major 3x3 homogeneous matrix as floats (what the BnB search de-duplicates on)
+};
+
+// The parameter fields of the reference this path reads (R/include/ndt_slam/ndt_slam_parameters.h:17-50,56-84), already derived as
+// NDTSlam::readParameters leaves them (size in cells after the int /= resolution; n_clusters = int((2 max_range / resolution)^2)).
+struct NDTMapParameters {
+  double resolution = 1.0;
+  int size_x = 50, size_y = 50;
+  double max_neighbour_manhattan_distance = 4.0;
+  int min_points_per_cell = 3;
+  float max_range = 16.0f;      // radar_preprocessor/max_range (cluster grid)
+  int n_clusters = 1024;
+  randt_grid_params grid() const;
+};
+struct NDTMatcherParameters {
+  int gnc_steps = 3;
+  int smoothing_steps = 3;
+  double loss_function_convexity = -2.0;
+  double loss_function_scale = 1.5;
+  double gnc_control_parameter_divisor = 1.3;
+  int max_iteration = 200;
+  double pose_reject_translation = 2.0, pose_reject_rotation = 2.0;
+  int n_results_kd_lookup = 4;
+  double ndt_weight = 50000.0;
+  bool use_analytic_expressions_for_optimization = false;
+  bool use_intensity_as_dimension = true;
+  bool optimize_on_manifold = true;
+  bool lookup_mahalanobis = true;
+  double csm_window_linear = 4.5, csm_window_angular = 0.45, csm_linear_step = 0.4, csm_cost_threshold = 0.82, csm_max_px_accurate_range = 4.0;
+  int csm_n_iter = 2;
+};
+
+class Context {
+ public:
+  explicit Context(int device = 0, void* cuda_stream = nullptr);
+  ~Context();
+  Context(const Context&) = delete;
+  Context& operator=(const Context&) = delete;
+  randt_ctx* get() const { return ctx_; }
+  void check(int rc) const;   // throws Error with randt_last_error()
+  uint64_t launchCount() const { return randt_ctx_launch_count(ctx_); }
+
+ private:
+  randt_ctx* ctx_ = nullptr;
+};
+
+// A batch of B independent NDT maps resident on the device (B = 1 is the reference's Map).
+class Map {
+ public:
+  Map(Context& ctx, const NDTMapParameters& p, uint32_t n_maps = 1);   // Map::initialize: empty maps
+  ~Map();
+  Map(Map&&) noexcept;
+  Map(const Map&) = delete;
+  // RadarPreprocessor clustering + HierarchicalMap::addClusters (R/src/local_fuser/local_fuser.cpp:102-105): replaces the content
+  // with the cells of the given scans.  pts4 = (x, y, unused, intensity) per point; scan b owns [scan_off[b], scan_off[b+1]).
+  void addClusters(const float* pts4, const uint32_t* scan_off, uint32_t n_scans);
+  void addClusters(const std::vector<float>& pts4) { const uint32_t off[2] = {0, (uint32_t)(pts4.size() / 4)}; addClusters(pts4.data(), off, 1); }
+  void transformMap(const SE2d* trans);            // one transform per map (Map::transformMap, float32 like the reference)
+  void transformMap(const SE2d& t) { transformMap(&t); }
+  void mergeMapCell(const Map& moving);             // Map::mergeMapCell for every map of the batch
+  size_t get_n_cells() const;                       // total over the batch
+  uint32_t n_maps() const;
+  // Map::getCellMeanAndCovariance (ndt_map.h:112-119): mean[3], row-major cov[9]; cached host copy, refreshed after mutation
+  bool getCellMeanAndCovariance(size_t idx, float* mean3, float* cov9) const;
+  const std::vector<uint32_t>& cellOffsets() const;  // [B+1]
+  randt_map* handle() const { return map_; }
+  Context& context() const { return *ctx_; }
+  const NDTMapParameters& parameters() const { return p_; }
+
+ private:
+  void sync_host() const;
+  Context* ctx_;
+  NDTMapParameters p_;
+  randt_map* map_ = nullptr;
+  mutable bool host_valid_ = false;
+  mutable std::vector<float> h_cells_;
+  mutable std::vector<uint32_t> h_off_;
+};
+
+// One ceres::CostFunction standing in for all residual blocks addNDTFactor would add for one pose: parameter block {4} =
+// [cos, sin, tx, ty] (manifold mode) or {2, 1} = pos, rot (vector mode).  Residuals: the P loss-corrected pair residuals, then one
+// extra entry sqrt(2 (sum rho/2 - sum rho' r^2/2)) with a zero Jacobian, so that 1/2 |residuals|^2 equals the robustified cost ceres
+// would report for the P blocks, and J^T J / J^T r equal what ceres accumulates with its per-block Corrector (exact for rho'' <= 0,
+// i.e. every Barron alpha < 2 and Welsch).  With no loss set the residuals and Jacobians are the raw ones and the extra entry is 0.
+class NdtCostFunction : public ceres::CostFunction {
+ public:
+  NdtCostFunction(Context& ctx, randt_problem* problem /*takes ownership*/, int variant);
+  ~NdtCostFunction() override;
+  bool Evaluate(double const* const* parameters, double* residuals, double** jacobians) const override;
+  void setLoss(const randt_loss* loss);            // LossFunctionWrapper::Reset of the GNC loop (ndt_matcher.cpp:392-393)
+  uint32_t numPairs() const { return n_pairs_; }
+  double maxRawResidual(const double* pose) const;  // Problem::Evaluate(apply_loss_function = false) + max (ndt_matcher.cpp:382-387)
+  randt_problem* problem() const { return problem_; }
+
+ private:
+  Context* ctx_;
+  randt_problem* problem_;
+  int variant_;
+  uint32_t n_pairs_ = 0;
+  bool has_loss_ = false;
+  randt_loss loss_{};
+  mutable std::vector<double> r_, J_;
+};
+
+class Matcher {
+ public:
+  explicit Matcher(Context& ctx) : ctx_(&ctx) {}
+  void initialize(const NDTMatcherParameters& parameters) { parameters_ = parameters; }
+  // association half of Matcher::addNDTFactor for a batch: problem b pairs moving map b with fixed map b at initial_guess[b]
+  randt_problem* associate(const SE2d* initial_guess, const Map& fixed_ndt, const Map& moving_ndt, bool use_intensity_as_dimension,
+                           int n_neighbours) const;
+  // Matcher::addNDTFactor as one batched cost function (single map pair)
+  std::unique_ptr<NdtCostFunction> addNDTFactor(const SE2d& initial_guess, const Map& fixed_ndt, const Map& moving_ndt,
+                                                bool use_intensity_as_dimension, int n_neighbours) const;
+  // Matcher::estimateLoopConstraint (ndt_matcher.cpp:426-493), B = 1
+  double estimateLoopConstraint(SE2d& trans, const Map& old_ndt, Map& new_ndt, int max_gnc_steps, bool use_intensity_as_dimension,
+                                double scale) const;
+  // the same for B independent (submap, scan) pairs in one device-resident solve (loop-closure candidate sweep); returns the scores
+  std::vector<double> estimateLoopConstraints(std::vector<SE2d>& trans, const Map& old_ndts, Map& new_ndts, int max_gnc_steps,
+                                              bool use_intensity_as_dimension, double scale) const;
+  // Matcher::estimateTransformGlobalBNB (ndt_matcher.cpp:495-608): same coarse-to-fine tree, every queued level evaluated in one sweep
+  double estimateTransformGlobalBNB(SE2d& trans, const Map& fixed_ndt, Map& moving_ndt, bool use_intensity_as_dimension, double scale,
+                                    double search_window_size_linear, double search_window_size_angular) const;
+  const NDTMatcherParameters& parameters() const { return parameters_; }
+  int variant(bool use_intensity_as_dimension) const;
+
+ private:
+  Context* ctx_;
+  NDTMatcherParameters parameters_;
+};
+
+}  // namespace randt
+
+// C entry points over the classes above, used by the Python tests (ctypes) to drive the C++ layer; not part of the drop-in ABI.
+extern "C" {
+RANDT_API int randt_hostapi_loop_constraints(int device, const randt_grid_params* gp, const float* fixed_pts4, const uint32_t* fixed_off,
+                                             const float* moving_pts4, const uint32_t* moving_off, uint32_t n_problems, int k,
+                                             double loss_function_scale, double convexity, double divisor, int max_gnc_steps, double loop_scale,
+                                             int optimize_on_manifold, double* poses_io /*[n][4]*/, double* scores /*[n]*/);
+RANDT_API int randt_hostapi_cost_function(int device, const randt_grid_params* gp, const float* fixed_pts4, uint32_t n_fixed,
+                                          const float* moving_pts4, uint32_t n_moving, int k, const double* guess4, const randt_loss* loss,
+                                          const double* pose4, double* residuals /*[cap]*/, double* jacobian /*[cap][4]*/, uint32_t cap,
+                                          uint32_t* num_residuals, double* max_raw);
+RANDT_API int randt_hostapi_bnb(int device, const randt_grid_params* gp, const float* fixed_pts4, uint32_t n_fixed, const float* moving_pts4,
+                                uint32_t n_moving, double convexity, double scale, double window_linear, double window_angular,
+                                double linear_step, double max_px_range, double cost_threshold, int n_iter, double* pose_io4, double* min_cost,
+                                uint32_t* n_evaluated);
+RANDT_API const char* randt_hostapi_last_error(void);
+}

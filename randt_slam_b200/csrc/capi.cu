@@ -42,6 +42,7 @@ struct randt_problem {
   float4 *cells_m = nullptr, *cells_f = nullptr;
   uint2* pairs = nullptr;
   Duo* duos = nullptr; uint32_t n_duos = 0;
+  DuoRec* duo_recs = nullptr; uint32_t* duo_p0 = nullptr;
   std::vector<uint32_t> h_duo_off;   // [S+1] duo offsets per segment
   Tile* tiles = nullptr; uint32_t n_tiles = 0;
   uint32_t* warp_off = nullptr; uint32_t n_warps = 0;
@@ -92,7 +93,7 @@ void free_map(randt_map* m) {
 }
 void free_problem(randt_problem* p) {
   if (!p) return;
-  cudaFree(p->cells_m); cudaFree(p->cells_f); cudaFree(p->pairs); cudaFree(p->duos); cudaFree(p->tiles); cudaFree(p->warp_off); cudaFree(p->seg_first_tile); cudaFree(p->seg_off);
+  cudaFree(p->cells_m); cudaFree(p->cells_f); cudaFree(p->pairs); cudaFree(p->duos); cudaFree(p->duo_recs); cudaFree(p->duo_p0); cudaFree(p->tiles); cudaFree(p->warp_off); cudaFree(p->seg_first_tile); cudaFree(p->seg_off);
   cudaFree(p->partials); cudaFree(p->seg_counters); cudaFree(p->d_poses); cudaFree(p->d_out); cudaFree(p->d_mu); cudaFree(p->d_r);
   cudaFree(p->d_J); cudaFree(p->d_sweep);
   cudaFree(p->lm_state); cudaFree(p->lm_eval_pose); cudaFree(p->lm_mu); cudaFree(p->lm_rec); cudaFree(p->lm_poses); cudaFree(p->lm_result);
@@ -103,6 +104,13 @@ void free_problem(randt_problem* p) {
 
 // tile list + per-segment bookkeeping from a host seg_off; uploads everything a DeviceProblem needs
 int finish_problem(randt_ctx* ctx, randt_problem* p) {
+  // record-major duo table (what K3 streams)
+  {
+    int nl = 0;
+    CK(dev_alloc(&p->duo_recs, p->n_duos)); CK(dev_alloc(&p->duo_p0, p->n_duos));
+    CK(launch_build_duo_records(p->cells_m, p->cells_f, p->duos, p->n_duos, p->duo_recs, p->duo_p0, ctx->stream, &nl));
+    ctx->launches += nl;
+  }
   std::vector<Tile> tiles;
   std::vector<uint32_t> first(p->S + 1, 0);
   // one warp owns a tile.  Big batches: tiles of up to kTileDuos duos (a whole ~200-pair registration per warp, no partials);
@@ -171,7 +179,7 @@ int finish_problem(randt_ctx* ctx, randt_problem* p) {
 
 DeviceProblem view(const randt_problem* p) {
   DeviceProblem d;
-  d.cells_m = p->cells_m; d.cells_f = p->cells_f; d.pairs = p->pairs; d.duos = p->duos; d.seg_off = p->seg_off; d.tiles = p->tiles; d.n_tiles = p->n_tiles; d.warp_off = p->warp_off; d.n_warps = p->n_warps;
+  d.cells_m = p->cells_m; d.cells_f = p->cells_f; d.pairs = p->pairs; d.duos = p->duos; d.duo_recs = p->duo_recs; d.duo_p0 = p->duo_p0; d.seg_off = p->seg_off; d.tiles = p->tiles; d.n_tiles = p->n_tiles; d.warp_off = p->warp_off; d.n_warps = p->n_warps;
   d.seg_first_tile = p->seg_first_tile; d.n_segments = p->S; d.n_pairs = p->P; d.partials = p->partials; d.seg_counters = p->seg_counters;
   d.seg_active = nullptr;
   return d;

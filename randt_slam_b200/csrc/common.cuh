@@ -26,6 +26,10 @@ struct LossParams {  // host-evaluated constants of the loss that do not depend 
 // the moving cell is loaded, converted and rotated once for both pairs.
 struct Duo { uint32_t im, jf0, jf1, p0; };   // moving cell, fixed cell of pair p0, fixed cell of pair p0 + 1 (kNoCell: none), first pair
 constexpr uint32_t kNoCell = 0xffffffffu;
+// What K3 streams: the duo with its three cells inlined (moving, fixed of pair p0, fixed of pair p0 + 1), 144 B.  A missing second
+// pair is marked by the bit pattern kNoSecondPair in the first float of the third cell (a NaN payload no arithmetic produces).
+struct __align__(16) DuoRec { float4 v[9]; };
+constexpr uint32_t kNoSecondPair = 0xffffffffu;
 
 // A work tile: duos [begin, end) of segment `seg`; `part` = index of the tile inside its segment.
 struct Tile { uint32_t seg, begin, end, part; };
@@ -34,7 +38,9 @@ struct DeviceProblem {
   const float4* cells_m;   // 3 x float4 per cell
   const float4* cells_f;
   const uint2* pairs;      // (im, jf), reference residual-block order
-  const Duo* duos;         // the same pairs grouped for K3
+  const Duo* duos;         // the same pairs grouped two by two (shared moving cell)
+  const DuoRec* duo_recs;  // [n_duos] record-major table K3 streams with bulk copies
+  const uint32_t* duo_p0;  // [n_duos] first pair of each duo (EMIT output rows)
   const uint32_t* seg_off; // [S+1] pair offsets per segment
   const Tile* tiles;       // in the balanced order: warp w owns tiles [warp_off[w], warp_off[w+1])
   uint32_t n_tiles;
@@ -62,6 +68,8 @@ cudaError_t launch_eval_fused(const DeviceProblem& p, int variant, const double*
                               bool want_jac, double* d_out, unsigned long long* d_bad, cudaStream_t s, int* n_launches);
 cudaError_t launch_eval_emit(const DeviceProblem& p, int variant, const double* d_poses, double* d_r, double* d_J,
                              unsigned long long* d_bad, cudaStream_t s, int* n_launches);
+cudaError_t launch_build_duo_records(const float4* cells_m, const float4* cells_f, const Duo* duos, uint32_t n_duos, DuoRec* recs,
+                                     uint32_t* duo_p0, cudaStream_t s, int* n_launches);
 cudaError_t launch_sweep_costs(const DeviceProblem& p, uint32_t pair_begin, uint32_t pair_end, int variant, const double* d_poses,
                                uint32_t n_poses, const LossParams& lp, double* d_cost, cudaStream_t s, int* n_launches);
 

@@ -348,14 +348,14 @@ constexpr int kStages = RANDT_K3_STAGES;
 constexpr int kMinCtas = RANDT_K3_MIN_CTAS;   // CTAs per SM the register allocation is bounded for
 
 struct __align__(16) ChunkMeta { uint32_t k, i, end, seg; };   // position in the tile order, first duo, tile end, segment (0xffffffff: past the end)
-struct __align__(16) StageBuf {
-  float4 cell[9][32];      // [component][lane]: moving a, b, c, fixed0 a, b, c, fixed1 a, b, c
-  uint4 duo[32];           // the lane's duo record (im, jf0, jf1, p0)
+struct __align__(128) StageBuf {
+  float4 rec[32][9];       // the chunk's 32 duo records (144 B each, see DuoRec in common.cuh), landed by ONE bulk copy
   double pose[4];
   double mu;
   uint32_t first;          // 1: first chunk of its tile (pose/mu valid)
   uint32_t pad_;
   ChunkMeta meta;
+  unsigned long long bar;  // mbarrier the bulk copy completes on
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -369,6 +369,36 @@ __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// ---- TMA 1-D bulk copy + mbarrier (sm_90+ PTX; SASS UBLKCP / SYNCS) ----
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(a), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, uint32_t bytes, unsigned long long* bar) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem);
+  const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(gmem), "r"(bytes), "r"(b)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 struct TileStream {   // generator (warp-uniform): the warp's range [k, k_end) of the balanced tile order, chunk by chunk; the following
   // tile's descriptor is prefetched.  The tile list and the per-segment active flags are read through the kernel parameters
@@ -404,42 +434,34 @@ struct TileStream {   // generator (warp-uniform): the warp's range [k, k_end) o
       fetch_next(P);
     }
   }
-  __device__ __forceinline__ uint4 fetch_duo(const DeviceProblem& P, int lane) const {
-    uint4 d = make_uint4(0, 0, kNoCell, 0);
-    if (k < k_end && i + lane < end) d = __ldg(reinterpret_cast<const uint4*>(P.duos) + i + lane);
-    return d;
-  }
 };
 
-// issue the asynchronous copies of the generator's current chunk into `sb` (duo record `du` was fetched one iteration earlier)
+// Stage the generator's current chunk into `sb`: lane 0 arms the stage's mbarrier with the byte count and issues ONE bulk
+// (TMA) copy of the chunk's duo records — they are contiguous in the record-major table — plus, for the first chunk of a tile,
+// 16-byte cp.async copies of the segment's pose and mu.  No per-lane address arithmetic, no gathers, no LSU traffic.
 template <int NP>
-__device__ __forceinline__ void stage_issue(const DeviceProblem& P, const TileStream& g, uint4 du, int lane, StageBuf* sb,
+__device__ __forceinline__ void stage_issue(const DeviceProblem& P, const TileStream& g, int lane, StageBuf* sb,
                                             const double* __restrict__ poses, const double* __restrict__ mu_per_seg) {
-  if (g.valid()) {
-    if (g.i + lane < g.end) {
-      const float4* pm = P.cells_m + 3 * (size_t)du.x;
-      const float4* pf = P.cells_f + 3 * (size_t)du.y;
-      cp_async16(&sb->cell[0][lane], pm); cp_async16(&sb->cell[1][lane], pm + 1); cp_async16(&sb->cell[2][lane], pm + 2);
-      cp_async16(&sb->cell[3][lane], pf); cp_async16(&sb->cell[4][lane], pf + 1); cp_async16(&sb->cell[5][lane], pf + 2);
-      if (du.z != kNoCell) {
-        const float4* pg = P.cells_f + 3 * (size_t)du.z;
-        cp_async16(&sb->cell[6][lane], pg); cp_async16(&sb->cell[7][lane], pg + 1); cp_async16(&sb->cell[8][lane], pg + 2);
-      }
-      sb->duo[lane] = du;
-    }
-    if (lane == 0) {
+  if (lane == 0) {
+    if (g.valid()) {
+      const uint32_t n_here = g.end > g.i ? min(32u, g.end - g.i) : 0u;
       const bool first = g.i == g.begin;
-      if (first && g.i < g.end) {
-        const double* ps = poses + (size_t)g.seg * NP;
-        if (NP == 4) { cp_async16(&sb->pose[0], ps); cp_async16(&sb->pose[2], ps + 2); }
-        else { cp_async8(&sb->pose[0], ps); cp_async8(&sb->pose[1], ps + 1); cp_async8(&sb->pose[2], ps + 2); }
-        if (mu_per_seg) cp_async8(&sb->mu, mu_per_seg + g.seg);
+      if (n_here) {
+        const uint32_t bytes = n_here * (uint32_t)sizeof(DuoRec);
+        mbar_expect_tx(&sb->bar, bytes);
+        bulk_g2s(&sb->rec[0][0], P.duo_recs + g.i, bytes, &sb->bar);
+        if (first) {
+          const double* ps = poses + (size_t)g.seg * NP;
+          if (NP == 4) { cp_async16(&sb->pose[0], ps); cp_async16(&sb->pose[2], ps + 2); }
+          else { cp_async8(&sb->pose[0], ps); cp_async8(&sb->pose[1], ps + 1); cp_async8(&sb->pose[2], ps + 2); }
+          if (mu_per_seg) cp_async8(&sb->mu, mu_per_seg + g.seg);
+        }
       }
       sb->first = first ? 1u : 0u;
       sb->meta.k = g.k; sb->meta.i = g.i; sb->meta.end = g.end; sb->meta.seg = g.seg;
+    } else {
+      sb->meta.seg = 0xffffffffu;
     }
-  } else if (lane == 0) {
-    sb->meta.seg = 0xffffffffu;
   }
   cp_async_commit();
 }
@@ -460,16 +482,21 @@ __global__ void __launch_bounds__(kK3Threads, kMinCtas) k3_fused_kernel(DevicePr
   if (w >= P.n_warps) return;
   StageBuf* stage = stage_all[warp];
 
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) mbar_init(&stage[s].bar, 1u);
+    fence_mbar_init();
+  }
+  __syncwarp();
   TileStream gen;
   gen.init(P, w);
-  // prologue: chunks 0 .. kStages-2 in flight, duo records of chunk kStages-1 in registers
-  uint4 du = gen.fetch_duo(P, lane);
+  // prologue: chunks 0 .. kStages-2 in flight
 #pragma unroll
   for (int s = 0; s < kStages - 1; ++s) {
-    stage_issue<NP>(P, gen, du, lane, &stage[s], poses, mu_per_seg);
+    stage_issue<NP>(P, gen, lane, &stage[s], poses, mu_per_seg);
     gen.advance(P);
-    du = gen.fetch_duo(P, lane);
   }
+  uint32_t phase_bits = 0u;     // bit s: parity the next completion of stage s's barrier will have
 
   PoseConst kc; LossConst lc;
   double acc[NS]; double max_dd = 0.0; uint32_t n_bad = 0;
@@ -477,28 +504,28 @@ __global__ void __launch_bounds__(kK3Threads, kMinCtas) k3_fused_kernel(DevicePr
   for (int e = 0; e < NS; ++e) acc[e] = 0.0;
   int slot = 0;
   while (true) {
-    // ---- stage chunk j + kStages - 1, fetch the duo records of chunk j + kStages ----
+    // ---- stage chunk j + kStages - 1 ----
     int islot = slot + kStages - 1; if (islot >= kStages) islot -= kStages;
-    stage_issue<NP>(P, gen, du, lane, &stage[islot], poses, mu_per_seg);
+    stage_issue<NP>(P, gen, lane, &stage[islot], poses, mu_per_seg);
     gen.advance(P);
-    du = gen.fetch_duo(P, lane);
     // ---- chunk j has landed ----
     cp_async_wait<kStages - 1>();
     __syncwarp();
-    const StageBuf* sb = &stage[slot];
+    StageBuf* sb = &stage[slot];
     const ChunkMeta cm = sb->meta;
     if (cm.seg == 0xffffffffu) break;
-    const bool live = cm.i < cm.end;          // false: tile of an inactive segment (dropped)
+    const bool live = cm.i < cm.end;          // false: tile of an inactive segment (dropped, nothing was copied)
+    if (live) { mbar_wait(&sb->bar, (phase_bits >> slot) & 1u); phase_bits ^= 1u << slot; }
     if (sb->first && live) {
       make_pose_const<VARIANT>(sb->pose, kc);
       make_loss_const(lp, mu_per_seg ? sb->mu : lp.mu, lc);
     }
     if (cm.i + lane < cm.end) {
       RawCell m, f[2];
-      m.a = sb->cell[0][lane]; m.b = sb->cell[1][lane]; m.c = sb->cell[2][lane];
-      f[0].a = sb->cell[3][lane]; f[0].b = sb->cell[4][lane]; f[0].c = sb->cell[5][lane];
-      f[1].a = sb->cell[6][lane]; f[1].b = sb->cell[7][lane]; f[1].c = sb->cell[8][lane];
-      const bool two = sb->duo[lane].z != kNoCell;
+      m.a = sb->rec[lane][0]; m.b = sb->rec[lane][1]; m.c = sb->rec[lane][2];
+      f[0].a = sb->rec[lane][3]; f[0].b = sb->rec[lane][4]; f[0].c = sb->rec[lane][5];
+      f[1].a = sb->rec[lane][6]; f[1].b = sb->rec[lane][7]; f[1].c = sb->rec[lane][8];
+      const bool two = __float_as_uint(f[1].a.x) != kNoSecondPair;
       Moving mv;
       moving_part<VARIANT>(kc, m, mv);
       double dd[2], N[2][4], wgt[2], hrho[2], wd[2];
@@ -590,7 +617,8 @@ __global__ void __launch_bounds__(kK3Threads, kMinCtas) k3_fused_kernel(DevicePr
       for (int e = 0; e < NS; ++e) acc[e] = 0.0;
       max_dd = 0.0; n_bad = 0;
     }
-    __syncwarp();   // every lane is done with this slot's descriptor/pose before lane 0 restages it
+    fence_proxy_async();   // this lane's reads of the slot are ordered before the next bulk (async-proxy) write into it
+    __syncwarp();          // every lane is done with this slot before lane 0 restages it
     if (++slot == kStages) slot = 0;
   }
   cp_async_wait<0>();
@@ -631,45 +659,52 @@ __global__ void __launch_bounds__(kK3Threads, kMinCtas) k3_emit_kernel(DevicePro
   const uint32_t w = blockIdx.x * kWarpsPerCta + warp;
   if (w >= P.n_warps) return;
   StageBuf* stage = stage_all[warp];
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) mbar_init(&stage[s].bar, 1u);
+    fence_mbar_init();
+  }
+  __syncwarp();
   TileStream gen;
   gen.init(P, w);
-  uint4 du = gen.fetch_duo(P, lane);
 #pragma unroll
   for (int s = 0; s < kStages - 1; ++s) {
-    stage_issue<NP>(P, gen, du, lane, &stage[s], poses, nullptr);
+    stage_issue<NP>(P, gen, lane, &stage[s], poses, nullptr);
     gen.advance(P);
-    du = gen.fetch_duo(P, lane);
   }
   PoseConst kc;
-  uint32_t n_bad = 0;
+  uint32_t n_bad = 0, phase_bits = 0u;
   int slot = 0;
   while (true) {
     int islot = slot + kStages - 1; if (islot >= kStages) islot -= kStages;
-    stage_issue<NP>(P, gen, du, lane, &stage[islot], poses, nullptr);
+    stage_issue<NP>(P, gen, lane, &stage[islot], poses, nullptr);
     gen.advance(P);
-    du = gen.fetch_duo(P, lane);
     cp_async_wait<kStages - 1>();
     __syncwarp();
-    const StageBuf* sb = &stage[slot];
+    StageBuf* sb = &stage[slot];
     const ChunkMeta cm = sb->meta;
     if (cm.seg == 0xffffffffu) break;
-    if (sb->first && cm.i < cm.end) make_pose_const<VARIANT>(sb->pose, kc);
+    const bool live = cm.i < cm.end;
+    if (live) { mbar_wait(&sb->bar, (phase_bits >> slot) & 1u); phase_bits ^= 1u << slot; }
+    if (sb->first && live) make_pose_const<VARIANT>(sb->pose, kc);
     if (cm.i + lane < cm.end) {
       RawCell m, f0, f1;
-      m.a = sb->cell[0][lane]; m.b = sb->cell[1][lane]; m.c = sb->cell[2][lane];
-      f0.a = sb->cell[3][lane]; f0.b = sb->cell[4][lane]; f0.c = sb->cell[5][lane];
-      const uint4 d = sb->duo[lane];
+      m.a = sb->rec[lane][0]; m.b = sb->rec[lane][1]; m.c = sb->rec[lane][2];
+      f0.a = sb->rec[lane][3]; f0.b = sb->rec[lane][4]; f0.c = sb->rec[lane][5];
+      const uint32_t p0 = __ldg(P.duo_p0 + cm.i + lane);     // first pair of the duo: where its rows go in r / J
       Moving mv;
       moving_part<VARIANT>(kc, m, mv);
       double N[4] = {0.0, 0.0, 0.0, 0.0};
       const double dd0 = fixed_part<VARIANT, WANT_JAC>(kc, mv, f0, N);
-      emit_one<VARIANT, WANT_JAC>(kc, d.w, dd0, N, r_out, J_out, n_bad);
-      if (d.z != kNoCell) {
-        f1.a = sb->cell[6][lane]; f1.b = sb->cell[7][lane]; f1.c = sb->cell[8][lane];
+      emit_one<VARIANT, WANT_JAC>(kc, p0, dd0, N, r_out, J_out, n_bad);
+      f1.a = sb->rec[lane][6];
+      if (__float_as_uint(f1.a.x) != kNoSecondPair) {
+        f1.b = sb->rec[lane][7]; f1.c = sb->rec[lane][8];
         const double dd1 = fixed_part<VARIANT, WANT_JAC>(kc, mv, f1, N);
-        emit_one<VARIANT, WANT_JAC>(kc, d.w + 1u, dd1, N, r_out, J_out, n_bad);
+        emit_one<VARIANT, WANT_JAC>(kc, p0 + 1u, dd1, N, r_out, J_out, n_bad);
       }
     }
+    fence_proxy_async();
     __syncwarp();
     if (++slot == kStages) slot = 0;
   }
@@ -722,6 +757,24 @@ __global__ void __launch_bounds__(kSweepThreads) k3_sweep_kernel(DeviceProblem P
   if (active) cost_out[pi] = cost;
 }
 
+// Record-major duo table: record d = [moving cell | fixed cell of pair p0 | fixed cell of pair p0+1 (or the kNoSecondPair marker)],
+// 9 x float4 = 144 B, so that the 32 duos of a chunk are one contiguous 4608-byte block that a single bulk copy can land.
+__global__ void __launch_bounds__(256) build_duo_records_kernel(const float4* __restrict__ cells_m, const float4* __restrict__ cells_f,
+                                                                const Duo* __restrict__ duos, uint32_t n_duos, float4* __restrict__ recs,
+                                                                uint32_t* __restrict__ duo_p0) {
+  const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (uint64_t)n_duos * 9u) return;
+  const uint32_t d = (uint32_t)(e / 9u), j = (uint32_t)(e - (uint64_t)d * 9u);
+  const Duo du = duos[d];
+  float4 v;
+  if (j < 3) v = __ldg(cells_m + 3 * (size_t)du.im + j);
+  else if (j < 6) v = __ldg(cells_f + 3 * (size_t)du.jf0 + (j - 3));
+  else if (du.jf1 != kNoCell) v = __ldg(cells_f + 3 * (size_t)du.jf1 + (j - 6));
+  else { const float mk = __uint_as_float(kNoSecondPair); v = make_float4(mk, mk, mk, mk); }
+  recs[e] = v;
+  if (j == 0) duo_p0[d] = du.p0;
+}
+
 int loss_code(const LossParams& lp) {
   if (lp.kind == RANDT_LOSS_NONE) return L_NONE;
   if (lp.kind == RANDT_LOSS_WELSCH) return L_WELSCH;
@@ -767,6 +820,15 @@ cudaError_t launch_sweep_v(const DeviceProblem& p, uint32_t pb, uint32_t pe, con
 }
 
 }  // namespace
+
+cudaError_t launch_build_duo_records(const float4* cells_m, const float4* cells_f, const Duo* duos, uint32_t n_duos, DuoRec* recs,
+                                     uint32_t* duo_p0, cudaStream_t s, int* n_launches) {
+  if (n_duos == 0) return cudaSuccess;
+  const uint64_t n = (uint64_t)n_duos * 9u;
+  build_duo_records_kernel<<<(unsigned)((n + 255u) / 256u), 256, 0, s>>>(cells_m, cells_f, duos, n_duos, reinterpret_cast<float4*>(recs), duo_p0);
+  if (n_launches) *n_launches += 1;
+  return cudaGetLastError();
+}
 
 cudaError_t launch_eval_fused(const DeviceProblem& p, int variant, const double* d_poses, const LossParams& lp, const double* d_mu,
                               bool want_jac, double* d_out, unsigned long long* d_bad, cudaStream_t s, int* n_launches) {

@@ -1,0 +1,426 @@
+// Host-side C++ mirror of the reference's Map / Matcher surface for the NDT hot path (see include/randt_host.hpp).
+// Pure orchestration over the C-ABI: every per-point / per-cell / per-pair operation runs in the CUDA kernels.
+#include "../../include/randt_host.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <deque>
+#include <set>
+#include <array>
+#include <tuple>
+
+namespace randt {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// SE2d
+// ---------------------------------------------------------------------------------------------------------------------
+SE2d::SE2d(double theta, double tx, double ty) { v[0] = std::cos(theta); v[1] = std::sin(theta); v[2] = tx; v[3] = ty; }
+double SE2d::angle() const { return std::atan2(v[1], v[0]); }
+SE2d SE2d::operator*(const SE2d& o) const {
+  SE2d r;
+  double re = v[0] * o.v[0] - v[1] * o.v[1], im = v[0] * o.v[1] + v[1] * o.v[0];
+  const double n2 = re * re + im * im;
+  if (n2 != 1.0) { const double sc = 2.0 / (1.0 + n2); re *= sc; im *= sc; }   // Sophus SO2 product: first-order renormalisation
+  r.v[0] = re; r.v[1] = im;
+  r.v[2] = v[2] + (v[0] * o.v[2] - v[1] * o.v[3]);
+  r.v[3] = v[3] + (v[1] * o.v[2] + v[0] * o.v[3]);
+  return r;
+}
+void SE2d::matrix3f(float out[9]) const {
+  const float m[9] = {(float)v[0], (float)v[1], 0.f, (float)-v[1], (float)v[0], 0.f, (float)v[2], (float)v[3], 1.f};
+  std::memcpy(out, m, sizeof(m));
+}
+
+randt_grid_params NDTMapParameters::grid() const {
+  randt_grid_params g;
+  g.max_range = max_range; g.n_clusters = n_clusters; g.min_points = min_points_per_cell; g.size_x = size_x; g.size_y = size_y;
+  g.resolution = resolution; g.max_linf = max_neighbour_manhattan_distance;
+  return g;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Context
+// ---------------------------------------------------------------------------------------------------------------------
+Context::Context(int device, void* cuda_stream) {
+  const int rc = randt_ctx_create(device, cuda_stream, &ctx_);
+  if (rc != RANDT_OK) throw Error(rc, "randt_ctx_create failed: no usable CUDA device " + std::to_string(device));
+}
+Context::~Context() { randt_ctx_destroy(ctx_); }
+void Context::check(int rc) const {
+  if (rc != RANDT_OK) throw Error(rc, std::string("randt: ") + randt_last_error(ctx_));
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Map
+// ---------------------------------------------------------------------------------------------------------------------
+Map::Map(Context& ctx, const NDTMapParameters& p, uint32_t n_maps) : ctx_(&ctx), p_(p) {
+  const std::vector<uint32_t> off(n_maps + 1, 0u);
+  const randt_grid_params g = p_.grid();
+  ctx_->check(randt_map_upload(ctx_->get(), nullptr, nullptr, off.data(), n_maps, nullptr, &g, &map_));
+}
+Map::~Map() { randt_map_destroy(map_); }
+Map::Map(Map&& o) noexcept : ctx_(o.ctx_), p_(o.p_), map_(o.map_) { o.map_ = nullptr; }
+
+void Map::addClusters(const float* pts4, const uint32_t* scan_off, uint32_t n_scans) {
+  const randt_grid_params g = p_.grid();
+  randt_map* fresh = nullptr;
+  ctx_->check(randt_voxelize(ctx_->get(), pts4, scan_off, n_scans, &g, 0, &fresh));
+  randt_map_destroy(map_);
+  map_ = fresh;
+  host_valid_ = false;
+}
+void Map::transformMap(const SE2d* trans) {
+  const uint32_t B = n_maps();
+  std::vector<float> t(4 * (size_t)B);
+  for (uint32_t b = 0; b < B; ++b) for (int i = 0; i < 4; ++i) t[4 * b + i] = (float)trans[b].v[i];   // Sophus -> Affine2f cast
+  ctx_->check(randt_map_transform(ctx_->get(), map_, t.data()));
+  host_valid_ = false;
+}
+void Map::mergeMapCell(const Map& moving) {
+  ctx_->check(randt_map_merge(ctx_->get(), map_, moving.map_));
+  host_valid_ = false;
+}
+uint32_t Map::n_maps() const { uint32_t b = 0; randt_map_info(map_, &b, nullptr, nullptr); return b; }
+size_t Map::get_n_cells() const { uint32_t n = 0; randt_map_info(map_, nullptr, &n, nullptr); return n; }
+void Map::sync_host() const {
+  if (host_valid_) return;
+  uint32_t b = 0, n = 0;
+  randt_map_info(map_, &b, &n, nullptr);
+  h_cells_.assign((size_t)n * 12, 0.f); h_off_.assign(b + 1, 0u);
+  ctx_->check(randt_map_download(ctx_->get(), map_, h_cells_.data(), nullptr, nullptr, h_off_.data(), nullptr));
+  host_valid_ = true;
+}
+bool Map::getCellMeanAndCovariance(size_t idx, float* mean3, float* cov9) const {
+  sync_host();
+  if (idx >= h_cells_.size() / 12) return false;
+  std::memcpy(mean3, &h_cells_[idx * 12], 3 * sizeof(float));
+  std::memcpy(cov9, &h_cells_[idx * 12 + 3], 9 * sizeof(float));
+  return true;
+}
+const std::vector<uint32_t>& Map::cellOffsets() const { sync_host(); return h_off_; }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// NdtCostFunction
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+// BarronLoss / WelschLoss::Evaluate wrapped in ScaledLoss (R/src/ndt_registration/ceres_loss_functions.cpp:10-39) — host copy used
+// only for the per-residual correction of the ceres adapter; the solver path evaluates the loss inside K3.
+void loss_rho(const randt_loss& l, double s, double rho[3]) {
+  if (l.kind == RANDT_LOSS_WELSCH) {
+    const double b = l.mu * l.scale * l.scale, c = -1.0 / b, ex = std::exp(s * c);
+    rho[0] = b * (1 - ex); rho[1] = ex; rho[2] = c * ex;
+  } else if (l.kind == RANDT_LOSS_BARRON) {
+    const double b = l.mu * l.scale * l.scale, c = 1 / b, factor = std::abs(l.alpha - 2.0), e = 0.5 * l.alpha;
+    if (l.alpha >= 2.0) { rho[0] = s; rho[1] = 1; rho[2] = 0; }
+    else if (std::abs(l.alpha) <= 0.05) {
+      const double sum = 1.0 + s * c, inv = 1.0 / sum;
+      rho[0] = b * std::log(sum); rho[1] = std::max(2.2250738585072014e-308, inv); rho[2] = -c * (inv * inv);
+    } else {
+      const double pre = b * factor / l.alpha, ts = 2 * c / factor, u = s * ts + 1.0;
+      rho[0] = pre * (std::pow(u, e) - 1.); rho[1] = pre * e * std::pow(u, e - 1.) * ts;
+      rho[2] = pre * e * (e - 1) * std::pow(u, e - 2.) * ts * ts;
+    }
+  } else { rho[0] = s; rho[1] = 1; rho[2] = 0; }
+  rho[0] *= l.weight; rho[1] *= l.weight; rho[2] *= l.weight;
+}
+}  // namespace
+
+NdtCostFunction::NdtCostFunction(Context& ctx, randt_problem* problem, int variant) : ctx_(&ctx), problem_(problem), variant_(variant) {
+  uint32_t S = 0;
+  randt_problem_info(problem_, &S, &n_pairs_, nullptr, nullptr);
+  if (S != 1) { randt_problem_destroy(problem_); throw Error(RANDT_E_INVALID, "NdtCostFunction needs a single-segment problem"); }
+  if (variant_ <= RANDT_VAR_SE2_XY) mutable_parameter_block_sizes()->push_back(4);
+  else { mutable_parameter_block_sizes()->push_back(2); mutable_parameter_block_sizes()->push_back(1); }   // pos[2], rot[1] (ndt_matcher.cpp:245)
+  set_num_residuals((int)n_pairs_ + 1);
+  r_.resize(n_pairs_); J_.resize((size_t)n_pairs_ * 4);
+}
+NdtCostFunction::~NdtCostFunction() { randt_problem_destroy(problem_); }
+void NdtCostFunction::setLoss(const randt_loss* loss) { has_loss_ = loss != nullptr; if (loss) loss_ = *loss; }
+
+double NdtCostFunction::maxRawResidual(const double* pose) const {
+  ctx_->check(randt_eval_emit(ctx_->get(), problem_, variant_, pose, r_.data(), nullptr));
+  double m = 0;
+  for (double r : r_) if (r > m) m = r;
+  return m;
+}
+
+bool NdtCostFunction::Evaluate(double const* const* parameters, double* residuals, double** jacobians) const {
+  const bool se2 = variant_ <= RANDT_VAR_SE2_XY;
+  double params[4];
+  if (se2) std::memcpy(params, parameters[0], 4 * sizeof(double));
+  else { params[0] = parameters[0][0]; params[1] = parameters[0][1]; params[2] = parameters[1][0]; }
+  const int np = se2 ? 4 : 3;
+  const bool want_j = jacobians && (jacobians[0] || (!se2 && jacobians[1]));
+  if (randt_eval_emit(ctx_->get(), problem_, variant_, params, r_.data(), want_j ? J_.data() : nullptr) != RANDT_OK) return false;
+  double deficit = 0.0;   // sum rho - sum rho' r^2  (>= 0 for a concave rho with rho(0) = 0)
+  for (uint32_t p = 0; p < n_pairs_; ++p) {
+    double r = r_[p];
+    if (!std::isfinite(r)) return false;   // degenerate pair: ceres rejects the step (Evaluate returns false)
+    double sc = 1.0;
+    if (has_loss_) {
+      double rho[3];
+      const double sq = r * r;
+      loss_rho(loss_, sq, rho);
+      sc = std::sqrt(rho[1]);               // Corrector with rho'' <= 0: residual and Jacobian scaled by sqrt(rho')
+      deficit += rho[0] - rho[1] * sq;
+    }
+    residuals[p] = sc * r;
+    if (want_j) {
+      const double* Jp = &J_[(size_t)p * np];
+      if (se2) { if (jacobians[0]) for (int i = 0; i < 4; ++i) jacobians[0][(size_t)p * 4 + i] = sc * Jp[i]; }
+      else {
+        if (jacobians[0]) { jacobians[0][(size_t)p * 2] = sc * Jp[0]; jacobians[0][(size_t)p * 2 + 1] = sc * Jp[1]; }
+        if (jacobians[1]) jacobians[1][p] = sc * Jp[2];
+      }
+    }
+  }
+  residuals[n_pairs_] = std::sqrt(std::max(0.0, deficit));
+  if (want_j) {
+    if (se2) { if (jacobians[0]) for (int i = 0; i < 4; ++i) jacobians[0][(size_t)n_pairs_ * 4 + i] = 0.0; }
+    else {
+      if (jacobians[0]) { jacobians[0][(size_t)n_pairs_ * 2] = 0.0; jacobians[0][(size_t)n_pairs_ * 2 + 1] = 0.0; }
+      if (jacobians[1]) jacobians[1][n_pairs_] = 0.0;
+    }
+  }
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Matcher
+// ---------------------------------------------------------------------------------------------------------------------
+int Matcher::variant(bool use_intensity_as_dimension) const {
+  const bool manifold = parameters_.optimize_on_manifold && !parameters_.use_analytic_expressions_for_optimization;
+  if (manifold) return use_intensity_as_dimension ? RANDT_VAR_SE2_INTENSITY : RANDT_VAR_SE2_XY;
+  return use_intensity_as_dimension ? RANDT_VAR_VEC_INTENSITY : RANDT_VAR_VEC_XY;
+}
+
+randt_problem* Matcher::associate(const SE2d* initial_guess, const Map& fixed_ndt, const Map& moving_ndt, bool use_intensity_as_dimension,
+                                  int n_neighbours) const {
+  const uint32_t B = fixed_ndt.n_maps();
+  std::vector<double> pose0(4 * (size_t)B);
+  for (uint32_t b = 0; b < B; ++b) std::memcpy(&pose0[4 * b], initial_guess[b].v, 4 * sizeof(double));
+  // ndt_matcher.cpp:201: Mahalanobis lookup needs both use_intensity_as_dimension and lookup_mahalanobis, else Euclidean xy
+  const int metric = (use_intensity_as_dimension && parameters_.lookup_mahalanobis) ? RANDT_LOOKUP_MAHALANOBIS_INTENSITY : RANDT_LOOKUP_EUCLID_XY;
+  randt_problem* prob = nullptr;
+  ctx_->check(randt_associate(ctx_->get(), fixed_ndt.handle(), moving_ndt.handle(), pose0.data(), n_neighbours, metric, &prob));
+  return prob;
+}
+
+std::unique_ptr<NdtCostFunction> Matcher::addNDTFactor(const SE2d& initial_guess, const Map& fixed_ndt, const Map& moving_ndt,
+                                                       bool use_intensity_as_dimension, int n_neighbours) const {
+  if (fixed_ndt.n_maps() != 1 || moving_ndt.n_maps() != 1) throw Error(RANDT_E_INVALID, "addNDTFactor takes single maps");
+  randt_problem* prob = associate(&initial_guess, fixed_ndt, moving_ndt, use_intensity_as_dimension, n_neighbours);
+  return std::unique_ptr<NdtCostFunction>(new NdtCostFunction(*ctx_, prob, variant(use_intensity_as_dimension)));
+}
+
+std::vector<double> Matcher::estimateLoopConstraints(std::vector<SE2d>& trans, const Map& old_ndts, Map& new_ndts, int max_gnc_steps,
+                                                     bool use_intensity_as_dimension, double scale) const {
+  const uint32_t B = old_ndts.n_maps();
+  if (trans.size() != B || new_ndts.n_maps() != B) throw Error(RANDT_E_INVALID, "estimateLoopConstraints: batch sizes differ");
+  randt_problem* prob = associate(trans.data(), old_ndts, new_ndts, use_intensity_as_dimension, parameters_.n_results_kd_lookup);
+  struct Guard { randt_problem* p; ~Guard() { randt_problem_destroy(p); } } guard{prob};
+  const int var = variant(use_intensity_as_dimension);
+  const int np = var <= RANDT_VAR_SE2_XY ? 4 : 3;
+  std::vector<double> poses((size_t)B * np), result((size_t)B * RANDT_REG_STRIDE);
+  for (uint32_t b = 0; b < B; ++b) {
+    if (np == 4) std::memcpy(&poses[4 * b], trans[b].v, 4 * sizeof(double));
+    else { poses[3 * b] = trans[b].v[2]; poses[3 * b + 1] = trans[b].v[3]; poses[3 * b + 2] = trans[b].angle(); }   // pos, rot = log()(2)
+  }
+  randt_loss loss;   // ScaledLoss(BarronLoss(scale, convexity, mu), 1)  (ndt_matcher.cpp:479)
+  loss.kind = RANDT_LOSS_BARRON; loss.scale = scale; loss.alpha = parameters_.loss_function_convexity; loss.mu = 1.0; loss.weight = 1.0;
+  randt_solver_options opt;
+  randt_solver_options_default(&opt);
+  opt.max_num_iterations = parameters_.max_iteration;
+  // the residual blocks hang off a copy of the pose that carries no manifold (ndt_matcher.cpp:445 vs 452 -> 233): raw ambient parameters
+  opt.use_manifold = 0;
+  opt.gnc_loss_scale = parameters_.loss_function_scale;
+  opt.gnc_divisor = parameters_.gnc_control_parameter_divisor;
+  opt.gnc_max_steps = max_gnc_steps;
+  ctx_->check(randt_register_batch(ctx_->get(), prob, var, poses.data(), &loss, &opt, result.data()));
+  std::vector<double> scores(B);
+  for (uint32_t b = 0; b < B; ++b) {
+    if (np == 4) std::memcpy(trans[b].v, &poses[4 * b], 4 * sizeof(double));
+    else trans[b] = SE2d(poses[3 * b + 2], poses[3 * b], poses[3 * b + 1]);
+    scores[b] = result[(size_t)b * RANDT_REG_STRIDE + RANDT_REG_SCORE];
+  }
+  return scores;
+}
+
+double Matcher::estimateLoopConstraint(SE2d& trans, const Map& old_ndt, Map& new_ndt, int max_gnc_steps, bool use_intensity_as_dimension,
+                                       double scale) const {
+  std::vector<SE2d> t(1, trans);
+  const std::vector<double> s = estimateLoopConstraints(t, old_ndt, new_ndt, max_gnc_steps, use_intensity_as_dimension, scale);
+  trans = t[0];
+  return s[0];
+}
+
+double Matcher::estimateTransformGlobalBNB(SE2d& trans, const Map& fixed_ndt, Map& moving_ndt, bool use_intensity_as_dimension, double scale,
+                                           double search_window_size_linear, double search_window_size_angular) const {
+  search_window_size_linear = std::min(search_window_size_linear, parameters_.csm_window_linear);
+  search_window_size_angular = std::min(search_window_size_angular, parameters_.csm_window_angular);
+  randt_problem* prob = associate(&trans, fixed_ndt, moving_ndt, use_intensity_as_dimension, 4);   // n_neighbours = 4 (ndt_matcher.cpp:521)
+  struct Guard { randt_problem* p; ~Guard() { randt_problem_destroy(p); } } guard{prob};
+  uint32_t n_blocks = 0;
+  randt_problem_info(prob, nullptr, &n_blocks, nullptr, nullptr);
+  const int var = variant(use_intensity_as_dimension);
+  randt_loss loss;   // bare BarronLoss(scale, convexity): mu = 1, no ScaledLoss (ndt_matcher.cpp:517)
+  loss.kind = RANDT_LOSS_BARRON; loss.scale = scale; loss.alpha = parameters_.loss_function_convexity; loss.mu = 1.0; loss.weight = 1.0;
+
+  const double linear_step = parameters_.csm_linear_step;
+  const double max_range = parameters_.csm_max_px_accurate_range;
+  const double angular_step = std::acos(1 - ((linear_step * linear_step) / (2 * max_range * max_range)));
+  const double cost_threshold = parameters_.csm_cost_threshold;
+  const size_t n_iter = (size_t)parameters_.csm_n_iter;
+  const double initial_linear_step = std::pow(2, (double)n_iter - 1) * linear_step;
+
+  typedef std::array<float, 9> Key;
+  std::set<Key> calculated_points;                       // the reference keeps a vector + std::find (O(n^2)); same membership test
+  auto key = [](const SE2d& t) { Key k; t.matrix3f(k.data()); return k; };
+  std::vector<std::pair<SE2d, size_t>> level;            // (transform, tree level) in the reference's queue order
+  for (double tx = -search_window_size_linear / 2.0; tx <= search_window_size_linear / 2.0; tx += initial_linear_step)
+    for (double ty = -search_window_size_linear / 2.0; ty <= search_window_size_linear / 2.0; ty += initial_linear_step)
+      for (double a = -search_window_size_angular / 2.0; a < search_window_size_angular / 2.0; a += angular_step) {
+        const SE2d cur = trans * SE2d(a, tx, ty);
+        level.emplace_back(cur, (size_t)1);
+        calculated_points.insert(key(cur));               // the coarsest level is not de-duplicated against itself (push_back only)
+      }
+  double min_cost = 100000.0;
+  SE2d best_trans;
+  const int np = var <= RANDT_VAR_SE2_XY ? 4 : 3;
+  // The reference pops one transform at a time; children always join the back of the queue, so evaluating everything that is
+  // queued in one sweep and then walking the results in queue order visits, prunes and expands exactly the same nodes.
+  while (!level.empty()) {
+    std::vector<double> poses(level.size() * (size_t)np), cost(level.size());
+    for (size_t i = 0; i < level.size(); ++i) {
+      const SE2d& t = level[i].first;
+      if (np == 4) std::memcpy(&poses[4 * i], t.v, 4 * sizeof(double));
+      else { poses[3 * i] = t.v[2]; poses[3 * i + 1] = t.v[3]; poses[3 * i + 2] = t.angle(); }
+    }
+    ctx_->check(randt_sweep_costs(ctx_->get(), prob, 0, var, poses.data(), (uint32_t)level.size(), &loss, cost.data()));
+    std::vector<std::pair<SE2d, size_t>> next;
+    for (size_t i = 0; i < level.size(); ++i) {
+      const double current_cost = cost[i] / (double)n_blocks;
+      const size_t current_level = level[i].second;
+      if (current_cost < cost_threshold) {
+        if (current_cost < min_cost) { best_trans = level[i].first; min_cost = current_cost; }
+        if (current_level < n_iter) {
+          const double step = std::pow(2.0, (double)current_level) * linear_step;
+          for (double tx = -step; tx <= step; tx += step)
+            for (double ty = -step; ty <= step; ty += step)
+              for (double a = -angular_step; a <= angular_step; a += angular_step) {
+                const SE2d sampled = level[i].first * SE2d(a, tx, ty);
+                if (calculated_points.insert(key(sampled)).second) next.emplace_back(sampled, current_level + 1);
+              }
+        }
+      }
+    }
+    level.swap(next);
+  }
+  trans = best_trans;
+  return min_cost;
+}
+
+}  // namespace randt
+
+// ---------------------------------------------------------------------------------------------------------------------
+// C hooks for the Python tests
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+thread_local std::string g_last_error;
+randt::NDTMapParameters map_params(const randt_grid_params& g) {
+  randt::NDTMapParameters p;
+  p.resolution = g.resolution; p.size_x = g.size_x; p.size_y = g.size_y; p.max_neighbour_manhattan_distance = g.max_linf;
+  p.min_points_per_cell = g.min_points; p.max_range = g.max_range; p.n_clusters = g.n_clusters;
+  return p;
+}
+template <typename F>
+int guarded(F&& f) {
+  try { f(); return RANDT_OK; }
+  catch (const randt::Error& e) { g_last_error = e.what(); return e.code; }
+  catch (const std::exception& e) { g_last_error = e.what(); return RANDT_E_INVALID; }
+}
+}  // namespace
+
+extern "C" {
+
+const char* randt_hostapi_last_error(void) { return g_last_error.c_str(); }
+
+int randt_hostapi_loop_constraints(int device, const randt_grid_params* gp, const float* fixed_pts4, const uint32_t* fixed_off,
+                                   const float* moving_pts4, const uint32_t* moving_off, uint32_t n, int k, double loss_function_scale,
+                                   double convexity, double divisor, int max_gnc_steps, double loop_scale, int optimize_on_manifold,
+                                   double* poses_io, double* scores) {
+  return guarded([&] {
+    randt::Context ctx(device);
+    const randt::NDTMapParameters mp = map_params(*gp);
+    randt::Map fixed(ctx, mp, n), moving(ctx, mp, n);
+    fixed.addClusters(fixed_pts4, fixed_off, n);
+    moving.addClusters(moving_pts4, moving_off, n);
+    randt::NDTMatcherParameters p;
+    p.n_results_kd_lookup = k; p.loss_function_scale = loss_function_scale; p.loss_function_convexity = convexity;
+    p.gnc_control_parameter_divisor = divisor; p.optimize_on_manifold = optimize_on_manifold != 0;
+    randt::Matcher m(ctx);
+    m.initialize(p);
+    std::vector<randt::SE2d> t(n);
+    for (uint32_t b = 0; b < n; ++b) std::memcpy(t[b].v, poses_io + 4 * b, 4 * sizeof(double));
+    std::vector<double> s;
+    if (n == 1) { s.push_back(m.estimateLoopConstraint(t[0], fixed, moving, max_gnc_steps, true, loop_scale)); }
+    else s = m.estimateLoopConstraints(t, fixed, moving, max_gnc_steps, true, loop_scale);
+    for (uint32_t b = 0; b < n; ++b) { std::memcpy(poses_io + 4 * b, t[b].v, 4 * sizeof(double)); scores[b] = s[b]; }
+  });
+}
+
+int randt_hostapi_cost_function(int device, const randt_grid_params* gp, const float* fixed_pts4, uint32_t n_fixed, const float* moving_pts4,
+                                uint32_t n_moving, int k, const double* guess4, const randt_loss* loss, const double* pose4, double* residuals,
+                                double* jacobian, uint32_t cap, uint32_t* num_residuals, double* max_raw) {
+  return guarded([&] {
+    randt::Context ctx(device);
+    const randt::NDTMapParameters mp = map_params(*gp);
+    randt::Map fixed(ctx, mp), moving(ctx, mp);
+    const uint32_t fo[2] = {0, n_fixed}, mo[2] = {0, n_moving};
+    fixed.addClusters(fixed_pts4, fo, 1);
+    moving.addClusters(moving_pts4, mo, 1);
+    randt::NDTMatcherParameters p;
+    p.n_results_kd_lookup = k;
+    randt::Matcher m(ctx);
+    m.initialize(p);
+    randt::SE2d g;
+    std::memcpy(g.v, guess4, 4 * sizeof(double));
+    std::unique_ptr<randt::NdtCostFunction> cf = m.addNDTFactor(g, fixed, moving, true, k);
+    const ceres::CostFunction* base = cf.get();   // driven through the ceres interface only
+    *num_residuals = (uint32_t)base->num_residuals();
+    if ((uint32_t)base->num_residuals() > cap) throw randt::Error(RANDT_E_CAPACITY, "residual buffer too small");
+    if (base->parameter_block_sizes().size() != 1 || base->parameter_block_sizes()[0] != 4) throw randt::Error(RANDT_E_INVALID, "unexpected block sizes");
+    cf->setLoss(loss);
+    const double* params[1] = {pose4};
+    double* jac[1] = {jacobian};
+    if (!base->Evaluate(params, residuals, jacobian ? jac : nullptr)) throw randt::Error(RANDT_E_NONFINITE, "Evaluate returned false");
+    if (max_raw) *max_raw = cf->maxRawResidual(pose4);
+  });
+}
+
+int randt_hostapi_bnb(int device, const randt_grid_params* gp, const float* fixed_pts4, uint32_t n_fixed, const float* moving_pts4, uint32_t n_moving,
+                      double convexity, double scale, double window_linear, double window_angular, double linear_step, double max_px_range,
+                      double cost_threshold, int n_iter, double* pose_io4, double* min_cost, uint32_t* n_evaluated) {
+  return guarded([&] {
+    randt::Context ctx(device);
+    const randt::NDTMapParameters mp = map_params(*gp);
+    randt::Map fixed(ctx, mp), moving(ctx, mp);
+    const uint32_t fo[2] = {0, n_fixed}, mo[2] = {0, n_moving};
+    fixed.addClusters(fixed_pts4, fo, 1);
+    moving.addClusters(moving_pts4, mo, 1);
+    randt::NDTMatcherParameters p;
+    p.loss_function_convexity = convexity; p.csm_linear_step = linear_step; p.csm_max_px_accurate_range = max_px_range;
+    p.csm_cost_threshold = cost_threshold; p.csm_n_iter = n_iter; p.csm_window_linear = window_linear; p.csm_window_angular = window_angular;
+    randt::Matcher m(ctx);
+    m.initialize(p);
+    randt::SE2d t;
+    std::memcpy(t.v, pose_io4, 4 * sizeof(double));
+    const uint64_t l0 = ctx.launchCount();
+    *min_cost = m.estimateTransformGlobalBNB(t, fixed, moving, true, scale, window_linear, window_angular);
+    if (n_evaluated) *n_evaluated = (uint32_t)(ctx.launchCount() - l0);
+    std::memcpy(pose_io4, t.v, 4 * sizeof(double));
+  });
+}
+
+}  // extern "C"
