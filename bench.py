@@ -157,6 +157,35 @@ def cpu_fused(host, poses, loss, n_problems, threads, repeats):
     return P_ * repeats / t, t, out
 
 
+def cpu_registrations(p, host, poses, n_sample, threads):
+    """oracle leg: Matcher::estimateLoopConstraint restated (GNC + ceres-LM, Jet<4> evaluation) on the first n_sample problems.
+    -> (registrations/s on one thread, registrations/s on `threads` threads, mean minimiser iterations)"""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle_py as O
+    seg = host["seg"]
+
+    def solve(s):
+        a, b = int(seg[s]), int(seg[s + 1])
+        pm = host["pm"][a:b]; pf = host["pf"][a:b]
+        m0, f0 = int(pm.min()), int(pf.min())
+        cm = host["cells_m"][m0:int(pm.max()) + 1]; cf = host["cells_f"][f0:int(pf.max()) + 1]
+        dummy_slot = np.full(p.size_x * p.size_y, -1, np.int32)     # pairs are given: the slot table is not consulted
+        r = O.loop_constraint(cf, dummy_slot, p.size_x, p.size_y, p.resolution, p.max_neighbor_linf_distance, cm, poses[s], p.n_results_nn_lookup,
+                              matcher_loss_scale=p.loss_function_scale, loop_scale=p.loop_closure_scale, alpha=p.loss_function_convexity,
+                              divisor=p.gnc_control_parameter_divisor, max_gnc_steps=p.loop_closure_gnc_steps, max_iterations=p.max_iteration,
+                              on_manifold=False, pairs=(pm - m0, pf - f0))
+        return r["iterations"]
+    t0 = time.perf_counter()
+    its = [solve(s) for s in range(n_sample)]
+    t1 = time.perf_counter() - t0
+    with ThreadPoolExecutor(max_workers=threads) as ex:       # the ctypes call releases the GIL
+        t0 = time.perf_counter()
+        reps = max(1, (threads * 2) // n_sample + 1)
+        list(ex.map(solve, [s % n_sample for s in range(n_sample * reps)]))
+        tN = time.perf_counter() - t0
+    return n_sample / t1, n_sample * reps / tN, float(np.mean(its))
+
+
 def run_reference(args, p, loss):
     """--impl reference: CPU restatement of the reference path (the reference itself is not buildable here)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -177,6 +206,7 @@ def run_reference(args, p, loss):
         cpu_fused(host, poses, loss, n_sample, threads, 1)
     dt = time.perf_counter() - t0
     value = P_ * args.steps / dt
+    reg1, regN, reg_it = cpu_registrations(p, host, poses, min(args.reg_cpu_sample, n_sample), threads) if args.reg_steps > 0 else (None, None, None)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -185,6 +215,8 @@ def run_reference(args, p, loss):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": "%d problems (%d pairs) per step, Jet<4> autodiff + Barron corrector + J^T J accumulation" % (n_sample, P_)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "registrations": {"value": regN, "unit": "registrations/s", "single_thread_value": reg1, "cores": threads, "mean_iterations": reg_it,
+                          "what": "Matcher::estimateLoopConstraint restated (GNC + ceres-LM, Jet<4> evaluation), oxford loop-closure parameters"},
     }
     print(json.dumps(line))
 
@@ -233,6 +265,8 @@ def main():
     ap.add_argument("--problems", type=int, default=DEFAULT_PROBLEMS, help="independent registration problems per GPU per step")
     ap.add_argument("--ref-problems", type=int, default=2048, help="problems per step of the CPU reference arm (bounded sample)")
     ap.add_argument("--cpu-sample", type=int, default=1024, help="problems in the cpu_baseline sample")
+    ap.add_argument("--reg-steps", type=int, default=3, help="timed full-batch GNC+LM registration solves (0 disables the registrations leg)")
+    ap.add_argument("--reg-cpu-sample", type=int, default=48, help="registrations the oracle solves for the CPU comparison")
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -311,17 +345,60 @@ def main():
             step_e2e()
         barrier()
         e2e_s = time.perf_counter() - t0
+        # ---- registrations: every problem of the batch solved to convergence (GNC + LM), K3 + K4, device resident ----
+        reg = None
+        if args.reg_steps > 0:
+            # estimateLoopConstraint semantics (ndt_matcher.cpp:426-493): loop-closure scale and GNC steps, raw ambient pose block
+            opt = capi.solver_options(use_manifold=0, gnc_loss_scale=p.loss_function_scale, gnc_divisor=p.gnc_control_parameter_divisor,
+                                      gnc_max_steps=p.loop_closure_gnc_steps, max_num_iterations=p.max_iteration)
+            d_reg = torch.empty_like(d_poses)
+            d_res = torch.zeros((S, capi.REG_STRIDE), dtype=torch.float64, device="cuda:%d" % local)
+            h_reg = torch.from_numpy(poses.copy()).pin_memory(); h_res = torch.zeros((S, capi.REG_STRIDE), dtype=torch.float64).pin_memory()
+
+            def step_reg():
+                d_reg.copy_(d_poses, non_blocking=True)
+                prob.register_batch_dev(d_reg.data_ptr(), d_res.data_ptr(), loss, opt)
+
+            step_reg()
+            barrier()
+            l1 = ctx.launch_count
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record(stream)
+            for _ in range(args.reg_steps):
+                step_reg()
+            r1.record(stream)
+            barrier()
+            reg_ms = r0.elapsed_time(r1) / args.reg_steps
+            reg_launches = (ctx.launch_count - l1) // args.reg_steps
+            # end to end through the host-pointer call: initial guesses H2D, refined poses + result records D2H
+            t0 = time.perf_counter()
+            for _ in range(args.reg_steps):
+                h_reg.numpy()[:] = poses
+                lp_ = capi.C.byref(loss)
+                ctx._check(capi.lib().randt_register_batch(ctx._h, prob._h, 0, capi._ptr(h_reg.numpy()), lp_, capi.C.byref(opt), capi._ptr(h_res.numpy())))
+            barrier()
+            reg_e2e_ms = (time.perf_counter() - t0) * 1e3 / args.reg_steps
+            res_np = d_res.cpu().numpy()
+            reg = {"ms_per_batch": reg_ms, "e2e_ms_per_batch": reg_e2e_ms, "launches_per_batch": int(reg_launches),
+                   "mean_iterations": float(res_np[:, capi.REG_ITERATIONS].mean()), "mean_gnc_solves": float(res_np[:, capi.REG_GNC_SOLVES].mean()),
+                   "failed": int((res_np[:, capi.REG_STATUS] != 0).sum()), "rows": res_np, "poses": d_reg.cpu().numpy()}
     bad = ctx.take_bad_pairs()
 
-    t_ms = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda:%d" % local)
+    t_ms = torch.tensor([ms, e2e_s * 1e3, reg["ms_per_batch"] if reg else 0.0, reg["e2e_ms_per_batch"] if reg else 0.0], dtype=torch.float64,
+                        device="cuda:%d" % local)
     tot = torch.tensor([float(Pn), float(S)], dtype=torch.float64, device="cuda:%d" % local)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
         # the only data exchange of the sharded job: gather every rank's per-problem result (here: cost) on all ranks
-        gathered = [torch.empty(S, dtype=torch.float64, device="cuda:%d" % local) for _ in range(world)]
-        dist.all_gather(gathered, d_out[:, 20].contiguous())
-    ms_all, e2e_ms_all = float(t_ms[0]), float(t_ms[1])
+        if reg:
+            from randt_slam_b200 import shard
+            rows = np.zeros((S, shard.ROW)); rows[:, :4] = reg["poses"]; rows[:, 4] = reg["rows"][:, capi.REG_SCORE]
+            rows[:, 5] = reg["rows"][:, capi.REG_ITERATIONS]; rows[:, 6] = reg["rows"][:, capi.REG_STATUS]
+            table = shard.gather_results(rows, rank * S, world * S, rank, world, device=torch.device("cuda", local))   # NCCL all_gather
+            assert table.shape[0] == world * S and not np.isnan(table[:, 4]).any()
+    ms_all, e2e_ms_all, reg_ms_all, reg_e2e_ms_all = float(t_ms[0]), float(t_ms[1]), float(t_ms[2]), float(t_ms[3])
+    seg_all = float(tot[1])
     pairs_all = float(tot[0])
 
     if rank == 0:
@@ -349,6 +426,13 @@ def main():
             "clocks": clocks,
             "degenerate_pairs": bad,
         }
+        if reg:
+            line["registrations"] = {
+                "value": seg_all / (reg_ms_all * 1e-3), "unit": "registrations/s", "e2e_value": seg_all / (reg_e2e_ms_all * 1e-3),
+                "ms_per_batch": reg_ms_all, "batch_per_gpu": S, "launches_per_batch": reg["launches_per_batch"],
+                "mean_iterations": reg["mean_iterations"], "mean_gnc_solves": reg["mean_gnc_solves"], "failed": reg["failed"],
+                "what": "full GNC + Levenberg-Marquardt solve of every problem of the batch (randt_register_batch: K3 fused + K4 per LM iteration), "
+                        "Matcher::estimateLoopConstraint semantics with the oxford loop-closure parameters"}
         if not args.no_cpu_baseline:
             from oracle import oracle_py as O
             n_s = min(args.cpu_sample, S)
@@ -362,6 +446,10 @@ def main():
             ref = np.concatenate([out_cpu["H"].reshape(n_s, 16), out_cpu["g"], out_cpu["cost"][:, None]], 1)
             got = np.concatenate([g[:, :16], g[:, 16:20], g[:, 20:21]], 1)
             err = float(np.max(np.abs(got - ref)) / np.max(np.abs(ref)))
+            if reg:
+                c1, cN, cit = cpu_registrations(p, host, poses, min(args.reg_cpu_sample, S), threads)
+                line["registrations"]["cpu_baseline"] = {"value": cN, "single_thread_value": c1, "cores": threads, "kind": "port", "mean_iterations": cit,
+                                                         "sample": "first %d problems" % min(args.reg_cpu_sample, S)}
             line["cpu_baseline"] = {"value": vN, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": "first %d problems (%d pairs) x %d passes, Jet<4> autodiff + corrector + J^T J" % (n_s, int(host["seg"][n_s]), reps),
                                     "single_thread_value": v1, "gpu_vs_oracle_max_rel_err_on_sample": err}

@@ -314,4 +314,63 @@ inline void sweep_costs(int variant, const Cell12* cm, const Cell12* cf, const u
   }
 }
 
+// a13  Matcher::estimateTransformGlobalBNB   R/src/ndt_registration/ndt_matcher.cpp:495-608, restated sequentially exactly as written:
+// coarse grid over the window, FIFO queue, cost = sum 0.5 rho(r^2) / num_blocks under a bare BarronLoss(scale, alpha) (mu = 1),
+// prune at cost_threshold, expand 3 x 3 x 3 children at half the linear step, de-duplicate on the float-cast 3x3 matrix.
+struct BnbResult { double pose[4]; double min_cost; int n_evaluated; };
+inline void se2_from(double a, double tx, double ty, double out[4]) { out[0] = std::cos(a); out[1] = std::sin(a); out[2] = tx; out[3] = ty; }
+inline BnbResult bnb_search(const NdtMap& fixed, const NdtMap& moving, const double trans0[4], int variant, double alpha, double scale,
+                            double window_linear, double window_angular, double linear_step, double max_px_range, double cost_threshold,
+                            int n_iter_in, int metric = LOOKUP_MAHALANOBIS_INTENSITY) {
+  BnbResult R{};
+  PairList pl;
+  associate(fixed, moving, trans0, 4, metric, pl);   // n_neighbours = 4 (ndt_matcher.cpp:521)
+  const size_t P = pl.im.size();
+  Loss loss; loss.kind = LOSS_BARRON; loss.a = scale; loss.alpha = alpha; loss.mu = 1.0; loss.weight = 1.0;
+  const double angular_step = std::acos(1 - ((linear_step * linear_step) / (2 * max_px_range * max_px_range)));
+  const size_t n_iter = (size_t)n_iter_in;
+  const double initial_linear_step = std::pow(2, (double)n_iter - 1) * linear_step;
+  struct Node { double t[4]; size_t level; };
+  std::vector<std::vector<float>> calculated;
+  auto key = [](const double t[4]) { return std::vector<float>{(float)t[0], (float)t[1], 0.f, (float)-t[1], (float)t[0], 0.f, (float)t[2], (float)t[3], 1.f}; };
+  std::vector<Node> queue;   // FIFO: index `head` is the front
+  for (double tx = -window_linear / 2.0; tx <= window_linear / 2.0; tx += initial_linear_step)
+    for (double ty = -window_linear / 2.0; ty <= window_linear / 2.0; ty += initial_linear_step)
+      for (double a = -window_angular / 2.0; a < window_angular / 2.0; a += angular_step) {
+        double d[4]; se2_from(a, tx, ty, d);
+        Node n; se2_mul(trans0, d, n.t); n.level = 1;
+        queue.push_back(n);
+        calculated.push_back(key(n.t));
+      }
+  double min_cost = 100000.0;
+  double best[4] = {1, 0, 0, 0};
+  const int np = variant_num_params(variant);
+  for (size_t head = 0; head < queue.size(); ++head) {
+    const Node cur = queue[head];
+    double params[4] = {cur.t[0], cur.t[1], cur.t[2], cur.t[3]};
+    if (np == 3) { params[0] = cur.t[2]; params[1] = cur.t[3]; params[2] = std::atan2(cur.t[1], cur.t[0]); }
+    FusedOut f;
+    accumulate_pairs(variant, params, moving.cells.data(), fixed.cells.data(), pl.im.data(), pl.jf.data(), P, loss, false, f);
+    R.n_evaluated++;
+    const double current_cost = f.cost / (double)P;
+    if (current_cost < cost_threshold) {
+      if (current_cost < min_cost) { for (int i = 0; i < 4; ++i) best[i] = cur.t[i]; min_cost = current_cost; }
+      if (cur.level < n_iter) {
+        const double step = std::pow(2.0, (double)cur.level) * linear_step;
+        for (double tx = -step; tx <= step; tx += step)
+          for (double ty = -step; ty <= step; ty += step)
+            for (double a = -angular_step; a <= angular_step; a += angular_step) {
+              double d[4]; se2_from(a, tx, ty, d);
+              Node n; se2_mul(cur.t, d, n.t); n.level = cur.level + 1;
+              const std::vector<float> k = key(n.t);
+              if (std::find(calculated.begin(), calculated.end(), k) == calculated.end()) { calculated.push_back(k); queue.push_back(n); }
+            }
+      }
+    }
+  }
+  for (int i = 0; i < 4; ++i) R.pose[i] = best[i];
+  R.min_cost = min_cost;
+  return R;
+}
+
 }  // namespace orc

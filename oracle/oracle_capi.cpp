@@ -213,4 +213,15 @@ void orc_sweep_costs(int variant, const float* cells_m, const float* cells_f, co
 void orc_se2_plus(const double* T4, const double* d3, double* out4) { se2_plus(T4, d3, out4); }
 void orc_se2_plus_jacobian(const double* T4, double* J12) { se2_plus_jacobian(T4, J12); }
 
+int orc_bnb(const float* f_cells, int n_f, const int32_t* f_slot, int size_x, int size_y, double res, double max_linf, const float* m_cells, int n_m,
+            const double* pose4, int variant, double alpha, double scale, double window_linear, double window_angular, double linear_step,
+            double max_px_range, double cost_threshold, int n_iter, double* out6) {
+  NdtMap F = view_map(f_cells, nullptr, n_f, f_slot, size_x, size_y, res, max_linf);
+  NdtMap M = view_map(m_cells, nullptr, n_m, nullptr, size_x, size_y, res, max_linf);
+  BnbResult R = bnb_search(F, M, pose4, variant, alpha, scale, window_linear, window_angular, linear_step, max_px_range, cost_threshold, n_iter);
+  for (int i = 0; i < 4; ++i) out6[i] = R.pose[i];
+  out6[4] = R.min_cost; out6[5] = R.n_evaluated;
+  return 0;
+}
+
 }  // extern "C"

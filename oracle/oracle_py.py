@@ -87,6 +87,7 @@ def _sig(L):
     L.orc_loop_constraint.restype = i
     L.orc_loop_constraint.argtypes = [pf, i, pi, i, i, d, d, pf, i, pd, i, i, i, d, d, d, d, i, i, i, d, pu, pu, i, pd]
     L.orc_sweep_costs.restype = None; L.orc_sweep_costs.argtypes = [i, pf, pf, pu, pu, sz, i, d, d, d, d, pd, sz, pd]
+    L.orc_bnb.restype = i; L.orc_bnb.argtypes = [pf, i, pi, i, i, d, d, pf, i, pd, i, d, d, d, d, d, d, d, i, pd]
     L.orc_se2_plus.restype = None; L.orc_se2_plus.argtypes = [pd, pd, pd]
     L.orc_se2_plus_jacobian.restype = None; L.orc_se2_plus_jacobian.argtypes = [pd, pd]
 
@@ -270,3 +271,14 @@ def se2_plus(T, d):
     T = _f64(T); d = _f64(d); out = np.zeros(4)
     lib().orc_se2_plus(_p(T, C.c_double), _p(d, C.c_double), _p(out, C.c_double))
     return out
+
+
+def bnb(f_cells, f_slot, size_x, size_y, res, max_linf, m_cells, pose, alpha, scale, window_linear=4.5, window_angular=0.45, linear_step=0.4,
+        max_px_range=4.0, cost_threshold=0.82, n_iter=2, variant=VAR_SE2_INTENSITY):
+    """Matcher::estimateTransformGlobalBNB restated sequentially -> dict(pose, min_cost, n_evaluated)"""
+    fc = _f32(f_cells).reshape(-1, 12); mc = _f32(m_cells).reshape(-1, 12); fs = _i32(f_slot); pose = _f64(pose)
+    out = np.zeros(6, np.float64)
+    lib().orc_bnb(_p(fc, C.c_float), len(fc), _p(fs, C.c_int32), size_x, size_y, float(res), float(max_linf), _p(mc, C.c_float), len(mc),
+                  _p(pose, C.c_double), int(variant), float(alpha), float(scale), float(window_linear), float(window_angular), float(linear_step),
+                  float(max_px_range), float(cost_threshold), int(n_iter), _p(out, C.c_double))
+    return dict(pose=out[:4].copy(), min_cost=out[4], n_evaluated=int(out[5]))

@@ -12,6 +12,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "librandt_gpu.so")
+HOST_LIB = os.path.join(HERE, "librandt_host.so")       # C++ mirror of the reference's Map / Matcher surface (host/randt_host.cpp)
+HOST_SRC = os.path.join(HERE, "host", "randt_host.cpp")
+HOST_HDR = os.path.join(HERE, "..", "include", "randt_host.hpp")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 EXTRA = os.environ.get("RANDT_NVCC_FLAGS", "").split()
@@ -56,6 +59,11 @@ def build_all(force=False, verbose=False):
     objs = [os.path.join(OBJ, src.replace(".cu", ".o")) for src in UNITS]
     if force or jobs or _newer(LIB, objs):
         run([nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart_static", "-lpthread", "-ldl", "-lrt"])
+    # host layer: plain C++17 over the C-ABI (no CUDA headers), linked against librandt_gpu.so next to it
+    if force or _newer(HOST_LIB, [HOST_SRC, HOST_HDR, LIB]):
+        cxx = os.environ.get("CXX", "g++")
+        run([cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-Wall", "-o", HOST_LIB, HOST_SRC,
+             "-L" + HERE, "-lrandt_gpu", "-Wl,-rpath,$ORIGIN"])
     return LIB
 
 

@@ -283,54 +283,64 @@ __host__ __device__ constexpr int bfly_lane_of_slot(int slot) {
   }
   return lane;
 }
-// totals of all N slots in every lane
+// slot -> owner lane after bfly_reduce<N, 16>, packed 5 bits per slot (N <= 12 per word)
 template <int N>
-__device__ __forceinline__ void warp_sum_all(double* a, int lane) {
-  bfly_reduce<N, 16>(a, lane);
-  const double mine = a[0];
-#pragma unroll
-  for (int s = 0; s < N; ++s) a[s] = __shfl_sync(kFull, mine, bfly_lane_of_slot<N>(s));
+__host__ __device__ constexpr unsigned long long bfly_lane_table(int first) {
+  unsigned long long t = 0;
+  for (int s = 0; s < 12 && first + s < N; ++s) t |= (unsigned long long)bfly_lane_of_slot<N>(first + s) << (5 * s);
+  return t;
 }
-__device__ __forceinline__ double warp_max(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(kFull, v, o));
-  return v;
+template <int N>
+__device__ __forceinline__ int bfly_owner(int slot) {
+  constexpr unsigned long long t0 = bfly_lane_table<N>(0), t1 = bfly_lane_table<N>(12);
+  return (int)(((slot < 12 ? t0 : t1) >> (5 * (slot < 12 ? slot : slot - 12))) & 31ull);
+}
+// max of non-negative finite doubles over the warp: two integer REDUX (the IEEE order of non-negative doubles is the order of
+// their bit patterns) instead of five 64-bit shuffle + compare rounds
+__device__ __forceinline__ double warp_max_nonneg(double v) {
+  const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+  const unsigned mh = __reduce_max_sync(kFull, hi);
+  const unsigned ml = __reduce_max_sync(kFull, hi == mh ? lo : 0u);
+  return __hiloint2double((int)mh, (int)ml);
 }
 
-// expand the basis normal equations of one segment into the 24-double output record
-// tot: [NH upper triangle (i <= j, row-major)] [NB gradient] [cost] [sum dd]; max_dd separately
-template <int VARIANT>
-__device__ void write_segment_out(const double* __restrict__ tot, double max_dd, const PoseConst& k, uint32_t n_pairs, double* __restrict__ out) {
+// Write the 24-double record of one segment cooperatively: lane e < 24 fetches the basis total its entry depends on from the lane
+// that owns it (`mine` = the caller's own slot total; owner(slot) maps a slot to its lane), scales it, and the warp stores the
+// record with one coalesced 8-byte-per-lane store.  Slots: [NH upper triangle (i <= j, row-major)] [NB gradient] [cost] [sum dd].
+template <int VARIANT, bool WANT_JAC, typename OwnerFn>
+__device__ __forceinline__ void write_segment_out(double mine, double max_dd, const PoseConst& k, uint32_t n_pairs, double* __restrict__ out,
+                                                  int lane, OwnerFn owner) {
   constexpr int NB = VarTraits<VARIANT>::NB;
   constexpr int NH = NB * (NB + 1) / 2;
-  double H[16], g[4];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) H[i] = 0.0;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) g[i] = 0.0;
-  if (VARIANT == 0) {
-    // ambient (c, s, tx, ty) = E^T (theta, x, y),  E rows: theta -> (ja, jb, 0, 0), x -> (0,0,1,0), y -> (0,0,0,1)
-    const double Htt = tot[0], Htx = tot[1], Hty = tot[2], Hxx = tot[3], Hxy = tot[4], Hyy = tot[5];
-    H[0] = k.ja * k.ja * Htt; H[1] = k.ja * k.jb * Htt; H[2] = k.ja * Htx; H[3] = k.ja * Hty;
-    H[4] = H[1];              H[5] = k.jb * k.jb * Htt; H[6] = k.jb * Htx; H[7] = k.jb * Hty;
-    H[8] = H[2];  H[9] = H[6];  H[10] = Hxx; H[11] = Hxy;
-    H[12] = H[3]; H[13] = H[7]; H[14] = Hxy; H[15] = Hyy;
-    g[0] = k.ja * tot[NH]; g[1] = k.jb * tot[NH]; g[2] = tot[NH + 1]; g[3] = tot[NH + 2];
-  } else {
-    int t = 0;
-#pragma unroll
-    for (int i = 0; i < NB; ++i)
-#pragma unroll
-      for (int j = i; j < NB; ++j) { H[i * 4 + j] = tot[t]; H[j * 4 + i] = tot[t]; ++t; }
-#pragma unroll
-    for (int i = 0; i < NB; ++i) g[i] = tot[NH + i];
-  }
-  double2* o2 = reinterpret_cast<double2*>(out);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) o2[i] = make_double2(H[2 * i], H[2 * i + 1]);
-  o2[8] = make_double2(g[0], g[1]); o2[9] = make_double2(g[2], g[3]);
-  o2[10] = make_double2(tot[NH + NB], sqrt(max_dd));       // cost, max raw residual
-  o2[11] = make_double2(tot[NH + NB + 1], (double)n_pairs);  // sum raw r^2, residual blocks
+  constexpr int NJ = WANT_JAC ? NH + NB : 0;
+  const int e = lane;
+  // entry e: H (e < 16: row r = e / 4, column c = e % 4), g (16..19), cost (20), max r (21), sum r^2 (22), n (23)
+  int slot = 0; double f = 0.0;
+  if (e < 20) {
+    if (WANT_JAC) {
+      const int r = e < 16 ? (e >> 2) : (e - 16), c = e & 3;
+      int tr, tc; double fr, fc;
+      if (VARIANT == 0) {   // ambient (c, s, tx, ty) from the tangent basis (theta, x, y): d theta/d c = ja, d theta/d s = jb
+        tr = r < 2 ? 0 : r - 1; tc = c < 2 ? 0 : c - 1;
+        fr = r == 0 ? k.ja : (r == 1 ? k.jb : 1.0); fc = c == 0 ? k.ja : (c == 1 ? k.jb : 1.0);
+      } else {
+        tr = r; tc = c; fr = r < NB ? 1.0 : 0.0; fc = c < NB ? 1.0 : 0.0;
+        if (tr >= NB) tr = 0;
+        if (tc >= NB) tc = 0;
+      }
+      if (e < 16) {
+        const int i = tr < tc ? tr : tc, j = tr < tc ? tc : tr;
+        slot = i * NB - (i * (i - 1)) / 2 + (j - i);
+        f = fr * fc;
+      } else { slot = NH + tr; f = fr; }
+    }
+  } else if (e == 20) { slot = NJ; f = 1.0; }
+  else if (e == 22) { slot = NJ + 1; f = 1.0; }
+  const double v = __shfl_sync(kFull, mine, owner(slot));
+  double val = f * v;
+  if (e == 21) val = max_dd > 0.0 ? max_dd * rsqrt_fast(max_dd) : 0.0;   // max raw residual
+  if (e == 23) val = (double)n_pairs;
+  if (e < RANDT_FUSED_STRIDE) out[e] = val;
 }
 
 // ---- the software-pipelined tile stream of one warp ------------------------------------------------------------------
@@ -397,7 +407,6 @@ __device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, uint32_t 
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(gmem), "r"(bytes), "r"(b)
                : "memory");
 }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 struct TileStream {   // generator (warp-uniform): the warp's range [k, k_end) of the balanced tile order, chunk by chunk; the following
@@ -498,7 +507,11 @@ __global__ void __launch_bounds__(kK3Threads, kMinCtas) k3_fused_kernel(DevicePr
   }
   uint32_t phase_bits = 0u;     // bit s: parity the next completion of stage s's barrier will have
 
-  PoseConst kc; LossConst lc;
+  // Pose and loss constants of the current tile live in shared memory (one copy per warp, broadcast LDS where they are used):
+  // ~26 fewer live registers per thread, which is what lets a fifth CTA fit on the SM.
+  __shared__ PoseConst kc_all[kWarpsPerCta];
+  __shared__ LossConst lc_all[kWarpsPerCta];
+  PoseConst& kc = kc_all[warp]; LossConst& lc = lc_all[warp];
   double acc[NS]; double max_dd = 0.0; uint32_t n_bad = 0;
 #pragma unroll
   for (int e = 0; e < NS; ++e) acc[e] = 0.0;
@@ -517,8 +530,13 @@ __global__ void __launch_bounds__(kK3Threads, kMinCtas) k3_fused_kernel(DevicePr
     const bool live = cm.i < cm.end;          // false: tile of an inactive segment (dropped, nothing was copied)
     if (live) { mbar_wait(&sb->bar, (phase_bits >> slot) & 1u); phase_bits ^= 1u << slot; }
     if (sb->first && live) {
-      make_pose_const<VARIANT>(sb->pose, kc);
-      make_loss_const(lp, mu_per_seg ? sb->mu : lp.mu, lc);
+      if (lane == 0) {
+        PoseConst k0; LossConst l0;
+        make_pose_const<VARIANT>(sb->pose, k0);
+        make_loss_const(lp, mu_per_seg ? sb->mu : lp.mu, l0);
+        kc = k0; lc = l0;
+      }
+      __syncwarp();
     }
     if (cm.i + lane < cm.end) {
       RawCell m, f[2];
@@ -560,33 +578,29 @@ __global__ void __launch_bounds__(kK3Threads, kMinCtas) k3_fused_kernel(DevicePr
     }
     // ---- tile finished: reduce across the warp and emit ----
     if (live && cm.i + 32 >= cm.end) {
-      warp_sum_all<NS>(acc, lane);
-      const double mx = warp_max(max_dd);
+      bfly_reduce<NS, 16>(acc, lane);          // slot s total now lives in lane bfly_owner<NS>(s) (acc[0])
+      const double mine = acc[0];
+      const double mx = warp_max_nonneg(max_dd);
       const uint32_t bad = __reduce_add_sync(kFull, n_bad);
       const uint32_t seg = cm.seg;
       const uint32_t first = P.seg_first_tile[seg], seg_tiles = P.seg_first_tile[seg + 1] - first;
-
+      const uint32_t n_pairs_seg = P.seg_off[seg + 1] - P.seg_off[seg];
       if (seg_tiles == 1) {
-        if (lane == 0) {
-          double rec[NH + NB + 2];
-#pragma unroll
-          for (int e = 0; e < NH + NB; ++e) rec[e] = WANT_JAC ? acc[e < NS ? e : 0] : 0.0;
-          rec[NH + NB] = acc[NJ]; rec[NH + NB + 1] = acc[NJ + 1];
-          write_segment_out<VARIANT>(rec, mx, kc, P.seg_off[seg + 1] - P.seg_off[seg], out + (size_t)seg * RANDT_FUSED_STRIDE);
-          if (bad) atomicAdd(bad_counter, (unsigned long long)bad);
-        }
+        write_segment_out<VARIANT, WANT_JAC>(mine, mx, kc, n_pairs_seg, out + (size_t)seg * RANDT_FUSED_STRIDE, lane,
+                                             [](int sl) { return bfly_owner<NS>(sl); });
+        if (lane == 0 && bad) atomicAdd(bad_counter, (unsigned long long)bad);
       } else {
-        // partial record of this tile: [NS sums][max dd][bad]
+        // partial record of this tile: [NS sums][max dd][bad], one entry per lane
         const uint32_t t = first + P.tiles[cm.k].part;
         double* part = P.partials + (size_t)t * kMaxAcc;
+        double pv = __shfl_sync(kFull, mine, bfly_owner<NS>(lane < NS ? lane : 0));
+        if (lane == NS) pv = mx;
+        if (lane == NS + 1) pv = (double)bad;
+        if (lane < NS + 2) part[lane] = pv;
+        __threadfence();
+        __syncwarp();
         uint32_t ticket = 0;
-        if (lane == 0) {
-#pragma unroll
-          for (int e = 0; e < NS; ++e) part[e] = acc[e];
-          part[NS] = mx; part[NS + 1] = (double)bad;
-          __threadfence();
-          ticket = atomicAdd(&P.seg_counters[seg], 1u);
-        }
+        if (lane == 0) ticket = atomicAdd(&P.seg_counters[seg], 1u);
         ticket = __shfl_sync(kFull, ticket, 0);
         if (ticket == seg_tiles - 1) {   // last tile of this segment to finish: fold the partials in tile order
           __threadfence();
@@ -597,17 +611,11 @@ __global__ void __launch_bounds__(kK3Threads, kMinCtas) k3_fused_kernel(DevicePr
               v = (lane == NS) ? fmax(v, x) : v + x;
             }
           }
-          double tot[NS];
-#pragma unroll
-          for (int e = 0; e < NS; ++e) tot[e] = __shfl_sync(kFull, v, e);
           const double mx_all = __shfl_sync(kFull, v, NS);
           const double bad_all = __shfl_sync(kFull, v, NS + 1);
+          write_segment_out<VARIANT, WANT_JAC>(v, mx_all, kc, n_pairs_seg, out + (size_t)seg * RANDT_FUSED_STRIDE, lane,
+                                               [](int sl) { return sl; });
           if (lane == 0) {
-            double rec[NH + NB + 2];
-#pragma unroll
-            for (int e = 0; e < NH + NB; ++e) rec[e] = WANT_JAC ? tot[e < NS ? e : 0] : 0.0;
-            rec[NH + NB] = tot[NJ]; rec[NH + NB + 1] = tot[NJ + 1];
-            write_segment_out<VARIANT>(rec, mx_all, kc, P.seg_off[seg + 1] - P.seg_off[seg], out + (size_t)seg * RANDT_FUSED_STRIDE);
             if (bad_all != 0.0) atomicAdd(bad_counter, (unsigned long long)bad_all);
             P.seg_counters[seg] = 0u;   // re-arm for the next launch
           }
@@ -617,8 +625,9 @@ __global__ void __launch_bounds__(kK3Threads, kMinCtas) k3_fused_kernel(DevicePr
       for (int e = 0; e < NS; ++e) acc[e] = 0.0;
       max_dd = 0.0; n_bad = 0;
     }
-    fence_proxy_async();   // this lane's reads of the slot are ordered before the next bulk (async-proxy) write into it
-    __syncwarp();          // every lane is done with this slot before lane 0 restages it
+    // Every lane's LDS of this slot has completed (the values were consumed above), so after the warp barrier lane 0 may let
+    // the next bulk copy overwrite it.
+    __syncwarp();
     if (++slot == kStages) slot = 0;
   }
   cp_async_wait<0>();
@@ -704,7 +713,6 @@ __global__ void __launch_bounds__(kK3Threads, kMinCtas) k3_emit_kernel(DevicePro
         emit_one<VARIANT, WANT_JAC>(kc, p0 + 1u, dd1, N, r_out, J_out, n_bad);
       }
     }
-    fence_proxy_async();
     __syncwarp();
     if (++slot == kStages) slot = 0;
   }

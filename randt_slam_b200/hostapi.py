@@ -1,0 +1,73 @@
+"""ctypes view of librandt_host.so's test hooks (randt_hostapi_*): drives the C++ mirror of the reference's Map / Matcher /
+ceres::CostFunction surface (include/randt_host.hpp) from the Python tests.  No compute here and no fallback."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import capi
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "librandt_host.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise capi.RandtError(capi.E_INVALID, "host library %s is missing: run `python -m randt_slam_b200.build`" % LIB_PATH)
+        capi.lib()   # librandt_gpu.so first (the host library links against it)
+        L = C.CDLL(LIB_PATH)
+        L.randt_hostapi_last_error.restype = C.c_char_p
+        for name in ("randt_hostapi_loop_constraints", "randt_hostapi_cost_function", "randt_hostapi_bnb"):
+            getattr(L, name).restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise capi.RandtError(rc, lib().randt_hostapi_last_error().decode())
+
+
+def _pf(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def loop_constraints(gp, fixed_scans, moving_scans, poses, k, loss_function_scale, convexity, divisor, max_gnc_steps, loop_scale,
+                     optimize_on_manifold=True, device=0):
+    """Map::addClusters x2 -> Matcher::estimateLoopConstraint(s) for n (fixed scan, moving scan) pairs -> (poses [n,4], scores [n])"""
+    n = len(fixed_scans)
+    f = np.ascontiguousarray(np.concatenate(fixed_scans), np.float32); m = np.ascontiguousarray(np.concatenate(moving_scans), np.float32)
+    fo = np.concatenate([[0], np.cumsum([len(s) for s in fixed_scans])]).astype(np.uint32)
+    mo = np.concatenate([[0], np.cumsum([len(s) for s in moving_scans])]).astype(np.uint32)
+    poses = np.ascontiguousarray(poses, np.float64).reshape(n, 4).copy()
+    scores = np.zeros(n, np.float64)
+    _check(lib().randt_hostapi_loop_constraints(C.c_int(device), C.byref(gp), _pf(f), _pf(fo), _pf(m), _pf(mo), C.c_uint32(n), C.c_int(k),
+                                                C.c_double(loss_function_scale), C.c_double(convexity), C.c_double(divisor), C.c_int(max_gnc_steps),
+                                                C.c_double(loop_scale), C.c_int(int(optimize_on_manifold)), _pf(poses), _pf(scores)))
+    return poses, scores
+
+
+def cost_function(gp, fixed_pts, moving_pts, k, guess, pose, loss=None, want_jac=True, device=0):
+    """Matcher::addNDTFactor as one ceres::CostFunction, evaluated through CostFunction::Evaluate -> (residuals, J [n,4], max raw r)"""
+    f = np.ascontiguousarray(fixed_pts, np.float32); m = np.ascontiguousarray(moving_pts, np.float32)
+    cap = 4 * len(m) + 8
+    res = np.zeros(cap, np.float64); J = np.zeros((cap, 4), np.float64) if want_jac else None
+    n = C.c_uint32(0); mx = C.c_double(0)
+    guess = np.ascontiguousarray(guess, np.float64); pose = np.ascontiguousarray(pose, np.float64)
+    _check(lib().randt_hostapi_cost_function(C.c_int(device), C.byref(gp), _pf(f), C.c_uint32(len(f)), _pf(m), C.c_uint32(len(m)), C.c_int(k),
+                                             _pf(guess), C.byref(loss) if loss is not None else None, _pf(pose), _pf(res),
+                                             _pf(J) if want_jac else None, C.c_uint32(cap), C.byref(n), C.byref(mx)))
+    return res[: n.value].copy(), (J[: n.value].copy() if want_jac else None), mx.value
+
+
+def bnb(gp, fixed_pts, moving_pts, pose, convexity, scale, window_linear=4.5, window_angular=0.45, linear_step=0.4, max_px_range=4.0,
+        cost_threshold=0.82, n_iter=2, device=0):
+    f = np.ascontiguousarray(fixed_pts, np.float32); m = np.ascontiguousarray(moving_pts, np.float32)
+    pose = np.ascontiguousarray(pose, np.float64).copy()
+    mc = C.c_double(0); ne = C.c_uint32(0)
+    _check(lib().randt_hostapi_bnb(C.c_int(device), C.byref(gp), _pf(f), C.c_uint32(len(f)), _pf(m), C.c_uint32(len(m)), C.c_double(convexity),
+                                   C.c_double(scale), C.c_double(window_linear), C.c_double(window_angular), C.c_double(linear_step),
+                                   C.c_double(max_px_range), C.c_double(cost_threshold), C.c_int(n_iter), _pf(pose), C.byref(mc), C.byref(ne)))
+    return pose, mc.value, ne.value

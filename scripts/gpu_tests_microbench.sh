@@ -1,0 +1,2 @@
+mkdir -p gpurun_out
+cd scripts/microbench && nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/fp64_pipe fp64_pipe.cu && /tmp/fp64_pipe | tee ../../gpurun_out/fp64_pipe.txt

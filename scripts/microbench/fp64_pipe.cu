@@ -79,6 +79,47 @@ __global__ void rcp_kernel(double* out, long long* cyc, double a) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
   if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
+// DFMA chains (ILP of them) with NF float->double conversions per step feeding one of the chains: do the XU conversions steal
+// fp64-pipe issue slots?  MODE 0: no conversion, 1: F2F.F64.F32 (XU), 2: integer bit conversion (ALU/FMA pipes)
+__device__ __forceinline__ double cvt_bits(float f) {   // exact for normal floats; 0 maps to 2^-127
+  const unsigned b = __float_as_uint(f);
+  const unsigned hi = (((b >> 3) & 0x0fffffffu) + 0x38000000u) | (b & 0x80000000u);
+  return __hiloint2double((int)hi, (int)(b << 29));
+}
+template <int ILP, int NF, int MODE>
+__global__ void mix_kernel(double* out, long long* cyc, const float* in, double a, double b) {
+  double x[ILP]; float v[NF > 0 ? NF : 1];
+#pragma unroll
+  for (int i = 0; i < ILP; ++i) x[i] = threadIdx.x * 1e-3 + i;
+#pragma unroll
+  for (int i = 0; i < NF; ++i) v[i] = in[threadIdx.x + 32 * i];
+  __syncthreads();
+  const long long t0 = clock64();
+#pragma unroll 1
+  for (int it = 0; it < ITERS / 8; ++it) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+#pragma unroll
+      for (int i = 0; i < ILP; ++i) x[i] = fma(x[i], a, b);
+      if (MODE != 0) {
+#pragma unroll
+        for (int i = 0; i < NF; ++i) {
+          const double d = MODE == 1 ? (double)v[i] : cvt_bits(v[i]);
+          x[i % ILP] += d;                                        // consumed by the fp64 chains (one extra DADD per conversion)
+          v[i] = __uint_as_float(__float_as_uint(v[i]) + 2u);   // next input differs (integer op, no fp pipe)
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < NF; ++i) x[i % ILP] += 1.5;
+      }
+    }
+  }
+  const long long t1 = clock64();
+  double s = 0; for (int i = 0; i < ILP; ++i) s += x[i];
+  for (int i = 0; i < NF; ++i) s += v[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
 template <typename K, typename... A>
 void run(const char* name, K k, int ilp, int threads, A... args) {
   long long* cyc; cudaMalloc(&cyc, 8 * 148);
@@ -106,6 +147,16 @@ int main() {
   RUN(f2f_only_kernel, "F2F", 8, in)
   RUN(rcp_kernel, "RCP64H", 1, 1.0)
   RUN(rcp_kernel, "RCP64H", 4, 1.0)
+  // K3-like mix: 10 fp64 ops (8 DFMA + 2 DADD) per 2 conversions
+  auto report_mix = [&](const char* name, int fp64_ops, int threads) {
+    cudaDeviceSynchronize();
+    cudaMemcpy(h, cyc, 8 * 148, cudaMemcpyDeviceToHost);
+    double c = 0; for (int i = 0; i < 148; ++i) c += h[i]; c /= 148;
+    printf("%-22s warps/SM=%2d : %.2f cyc per step -> %.1f fp64 thread-inst/clk/SM\n", name, threads / 32, c / ITERS, (double)threads * fp64_ops * ITERS / c);
+  };
+  for (int th : {128, 256, 512, 640, 1024}) { mix_kernel<8, 2, 0><<<148, th>>>(out, cyc, in, 1.0000001, 1e-9); report_mix("8 DFMA+2 DADD", 10, th); }
+  for (int th : {128, 256, 512, 640, 1024}) { mix_kernel<8, 2, 1><<<148, th>>>(out, cyc, in, 1.0000001, 1e-9); report_mix("8 DFMA+2 DADD+2 F2F", 10, th); }
+  for (int th : {128, 256, 512, 640, 1024}) { mix_kernel<8, 2, 2><<<148, th>>>(out, cyc, in, 1.0000001, 1e-9); report_mix("8 DFMA+2 DADD+2 icvt", 10, th); }
   cudaError_t e = cudaDeviceSynchronize();
   printf("status: %s\n", cudaGetErrorString(e));
   return 0;
