@@ -50,108 +50,123 @@ __device__ void se2_plus(const double* T, const double* d, double* out) {
   out[3] = T[3] + (T[1] * ex + T[0] * ey);
 }
 
-struct Dims { int np, nt; bool manifold; };
+// compile-time problem shape: NP ambient parameters, NT tangent dimensions (all loops unroll, every array stays in registers)
+template <int NP_, bool MANIFOLD_>
+struct Dims {
+  static constexpr int np = NP_;
+  static constexpr bool manifold = MANIFOLD_;
+  static constexpr int nt = MANIFOLD_ ? 3 : NP_;
+};
 
-__device__ __forceinline__ void plus(const Dims& D, const double* x, const double* delta, double* out) {
-  if (D.manifold) se2_plus(x, delta, out);
-  else for (int i = 0; i < D.np; ++i) out[i] = x[i] + delta[i];
+template <typename D>
+__device__ __forceinline__ void plus(const double* x, const double* delta, double* out) {
+  if (D::manifold) se2_plus(x, delta, out);
+  else {
+#pragma unroll
+    for (int i = 0; i < D::np; ++i) out[i] = x[i] + delta[i];
+  }
 }
 
 // cost, tangent gradient and tangent J^T J of the evaluated point `x` from a K3 fused record (ambient 4x4 layout)
-__device__ void load_normal_eq(const Dims& D, const double* __restrict__ rec, const double* x, LmState& st) {
+template <typename D>
+__device__ __forceinline__ void load_normal_eq(const double* __restrict__ rec, const double* x, LmState& st) {
   st.cost = rec[RANDT_FUSED_COST];
-  if (!D.manifold) {
-    for (int a = 0; a < D.nt; ++a) {
+  if (!D::manifold) {
+    _Pragma("unroll") for (int a = 0; a < D::nt; ++a) {
       st.g[a] = rec[RANDT_FUSED_G + a];
-      for (int b = 0; b < D.nt; ++b) st.H[a * 4 + b] = rec[RANDT_FUSED_H + a * 4 + b];
+      _Pragma("unroll") for (int b = 0; b < D::nt; ++b) st.H[a * 4 + b] = rec[RANDT_FUSED_H + a * 4 + b];
     }
   } else {
     // Sophus::Manifold<SE2>::PlusJacobian = Dx_this_mul_exp_x_at_0 (4 x 3): rows [0,0,-s], [0,0,c], [c,-s,0], [s,c,0]
     const double c = x[0], s = x[1];
     const double Pj[4][3] = {{0, 0, -s}, {0, 0, c}, {c, -s, 0}, {s, c, 0}};
-    for (int a = 0; a < 3; ++a) {
+    _Pragma("unroll") for (int a = 0; a < 3; ++a) {
       double ga = 0;
-      for (int i = 0; i < 4; ++i) ga += Pj[i][a] * rec[RANDT_FUSED_G + i];
+      _Pragma("unroll") for (int i = 0; i < 4; ++i) ga += Pj[i][a] * rec[RANDT_FUSED_G + i];
       st.g[a] = ga;
-      for (int b = 0; b < 3; ++b) {
+      _Pragma("unroll") for (int b = 0; b < 3; ++b) {
         double h = 0;
-        for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) h += Pj[i][a] * rec[RANDT_FUSED_H + i * 4 + j] * Pj[j][b];
+        _Pragma("unroll") for (int i = 0; i < 4; ++i) _Pragma("unroll") for (int j = 0; j < 4; ++j) h += Pj[i][a] * rec[RANDT_FUSED_H + i * 4 + j] * Pj[j][b];
         st.H[a * 4 + b] = h;
       }
     }
   }
 }
 
-__device__ double grad_max_norm(const Dims& D, const LmState& st) {
+template <typename D>
+__device__ __forceinline__ double grad_max_norm(const LmState& st) {
   double negg[4], tmp[4];
-  for (int i = 0; i < D.nt; ++i) negg[i] = -st.g[i];
-  plus(D, st.x, negg, tmp);
+  _Pragma("unroll") for (int i = 0; i < D::nt; ++i) negg[i] = -st.g[i];
+  plus<D>(st.x, negg, tmp);
   double m = 0;
-  for (int i = 0; i < D.np; ++i) m = fmax(m, fabs(st.x[i] - tmp[i]));
+  _Pragma("unroll") for (int i = 0; i < D::np; ++i) m = fmax(m, fabs(st.x[i] - tmp[i]));
   return m;
 }
 
 // in-place Cholesky solve of the n x n system A y = b (row-major, leading dimension 4); false if A is not positive definite
-__device__ bool chol_solve(double* A, const double* b, int n, double* y) {
-  for (int j = 0; j < n; ++j) {
+template <int n>
+__device__ __forceinline__ bool chol_solve(double* A, const double* b, double* y) {
+  _Pragma("unroll") for (int j = 0; j < n; ++j) {
     double d = A[j * 4 + j];
-    for (int k = 0; k < j; ++k) d -= A[j * 4 + k] * A[j * 4 + k];
+    _Pragma("unroll") for (int k = 0; k < j; ++k) d -= A[j * 4 + k] * A[j * 4 + k];
     if (!(d > 0.0) || !isfinite(d)) return false;
     d = sqrt(d);
     A[j * 4 + j] = d;
-    for (int i = j + 1; i < n; ++i) {
+    _Pragma("unroll") for (int i = j + 1; i < n; ++i) {
       double s = A[i * 4 + j];
-      for (int k = 0; k < j; ++k) s -= A[i * 4 + k] * A[j * 4 + k];
+      _Pragma("unroll") for (int k = 0; k < j; ++k) s -= A[i * 4 + k] * A[j * 4 + k];
       A[i * 4 + j] = s / d;
     }
   }
-  for (int i = 0; i < n; ++i) { double s = b[i]; for (int k = 0; k < i; ++k) s -= A[i * 4 + k] * y[k]; y[i] = s / A[i * 4 + i]; }
-  for (int i = n - 1; i >= 0; --i) { double s = y[i]; for (int k = i + 1; k < n; ++k) s -= A[k * 4 + i] * y[k]; y[i] = s / A[i * 4 + i]; }
-  for (int i = 0; i < n; ++i) if (!isfinite(y[i])) return false;
+  _Pragma("unroll") for (int i = 0; i < n; ++i) { double s = b[i]; _Pragma("unroll") for (int k = 0; k < i; ++k) s -= A[i * 4 + k] * y[k]; y[i] = s / A[i * 4 + i]; }
+  _Pragma("unroll") for (int i = n - 1; i >= 0; --i) { double s = y[i]; _Pragma("unroll") for (int k = i + 1; k < n; ++k) s -= A[k * 4 + i] * y[k]; y[i] = s / A[i * 4 + i]; }
+  _Pragma("unroll") for (int i = 0; i < n; ++i) if (!isfinite(y[i])) return false;
   return true;
 }
 
-__device__ void begin_solve(const Dims& D, const randt_solver_options& o, const double* __restrict__ rec, LmState& st) {
-  load_normal_eq(D, rec, st.x, st);
+template <typename D>
+__device__ __forceinline__ void begin_solve(const randt_solver_options& o, const double* __restrict__ rec, LmState& st) {
+  load_normal_eq<D>(rec, st.x, st);
   st.n_jac_evals += 1;
   st.min_cost = st.cost;
   st.solve_iterations = 1;
-  for (int i = 0; i < D.nt; ++i) st.scale[i] = o.jacobi_scaling ? 1.0 / (1.0 + sqrt(st.H[i * 4 + i])) : 1.0;
-  st.x_norm = norm_n(st.x, D.np);
+  _Pragma("unroll") for (int i = 0; i < D::nt; ++i) st.scale[i] = o.jacobi_scaling ? 1.0 / (1.0 + sqrt(st.H[i * 4 + i])) : 1.0;
+  st.x_norm = norm_n(st.x, D::np);
   st.radius = o.initial_trust_region_radius;
   st.decrease_factor = 2.0;
   st.reuse_diagonal = 0;
   st.last_successful = 1;     // iteration 0 counts as successful for the gradient test
   st.consecutive_invalid = 0;
-  st.gmax = grad_max_norm(D, st);
+  st.gmax = grad_max_norm<D>(st);
   st.iteration = 0;
 }
 
 // Runs the minimiser until it needs the cost at a candidate point (true, st.cand set) or terminates (false, st.termination set).
-__device__ bool next_candidate(const Dims& D, const randt_solver_options& o, LmState& st) {
-  const int nt = D.nt;
+template <typename D>
+__device__ __forceinline__ bool next_candidate(const randt_solver_options& o, LmState& st) {
+  constexpr int nt = D::nt;
   while (true) {
     if (st.iteration >= o.max_num_iterations) { st.termination = TERM_NO_CONVERGENCE; return false; }
     if (st.last_successful && st.gmax <= o.gradient_tolerance) { st.termination = TERM_CONVERGENCE; return false; }
     if (st.radius <= o.min_trust_region_radius) { st.termination = TERM_CONVERGENCE; return false; }
     st.iteration += 1;
     double gs[4], Hs[16], A[16], y[4], step[4];
-    for (int i = 0; i < nt; ++i) {
+    _Pragma("unroll") for (int i = 0; i < nt; ++i) {
       gs[i] = st.g[i] * st.scale[i];
-      for (int j = 0; j < nt; ++j) Hs[i * 4 + j] = st.H[i * 4 + j] * st.scale[i] * st.scale[j];
+      _Pragma("unroll") for (int j = 0; j < nt; ++j) Hs[i * 4 + j] = st.H[i * 4 + j] * st.scale[i] * st.scale[j];
     }
     if (!st.reuse_diagonal)
-      for (int i = 0; i < nt; ++i) st.diag[i] = fmin(fmax(Hs[i * 4 + i], o.min_lm_diagonal), o.max_lm_diagonal);
-    for (int i = 0; i < nt; ++i) for (int j = 0; j < nt; ++j) A[i * 4 + j] = Hs[i * 4 + j] + (i == j ? st.diag[i] / st.radius : 0.0);
-    bool valid = chol_solve(A, gs, nt, y);
+      _Pragma("unroll") for (int i = 0; i < nt; ++i) st.diag[i] = fmin(fmax(Hs[i * 4 + i], o.min_lm_diagonal), o.max_lm_diagonal);
+    _Pragma("unroll") for (int i = 0; i < nt; ++i) _Pragma("unroll") for (int j = 0; j < nt; ++j) A[i * 4 + j] = Hs[i * 4 + j] + (i == j ? st.diag[i] / st.radius : 0.0);
+    bool valid = chol_solve<nt>(A, gs, y);
     st.reuse_diagonal = 1;
     if (valid) {
       double sg = 0, sHs = 0;
-      for (int i = 0; i < nt; ++i) step[i] = -y[i];
-      for (int i = 0; i < nt; ++i) {
+      _Pragma("unroll") for (int i = 0; i < nt; ++i) step[i] = -y[i];
+      _Pragma("unroll") for (int i = 0; i < nt; ++i) {
         sg += step[i] * gs[i];
         double r = 0;
-        for (int j = 0; j < nt; ++j) r += Hs[i * 4 + j] * step[j];
+        _Pragma("unroll") for (int j = 0; j < nt; ++j) r += Hs[i * 4 + j] * step[j];
         sHs += step[i] * r;
       }
       st.model_cost_change = -(sg + 0.5 * sHs);
@@ -166,19 +181,20 @@ __device__ bool next_candidate(const Dims& D, const randt_solver_options& o, LmS
     }
     st.consecutive_invalid = 0;
     double delta[4];
-    for (int i = 0; i < nt; ++i) delta[i] = step[i] * st.scale[i];
-    plus(D, st.x, delta, st.cand);
+    _Pragma("unroll") for (int i = 0; i < nt; ++i) delta[i] = step[i] * st.scale[i];
+    plus<D>(st.x, delta, st.cand);
     return true;
   }
 }
 
 // Consumes the evaluation of st.cand.  Returns false when the solve terminated on a tolerance.
-__device__ bool on_candidate(const Dims& D, const randt_solver_options& o, const double* __restrict__ rec, LmState& st) {
+template <typename D>
+__device__ __forceinline__ bool on_candidate(const randt_solver_options& o, const double* __restrict__ rec, LmState& st) {
   double cand_cost = rec[RANDT_FUSED_COST];
   if (!isfinite(cand_cost)) cand_cost = DBL_MAX;
   st.n_cost_evals += 1;
   double sn = 0;
-  for (int i = 0; i < D.np; ++i) sn += (st.x[i] - st.cand[i]) * (st.x[i] - st.cand[i]);
+  _Pragma("unroll") for (int i = 0; i < D::np; ++i) sn += (st.x[i] - st.cand[i]) * (st.x[i] - st.cand[i]);
   sn = sqrt(sn);
   if (sn <= o.parameter_tolerance * (st.x_norm + o.parameter_tolerance)) { st.termination = TERM_CONVERGENCE; return false; }
   const double cost_change = st.cost - cand_cost;
@@ -186,11 +202,11 @@ __device__ bool on_candidate(const Dims& D, const randt_solver_options& o, const
   const double relative_decrease = cost_change / st.model_cost_change;
   st.solve_iterations += 1;
   if (relative_decrease > o.min_relative_decrease) {
-    for (int i = 0; i < D.np; ++i) st.x[i] = st.cand[i];
-    st.x_norm = norm_n(st.x, D.np);
-    load_normal_eq(D, rec, st.x, st);       // the candidate was evaluated with its Jacobian: nothing to re-evaluate
+    _Pragma("unroll") for (int i = 0; i < D::np; ++i) st.x[i] = st.cand[i];
+    st.x_norm = norm_n(st.x, D::np);
+    load_normal_eq<D>(rec, st.x, st);       // the candidate was evaluated with its Jacobian: nothing to re-evaluate
     st.n_jac_evals += 1;
-    st.gmax = grad_max_norm(D, st);
+    st.gmax = grad_max_norm<D>(st);
     const double t = 2.0 * relative_decrease - 1.0;
     st.radius = st.radius / fmax(1.0 / 3.0, 1.0 - t * t * t);
     st.radius = fmin(o.max_trust_region_radius, st.radius);
@@ -222,14 +238,16 @@ __global__ void __launch_bounds__(128) k4_init_kernel(uint32_t S, int np, const 
   for (int i = 0; i < RANDT_FUSED_STRIDE; ++i) rec[(size_t)s * RANDT_FUSED_STRIDE + i] = 0.0;   // segments without pairs get no K3 record
 }
 
-__global__ void __launch_bounds__(128) k4_lm_step_kernel(uint32_t S, int np, int use_manifold, randt_solver_options o,
+template <int NP, bool MANIFOLD>
+__global__ void __launch_bounds__(64) k4_lm_step_kernel(uint32_t S, randt_solver_options o,
                                                          const double* __restrict__ rec_all, LmState* __restrict__ state,
                                                          double* __restrict__ eval_pose, double* __restrict__ mu_arr,
                                                          uint32_t* __restrict__ active, uint32_t* __restrict__ n_active,
                                                          double* __restrict__ poses_out, double* __restrict__ result) {
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= S || active[s] == 0u) return;
-  Dims D; D.np = np; D.manifold = (use_manifold != 0) && np == 4; D.nt = D.manifold ? 3 : np;
+  typedef Dims<NP, MANIFOLD> D;
+  constexpr int np = NP;
   const double* rec = rec_all + (size_t)s * RANDT_FUSED_STRIDE;
   LmState st = state[s];
   bool solve_ended = false, need_start = false;
@@ -245,11 +263,11 @@ __global__ void __launch_bounds__(128) k4_lm_step_kernel(uint32_t S, int np, int
       need_start = true;
     }
   } else if (st.phase == PH_SOLVE_START) {
-    begin_solve(D, o, rec, st);
-    if (!next_candidate(D, o, st)) solve_ended = true;
+    begin_solve<D>(o, rec, st);
+    if (!next_candidate<D>(o, st)) solve_ended = true;
     else st.phase = PH_CANDIDATE;
   } else if (st.phase == PH_CANDIDATE) {
-    if (!on_candidate(D, o, rec, st) || !next_candidate(D, o, st)) solve_ended = true;
+    if (!on_candidate<D>(o, rec, st) || !next_candidate<D>(o, st)) solve_ended = true;
   }
   if (solve_ended) {
     st.gnc_solves += 1;
@@ -297,8 +315,10 @@ cudaError_t launch_lm_step(uint32_t S, int np, int use_manifold, const randt_sol
                            double* eval_pose, double* mu, uint32_t* active, uint32_t* n_active, double* poses_out, double* result,
                            cudaStream_t s, int* n_launches) {
   if (S == 0) return cudaSuccess;
-  const int grid = (int)((S + 127u) / 128u);
-  k4_lm_step_kernel<<<grid, 128, 0, s>>>(S, np, use_manifold, o, rec, state, eval_pose, mu, active, n_active, poses_out, result);
+  const int grid = (int)((S + 63u) / 64u);
+  if (np == 4 && use_manifold) k4_lm_step_kernel<4, true><<<grid, 64, 0, s>>>(S, o, rec, state, eval_pose, mu, active, n_active, poses_out, result);
+  else if (np == 4)           k4_lm_step_kernel<4, false><<<grid, 64, 0, s>>>(S, o, rec, state, eval_pose, mu, active, n_active, poses_out, result);
+  else                        k4_lm_step_kernel<3, false><<<grid, 64, 0, s>>>(S, o, rec, state, eval_pose, mu, active, n_active, poses_out, result);
   if (n_launches) *n_launches += 1;
   return cudaGetLastError();
 }

@@ -1,5 +1,6 @@
 # quick GPU pass: parity tests + bench (no profiler)
-set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
-timeout 600 python bench.py --steps 200 --warmup 10 > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; tail -5 gpurun_out/bench_quick.err; cat gpurun_out/bench_quick.json
+TAG=${1:-quick}
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+timeout 600 python bench.py --steps 200 --warmup 10 --no-cpu-baseline > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err; tail -5 gpurun_out/bench_${TAG}.err; python -c "
+import json; d=json.load(open('gpurun_out/bench_${TAG}.json')); print('VALUE', d['value']/1e9, 'ms', d['ms_per_step'], 'frac', d['roofline']['frac'], 'e2e', d['e2e']['value']/1e9); r=d.get('registrations'); print('REG', r and {k:v for k,v in r.items() if k not in ('what',)})"
