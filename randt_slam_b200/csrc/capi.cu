@@ -44,7 +44,8 @@ struct randt_problem {
   Duo* duos = nullptr; uint32_t n_duos = 0;
   DuoRec* duo_recs = nullptr; uint32_t* duo_p0 = nullptr;
   std::vector<uint32_t> h_duo_off;   // [S+1] duo offsets per segment
-  Tile* tiles = nullptr; uint32_t n_tiles = 0;
+  uint32_t n_tiles = 0;
+  ChunkDesc* chunks = nullptr; uint32_t n_chunks = 0;
   uint32_t* warp_off = nullptr; uint32_t n_warps = 0;
   uint32_t* seg_first_tile = nullptr;
   uint32_t* seg_off = nullptr;
@@ -58,6 +59,7 @@ struct randt_problem {
   // workspace of the batched solver (randt_register_batch), allocated on first use
   LmState* lm_state = nullptr; double *lm_eval_pose = nullptr, *lm_mu = nullptr, *lm_rec = nullptr, *lm_poses = nullptr, *lm_result = nullptr;
   uint32_t *lm_active = nullptr, *lm_n_active = nullptr;
+  ChunkDesc* lm_chunks = nullptr; uint32_t *lm_flags = nullptr, *lm_scan = nullptr, *lm_bs = nullptr, *lm_warp_off = nullptr;   // re-planned schedule
   uint32_t* h_n_active = nullptr;   // pinned
 };
 
@@ -93,11 +95,12 @@ void free_map(randt_map* m) {
 }
 void free_problem(randt_problem* p) {
   if (!p) return;
-  cudaFree(p->cells_m); cudaFree(p->cells_f); cudaFree(p->pairs); cudaFree(p->duos); cudaFree(p->duo_recs); cudaFree(p->duo_p0); cudaFree(p->tiles); cudaFree(p->warp_off); cudaFree(p->seg_first_tile); cudaFree(p->seg_off);
+  cudaFree(p->cells_m); cudaFree(p->cells_f); cudaFree(p->pairs); cudaFree(p->duos); cudaFree(p->duo_recs); cudaFree(p->duo_p0); cudaFree(p->chunks); cudaFree(p->warp_off); cudaFree(p->seg_first_tile); cudaFree(p->seg_off);
   cudaFree(p->partials); cudaFree(p->seg_counters); cudaFree(p->d_poses); cudaFree(p->d_out); cudaFree(p->d_mu); cudaFree(p->d_r);
   cudaFree(p->d_J); cudaFree(p->d_sweep);
   cudaFree(p->lm_state); cudaFree(p->lm_eval_pose); cudaFree(p->lm_mu); cudaFree(p->lm_rec); cudaFree(p->lm_poses); cudaFree(p->lm_result);
   cudaFree(p->lm_active); cudaFree(p->lm_n_active);
+  cudaFree(p->lm_chunks); cudaFree(p->lm_flags); cudaFree(p->lm_scan); cudaFree(p->lm_bs); cudaFree(p->lm_warp_off);
   if (p->h_n_active) cudaFreeHost(p->h_n_active);
   delete p;
 }
@@ -146,22 +149,33 @@ int finish_problem(randt_ctx* ctx, randt_problem* p) {
       l.first += cost(t);
       heap.push(l);
     }
-    std::vector<Tile> sorted; sorted.reserve(tiles.size());
+    // chunk descriptors, warp after warp
+    std::vector<ChunkDesc> chunks; chunks.reserve(p->n_duos / 32 + tiles.size() + 1);
     std::vector<uint32_t> woff(n_warps + 1, 0);
     for (uint32_t w = 0; w < n_warps; ++w) {
       std::sort(mine[w].begin(), mine[w].end());
-      for (uint32_t t : mine[w]) sorted.push_back(tiles[t]);
-      woff[w + 1] = (uint32_t)sorted.size();
+      for (uint32_t t : mine[w]) {
+        const Tile& tl = tiles[t];
+        const bool solo = first[tl.seg + 1] - first[tl.seg] == 1u;
+        for (uint32_t b = tl.begin; b < tl.end; b += 32u) {
+          ChunkDesc c;
+          c.duo_begin = b; c.seg = tl.seg; c.part = first[tl.seg] + tl.part;
+          c.meta = std::min(32u, tl.end - b) | (b == tl.begin ? kChunkFirst : 0u) | (b + 32u >= tl.end ? kChunkLast : 0u) | (solo ? kChunkSolo : 0u);
+          chunks.push_back(c);
+        }
+      }
+      woff[w + 1] = (uint32_t)chunks.size();
     }
-    tiles.swap(sorted);
     p->n_warps = n_warps;
+    p->n_chunks = (uint32_t)chunks.size();
+    CK(dev_alloc(&p->chunks, chunks.size()));
     CK(dev_alloc(&p->warp_off, woff.size()));
+    if (!chunks.empty()) CK(cudaMemcpyAsync(p->chunks, chunks.data(), chunks.size() * sizeof(ChunkDesc), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(p->warp_off, woff.data(), woff.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
   }
   for (uint32_t s = 0; s < p->S; ++s) if (p->h_seg_off[s + 1] == p->h_seg_off[s]) p->has_empty_segment = true;
   p->n_tiles = (uint32_t)tiles.size();
-  CK(dev_alloc(&p->tiles, tiles.size()));
   CK(dev_alloc(&p->seg_first_tile, first.size()));
   CK(dev_alloc(&p->seg_off, p->h_seg_off.size()));
   CK(dev_alloc(&p->partials, (size_t)tiles.size() * kMaxAcc));
@@ -169,7 +183,6 @@ int finish_problem(randt_ctx* ctx, randt_problem* p) {
   CK(dev_alloc(&p->d_poses, (size_t)p->S * 4));
   CK(dev_alloc(&p->d_out, (size_t)p->S * RANDT_FUSED_STRIDE));
   CK(dev_alloc(&p->d_mu, p->S));
-  if (!tiles.empty()) CK(cudaMemcpyAsync(p->tiles, tiles.data(), tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(p->seg_first_tile, first.data(), first.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(p->seg_off, p->h_seg_off.data(), p->h_seg_off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemsetAsync(p->seg_counters, 0, std::max<size_t>(1, p->S) * sizeof(uint32_t), ctx->stream));
@@ -179,7 +192,7 @@ int finish_problem(randt_ctx* ctx, randt_problem* p) {
 
 DeviceProblem view(const randt_problem* p) {
   DeviceProblem d;
-  d.cells_m = p->cells_m; d.cells_f = p->cells_f; d.pairs = p->pairs; d.duos = p->duos; d.duo_recs = p->duo_recs; d.duo_p0 = p->duo_p0; d.seg_off = p->seg_off; d.tiles = p->tiles; d.n_tiles = p->n_tiles; d.warp_off = p->warp_off; d.n_warps = p->n_warps;
+  d.cells_m = p->cells_m; d.cells_f = p->cells_f; d.pairs = p->pairs; d.duos = p->duos; d.duo_recs = p->duo_recs; d.duo_p0 = p->duo_p0; d.seg_off = p->seg_off; d.chunks = p->chunks; d.n_chunks = p->n_chunks; d.warp_off = p->warp_off; d.n_warps = p->n_warps;
   d.seg_first_tile = p->seg_first_tile; d.n_segments = p->S; d.n_pairs = p->P; d.partials = p->partials; d.seg_counters = p->seg_counters;
   d.seg_active = nullptr;
   return d;
@@ -701,6 +714,8 @@ int randt_register_batch_dev(randt_ctx* ctx, const randt_problem* cp, int varian
     CK(dev_alloc(&p->lm_state, S)); CK(dev_alloc(&p->lm_eval_pose, (size_t)S * 4)); CK(dev_alloc(&p->lm_mu, S));
     CK(dev_alloc(&p->lm_rec, (size_t)S * RANDT_FUSED_STRIDE)); CK(dev_alloc(&p->lm_active, S)); CK(dev_alloc(&p->lm_n_active, 1));
     CK(cudaHostAlloc(reinterpret_cast<void**>(&p->h_n_active), sizeof(uint32_t), cudaHostAllocDefault));
+    CK(dev_alloc(&p->lm_chunks, p->n_chunks)); CK(dev_alloc(&p->lm_flags, p->n_chunks)); CK(dev_alloc(&p->lm_scan, (size_t)p->n_chunks + 1));
+    CK(dev_alloc(&p->lm_bs, p->n_chunks / 1024 + 2)); CK(dev_alloc(&p->lm_warp_off, (size_t)p->n_warps + 1));
   }
   int nl = 0;
   CK(launch_lm_init(S, np, d_poses, p->lm_state, p->lm_eval_pose, p->lm_mu, p->lm_active, p->lm_rec, p->lm_n_active, ctx->stream, &nl));
@@ -710,6 +725,7 @@ int randt_register_batch_dev(randt_ctx* ctx, const randt_problem* cp, int varian
   // every solve needs at most max_num_iterations candidate evaluations + its start evaluation; one more launch seeds the GNC
   const long long cap = 2 + (long long)(opt->gnc_max_steps + 1) * ((long long)opt->max_num_iterations + 2);
   bool done = false;
+  uint32_t planned_for = S;     // active segments when the schedule in use was made
   for (long long it = 0; it < cap && !done; ++it) {
     CK(launch_eval_fused(v, variant, p->lm_eval_pose, lp, p->lm_mu, true, p->lm_rec, ctx->d_bad, ctx->stream, &nl));
     CK(launch_lm_step(S, np, opt->use_manifold, *opt, p->lm_rec, p->lm_state, p->lm_eval_pose, p->lm_mu, p->lm_active, p->lm_n_active, d_poses,
@@ -717,7 +733,15 @@ int randt_register_batch_dev(randt_ctx* ctx, const randt_problem* cp, int varian
     if ((it + 1) % poll == 0 || it + 1 == cap) {
       CK(cudaMemcpyAsync(p->h_n_active, p->lm_n_active, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
       CK(cudaStreamSynchronize(ctx->stream));
-      done = *p->h_n_active == 0u;
+      const uint32_t n_act = *p->h_n_active;
+      done = n_act == 0u;
+      // finished segments leave holes K3 has to step over: compact the schedule once a quarter of its segments are gone
+      if (!done && (unsigned long long)n_act * 4ull <= (unsigned long long)planned_for * 3ull) {
+        CK(launch_replan(p->chunks, p->n_chunks, p->lm_active, p->n_warps, p->lm_flags, p->lm_scan, p->lm_bs, p->lm_chunks, p->lm_warp_off,
+                         ctx->stream, &nl));
+        v.chunks = p->lm_chunks; v.warp_off = p->lm_warp_off;
+        planned_for = n_act;
+      }
     }
   }
   ctx->launches += nl;

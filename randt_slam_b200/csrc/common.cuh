@@ -31,8 +31,13 @@ constexpr uint32_t kNoCell = 0xffffffffu;
 struct __align__(16) DuoRec { float4 v[9]; };
 constexpr uint32_t kNoSecondPair = 0xffffffffu;
 
-// A work tile: duos [begin, end) of segment `seg`; `part` = index of the tile inside its segment.
+// A work tile: duos [begin, end) of segment `seg`; `part` = index of the tile inside its segment.  One warp owns a tile.
 struct Tile { uint32_t seg, begin, end, part; };
+// What the kernels walk: a tile cut into chunks of <= 32 duos (one per lane).  meta: bits 0..5 = duos in the chunk (0 marks the end of
+// a warp's list), kChunkFirst / kChunkLast = first / last chunk of its tile, kChunkSolo = the tile is its segment's only tile.
+// part = index of the tile's partial record (seg_first_tile[seg] + tile.part), used when a segment spans several tiles.
+struct __align__(16) ChunkDesc { uint32_t duo_begin, meta, seg, part; };
+constexpr uint32_t kChunkCountMask = 0x3fu, kChunkFirst = 0x100u, kChunkLast = 0x200u, kChunkSolo = 0x400u;
 
 struct DeviceProblem {
   const float4* cells_m;   // 3 x float4 per cell
@@ -42,8 +47,8 @@ struct DeviceProblem {
   const DuoRec* duo_recs;  // [n_duos] record-major table K3 streams with bulk copies
   const uint32_t* duo_p0;  // [n_duos] first pair of each duo (EMIT output rows)
   const uint32_t* seg_off; // [S+1] pair offsets per segment
-  const Tile* tiles;       // in the balanced order: warp w owns tiles [warp_off[w], warp_off[w+1])
-  uint32_t n_tiles;
+  const ChunkDesc* chunks; // in the balanced order: warp w owns chunks [warp_off[w], warp_off[w+1])
+  uint32_t n_chunks;
   const uint32_t* warp_off;  // [n_warps+1]
   uint32_t n_warps;
   const uint32_t* seg_first_tile;  // [S+1]
@@ -139,6 +144,8 @@ cudaError_t launch_lm_init(uint32_t S, int np, const double* d_poses0, LmState* 
 cudaError_t launch_lm_step(uint32_t S, int np, int use_manifold, const randt_solver_options& o, const double* rec, LmState* state,
                            double* eval_pose, double* mu, uint32_t* active, uint32_t* n_active, double* poses_out, double* result,
                            cudaStream_t s, int* n_launches);
+cudaError_t launch_replan(const ChunkDesc* chunks, uint32_t n_chunks, const uint32_t* active, uint32_t n_warps, uint32_t* flags, uint32_t* scan,
+                          uint32_t* block_sums, ChunkDesc* kept, uint32_t* warp_off, cudaStream_t s, int* n_launches);
 
 // static_cast<unsigned>(double) as x86-64 gcc defines it for negative inputs: truncate to int64, keep the low 32 bits
 __host__ __device__ inline uint32_t to_u32_trunc(double v) {

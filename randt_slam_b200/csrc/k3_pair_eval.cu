@@ -357,14 +357,10 @@ constexpr int kWarpsPerCta = kK3Threads / 32;
 constexpr int kStages = RANDT_K3_STAGES;
 constexpr int kMinCtas = RANDT_K3_MIN_CTAS;   // CTAs per SM the register allocation is bounded for
 
-struct __align__(16) ChunkMeta { uint32_t k, i, end, seg; };   // position in the tile order, first duo, tile end, segment (0xffffffff: past the end)
 struct __align__(128) StageBuf {
-  float4 rec[32][9];       // the chunk's 32 duo records (144 B each, see DuoRec in common.cuh), landed by ONE bulk copy
-  double pose[4];
+  float4 rec[32][9];       // the chunk's duo records (144 B each, see DuoRec in common.cuh), landed by ONE bulk copy
+  double pose[4];          // pose and GNC mu of the chunk's segment (valid for the first chunk of a tile)
   double mu;
-  uint32_t first;          // 1: first chunk of its tile (pose/mu valid)
-  uint32_t pad_;
-  ChunkMeta meta;
   unsigned long long bar;  // mbarrier the bulk copy completes on
 };
 
@@ -409,67 +405,51 @@ __device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, uint32_t 
 }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
-struct TileStream {   // generator (warp-uniform): the warp's range [k, k_end) of the balanced tile order, chunk by chunk; the following
-  // tile's descriptor is prefetched.  The tile list and the per-segment active flags are read through the kernel parameters
-  // (constant bank), not kept in registers.  Tiles of inactive segments (P.seg_active[seg] == 0) are emitted as one empty chunk
-  // (end == begin) that the consumer drops.
-  uint32_t k, k_end;
-  uint32_t i, end, seg, begin;
-  uint32_t la_seg, la_begin, la_end;   // descriptor of tile k + 1 (valid when k + 1 < k_end)
-  __device__ __forceinline__ void fetch_next(const DeviceProblem& P) {
-    if (k + 1 < k_end) {
-      const Tile n = P.tiles[k + 1];
-      la_seg = n.seg; la_begin = n.begin; la_end = n.end;
-      if (P.seg_active && P.seg_active[n.seg] == 0u) la_end = n.begin;
+// ---- the warp's work queue -------------------------------------------------------------------------------------------
+// The host cuts every tile into chunk descriptors (common.cuh: ChunkDesc) and stores them warp after warp in the balanced order, so
+// the device side of the schedule is a flat list walk: 32 descriptors at a time are pulled into shared memory with one coalesced
+// load (plus their segments' active flags, folded into a ballot mask); per chunk, lane 0 arms the stage's mbarrier and issues ONE
+// bulk (TMA) copy of the chunk's duo records plus, for the first chunk of a tile, 16-byte cp.async copies of the segment's pose
+// and mu.  No per-chunk index arithmetic, no gathers, no LSU traffic for the cell data.
+struct WarpQueue {
+  ChunkDesc* q;        // [32] in shared memory
+  uint32_t c_base, c_end, act_mask;
+  __device__ __forceinline__ void refill(const DeviceProblem& P, int lane) {
+    ChunkDesc d; d.duo_begin = 0; d.meta = 0; d.seg = 0; d.part = 0;
+    const uint32_t idx = c_base + (uint32_t)lane;
+    uint32_t on = 0;
+    if (idx < c_end) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(P.chunks) + idx);
+      d.duo_begin = v.x; d.meta = v.y; d.seg = v.z; d.part = v.w;
+      on = P.seg_active ? P.seg_active[d.seg] : 1u;
     }
+    *reinterpret_cast<uint4*>(&q[lane]) = make_uint4(d.duo_begin, d.meta, d.seg, d.part);
+    act_mask = __ballot_sync(kFull, on != 0u);
+    __syncwarp();
   }
-  __device__ __forceinline__ void init(const DeviceProblem& P, uint32_t w) {
-    k = P.warp_off[w]; k_end = P.warp_off[w + 1];
-    i = 0; end = 0; seg = 0; begin = 0;
-    la_seg = 0; la_begin = 0; la_end = 0;
-    if (k < k_end) {
-      const Tile c = P.tiles[k]; i = c.begin; begin = c.begin; end = c.end; seg = c.seg;
-      if (P.seg_active && P.seg_active[c.seg] == 0u) end = begin;
-    }
-    fetch_next(P);
-  }
-  __device__ __forceinline__ bool valid() const { return k < k_end; }
-  __device__ __forceinline__ void advance(const DeviceProblem& P) {
-    if (k >= k_end) return;
-    i += 32;
-    if (i >= end) {
-      ++k;
-      i = la_begin; begin = la_begin; end = la_end; seg = la_seg;
-      fetch_next(P);
-    }
+  __device__ __forceinline__ ChunkDesc get(int j) const {
+    const uint4 v = *reinterpret_cast<const uint4*>(&q[j]);
+    ChunkDesc d; d.duo_begin = v.x; d.meta = v.y; d.seg = v.z; d.part = v.w;
+    return d;
   }
 };
 
-// Stage the generator's current chunk into `sb`: lane 0 arms the stage's mbarrier with the byte count and issues ONE bulk
-// (TMA) copy of the chunk's duo records — they are contiguous in the record-major table — plus, for the first chunk of a tile,
-// 16-byte cp.async copies of the segment's pose and mu.  No per-lane address arithmetic, no gathers, no LSU traffic.
 template <int NP>
-__device__ __forceinline__ void stage_issue(const DeviceProblem& P, const TileStream& g, int lane, StageBuf* sb,
+__device__ __forceinline__ void stage_issue(const DeviceProblem& P, const WarpQueue& wq, int j, int lane, StageBuf* sb,
                                             const double* __restrict__ poses, const double* __restrict__ mu_per_seg) {
-  if (lane == 0) {
-    if (g.valid()) {
-      const uint32_t n_here = g.end > g.i ? min(32u, g.end - g.i) : 0u;
-      const bool first = g.i == g.begin;
-      if (n_here) {
-        const uint32_t bytes = n_here * (uint32_t)sizeof(DuoRec);
-        mbar_expect_tx(&sb->bar, bytes);
-        bulk_g2s(&sb->rec[0][0], P.duo_recs + g.i, bytes, &sb->bar);
-        if (first) {
-          const double* ps = poses + (size_t)g.seg * NP;
-          if (NP == 4) { cp_async16(&sb->pose[0], ps); cp_async16(&sb->pose[2], ps + 2); }
-          else { cp_async8(&sb->pose[0], ps); cp_async8(&sb->pose[1], ps + 1); cp_async8(&sb->pose[2], ps + 2); }
-          if (mu_per_seg) cp_async8(&sb->mu, mu_per_seg + g.seg);
-        }
+  if (lane == 0 && ((wq.act_mask >> j) & 1u)) {
+    const ChunkDesc d = wq.get(j);
+    const uint32_t n_here = d.meta & kChunkCountMask;
+    if (n_here) {
+      const uint32_t bytes = n_here * (uint32_t)sizeof(DuoRec);
+      mbar_expect_tx(&sb->bar, bytes);
+      bulk_g2s(&sb->rec[0][0], P.duo_recs + d.duo_begin, bytes, &sb->bar);
+      if (d.meta & kChunkFirst) {
+        const double* ps = poses + (size_t)d.seg * NP;
+        if (NP == 4) { cp_async16(&sb->pose[0], ps); cp_async16(&sb->pose[2], ps + 2); }
+        else { cp_async8(&sb->pose[0], ps); cp_async8(&sb->pose[1], ps + 1); cp_async8(&sb->pose[2], ps + 2); }
+        if (mu_per_seg) cp_async8(&sb->mu, mu_per_seg + d.seg);
       }
-      sb->first = first ? 1u : 0u;
-      sb->meta.k = g.k; sb->meta.i = g.i; sb->meta.end = g.end; sb->meta.seg = g.seg;
-    } else {
-      sb->meta.seg = 0xffffffffu;
     }
   }
   cp_async_commit();
@@ -490,46 +470,48 @@ __global__ void __launch_bounds__(kK3Threads, kMinCtas) k3_fused_kernel(DevicePr
   const uint32_t w = blockIdx.x * kWarpsPerCta + warp;
   if (w >= P.n_warps) return;
   StageBuf* stage = stage_all[warp];
+  __shared__ ChunkDesc queue_all[kWarpsPerCta][32];
+  WarpQueue wq;
+  wq.q = queue_all[warp];
+  wq.c_base = P.warp_off[w]; wq.c_end = P.warp_off[w + 1];
+  if (wq.c_base >= wq.c_end) return;
 
   if (lane == 0) {
 #pragma unroll
     for (int s = 0; s < kStages; ++s) mbar_init(&stage[s].bar, 1u);
     fence_mbar_init();
   }
-  __syncwarp();
-  TileStream gen;
-  gen.init(P, w);
-  // prologue: chunks 0 .. kStages-2 in flight
+  wq.refill(P, lane);        // includes the warp barrier that publishes the mbarrier init
+  // prologue: chunks 0 .. kStages-2 in flight (a warp owns at least one chunk; kStages - 1 <= 31 descriptors are in the queue)
 #pragma unroll
-  for (int s = 0; s < kStages - 1; ++s) {
-    stage_issue<NP>(P, gen, lane, &stage[s], poses, mu_per_seg);
-    gen.advance(P);
-  }
+  for (int s = 0; s < kStages - 1; ++s) stage_issue<NP>(P, wq, s, lane, &stage[s], poses, mu_per_seg);
   uint32_t phase_bits = 0u;     // bit s: parity the next completion of stage s's barrier will have
 
   // Pose and loss constants of the current tile live in shared memory (one copy per warp, broadcast LDS where they are used):
-  // ~26 fewer live registers per thread, which is what lets a fifth CTA fit on the SM.
+  // ~26 fewer live registers per thread.
   __shared__ PoseConst kc_all[kWarpsPerCta];
   __shared__ LossConst lc_all[kWarpsPerCta];
   PoseConst& kc = kc_all[warp]; LossConst& lc = lc_all[warp];
   double acc[NS]; double max_dd = 0.0; uint32_t n_bad = 0;
 #pragma unroll
   for (int e = 0; e < NS; ++e) acc[e] = 0.0;
-  int slot = 0;
+  int slot = 0, jj = 0;
   while (true) {
+    const ChunkDesc cm = wq.get(jj);
+    const uint32_t n_here = cm.meta & kChunkCountMask;
+    if (n_here == 0u) break;                                  // past the warp's last chunk
+    const bool live = (wq.act_mask >> jj) & 1u;               // false: chunk of an inactive segment (nothing was copied)
     // ---- stage chunk j + kStages - 1 ----
+    int jn = jj + kStages - 1;
+    if (jn >= 32) { wq.c_base += 32u; wq.refill(P, lane); jn -= 32; jj -= 32; }   // cm is already in registers
     int islot = slot + kStages - 1; if (islot >= kStages) islot -= kStages;
-    stage_issue<NP>(P, gen, lane, &stage[islot], poses, mu_per_seg);
-    gen.advance(P);
+    stage_issue<NP>(P, wq, jn, lane, &stage[islot], poses, mu_per_seg);
     // ---- chunk j has landed ----
     cp_async_wait<kStages - 1>();
     __syncwarp();
     StageBuf* sb = &stage[slot];
-    const ChunkMeta cm = sb->meta;
-    if (cm.seg == 0xffffffffu) break;
-    const bool live = cm.i < cm.end;          // false: tile of an inactive segment (dropped, nothing was copied)
     if (live) { mbar_wait(&sb->bar, (phase_bits >> slot) & 1u); phase_bits ^= 1u << slot; }
-    if (sb->first && live) {
+    if ((cm.meta & kChunkFirst) && live) {
       if (lane == 0) {
         PoseConst k0; LossConst l0;
         make_pose_const<VARIANT>(sb->pose, k0);
@@ -538,7 +520,7 @@ __global__ void __launch_bounds__(kK3Threads, kMinCtas) k3_fused_kernel(DevicePr
       }
       __syncwarp();
     }
-    if (cm.i + lane < cm.end) {
+    if (live && (uint32_t)lane < n_here) {
       RawCell m, f[2];
       m.a = sb->rec[lane][0]; m.b = sb->rec[lane][1]; m.c = sb->rec[lane][2];
       f[0].a = sb->rec[lane][3]; f[0].b = sb->rec[lane][4]; f[0].c = sb->rec[lane][5];
@@ -577,22 +559,21 @@ __global__ void __launch_bounds__(kK3Threads, kMinCtas) k3_fused_kernel(DevicePr
       }
     }
     // ---- tile finished: reduce across the warp and emit ----
-    if (live && cm.i + 32 >= cm.end) {
+    if (live && (cm.meta & kChunkLast)) {
       bfly_reduce<NS, 16>(acc, lane);          // slot s total now lives in lane bfly_owner<NS>(s) (acc[0])
       const double mine = acc[0];
       const double mx = warp_max_nonneg(max_dd);
       const uint32_t bad = __reduce_add_sync(kFull, n_bad);
       const uint32_t seg = cm.seg;
-      const uint32_t first = P.seg_first_tile[seg], seg_tiles = P.seg_first_tile[seg + 1] - first;
       const uint32_t n_pairs_seg = P.seg_off[seg + 1] - P.seg_off[seg];
-      if (seg_tiles == 1) {
+      if (cm.meta & kChunkSolo) {
         write_segment_out<VARIANT, WANT_JAC>(mine, mx, kc, n_pairs_seg, out + (size_t)seg * RANDT_FUSED_STRIDE, lane,
                                              [](int sl) { return bfly_owner<NS>(sl); });
         if (lane == 0 && bad) atomicAdd(bad_counter, (unsigned long long)bad);
       } else {
         // partial record of this tile: [NS sums][max dd][bad], one entry per lane
-        const uint32_t t = first + P.tiles[cm.k].part;
-        double* part = P.partials + (size_t)t * kMaxAcc;
+        const uint32_t first = P.seg_first_tile[seg], seg_tiles = P.seg_first_tile[seg + 1] - first;
+        double* part = P.partials + (size_t)cm.part * kMaxAcc;
         double pv = __shfl_sync(kFull, mine, bfly_owner<NS>(lane < NS ? lane : 0));
         if (lane == NS) pv = mx;
         if (lane == NS + 1) pv = (double)bad;
@@ -629,6 +610,7 @@ __global__ void __launch_bounds__(kK3Threads, kMinCtas) k3_fused_kernel(DevicePr
     // the next bulk copy overwrite it.
     __syncwarp();
     if (++slot == kStages) slot = 0;
+    ++jj;
   }
   cp_async_wait<0>();
 }
@@ -668,39 +650,41 @@ __global__ void __launch_bounds__(kK3Threads, kMinCtas) k3_emit_kernel(DevicePro
   const uint32_t w = blockIdx.x * kWarpsPerCta + warp;
   if (w >= P.n_warps) return;
   StageBuf* stage = stage_all[warp];
+  __shared__ ChunkDesc queue_all[kWarpsPerCta][32];
+  WarpQueue wq;
+  wq.q = queue_all[warp];
+  wq.c_base = P.warp_off[w]; wq.c_end = P.warp_off[w + 1];
+  if (wq.c_base >= wq.c_end) return;
   if (lane == 0) {
 #pragma unroll
     for (int s = 0; s < kStages; ++s) mbar_init(&stage[s].bar, 1u);
     fence_mbar_init();
   }
-  __syncwarp();
-  TileStream gen;
-  gen.init(P, w);
+  wq.refill(P, lane);
 #pragma unroll
-  for (int s = 0; s < kStages - 1; ++s) {
-    stage_issue<NP>(P, gen, lane, &stage[s], poses, nullptr);
-    gen.advance(P);
-  }
+  for (int s = 0; s < kStages - 1; ++s) stage_issue<NP>(P, wq, s, lane, &stage[s], poses, nullptr);
   PoseConst kc;
   uint32_t n_bad = 0, phase_bits = 0u;
-  int slot = 0;
+  int slot = 0, jj = 0;
   while (true) {
+    const ChunkDesc cm = wq.get(jj);
+    const uint32_t n_here = cm.meta & kChunkCountMask;
+    if (n_here == 0u) break;
+    const bool live = (wq.act_mask >> jj) & 1u;
+    int jn = jj + kStages - 1;
+    if (jn >= 32) { wq.c_base += 32u; wq.refill(P, lane); jn -= 32; jj -= 32; }
     int islot = slot + kStages - 1; if (islot >= kStages) islot -= kStages;
-    stage_issue<NP>(P, gen, lane, &stage[islot], poses, nullptr);
-    gen.advance(P);
+    stage_issue<NP>(P, wq, jn, lane, &stage[islot], poses, nullptr);
     cp_async_wait<kStages - 1>();
     __syncwarp();
     StageBuf* sb = &stage[slot];
-    const ChunkMeta cm = sb->meta;
-    if (cm.seg == 0xffffffffu) break;
-    const bool live = cm.i < cm.end;
     if (live) { mbar_wait(&sb->bar, (phase_bits >> slot) & 1u); phase_bits ^= 1u << slot; }
-    if (sb->first && live) make_pose_const<VARIANT>(sb->pose, kc);
-    if (cm.i + lane < cm.end) {
+    if ((cm.meta & kChunkFirst) && live) make_pose_const<VARIANT>(sb->pose, kc);
+    if (live && (uint32_t)lane < n_here) {
       RawCell m, f0, f1;
       m.a = sb->rec[lane][0]; m.b = sb->rec[lane][1]; m.c = sb->rec[lane][2];
       f0.a = sb->rec[lane][3]; f0.b = sb->rec[lane][4]; f0.c = sb->rec[lane][5];
-      const uint32_t p0 = __ldg(P.duo_p0 + cm.i + lane);     // first pair of the duo: where its rows go in r / J
+      const uint32_t p0 = __ldg(P.duo_p0 + cm.duo_begin + lane);     // first pair of the duo: where its rows go in r / J
       Moving mv;
       moving_part<VARIANT>(kc, m, mv);
       double N[4] = {0.0, 0.0, 0.0, 0.0};
@@ -715,6 +699,7 @@ __global__ void __launch_bounds__(kK3Threads, kMinCtas) k3_emit_kernel(DevicePro
     }
     __syncwarp();
     if (++slot == kStages) slot = 0;
+    ++jj;
   }
   cp_async_wait<0>();
   const uint32_t bad = __reduce_add_sync(kFull, n_bad);
@@ -840,7 +825,7 @@ cudaError_t launch_build_duo_records(const float4* cells_m, const float4* cells_
 
 cudaError_t launch_eval_fused(const DeviceProblem& p, int variant, const double* d_poses, const LossParams& lp, const double* d_mu,
                               bool want_jac, double* d_out, unsigned long long* d_bad, cudaStream_t s, int* n_launches) {
-  if (p.n_tiles == 0) return cudaSuccess;
+  if (p.n_chunks == 0) return cudaSuccess;
   cudaError_t e;
   switch (variant) {
     case 0: e = launch_fused_v<0>(p, d_poses, lp, d_mu, want_jac, d_out, d_bad, s); break;
@@ -855,7 +840,7 @@ cudaError_t launch_eval_fused(const DeviceProblem& p, int variant, const double*
 
 cudaError_t launch_eval_emit(const DeviceProblem& p, int variant, const double* d_poses, double* d_r, double* d_J,
                              unsigned long long* d_bad, cudaStream_t s, int* n_launches) {
-  if (p.n_tiles == 0) return cudaSuccess;
+  if (p.n_chunks == 0) return cudaSuccess;
   const int grid = stream_grid(p.n_warps);
 #define RANDT_EMIT(V)                                                                                              \
   if (d_J) k3_emit_kernel<V, true><<<grid, kK3Threads, 0, s>>>(p, d_poses, d_r, d_J, d_bad);             \

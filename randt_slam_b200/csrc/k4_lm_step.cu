@@ -301,6 +301,31 @@ __global__ void __launch_bounds__(64) k4_lm_step_kernel(uint32_t S, randt_solver
   state[s] = st;
 }
 
+// ---- re-planning the K3 schedule for the segments that are still active ------------------------------------------------
+// As segments finish, the static chunk list fills with chunks K3 must step over; when the active count has dropped enough, the
+// solver compacts the list (order preserved, so tiles stay contiguous) and hands every warp an equal share of what is left.
+__global__ void __launch_bounds__(256) k4_chunk_flags_kernel(const ChunkDesc* __restrict__ chunks, uint32_t n, const uint32_t* __restrict__ active,
+                                                             uint32_t* __restrict__ flags) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flags[i] = active[chunks[i].seg] != 0u ? 1u : 0u;
+}
+__global__ void __launch_bounds__(256) k4_compact_chunks_kernel(const ChunkDesc* __restrict__ chunks, uint32_t n, const uint32_t* __restrict__ flags,
+                                                                const uint32_t* __restrict__ scan, ChunkDesc* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && flags[i]) out[scan[i]] = chunks[i];
+}
+// warp w starts at the first tile boundary at or after its equal share w * n_kept / n_warps
+__global__ void __launch_bounds__(256) k4_warp_ranges_kernel(const ChunkDesc* __restrict__ kept, const uint32_t* __restrict__ n_kept_ptr, uint32_t n_warps,
+                                                             uint32_t* __restrict__ warp_off) {
+  const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w > n_warps) return;
+  const uint32_t n = *n_kept_ptr;
+  uint32_t i = (uint32_t)(((unsigned long long)w * n + n_warps - 1u) / n_warps);
+  if (w == n_warps) i = n;
+  while (i < n && !(kept[i].meta & kChunkFirst)) ++i;
+  warp_off[w] = i;
+}
+
 }  // namespace
 
 cudaError_t launch_lm_init(uint32_t S, int np, const double* d_poses0, LmState* state, double* eval_pose, double* mu, uint32_t* active,
@@ -320,6 +345,19 @@ cudaError_t launch_lm_step(uint32_t S, int np, int use_manifold, const randt_sol
   else if (np == 4)           k4_lm_step_kernel<4, false><<<grid, 64, 0, s>>>(S, o, rec, state, eval_pose, mu, active, n_active, poses_out, result);
   else                        k4_lm_step_kernel<3, false><<<grid, 64, 0, s>>>(S, o, rec, state, eval_pose, mu, active, n_active, poses_out, result);
   if (n_launches) *n_launches += 1;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_replan(const ChunkDesc* chunks, uint32_t n_chunks, const uint32_t* active, uint32_t n_warps, uint32_t* flags, uint32_t* scan,
+                          uint32_t* block_sums, ChunkDesc* kept, uint32_t* warp_off, cudaStream_t s, int* n_launches) {
+  if (n_chunks == 0) return cudaSuccess;
+  const unsigned grid = (n_chunks + 255u) / 256u;
+  k4_chunk_flags_kernel<<<grid, 256, 0, s>>>(chunks, n_chunks, active, flags);
+  cudaError_t e = launch_exclusive_scan_u32(flags, scan, n_chunks, block_sums, s, n_launches);
+  if (e != cudaSuccess) return e;
+  k4_compact_chunks_kernel<<<grid, 256, 0, s>>>(chunks, n_chunks, flags, scan, kept);
+  k4_warp_ranges_kernel<<<(n_warps + 256u) / 256u, 256, 0, s>>>(kept, scan + n_chunks, n_warps, warp_off);
+  if (n_launches) *n_launches += 3;
   return cudaGetLastError();
 }
 
