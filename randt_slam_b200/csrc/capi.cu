@@ -60,7 +60,8 @@ struct randt_problem {
   LmState* lm_state = nullptr; double *lm_eval_pose = nullptr, *lm_mu = nullptr, *lm_rec = nullptr, *lm_poses = nullptr, *lm_result = nullptr;
   uint32_t *lm_active = nullptr, *lm_n_active = nullptr;
   ChunkDesc* lm_chunks = nullptr; uint32_t *lm_flags = nullptr, *lm_scan = nullptr, *lm_bs = nullptr, *lm_warp_off = nullptr;   // re-planned schedule
-  uint32_t* h_n_active = nullptr;   // pinned
+  uint32_t* h_n_active = nullptr;   // pinned [2]
+  cudaEvent_t lm_ev[2] = {nullptr, nullptr};
 };
 
 namespace {
@@ -102,6 +103,8 @@ void free_problem(randt_problem* p) {
   cudaFree(p->lm_active); cudaFree(p->lm_n_active);
   cudaFree(p->lm_chunks); cudaFree(p->lm_flags); cudaFree(p->lm_scan); cudaFree(p->lm_bs); cudaFree(p->lm_warp_off);
   if (p->h_n_active) cudaFreeHost(p->h_n_active);
+  if (p->lm_ev[0]) cudaEventDestroy(p->lm_ev[0]);
+  if (p->lm_ev[1]) cudaEventDestroy(p->lm_ev[1]);
   delete p;
 }
 
@@ -713,7 +716,8 @@ int randt_register_batch_dev(randt_ctx* ctx, const randt_problem* cp, int varian
   if (!p->lm_state) {
     CK(dev_alloc(&p->lm_state, S)); CK(dev_alloc(&p->lm_eval_pose, (size_t)S * 4)); CK(dev_alloc(&p->lm_mu, S));
     CK(dev_alloc(&p->lm_rec, (size_t)S * RANDT_FUSED_STRIDE)); CK(dev_alloc(&p->lm_active, S)); CK(dev_alloc(&p->lm_n_active, 1));
-    CK(cudaHostAlloc(reinterpret_cast<void**>(&p->h_n_active), sizeof(uint32_t), cudaHostAllocDefault));
+    CK(cudaHostAlloc(reinterpret_cast<void**>(&p->h_n_active), 2 * sizeof(uint32_t), cudaHostAllocDefault));
+    CK(cudaEventCreateWithFlags(&p->lm_ev[0], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&p->lm_ev[1], cudaEventDisableTiming));
     CK(dev_alloc(&p->lm_chunks, p->n_chunks)); CK(dev_alloc(&p->lm_flags, p->n_chunks)); CK(dev_alloc(&p->lm_scan, (size_t)p->n_chunks + 1));
     CK(dev_alloc(&p->lm_bs, p->n_chunks / 1024 + 2)); CK(dev_alloc(&p->lm_warp_off, (size_t)p->n_warps + 1));
   }
@@ -724,16 +728,22 @@ int randt_register_batch_dev(randt_ctx* ctx, const randt_problem* cp, int varian
   const int poll = opt->poll_interval > 0 ? opt->poll_interval : 4;
   // every solve needs at most max_num_iterations candidate evaluations + its start evaluation; one more launch seeds the GNC
   const long long cap = 2 + (long long)(opt->gnc_max_steps + 1) * ((long long)opt->max_num_iterations + 2);
+  // Iterations are enqueued in groups of `poll`; the active counter of group g is read back while group g + 1 already runs, so the
+  // GPU never waits for the host (the price: up to one group of no-op launches after the last segment has finished).
   bool done = false;
   uint32_t planned_for = S;     // active segments when the schedule in use was made
-  for (long long it = 0; it < cap && !done; ++it) {
-    CK(launch_eval_fused(v, variant, p->lm_eval_pose, lp, p->lm_mu, true, p->lm_rec, ctx->d_bad, ctx->stream, &nl));
-    CK(launch_lm_step(S, np, opt->use_manifold, *opt, p->lm_rec, p->lm_state, p->lm_eval_pose, p->lm_mu, p->lm_active, p->lm_n_active, d_poses,
-                      d_result, ctx->stream, &nl));
-    if ((it + 1) % poll == 0 || it + 1 == cap) {
-      CK(cudaMemcpyAsync(p->h_n_active, p->lm_n_active, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-      CK(cudaStreamSynchronize(ctx->stream));
-      const uint32_t n_act = *p->h_n_active;
+  const long long n_groups = (cap + poll - 1) / poll;
+  for (long long g = 0; g < n_groups && !done; ++g) {
+    for (int i = 0; i < poll; ++i) {
+      CK(launch_eval_fused(v, variant, p->lm_eval_pose, lp, p->lm_mu, true, p->lm_rec, ctx->d_bad, ctx->stream, &nl));
+      CK(launch_lm_step(S, np, opt->use_manifold, *opt, p->lm_rec, p->lm_state, p->lm_eval_pose, p->lm_mu, p->lm_active, p->lm_n_active, d_poses,
+                        d_result, ctx->stream, &nl));
+    }
+    CK(cudaMemcpyAsync(&p->h_n_active[g & 1], p->lm_n_active, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaEventRecord(p->lm_ev[g & 1], ctx->stream));
+    if (g >= 1) {
+      CK(cudaEventSynchronize(p->lm_ev[(g - 1) & 1]));
+      const uint32_t n_act = p->h_n_active[(g - 1) & 1];
       done = n_act == 0u;
       // finished segments leave holes K3 has to step over: compact the schedule once a quarter of its segments are gone
       if (!done && (unsigned long long)n_act * 4ull <= (unsigned long long)planned_for * 3ull) {
@@ -744,6 +754,8 @@ int randt_register_batch_dev(randt_ctx* ctx, const randt_problem* cp, int varian
       }
     }
   }
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (!done) done = p->h_n_active[(n_groups - 1) & 1] == 0u;
   ctx->launches += nl;
   if (!done) return fail(ctx, RANDT_E_NONFINITE, "randt_register_batch: iteration cap reached with active segments (non-finite evaluations?)");
   return RANDT_OK;
