@@ -197,7 +197,7 @@ DeviceProblem view(const randt_problem* p) {
   DeviceProblem d;
   d.cells_m = p->cells_m; d.cells_f = p->cells_f; d.pairs = p->pairs; d.duos = p->duos; d.duo_recs = p->duo_recs; d.duo_p0 = p->duo_p0; d.seg_off = p->seg_off; d.chunks = p->chunks; d.n_chunks = p->n_chunks; d.warp_off = p->warp_off; d.n_warps = p->n_warps;
   d.seg_first_tile = p->seg_first_tile; d.n_segments = p->S; d.n_pairs = p->P; d.partials = p->partials; d.seg_counters = p->seg_counters;
-  d.seg_active = nullptr;
+  d.seg_active = nullptr; d.plan_static = 1u;
   return d;
 }
 
@@ -749,7 +749,7 @@ int randt_register_batch_dev(randt_ctx* ctx, const randt_problem* cp, int varian
       if (!done && (unsigned long long)n_act * 4ull <= (unsigned long long)planned_for * 3ull) {
         CK(launch_replan(p->chunks, p->n_chunks, p->lm_active, p->n_warps, p->lm_flags, p->lm_scan, p->lm_bs, p->lm_chunks, p->lm_warp_off,
                          ctx->stream, &nl));
-        v.chunks = p->lm_chunks; v.warp_off = p->lm_warp_off;
+        v.chunks = p->lm_chunks; v.warp_off = p->lm_warp_off; v.plan_static = 0u;
         planned_for = n_act;
       }
     }

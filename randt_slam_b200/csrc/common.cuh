@@ -51,6 +51,7 @@ struct DeviceProblem {
   uint32_t n_chunks;
   const uint32_t* warp_off;  // [n_warps+1]
   uint32_t n_warps;
+  uint32_t plan_static;      // 1: chunks / warp_off are the problem's immutable schedule; 0: produced by a preceding kernel (solver re-plan)
   const uint32_t* seg_first_tile;  // [S+1]
   uint32_t n_segments;
   uint32_t n_pairs;

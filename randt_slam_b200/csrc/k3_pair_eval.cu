@@ -428,6 +428,10 @@ __device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, uint32_t 
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(gmem), "r"(bytes), "r"(b)
                : "memory");
 }
+// programmatic dependent launch (sm_90+): let the next kernel of the stream start its prologue while this grid drains, and wait for
+// the previous grid's memory before touching anything it may have produced
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 // ---- the warp's work queue -------------------------------------------------------------------------------------------
@@ -439,19 +443,20 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 struct WarpQueue {
   ChunkDesc* q;        // [32] in shared memory
   uint32_t c_base, c_end, act_mask;
-  __device__ __forceinline__ void refill(const DeviceProblem& P, int lane) {
-    ChunkDesc d; d.duo_begin = 0; d.meta = 0; d.seg = 0; d.part = 0;
+  __device__ __forceinline__ uint4 load_desc(const DeviceProblem& P, int lane) const {   // (duo_begin, meta, seg, part); meta 0 past the end
     const uint32_t idx = c_base + (uint32_t)lane;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (idx < c_end) v = __ldg(reinterpret_cast<const uint4*>(P.chunks) + idx);
+    return v;
+  }
+  __device__ __forceinline__ void publish(const DeviceProblem& P, uint4 v, int lane) {      // active flags, queue, warp barrier
     uint32_t on = 0;
-    if (idx < c_end) {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(P.chunks) + idx);
-      d.duo_begin = v.x; d.meta = v.y; d.seg = v.z; d.part = v.w;
-      on = P.seg_active ? P.seg_active[d.seg] : 1u;
-    }
-    *reinterpret_cast<uint4*>(&q[lane]) = make_uint4(d.duo_begin, d.meta, d.seg, d.part);
+    if (v.y & kChunkCountMask) on = P.seg_active ? P.seg_active[v.z] : 1u;
+    *reinterpret_cast<uint4*>(&q[lane]) = v;
     act_mask = __ballot_sync(kFull, on != 0u);
     __syncwarp();
   }
+  __device__ __forceinline__ void refill(const DeviceProblem& P, int lane) { publish(P, load_desc(P, lane), lane); }
   __device__ __forceinline__ ChunkDesc get(int j) const {
     const uint4 v = *reinterpret_cast<const uint4*>(&q[j]);
     ChunkDesc d; d.duo_begin = v.x; d.meta = v.y; d.seg = v.z; d.part = v.w;
@@ -498,15 +503,21 @@ __global__ void __launch_bounds__(kK3Threads, kMinCtas) k3_fused_kernel(DevicePr
   __shared__ ChunkDesc queue_all[kWarpsPerCta][32];
   WarpQueue wq;
   wq.q = queue_all[warp];
-  wq.c_base = P.warp_off[w]; wq.c_end = P.warp_off[w + 1];
-  if (wq.c_base >= wq.c_end) return;
-
+  griddep_launch_dependents();
   if (lane == 0) {
 #pragma unroll
     for (int s = 0; s < kStages; ++s) mbar_init(&stage[s].bar, 1u);
     fence_mbar_init();
   }
-  wq.refill(P, lane);        // includes the warp barrier that publishes the mbarrier init
+  // Everything the previous kernel of the stream may have written (poses, mu, active flags, `out`, a re-planned schedule) is read
+  // after griddep_wait(); the static schedule of a problem is immutable, so its first descriptors are fetched while the
+  // previous grid is still draining.
+  if (!P.plan_static) griddep_wait();
+  wq.c_base = P.warp_off[w]; wq.c_end = P.warp_off[w + 1];
+  const uint4 v_first = wq.load_desc(P, lane);
+  if (P.plan_static) griddep_wait();
+  if (wq.c_base >= wq.c_end) return;
+  wq.publish(P, v_first, lane);        // includes the warp barrier that publishes the mbarrier init
   // prologue: chunks 0 .. kStages-2 in flight (a warp owns at least one chunk; kStages - 1 <= 31 descriptors are in the queue)
 #pragma unroll
   for (int s = 0; s < kStages - 1; ++s) stage_issue<NP>(P, wq, s, lane, &stage[s], poses, mu_per_seg);
@@ -806,9 +817,14 @@ template <int VARIANT, int LOSS>
 cudaError_t launch_fused_vl(const DeviceProblem& p, const double* d_poses, const LossParams& lp, const double* d_mu, bool want_jac,
                             double* d_out, unsigned long long* bad, cudaStream_t s) {
   const int grid = stream_grid(p.n_warps);
-  if (want_jac) k3_fused_kernel<VARIANT, LOSS, true><<<grid, kK3Threads, 0, s>>>(p, d_poses, lp, d_mu, d_out, bad);
-  else          k3_fused_kernel<VARIANT, LOSS, false><<<grid, kK3Threads, 0, s>>>(p, d_poses, lp, d_mu, d_out, bad);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kK3Threads); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  if (want_jac) return cudaLaunchKernelEx(&cfg, k3_fused_kernel<VARIANT, LOSS, true>, p, d_poses, lp, d_mu, d_out, bad);
+  return cudaLaunchKernelEx(&cfg, k3_fused_kernel<VARIANT, LOSS, false>, p, d_poses, lp, d_mu, d_out, bad);
 }
 template <int VARIANT>
 cudaError_t launch_fused_v(const DeviceProblem& p, const double* d_poses, const LossParams& lp, const double* d_mu, bool want_jac,

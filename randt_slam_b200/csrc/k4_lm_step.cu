@@ -244,6 +244,8 @@ __global__ void __launch_bounds__(64) k4_lm_step_kernel(uint32_t S, randt_solver
                                                          double* __restrict__ eval_pose, double* __restrict__ mu_arr,
                                                          uint32_t* __restrict__ active, uint32_t* __restrict__ n_active,
                                                          double* __restrict__ poses_out, double* __restrict__ result) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");      // the records of the K3 launch just before
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= S || active[s] == 0u) return;
   typedef Dims<NP, MANIFOLD> D;
@@ -340,12 +342,16 @@ cudaError_t launch_lm_step(uint32_t S, int np, int use_manifold, const randt_sol
                            double* eval_pose, double* mu, uint32_t* active, uint32_t* n_active, double* poses_out, double* result,
                            cudaStream_t s, int* n_launches) {
   if (S == 0) return cudaSuccess;
-  const int grid = (int)((S + 63u) / 64u);
-  if (np == 4 && use_manifold) k4_lm_step_kernel<4, true><<<grid, 64, 0, s>>>(S, o, rec, state, eval_pose, mu, active, n_active, poses_out, result);
-  else if (np == 4)           k4_lm_step_kernel<4, false><<<grid, 64, 0, s>>>(S, o, rec, state, eval_pose, mu, active, n_active, poses_out, result);
-  else                        k4_lm_step_kernel<3, false><<<grid, 64, 0, s>>>(S, o, rec, state, eval_pose, mu, active, n_active, poses_out, result);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((S + 63u) / 64u); cfg.blockDim = dim3(64); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
   if (n_launches) *n_launches += 1;
-  return cudaGetLastError();
+  if (np == 4 && use_manifold) return cudaLaunchKernelEx(&cfg, k4_lm_step_kernel<4, true>, S, o, rec, state, eval_pose, mu, active, n_active, poses_out, result);
+  if (np == 4) return cudaLaunchKernelEx(&cfg, k4_lm_step_kernel<4, false>, S, o, rec, state, eval_pose, mu, active, n_active, poses_out, result);
+  return cudaLaunchKernelEx(&cfg, k4_lm_step_kernel<3, false>, S, o, rec, state, eval_pose, mu, active, n_active, poses_out, result);
 }
 
 cudaError_t launch_replan(const ChunkDesc* chunks, uint32_t n_chunks, const uint32_t* active, uint32_t n_warps, uint32_t* flags, uint32_t* scan,
