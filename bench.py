@@ -104,6 +104,21 @@ def build_problem(ctx, capi, p, n_problems, seed0):
     return prob, poses, stats, host
 
 
+def measured_traffic(pairs):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one K3 fused launch from the committed `ncu --set full` capture of this very
+    workload (profiles/r01_k3_fused_*_ncu_summary.txt, newest); None when the capture was taken on a different batch size."""
+    import glob
+    import re
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r01_k3_fused_*_ncu_summary.txt"))):
+        txt = open(path).read()
+        m_pairs = re.search(r"([\d ]+) pairs per launch", txt)
+        rd = re.search(r"dram__bytes_read\.sum\s+Mbyte\s+([\d.]+)", txt); wr = re.search(r"dram__bytes_write\.sum\s+Mbyte\s+([\d.]+)", txt)
+        if m_pairs and rd and wr and int(m_pairs.group(1).replace(" ", "")) == pairs:
+            best = (float(rd.group(1)) + float(wr.group(1))) * 1e6
+    return best
+
+
 def algorithmic_bytes(st, fused=True):
     """48 (N_m + N_f) + 8 P + 32 S + OUT, with N_f = fixed cells the pair list references; OUT = 192 S (fused)."""
     return 48 * (st["n_m"] + st["n_f_referenced"]) + 8 * st["pairs"] + 32 * st["segments"] + 192 * st["segments"]
@@ -421,7 +436,7 @@ def main():
                     "ms_per_step": e2e_ms_all / args.steps, "api": "randt_eval_fused (host pointers)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
-                         "traffic": None, "peak_source": pk_src, "kernel": "k3_fused_kernel<0,BARRON_M2,true>",
+                         "traffic": measured_traffic(Pn), "peak_source": pk_src, "kernel": "k3_fused_kernel<0,BARRON_M2,true>",
                          "algorithmic_bytes_per_launch": alg, "kernel_ms": kern_ms},
             "clocks": clocks,
             "degenerate_pairs": bad,

@@ -137,6 +137,11 @@ RANDT_API int randt_map_transform(randt_ctx* ctx, randt_map* map, const float* t
 RANDT_API int randt_map_merge(randt_ctx* ctx, randt_map* fixed, const randt_map* moving);
 RANDT_API void randt_map_destroy(randt_map* map);
 
+/* Map::calculateCSDivergence (R/src/ndt_representation/ndt_map.cpp:42-99): Cauchy-Schwarz divergence between fixed map b and moving map b
+ * (already transformed into the fixed frame, as R/src/local_fuser/local_fuser.cpp:338-339 does) for every b; out: host float64 [n_maps].
+ * The reference leaves its three accumulators uninitialised; they start at zero here. */
+RANDT_API int randt_cs_divergence(randt_ctx* ctx, const randt_map* fixed, const randt_map* moving, double* out);
+
 /* ---- K2: association ----------------------------------------------------------------------------------
  * Replaces the association half of Matcher::addNDTFactor (R/src/ndt_registration/ndt_matcher.cpp:200-217,249-253):
  * transform each moving cell by the initial guess (float32), Map::getClosestCells (ndt_map.cpp:101-151,163-175) with the

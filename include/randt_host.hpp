@@ -126,6 +126,8 @@ class Map {
   void transformMap(const SE2d* trans);            // one transform per map (Map::transformMap, float32 like the reference)
   void transformMap(const SE2d& t) { transformMap(&t); }
   void mergeMapCell(const Map& moving);             // Map::mergeMapCell for every map of the batch
+  // Map::calculateCSDivergence (ndt_map.cpp:42-99) against the (already transformed) moving map, one value per map of the batch
+  std::vector<double> calculateCSDivergence(const Map& m_map) const;
   size_t get_n_cells() const;                       // total over the batch
   uint32_t n_maps() const;
   // Map::getCellMeanAndCovariance (ndt_map.h:112-119): mean[3], row-major cov[9]; cached host copy, refreshed after mutation

@@ -671,4 +671,59 @@ inline double gnc_initial_mu(double max_residual, double loss_scale, double divi
   return std::min(mu, std::pow(divisor, steps - 1));
 }
 
+// ------------------------------------------------------------------------------------------
+// Map::calculateCSDivergence     R/src/ndt_representation/ndt_map.cpp:42-99   
+// float32 3x3 algebra in Eigen's evaluation order, fp64 accumulation in the reference's loop order.  The reference leaves
+// interaction_term / fixed_term / moving_term uninitialised (quirk B.15); the oracle starts them at 0.
+// `moving` must already be expressed in the fixed map's frame (R/src/local_fuser/local_fuser.cpp:338).
+// ------------------------------------------------------------------------------------------
+inline float det3_f(const float m[9]) {   // Eigen determinant_impl<Matrix3f>: helper(0,1,2) - helper(1,0,2) + helper(2,0,1)
+  auto M = [&](int r, int c) { return m[r * 3 + c]; };
+  const float h0 = M(0, 0) * (M(1, 1) * M(2, 2) - M(1, 2) * M(2, 1));
+  const float h1 = M(0, 1) * (M(1, 0) * M(2, 2) - M(1, 2) * M(2, 0));
+  const float h2 = M(0, 2) * (M(1, 0) * M(2, 1) - M(1, 1) * M(2, 0));
+  return (h0 - h1) + h2;
+}
+inline void inv3_f(const float m[9], float inv[9]) {   // Eigen compute_inverse_size3
+  auto M = [&](int r, int c) { return m[r * 3 + c]; };
+  auto cof = [&](int i, int j) {
+    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+    return M(i1, j1) * M(i2, j2) - M(i1, j2) * M(i2, j1);
+  };
+  const float c0 = cof(0, 0), c1 = cof(1, 0), c2 = cof(2, 0);
+  const float det = c0 * M(0, 0) + (c1 * M(1, 0) + c2 * M(2, 0));
+  const float invdet = 1.0f / det;
+  inv[0] = c0 * invdet; inv[1] = c1 * invdet; inv[2] = c2 * invdet;
+  inv[3] = cof(0, 1) * invdet; inv[4] = cof(1, 1) * invdet; inv[5] = cof(2, 1) * invdet;
+  inv[6] = cof(0, 2) * invdet; inv[7] = cof(1, 2) * invdet; inv[8] = cof(2, 2) * invdet;
+}
+inline double cs_gauss_overlap(const Cell12& a, const Cell12& b) {
+  float d[3], S[9], Si[9];
+  for (int i = 0; i < 3; ++i) d[i] = a.mu[i] - b.mu[i];
+  for (int i = 0; i < 9; ++i) S[i] = a.cov[i] + b.cov[i];
+  inv3_f(S, Si);
+  float t[3];
+  for (int j = 0; j < 3; ++j) t[j] = d[0] * Si[j] + (d[1] * Si[3 + j] + d[2] * Si[6 + j]);
+  const double e = (double)(t[0] * d[0] + (t[1] * d[1] + t[2] * d[2]));
+  return (0.5 / std::sqrt(M_PI * M_PI * (double)det3_f(S))) * std::exp(-0.5 * e);
+}
+inline double cs_divergence(const Cell12* fixed, size_t nf, const Cell12* moving, size_t nm, double terms[3] = nullptr) {
+  double interaction_term = 0.0, fixed_term = 0.0, moving_term = 0.0;
+  for (size_t f = 0; f < nf; ++f) {
+    if (det3_f(fixed[f].cov) < 0.00001) continue;
+    for (size_t q = 0; q < nm; ++q) interaction_term += cs_gauss_overlap(fixed[f], moving[q]);
+    float inv[9]; inv3_f(fixed[f].cov, inv);
+    fixed_term += std::sqrt((double)det3_f(inv)) / (2 * M_PI);
+    for (size_t q = 0; q < f; ++q) fixed_term += 2 * cs_gauss_overlap(fixed[f], fixed[q]);
+  }
+  for (size_t f = 0; f < nm; ++f) {
+    if (det3_f(moving[f].cov) < 0.00001) continue;
+    float inv[9]; inv3_f(moving[f].cov, inv);
+    moving_term += std::sqrt((double)det3_f(inv)) / (2 * M_PI);
+    for (size_t q = 0; q < f; ++q) moving_term += 2 * cs_gauss_overlap(moving[f], moving[q]);
+  }
+  if (terms) { terms[0] = interaction_term; terms[1] = fixed_term; terms[2] = moving_term; }
+  return -std::log(interaction_term) + 0.5 * std::log(fixed_term) + 0.5 * std::log(moving_term);
+}
+
 }  // namespace orc

@@ -224,4 +224,8 @@ int orc_bnb(const float* f_cells, int n_f, const int32_t* f_slot, int size_x, in
   return 0;
 }
 
+double orc_cs_divergence(const float* f_cells, size_t n_f, const float* m_cells, size_t n_m, double* terms3) {
+  return cs_divergence(reinterpret_cast<const Cell12*>(f_cells), n_f, reinterpret_cast<const Cell12*>(m_cells), n_m, terms3);
+}
+
 }  // extern "C"

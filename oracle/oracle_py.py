@@ -88,6 +88,7 @@ def _sig(L):
     L.orc_loop_constraint.argtypes = [pf, i, pi, i, i, d, d, pf, i, pd, i, i, i, d, d, d, d, i, i, i, d, pu, pu, i, pd]
     L.orc_sweep_costs.restype = None; L.orc_sweep_costs.argtypes = [i, pf, pf, pu, pu, sz, i, d, d, d, d, pd, sz, pd]
     L.orc_bnb.restype = i; L.orc_bnb.argtypes = [pf, i, pi, i, i, d, d, pf, i, pd, i, d, d, d, d, d, d, d, i, pd]
+    L.orc_cs_divergence.restype = d; L.orc_cs_divergence.argtypes = [pf, sz, pf, sz, pd]
     L.orc_se2_plus.restype = None; L.orc_se2_plus.argtypes = [pd, pd, pd]
     L.orc_se2_plus_jacobian.restype = None; L.orc_se2_plus_jacobian.argtypes = [pd, pd]
 
@@ -282,3 +283,11 @@ def bnb(f_cells, f_slot, size_x, size_y, res, max_linf, m_cells, pose, alpha, sc
                   _p(pose, C.c_double), int(variant), float(alpha), float(scale), float(window_linear), float(window_angular), float(linear_step),
                   float(max_px_range), float(cost_threshold), int(n_iter), _p(out, C.c_double))
     return dict(pose=out[:4].copy(), min_cost=out[4], n_evaluated=int(out[5]))
+
+
+def cs_divergence(f_cells, m_cells):
+    """Map::calculateCSDivergence restated -> (divergence, [interaction, fixed, moving] terms)"""
+    fc = _f32(f_cells).reshape(-1, 12); mc = _f32(m_cells).reshape(-1, 12)
+    terms = np.zeros(3, np.float64)
+    v = lib().orc_cs_divergence(_p(fc, C.c_float), len(fc), _p(mc, C.c_float), len(mc), _p(terms, C.c_double))
+    return v, terms

@@ -24,6 +24,7 @@ UNITS = {
     "k4_lm_step.cu": [],
     "k2_associate.cu": ["-fmad=false"],
     "k1_voxelize.cu": ["-fmad=false"],
+    "k5_cs_divergence.cu": ["-fmad=false"],
     "capi.cu": [],
 }
 

@@ -88,6 +88,7 @@ _SIGS = {
     "randt_map_transform": (_i, [_vp, _vp, _vp]),
     "randt_map_merge": (_i, [_vp, _vp, _vp]),
     "randt_map_destroy": (None, [_vp]),
+    "randt_cs_divergence": (_i, [_vp, _vp, _vp, _vp]),
     "randt_associate": (_i, [_vp, _vp, _vp, _vp, _i, _i, C.POINTER(_vp)]),
     "randt_problem_create": (_i, [_vp, _vp, _u32, _vp, _u32, _vp, _vp, _u32, _vp, _u32, C.POINTER(_vp)]),
     "randt_problem_info": (_i, [_vp, C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_u32)]),
@@ -258,6 +259,12 @@ class Map:
 
     def merge(self, moving):
         self.ctx._check(lib().randt_map_merge(self.ctx._h, self._h, moving._h))
+
+    def cs_divergence(self, moving):
+        """Map::calculateCSDivergence for every map pair of the batch -> float64 [B]"""
+        out = np.zeros(self.info()[0], np.float64)
+        self.ctx._check(lib().randt_cs_divergence(self.ctx._h, self._h, moving._h, _ptr(out)))
+        return out
 
 
 class Problem:

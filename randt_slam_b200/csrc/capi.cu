@@ -457,6 +457,27 @@ int randt_map_merge(randt_ctx* ctx, randt_map* F, const randt_map* M) {
   return RANDT_OK;
 }
 
+int randt_cs_divergence(randt_ctx* ctx, const randt_map* F, const randt_map* M, double* out) {
+  if (!ctx || !F || !M || !out) return fail(ctx, RANDT_E_INVALID, "randt_cs_divergence: null argument");
+  if (F->B != M->B) return fail(ctx, RANDT_E_INVALID, "randt_cs_divergence: fixed and moving batches differ in size");
+  CK(cudaSetDevice(ctx->device));
+  const uint32_t B = F->B;
+  if (B == 0) return RANDT_OK;
+  double *d_part = nullptr, *d_out = nullptr; uint32_t* d_tick = nullptr;
+  int nl = 0;
+  cudaError_t e = dev_alloc(&d_part, (size_t)B * cs_divergence_split() * 3);
+  if (e == cudaSuccess) e = dev_alloc(&d_out, B);
+  if (e == cudaSuccess) e = dev_alloc(&d_tick, B);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_tick, 0, (size_t)B * sizeof(uint32_t), ctx->stream);
+  if (e == cudaSuccess) e = launch_cs_divergence(F->cells, F->cell_off, M->cells, M->cell_off, B, d_part, d_tick, d_out, ctx->stream, &nl);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_part); cudaFree(d_out); cudaFree(d_tick);
+  if (e != cudaSuccess) return fail(ctx, RANDT_E_CUDA, "randt_cs_divergence", e);
+  ctx->launches += nl;
+  return RANDT_OK;
+}
+
 void randt_map_destroy(randt_map* m) { if (m) { cudaSetDevice(m->device); free_map(m); } }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -148,6 +148,11 @@ cudaError_t launch_lm_step(uint32_t S, int np, int use_manifold, const randt_sol
 cudaError_t launch_replan(const ChunkDesc* chunks, uint32_t n_chunks, const uint32_t* active, uint32_t n_warps, uint32_t* flags, uint32_t* scan,
                           uint32_t* block_sums, ChunkDesc* kept, uint32_t* warp_off, cudaStream_t s, int* n_launches);
 
+// k5_cs_divergence.cu
+cudaError_t launch_cs_divergence(const float4* cells_f, const uint32_t* off_f, const float4* cells_m, const uint32_t* off_m, uint32_t n_maps,
+                                 double* d_partials, uint32_t* d_tickets, double* d_out, cudaStream_t s, int* n_launches);
+int cs_divergence_split();
+
 // static_cast<unsigned>(double) as x86-64 gcc defines it for negative inputs: truncate to int64, keep the low 32 bits
 __host__ __device__ inline uint32_t to_u32_trunc(double v) {
   if (!(v > -9.2e18 && v < 9.2e18)) return 0u;

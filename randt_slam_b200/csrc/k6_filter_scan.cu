@@ -1,0 +1,164 @@
+// K6 — per-azimuth peak filter of a raw polar radar scan (sm_100a).  Compiled with -fmad=false.
+//
+// Replaces RadarPreprocessor::filterScan   R/src/radar_preprocessing/radar_preprocessor.cpp:45-125  (the only
+// HBM-scale input of the path — 400 azimuths x ~3000 range bins x 16 B = 19 MB per Oxford scan against 80 KB of filtered points):
+//   pass 1  for every azimuth, the first strongest return with min_range < range < max_range (strict `>` against a running
+//           maximum that starts at 0); the reference emits an azimuth's peak when the NEXT azimuth starts, so the last azimuth of
+//           a scan never contributes, and an azimuth without a valid return contributes nothing (except that a scan whose very
+//           first azimuth is empty emits point 0);
+//   pass 2  from each peak, walk inwards and outwards while the intensity keeps falling, the range step stays below
+//           beam_distance_increment_threshold and the range stays above min_range; keep the points of that run that pass the
+//           range / min_intensity gates; transform them to the base frame (pcl::transformPointCloud with an Affine3f).
+// The reference finds azimuth boundaries by comparing atan2(y, x) of every point with the first point of the current azimuth
+// (tolerance 1e-4 rad).  This kernel takes the organised shape (n_azimuths x n_bins, what cloud_in->height/width carry) and
+// VERIFIES that the angle rule would cut the scan at exactly those rows; if not it reports RANDT_E_INVALID instead of guessing.
+//
+// k6_row_peak_kernel: one CTA per azimuth, coalesced float4 loads, block arg-max with lowest-index tie-break (= first-wins).
+// k6_runs_kernel: one thread per emitted peak walks its run (tens of dependent loads), block scan of the kept counts, ordered
+// write of the transformed points.  HBM-bound: 16 B per raw point read once, algorithmic bytes 16 n_az n_bins + 16 n_out.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace randt {
+namespace {
+
+constexpr int kRowThreads = 256;
+constexpr uint32_t kNoPeak = 0xffffffffu;
+
+// std::hypot(float, float): glibc evaluates it in double and rounds once
+__device__ __forceinline__ float hypot_ref(float x, float y) { return (float)sqrt((double)x * (double)x + (double)y * (double)y); }
+
+__global__ void __launch_bounds__(kRowThreads) k6_row_peak_kernel(const float4* __restrict__ raw, uint32_t n_az, uint32_t n_bins, float min_d,
+                                                                  float max_d, uint32_t* __restrict__ peak_idx, float* __restrict__ row_angle,
+                                                                  int* __restrict__ status) {
+  const uint32_t row = blockIdx.x;
+  const float4* p = raw + (size_t)row * n_bins;
+  const float a0 = atan2f(p[0].y, p[0].x);
+  float best = 0.0f; uint32_t best_i = kNoPeak; bool bad = false;
+  for (uint32_t b = threadIdx.x; b < n_bins; b += kRowThreads) {
+    const float4 v = __ldg(p + b);
+    const float dist = hypot_ref(v.x, v.y);
+    if (fabsf(atan2f(v.y, v.x) - a0) > 0.0001f) bad = true;      // the reference would start a new azimuth inside this row
+    if (dist > min_d && dist < max_d && v.w > best) { best = v.w; best_i = b; }   // ascending b per thread: first-wins inside the thread
+  }
+  __shared__ float s_val[kRowThreads];
+  __shared__ uint32_t s_idx[kRowThreads];
+  __shared__ int s_bad;
+  if (threadIdx.x == 0) s_bad = 0;
+  s_val[threadIdx.x] = best; s_idx[threadIdx.x] = best_i;
+  __syncthreads();
+  if (bad) s_bad = 1;
+  for (int o = kRowThreads / 2; o > 0; o >>= 1) {
+    __syncthreads();
+    if ((int)threadIdx.x < o) {
+      const float v2 = s_val[threadIdx.x + o]; const uint32_t i2 = s_idx[threadIdx.x + o];
+      if (v2 > s_val[threadIdx.x] || (v2 == s_val[threadIdx.x] && i2 < s_idx[threadIdx.x])) { s_val[threadIdx.x] = v2; s_idx[threadIdx.x] = i2; }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    peak_idx[row] = s_idx[0] == kNoPeak ? kNoPeak : row * n_bins + s_idx[0];
+    row_angle[row] = a0;
+    if (s_bad) atomicExch(status, 1);
+  }
+}
+
+struct FilterDev { float min_d, max_d, min_i; double beam_thr; float tf[12]; };
+
+__global__ void __launch_bounds__(1024) k6_runs_kernel(const float4* __restrict__ raw, uint32_t n_az, uint32_t n_bins, FilterDev f,
+                                                       const uint32_t* __restrict__ peak_idx, const float* __restrict__ row_angle,
+                                                       float4* __restrict__ out, uint32_t cap, uint32_t* __restrict__ n_out, int* __restrict__ status) {
+  // the reference's cut rule between consecutive rows: |angle(first of row r+1) - angle(first of row r)| must exceed 1e-4
+  __shared__ uint32_t s_scan[1024];
+  __shared__ uint32_t s_carry;
+  const uint32_t n_pts = n_az * n_bins;
+  for (uint32_t r = threadIdx.x; r + 1 < n_az; r += blockDim.x)
+    if (!(fabsf(row_angle[r + 1] - row_angle[r]) > 0.0001f)) atomicExch(status, 1);
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  // rows 0 .. n_az-2 emit (the last azimuth is never closed); row 0 without a valid return emits point 0
+  const uint32_t n_rows = n_az > 0 ? n_az - 1 : 0;
+  for (uint32_t base = 0; base < n_rows; base += blockDim.x) {
+    const uint32_t r = base + threadIdx.x;
+    uint32_t peak = kNoPeak, lo = 0, hi = 0, cnt = 0;
+    if (r < n_rows) {
+      peak = peak_idx[r];
+      if (peak == kNoPeak && r == 0) peak = 0;
+    }
+    if (peak != kNoPeak) {
+      uint32_t k = 0;
+      while (true) {        // towards the sensor
+        const uint32_t cur = peak - k;
+        if (cur == 0) { lo = cur; break; }              // size_t wrap check of the reference (closer_idx is then left as is: defined here)
+        const float4 a = __ldg(raw + cur), b = __ldg(raw + cur - 1);
+        const float da = hypot_ref(a.x, a.y), db = hypot_ref(b.x, b.y);
+        if (((double)(da - db) > f.beam_thr) || (a.w <= b.w) || (da < f.min_d)) { lo = cur; break; }
+        ++k;
+      }
+      k = 0;
+      while (true) {        // away from the sensor
+        const uint32_t cur = peak + k;
+        if (cur + 1 > n_pts - 1) { hi = cur; break; }
+        const float4 a = __ldg(raw + cur), b = __ldg(raw + cur + 1);
+        const float da = hypot_ref(a.x, a.y), db = hypot_ref(b.x, b.y);
+        if (((double)(da - db) > f.beam_thr) || (a.w <= b.w) || (da < f.min_d)) { hi = cur; break; }
+        ++k;
+      }
+      for (uint32_t j = lo; j <= hi; ++j) {
+        const float4 v = __ldg(raw + j);
+        const float dist = hypot_ref(v.x, v.y);
+        if (dist > f.min_d && dist < f.max_d && v.w > f.min_i) ++cnt;
+      }
+    }
+    // block exclusive scan of cnt (Hillis-Steele in shared memory)
+    s_scan[threadIdx.x] = cnt;
+    __syncthreads();
+    for (uint32_t o = 1; o < blockDim.x; o <<= 1) {
+      uint32_t v = 0;
+      if (threadIdx.x >= o) v = s_scan[threadIdx.x - o];
+      __syncthreads();
+      s_scan[threadIdx.x] += v;
+      __syncthreads();
+    }
+    const uint32_t incl = s_scan[threadIdx.x], total = s_scan[blockDim.x - 1];
+    uint32_t w = s_carry + incl - cnt;
+    if (peak != kNoPeak) {
+      for (uint32_t j = lo; j <= hi; ++j) {
+        const float4 v = __ldg(raw + j);
+        const float dist = hypot_ref(v.x, v.y);
+        if (dist > f.min_d && dist < f.max_d && v.w > f.min_i) {
+          if (w < cap) {
+            // pcl::transformPointCloud (Affine3f, SSE path): (x c0 + y c1) + (z c2 + c3) per output row
+            float4 o;
+            o.x = (v.x * f.tf[0] + v.y * f.tf[1]) + (v.z * f.tf[2] + f.tf[3]);
+            o.y = (v.x * f.tf[4] + v.y * f.tf[5]) + (v.z * f.tf[6] + f.tf[7]);
+            o.z = (v.x * f.tf[8] + v.y * f.tf[9]) + (v.z * f.tf[10] + f.tf[11]);
+            o.w = v.w;
+            out[w] = o;
+          }
+          ++w;
+        }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { *n_out = s_carry; if (s_carry > cap) atomicExch(status, 2); }
+}
+
+}  // namespace
+
+cudaError_t launch_filter_scan(const float4* d_raw, uint32_t n_az, uint32_t n_bins, const randt_filter_params& fp, uint32_t* d_peak, float* d_angle,
+                               float4* d_out, uint32_t cap, uint32_t* d_n_out, int* d_status, cudaStream_t s, int* n_launches) {
+  if (n_az == 0 || n_bins == 0) return cudaMemsetAsync(d_n_out, 0, sizeof(uint32_t), s);
+  FilterDev f; f.min_d = fp.min_range; f.max_d = fp.max_range; f.min_i = fp.min_intensity; f.beam_thr = fp.beam_distance_increment_threshold;
+  for (int i = 0; i < 12; ++i) f.tf[i] = fp.sensor_to_base[i];
+  k6_row_peak_kernel<<<n_az, kRowThreads, 0, s>>>(d_raw, n_az, n_bins, f.min_d, f.max_d, d_peak, d_angle, d_status);
+  k6_runs_kernel<<<1, 1024, 0, s>>>(d_raw, n_az, n_bins, f, d_peak, d_angle, d_out, cap, d_n_out, d_status);
+  if (n_launches) *n_launches += 2;
+  return cudaGetLastError();
+}
+
+}  // namespace randt

@@ -81,6 +81,11 @@ void Map::mergeMapCell(const Map& moving) {
   ctx_->check(randt_map_merge(ctx_->get(), map_, moving.map_));
   host_valid_ = false;
 }
+std::vector<double> Map::calculateCSDivergence(const Map& m_map) const {
+  std::vector<double> out(n_maps(), 0.0);
+  ctx_->check(randt_cs_divergence(ctx_->get(), map_, m_map.map_, out.data()));
+  return out;
+}
 uint32_t Map::n_maps() const { uint32_t b = 0; randt_map_info(map_, &b, nullptr, nullptr); return b; }
 size_t Map::get_n_cells() const { uint32_t n = 0; randt_map_info(map_, nullptr, &n, nullptr); return n; }
 void Map::sync_host() const {

@@ -144,3 +144,34 @@ def test_transform_and_merge_match_oracle(oracle, gpu_ctx):
             assert np.array_equal(d["slot"][b], s)
             assert np.array_equal(d["cells"][a:z].view(np.uint32), c.view(np.uint32)), "mergeMapCell differs at step %d" % step
     assert len(subs[0]["cells"]) > 60
+
+
+def test_cs_divergence_matches_oracle(oracle, gpu_ctx):
+    """Map::calculateCSDivergence (ndt_map.cpp:42-99) for a batch of (submap, transformed scan) pairs; fp64 sums of float32 terms:
+    asserted 1e-9 absolute on the divergence (a log of sums ~1e2)"""
+    p = P.OXFORD
+    gp = capi.grid_params(p)
+    B = 3
+    fixed = [H.build_submap(oracle, p, 50 + b, n_scans=3) for b in range(B)]
+    moving, trans = [], []
+    for b in range(B):
+        pts = H.make_scan(p, 50 + b, (0.5, -0.3, 0.02), 800 + b)
+        mv = oracle.voxelize(pts, *H.vox_args(p))
+        t = np.array([math.cos(0.02 + 0.01 * b), math.sin(0.02 + 0.01 * b), 0.5, -0.3 + 0.1 * b], np.float32)
+        moving.append(oracle.transform_cells(mv["cells"], *t)); trans.append(t)
+    f_off = np.concatenate([[0], np.cumsum([len(f["cells"]) for f in fixed])]).astype(np.uint32)
+    m_off = np.concatenate([[0], np.cumsum([len(m) for m in moving])]).astype(np.uint32)
+    fm = gpu_ctx.map_upload(np.concatenate([f["cells"] for f in fixed]), f_off, gp)
+    mm = gpu_ctx.map_upload(np.concatenate(moving), m_off, gp)
+    cs = fm.cs_divergence(mm)
+    cs2 = fm.cs_divergence(mm)
+    assert np.array_equal(cs, cs2), "deterministic reduction"
+    for b in range(B):
+        want, terms = oracle.cs_divergence(fixed[b]["cells"], moving[b])
+        assert np.isfinite(want) and np.all(terms > 0)
+        assert abs(cs[b] - want) < 1e-9, (b, cs[b], want)
+    # a far-away scan overlaps less: larger divergence
+    far = oracle.transform_cells(moving[0], 1.0, 0.0, 30.0, 0.0)
+    mm2 = gpu_ctx.map_upload(far, [0, len(far)], gp)
+    fm0 = gpu_ctx.map_upload(fixed[0]["cells"], [0, len(fixed[0]["cells"])], gp)
+    assert fm0.cs_divergence(mm2)[0] > cs[0] + 1.0

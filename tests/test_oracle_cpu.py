@@ -264,3 +264,25 @@ def test_loop_constraint_recovers_pose(oracle, on_manifold):
     assert abs(res["pose"][2] - true[0]) < 0.15 and abs(res["pose"][3] - true[1]) < 0.15 and abs(th - true[2]) < 0.01
     if on_manifold:
         assert abs(math.hypot(res["pose"][0], res["pose"][1]) - 1.0) < 1e-12
+
+
+def test_cs_divergence_restatement(oracle):
+    """Map::calculateCSDivergence (ndt_map.cpp:42-99): independent numpy evaluation of the same sums (fp64 algebra) agrees to the
+    float32 rounding of the reference's 3x3 inverses; cells below the determinant gate are skipped as rows but kept as columns"""
+    rng = np.random.default_rng(3)
+    a = H.random_cells(rng, 30, extent=3.0); b = H.random_cells(rng, 25, extent=3.0)
+    a[4, 3:] *= 1e-3                                   # det(S) < 1e-5: this fixed row is skipped entirely
+    got, terms = oracle.cs_divergence(a, b)
+
+    def G(x, y):
+        d = x[:3].astype(np.float64) - y[:3]; S = (x[3:].astype(np.float64) + y[3:]).reshape(3, 3)
+        return 0.5 / math.sqrt(math.pi ** 2 * np.linalg.det(S)) * math.exp(-0.5 * d @ np.linalg.solve(S, d))
+    ok = lambda c: np.linalg.det(c[3:].astype(np.float64).reshape(3, 3)) >= 1e-5
+    I = sum(G(f, q) for f in a if ok(f) for q in b)
+    F = sum(1 / (2 * math.pi * math.sqrt(np.linalg.det(f[3:].astype(np.float64).reshape(3, 3)))) + 2 * sum(G(f, a[j]) for j in range(i))
+            for i, f in enumerate(a) if ok(f))
+    M = sum(1 / (2 * math.pi * math.sqrt(np.linalg.det(f[3:].astype(np.float64).reshape(3, 3)))) + 2 * sum(G(f, b[j]) for j in range(i))
+            for i, f in enumerate(b) if ok(f))
+    assert not ok(a[4])
+    assert np.allclose(terms, [I, F, M], rtol=2e-4)
+    assert abs(got - (-math.log(I) + 0.5 * math.log(F) + 0.5 * math.log(M))) < 5e-4
