@@ -109,6 +109,22 @@ RANDT_API void randt_dev_free(void* p);
 RANDT_API int randt_memcpy_h2d(randt_ctx* ctx, void* dst, const void* src, size_t bytes);
 RANDT_API int randt_memcpy_d2h(randt_ctx* ctx, void* dst, const void* src, size_t bytes);
 
+/* ---- K6: raw-scan peak filter ---------------------------------------------------------------------------
+ * Replaces RadarPreprocessor::filterScan (R/src/radar_preprocessing/radar_preprocessor.cpp:45-125): per-azimuth strongest return, the falling
+ * flanks around it, range / intensity gates, sensor -> base transform.  raw4: float32 [n_azimuths * n_bins][4] = (x, y, z, intensity) in
+ * the sensor frame, azimuth-major (the organised cloud cloud_in->height x width carries).  out4: filtered points (x, y, z, intensity) in the
+ * base frame, in the reference's order — exactly randt_voxelize()'s input.  *_on_device != 0: the pointer is a device pointer.
+ * Returns RANDT_E_INVALID if the reference's angle rule (new azimuth when |atan2(y, x) - first angle| > 1e-4) would not cut the scan at the
+ * given rows, RANDT_E_CAPACITY if more than `cap` points survive (n_out then holds the required count). */
+typedef struct randt_filter_params {
+  float min_range, max_range, min_intensity;   /* radar_preprocessor/{min_range, max_range, min_intensity} (float members, radar_preprocessor.h:59-61) */
+  float pad_;
+  double beam_distance_increment_threshold;     /* radar_preprocessor/beam_distance_increment_threshold */
+  float sensor_to_base[12];                     /* row-major 3x4 of initial_transform_radar_baselink (Eigen::Affine3f) */
+} randt_filter_params;
+RANDT_API int randt_filter_scan(randt_ctx* ctx, const float* raw4, uint32_t n_azimuths, uint32_t n_bins, const randt_filter_params* params,
+                                int raw_on_device, float* out4, int out_on_device, uint32_t cap, uint32_t* n_out);
+
 /* ---- K1: voxelisation ---------------------------------------------------------------------------------
  * Replaces Grid::cluster (R/src/radar_preprocessing/grid.cpp:7-14), ClusterGenerator::labelClouds
  * (R/src/radar_preprocessing/radar_preprocessor.cpp:151-169), Map::insertCluster (R/src/ndt_representation/ndt_map.cpp:238-245)

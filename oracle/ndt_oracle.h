@@ -726,4 +726,61 @@ inline double cs_divergence(const Cell12* fixed, size_t nf, const Cell12* moving
   return -std::log(interaction_term) + 0.5 * std::log(fixed_term) + 0.5 * std::log(moving_term);
 }
 
+// ------------------------------------------------------------------------------------------
+// RadarPreprocessor::filterScan   R/src/radar_preprocessing/radar_preprocessor.cpp:45-125   
+// Restated sequentially as written.  The two `while(true)` walks leave closer_idx / further_idx uninitialised when their
+// size_t wrap-around guard fires first (UB in the reference); the oracle defines them as the position reached.
+// tf: row-major 3x4 of initial_transform_radar_baselink (Affine3f); pcl::transformPointCloud's SSE path evaluates each row as
+// (x c0 + y c1) + (z c2 + c3).
+// ------------------------------------------------------------------------------------------
+struct FilterParams { float min_distance, max_distance, min_intensity; double beam_thr; float tf[12]; };
+inline void filter_scan(const Pt4* raw, size_t n, const FilterParams& fp, std::vector<Pt4>& out, std::vector<size_t>* peaks = nullptr) {
+  out.clear();
+  float current_angle = 1000;
+  float max_intensity = 0;
+  size_t current_max_idx = 0;
+  std::vector<size_t> max_idzs;
+  for (size_t i = 0; i < n; ++i) {
+    const float dist = std::hypot(raw[i].x, raw[i].y);
+    const float angle = std::atan2(raw[i].y, raw[i].x);
+    const float intensity = raw[i].i;
+    if (std::abs(angle - current_angle) > 0.0001) {
+      if (current_angle < 3 * M_PI) {
+        if (max_idzs.empty() || max_idzs.back() != current_max_idx) max_idzs.push_back(current_max_idx);
+        max_intensity = 0;
+      }
+      current_angle = angle;
+    }
+    if (dist > fp.min_distance && dist < fp.max_distance && intensity > max_intensity) { max_intensity = intensity; current_max_idx = i; }
+  }
+  if (peaks) *peaks = max_idzs;
+  auto hyp = [&](size_t k) { return std::hypot(raw[k].x, raw[k].y); };
+  for (size_t m = 0; m < max_idzs.size(); ++m) {
+    const size_t s = max_idzs[m];
+    size_t closer = s, further = s, k = 0;
+    while (true) {
+      if (s - k - 1 > n - 1) { closer = s - k; break; }                       // size_t wrap: reached index 0
+      if (((hyp(s - k) - hyp(s - k - 1)) > fp.beam_thr) || (raw[s - k].i <= raw[s - k - 1].i) || (hyp(s - k) < fp.min_distance)) { closer = s - k; break; }
+      ++k;
+    }
+    k = 0;
+    while (true) {
+      if (s + k + 1 > n - 1) { further = s + k; break; }
+      if (((hyp(s + k) - hyp(s + k + 1)) > fp.beam_thr) || (raw[s + k].i <= raw[s + k + 1].i) || (hyp(s + k) < fp.min_distance)) { further = s + k; break; }
+      ++k;
+    }
+    for (size_t j = closer; j <= further; ++j) {
+      const float dist = std::hypot(raw[j].x, raw[j].y);
+      if (dist > fp.min_distance && dist < fp.max_distance && raw[j].i > fp.min_intensity) {
+        Pt4 o;
+        o.x = (raw[j].x * fp.tf[0] + raw[j].y * fp.tf[1]) + (raw[j].z * fp.tf[2] + fp.tf[3]);
+        o.y = (raw[j].x * fp.tf[4] + raw[j].y * fp.tf[5]) + (raw[j].z * fp.tf[6] + fp.tf[7]);
+        o.z = (raw[j].x * fp.tf[8] + raw[j].y * fp.tf[9]) + (raw[j].z * fp.tf[10] + fp.tf[11]);
+        o.i = raw[j].i;
+        out.push_back(o);
+      }
+    }
+  }
+}
+
 }  // namespace orc

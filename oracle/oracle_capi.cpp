@@ -228,4 +228,16 @@ double orc_cs_divergence(const float* f_cells, size_t n_f, const float* m_cells,
   return cs_divergence(reinterpret_cast<const Cell12*>(f_cells), n_f, reinterpret_cast<const Cell12*>(m_cells), n_m, terms3);
 }
 
+int orc_filter_scan(const float* raw4, size_t n, float min_d, float max_d, float min_i, double beam_thr, const float* tf12, float* out4, size_t cap,
+                    size_t* n_peaks) {
+  FilterParams fp; fp.min_distance = min_d; fp.max_distance = max_d; fp.min_intensity = min_i; fp.beam_thr = beam_thr;
+  for (int i = 0; i < 12; ++i) fp.tf[i] = tf12[i];
+  std::vector<Pt4> out; std::vector<size_t> peaks;
+  filter_scan(reinterpret_cast<const Pt4*>(raw4), n, fp, out, &peaks);
+  if (n_peaks) *n_peaks = peaks.size();
+  if (out.size() > cap) return -1;
+  std::memcpy(out4, out.data(), out.size() * sizeof(Pt4));
+  return (int)out.size();
+}
+
 }  // extern "C"

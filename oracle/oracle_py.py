@@ -89,6 +89,7 @@ def _sig(L):
     L.orc_sweep_costs.restype = None; L.orc_sweep_costs.argtypes = [i, pf, pf, pu, pu, sz, i, d, d, d, d, pd, sz, pd]
     L.orc_bnb.restype = i; L.orc_bnb.argtypes = [pf, i, pi, i, i, d, d, pf, i, pd, i, d, d, d, d, d, d, d, i, pd]
     L.orc_cs_divergence.restype = d; L.orc_cs_divergence.argtypes = [pf, sz, pf, sz, pd]
+    L.orc_filter_scan.restype = i; L.orc_filter_scan.argtypes = [pf, sz, f, f, f, d, pf, pf, sz, C.POINTER(sz)]
     L.orc_se2_plus.restype = None; L.orc_se2_plus.argtypes = [pd, pd, pd]
     L.orc_se2_plus_jacobian.restype = None; L.orc_se2_plus_jacobian.argtypes = [pd, pd]
 
@@ -291,3 +292,15 @@ def cs_divergence(f_cells, m_cells):
     terms = np.zeros(3, np.float64)
     v = lib().orc_cs_divergence(_p(fc, C.c_float), len(fc), _p(mc, C.c_float), len(mc), _p(terms, C.c_double))
     return v, terms
+
+
+def filter_scan(raw4, min_range, max_range, min_intensity, beam_thr, tf12=None):
+    """RadarPreprocessor::filterScan restated -> (filtered points [n, 4] in the base frame, number of emitted peaks)"""
+    raw = _f32(raw4).reshape(-1, 4)
+    tf = _f32(np.eye(4)[:3] if tf12 is None else tf12).reshape(12)
+    out = np.zeros((max(16, len(raw)), 4), np.float32)
+    npk = C.c_size_t(0)
+    n = lib().orc_filter_scan(_p(raw, C.c_float), len(raw), float(min_range), float(max_range), float(min_intensity), float(beam_thr),
+                              _p(tf, C.c_float), _p(out, C.c_float), len(out), C.byref(npk))
+    assert n >= 0
+    return out[:n].copy(), int(npk.value)

@@ -25,6 +25,7 @@ UNITS = {
     "k2_associate.cu": ["-fmad=false"],
     "k1_voxelize.cu": ["-fmad=false"],
     "k5_cs_divergence.cu": ["-fmad=false"],
+    "k6_filter_scan.cu": ["-fmad=false"],
     "capi.cu": [],
 }
 

@@ -56,6 +56,18 @@ def solver_options(**kw):
     return o
 
 
+class FilterParams(C.Structure):
+    _fields_ = [("min_range", C.c_float), ("max_range", C.c_float), ("min_intensity", C.c_float), ("pad_", C.c_float),
+                ("beam_distance_increment_threshold", C.c_double), ("sensor_to_base", C.c_float * 12)]
+
+
+def filter_params(p, sensor_to_base=None):
+    """from a params.NdtParams; sensor_to_base: 3x4 row-major Affine3f (identity by default)"""
+    tf = np.eye(4, dtype=np.float32)[:3] if sensor_to_base is None else np.asarray(sensor_to_base, np.float32).reshape(3, 4)
+    return FilterParams(float(p.min_range), float(p.max_range), float(p.min_intensity), 0.0, float(p.beam_distance_increment_threshold),
+                        (C.c_float * 12)(*tf.reshape(12).tolist()))
+
+
 def grid_params(p):
     """from a randt_slam_b200.params.NdtParams"""
     return GridParams(float(p.max_range), int(p.n_clusters), int(p.min_points_per_cell), int(p.size_x), int(p.size_y),
@@ -81,6 +93,7 @@ _SIGS = {
     "randt_dev_free": (None, [_vp]),
     "randt_memcpy_h2d": (_i, [_vp, _vp, _vp, C.c_size_t]),
     "randt_memcpy_d2h": (_i, [_vp, _vp, _vp, C.c_size_t]),
+    "randt_filter_scan": (_i, [_vp, _vp, _u32, _u32, C.POINTER(FilterParams), _i, _vp, _i, _u32, C.POINTER(_u32)]),
     "randt_voxelize": (_i, [_vp, _vp, _vp, _u32, C.POINTER(GridParams), _i, C.POINTER(_vp)]),
     "randt_map_upload": (_i, [_vp, _vp, _vp, _vp, _u32, _vp, C.POINTER(GridParams), C.POINTER(_vp)]),
     "randt_map_info": (_i, [_vp, C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_u32)]),
@@ -187,6 +200,17 @@ class Context:
         n = C.c_uint64(0)
         self._check(lib().randt_ctx_take_bad_pairs(self._h, C.byref(n)))
         return int(n.value)
+
+    # ---- K6 ----
+    def filter_scan(self, raw4, n_azimuths, n_bins, fp, cap=None):
+        """RadarPreprocessor::filterScan -> float32 [n, 4] filtered points in the base frame"""
+        raw4 = _f32(raw4, (-1, 4))
+        assert len(raw4) == n_azimuths * n_bins
+        cap = int(cap if cap is not None else max(16, len(raw4)))
+        out = np.zeros((cap, 4), np.float32)
+        n = C.c_uint32(0)
+        self._check(lib().randt_filter_scan(self._h, _ptr(raw4), int(n_azimuths), int(n_bins), C.byref(fp), 0, _ptr(out), 0, cap, C.byref(n)))
+        return out[: n.value].copy()
 
     # ---- K1 ----
     def voxelize(self, pts, scan_off, gp, pts_on_device=False):

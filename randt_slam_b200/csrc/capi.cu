@@ -349,6 +349,43 @@ int randt_voxelize(randt_ctx* ctx, const float* pts4, const uint32_t* scan_off, 
   return RANDT_OK;
 }
 
+int randt_filter_scan(randt_ctx* ctx, const float* raw4, uint32_t n_az, uint32_t n_bins, const randt_filter_params* fp, int raw_on_device,
+                      float* out4, int out_on_device, uint32_t cap, uint32_t* n_out) {
+  if (!ctx || !fp || !n_out || (!raw4 && n_az && n_bins) || (!out4 && cap)) return fail(ctx, RANDT_E_INVALID, "randt_filter_scan: null argument");
+  if ((unsigned long long)n_az * n_bins > 0x7fffffffull) return fail(ctx, RANDT_E_CAPACITY, "randt_filter_scan: scan too large");
+  CK(cudaSetDevice(ctx->device));
+  *n_out = 0;
+  const size_t n = (size_t)n_az * n_bins;
+  float4 *d_raw = nullptr, *d_out = nullptr; uint32_t *d_peak = nullptr, *d_n = nullptr; float* d_angle = nullptr; int* d_status = nullptr;
+  bool own_raw = false, own_out = false;
+  int nl = 0;
+  auto cleanup = [&]() { if (own_raw) cudaFree(d_raw); if (own_out) cudaFree(d_out); cudaFree(d_peak); cudaFree(d_n); cudaFree(d_angle); cudaFree(d_status); };
+  cudaError_t e = cudaSuccess;
+  if (raw_on_device) d_raw = const_cast<float4*>(reinterpret_cast<const float4*>(raw4));
+  else { own_raw = true; e = dev_alloc(&d_raw, n); if (e == cudaSuccess && n) e = cudaMemcpyAsync(d_raw, raw4, n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream); }
+  if (out_on_device) d_out = reinterpret_cast<float4*>(out4);
+  else if (e == cudaSuccess) { own_out = true; e = dev_alloc(&d_out, cap); }
+  if (e == cudaSuccess) e = dev_alloc(&d_peak, n_az);
+  if (e == cudaSuccess) e = dev_alloc(&d_angle, n_az);
+  if (e == cudaSuccess) e = dev_alloc(&d_n, 1);
+  if (e == cudaSuccess) e = dev_alloc(&d_status, 1);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_status, 0, sizeof(int), ctx->stream);
+  if (e == cudaSuccess) e = launch_filter_scan(d_raw, n_az, n_bins, *fp, d_peak, d_angle, d_out, cap, d_n, d_status, ctx->stream, &nl);
+  int h_status = 0; uint32_t h_n = 0;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&h_status, d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&h_n, d_n, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess && !out_on_device && h_status == 0 && h_n)
+    e = cudaMemcpy(out4, d_out, (size_t)std::min(h_n, cap) * sizeof(float4), cudaMemcpyDeviceToHost);
+  cleanup();
+  if (e != cudaSuccess) return fail(ctx, RANDT_E_CUDA, "randt_filter_scan", e);
+  ctx->launches += nl;
+  *n_out = h_n;
+  if (h_status == 1) return fail(ctx, RANDT_E_INVALID, "randt_filter_scan: the scan is not organised by azimuth (the reference's angle rule cuts it elsewhere)");
+  if (h_status == 2) return fail(ctx, RANDT_E_CAPACITY, "randt_filter_scan: output capacity too small");
+  return RANDT_OK;
+}
+
 int randt_map_upload(randt_ctx* ctx, const float* cells, const uint32_t* npts, const uint32_t* cell_off, uint32_t n_maps, const int32_t* slot,
                      const randt_grid_params* gp, randt_map** out) {
   if (!ctx || !out || !gp || !cell_off) return fail(ctx, RANDT_E_INVALID, "randt_map_upload: null argument");

@@ -88,6 +88,26 @@ def make_scan(scene, pose, params, seed, n_azimuth=400, bin_size=0.0438, half_bi
     return out
 
 
+def make_raw_scan(scene, pose, params, seed, n_azimuth=400, n_bins=3000, bin_size=0.0438, floor=(5.0, 45.0), peak=(90.0, 220.0), width_bins=4.0):
+    """One RAW polar scan as the organised point cloud RadarPreprocessor::filterScan receives: float32 [n_azimuth * n_bins, 4] =
+    (x, y, 0, intensity) in the sensor frame, azimuth-major, every range bin present (noise floor plus a peak around each wall hit)."""
+    rng = np.random.default_rng(seed)
+    _, rr = cast(scene, pose, n_azimuth, params.max_range, rng)
+    az = (np.arange(n_azimuth) + 0.5) * (2 * math.pi / n_azimuth)
+    az = np.where(az > math.pi, az - 2 * math.pi, az)                  # atan2 range; the half-step offset keeps rows away from +-pi
+    r = (np.arange(n_bins) + 1.0) * bin_size                            # bin 0 would sit on the sensor (atan2(0, 0) = 0 for every azimuth)
+    inten = rng.uniform(floor[0], floor[1], (n_azimuth, n_bins))
+    hit = np.isfinite(rr)
+    amp = rng.uniform(peak[0], peak[1], n_azimuth)
+    bump = amp[:, None] * np.exp(-0.5 * ((r[None, :] - np.where(hit, rr, -1e9)[:, None]) / (width_bins * bin_size)) ** 2)
+    inten = np.clip(inten + bump, 0.0, 255.0)
+    out = np.zeros((n_azimuth, n_bins, 4), np.float32)
+    out[:, :, 0] = r[None, :] * np.cos(az)[:, None]
+    out[:, :, 1] = r[None, :] * np.sin(az)[:, None]
+    out[:, :, 3] = inten
+    return out.reshape(-1, 4)
+
+
 def pose_to_se2(x, y, theta):
     """Sophus SE2d storage order [cos, sin, tx, ty]"""
     return np.array([math.cos(theta), math.sin(theta), x, y], np.float64)

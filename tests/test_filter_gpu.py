@@ -1,0 +1,72 @@
+"""K6 (raw-scan peak filter, RadarPreprocessor::filterScan, R/src/radar_preprocessing/radar_preprocessor.cpp:45-125) vs the oracle's
+sequential restatement: the kept points, their order and their transformed coordinates must be bit-identical (index work + float32
+arithmetic in the same order)."""
+import math
+
+import numpy as np
+import pytest
+
+from randt_slam_b200 import capi, params as P, synth
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+TF = np.array([[math.cos(0.3), -math.sin(0.3), 0.0, 1.25], [math.sin(0.3), math.cos(0.3), 0.0, -0.4], [0.0, 0.0, 1.0, 0.0]], np.float32)
+
+
+def oracle_filter(oracle, raw, p, tf=None):
+    return oracle.filter_scan(raw, p.min_range, p.max_range, p.min_intensity, p.beam_distance_increment_threshold, tf)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_filter_scan_matches_oracle(oracle, gpu_ctx, seed):
+    p = P.OXFORD
+    n_az, n_bins = 400, 1200
+    raw = synth.make_raw_scan(synth.scene_for(p, 10 + seed), (0.2 * seed, -0.1, 0.01 * seed), p, seed, n_azimuth=n_az, n_bins=n_bins, bin_size=0.09)
+    want, n_peaks = oracle_filter(oracle, raw, p, TF)
+    got = gpu_ctx.filter_scan(raw, n_az, n_bins, capi.filter_params(p, TF))
+    assert n_peaks > 200 and len(want) > 1000
+    assert got.shape == want.shape
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_filter_scan_edge_cases(oracle, gpu_ctx):
+    p = P.OXFORD
+    n_az, n_bins = 64, 300
+    raw = synth.make_raw_scan(synth.scene_for(p, 5), (0, 0, 0), p, 5, n_azimuth=n_az, n_bins=n_bins, bin_size=0.3).reshape(n_az, n_bins, 4)
+    raw[0, :, 3] = 0.0            # first azimuth without any valid return: the reference emits point 0
+    raw[7, :, 3] = 0.0            # an empty azimuth in the middle contributes nothing
+    raw[9, :, 3] = 80.0           # plateau: first strongest return wins, the walk stops immediately (intensity not falling)
+    raw[-1, :, 3] = 250.0         # the last azimuth is never emitted
+    raw = raw.reshape(-1, 4)
+    want, _ = oracle_filter(oracle, raw, p)
+    got = gpu_ctx.filter_scan(raw, n_az, n_bins, capi.filter_params(p))
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert not np.any(np.isclose(got[:, 3], 250.0))
+    # capacity
+    with pytest.raises(capi.RandtError) as e:
+        gpu_ctx.filter_scan(raw, n_az, n_bins, capi.filter_params(p), cap=4)
+    assert e.value.code == capi.E_CAPACITY
+
+
+def test_filter_scan_rejects_unorganised_input(gpu_ctx):
+    p = P.OXFORD
+    n_az, n_bins = 32, 200
+    raw = synth.make_raw_scan(synth.scene_for(p, 6), (0, 0, 0), p, 6, n_azimuth=n_az, n_bins=n_bins, bin_size=0.4).reshape(n_az, n_bins, 4)
+    raw[3, 100:] = raw[4, 100:]          # half of a row belongs to the next azimuth
+    with pytest.raises(capi.RandtError) as e:
+        gpu_ctx.filter_scan(raw.reshape(-1, 4), n_az, n_bins, capi.filter_params(p))
+    assert e.value.code == capi.E_INVALID
+
+
+def test_filter_then_voxelize_equals_oracle_chain(oracle, gpu_ctx):
+    """raw scan -> filterScan -> Grid::cluster ... Cell::updateCell, all on the device, against the oracle's chain"""
+    p = P.OXFORD
+    n_az, n_bins = 400, 1200
+    raw = synth.make_raw_scan(synth.scene_for(p, 21), (0.3, 0.2, 0.02), p, 21, n_azimuth=n_az, n_bins=n_bins, bin_size=0.09)
+    pts = gpu_ctx.filter_scan(raw, n_az, n_bins, capi.filter_params(p))
+    m = gpu_ctx.voxelize(pts, [0, len(pts)], capi.grid_params(p)).download()
+    want_pts, _ = oracle_filter(oracle, raw, p)
+    v = oracle.voxelize(want_pts, *H.vox_args(p))
+    assert len(v["cells"]) > 30
+    assert np.array_equal(m["cells"].view(np.uint32), v["cells"].view(np.uint32))
