@@ -212,6 +212,12 @@ class Context:
         self._check(lib().randt_filter_scan(self._h, _ptr(raw4), int(n_azimuths), int(n_bins), C.byref(fp), 0, _ptr(out), 0, cap, C.byref(n)))
         return out[: n.value].copy()
 
+    def filter_scan_dev(self, d_raw, n_azimuths, n_bins, fp, d_out, cap):
+        """device pointers in and out (ints); returns the number of kept points"""
+        n = C.c_uint32(0)
+        self._check(lib().randt_filter_scan(self._h, _ptr(d_raw), int(n_azimuths), int(n_bins), C.byref(fp), 1, _ptr(d_out), 1, int(cap), C.byref(n)))
+        return int(n.value)
+
     # ---- K1 ----
     def voxelize(self, pts, scan_off, gp, pts_on_device=False):
         """pts: float32 [N,4] host array (or int device pointer); scan_off: uint32 [B+1] -> Map"""
