@@ -45,8 +45,9 @@ struct randt_problem {
   DuoRec* duo_recs = nullptr; uint32_t* duo_p0 = nullptr;
   std::vector<uint32_t> h_duo_off;   // [S+1] duo offsets per segment
   uint32_t n_tiles = 0;
-  ChunkDesc* chunks = nullptr; uint32_t n_chunks = 0;
-  uint32_t* warp_off = nullptr; uint32_t n_warps = 0;
+  ChunkDesc* chunks = nullptr; uint32_t n_chunks = 0;             // plan B: one tile per chunk (solver, EMIT)
+  ChunkDesc* chunks_full = nullptr; uint32_t n_chunks_full = 0;   // plan A: split chunks allowed (full FUSED evaluation)
+  uint32_t *warp_off = nullptr, *warp_off_full = nullptr; uint32_t n_warps = 0;
   uint32_t* seg_first_tile = nullptr;
   uint32_t* seg_off = nullptr;
   double* partials = nullptr;
@@ -96,7 +97,7 @@ void free_map(randt_map* m) {
 }
 void free_problem(randt_problem* p) {
   if (!p) return;
-  cudaFree(p->cells_m); cudaFree(p->cells_f); cudaFree(p->pairs); cudaFree(p->duos); cudaFree(p->duo_recs); cudaFree(p->duo_p0); cudaFree(p->chunks); cudaFree(p->warp_off); cudaFree(p->seg_first_tile); cudaFree(p->seg_off);
+  cudaFree(p->cells_m); cudaFree(p->cells_f); cudaFree(p->pairs); cudaFree(p->duos); cudaFree(p->duo_recs); cudaFree(p->duo_p0); cudaFree(p->chunks); cudaFree(p->warp_off); cudaFree(p->chunks_full); cudaFree(p->warp_off_full); cudaFree(p->seg_first_tile); cudaFree(p->seg_off);
   cudaFree(p->partials); cudaFree(p->seg_counters); cudaFree(p->d_poses); cudaFree(p->d_out); cudaFree(p->d_mu); cudaFree(p->d_r);
   cudaFree(p->d_J); cudaFree(p->d_sweep);
   cudaFree(p->lm_state); cudaFree(p->lm_eval_pose); cudaFree(p->lm_mu); cudaFree(p->lm_rec); cudaFree(p->lm_poses); cudaFree(p->lm_result);
@@ -108,15 +109,8 @@ void free_problem(randt_problem* p) {
   delete p;
 }
 
-// tile list + per-segment bookkeeping from a host seg_off; uploads everything a DeviceProblem needs
+// tile list, balanced schedule, record table and per-segment bookkeeping from a host seg_off; uploads everything a DeviceProblem needs
 int finish_problem(randt_ctx* ctx, randt_problem* p) {
-  // record-major duo table (what K3 streams)
-  {
-    int nl = 0;
-    CK(dev_alloc(&p->duo_recs, p->n_duos)); CK(dev_alloc(&p->duo_p0, p->n_duos));
-    CK(launch_build_duo_records(p->cells_m, p->cells_f, p->duos, p->n_duos, p->duo_recs, p->duo_p0, ctx->stream, &nl));
-    ctx->launches += nl;
-  }
   std::vector<Tile> tiles;
   std::vector<uint32_t> first(p->S + 1, 0);
   // one warp owns a tile.  Big batches: tiles of up to kTileDuos duos (a whole ~200-pair registration per warp, no partials);
@@ -133,52 +127,102 @@ int finish_problem(randt_ctx* ctx, randt_problem* p) {
   }
   first[p->S] = (uint32_t)tiles.size();
   // Balanced static schedule: longest-processing-time assignment of tiles to the resident warps of the persistent grid (a tile
-  // costs its chunks of 32 duos plus a fixed reduce/emit overhead), then the tile list is stored warp after warp.  Registration
-  // problems differ in size, and one warp walks only ~7 of them per launch at the bench size, so round-robin striding leaves
-  // warps (and whole SMs) idle at the tail.
+  // costs its duos plus a fixed prologue/reduce/emit overhead).  Registration problems differ in size, and one warp walks only ~7
+  // of them per launch at the bench size, so round-robin striding leaves warps (and whole SMs) idle at the tail.
+  const uint32_t n_warps = std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)kK3MaxWarps, (uint32_t)tiles.size()));
+  std::vector<std::vector<uint32_t>> mine(n_warps);
   {
-    const uint32_t n_warps = std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)kK3MaxWarps, (uint32_t)tiles.size()));
     std::vector<uint32_t> order(tiles.size());
     for (uint32_t t = 0; t < tiles.size(); ++t) order[t] = t;
-    auto cost = [&](uint32_t t) { return ((tiles[t].end - tiles[t].begin + 31u) / 32u) * 32u + 6u; };
+    auto cost = [&](uint32_t t) { return (tiles[t].end - tiles[t].begin) + 24u; };
     std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return cost(a) > cost(b); });
     typedef std::pair<uint64_t, uint32_t> Load;   // (assigned cost, warp)
     std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
     for (uint32_t w = 0; w < n_warps; ++w) heap.push(Load(0, w));
-    std::vector<std::vector<uint32_t>> mine(n_warps);
     for (uint32_t t : order) {
       Load l = heap.top(); heap.pop();
       mine[l.second].push_back(t);
       l.first += cost(t);
       heap.push(l);
     }
-    // chunk descriptors, warp after warp
-    std::vector<ChunkDesc> chunks; chunks.reserve(p->n_duos / 32 + tiles.size() + 1);
-    std::vector<uint32_t> woff(n_warps + 1, 0);
-    for (uint32_t w = 0; w < n_warps; ++w) {
-      std::sort(mine[w].begin(), mine[w].end());
-      for (uint32_t t : mine[w]) {
-        const Tile& tl = tiles[t];
-        const bool solo = first[tl.seg + 1] - first[tl.seg] == 1u;
-        for (uint32_t b = tl.begin; b < tl.end; b += 32u) {
-          ChunkDesc c;
-          c.duo_begin = b; c.seg = tl.seg; c.part = first[tl.seg] + tl.part;
-          c.meta = std::min(32u, tl.end - b) | (b == tl.begin ? kChunkFirst : 0u) | (b + 32u >= tl.end ? kChunkLast : 0u) | (solo ? kChunkSolo : 0u);
-          chunks.push_back(c);
-        }
-      }
-      woff[w + 1] = (uint32_t)chunks.size();
-    }
-    p->n_warps = n_warps;
-    p->n_chunks = (uint32_t)chunks.size();
-    CK(dev_alloc(&p->chunks, chunks.size()));
-    CK(dev_alloc(&p->warp_off, woff.size()));
-    if (!chunks.empty()) CK(cudaMemcpyAsync(p->chunks, chunks.data(), chunks.size() * sizeof(ChunkDesc), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(p->warp_off, woff.data(), woff.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
   }
-  for (uint32_t s = 0; s < p->S; ++s) if (p->h_seg_off[s + 1] == p->h_seg_off[s]) p->has_empty_segment = true;
+  // Records are laid out in schedule order (warp after warp, tile after tile), so that a warp streams one contiguous range and the
+  // tail of one tile and the head of the next can share a chunk.  Two chunk lists over the same records:
+  //   plan A (full evaluation): consecutive solo tiles of a warp are packed — the last, partly filled chunk of a tile takes the first
+  //           duos of the next tile (kChunkSplit), which keeps the lanes busy when problems are only ~3 chunks long;
+  //   plan B (solver with active flags, EMIT): every chunk belongs to one tile.
+  std::vector<uint32_t> tile_rec_begin, tile_duo_begin;
+  tile_rec_begin.reserve(tiles.size() + 1); tile_duo_begin.reserve(tiles.size());
+  std::vector<ChunkDesc> planA, planB;
+  planA.reserve(p->n_duos / 32 + tiles.size() + 1); planB.reserve(p->n_duos / 32 + tiles.size() + 1);
+  std::vector<uint32_t> woffA(n_warps + 1, 0), woffB(n_warps + 1, 0);
+  uint32_t rec = 0;
+  for (uint32_t w = 0; w < n_warps; ++w) {
+    std::sort(mine[w].begin(), mine[w].end());
+    bool open = false;      // the last chunk of plan A ends a solo tile, is not split yet and has free lanes
+    for (uint32_t t : mine[w]) {
+      const Tile& tl = tiles[t];
+      const bool solo = first[tl.seg + 1] - first[tl.seg] == 1u;
+      const uint32_t len = tl.end - tl.begin, rb = rec;
+      tile_rec_begin.push_back(rb); tile_duo_begin.push_back(tl.begin);
+      rec += len;
+      const uint32_t part = first[tl.seg] + tl.part;
+      for (uint32_t o = 0; o < len; o += 32u) {
+        ChunkDesc c;
+        c.duo_begin = rb + o; c.seg = tl.seg; c.part = part;
+        c.meta = std::min(32u, len - o) | (o == 0 ? kChunkFirst : 0u) | (o + 32u >= len ? kChunkLast : 0u) | (solo ? kChunkSolo : 0u);
+        planB.push_back(c);
+      }
+      uint32_t o = 0;
+      if (solo && open) {   // this tile starts in the free lanes of the previous tile's last chunk
+        ChunkDesc& pc = planA.back();
+        const uint32_t n_old = pc.meta & kChunkCountMask, take = std::min(32u - n_old, len);
+        pc.meta = (pc.meta & ~kChunkCountMask) | (n_old + take) | kChunkSplit | (n_old << kChunkSplitShift) | (take == len ? kChunkNewLast : 0u);
+        pc.part = tl.seg;
+        o = take;
+      }
+      open = false;
+      for (; o < len; o += 32u) {
+        ChunkDesc c;
+        c.duo_begin = rb + o; c.seg = tl.seg; c.part = part;
+        const uint32_t n = std::min(32u, len - o);
+        c.meta = n | (o == 0 ? kChunkFirst : 0u) | (o + 32u >= len ? kChunkLast : 0u) | (solo ? kChunkSolo : 0u);
+        planA.push_back(c);
+        open = solo && (o + 32u >= len) && n < 32u;
+      }
+    }
+    woffA[w + 1] = (uint32_t)planA.size(); woffB[w + 1] = (uint32_t)planB.size();
+  }
+  tile_rec_begin.push_back(rec);
+  p->n_warps = n_warps;
+  p->n_chunks = (uint32_t)planB.size(); p->n_chunks_full = (uint32_t)planA.size();
   p->n_tiles = (uint32_t)tiles.size();
+  for (uint32_t s = 0; s < p->S; ++s) if (p->h_seg_off[s + 1] == p->h_seg_off[s]) p->has_empty_segment = true;
+  CK(dev_alloc(&p->chunks, planB.size())); CK(dev_alloc(&p->chunks_full, planA.size()));
+  CK(dev_alloc(&p->warp_off, woffB.size())); CK(dev_alloc(&p->warp_off_full, woffA.size()));
+  if (!planB.empty()) CK(cudaMemcpyAsync(p->chunks, planB.data(), planB.size() * sizeof(ChunkDesc), cudaMemcpyHostToDevice, ctx->stream));
+  if (!planA.empty()) CK(cudaMemcpyAsync(p->chunks_full, planA.data(), planA.size() * sizeof(ChunkDesc), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(p->warp_off, woffB.data(), woffB.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(p->warp_off_full, woffA.data(), woffA.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  // record-major duo table in schedule order (what K3 streams)
+  {
+    int nl = 0;
+    uint32_t *d_trb = nullptr, *d_tdb = nullptr; Duo* d_stream = nullptr;
+    cudaError_t e = dev_alloc(&d_trb, tile_rec_begin.size());
+    if (e == cudaSuccess) e = dev_alloc(&d_tdb, tile_duo_begin.size());
+    if (e == cudaSuccess) e = dev_alloc(&d_stream, p->n_duos);
+    if (e == cudaSuccess) e = dev_alloc(&p->duo_recs, p->n_duos);
+    if (e == cudaSuccess) e = dev_alloc(&p->duo_p0, p->n_duos);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_trb, tile_rec_begin.data(), tile_rec_begin.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && !tile_duo_begin.empty())
+      e = cudaMemcpyAsync(d_tdb, tile_duo_begin.data(), tile_duo_begin.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = launch_permute_duos(p->duos, d_trb, d_tdb, (uint32_t)tiles.size(), p->n_duos, d_stream, ctx->stream, &nl);
+    if (e == cudaSuccess) e = launch_build_duo_records(p->cells_m, p->cells_f, d_stream, p->n_duos, p->duo_recs, p->duo_p0, ctx->stream, &nl);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_trb); cudaFree(d_tdb); cudaFree(d_stream);
+    if (e != cudaSuccess) return fail(ctx, RANDT_E_CUDA, "finish_problem: record table", e);
+    ctx->launches += nl;
+  }
   CK(dev_alloc(&p->seg_first_tile, first.size()));
   CK(dev_alloc(&p->seg_off, p->h_seg_off.size()));
   CK(dev_alloc(&p->partials, (size_t)tiles.size() * kMaxAcc));
@@ -699,7 +743,9 @@ int randt_eval_fused_dev(randt_ctx* ctx, const randt_problem* p, int variant, co
   // segments without pairs produce no tile: clear their records up front
   if (p->has_empty_segment) CK(cudaMemsetAsync(d_out, 0, (size_t)p->S * RANDT_FUSED_STRIDE * sizeof(double), ctx->stream));
   int nl = 0;
-  CK(launch_eval_fused(view(p), variant, d_poses, lp, d_mu_per_seg, want_jac != 0, d_out, ctx->d_bad, ctx->stream, &nl));
+  DeviceProblem v = view(p);
+  v.chunks = p->chunks_full; v.n_chunks = p->n_chunks_full; v.warp_off = p->warp_off_full;   // every segment is evaluated: packed schedule
+  CK(launch_eval_fused(v, variant, d_poses, lp, d_mu_per_seg, want_jac != 0, d_out, ctx->d_bad, ctx->stream, &nl));
   ctx->launches += nl;
   return RANDT_OK;
 }

@@ -38,6 +38,12 @@ struct Tile { uint32_t seg, begin, end, part; };
 // part = index of the tile's partial record (seg_first_tile[seg] + tile.part), used when a segment spans several tiles.
 struct __align__(16) ChunkDesc { uint32_t duo_begin, meta, seg, part; };
 constexpr uint32_t kChunkCountMask = 0x3fu, kChunkFirst = 0x100u, kChunkLast = 0x200u, kChunkSolo = 0x400u;
+// Split chunks (full-evaluation schedule only): lanes [0, sp) finish one solo tile (segment `seg`, which therefore has kChunkLast) and
+// lanes [sp, count) start the next solo tile of the same warp, whose segment is carried in `part`; sp sits in bits 16..21.
+// kChunkNewLast: that second tile also ends inside this chunk.  The record table is laid out in schedule order so that the two
+// tiles' records are adjacent.
+constexpr uint32_t kChunkSplit = 0x800u, kChunkNewLast = 0x1000u;
+constexpr int kChunkSplitShift = 16;
 
 struct DeviceProblem {
   const float4* cells_m;   // 3 x float4 per cell
@@ -74,6 +80,8 @@ cudaError_t launch_eval_fused(const DeviceProblem& p, int variant, const double*
                               bool want_jac, double* d_out, unsigned long long* d_bad, cudaStream_t s, int* n_launches);
 cudaError_t launch_eval_emit(const DeviceProblem& p, int variant, const double* d_poses, double* d_r, double* d_J,
                              unsigned long long* d_bad, cudaStream_t s, int* n_launches);
+cudaError_t launch_permute_duos(const Duo* in, const uint32_t* tile_rec_begin, const uint32_t* tile_duo_begin, uint32_t n_tiles, uint32_t n_duos,
+                                Duo* out, cudaStream_t s, int* n_launches);
 cudaError_t launch_build_duo_records(const float4* cells_m, const float4* cells_f, const Duo* duos, uint32_t n_duos, DuoRec* recs,
                                      uint32_t* duo_p0, cudaStream_t s, int* n_launches);
 cudaError_t launch_sweep_costs(const DeviceProblem& p, uint32_t pair_begin, uint32_t pair_end, int variant, const double* d_poses,

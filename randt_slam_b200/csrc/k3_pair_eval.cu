@@ -384,8 +384,8 @@ constexpr int kMinCtas = RANDT_K3_MIN_CTAS;   // CTAs per SM the register alloca
 
 struct __align__(128) StageBuf {
   float4 rec[32][9];       // the chunk's duo records (144 B each, see DuoRec in common.cuh), landed by ONE bulk copy
-  double pose[4];          // pose and GNC mu of the chunk's segment (valid for the first chunk of a tile)
-  double mu;
+  double pose[2][4];       // [0]: pose of the tile at lane 0 (valid for the first chunk of a tile); [1]: pose of the tile that starts
+  double mu[2];            //      inside a split chunk; mu likewise
   unsigned long long bar;  // mbarrier the bulk copy completes on
 };
 
@@ -474,15 +474,110 @@ __device__ __forceinline__ void stage_issue(const DeviceProblem& P, const WarpQu
       const uint32_t bytes = n_here * (uint32_t)sizeof(DuoRec);
       mbar_expect_tx(&sb->bar, bytes);
       bulk_g2s(&sb->rec[0][0], P.duo_recs + d.duo_begin, bytes, &sb->bar);
-      if (d.meta & kChunkFirst) {
-        const double* ps = poses + (size_t)d.seg * NP;
-        if (NP == 4) { cp_async16(&sb->pose[0], ps); cp_async16(&sb->pose[2], ps + 2); }
-        else { cp_async8(&sb->pose[0], ps); cp_async8(&sb->pose[1], ps + 1); cp_async8(&sb->pose[2], ps + 2); }
-        if (mu_per_seg) cp_async8(&sb->mu, mu_per_seg + d.seg);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (d.meta & (h == 0 ? kChunkFirst : kChunkSplit)) {
+          const uint32_t sg = h == 0 ? d.seg : d.part;          // a split chunk carries its second segment in `part`
+          const double* ps = poses + (size_t)sg * NP;
+          if (NP == 4) { cp_async16(&sb->pose[h][0], ps); cp_async16(&sb->pose[h][2], ps + 2); }
+          else { cp_async8(&sb->pose[h][0], ps); cp_async8(&sb->pose[h][1], ps + 1); cp_async8(&sb->pose[h][2], ps + 2); }
+          if (mu_per_seg) cp_async8(&sb->mu[h], mu_per_seg + sg);
+        }
       }
     }
   }
   cp_async_commit();
+}
+
+// Tile finished: reduce the per-lane sums across the warp (through `scratch`, the just-consumed stage buffer) and emit the
+// segment's record — directly when the tile is its segment's only one, else as a partial that the last tile to finish folds.
+template <int VARIANT, bool WANT_JAC, int NS>
+__device__ __forceinline__ void finish_tile(const DeviceProblem& P, const double* vals, double max_dd, uint32_t n_bad, uint32_t seg, bool solo,
+                                            uint32_t part_slot, const PoseConst& kc, double* scratch, double* __restrict__ out,
+                                            unsigned long long* __restrict__ bad_counter, int lane) {
+  const double mine = smem_reduce<NS>(vals, scratch, lane);   // slot s total: lanes 2s, 2s+1
+  const double mx = warp_max_nonneg(max_dd);
+  const uint32_t bad = __reduce_add_sync(kFull, n_bad);
+  const uint32_t n_pairs_seg = P.seg_off[seg + 1] - P.seg_off[seg];
+  if (solo) {
+    write_segment_out<VARIANT, WANT_JAC>(mine, mx, kc, n_pairs_seg, out + (size_t)seg * RANDT_FUSED_STRIDE, lane, [](int sl) { return 2 * sl; });
+    if (lane == 0 && bad) atomicAdd(bad_counter, (unsigned long long)bad);
+  } else {
+    // partial record of this tile: [NS sums][max dd][bad], one entry per lane
+    const uint32_t first = P.seg_first_tile[seg], seg_tiles = P.seg_first_tile[seg + 1] - first;
+    double* part = P.partials + (size_t)part_slot * kMaxAcc;
+    double pv = __shfl_sync(kFull, mine, 2 * (lane < NS ? lane : 0));
+    if (lane == NS) pv = mx;
+    if (lane == NS + 1) pv = (double)bad;
+    if (lane < NS + 2) part[lane] = pv;
+    __threadfence();
+    __syncwarp();
+    uint32_t ticket = 0;
+    if (lane == 0) ticket = atomicAdd(&P.seg_counters[seg], 1u);
+    ticket = __shfl_sync(kFull, ticket, 0);
+    if (ticket == seg_tiles - 1) {   // last tile of this segment to finish: fold the partials in tile order
+      __threadfence();
+      double v = 0.0;
+      if (lane < NS + 2) {
+        for (uint32_t u = 0; u < seg_tiles; ++u) {
+          const double x = __ldcg(P.partials + (size_t)(first + u) * kMaxAcc + lane);
+          v = (lane == NS) ? fmax(v, x) : v + x;
+        }
+      }
+      const double mx_all = __shfl_sync(kFull, v, NS);
+      const double bad_all = __shfl_sync(kFull, v, NS + 1);
+      write_segment_out<VARIANT, WANT_JAC>(v, mx_all, kc, n_pairs_seg, out + (size_t)seg * RANDT_FUSED_STRIDE, lane, [](int sl) { return sl; });
+      if (lane == 0) {
+        if (bad_all != 0.0) atomicAdd(bad_counter, (unsigned long long)bad_all);
+        P.seg_counters[seg] = 0u;   // re-arm for the next launch
+      }
+    }
+  }
+}
+
+// One lane's duo (two pairs sharing their moving cell) added into `acc` (H upper triangle, g, cost, sum dd), max dd, bad count.
+template <int VARIANT, int LOSS, bool WANT_JAC, int NS>
+__device__ __forceinline__ void accumulate_duo(const PoseConst& kc, const LossConst& lc, const StageBuf* sb, int lane, double* acc, double& max_dd,
+                                               uint32_t& n_bad) {
+  constexpr int NB = VarTraits<VARIANT>::NB;
+  constexpr int NH = NB * (NB + 1) / 2;
+  constexpr int NJ = WANT_JAC ? NH + NB : 0;
+  RawCell m, f[2];
+  m.a = sb->rec[lane][0]; m.b = sb->rec[lane][1]; m.c = sb->rec[lane][2];
+  f[0].a = sb->rec[lane][3]; f[0].b = sb->rec[lane][4]; f[0].c = sb->rec[lane][5];
+  f[1].a = sb->rec[lane][6]; f[1].b = sb->rec[lane][7]; f[1].c = sb->rec[lane][8];
+  const bool two = __float_as_uint(f[1].a.x) != kNoSecondPair;
+  Moving mv;
+  moving_part<VARIANT>(kc, m, mv);
+  double dd[2], N[2][4], wgt[2], hrho[2], wd[2];
+  bool ok[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) dd[j] = fixed_part<VARIANT, WANT_JAC>(kc, mv, f[j], N[j]);
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    ok[j] = dd_valid(dd[j]);
+    loss_eval<LOSS>(dd[j], lc, wgt[j], hrho[j], wd[j]);
+  }
+  const bool use1 = two && ok[1];
+  n_bad += (ok[0] ? 0u : 1u) + ((two && !ok[1]) ? 1u : 0u);
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    if (j == 0 ? ok[0] : use1) {
+      if (WANT_JAC) {
+        int q = 0;
+#pragma unroll
+        for (int a = 0; a < NB; ++a) {
+          const double wa = wd[j] * N[j][a];
+#pragma unroll
+          for (int b2 = a; b2 < NB; ++b2) { acc[q] = fma(wa, N[j][b2], acc[q]); ++q; }
+          acc[NH + a] = fma(wgt[j], N[j][a], acc[NH + a]);
+        }
+      }
+      acc[NJ] += hrho[j];
+      acc[NJ + 1] += dd[j];
+      max_dd = fmax(max_dd, dd[j]);
+    }
+  }
 }
 
 template <int VARIANT, int LOSS, bool WANT_JAC>
@@ -523,11 +618,12 @@ __global__ void __launch_bounds__(kK3Threads, kMinCtas) k3_fused_kernel(DevicePr
   for (int s = 0; s < kStages - 1; ++s) stage_issue<NP>(P, wq, s, lane, &stage[s], poses, mu_per_seg);
   uint32_t phase_bits = 0u;     // bit s: parity the next completion of stage s's barrier will have
 
-  // Pose and loss constants of the current tile live in shared memory (one copy per warp, broadcast LDS where they are used):
+  // Pose and loss constants of the tile(s) in flight live in shared memory (two slots per warp: a split chunk carries the tail of
+  // one tile and the head of the next; slot `ts` belongs to the tile at lane 0), read by (mostly broadcast) LDS where they are used:
   // ~26 fewer live registers per thread.
-  __shared__ PoseConst kc_all[kWarpsPerCta];
-  __shared__ LossConst lc_all[kWarpsPerCta];
-  PoseConst& kc = kc_all[warp]; LossConst& lc = lc_all[warp];
+  __shared__ PoseConst kc_all[kWarpsPerCta][2];
+  __shared__ LossConst lc_all[kWarpsPerCta][2];
+  int ts = 0;
   double acc[NS]; double max_dd = 0.0; uint32_t n_bad = 0;
 #pragma unroll
   for (int e = 0; e < NS; ++e) acc[e] = 0.0;
@@ -547,99 +643,52 @@ __global__ void __launch_bounds__(kK3Threads, kMinCtas) k3_fused_kernel(DevicePr
     __syncwarp();
     StageBuf* sb = &stage[slot];
     if (live) { mbar_wait(&sb->bar, (phase_bits >> slot) & 1u); phase_bits ^= 1u << slot; }
-    if ((cm.meta & kChunkFirst) && live) {
-      if (lane == 0) {
+    const bool split = (cm.meta & kChunkSplit) != 0u;         // lanes >= sp belong to the next tile (segment cm.part)
+    const uint32_t sp = split ? ((cm.meta >> kChunkSplitShift) & 63u) : n_here;
+    if (live && (cm.meta & (kChunkFirst | kChunkSplit))) {
+      // lane 0: constants of a tile starting at lane 0 -> slot ts; lane 1: constants of the tile starting at lane sp -> slot ts ^ 1
+      if (lane < 2 && (cm.meta & (lane == 0 ? kChunkFirst : kChunkSplit))) {
         PoseConst k0; LossConst l0;
-        make_pose_const<VARIANT>(sb->pose, k0);
-        make_loss_const(lp, mu_per_seg ? sb->mu : lp.mu, l0);
-        kc = k0; lc = l0;
+        make_pose_const<VARIANT>(sb->pose[lane], k0);
+        make_loss_const(lp, mu_per_seg ? sb->mu[lane] : lp.mu, l0);
+        kc_all[warp][ts ^ lane] = k0; lc_all[warp][ts ^ lane] = l0;
       }
       __syncwarp();
     }
-    if (live && (uint32_t)lane < n_here) {
-      RawCell m, f[2];
-      m.a = sb->rec[lane][0]; m.b = sb->rec[lane][1]; m.c = sb->rec[lane][2];
-      f[0].a = sb->rec[lane][3]; f[0].b = sb->rec[lane][4]; f[0].c = sb->rec[lane][5];
-      f[1].a = sb->rec[lane][6]; f[1].b = sb->rec[lane][7]; f[1].c = sb->rec[lane][8];
-      const bool two = __float_as_uint(f[1].a.x) != kNoSecondPair;
-      Moving mv;
-      moving_part<VARIANT>(kc, m, mv);
-      double dd[2], N[2][4], wgt[2], hrho[2], wd[2];
-      bool ok[2];
+    double* scratch = reinterpret_cast<double*>(&sb->rec[0][0]);
+    if (!split) {
+      const PoseConst& kc = kc_all[warp][ts]; const LossConst& lc = lc_all[warp][ts];
+      if (live && (uint32_t)lane < n_here) accumulate_duo<VARIANT, LOSS, WANT_JAC, NS>(kc, lc, sb, lane, acc, max_dd, n_bad);
+      if (live && (cm.meta & kChunkLast)) {
+        finish_tile<VARIANT, WANT_JAC, NS>(P, acc, max_dd, n_bad, cm.seg, (cm.meta & kChunkSolo) != 0u, cm.part, kc, scratch, out, bad_counter, lane);
 #pragma unroll
-      for (int j = 0; j < 2; ++j) dd[j] = fixed_part<VARIANT, WANT_JAC>(kc, mv, f[j], N[j]);
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        ok[j] = dd_valid(dd[j]);
-        loss_eval<LOSS>(dd[j], lc, wgt[j], hrho[j], wd[j]);
+        for (int e = 0; e < NS; ++e) acc[e] = 0.0;
+        max_dd = 0.0; n_bad = 0;
       }
-      const bool use1 = two && ok[1];
-      n_bad += (ok[0] ? 0u : 1u) + ((two && !ok[1]) ? 1u : 0u);
+    } else {
+      // the tail of one (solo) tile in lanes [0, sp) and the head of the next in lanes [sp, n_here): every lane evaluates its duo
+      // with its own tile's constants into a private set of sums, which then joins the right tile's totals
+      const bool mine_new = (uint32_t)lane >= sp;
+      const int my = mine_new ? (ts ^ 1) : ts;
+      double c[NS]; double mc = 0.0; uint32_t cb = 0;
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        if (j == 0 ? ok[0] : use1) {
-          if (WANT_JAC) {
-            int q = 0;
+      for (int e = 0; e < NS; ++e) c[e] = 0.0;
+      if ((uint32_t)lane < n_here) accumulate_duo<VARIANT, LOSS, WANT_JAC, NS>(kc_all[warp][my], lc_all[warp][my], sb, lane, c, mc, cb);
+      double vals[NS];
 #pragma unroll
-            for (int a = 0; a < NB; ++a) {
-              const double wa = wd[j] * N[j][a];
+      for (int e = 0; e < NS; ++e) vals[e] = acc[e] + (mine_new ? 0.0 : c[e]);
+      finish_tile<VARIANT, WANT_JAC, NS>(P, vals, fmax(max_dd, mine_new ? 0.0 : mc), n_bad + (mine_new ? 0u : cb), cm.seg, true, 0u, kc_all[warp][ts],
+                                         scratch, out, bad_counter, lane);
 #pragma unroll
-              for (int b2 = a; b2 < NB; ++b2) { acc[q] = fma(wa, N[j][b2], acc[q]); ++q; }
-              acc[NH + a] = fma(wgt[j], N[j][a], acc[NH + a]);
-            }
-          }
-          acc[NJ] += hrho[j];
-          acc[NJ + 1] += dd[j];
-          max_dd = fmax(max_dd, dd[j]);
-        }
+      for (int e = 0; e < NS; ++e) acc[e] = mine_new ? c[e] : 0.0;
+      max_dd = mine_new ? mc : 0.0; n_bad = mine_new ? cb : 0u;
+      if (cm.meta & kChunkNewLast) {      // the second tile is shorter than the rest of the chunk: it ends here too
+        finish_tile<VARIANT, WANT_JAC, NS>(P, acc, max_dd, n_bad, cm.part, true, 0u, kc_all[warp][ts ^ 1], scratch, out, bad_counter, lane);
+#pragma unroll
+        for (int e = 0; e < NS; ++e) acc[e] = 0.0;
+        max_dd = 0.0; n_bad = 0;
       }
-    }
-    // ---- tile finished: reduce across the warp and emit ----
-    if (live && (cm.meta & kChunkLast)) {
-      const double mine = smem_reduce<NS>(acc, reinterpret_cast<double*>(&sb->rec[0][0]), lane);   // slot s total: lanes 2s, 2s+1
-      const double mx = warp_max_nonneg(max_dd);
-      const uint32_t bad = __reduce_add_sync(kFull, n_bad);
-      const uint32_t seg = cm.seg;
-      const uint32_t n_pairs_seg = P.seg_off[seg + 1] - P.seg_off[seg];
-      if (cm.meta & kChunkSolo) {
-        write_segment_out<VARIANT, WANT_JAC>(mine, mx, kc, n_pairs_seg, out + (size_t)seg * RANDT_FUSED_STRIDE, lane,
-                                             [](int sl) { return 2 * sl; });
-        if (lane == 0 && bad) atomicAdd(bad_counter, (unsigned long long)bad);
-      } else {
-        // partial record of this tile: [NS sums][max dd][bad], one entry per lane
-        const uint32_t first = P.seg_first_tile[seg], seg_tiles = P.seg_first_tile[seg + 1] - first;
-        double* part = P.partials + (size_t)cm.part * kMaxAcc;
-        double pv = __shfl_sync(kFull, mine, 2 * (lane < NS ? lane : 0));
-        if (lane == NS) pv = mx;
-        if (lane == NS + 1) pv = (double)bad;
-        if (lane < NS + 2) part[lane] = pv;
-        __threadfence();
-        __syncwarp();
-        uint32_t ticket = 0;
-        if (lane == 0) ticket = atomicAdd(&P.seg_counters[seg], 1u);
-        ticket = __shfl_sync(kFull, ticket, 0);
-        if (ticket == seg_tiles - 1) {   // last tile of this segment to finish: fold the partials in tile order
-          __threadfence();
-          double v = 0.0;
-          if (lane < NS + 2) {
-            for (uint32_t u = 0; u < seg_tiles; ++u) {
-              const double x = __ldcg(P.partials + (size_t)(first + u) * kMaxAcc + lane);
-              v = (lane == NS) ? fmax(v, x) : v + x;
-            }
-          }
-          const double mx_all = __shfl_sync(kFull, v, NS);
-          const double bad_all = __shfl_sync(kFull, v, NS + 1);
-          write_segment_out<VARIANT, WANT_JAC>(v, mx_all, kc, n_pairs_seg, out + (size_t)seg * RANDT_FUSED_STRIDE, lane,
-                                               [](int sl) { return sl; });
-          if (lane == 0) {
-            if (bad_all != 0.0) atomicAdd(bad_counter, (unsigned long long)bad_all);
-            P.seg_counters[seg] = 0u;   // re-arm for the next launch
-          }
-        }
-      }
-#pragma unroll
-      for (int e = 0; e < NS; ++e) acc[e] = 0.0;
-      max_dd = 0.0; n_bad = 0;
+      ts ^= 1;                            // the tile that started here is the one at lane 0 of the next chunk
     }
     // Every lane's LDS of this slot has completed (the values were consumed above), so after the warp barrier lane 0 may let
     // the next bulk copy overwrite it.
@@ -714,7 +763,7 @@ __global__ void __launch_bounds__(kK3Threads, kMinCtas) k3_emit_kernel(DevicePro
     __syncwarp();
     StageBuf* sb = &stage[slot];
     if (live) { mbar_wait(&sb->bar, (phase_bits >> slot) & 1u); phase_bits ^= 1u << slot; }
-    if ((cm.meta & kChunkFirst) && live) make_pose_const<VARIANT>(sb->pose, kc);
+    if ((cm.meta & kChunkFirst) && live) make_pose_const<VARIANT>(sb->pose[0], kc);
     if (live && (uint32_t)lane < n_here) {
       RawCell m, f0, f1;
       m.a = sb->rec[lane][0]; m.b = sb->rec[lane][1]; m.c = sb->rec[lane][2];
@@ -853,6 +902,25 @@ cudaError_t launch_sweep_v(const DeviceProblem& p, uint32_t pb, uint32_t pe, con
 }
 
 }  // namespace
+
+// duos in schedule order: record r belongs to the tile t with tile_rec_begin[t] <= r < tile_rec_begin[t+1] (tiles in the order the
+// warps walk them) and is that tile's (r - tile_rec_begin[t])-th duo
+__global__ void __launch_bounds__(256) permute_duos_kernel(const Duo* __restrict__ in, const uint32_t* __restrict__ tile_rec_begin,
+                                                           const uint32_t* __restrict__ tile_duo_begin, uint32_t n_tiles, uint32_t n_duos,
+                                                           Duo* __restrict__ out) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_duos) return;
+  uint32_t lo = 0, hi = n_tiles;          // largest t with tile_rec_begin[t] <= r
+  while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (tile_rec_begin[mid] <= r) lo = mid; else hi = mid; }
+  out[r] = in[tile_duo_begin[lo] + (r - tile_rec_begin[lo])];
+}
+cudaError_t launch_permute_duos(const Duo* in, const uint32_t* tile_rec_begin, const uint32_t* tile_duo_begin, uint32_t n_tiles, uint32_t n_duos,
+                                Duo* out, cudaStream_t s, int* n_launches) {
+  if (n_duos == 0) return cudaSuccess;
+  permute_duos_kernel<<<(n_duos + 255u) / 256u, 256, 0, s>>>(in, tile_rec_begin, tile_duo_begin, n_tiles, n_duos, out);
+  if (n_launches) *n_launches += 1;
+  return cudaGetLastError();
+}
 
 cudaError_t launch_build_duo_records(const float4* cells_m, const float4* cells_f, const Duo* duos, uint32_t n_duos, DuoRec* recs,
                                      uint32_t* duo_p0, cudaStream_t s, int* n_launches) {
