@@ -3,6 +3,7 @@
 // per-pair work runs in the kernels of k1_voxelize.cu, k2_associate.cu and k3_pair_eval.cu.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -849,6 +850,7 @@ int randt_register_batch_dev(randt_ctx* ctx, const randt_problem* cp, int varian
       CK(cudaEventSynchronize(p->lm_ev[(g - 1) & 1]));
       const uint32_t n_act = p->h_n_active[(g - 1) & 1];
       done = n_act == 0u;
+      if (getenv("RANDT_DEBUG_SOLVER")) fprintf(stderr, "[randt solver] group %lld (iterations <= %lld): %u active\n", g - 1, g * poll, n_act);
       // finished segments leave holes K3 has to step over: compact the schedule once a quarter of its segments are gone
       if (!done && (unsigned long long)n_act * 4ull <= (unsigned long long)planned_for * 3ull) {
         CK(launch_replan(p->chunks, p->n_chunks, p->lm_active, p->n_warps, p->lm_flags, p->lm_scan, p->lm_bs, p->lm_chunks, p->lm_warp_off,

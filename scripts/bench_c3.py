@@ -29,7 +29,9 @@ def draw_cells(rng, n, half, res):
     cov = np.zeros((n, 3, 3))
     cov[:, 0, 0] = c * c * l1 + s * s * l2; cov[:, 1, 1] = s * s * l1 + c * c * l2; cov[:, 0, 1] = cov[:, 1, 0] = c * s * (l1 - l2)
     cov[:, 2, 2] = rng.uniform(20, 400, n)
-    x = rng.normal(0, 0.1, (n, 2)); cov[:, 0, 2] = cov[:, 2, 0] = x[:, 0]; cov[:, 1, 2] = cov[:, 2, 1] = x[:, 1]
+    # xy-intensity cross terms with correlations in (-0.4, 0.4) of the smaller xy eigenvalue (SURVEY's N(0, 0.1) is not PSD for thin cells)
+    x = rng.uniform(-0.4, 0.4, (n, 2)) * np.sqrt(np.minimum(l1, l2) * cov[:, 2, 2])[:, None]
+    cov[:, 0, 2] = cov[:, 2, 0] = x[:, 0]; cov[:, 1, 2] = cov[:, 2, 1] = x[:, 1]
     out = np.zeros((n, 12), np.float32); out[:, :3] = mu; out[:, 3:] = cov.reshape(n, 9)
     order = np.argsort(slots)          # grid order, like a voxelised map
     return out[order]
