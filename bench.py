@@ -100,7 +100,7 @@ def build_problem(ctx, capi, p, n_problems, seed0):
     pm, pf, seg = prob.download()
     stats = dict(n_m=int(prob.n_m), n_f=int(prob.n_f), pairs=int(prob.n_pairs), segments=int(prob.n_segments),
                  n_f_referenced=int(len(np.unique(pf))))
-    host = dict(cells_m=m_cells, cells_f=f_cells, pm=pm, pf=pf, seg=seg)
+    host = dict(cells_m=m_cells, cells_f=f_cells, pm=pm, pf=pf, seg=seg, f_off=f_off, m_off=m_off, slot=slot)
     return prob, poses, stats, host
 
 
@@ -428,6 +428,35 @@ def main():
                    "kept_points_per_scan": kept // len(raws), "cells_per_scan": cells // len(raws),
                    "what": "randt_filter_scan (K6, device in/out) + randt_voxelize (K1) per scan, wall clock incl. the two small D2H syncs; "
                            "the Oxford sensor delivers 4 scans/s"}
+        # ---- construction-time stages: K1 voxelise and K2 associate on resident batches ----
+        stages = None
+        if args.pre_scans > 0:
+            sub_, _, mov_, _ = pool_scans(p, args.seed + 100 * rank)
+            base = sub_[:POOL] + mov_
+            reps_ = 8                                        # 256 scans per call
+            pts_np = np.concatenate(base * reps_)
+            off_np = np.concatenate([[0], np.cumsum([len(s) for s in base * reps_])]).astype(np.uint32)
+            d_pts_all = torch.from_numpy(pts_np).to("cuda:%d" % local)
+            gp_ = capi.grid_params(p)
+            ctx.voxelize(d_pts_all.data_ptr(), off_np, gp_, pts_on_device=True).close()
+            barrier(); t0 = time.perf_counter()
+            for _ in range(5):
+                mvox = ctx.voxelize(d_pts_all.data_ptr(), off_np, gp_, pts_on_device=True)
+                n_cells_vox = mvox.info()[1]; mvox.close()
+            barrier(); t_vox = (time.perf_counter() - t0) / 5
+            # K2 on the bench batch: re-associate the resident problem's maps
+            Fm = ctx.map_upload(host["cells_f"], host["f_off"], gp_, slot=host["slot"])
+            Mm = ctx.map_upload(host["cells_m"], host["m_off"], gp_)
+            ctx.associate(Fm, Mm, poses, p.n_results_nn_lookup, capi.LOOKUP_MAHALANOBIS).close()
+            barrier(); t0 = time.perf_counter()
+            for _ in range(3):
+                ctx.associate(Fm, Mm, poses, p.n_results_nn_lookup, capi.LOOKUP_MAHALANOBIS).close()
+            barrier(); t_as = (time.perf_counter() - t0) / 3
+            Fm.close(); Mm.close()
+            stages = {"voxelize": {"points_per_s": len(pts_np) / t_vox, "scans_per_s": (len(off_np) - 1) / t_vox, "ms_per_call": t_vox * 1e3, "scans_per_call": len(off_np) - 1,
+                                   "points_per_call": int(len(pts_np)), "cells_per_call": int(n_cells_vox), "what": "randt_voxelize (K1), points resident, incl. per-call allocation and count readback"},
+                      "associate": {"queries_per_s": st["n_m"] / t_as, "ms_per_call": t_as * 1e3, "queries_per_call": st["n_m"],
+                                    "what": "randt_associate (K2 + pair/duo compaction + record table + schedule), maps resident"}}
     bad = ctx.take_bad_pairs()
 
     t_ms = torch.tensor([ms, e2e_s * 1e3, reg["ms_per_batch"] if reg else 0.0, reg["e2e_ms_per_batch"] if reg else 0.0], dtype=torch.float64,
@@ -474,6 +503,22 @@ def main():
         }
         if pre:
             line["preprocess"] = pre
+        if stages:
+            if not args.no_cpu_baseline:
+                from oracle import oracle_py as O
+                va = (p.n_clusters, p.max_range, p.min_points_per_cell, p.size_x, p.size_y, p.resolution, p.max_neighbor_linf_distance)
+                t0 = time.perf_counter()
+                for sc_ in base[:8]:
+                    O.voxelize(sc_, *va)
+                stages["voxelize"]["cpu_points_per_s_1thread"] = sum(len(s_) for s_ in base[:8]) / (time.perf_counter() - t0)
+                t0 = time.perf_counter(); nq = 0
+                for s_ in range(8):
+                    a_, b_ = int(host["f_off"][s_]), int(host["f_off"][s_ + 1]); c_, d_ = int(host["m_off"][s_]), int(host["m_off"][s_ + 1])
+                    O.associate(host["cells_f"][a_:b_], host["slot"][s_], p.size_x, p.size_y, p.resolution, p.max_neighbor_linf_distance,
+                                host["cells_m"][c_:d_], poses[s_], p.n_results_nn_lookup)
+                    nq += d_ - c_
+                stages["associate"]["cpu_queries_per_s_1thread"] = nq / (time.perf_counter() - t0)
+            line["stages"] = stages
         if reg:
             line["registrations"] = {
                 "value": seg_all / (reg_ms_all * 1e-3), "unit": "registrations/s", "e2e_value": seg_all / (reg_e2e_ms_all * 1e-3),

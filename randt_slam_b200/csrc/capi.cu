@@ -84,8 +84,27 @@ int fail(randt_ctx* ctx, int code, const char* what, cudaError_t e = cudaSuccess
     if (e__ != cudaSuccess) return fail(ctx, RANDT_E_CUDA, #call, e__);          \
   } while (0)
 
+// Device memory comes from the stream-ordered pool (cudaMallocAsync) while an API call is running on a context: allocation and
+// release are then queue operations on the context's stream instead of device-wide synchronisations, which is what the per-scan
+// calls (voxelise, associate, merge) are made of.  Outside a call (the destroy functions) plain cudaFree is used, which is valid
+// for pool memory as well.
+thread_local cudaStream_t t_stream = nullptr;
+thread_local bool t_in_call = false;
+struct StreamScope {
+  cudaStream_t prev; bool prev_in;
+  explicit StreamScope(cudaStream_t s) : prev(t_stream), prev_in(t_in_call) { t_stream = s; t_in_call = true; }
+  ~StreamScope() { t_stream = prev; t_in_call = prev_in; }
+};
 template <typename T>
-cudaError_t dev_alloc(T** p, size_t n) { *p = nullptr; if (n == 0) n = 1; return cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)); }
+cudaError_t dev_alloc(T** p, size_t n) {
+  *p = nullptr; if (n == 0) n = 1;
+  if (t_in_call) return cudaMallocAsync(reinterpret_cast<void**>(p), n * sizeof(T), t_stream);
+  return cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T));
+}
+inline void dev_free(void* p) {
+  if (!p) return;
+  if (t_in_call) cudaFreeAsync(p, t_stream); else cudaFree(p);
+}
 
 bool same_geom(const randt_grid_params& a, const randt_grid_params& b) {
   return a.size_x == b.size_x && a.size_y == b.size_y && a.resolution == b.resolution;
@@ -93,17 +112,17 @@ bool same_geom(const randt_grid_params& a, const randt_grid_params& b) {
 
 void free_map(randt_map* m) {
   if (!m) return;
-  cudaFree(m->cells); cudaFree(m->npts); cudaFree(m->labels); cudaFree(m->cell_off); cudaFree(m->slot);
+  dev_free(m->cells); dev_free(m->npts); dev_free(m->labels); dev_free(m->cell_off); dev_free(m->slot);
   delete m;
 }
 void free_problem(randt_problem* p) {
   if (!p) return;
-  cudaFree(p->cells_m); cudaFree(p->cells_f); cudaFree(p->pairs); cudaFree(p->duos); cudaFree(p->duo_recs); cudaFree(p->duo_p0); cudaFree(p->chunks); cudaFree(p->warp_off); cudaFree(p->chunks_full); cudaFree(p->warp_off_full); cudaFree(p->seg_first_tile); cudaFree(p->seg_off);
-  cudaFree(p->partials); cudaFree(p->seg_counters); cudaFree(p->d_poses); cudaFree(p->d_out); cudaFree(p->d_mu); cudaFree(p->d_r);
-  cudaFree(p->d_J); cudaFree(p->d_sweep);
-  cudaFree(p->lm_state); cudaFree(p->lm_eval_pose); cudaFree(p->lm_mu); cudaFree(p->lm_rec); cudaFree(p->lm_poses); cudaFree(p->lm_result);
-  cudaFree(p->lm_active); cudaFree(p->lm_n_active);
-  cudaFree(p->lm_chunks); cudaFree(p->lm_flags); cudaFree(p->lm_scan); cudaFree(p->lm_bs); cudaFree(p->lm_warp_off);
+  dev_free(p->cells_m); dev_free(p->cells_f); dev_free(p->pairs); dev_free(p->duos); dev_free(p->duo_recs); dev_free(p->duo_p0); dev_free(p->chunks); dev_free(p->warp_off); dev_free(p->chunks_full); dev_free(p->warp_off_full); dev_free(p->seg_first_tile); dev_free(p->seg_off);
+  dev_free(p->partials); dev_free(p->seg_counters); dev_free(p->d_poses); dev_free(p->d_out); dev_free(p->d_mu); dev_free(p->d_r);
+  dev_free(p->d_J); dev_free(p->d_sweep);
+  dev_free(p->lm_state); dev_free(p->lm_eval_pose); dev_free(p->lm_mu); dev_free(p->lm_rec); dev_free(p->lm_poses); dev_free(p->lm_result);
+  dev_free(p->lm_active); dev_free(p->lm_n_active);
+  dev_free(p->lm_chunks); dev_free(p->lm_flags); dev_free(p->lm_scan); dev_free(p->lm_bs); dev_free(p->lm_warp_off);
   if (p->h_n_active) cudaFreeHost(p->h_n_active);
   if (p->lm_ev[0]) cudaEventDestroy(p->lm_ev[0]);
   if (p->lm_ev[1]) cudaEventDestroy(p->lm_ev[1]);
@@ -220,7 +239,7 @@ int finish_problem(randt_ctx* ctx, randt_problem* p) {
     if (e == cudaSuccess) e = launch_permute_duos(p->duos, d_trb, d_tdb, (uint32_t)tiles.size(), p->n_duos, d_stream, ctx->stream, &nl);
     if (e == cudaSuccess) e = launch_build_duo_records(p->cells_m, p->cells_f, d_stream, p->n_duos, p->duo_recs, p->duo_p0, ctx->stream, &nl);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_trb); cudaFree(d_tdb); cudaFree(d_stream);
+    dev_free(d_trb); dev_free(d_tdb); dev_free(d_stream);
     if (e != cudaSuccess) return fail(ctx, RANDT_E_CUDA, "finish_problem: record table", e);
     ctx->launches += nl;
   }
@@ -285,6 +304,13 @@ int randt_ctx_create(int device, void* stream, randt_ctx** out) {
     if (stream) { ctx->stream = (cudaStream_t)stream; ctx->own_stream = false; }
     else { e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking); ctx->own_stream = true; }
   }
+  if (e == cudaSuccess) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long keep = ~0ull;     // never trim: the per-scan calls reuse the same few buffers
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_bad), sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_bad, 0, sizeof(unsigned long long), ctx->stream);
   if (e != cudaSuccess) { delete ctx; return RANDT_E_CUDA; }
@@ -296,7 +322,7 @@ void randt_ctx_destroy(randt_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  cudaFree(ctx->d_bad);
+  dev_free(ctx->d_bad);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -334,6 +360,7 @@ int randt_voxelize(randt_ctx* ctx, const float* pts4, const uint32_t* scan_off, 
   if (gp->n_clusters <= 0 || gp->size_x <= 0 || gp->size_y <= 0 || !(gp->resolution > 0) || !(gp->max_range > 0))
     return fail(ctx, RANDT_E_INVALID, "randt_voxelize: bad grid parameters");
   CK(cudaSetDevice(ctx->device));
+  StreamScope scope__(ctx->stream);
   const uint32_t B = n_scans;
   if (scan_off[0] != 0) return fail(ctx, RANDT_E_INVALID, "randt_voxelize: scan_off[0] must be 0");
   const uint32_t n_pts = scan_off[B];
@@ -349,9 +376,9 @@ int randt_voxelize(randt_ctx* ctx, const float* pts4, const uint32_t* scan_off, 
   int32_t *d_labels_scratch = nullptr, *d_labels_p = nullptr; float4* d_cells_p = nullptr; int* d_status = nullptr;
   int rc = RANDT_OK;
   auto cleanup = [&]() {
-    if (own_pts) cudaFree(d_pts);
-    cudaFree(d_scan_off); cudaFree(d_cnt); cudaFree(d_order); cudaFree(d_npts_p); cudaFree(d_labels_scratch); cudaFree(d_labels_p);
-    cudaFree(d_cells_p); cudaFree(d_status);
+    if (own_pts) dev_free(d_pts);
+    dev_free(d_scan_off); dev_free(d_cnt); dev_free(d_order); dev_free(d_npts_p); dev_free(d_labels_scratch); dev_free(d_labels_p);
+    dev_free(d_cells_p); dev_free(d_status);
   };
 #define CKV(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rc = fail(ctx, RANDT_E_CUDA, #call, e__); cleanup(); free_map(m); return rc; } } while (0)
   if (pts_on_device) d_pts = const_cast<float4*>(reinterpret_cast<const float4*>(pts4));
@@ -399,12 +426,13 @@ int randt_filter_scan(randt_ctx* ctx, const float* raw4, uint32_t n_az, uint32_t
   if (!ctx || !fp || !n_out || (!raw4 && n_az && n_bins) || (!out4 && cap)) return fail(ctx, RANDT_E_INVALID, "randt_filter_scan: null argument");
   if ((unsigned long long)n_az * n_bins > 0x7fffffffull) return fail(ctx, RANDT_E_CAPACITY, "randt_filter_scan: scan too large");
   CK(cudaSetDevice(ctx->device));
+  StreamScope scope__(ctx->stream);
   *n_out = 0;
   const size_t n = (size_t)n_az * n_bins;
   float4 *d_raw = nullptr, *d_out = nullptr; uint32_t *d_peak = nullptr, *d_n = nullptr; float* d_angle = nullptr; int* d_status = nullptr;
   bool own_raw = false, own_out = false;
   int nl = 0;
-  auto cleanup = [&]() { if (own_raw) cudaFree(d_raw); if (own_out) cudaFree(d_out); cudaFree(d_peak); cudaFree(d_n); cudaFree(d_angle); cudaFree(d_status); };
+  auto cleanup = [&]() { if (own_raw) dev_free(d_raw); if (own_out) dev_free(d_out); dev_free(d_peak); dev_free(d_n); dev_free(d_angle); dev_free(d_status); };
   cudaError_t e = cudaSuccess;
   if (raw_on_device) d_raw = const_cast<float4*>(reinterpret_cast<const float4*>(raw4));
   else { own_raw = true; e = dev_alloc(&d_raw, n); if (e == cudaSuccess && n) e = cudaMemcpyAsync(d_raw, raw4, n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream); }
@@ -437,6 +465,7 @@ int randt_map_upload(randt_ctx* ctx, const float* cells, const uint32_t* npts, c
   *out = nullptr;
   if (gp->size_x <= 0 || gp->size_y <= 0 || !(gp->resolution > 0)) return fail(ctx, RANDT_E_INVALID, "randt_map_upload: bad map geometry");
   CK(cudaSetDevice(ctx->device));
+  StreamScope scope__(ctx->stream);
   randt_map* m = new (std::nothrow) randt_map();
   if (!m) return RANDT_E_NOMEM;
   m->device = ctx->device; m->gp = *gp; m->geom = make_geom(*gp); m->B = n_maps;
@@ -478,6 +507,7 @@ int randt_map_info(const randt_map* m, uint32_t* n_maps, uint32_t* n_cells_total
 int randt_map_download(randt_ctx* ctx, const randt_map* m, float* cells, uint32_t* npts, int32_t* labels, uint32_t* cell_off, int32_t* slot) {
   if (!ctx || !m) return fail(ctx, RANDT_E_INVALID, "randt_map_download: null argument");
   CK(cudaSetDevice(ctx->device));
+  StreamScope scope__(ctx->stream);
   if (cells && m->n_cells) CK(cudaMemcpyAsync(cells, m->cells, (size_t)m->n_cells * 48, cudaMemcpyDeviceToHost, ctx->stream));
   if (npts && m->n_cells) CK(cudaMemcpyAsync(npts, m->npts, (size_t)m->n_cells * 4, cudaMemcpyDeviceToHost, ctx->stream));
   if (labels) {
@@ -493,13 +523,14 @@ int randt_map_download(randt_ctx* ctx, const randt_map* m, float* cells, uint32_
 int randt_map_transform(randt_ctx* ctx, randt_map* m, const float* trans) {
   if (!ctx || !m || !trans) return fail(ctx, RANDT_E_INVALID, "randt_map_transform: null argument");
   CK(cudaSetDevice(ctx->device));
+  StreamScope scope__(ctx->stream);
   float4* d_t = nullptr;
   CK(dev_alloc(&d_t, m->B));
   int nl = 0;
   cudaError_t e = cudaMemcpyAsync(d_t, trans, (size_t)m->B * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = launch_transform_cells(m->cells, m->cell_off, m->B, m->max_per_map, d_t, ctx->stream, &nl);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(d_t);
+  dev_free(d_t);
   if (e != cudaSuccess) return fail(ctx, RANDT_E_CUDA, "randt_map_transform", e);
   ctx->launches += nl;
   return RANDT_OK;
@@ -509,6 +540,7 @@ int randt_map_merge(randt_ctx* ctx, randt_map* F, const randt_map* M) {
   if (!ctx || !F || !M) return fail(ctx, RANDT_E_INVALID, "randt_map_merge: null argument");
   if (F->B != M->B || !same_geom(F->gp, M->gp)) return fail(ctx, RANDT_E_INVALID, "randt_map_merge: batch size / geometry mismatch");
   CK(cudaSetDevice(ctx->device));
+  StreamScope scope__(ctx->stream);
   const uint32_t B = F->B;
   uint32_t cap = 1;
   for (uint32_t b = 0; b < B; ++b) cap = std::max(cap, (F->h_cell_off[b + 1] - F->h_cell_off[b]) + (M->h_cell_off[b + 1] - M->h_cell_off[b]));
@@ -516,8 +548,8 @@ int randt_map_merge(randt_ctx* ctx, randt_map* F, const randt_map* M) {
   for (uint32_t b = 0; b <= B; ++b) h_ooff[b] = b * cap;
   float4 *o_cells = nullptr, *n_cells = nullptr; uint32_t *o_npts = nullptr, *o_cnt = nullptr, *d_ooff = nullptr, *n_npts = nullptr, *n_off = nullptr;
   int nl = 0; int rc = RANDT_OK;
-  auto cleanup = [&]() { cudaFree(o_cells); cudaFree(o_npts); cudaFree(o_cnt); cudaFree(d_ooff); };
-#define CKG(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rc = fail(ctx, RANDT_E_CUDA, #call, e__); cleanup(); cudaFree(n_cells); cudaFree(n_npts); cudaFree(n_off); return rc; } } while (0)
+  auto cleanup = [&]() { dev_free(o_cells); dev_free(o_npts); dev_free(o_cnt); dev_free(d_ooff); };
+#define CKG(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rc = fail(ctx, RANDT_E_CUDA, #call, e__); cleanup(); dev_free(n_cells); dev_free(n_npts); dev_free(n_off); return rc; } } while (0)
   CKG(dev_alloc(&o_cells, (size_t)B * cap * 3)); CKG(dev_alloc(&o_npts, (size_t)B * cap)); CKG(dev_alloc(&o_cnt, B)); CKG(dev_alloc(&d_ooff, B + 1));
   CKG(cudaMemcpyAsync(d_ooff, h_ooff.data(), (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
   CKG(launch_merge_maps(F->cells, F->npts, F->cell_off, F->slot, M->cells, M->npts, M->cell_off, B, F->geom, d_ooff, o_cells, o_npts, o_cnt, ctx->stream, &nl));
@@ -532,7 +564,7 @@ int randt_map_merge(randt_ctx* ctx, randt_map* F, const randt_map* M) {
   CKG(cudaStreamSynchronize(ctx->stream));
 #undef CKG
   cleanup();
-  cudaFree(F->cells); cudaFree(F->npts); cudaFree(F->cell_off); cudaFree(F->labels);
+  dev_free(F->cells); dev_free(F->npts); dev_free(F->cell_off); dev_free(F->labels);
   F->cells = n_cells; F->npts = n_npts; F->cell_off = n_off; F->labels = nullptr;
   F->h_cell_off = new_off; F->n_cells = new_off[B]; F->max_per_map = max_per;
   ctx->launches += nl;
@@ -543,6 +575,7 @@ int randt_cs_divergence(randt_ctx* ctx, const randt_map* F, const randt_map* M, 
   if (!ctx || !F || !M || !out) return fail(ctx, RANDT_E_INVALID, "randt_cs_divergence: null argument");
   if (F->B != M->B) return fail(ctx, RANDT_E_INVALID, "randt_cs_divergence: fixed and moving batches differ in size");
   CK(cudaSetDevice(ctx->device));
+  StreamScope scope__(ctx->stream);
   const uint32_t B = F->B;
   if (B == 0) return RANDT_OK;
   double *d_part = nullptr, *d_out = nullptr; uint32_t* d_tick = nullptr;
@@ -554,7 +587,7 @@ int randt_cs_divergence(randt_ctx* ctx, const randt_map* F, const randt_map* M, 
   if (e == cudaSuccess) e = launch_cs_divergence(F->cells, F->cell_off, M->cells, M->cell_off, B, d_part, d_tick, d_out, ctx->stream, &nl);
   if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(d_part); cudaFree(d_out); cudaFree(d_tick);
+  dev_free(d_part); dev_free(d_out); dev_free(d_tick);
   if (e != cudaSuccess) return fail(ctx, RANDT_E_CUDA, "randt_cs_divergence", e);
   ctx->launches += nl;
   return RANDT_OK;
@@ -576,13 +609,14 @@ int randt_associate(randt_ctx* ctx, const randt_map* F, const randt_map* M, cons
   if (2 * (geom.r_stop > 0 ? geom.r_stop - 1 : 0) + 1 > geom.size_x)
     return fail(ctx, RANDT_E_CAPACITY, "randt_associate: search window wider than the map (duplicate window slots are not supported)");
   CK(cudaSetDevice(ctx->device));
+  StreamScope scope__(ctx->stream);
   const uint32_t B = F->B, n_m = M->n_cells;
   randt_problem* p = new (std::nothrow) randt_problem();
   if (!p) return RANDT_E_NOMEM;
   p->device = ctx->device; p->S = B; p->n_m = n_m; p->n_f = F->n_cells;
   float4* d_pose = nullptr; uint32_t *d_nn = nullptr, *d_cnt = nullptr, *d_scan = nullptr, *d_bs = nullptr, *d_cnt2 = nullptr, *d_scan2 = nullptr;
   int rc = RANDT_OK; int nl = 0;
-  auto cleanup = [&]() { cudaFree(d_pose); cudaFree(d_nn); cudaFree(d_cnt); cudaFree(d_scan); cudaFree(d_bs); cudaFree(d_cnt2); cudaFree(d_scan2); };
+  auto cleanup = [&]() { dev_free(d_pose); dev_free(d_nn); dev_free(d_cnt); dev_free(d_scan); dev_free(d_bs); dev_free(d_cnt2); dev_free(d_scan2); };
 #define CKA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rc = fail(ctx, RANDT_E_CUDA, #call, e__); cleanup(); free_problem(p); return rc; } } while (0)
   std::vector<float4> h_pose(B);
   for (uint32_t b = 0; b < B; ++b) h_pose[b] = make_float4((float)pose0[4 * b], (float)pose0[4 * b + 1], (float)pose0[4 * b + 2], (float)pose0[4 * b + 3]);
@@ -636,6 +670,7 @@ int randt_problem_create(randt_ctx* ctx, const float* cells_m, uint32_t n_m, con
   for (uint32_t s = 0; s < n_segments; ++s) if (seg_off[s + 1] < seg_off[s]) return fail(ctx, RANDT_E_INVALID, "randt_problem_create: seg_off not monotone");
   for (uint32_t i = 0; i < n_pairs; ++i) if (pair_m[i] >= n_m || pair_f[i] >= n_f) return fail(ctx, RANDT_E_INVALID, "randt_problem_create: pair index out of range");
   CK(cudaSetDevice(ctx->device));
+  StreamScope scope__(ctx->stream);
   randt_problem* p = new (std::nothrow) randt_problem();
   if (!p) return RANDT_E_NOMEM;
   p->device = ctx->device; p->S = n_segments; p->P = n_pairs; p->n_m = n_m; p->n_f = n_f;
@@ -682,6 +717,7 @@ int randt_problem_info(const randt_problem* p, uint32_t* n_segments, uint32_t* n
 int randt_problem_download(randt_ctx* ctx, const randt_problem* p, uint32_t* pair_m, uint32_t* pair_f, uint32_t* seg_off) {
   if (!ctx || !p) return fail(ctx, RANDT_E_INVALID, "randt_problem_download: null argument");
   CK(cudaSetDevice(ctx->device));
+  StreamScope scope__(ctx->stream);
   if ((pair_m || pair_f) && p->P) {
     std::vector<uint2> h(p->P);
     CK(cudaMemcpyAsync(h.data(), p->pairs, (size_t)p->P * sizeof(uint2), cudaMemcpyDeviceToHost, ctx->stream));
@@ -696,6 +732,7 @@ int randt_problem_download(randt_ctx* ctx, const randt_problem* p, uint32_t* pai
 int randt_problem_download_cells(randt_ctx* ctx, const randt_problem* p, float* cells_m, float* cells_f) {
   if (!ctx || !p) return fail(ctx, RANDT_E_INVALID, "randt_problem_download_cells: null argument");
   CK(cudaSetDevice(ctx->device));
+  StreamScope scope__(ctx->stream);
   if (cells_m && p->n_m) CK(cudaMemcpyAsync(cells_m, p->cells_m, (size_t)p->n_m * 48, cudaMemcpyDeviceToHost, ctx->stream));
   if (cells_f && p->n_f) CK(cudaMemcpyAsync(cells_f, p->cells_f, (size_t)p->n_f * 48, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -711,6 +748,7 @@ int randt_eval_emit_dev(randt_ctx* ctx, const randt_problem* p, int variant, con
   if (!ctx || !p || !d_poses || !d_r) return fail(ctx, RANDT_E_INVALID, "randt_eval_emit_dev: null argument");
   if (check_variant(ctx, variant)) return RANDT_E_INVALID;
   CK(cudaSetDevice(ctx->device));
+  StreamScope scope__(ctx->stream);
   int nl = 0;
   CK(launch_eval_emit(view(p), variant, d_poses, d_r, d_J, ctx->d_bad, ctx->stream, &nl));
   ctx->launches += nl;
@@ -722,6 +760,7 @@ int randt_eval_emit(randt_ctx* ctx, const randt_problem* cp, int variant, const 
   if (check_variant(ctx, variant)) return RANDT_E_INVALID;
   randt_problem* p = const_cast<randt_problem*>(cp);
   CK(cudaSetDevice(ctx->device));
+  StreamScope scope__(ctx->stream);
   const int np = np_of(variant);
   if (!p->d_r) CK(dev_alloc(&p->d_r, p->P));
   if (J && !p->d_J) CK(dev_alloc(&p->d_J, (size_t)p->P * 4));
@@ -741,6 +780,7 @@ int randt_eval_fused_dev(randt_ctx* ctx, const randt_problem* p, int variant, co
   LossParams lp;
   if (int rc = make_loss(ctx, loss, &lp)) return rc;
   CK(cudaSetDevice(ctx->device));
+  StreamScope scope__(ctx->stream);
   // segments without pairs produce no tile: clear their records up front
   if (p->has_empty_segment) CK(cudaMemsetAsync(d_out, 0, (size_t)p->S * RANDT_FUSED_STRIDE * sizeof(double), ctx->stream));
   int nl = 0;
@@ -757,6 +797,7 @@ int randt_eval_fused(randt_ctx* ctx, const randt_problem* cp, int variant, const
   if (check_variant(ctx, variant)) return RANDT_E_INVALID;
   randt_problem* p = const_cast<randt_problem*>(cp);
   CK(cudaSetDevice(ctx->device));
+  StreamScope scope__(ctx->stream);
   const int np = np_of(variant);
   CK(cudaMemcpyAsync(p->d_poses, poses, (size_t)p->S * np * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   if (mu_per_seg) CK(cudaMemcpyAsync(p->d_mu, mu_per_seg, (size_t)p->S * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -776,9 +817,10 @@ int randt_sweep_costs(randt_ctx* ctx, const randt_problem* cp, uint32_t seg, int
   LossParams lp;
   if (int rc = make_loss(ctx, loss, &lp)) return rc;
   CK(cudaSetDevice(ctx->device));
+  StreamScope scope__(ctx->stream);
   const int np = np_of(variant);
   const size_t need = (size_t)n_poses * (np + 1);
-  if (p->sweep_cap < need) { cudaFree(p->d_sweep); p->d_sweep = nullptr; p->sweep_cap = 0; CK(dev_alloc(&p->d_sweep, need)); p->sweep_cap = need; }
+  if (p->sweep_cap < need) { dev_free(p->d_sweep); p->d_sweep = nullptr; p->sweep_cap = 0; CK(dev_alloc(&p->d_sweep, need)); p->sweep_cap = need; }
   double* d_p = p->d_sweep; double* d_c = p->d_sweep + (size_t)n_poses * np;
   if (n_poses) CK(cudaMemcpyAsync(d_p, poses, (size_t)n_poses * np * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   int nl = 0;
@@ -815,6 +857,7 @@ int randt_register_batch_dev(randt_ctx* ctx, const randt_problem* cp, int varian
   if (int rc = make_loss(ctx, &l0, &lp)) return rc;
   randt_problem* p = const_cast<randt_problem*>(cp);
   CK(cudaSetDevice(ctx->device));
+  StreamScope scope__(ctx->stream);
   const uint32_t S = p->S;
   const int np = np_of(variant);
   if (S == 0) return RANDT_OK;
@@ -873,6 +916,7 @@ int randt_register_batch(randt_ctx* ctx, const randt_problem* cp, int variant, d
   if (check_variant(ctx, variant)) return RANDT_E_INVALID;
   randt_problem* p = const_cast<randt_problem*>(cp);
   CK(cudaSetDevice(ctx->device));
+  StreamScope scope__(ctx->stream);
   const uint32_t S = p->S;
   const int np = np_of(variant);
   if (S == 0) return RANDT_OK;

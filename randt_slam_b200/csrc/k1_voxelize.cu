@@ -104,16 +104,34 @@ struct CellOut { float mu[3]; float cov[9]; };
 // Cell::updateCell for a fresh cell: two sequential float32 passes over the cell's points (ndt_cell.cpp:43-65), then the
 // xy eigenvalue floor and the +1e-6 on the intensity variance (ndt_cell.cpp:102-112).
 __device__ void cell_stats(const float4* __restrict__ pts, const uint32_t* __restrict__ order, uint32_t n, CellOut& o) {
+  // The sums are sequential in point order (that is what makes the result bit-identical to the reference), but the loads are not:
+  // eight index loads, then eight point gathers are in flight together before their values are added one after the other.
+  constexpr int U = 8;
   float sx = 0.f, sy = 0.f, si = 0.f;
-  for (uint32_t k = 0; k < n; ++k) { const float4 p = __ldg(pts + order[k]); sx += p.x; sy += p.y; si += p.w; }
+  for (uint32_t k0 = 0; k0 < n; k0 += U) {
+    uint32_t id[U]; float4 p[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) id[j] = (k0 + j < n) ? order[k0 + j] : order[k0];
+#pragma unroll
+    for (int j = 0; j < U; ++j) p[j] = __ldg(pts + id[j]);
+#pragma unroll
+    for (int j = 0; j < U; ++j) if (k0 + j < n) { sx += p[j].x; sy += p[j].y; si += p[j].w; }
+  }
   const float nf = (float)n;
   const float mx = sx / nf, my = sy / nf, mz = si / nf;
   float c00 = 0.f, c11 = 0.f, c22 = 0.f, c01 = 0.f, c02 = 0.f, c12 = 0.f;
-  for (uint32_t k = 0; k < n; ++k) {
-    const float4 p = __ldg(pts + order[k]);
-    const float dx = p.x - mx, dy = p.y - my, di = p.w - mz;
-    c00 += dx * dx; c11 += dy * dy; c22 += di * di;
-    c01 += dx * dy; c02 += dx * di; c12 += dy * di;
+  for (uint32_t k0 = 0; k0 < n; k0 += U) {
+    uint32_t id[U]; float4 p[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) id[j] = (k0 + j < n) ? order[k0 + j] : order[k0];
+#pragma unroll
+    for (int j = 0; j < U; ++j) p[j] = __ldg(pts + id[j]);
+#pragma unroll
+    for (int j = 0; j < U; ++j) if (k0 + j < n) {
+      const float dx = p[j].x - mx, dy = p[j].y - my, di = p[j].w - mz;
+      c00 += dx * dx; c11 += dy * dy; c22 += di * di;
+      c01 += dx * dy; c02 += dx * di; c12 += dy * di;
+    }
   }
   o.mu[0] = mx; o.mu[1] = my; o.mu[2] = mz;
   o.cov[0] = c00 / nf; o.cov[1] = c01 / nf; o.cov[2] = c02 / nf;
