@@ -493,7 +493,9 @@ def main():
                        "l2_policy": "inputs larger than L2 (%.0f MB resident vs 126 MB), no flush" % (resident / 1e6),
                        "preset": p.name, "parallelism": "problems sharded across ranks, no data-path collective" if world > 1 else "single GPU"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(S * 32), "d2h_bytes_per_step": int(S * 192),
-                    "ms_per_step": e2e_ms_all / args.steps, "api": "randt_eval_fused (host pointers)"},
+                    "ms_per_step": e2e_ms_all / args.steps,
+                    "api": "randt_eval_fused (host pointers): poses copied H2D from pinned memory, the per-pose records stored by the kernel "
+                           "directly into the caller's pinned result buffer (device->host bytes over PCIe, no staging copy)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
                          "traffic": measured_traffic(Pn), "peak_source": pk_src, "kernel": "k3_fused_kernel<0,BARRON_M2,true>",

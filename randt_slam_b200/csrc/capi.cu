@@ -801,9 +801,18 @@ int randt_eval_fused(randt_ctx* ctx, const randt_problem* cp, int variant, const
   const int np = np_of(variant);
   CK(cudaMemcpyAsync(p->d_poses, poses, (size_t)p->S * np * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   if (mu_per_seg) CK(cudaMemcpyAsync(p->d_mu, mu_per_seg, (size_t)p->S * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  int rc = randt_eval_fused_dev(ctx, p, variant, p->d_poses, loss, mu_per_seg ? p->d_mu : nullptr, want_jac, p->d_out);
+  // When the caller's result buffer is pinned (mapped) host memory, K3 stores its 192-byte records straight into it: the writes
+  // travel over PCIe while the rest of the batch is still being evaluated, instead of a 192 S byte copy after the kernel.
+  double* d_out = p->d_out;
+  bool direct = false;
+  if (!p->has_empty_segment) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, out) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) { d_out = static_cast<double*>(at.devicePointer); direct = true; }
+    else cudaGetLastError();
+  }
+  int rc = randt_eval_fused_dev(ctx, p, variant, p->d_poses, loss, mu_per_seg ? p->d_mu : nullptr, want_jac, d_out);
   if (rc) return rc;
-  if (p->S) CK(cudaMemcpyAsync(out, p->d_out, (size_t)p->S * RANDT_FUSED_STRIDE * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (p->S && !direct) CK(cudaMemcpyAsync(out, p->d_out, (size_t)p->S * RANDT_FUSED_STRIDE * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return RANDT_OK;
 }

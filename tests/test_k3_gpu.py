@@ -168,3 +168,26 @@ def test_invalid_arguments(gpu_ctx):
         prob.eval_emit(np.zeros(3), variant=7)
     with pytest.raises(capi.RandtError):
         prob.eval_fused(np.array([1.0, 0, 0, 0]), capi.make_loss(capi.LOSS_BARRON, scale=-1.0))
+
+
+def test_fused_writes_directly_into_pinned_host_memory(oracle, gpu_ctx):
+    """pinned (mapped) result buffers are written by K3 itself (no staging copy): same bits as the staged path"""
+    import ctypes
+    case = H.make_registration_case(oracle, P.OXFORD, seed=9)
+    cm, cf, im, jf = case["moving"]["cells"], case["fixed"]["cells"], case["im"], case["jf"]
+    n = len(im)
+    seg = [0, n // 4, n // 2, n]
+    poses = np.stack([case["pose0"], synth.pose_to_se2(0.55, -0.35, 0.025), synth.pose_to_se2(0.45, -0.25, 0.015)])
+    prob = gpu_ctx.problem_create(cm, cf, im, jf, seg)
+    loss = capi.make_loss(capi.LOSS_BARRON, 1.0, -2.0, 1.3, 0.5)
+    staged = prob.eval_fused(poses, loss)                       # pageable numpy buffer -> device scratch + copy
+    nbytes = 3 * capi.FUSED_STRIDE * 8
+    ptr = capi.lib().randt_host_alloc(nbytes)
+    assert ptr
+    try:
+        pinned = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_double)), shape=(3, capi.FUSED_STRIDE))
+        pinned[:] = -1.0
+        out = prob.eval_fused(poses, loss, out=pinned)
+        assert out is pinned and np.array_equal(pinned, staged)
+    finally:
+        capi.lib().randt_host_free(ptr)
