@@ -103,32 +103,29 @@ struct CellOut { float mu[3]; float cov[9]; };
 
 // Cell::updateCell for a fresh cell: two sequential float32 passes over the cell's points (ndt_cell.cpp:43-65), then the
 // xy eigenvalue floor and the +1e-6 on the intensity variance (ndt_cell.cpp:102-112).
-__device__ void cell_stats(const float4* __restrict__ pts, const uint32_t* __restrict__ order, uint32_t n, CellOut& o) {
-  // The sums are sequential in point order (that is what makes the result bit-identical to the reference), but the loads are not:
-  // eight index loads, then eight point gathers are in flight together before their values are added one after the other.
-  constexpr int U = 8;
+// One WARP per cell: the 32 lanes fetch 32 points at a time (index, then point: two memory round trips per 32 points instead of
+// per point), and every lane then adds the 32 values in point order through shuffles — all lanes carry the same running sums, so
+// the order (and with it every rounding) is exactly the reference's sequential loop.
+__device__ void cell_stats_warp(const float4* __restrict__ pts, const uint32_t* __restrict__ order, uint32_t n, int lane, CellOut& o) {
+  constexpr unsigned kAll = 0xffffffffu;
   float sx = 0.f, sy = 0.f, si = 0.f;
-  for (uint32_t k0 = 0; k0 < n; k0 += U) {
-    uint32_t id[U]; float4 p[U];
-#pragma unroll
-    for (int j = 0; j < U; ++j) id[j] = (k0 + j < n) ? order[k0 + j] : order[k0];
-#pragma unroll
-    for (int j = 0; j < U; ++j) p[j] = __ldg(pts + id[j]);
-#pragma unroll
-    for (int j = 0; j < U; ++j) if (k0 + j < n) { sx += p[j].x; sy += p[j].y; si += p[j].w; }
+  for (uint32_t k0 = 0; k0 < n; k0 += 32) {
+    const uint32_t m = min(32u, n - k0);
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if ((uint32_t)lane < m) p = __ldg(pts + order[k0 + lane]);
+    for (uint32_t j = 0; j < m; ++j) {
+      sx += __shfl_sync(kAll, p.x, (int)j); sy += __shfl_sync(kAll, p.y, (int)j); si += __shfl_sync(kAll, p.w, (int)j);
+    }
   }
   const float nf = (float)n;
   const float mx = sx / nf, my = sy / nf, mz = si / nf;
   float c00 = 0.f, c11 = 0.f, c22 = 0.f, c01 = 0.f, c02 = 0.f, c12 = 0.f;
-  for (uint32_t k0 = 0; k0 < n; k0 += U) {
-    uint32_t id[U]; float4 p[U];
-#pragma unroll
-    for (int j = 0; j < U; ++j) id[j] = (k0 + j < n) ? order[k0 + j] : order[k0];
-#pragma unroll
-    for (int j = 0; j < U; ++j) p[j] = __ldg(pts + id[j]);
-#pragma unroll
-    for (int j = 0; j < U; ++j) if (k0 + j < n) {
-      const float dx = p[j].x - mx, dy = p[j].y - my, di = p[j].w - mz;
+  for (uint32_t k0 = 0; k0 < n; k0 += 32) {
+    const uint32_t m = min(32u, n - k0);
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if ((uint32_t)lane < m) p = __ldg(pts + order[k0 + lane]);
+    for (uint32_t j = 0; j < m; ++j) {
+      const float dx = __shfl_sync(kAll, p.x, (int)j) - mx, dy = __shfl_sync(kAll, p.y, (int)j) - my, di = __shfl_sync(kAll, p.w, (int)j) - mz;
       c00 += dx * dx; c11 += dy * dy; c22 += di * di;
       c01 += dx * dy; c02 += dx * di; c12 += dy * di;
     }
@@ -263,8 +260,7 @@ __global__ void __launch_bounds__(kVoxThreads) k1_voxelize_kernel(const float4* 
   }
   __syncthreads();
 
-  // ---- phase 4: one thread per occupied label: keep test, sequential float32 statistics ----
-  // cluster c (rank among occupied bins) is kept iff count > min_points; kept clusters are numbered in ascending label order.
+  // ---- phase 4a: keep test (count > min_points), kept clusters numbered in ascending label order ----
   uint32_t carry_keep = 0;
   for (uint32_t base = 0; base < span; base += kVoxThreads) {
     const uint32_t bin = base + tid;
@@ -276,23 +272,32 @@ __global__ void __launch_bounds__(kVoxThreads) k1_voxelize_kernel(const float4* 
     if (keep) {
       const uint32_t ci = carry_keep + ex;
       if (ci < cell_cap) {
-        CellOut o;
-        cell_stats(pts, order + p0 + bin_start[bin], cnt, o);
-        const uint32_t s = coord_to_index(geom, o.mu[0], o.mu[1]);
-        float4* dst = cells_out + 3 * ((size_t)b * cell_cap + ci);
-        dst[0] = make_float4(o.mu[0], o.mu[1], o.mu[2], o.cov[0]);
-        dst[1] = make_float4(o.cov[1], o.cov[2], o.cov[3], o.cov[4]);
-        dst[2] = make_float4(o.cov[5], o.cov[6], o.cov[7], o.cov[8]);
         npts_out[(size_t)b * cell_cap + ci] = cnt;
         labels_out[(size_t)b * cell_cap + ci] = (int32_t)bin + lab_min;
-        // the reference would throw (vector::at) for a mean outside the map; flagged instead, cell kept without a slot
-        if (s < geom.n_slots) atomicMax(&slot[s], (int32_t)ci);   // "later cluster wins" == largest kept index
-        else status[b] = VOX_OUT_OF_MAP;
       } else {
         status[b] = VOX_CELL_CAP;
       }
     }
     carry_keep += t_keep;
+  }
+  __syncthreads();
+  // ---- phase 4b: one warp per kept cell: sequential float32 statistics, slot table ----
+  const uint32_t n_keep = min(carry_keep, cell_cap);
+  for (uint32_t ci = warp; ci < n_keep; ci += kVoxWarps) {
+    const uint32_t bin = (uint32_t)(labels_out[(size_t)b * cell_cap + ci] - lab_min);
+    const uint32_t cnt = npts_out[(size_t)b * cell_cap + ci];
+    CellOut o;
+    cell_stats_warp(pts, order + p0 + bin_start[bin], cnt, lane, o);
+    if (lane == 0) {
+      const uint32_t s = coord_to_index(geom, o.mu[0], o.mu[1]);
+      float4* dst = cells_out + 3 * ((size_t)b * cell_cap + ci);
+      dst[0] = make_float4(o.mu[0], o.mu[1], o.mu[2], o.cov[0]);
+      dst[1] = make_float4(o.cov[1], o.cov[2], o.cov[3], o.cov[4]);
+      dst[2] = make_float4(o.cov[5], o.cov[6], o.cov[7], o.cov[8]);
+      // the reference would throw (vector::at) for a mean outside the map; flagged instead, cell kept without a slot
+      if (s < geom.n_slots) atomicMax(&slot[s], (int32_t)ci);   // "later cluster wins" == largest kept index
+      else status[b] = VOX_OUT_OF_MAP;
+    }
   }
   if (tid == 0) cell_count[b] = min(carry_keep, cell_cap);
 }
