@@ -191,3 +191,60 @@ def test_fused_writes_directly_into_pinned_host_memory(oracle, gpu_ctx):
         assert out is pinned and np.array_equal(pinned, staged)
     finally:
         capi.lib().randt_host_free(ptr)
+
+
+@pytest.mark.parametrize("k", [1, 2, 4])
+def test_fused_ragged_segments_cover_every_chunk_shape(oracle, gpu_ctx, k):
+    """segments of 1 ... 700 duos in one batch: single-chunk tiles, tiles ending exactly on a chunk, split chunks whose second tile also
+    ends inside the chunk (several tiny segments in a row), multi-tile segments folded through partial records, empty segments"""
+    rng = np.random.default_rng(100 + k)
+    sizes = [1, 2, 31, 32, 33, 5, 63, 64, 65, 1, 1, 1, 40, 0, 255, 256, 257, 3, 600, 17, 96, 0, 700, 29, 30, 31, 32, 33, 34, 7]
+    n_m = sum(sizes)
+    cm = H.random_cells(rng, max(n_m, 1), extent=6.0); cf = H.random_cells(rng, 900, extent=6.0)
+    im, jf, seg = [], [], [0]
+    m = 0
+    for sz in sizes:                      # sz moving cells, each with k neighbours (k consecutive pairs share their moving cell)
+        for _ in range(sz):
+            for j in rng.choice(900, k, replace=False):
+                im.append(m); jf.append(int(j))
+            m += 1
+        seg.append(len(im))
+    im = np.array(im, np.uint32); jf = np.array(jf, np.uint32)
+    S = len(sizes)
+    poses = np.stack([synth.pose_to_se2(*rng.uniform(-0.3, 0.3, 3)) for _ in range(S)])
+    mus = rng.uniform(1.0, 3.0, S)
+    loss = capi.make_loss(capi.LOSS_BARRON, 1.5, -2.0, 1.0, 0.02)
+    prob = gpu_ctx.problem_create(cm, cf, im, jf, seg)
+    out = capi.unpack_fused(prob.eval_fused(poses, loss, mu_per_seg=mus))
+    fo, _ = oracle.fused_batch(0, cm, cf, im, jf, seg, poses, (loss.kind, loss.scale, loss.alpha, 1.0, loss.weight), mu_per_seg=mus)
+    for s_ in range(S):
+        if sizes[s_] == 0:
+            assert out["n"][s_] == 0 and out["cost"][s_] == 0 and np.all(out["H"][s_] == 0)
+            continue
+        assert out["n"][s_] == sizes[s_] * k
+        assert H.rel_err(out["H"][s_], fo["H"][s_]) < 1e-9, (s_, sizes[s_])
+        assert H.rel_err(out["g"][s_], fo["g"][s_]) < 1e-9, (s_, sizes[s_])
+        assert abs(out["cost"][s_] - fo["cost"][s_]) <= 1e-10 * abs(fo["cost"][s_])
+        assert abs(out["max_r"][s_] - fo["max_r"][s_]) <= 1e-12 * fo["max_r"][s_]
+    # EMIT walks the unsplit schedule over the same record table
+    r, J = prob.eval_emit(poses)
+    for s_ in (0, 4, 18, 22):
+        a, b = seg[s_], seg[s_ + 1]
+        ro, Jo = oracle.eval_pairs(0, cm, cf, im[a:b], jf[a:b], poses[s_], 0)
+        assert np.max(np.abs(r[a:b] - ro) / ro) < TOL and rowwise(J[a:b], Jo) < 1e-8
+
+
+def test_fused_one_very_long_segment(oracle, gpu_ctx):
+    """a single segment of 300 k pairs: ~590 tiles folded by the ticket/partial path"""
+    rng = np.random.default_rng(5)
+    cm = H.random_cells(rng, 4000, extent=10.0); cf = H.random_cells(rng, 6000, extent=10.0)
+    P_ = 300000
+    im = np.sort(rng.integers(0, 4000, P_)).astype(np.uint32); jf = rng.integers(0, 6000, P_).astype(np.uint32)
+    pose = synth.pose_to_se2(0.1, -0.2, 0.03)
+    loss = capi.make_loss(capi.LOSS_BARRON, 2.0, -1.0, 1.7, 1e-3)
+    prob = gpu_ctx.problem_create(cm, cf, im, jf, [0, P_])
+    o = capi.unpack_fused(prob.eval_fused(pose, loss))
+    fo = oracle.fused(0, cm, cf, im, jf, pose, (loss.kind, loss.scale, loss.alpha, loss.mu, loss.weight), True)
+    assert o["n"][0] == P_
+    assert H.rel_err(o["H"][0], fo["H"]) < 1e-9 and H.rel_err(o["g"][0], fo["g"]) < 1e-9
+    assert abs(o["cost"][0] - fo["cost"]) <= 1e-10 * fo["cost"]
