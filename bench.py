@@ -233,7 +233,7 @@ def run_reference(args, p, loss):
         "registrations": {"value": regN, "unit": "registrations/s", "single_thread_value": reg1, "cores": threads, "mean_iterations": reg_it,
                           "what": "Matcher::estimateLoopConstraint restated (GNC + ceres-LM, Jet<4> evaluation), oxford loop-closure parameters"},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_name(p):
@@ -271,7 +271,21 @@ def build_host_workload(p, n_problems, seed0):
     return host, poses
 
 
+_OUT = None
+
+
+def emit(line):
+    """the ONE JSON line, on the process's original stdout"""
+    _OUT.write(json.dumps(line) + "\n")
+    _OUT.flush()
+
+
 def main():
+    # Libraries (NCCL's version banner, for one) write to file descriptor 1; keep the real stdout for the JSON line only.
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -548,7 +562,7 @@ def main():
             line["cpu_baseline"] = {"value": vN, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": "first %d problems (%d pairs) x %d passes, Jet<4> autodiff + corrector + J^T J" % (n_s, int(host["seg"][n_s]), reps),
                                     "single_thread_value": v1, "gpu_vs_oracle_max_rel_err_on_sample": err}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -16,7 +16,12 @@
  *    Cell::new_mean_ / new_cov_ hold (R/include/ndt_representation/ndt_cell.h:167-168).
  *  - "pose" = 4 float64 in Sophus::SE2d::data() order [cos, sin, tx, ty] (R/src/ndt_registration/ndt_matcher.cpp:233,292)
  *    for the SE2 variants, or 3 float64 [x, y, theta] for the vector variants.
- *  - *_dev entry points take device pointers, enqueue on the context stream and do not synchronise.
+ *  - a randt_map / randt_problem carries scratch buffers for the calls made on it: use one object from one thread at a time (different
+ *    objects may be used concurrently on different contexts).  Per-call device memory comes from the stream-ordered pool of the device.
+ *  - *_dev entry points take device pointers, enqueue on the context stream and do not synchronise (randt_register_batch_dev is the
+ *    exception: it polls the device and returns when every segment has finished).
+ *  - kernels are launched with programmatic stream serialisation: a randt kernel may begin its prologue while the previous kernel of the
+ *    stream drains, but reads caller-visible data only after that kernel has completed (griddepcontrol.wait).
  */
 #ifndef RANDT_GPU_H
 #define RANDT_GPU_H

@@ -286,3 +286,35 @@ def test_cs_divergence_restatement(oracle):
     assert not ok(a[4])
     assert np.allclose(terms, [I, F, M], rtol=2e-4)
     assert abs(got - (-math.log(I) + 0.5 * math.log(F) + 0.5 * math.log(M))) < 5e-4
+
+
+def test_randomised_autodiff_vs_closed_form_and_loss_derivatives(oracle):
+    """hypothesis-driven: for arbitrary poses (incl. un-normalised (c, s)) and cell pairs the dual-number functor and the closed form
+    agree; rho' and rho'' of every loss are the derivatives of rho"""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(seed=st.integers(0, 2 ** 31 - 1), theta=st.floats(-3.1, 3.1), scale=st.floats(0.7, 1.4), tx=st.floats(-5, 5), ty=st.floats(-5, 5))
+    def check_pairs(seed, theta, scale, tx, ty):
+        rng = np.random.default_rng(seed)
+        cm = H.random_cells(rng, 6, extent=3.0); cf = H.random_cells(rng, 6, extent=3.0)
+        idx = np.arange(6, dtype=np.uint32)
+        pose = np.array([scale * math.cos(theta), scale * math.sin(theta), tx, ty])
+        r0, J0 = oracle.eval_pairs(0, cm, cf, idx, idx, pose, 0)
+        r1, J1 = oracle.eval_pairs(0, cm, cf, idx, idx, pose, 1)
+        assert np.all(r0 >= 0) and np.all(np.isfinite(J0))
+        assert np.max(np.abs(r0 - r1) / r0) < 1e-10
+        assert np.max(np.abs(J0 - J1) / np.max(np.abs(J0), axis=1, keepdims=True)) < 1e-8
+
+    @settings(max_examples=60, deadline=None)
+    @given(kind=st.sampled_from([1, 2]), a=st.floats(0.3, 3.0), alpha=st.sampled_from([-2.0, -1.5, -1.0, 0.02, 1.0]), mu=st.floats(1.0, 5.0),
+           s=st.floats(1e-3, 50.0))
+    def check_loss(kind, a, alpha, mu, s):
+        h = 1e-5 * s
+        r = oracle.loss_eval(kind, a, alpha, mu, 1.0, s); rp = oracle.loss_eval(kind, a, alpha, mu, 1.0, s + h); rm = oracle.loss_eval(kind, a, alpha, mu, 1.0, s - h)
+        assert abs((rp[0] - rm[0]) / (2 * h) - r[1]) <= 1e-6 * abs(r[1]) + 1e-12
+        assert abs((rp[1] - rm[1]) / (2 * h) - r[2]) <= 1e-5 * abs(r[2]) + 1e-12
+        assert r[1] > 0 and r[2] <= 0          # monotone and concave: the Corrector's rho'' <= 0 branch, which K3 implements
+
+    check_pairs()
+    check_loss()
