@@ -466,9 +466,19 @@ def main():
             for _ in range(3):
                 ctx.associate(Fm, Mm, poses, p.n_results_nn_lookup, capi.LOOKUP_MAHALANOBIS).close()
             barrier(); t_as = (time.perf_counter() - t0) / 3
+            # K5: Cauchy-Schwarz divergence of every (submap, scan) pair of the batch (moving maps taken as already aligned)
+            Fm.cs_divergence(Mm)
+            barrier(); t0 = time.perf_counter()
+            for _ in range(3):
+                cs_all = Fm.cs_divergence(Mm)
+            barrier(); t_cs = (time.perf_counter() - t0) / 3
+            nf_ = np.diff(host["f_off"]).astype(np.float64); nm_ = np.diff(host["m_off"]).astype(np.float64)
+            cs_terms = float(np.sum(nf_ * nm_ + nf_ * (nf_ - 1) / 2 + nm_ * (nm_ - 1) / 2))
             Fm.close(); Mm.close()
             stages = {"voxelize": {"points_per_s": len(pts_np) / t_vox, "scans_per_s": (len(off_np) - 1) / t_vox, "ms_per_call": t_vox * 1e3, "scans_per_call": len(off_np) - 1,
                                    "points_per_call": int(len(pts_np)), "cells_per_call": int(n_cells_vox), "what": "randt_voxelize (K1), points resident, incl. per-call allocation and count readback"},
+                      "cs_divergence": {"map_pairs_per_s": S / t_cs, "gaussian_overlaps_per_s": cs_terms / t_cs, "ms_per_call": t_cs * 1e3, "map_pairs_per_call": S,
+                                        "finite": bool(np.isfinite(cs_all).all()), "what": "randt_cs_divergence (K5), maps resident: all-pairs 3x3 inverse + det + exp"},
                       "associate": {"queries_per_s": st["n_m"] / t_as, "ms_per_call": t_as * 1e3, "queries_per_call": st["n_m"],
                                     "what": "randt_associate (K2 + pair/duo compaction + record table + schedule), maps resident"}}
     bad = ctx.take_bad_pairs()
@@ -534,6 +544,12 @@ def main():
                                 host["cells_m"][c_:d_], poses[s_], p.n_results_nn_lookup)
                     nq += d_ - c_
                 stages["associate"]["cpu_queries_per_s_1thread"] = nq / (time.perf_counter() - t0)
+                t0 = time.perf_counter(); nt = 0.0
+                for s_ in range(4):
+                    a_, b_ = int(host["f_off"][s_]), int(host["f_off"][s_ + 1]); c_, d_ = int(host["m_off"][s_]), int(host["m_off"][s_ + 1])
+                    O.cs_divergence(host["cells_f"][a_:b_], host["cells_m"][c_:d_])
+                    nt += (b_ - a_) * (d_ - c_) + (b_ - a_) * (b_ - a_ - 1) / 2 + (d_ - c_) * (d_ - c_ - 1) / 2
+                stages["cs_divergence"]["cpu_gaussian_overlaps_per_s_1thread"] = nt / (time.perf_counter() - t0)
             line["stages"] = stages
         if reg:
             line["registrations"] = {
