@@ -124,3 +124,42 @@ def test_register_batch_rejects_bad_options(gpu_ctx):
     prob = gpu_ctx.problem_create(cm, cm, [0], [0], [0, 1])
     with pytest.raises(capi.RandtError):
         prob.register_batch(np.array([[1.0, 0, 0, 0]]), None, capi.solver_options(gnc_divisor=1.0))
+
+
+def test_register_batch_many_segments(oracle, gpu_ctx):
+    """a batch of 4500+ segments (whole-segment tiles, schedule re-planned as segments finish): every replica of a (problem, guess)
+    pair gives the same bits wherever it sits in the batch, and agrees with the solo solve (whose 32-duo tiles add the same terms in
+    another order) to 1e-9"""
+    p = P.OXFORD
+    guesses = [(0.5, -0.3, 0.02), (0.2, -0.1, 0.0), (0.9, -0.6, 0.05)]
+    cases, cm, cf, pm, pf, seg, poses = build_batch(oracle, p, [31, 32, 33], guesses)
+    loss = capi.make_loss(capi.LOSS_BARRON, p.loop_closure_scale, p.loss_function_convexity, 1.0, 1.0)
+    opt = capi.solver_options(use_manifold=1, gnc_loss_scale=p.loss_function_scale, gnc_divisor=p.gnc_control_parameter_divisor, gnc_max_steps=3)
+    solo = gpu_ctx.problem_create(cm, cf, pm, pf, seg)
+    want_pose, want_res = solo.register_batch(poses, loss, opt)
+    # 4500 segments over the same cell tables: segment s is a replica of problem s % 3 (an occasional empty segment in between)
+    reps = 1500
+    big_pm, big_pf, big_seg, big_pose, kind = [], [], [0], [], []
+    for r in range(reps):
+        for j in range(3):
+            a, b = int(seg[j]), int(seg[j + 1])
+            big_pm.append(pm[a:b]); big_pf.append(pf[a:b]); big_seg.append(big_seg[-1] + (b - a)); big_pose.append(poses[j]); kind.append(j)
+        if r % 400 == 7:
+            big_seg.append(big_seg[-1]); big_pose.append(poses[0]); kind.append(-1)
+    prob = gpu_ctx.problem_create(cm, cf, np.concatenate(big_pm), np.concatenate(big_pf), np.array(big_seg, np.uint32))
+    assert prob.n_segments >= 4096
+    out, res = prob.register_batch(np.stack(big_pose), loss, opt)
+    kind = np.array(kind)
+    for j in range(3):
+        sel = kind == j
+        first = int(np.nonzero(sel)[0][0])
+        assert np.array_equal(out[sel], np.broadcast_to(out[first], out[sel].shape)), j
+        assert np.array_equal(res[sel], np.broadcast_to(res[first], res[sel].shape)), j
+        assert np.max(np.abs(out[first] - want_pose[j])) < 1e-9
+        assert int(res[first, capi.REG_ITERATIONS]) == int(want_res[j, capi.REG_ITERATIONS])
+    assert np.all(res[kind == -1, capi.REG_STATUS] == 1)
+    o = oracle.loop_constraint(cases[1]["fixed"]["cells"], cases[1]["fixed"]["slot"], p.size_x, p.size_y, p.resolution, p.max_neighbor_linf_distance,
+                               cases[1]["moving"]["cells"], cases[1]["pose0"], p.n_results_nn_lookup, matcher_loss_scale=p.loss_function_scale,
+                               loop_scale=p.loop_closure_scale, alpha=p.loss_function_convexity, divisor=p.gnc_control_parameter_divisor, max_gnc_steps=3,
+                               on_manifold=True, pairs=(cases[1]["im"], cases[1]["jf"]))
+    assert np.max(np.abs(want_pose[1] - o["pose"])) < 1e-7 and int(want_res[1, capi.REG_ITERATIONS]) == o["iterations"]
