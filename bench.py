@@ -447,7 +447,7 @@ def main():
                 if dtp is not None:
                     same = all(np.array_equal(w_["res"][:, capi.REG_ITERATIONS], workers[0]["res"][:, capi.REG_ITERATIONS]) for w_ in workers)
                     pipe = {"value": args.reg_streams * args.reg_steps * S / dtp, "streams": args.reg_streams,
-                            "ms_per_batch_effective": dtp * 1e3 / (args.reg_streams * args.reg_steps), "identical_results_across_streams": bool(same),
+                            "ms_per_batch_effective": dtp * 1e3 / (args.reg_streams * args.reg_steps), "identical_results_across_streams": bool(same), "scope": "this rank's GPU only",
                             "what": "%d independent batches of %d registrations solved concurrently through randt_register_batch (host poses in, poses + "
                                     "records out), one context + stream + host thread each" % (args.reg_streams, S)}
                 else:
