@@ -29,18 +29,45 @@ constexpr uint32_t kNoPeak = 0xffffffffu;
 // std::hypot(float, float): glibc evaluates it in double and rounds once
 __device__ __forceinline__ float hypot_ref(float x, float y) { return (float)sqrt((double)x * (double)x + (double)y * (double)y); }
 
+// Per point the reference evaluates hypot (range gate) and atan2 (azimuth cut).  Both are only DECISIONS against thresholds, so
+// the kernel takes them with cheap float32 bounds and falls back to the exact evaluation in the narrow bands where the bound
+// cannot decide (relative width 1e-5 around the range limits; azimuth deviations between 0.45e-4 and the 1e-4 cut):
+//   range:  d2 = x^2 + y^2 in float carries a relative error < 3e-7, and fl32(sqrt) adds < 6e-8, so d2 outside (1 -+ 1e-5) lim^2 decides;
+//   angle:  |atan2(p) - atan2(p0)| <= 1e-4 is certain when |p0 x p| <= 0.45e-4 (p0 . p) with p0 . p > 0 (the true angle is then < 0.45e-4 and
+//           the two float roundings add < 1e-6) — unless the row lies on the +-pi branch cut of atan2, which rows flag up front.
 __global__ void __launch_bounds__(kRowThreads) k6_row_peak_kernel(const float4* __restrict__ raw, uint32_t n_az, uint32_t n_bins, float min_d,
                                                                   float max_d, uint32_t* __restrict__ peak_idx, float* __restrict__ row_angle,
                                                                   int* __restrict__ status) {
   const uint32_t row = blockIdx.x;
   const float4* p = raw + (size_t)row * n_bins;
-  const float a0 = atan2f(p[0].y, p[0].x);
+  const float4 first = __ldg(p);
+  const float x0 = first.x, y0 = first.y;
+  const float a0 = atan2f(y0, x0);
+  const bool near_cut = !(x0 > 0.0f || fabsf(y0) > 1e-3f * fabsf(x0));    // within ~1e-3 rad of +-pi (or at the origin): always exact
+  const float lo2 = min_d * min_d, hi2 = max_d * max_d;
+  const float lo2_in = lo2 * 1.00001f, lo2_out = lo2 * 0.99999f, hi2_in = hi2 * 0.99999f, hi2_out = hi2 * 1.00001f;
   float best = 0.0f; uint32_t best_i = kNoPeak; bool bad = false;
-  for (uint32_t b = threadIdx.x; b < n_bins; b += kRowThreads) {
-    const float4 v = __ldg(p + b);
-    const float dist = hypot_ref(v.x, v.y);
-    if (fabsf(atan2f(v.y, v.x) - a0) > 0.0001f) bad = true;      // the reference would start a new azimuth inside this row
-    if (dist > min_d && dist < max_d && v.w > best) { best = v.w; best_i = b; }   // ascending b per thread: first-wins inside the thread
+  constexpr int U = 4;                                                      // independent 16-byte loads in flight per thread (12 was slower: 12.8 vs 9.9 us)
+  for (uint32_t b0 = threadIdx.x; b0 < n_bins; b0 += kRowThreads * U) {
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) { const uint32_t b = b0 + u * kRowThreads; v[u] = b < n_bins ? __ldg(p + b) : first; }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t b = b0 + u * kRowThreads;
+      if (b >= n_bins) continue;
+      const float x = v[u].x, y = v[u].y;
+      // azimuth rule
+      const float cr = x0 * y - y0 * x, dt = x0 * x + y0 * y;
+      if (near_cut || !(fabsf(cr) <= 0.45e-4f * dt)) { if (fabsf(atan2f(y, x) - a0) > 0.0001f) bad = true; }
+      // range gate
+      const float d2 = x * x + y * y;
+      bool in_range;
+      if (d2 > lo2_in && d2 < hi2_in) in_range = true;
+      else if (d2 < lo2_out || d2 > hi2_out) in_range = false;
+      else { const float dist = hypot_ref(x, y); in_range = dist > min_d && dist < max_d; }
+      if (in_range && v[u].w > best) { best = v[u].w; best_i = b; }       // ascending b per thread: first-wins inside the thread
+    }
   }
   __shared__ float s_val[kRowThreads];
   __shared__ uint32_t s_idx[kRowThreads];

@@ -70,3 +70,32 @@ def test_filter_then_voxelize_equals_oracle_chain(oracle, gpu_ctx):
     v = oracle.voxelize(want_pts, *H.vox_args(p))
     assert len(v["cells"]) > 30
     assert np.array_equal(m["cells"].view(np.uint32), v["cells"].view(np.uint32))
+
+
+def test_filter_scan_threshold_bands_take_the_exact_path(oracle, gpu_ctx):
+    """returns within a few ulp of min_range / max_range and azimuth deviations between the kernel's fast bound (0.45e-4 rad) and the
+    reference's 1e-4 rad cut must be decided exactly like the reference decides them"""
+    p = P.OXFORD
+    n_az, n_bins = 48, 256
+    raw = synth.make_raw_scan(synth.scene_for(p, 8), (0, 0, 0), p, 8, n_azimuth=n_az, n_bins=n_bins, bin_size=0.5).reshape(n_az, n_bins, 4)
+    rng = np.random.default_rng(0)
+    for row in range(2, 40, 3):
+        az = math.atan2(float(raw[row, 10, 1]), float(raw[row, 10, 0]))
+        for j, lim in enumerate((p.min_range, p.max_range)):
+            for k in range(6):               # ranges lim * (1 + {-3..2} * 6e-8): float neighbours of the limit
+                r = np.float32(lim) * np.float32(1.0 + (k - 3) * 6e-8)
+                b = 20 + 8 * j + k
+                raw[row, b, 0] = np.float32(r * math.cos(az)); raw[row, b, 1] = np.float32(r * math.sin(az)); raw[row, b, 3] = 200.0 + k
+        # an azimuth wobble of 0.7e-4 rad: above the fast bound, below the reference's cut -> must not split the row
+        r = 30.0
+        raw[row, 100, 0] = np.float32(r * math.cos(az + 0.7e-4)); raw[row, 100, 1] = np.float32(r * math.sin(az + 0.7e-4))
+    flat = raw.reshape(-1, 4)
+    want, _ = oracle_filter(oracle, flat, p)
+    got = gpu_ctx.filter_scan(flat, n_az, n_bins, capi.filter_params(p))
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    # a wobble of 1.3e-4 rad does split the row in the reference: rejected
+    raw[5, 100, 0] = np.float32(30.0 * math.cos(math.atan2(float(raw[5, 10, 1]), float(raw[5, 10, 0])) + 1.3e-4))
+    raw[5, 100, 1] = np.float32(30.0 * math.sin(math.atan2(float(raw[5, 10, 1]), float(raw[5, 10, 0])) + 1.3e-4))
+    with pytest.raises(capi.RandtError) as e:
+        gpu_ctx.filter_scan(raw.reshape(-1, 4), n_az, n_bins, capi.filter_params(p))
+    assert e.value.code == capi.E_INVALID
