@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <memory>
 #include <new>
 #include <queue>
 #include <utility>
@@ -15,10 +16,30 @@
 
 using namespace randt;
 
+// The stream of a context, shared with the maps and problems created on it: an owned stream outlives its context for as long as such
+// objects exist, so that their destroy functions can release device memory in stream order (cudaFreeAsync) instead of through the
+// device-wide synchronisation of cudaFree.  Also carries the small pinned/event resources the batched solver polls with.
+struct StreamRef {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own = false;
+  uint32_t* h_n_active = nullptr;            // pinned [2]
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  ~StreamRef() {
+    cudaSetDevice(device);
+    if (own && stream) cudaStreamSynchronize(stream);
+    if (h_n_active) cudaFreeHost(h_n_active);
+    if (ev[0]) cudaEventDestroy(ev[0]);
+    if (ev[1]) cudaEventDestroy(ev[1]);
+    if (own && stream) cudaStreamDestroy(stream);
+  }
+};
+
 struct randt_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  std::shared_ptr<StreamRef> sref;
   std::string err;
   uint64_t launches = 0;
   unsigned long long* d_bad = nullptr;   // count of degenerate pairs seen by K3
@@ -26,6 +47,7 @@ struct randt_ctx {
 
 struct randt_map {
   int device = 0;
+  std::shared_ptr<StreamRef> sref;   // stream of the creating context
   randt_grid_params gp{};
   MapGeomDev geom{};
   uint32_t B = 0, n_cells = 0, max_per_map = 0;
@@ -39,6 +61,7 @@ struct randt_map {
 
 struct randt_problem {
   int device = 0;
+  std::shared_ptr<StreamRef> sref;   // stream of the creating context
   uint32_t S = 0, P = 0, n_m = 0, n_f = 0;
   float4 *cells_m = nullptr, *cells_f = nullptr;
   uint2* pairs = nullptr;
@@ -62,8 +85,6 @@ struct randt_problem {
   LmState* lm_state = nullptr; double *lm_eval_pose = nullptr, *lm_mu = nullptr, *lm_rec = nullptr, *lm_poses = nullptr, *lm_result = nullptr;
   uint32_t *lm_active = nullptr, *lm_n_active = nullptr;
   ChunkDesc* lm_chunks = nullptr; uint32_t *lm_flags = nullptr, *lm_scan = nullptr, *lm_bs = nullptr, *lm_warp_off = nullptr;   // re-planned schedule
-  uint32_t* h_n_active = nullptr;   // pinned [2]
-  cudaEvent_t lm_ev[2] = {nullptr, nullptr};
 };
 
 namespace {
@@ -123,9 +144,6 @@ void free_problem(randt_problem* p) {
   dev_free(p->lm_state); dev_free(p->lm_eval_pose); dev_free(p->lm_mu); dev_free(p->lm_rec); dev_free(p->lm_poses); dev_free(p->lm_result);
   dev_free(p->lm_active); dev_free(p->lm_n_active);
   dev_free(p->lm_chunks); dev_free(p->lm_flags); dev_free(p->lm_scan); dev_free(p->lm_bs); dev_free(p->lm_warp_off);
-  if (p->h_n_active) cudaFreeHost(p->h_n_active);
-  if (p->lm_ev[0]) cudaEventDestroy(p->lm_ev[0]);
-  if (p->lm_ev[1]) cudaEventDestroy(p->lm_ev[1]);
   delete p;
 }
 
@@ -303,6 +321,10 @@ int randt_ctx_create(int device, void* stream, randt_ctx** out) {
   if (e == cudaSuccess) {
     if (stream) { ctx->stream = (cudaStream_t)stream; ctx->own_stream = false; }
     else { e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking); ctx->own_stream = true; }
+    if (e == cudaSuccess) {
+      ctx->sref = std::make_shared<StreamRef>();
+      ctx->sref->device = device; ctx->sref->stream = ctx->stream; ctx->sref->own = ctx->own_stream;
+    }
   }
   if (e == cudaSuccess) {
     cudaMemPool_t pool;
@@ -323,8 +345,7 @@ void randt_ctx_destroy(randt_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   dev_free(ctx->d_bad);
-  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
-  delete ctx;
+  delete ctx;      // the stream itself goes with the last object that was created on this context (StreamRef)
 }
 
 const char* randt_last_error(const randt_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
@@ -370,7 +391,7 @@ int randt_voxelize(randt_ctx* ctx, const float* pts4, const uint32_t* scan_off, 
   const uint32_t cell_cap = std::max<uint32_t>(1, max_pts / div);   // a kept cell has > min_points points
   randt_map* m = new (std::nothrow) randt_map();
   if (!m) return RANDT_E_NOMEM;
-  m->device = ctx->device; m->gp = *gp; m->geom = make_geom(*gp); m->B = B;
+  m->device = ctx->device; m->sref = ctx->sref; m->gp = *gp; m->geom = make_geom(*gp); m->B = B;
   float4* d_pts = nullptr; bool own_pts = false;
   uint32_t *d_scan_off = nullptr, *d_cnt = nullptr, *d_order = nullptr, *d_npts_p = nullptr;
   int32_t *d_labels_scratch = nullptr, *d_labels_p = nullptr; float4* d_cells_p = nullptr; int* d_status = nullptr;
@@ -468,7 +489,7 @@ int randt_map_upload(randt_ctx* ctx, const float* cells, const uint32_t* npts, c
   StreamScope scope__(ctx->stream);
   randt_map* m = new (std::nothrow) randt_map();
   if (!m) return RANDT_E_NOMEM;
-  m->device = ctx->device; m->gp = *gp; m->geom = make_geom(*gp); m->B = n_maps;
+  m->device = ctx->device; m->sref = ctx->sref; m->gp = *gp; m->geom = make_geom(*gp); m->B = n_maps;
   m->h_cell_off.assign(cell_off, cell_off + n_maps + 1);
   for (uint32_t b = 0; b < n_maps; ++b) {
     if (cell_off[b + 1] < cell_off[b]) { free_map(m); return fail(ctx, RANDT_E_INVALID, "cell_off not monotone"); }
@@ -593,7 +614,13 @@ int randt_cs_divergence(randt_ctx* ctx, const randt_map* F, const randt_map* M, 
   return RANDT_OK;
 }
 
-void randt_map_destroy(randt_map* m) { if (m) { cudaSetDevice(m->device); free_map(m); } }
+void randt_map_destroy(randt_map* m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  std::shared_ptr<StreamRef> sr = m->sref;      // keeps the stream alive until the frees are queued
+  if (sr && sr->own) { StreamScope scope__(sr->stream); free_map(m); }
+  else free_map(m);                             // borrowed stream (may be gone by now): cudaFree
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // K2
@@ -613,7 +640,7 @@ int randt_associate(randt_ctx* ctx, const randt_map* F, const randt_map* M, cons
   const uint32_t B = F->B, n_m = M->n_cells;
   randt_problem* p = new (std::nothrow) randt_problem();
   if (!p) return RANDT_E_NOMEM;
-  p->device = ctx->device; p->S = B; p->n_m = n_m; p->n_f = F->n_cells;
+  p->device = ctx->device; p->sref = ctx->sref; p->S = B; p->n_m = n_m; p->n_f = F->n_cells;
   float4* d_pose = nullptr; uint32_t *d_nn = nullptr, *d_cnt = nullptr, *d_scan = nullptr, *d_bs = nullptr, *d_cnt2 = nullptr, *d_scan2 = nullptr;
   int rc = RANDT_OK; int nl = 0;
   auto cleanup = [&]() { dev_free(d_pose); dev_free(d_nn); dev_free(d_cnt); dev_free(d_scan); dev_free(d_bs); dev_free(d_cnt2); dev_free(d_scan2); };
@@ -673,7 +700,7 @@ int randt_problem_create(randt_ctx* ctx, const float* cells_m, uint32_t n_m, con
   StreamScope scope__(ctx->stream);
   randt_problem* p = new (std::nothrow) randt_problem();
   if (!p) return RANDT_E_NOMEM;
-  p->device = ctx->device; p->S = n_segments; p->P = n_pairs; p->n_m = n_m; p->n_f = n_f;
+  p->device = ctx->device; p->sref = ctx->sref; p->S = n_segments; p->P = n_pairs; p->n_m = n_m; p->n_f = n_f;
   p->h_seg_off.assign(seg_off, seg_off + n_segments + 1);
   std::vector<uint2> h_pairs(n_pairs);
   for (uint32_t i = 0; i < n_pairs; ++i) h_pairs[i] = make_uint2(pair_m[i], pair_f[i]);
@@ -739,7 +766,13 @@ int randt_problem_download_cells(randt_ctx* ctx, const randt_problem* p, float* 
   return RANDT_OK;
 }
 
-void randt_problem_destroy(randt_problem* p) { if (p) { cudaSetDevice(p->device); free_problem(p); } }
+void randt_problem_destroy(randt_problem* p) {
+  if (!p) return;
+  cudaSetDevice(p->device);
+  std::shared_ptr<StreamRef> sr = p->sref;
+  if (sr && sr->own) { StreamScope scope__(sr->stream); free_problem(p); }
+  else free_problem(p);
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // K3
@@ -873,10 +906,13 @@ int randt_register_batch_dev(randt_ctx* ctx, const randt_problem* cp, int varian
   if (!p->lm_state) {
     CK(dev_alloc(&p->lm_state, S)); CK(dev_alloc(&p->lm_eval_pose, (size_t)S * 4)); CK(dev_alloc(&p->lm_mu, S));
     CK(dev_alloc(&p->lm_rec, (size_t)S * RANDT_FUSED_STRIDE)); CK(dev_alloc(&p->lm_active, S)); CK(dev_alloc(&p->lm_n_active, 1));
-    CK(cudaHostAlloc(reinterpret_cast<void**>(&p->h_n_active), 2 * sizeof(uint32_t), cudaHostAllocDefault));
-    CK(cudaEventCreateWithFlags(&p->lm_ev[0], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&p->lm_ev[1], cudaEventDisableTiming));
     CK(dev_alloc(&p->lm_chunks, p->n_chunks)); CK(dev_alloc(&p->lm_flags, p->n_chunks)); CK(dev_alloc(&p->lm_scan, (size_t)p->n_chunks + 1));
     CK(dev_alloc(&p->lm_bs, p->n_chunks / 1024 + 2)); CK(dev_alloc(&p->lm_warp_off, (size_t)p->n_warps + 1));
+  }
+  StreamRef& sr = *ctx->sref;
+  if (!sr.h_n_active) {
+    CK(cudaHostAlloc(reinterpret_cast<void**>(&sr.h_n_active), 2 * sizeof(uint32_t), cudaHostAllocDefault));
+    CK(cudaEventCreateWithFlags(&sr.ev[0], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&sr.ev[1], cudaEventDisableTiming));
   }
   int nl = 0;
   CK(launch_lm_init(S, np, d_poses, p->lm_state, p->lm_eval_pose, p->lm_mu, p->lm_active, p->lm_rec, p->lm_n_active, ctx->stream, &nl));
@@ -896,11 +932,11 @@ int randt_register_batch_dev(randt_ctx* ctx, const randt_problem* cp, int varian
       CK(launch_lm_step(S, np, opt->use_manifold, *opt, p->lm_rec, p->lm_state, p->lm_eval_pose, p->lm_mu, p->lm_active, p->lm_n_active, d_poses,
                         d_result, ctx->stream, &nl));
     }
-    CK(cudaMemcpyAsync(&p->h_n_active[g & 1], p->lm_n_active, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaEventRecord(p->lm_ev[g & 1], ctx->stream));
+    CK(cudaMemcpyAsync(&sr.h_n_active[g & 1], p->lm_n_active, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaEventRecord(sr.ev[g & 1], ctx->stream));
     if (g >= 1) {
-      CK(cudaEventSynchronize(p->lm_ev[(g - 1) & 1]));
-      const uint32_t n_act = p->h_n_active[(g - 1) & 1];
+      CK(cudaEventSynchronize(sr.ev[(g - 1) & 1]));
+      const uint32_t n_act = sr.h_n_active[(g - 1) & 1];
       done = n_act == 0u;
       if (getenv("RANDT_DEBUG_SOLVER")) fprintf(stderr, "[randt solver] group %lld (iterations <= %lld): %u active\n", g - 1, g * poll, n_act);
       // finished segments leave holes K3 has to step over: compact the schedule once a quarter of its segments are gone
@@ -913,7 +949,7 @@ int randt_register_batch_dev(randt_ctx* ctx, const randt_problem* cp, int varian
     }
   }
   CK(cudaStreamSynchronize(ctx->stream));
-  if (!done) done = p->h_n_active[(n_groups - 1) & 1] == 0u;
+  if (!done) done = sr.h_n_active[(n_groups - 1) & 1] == 0u;
   ctx->launches += nl;
   if (!done) return fail(ctx, RANDT_E_NONFINITE, "randt_register_batch: iteration cap reached with active segments (non-finite evaluations?)");
   return RANDT_OK;
