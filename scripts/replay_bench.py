@@ -1,9 +1,9 @@
 #!/usr/bin/env python
 """Sequence replay (BASELINE configs[4]): R independent synthetic drives processed scan by scan, in lockstep, through the device path —
-K6 peak filter (optional, --raw) -> K1 voxelise -> K2 associate against each drive's growing submap -> K3 + K4 registration (manifold
+K1 voxelise -> K2 associate against each drive's growing submap -> K3 + K4 registration (manifold
 mode, odometry loss ScaledLoss(Barron(a, alpha, mu), ndt_weight / (n_cells k)), gnc_steps of the preset) -> keyframe insertion every
-second scan (transform + merge).  A single drive (R = 1) is a chain of tiny dependent launches — latency-bound, the GPU cannot beat
-a CPU core there ("replicas only"); R drives in lockstep turn every step into one batched call.
+second scan (transform + merge).  A single drive (R = 1) is a chain of tiny dependent launches — latency-bound, about one CPU core's
+worth ("replicas only"); R drives in lockstep turn every step into one batched call.
 Prints one JSON line with scans/s for the device path and for the same chain on the CPU oracle (one host thread, a bounded sample).
 usage: python scripts/replay_bench.py [--replicas 256] [--scans 24]"""
 import argparse
@@ -99,12 +99,17 @@ def main():
             drives = [pool[j % args.pool] for j in range(R)]
             device_replay(ctx, p, drives, min(args.scans, 6))          # warm-up (pool allocations, first launches)
             poses, dt, its = device_replay(ctx, p, drives, args.scans)
-            err = max(abs(poses[j, 2] - drives[j][0][-1][0]) + abs(poses[j, 3] - drives[j][0][-1][1]) for j in range(R))
+            err = np.array([math.hypot(poses[j, 2] - drives[j][0][-1][0], poses[j, 3] - drives[j][0][-1][1]) for j in range(R)])
             out["device_R%d" % R] = {"replicas": R, "scans_per_s": R * (args.scans - 1) / dt, "ms_per_step": dt * 1e3 / (args.scans - 1),
-                                     "mean_lm_iterations_per_scan": its, "max_final_position_error_m": float(err)}
+                                     "mean_lm_iterations_per_scan": its, "median_final_position_error_m": float(np.median(err)),
+                                     "drives_within_0.5m": int((err < 0.5).sum())}
+            if R == 1:
+                pose_r1 = poses[0].copy()
     po, dto = oracle_replay(p, pool[0], args.scans)
     out["oracle_1thread"] = {"scans_per_s": (args.scans - 1) / dto, "ms_per_scan": dto * 1e3 / (args.scans - 1),
-                             "final_pose_vs_device_R1": None}
+                             "max_abs_pose_difference_vs_device_R1": float(np.max(np.abs(po - pose_r1)))}
+    out["note"] = ("NDT-only odometry without the reference's motion-model / IMU factors and pose-rejection gate (host side, out of scope): a drive "
+                   "whose synthetic scene offers too little structure may lose track; that is counted, not hidden")
     out["sensor_rate_hz"] = 4.02
     print(json.dumps(out))
 
