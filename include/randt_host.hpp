@@ -133,6 +133,11 @@ class Map {
   // Map::getCellMeanAndCovariance (ndt_map.h:112-119): mean[3], row-major cov[9]; cached host copy, refreshed after mutation
   bool getCellMeanAndCovariance(size_t idx, float* mean3, float* cov9) const;
   const std::vector<uint32_t>& cellOffsets() const;  // [B+1]
+  // The wire format of an NDT cell (ndt_msgs/Mean + ndt_msgs/Covariance, ros/ndt_msgs/msg/{Mean,Covariance}.msg) as
+  // NDTSlam::createVisualizationMsg fills it (R/src/ndt_slam/ndt_slam.cpp:370-393): per cell float64 (x, y, i) and
+  // (xx, xy, xi, yy, yi, ii) — the upper triangle of the float32 covariance.  mean_intensity (a per-cluster maximum kept only for
+  // rviz) is not produced by this path.
+  void exportNormalDistributions(std::vector<double>& mean_xyi, std::vector<double>& cov_xx_xy_xi_yy_yi_ii) const;
   randt_map* handle() const { return map_; }
   Context& context() const { return *ctx_; }
   const NDTMapParameters& parameters() const { return p_; }
@@ -215,5 +220,7 @@ RANDT_API int randt_hostapi_bnb(int device, const randt_grid_params* gp, const f
                                 uint32_t n_moving, double convexity, double scale, double window_linear, double window_angular,
                                 double linear_step, double max_px_range, double cost_threshold, int n_iter, double* pose_io4, double* min_cost,
                                 uint32_t* n_evaluated);
+RANDT_API int randt_hostapi_export(int device, const randt_grid_params* gp, const float* pts4, uint32_t n_pts, double* mean3 /*[cap][3]*/,
+                                   double* cov6 /*[cap][6]*/, uint32_t cap, uint32_t* n_cells);
 RANDT_API const char* randt_hostapi_last_error(void);
 }

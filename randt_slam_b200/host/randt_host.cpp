@@ -104,6 +104,17 @@ bool Map::getCellMeanAndCovariance(size_t idx, float* mean3, float* cov9) const 
   return true;
 }
 const std::vector<uint32_t>& Map::cellOffsets() const { sync_host(); return h_off_; }
+void Map::exportNormalDistributions(std::vector<double>& mean, std::vector<double>& cov) const {
+  sync_host();
+  const size_t n = h_cells_.size() / 12;
+  mean.resize(3 * n); cov.resize(6 * n);
+  for (size_t i = 0; i < n; ++i) {
+    const float* c = &h_cells_[12 * i];
+    mean[3 * i] = c[0]; mean[3 * i + 1] = c[1]; mean[3 * i + 2] = c[2];
+    cov[6 * i] = c[3]; cov[6 * i + 1] = c[4]; cov[6 * i + 2] = c[5];            // cov(0,0), cov(0,1), cov(0,2)
+    cov[6 * i + 3] = c[7]; cov[6 * i + 4] = c[8]; cov[6 * i + 5] = c[11];       // cov(1,1), cov(1,2), cov(2,2)
+  }
+}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // NdtCostFunction
@@ -401,6 +412,22 @@ int randt_hostapi_cost_function(int device, const randt_grid_params* gp, const f
     double* jac[1] = {jacobian};
     if (!base->Evaluate(params, residuals, jacobian ? jac : nullptr)) throw randt::Error(RANDT_E_NONFINITE, "Evaluate returned false");
     if (max_raw) *max_raw = cf->maxRawResidual(pose4);
+  });
+}
+
+int randt_hostapi_export(int device, const randt_grid_params* gp, const float* pts4, uint32_t n_pts, double* mean3, double* cov6, uint32_t cap,
+                         uint32_t* n_cells) {
+  return guarded([&] {
+    randt::Context ctx(device);
+    randt::Map map(ctx, map_params(*gp));
+    const uint32_t off[2] = {0, n_pts};
+    map.addClusters(pts4, off, 1);
+    std::vector<double> m, c;
+    map.exportNormalDistributions(m, c);
+    *n_cells = (uint32_t)(m.size() / 3);
+    if (*n_cells > cap) throw randt::Error(RANDT_E_CAPACITY, "export buffer too small");
+    std::memcpy(mean3, m.data(), m.size() * sizeof(double));
+    std::memcpy(cov6, c.data(), c.size() * sizeof(double));
   });
 }
 

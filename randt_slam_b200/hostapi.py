@@ -19,7 +19,7 @@ def lib():
         capi.lib()   # librandt_gpu.so first (the host library links against it)
         L = C.CDLL(LIB_PATH)
         L.randt_hostapi_last_error.restype = C.c_char_p
-        for name in ("randt_hostapi_loop_constraints", "randt_hostapi_cost_function", "randt_hostapi_bnb"):
+        for name in ("randt_hostapi_loop_constraints", "randt_hostapi_cost_function", "randt_hostapi_bnb", "randt_hostapi_export"):
             getattr(L, name).restype = C.c_int
         _lib = L
     return _lib
@@ -71,3 +71,12 @@ def bnb(gp, fixed_pts, moving_pts, pose, convexity, scale, window_linear=4.5, wi
                                    C.c_double(scale), C.c_double(window_linear), C.c_double(window_angular), C.c_double(linear_step),
                                    C.c_double(max_px_range), C.c_double(cost_threshold), C.c_int(n_iter), _pf(pose), C.byref(mc), C.byref(ne)))
     return pose, mc.value, ne.value
+
+
+def export_normal_distributions(gp, pts, device=0):
+    """Map::addClusters + the ndt_msgs Mean/Covariance export -> (mean [n,3], cov [n,6]) float64"""
+    pts = np.ascontiguousarray(pts, np.float32)
+    cap = max(16, len(pts))
+    mean = np.zeros((cap, 3)); cov = np.zeros((cap, 6)); n = C.c_uint32(0)
+    _check(lib().randt_hostapi_export(C.c_int(device), C.byref(gp), _pf(pts), C.c_uint32(len(pts)), _pf(mean), _pf(cov), C.c_uint32(cap), C.byref(n)))
+    return mean[: n.value].copy(), cov[: n.value].copy()

@@ -92,3 +92,15 @@ def test_host_layer_reports_errors(oracle):
     pts = np.zeros((50, 4), np.float32); pts[:, 0] = 1e6; pts[:25, 0] = -1e6; pts[:, 3] = 90
     with pytest.raises(capi.RandtError):
         hostapi.loop_constraints(gp, [pts], [pts], [synth.pose_to_se2(0, 0, 0)], 2, 1.0, -2.0, 1.1, 2, 0.5)
+
+
+def test_export_normal_distributions_wire_format(oracle):
+    """ndt_msgs Mean (x, y, i) + Covariance (xx, xy, xi, yy, yi, ii) as NDTSlam::createVisualizationMsg fills them (ndt_slam.cpp:370-393)"""
+    p = P.OXFORD
+    pts = H.make_scan(p, 80, (0.0, 0.0, 0.0), 7)
+    mean, cov = hostapi.export_normal_distributions(capi.grid_params(p), pts)
+    v = oracle.voxelize(pts, *H.vox_args(p))["cells"]
+    assert mean.shape == (len(v), 3) and cov.shape == (len(v), 6)
+    assert np.array_equal(mean, v[:, :3].astype(np.float64))
+    c = v[:, 3:].reshape(-1, 3, 3).astype(np.float64)
+    assert np.array_equal(cov, np.stack([c[:, 0, 0], c[:, 0, 1], c[:, 0, 2], c[:, 1, 1], c[:, 1, 2], c[:, 2, 2]], 1))
