@@ -197,6 +197,12 @@ RANDT_API int randt_eval_emit_dev(randt_ctx* ctx, const randt_problem* p, int va
  * overrides loss->mu per segment.  want_jac == 0 computes cost/max/sumsq only (trust-region candidate evaluation, BnB sweep). */
 RANDT_API int randt_eval_fused(randt_ctx* ctx, const randt_problem* p, int variant, const double* poses, const randt_loss* loss,
                                const double* mu_per_seg, int want_jac, double* out);
+/* Enqueue-only form for a caller that scores one pose set after another (the BnB levels of ndt_matcher.cpp:560-576, pose grids):
+ * poses, mu_per_seg and out must be pinned host memory (randt_host_alloc); the upload of call i+1 and the copy-out of call i-1 overlap
+ * the kernel of call i (two copy streams, two device slots each way).  The buffers of a call may be read / reused after
+ * randt_ctx_sync(), or once call i+2 has left the context's stream; give the calls in flight their own buffers. */
+RANDT_API int randt_eval_fused_async(randt_ctx* ctx, const randt_problem* p, int variant, const double* poses, const randt_loss* loss,
+                                     const double* mu_per_seg, int want_jac, double* out);
 RANDT_API int randt_eval_fused_dev(randt_ctx* ctx, const randt_problem* p, int variant, const double* d_poses, const randt_loss* loss,
                                    const double* d_mu_per_seg, int want_jac, double* d_out);
 /* Cost of ONE segment's pair list at many candidate poses (the inner loop of Matcher::estimateTransformGlobalBNB,

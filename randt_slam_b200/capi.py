@@ -111,6 +111,7 @@ _SIGS = {
     "randt_eval_emit": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "randt_eval_emit_dev": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "randt_eval_fused": (_i, [_vp, _vp, _i, _vp, C.POINTER(Loss), _vp, _i, _vp]),
+    "randt_eval_fused_async": (_i, [_vp, _vp, _i, _vp, C.POINTER(Loss), _vp, _i, _vp]),
     "randt_eval_fused_dev": (_i, [_vp, _vp, _i, _vp, C.POINTER(Loss), _vp, _i, _vp]),
     "randt_sweep_costs": (_i, [_vp, _vp, _u32, _i, _vp, _u32, C.POINTER(Loss), _vp]),
     "randt_solver_options_default": (None, [_vp]),
@@ -343,6 +344,16 @@ class Problem:
         self.ctx._check(lib().randt_eval_fused(self.ctx._h, self._h, int(variant), _ptr(poses), lp, _ptr(mu), int(want_jac), _ptr(out)))
         return out
 
+    def eval_fused_async(self, poses, out, loss=None, mu_per_seg=None, want_jac=True, variant=VAR_SE2_INTENSITY):
+        """enqueue-only evaluation: `poses`, `mu_per_seg` and `out` are float64 arrays in pinned host memory (pinned_array);
+        valid after Context.sync()"""
+        for a in (poses, out, mu_per_seg):
+            if a is not None and not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous):
+                raise TypeError("eval_fused_async needs C-contiguous float64 arrays")
+        lp = C.byref(loss) if loss is not None else None
+        self.ctx._check(lib().randt_eval_fused_async(self.ctx._h, self._h, int(variant), _ptr(poses), lp, _ptr(mu_per_seg), int(want_jac),
+                                                     _ptr(out)))
+
     def eval_fused_dev(self, d_poses, d_out, loss=None, d_mu=None, want_jac=True, variant=VAR_SE2_INTENSITY):
         lp = C.byref(loss) if loss is not None else None
         self.ctx._check(lib().randt_eval_fused_dev(self.ctx._h, self._h, int(variant), _ptr(d_poses), lp, _ptr(d_mu), int(want_jac),
@@ -377,3 +388,26 @@ def unpack_fused(o):
     o = np.asarray(o)
     return dict(H=o[..., :16].reshape(o.shape[:-1] + (4, 4)), g=o[..., 16:20], cost=o[..., 20], max_r=o[..., 21], sum_sq=o[..., 22],
                 n=o[..., 23])
+
+
+class PinnedArray:
+    """float64 array in pinned host memory from randt_host_alloc (what the *_async entry points take); .a is the numpy view"""
+
+    def __init__(self, shape):
+        n = int(np.prod(shape))
+        self._p = lib().randt_host_alloc(C.c_size_t(max(8, 8 * n)))
+        if not self._p:
+            raise MemoryError("randt_host_alloc failed")
+        self.a = np.ctypeslib.as_array((C.c_double * n).from_address(self._p)).reshape(shape)
+        self.a[...] = 0.0
+
+    def close(self):
+        if self._p:
+            self.a = None
+            lib().randt_host_free(C.c_void_p(self._p)); self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -25,9 +25,26 @@ struct StreamRef {
   bool own = false;
   uint32_t* h_n_active = nullptr;            // pinned [2]
   cudaEvent_t ev[2] = {nullptr, nullptr};
+  // input pipeline of randt_eval_fused_async: a copy stream and a two-slot device ring for the poses of the calls in flight
+  cudaStream_t copy = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  double* ring[2] = {nullptr, nullptr}; size_t ring_cap[2] = {0, 0}; uint64_t ring_n = 0;
+  cudaStream_t copy_out = nullptr; cudaEvent_t ev_d2h[2] = {nullptr, nullptr};
+  double* oring[2] = {nullptr, nullptr}; size_t oring_cap[2] = {0, 0};
   ~StreamRef() {
     cudaSetDevice(device);
+    if (copy) cudaStreamSynchronize(copy);
+    if (copy_out) cudaStreamSynchronize(copy_out);
     if (own && stream) cudaStreamSynchronize(stream);
+    for (int i = 0; i < 2; ++i) {
+      if (ev_d2h[i]) cudaEventDestroy(ev_d2h[i]);
+      if (oring[i]) cudaFree(oring[i]);
+      if (ev_in[i]) cudaEventDestroy(ev_in[i]);
+      if (ev_done[i]) cudaEventDestroy(ev_done[i]);
+      if (ring[i]) cudaFree(ring[i]);
+    }
+    if (copy) cudaStreamDestroy(copy);
+    if (copy_out) cudaStreamDestroy(copy_out);
     if (h_n_active) cudaFreeHost(h_n_active);
     if (ev[0]) cudaEventDestroy(ev[0]);
     if (ev[1]) cudaEventDestroy(ev[1]);
@@ -350,7 +367,12 @@ void randt_ctx_destroy(randt_ctx* ctx) {
 
 const char* randt_last_error(const randt_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 void* randt_ctx_stream(const randt_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
-int randt_ctx_sync(randt_ctx* ctx) { if (!ctx) return RANDT_E_INVALID; CK(cudaStreamSynchronize(ctx->stream)); return RANDT_OK; }
+int randt_ctx_sync(randt_ctx* ctx) {
+  if (!ctx) return RANDT_E_INVALID;
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->sref && ctx->sref->copy_out) CK(cudaStreamSynchronize(ctx->sref->copy_out));
+  return RANDT_OK;
+}
 uint64_t randt_ctx_launch_count(const randt_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 void* randt_host_alloc(size_t bytes) { void* p = nullptr; return cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess ? p : nullptr; }
@@ -847,6 +869,72 @@ int randt_eval_fused(randt_ctx* ctx, const randt_problem* cp, int variant, const
   if (rc) return rc;
   if (p->S && !direct) CK(cudaMemcpyAsync(out, p->d_out, (size_t)p->S * RANDT_FUSED_STRIDE * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  return RANDT_OK;
+}
+
+// Pipelined form of randt_eval_fused for callers that evaluate one pose set after another (BnB levels, pose-grid scoring): the call
+// only enqueues.  The poses travel on a copy stream into one of two device slots, so that the upload of call i+1 overlaps the
+// kernel of call i, and the records of call i leave on a third stream while the kernel of call i+1 runs.  randt_ctx_sync() orders the
+// host with all results; short of that, the records of call i are in host memory once call i+2 has left the context's stream.
+int randt_eval_fused_async(randt_ctx* ctx, const randt_problem* cp, int variant, const double* poses, const randt_loss* loss,
+                           const double* mu_per_seg, int want_jac, double* out) {
+  if (!ctx || !cp || !poses || !out) return fail(ctx, RANDT_E_INVALID, "randt_eval_fused_async: null argument");
+  if (check_variant(ctx, variant)) return RANDT_E_INVALID;
+  randt_problem* p = const_cast<randt_problem*>(cp);
+  CK(cudaSetDevice(ctx->device));
+  auto pinned_dev_ptr = [](const void* h) -> void* {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, h) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) return at.devicePointer;
+    cudaGetLastError();
+    return nullptr;
+  };
+  double* out_dev = static_cast<double*>(pinned_dev_ptr(out));
+  if (!out_dev || !pinned_dev_ptr(poses) || (mu_per_seg && !pinned_dev_ptr(mu_per_seg)))
+    return fail(ctx, RANDT_E_INVALID, "randt_eval_fused_async: poses, mu_per_seg and out must be pinned host memory (randt_host_alloc)");
+  if (p->S == 0) return RANDT_OK;
+  StreamRef& r = *ctx->sref;
+  if (!r.copy) {
+    CK(cudaStreamCreateWithFlags(&r.copy, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&r.copy_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CK(cudaEventCreateWithFlags(&r.ev_in[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&r.ev_done[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&r.ev_d2h[i], cudaEventDisableTiming));
+    }
+  }
+  const int np = np_of(variant);
+  const int slot = (int)(r.ring_n++ & 1);
+  const size_t n_pose = (size_t)p->S * np, need = n_pose + (mu_per_seg ? p->S : 0);
+  // the slot is free once the kernel that read it two calls ago has finished
+  CK(cudaStreamWaitEvent(r.copy, r.ev_done[slot], 0));
+  if (r.ring_cap[slot] < need) {
+    if (r.ring[slot]) CK(cudaFreeAsync(r.ring[slot], r.copy));
+    r.ring[slot] = nullptr; r.ring_cap[slot] = 0;
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&r.ring[slot]), need * sizeof(double), r.copy));
+    r.ring_cap[slot] = need;
+  }
+  double* d_in = r.ring[slot];
+  CK(cudaMemcpyAsync(d_in, poses, n_pose * sizeof(double), cudaMemcpyHostToDevice, r.copy));
+  if (mu_per_seg) CK(cudaMemcpyAsync(d_in + n_pose, mu_per_seg, (size_t)p->S * sizeof(double), cudaMemcpyHostToDevice, r.copy));
+  CK(cudaEventRecord(r.ev_in[slot], r.copy));
+  CK(cudaStreamWaitEvent(ctx->stream, r.ev_in[slot], 0));
+  // Records go to a device slot and leave on a third stream: a DMA copy moves the 192 S bytes at the full PCIe rate while the next
+  // call's kernel runs (stores from the kernel straight into mapped host memory, as the blocking call does, reach ~3/4 of that rate).
+  const size_t n_out = (size_t)p->S * RANDT_FUSED_STRIDE;
+  CK(cudaStreamWaitEvent(ctx->stream, r.ev_d2h[slot], 0));     // the copy-out of two calls ago has drained this slot
+  if (r.oring_cap[slot] < n_out) {
+    if (r.oring[slot]) CK(cudaFreeAsync(r.oring[slot], ctx->stream));
+    r.oring[slot] = nullptr; r.oring_cap[slot] = 0;
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&r.oring[slot]), n_out * sizeof(double), ctx->stream));
+    r.oring_cap[slot] = n_out;
+  }
+  double* d_out = r.oring[slot];
+  int rc = randt_eval_fused_dev(ctx, p, variant, d_in, loss, mu_per_seg ? d_in + n_pose : nullptr, want_jac, d_out);
+  if (rc) return rc;
+  CK(cudaEventRecord(r.ev_done[slot], ctx->stream));
+  CK(cudaStreamWaitEvent(r.copy_out, r.ev_done[slot], 0));
+  CK(cudaMemcpyAsync(out, d_out, n_out * sizeof(double), cudaMemcpyDeviceToHost, r.copy_out));
+  CK(cudaEventRecord(r.ev_d2h[slot], r.copy_out));             // randt_ctx_sync() waits for the copy-out stream as well
   return RANDT_OK;
 }
 

@@ -193,6 +193,41 @@ def test_fused_writes_directly_into_pinned_host_memory(oracle, gpu_ctx):
         capi.lib().randt_host_free(ptr)
 
 
+@pytest.mark.parametrize("with_empty", [False, True])
+def test_fused_async_pipeline_matches_the_blocking_call(oracle, gpu_ctx, with_empty):
+    """randt_eval_fused_async: six calls in flight over a two-slot input ring, each with its own poses / mu and result buffer; results
+    equal the blocking call bit for bit (direct pinned stores without empty segments, staged copy with one), and pageable buffers
+    are rejected"""
+    case = H.make_registration_case(oracle, P.OXFORD, seed=12)
+    cm, cf, im, jf = case["moving"]["cells"], case["fixed"]["cells"], case["im"], case["jf"]
+    n = len(im)
+    seg = [0, n // 5, n // 5, n // 2, n] if with_empty else [0, n // 5, n // 3, n // 2, n]
+    S = len(seg) - 1
+    prob = gpu_ctx.problem_create(cm, cf, im, jf, seg)
+    loss = capi.make_loss(capi.LOSS_BARRON, 1.0, -2.0, 1.0, 0.5)
+    rng = np.random.default_rng(5)
+    n_calls = 6
+    bufs = [(capi.PinnedArray((S, 4)), capi.PinnedArray((S,)), capi.PinnedArray((S, capi.FUSED_STRIDE))) for _ in range(n_calls)]
+    try:
+        for hp, hm, ho in bufs:
+            hp.a[...] = np.stack([synth.pose_to_se2(*(np.array([0.5, -0.3, 0.02]) + rng.uniform(-0.05, 0.05, 3))) for _ in range(S)])
+            hm.a[...] = rng.uniform(1.0, 4.0, S)
+            ho.a[...] = -1.0
+        for i, (hp, hm, ho) in enumerate(bufs):
+            prob.eval_fused_async(hp.a, ho.a, loss, mu_per_seg=hm.a if i % 2 else None)
+        gpu_ctx.sync()
+        for i, (hp, hm, ho) in enumerate(bufs):
+            want = prob.eval_fused(hp.a.copy(), loss, mu_per_seg=hm.a.copy() if i % 2 else None)
+            assert np.array_equal(ho.a, want), i
+        with pytest.raises(capi.RandtError):
+            prob.eval_fused_async(np.zeros((S, 4)), bufs[0][2].a, loss)
+    finally:
+        gpu_ctx.sync()
+        for t in bufs:
+            for b in t:
+                b.close()
+
+
 @pytest.mark.parametrize("k", [1, 2, 4])
 def test_fused_ragged_segments_cover_every_chunk_shape(oracle, gpu_ctx, k):
     """segments of 1 ... 700 duos in one batch: single-chunk tiles, tiles ending exactly on a chunk, split chunks whose second tile also
