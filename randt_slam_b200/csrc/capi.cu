@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <memory>
 #include <new>
 #include <queue>
@@ -166,6 +167,14 @@ void free_problem(randt_problem* p) {
 
 // tile list, balanced schedule, record table and per-segment bookkeeping from a host seg_off; uploads everything a DeviceProblem needs
 int finish_problem(randt_ctx* ctx, randt_problem* p) {
+  static const bool trace = getenv("RANDT_DEBUG_TIMING") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!trace) return;
+    auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "[randt] finish_problem %-18s %8.1f us\n", what, std::chrono::duration<double, std::micro>(t - t_prev).count());
+    t_prev = t;
+  };
   std::vector<Tile> tiles;
   std::vector<uint32_t> first(p->S + 1, 0);
   // one warp owns a tile.  Big batches: tiles of up to kTileDuos duos (a whole ~200-pair registration per warp, no partials);
@@ -181,26 +190,42 @@ int finish_problem(randt_ctx* ctx, randt_problem* p) {
     }
   }
   first[p->S] = (uint32_t)tiles.size();
+  lap("tiles");
   // Balanced static schedule: longest-processing-time assignment of tiles to the resident warps of the persistent grid (a tile
   // costs its duos plus a fixed prologue/reduce/emit overhead).  Registration problems differ in size, and one warp walks only ~7
   // of them per launch at the bench size, so round-robin striding leaves warps (and whole SMs) idle at the tail.
   const uint32_t n_warps = std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)kK3MaxWarps, (uint32_t)tiles.size()));
-  std::vector<std::vector<uint32_t>> mine(n_warps);
+  // (tile costs are small integers: counting sort and a bucket queue make this linear in the number of tiles)
+  const uint32_t T = (uint32_t)tiles.size();
+  std::vector<uint32_t> mine_off(n_warps + 1, 0), mine(T);    // tiles of warp w, ascending: mine[mine_off[w] .. mine_off[w + 1])
   {
-    std::vector<uint32_t> order(tiles.size());
-    for (uint32_t t = 0; t < tiles.size(); ++t) order[t] = t;
     auto cost = [&](uint32_t t) { return (tiles[t].end - tiles[t].begin) + 24u; };
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return cost(a) > cost(b); });
-    typedef std::pair<uint64_t, uint32_t> Load;   // (assigned cost, warp)
-    std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
-    for (uint32_t w = 0; w < n_warps; ++w) heap.push(Load(0, w));
+    const uint32_t max_cost = tile_duos + 24u;
+    std::vector<uint32_t> bucket(max_cost + 2, 0), order(T), warp_of(T);
+    for (uint32_t t = 0; t < T; ++t) ++bucket[max_cost - cost(t) + 1];
+    for (uint32_t c = 0; c <= max_cost; ++c) bucket[c + 1] += bucket[c];
+    for (uint32_t t = 0; t < T; ++t) order[bucket[max_cost - cost(t)]++] = t;      // descending cost, ties in tile order
+    // least-loaded warp through a bucket queue over the (integer) loads: the minimum load never decreases, and greedy assignment
+    // keeps every load below average + max_cost
+    uint64_t total = 0;
+    for (uint32_t t = 0; t < T; ++t) total += cost(t);
+    const uint32_t n_loads = (uint32_t)(total / n_warps) + 2u * max_cost + 2u;
+    std::vector<int32_t> head(n_loads, -1), next(n_warps, -1);
+    for (uint32_t w = n_warps; w-- > 0;) { next[w] = head[0]; head[0] = (int32_t)w; }
+    uint32_t cur = 0;
     for (uint32_t t : order) {
-      Load l = heap.top(); heap.pop();
-      mine[l.second].push_back(t);
-      l.first += cost(t);
-      heap.push(l);
+      while (head[cur] < 0) ++cur;
+      const uint32_t w = (uint32_t)head[cur];
+      head[cur] = next[w];
+      warp_of[t] = w; ++mine_off[w + 1];
+      const uint32_t nl = cur + cost(t);
+      next[w] = head[nl]; head[nl] = (int32_t)w;
     }
+    for (uint32_t w = 0; w < n_warps; ++w) mine_off[w + 1] += mine_off[w];
+    std::vector<uint32_t> fill(mine_off.begin(), mine_off.end() - 1);
+    for (uint32_t t = 0; t < T; ++t) mine[fill[warp_of[t]]++] = t;
   }
+  lap("lpt");
   // Records are laid out in schedule order (warp after warp, tile after tile), so that a warp streams one contiguous range and the
   // tail of one tile and the head of the next can share a chunk.  Two chunk lists over the same records:
   //   plan A (full evaluation): consecutive solo tiles of a warp are packed — the last, partly filled chunk of a tile takes the first
@@ -213,9 +238,9 @@ int finish_problem(randt_ctx* ctx, randt_problem* p) {
   std::vector<uint32_t> woffA(n_warps + 1, 0), woffB(n_warps + 1, 0);
   uint32_t rec = 0;
   for (uint32_t w = 0; w < n_warps; ++w) {
-    std::sort(mine[w].begin(), mine[w].end());
     bool open = false;      // the last chunk of plan A ends a solo tile, is not split yet and has free lanes
-    for (uint32_t t : mine[w]) {
+    for (uint32_t q = mine_off[w]; q < mine_off[w + 1]; ++q) {
+      const uint32_t t = mine[q];
       const Tile& tl = tiles[t];
       const bool solo = first[tl.seg + 1] - first[tl.seg] == 1u;
       const uint32_t len = tl.end - tl.begin, rb = rec;
@@ -249,6 +274,7 @@ int finish_problem(randt_ctx* ctx, randt_problem* p) {
     woffA[w + 1] = (uint32_t)planA.size(); woffB[w + 1] = (uint32_t)planB.size();
   }
   tile_rec_begin.push_back(rec);
+  lap("chunk plans");
   p->n_warps = n_warps;
   p->n_chunks = (uint32_t)planB.size(); p->n_chunks_full = (uint32_t)planA.size();
   p->n_tiles = (uint32_t)tiles.size();
@@ -274,6 +300,7 @@ int finish_problem(randt_ctx* ctx, randt_problem* p) {
     if (e == cudaSuccess) e = launch_permute_duos(p->duos, d_trb, d_tdb, (uint32_t)tiles.size(), p->n_duos, d_stream, ctx->stream, &nl);
     if (e == cudaSuccess) e = launch_build_duo_records(p->cells_m, p->cells_f, d_stream, p->n_duos, p->duo_recs, p->duo_p0, ctx->stream, &nl);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    lap("uploads + records");
     dev_free(d_trb); dev_free(d_tdb); dev_free(d_stream);
     if (e != cudaSuccess) return fail(ctx, RANDT_E_CUDA, "finish_problem: record table", e);
     ctx->launches += nl;
@@ -289,6 +316,7 @@ int finish_problem(randt_ctx* ctx, randt_problem* p) {
   CK(cudaMemcpyAsync(p->seg_off, p->h_seg_off.data(), p->h_seg_off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemsetAsync(p->seg_counters, 0, std::max<size_t>(1, p->S) * sizeof(uint32_t), ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));   // the host vectors above go out of scope
+  lap("tail");
   return RANDT_OK;
 }
 
@@ -663,9 +691,9 @@ int randt_associate(randt_ctx* ctx, const randt_map* F, const randt_map* M, cons
   randt_problem* p = new (std::nothrow) randt_problem();
   if (!p) return RANDT_E_NOMEM;
   p->device = ctx->device; p->sref = ctx->sref; p->S = B; p->n_m = n_m; p->n_f = F->n_cells;
-  float4* d_pose = nullptr; uint32_t *d_nn = nullptr, *d_cnt = nullptr, *d_scan = nullptr, *d_bs = nullptr, *d_cnt2 = nullptr, *d_scan2 = nullptr;
+  float4* d_pose = nullptr; uint32_t *d_nn = nullptr, *d_cnt = nullptr, *d_scan = nullptr, *d_bs = nullptr, *d_cnt2 = nullptr, *d_scan2 = nullptr, *d_offs = nullptr;
   int rc = RANDT_OK; int nl = 0;
-  auto cleanup = [&]() { dev_free(d_pose); dev_free(d_nn); dev_free(d_cnt); dev_free(d_scan); dev_free(d_bs); dev_free(d_cnt2); dev_free(d_scan2); };
+  auto cleanup = [&]() { dev_free(d_pose); dev_free(d_nn); dev_free(d_cnt); dev_free(d_scan); dev_free(d_bs); dev_free(d_cnt2); dev_free(d_scan2); dev_free(d_offs); };
 #define CKA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rc = fail(ctx, RANDT_E_CUDA, #call, e__); cleanup(); free_problem(p); return rc; } } while (0)
   std::vector<float4> h_pose(B);
   for (uint32_t b = 0; b < B; ++b) h_pose[b] = make_float4((float)pose0[4 * b], (float)pose0[4 * b + 1], (float)pose0[4 * b + 2], (float)pose0[4 * b + 3]);
@@ -674,30 +702,29 @@ int randt_associate(randt_ctx* ctx, const randt_map* F, const randt_map* M, cons
   CKA(dev_alloc(&d_nn, (size_t)n_m * k)); CKA(dev_alloc(&d_cnt, n_m)); CKA(dev_alloc(&d_scan, (size_t)n_m + 1)); CKA(dev_alloc(&d_bs, n_m / 1024 + 2));
   CKA(launch_associate(F->cells, F->cell_off, F->slot, M->cells, M->cell_off, B, n_m, M->max_per_map, geom, d_pose, k, metric, d_nn, d_cnt, ctx->stream, &nl));
   CKA(launch_exclusive_scan_u32(d_cnt, d_scan, n_m, d_bs, ctx->stream, &nl));
-  std::vector<uint32_t> h_scan((size_t)n_m + 1);
-  CKA(cudaMemcpyAsync(h_scan.data(), d_scan, ((size_t)n_m + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CKA(cudaStreamSynchronize(ctx->stream));
-  p->P = h_scan[n_m];
-  p->h_seg_off.resize(B + 1);
-  for (uint32_t b = 0; b <= B; ++b) p->h_seg_off[b] = h_scan[M->h_cell_off[b]];
-  CKA(dev_alloc(&p->pairs, p->P));
-  CKA(launch_compact_pairs(d_nn, d_cnt, d_scan, M->cell_off, F->cell_off, B, n_m, M->max_per_map, k, p->pairs, ctx->stream, &nl));
   // duos (K3's grouping): ceil(cnt / 2) per moving cell
   CKA(dev_alloc(&d_cnt2, n_m)); CKA(dev_alloc(&d_scan2, (size_t)n_m + 1));
   CKA(launch_duo_counts(d_cnt, n_m, d_cnt2, ctx->stream, &nl));
   CKA(launch_exclusive_scan_u32(d_cnt2, d_scan2, n_m, d_bs, ctx->stream, &nl));
-  CKA(cudaMemcpyAsync(h_scan.data(), d_scan2, ((size_t)n_m + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CKA(cudaStreamSynchronize(ctx->stream));
-  p->n_duos = h_scan[n_m];
-  p->h_duo_off.resize(B + 1);
-  for (uint32_t b = 0; b <= B; ++b) p->h_duo_off[b] = h_scan[M->h_cell_off[b]];
-  CKA(dev_alloc(&p->duos, p->n_duos));
+  // The host only needs the B+1 per-map offsets of both scans: gather them on the device and read them back once, after everything
+  // else of this call has been queued.  The pair / duo tables are sized by their bounds (k and ceil(k/2) per moving cell; nearly
+  // every cell finds its k neighbours), so no size has to come back before the compaction kernels run.
+  CKA(dev_alloc(&d_offs, 2 * ((size_t)B + 1)));
+  CKA(launch_gather_offsets(d_scan, d_scan2, M->cell_off, B + 1, d_offs, ctx->stream, &nl));
+  CKA(dev_alloc(&p->pairs, (size_t)n_m * k));
+  CKA(launch_compact_pairs(d_nn, d_cnt, d_scan, M->cell_off, F->cell_off, B, n_m, M->max_per_map, k, p->pairs, ctx->stream, &nl));
+  CKA(dev_alloc(&p->duos, (size_t)n_m * ((k + 1) / 2)));
   CKA(launch_compact_duos(d_nn, d_cnt, d_scan, d_scan2, M->cell_off, F->cell_off, B, n_m, M->max_per_map, k, p->duos, ctx->stream, &nl));
   // snapshot the cell tables (the reference's functors copy their cells; maps may be merged/transformed afterwards)
   CKA(dev_alloc(&p->cells_m, (size_t)n_m * 3)); CKA(dev_alloc(&p->cells_f, (size_t)F->n_cells * 3));
   if (n_m) CKA(cudaMemcpyAsync(p->cells_m, M->cells, (size_t)n_m * 48, cudaMemcpyDeviceToDevice, ctx->stream));
   if (F->n_cells) CKA(cudaMemcpyAsync(p->cells_f, F->cells, (size_t)F->n_cells * 48, cudaMemcpyDeviceToDevice, ctx->stream));
+  std::vector<uint32_t> h_offs(2 * ((size_t)B + 1));
+  CKA(cudaMemcpyAsync(h_offs.data(), d_offs, h_offs.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CKA(cudaStreamSynchronize(ctx->stream));
+  p->h_seg_off.assign(h_offs.begin(), h_offs.begin() + B + 1);
+  p->h_duo_off.assign(h_offs.begin() + B + 1, h_offs.end());
+  p->P = p->h_seg_off[B]; p->n_duos = p->h_duo_off[B];
 #undef CKA
   cleanup();
   ctx->launches += nl;

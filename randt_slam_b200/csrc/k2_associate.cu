@@ -159,6 +159,15 @@ __global__ void k2_duo_counts_kernel(const uint32_t* __restrict__ cnt, uint32_t 
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) cnt2[i] = (cnt[i] + 1u) >> 1;
 }
+// out[b] = scan[cell_off[b]], out[n_off + b] = scan2[cell_off[b]]: the per-map pair / duo offsets, so that the host reads B+1 values
+// per table instead of the whole scans
+__global__ void k2_gather_offsets_kernel(const uint32_t* __restrict__ scan, const uint32_t* __restrict__ scan2,
+                                         const uint32_t* __restrict__ cell_off, uint32_t n_off, uint32_t* __restrict__ out) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_off) return;
+  const uint32_t c = cell_off[b];
+  out[b] = scan[c]; out[n_off + b] = scan2[c];
+}
 __global__ void k2_compact_duos_kernel(const uint32_t* __restrict__ nn, const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ scan,
                                        const uint32_t* __restrict__ scan2, const uint32_t* __restrict__ cell_off_m,
                                        const uint32_t* __restrict__ cell_off_f, int k, Duo* __restrict__ duos) {
@@ -260,6 +269,14 @@ cudaError_t launch_compact_pairs(const uint32_t* d_nn, const uint32_t* d_cnt, co
 cudaError_t launch_duo_counts(const uint32_t* d_cnt, uint32_t n, uint32_t* d_cnt2, cudaStream_t s, int* n_launches) {
   if (n == 0) return cudaSuccess;
   k2_duo_counts_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_cnt, n, d_cnt2);
+  if (n_launches) *n_launches += 1;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gather_offsets(const uint32_t* d_scan, const uint32_t* d_scan2, const uint32_t* cell_off, uint32_t n_off, uint32_t* d_out,
+                                  cudaStream_t s, int* n_launches) {
+  if (n_off == 0) return cudaSuccess;
+  k2_gather_offsets_kernel<<<(n_off + 255) / 256, 256, 0, s>>>(d_scan, d_scan2, cell_off, n_off, d_out);
   if (n_launches) *n_launches += 1;
   return cudaGetLastError();
 }
