@@ -15,6 +15,7 @@ VAR_SE2_INTENSITY, VAR_SE2_XY, VAR_VEC_INTENSITY, VAR_VEC_XY = 0, 1, 2, 3
 LOSS_NONE, LOSS_BARRON, LOSS_WELSCH = 0, 1, 2
 LOOKUP_MAHALANOBIS, LOOKUP_EUCLID = 0, 1
 FUSED_STRIDE = 24
+FUSED_H, FUSED_G, FUSED_COST, FUSED_MAXR, FUSED_SUMSQ, FUSED_N = 0, 16, 20, 21, 22, 23   # RANDT_FUSED_* of include/randt_gpu.h
 E_INVALID, E_CUDA, E_CAPACITY, E_NONFINITE, E_NOMEM = -1, -2, -3, -4, -5
 
 

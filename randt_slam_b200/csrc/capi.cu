@@ -1039,6 +1039,7 @@ int randt_register_batch_dev(randt_ctx* ctx, const randt_problem* cp, int varian
   // Iterations are enqueued in groups of `poll`; the active counter of group g is read back while group g + 1 already runs, so the
   // GPU never waits for the host (the price: up to one group of no-op launches after the last segment has finished).
   bool done = false;
+  const auto t_solver0 = std::chrono::steady_clock::now();
   uint32_t planned_for = S;     // active segments when the schedule in use was made
   const long long n_groups = (cap + poll - 1) / poll;
   for (long long g = 0; g < n_groups && !done; ++g) {
@@ -1053,7 +1054,9 @@ int randt_register_batch_dev(randt_ctx* ctx, const randt_problem* cp, int varian
       CK(cudaEventSynchronize(sr.ev[(g - 1) & 1]));
       const uint32_t n_act = sr.h_n_active[(g - 1) & 1];
       done = n_act == 0u;
-      if (getenv("RANDT_DEBUG_SOLVER")) fprintf(stderr, "[randt solver] group %lld (iterations <= %lld): %u active\n", g - 1, g * poll, n_act);
+      if (getenv("RANDT_DEBUG_SOLVER"))
+        fprintf(stderr, "[randt solver] group %lld (iterations <= %lld): %u active  t=%.1f us\n", g - 1, g * poll, n_act,
+                std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_solver0).count());
       // finished segments leave holes K3 has to step over: compact the schedule once a quarter of its segments are gone
       if (!done && (unsigned long long)n_act * 4ull <= (unsigned long long)planned_for * 3ull) {
         CK(launch_replan(p->chunks, p->n_chunks, p->lm_active, p->n_warps, p->lm_flags, p->lm_scan, p->lm_bs, p->lm_chunks, p->lm_warp_off,
