@@ -187,6 +187,15 @@ class Matcher {
   // Matcher::addNDTFactor as one batched cost function (single map pair)
   std::unique_ptr<NdtCostFunction> addNDTFactor(const SE2d& initial_guess, const Map& fixed_ndt, const Map& moving_ndt,
                                                 bool use_intensity_as_dimension, int n_neighbours) const;
+  // The NDT part of Matcher::estimateTransformCeres (ndt_matcher.cpp:321-424) for the newest state of the window: residual blocks
+  // of the moving scan against EVERY fixed map (the current submap, plus the previous one while they overlap: local_fuser.cpp:129-138)
+  // in the reference's block order, loss ScaledLoss(Barron(loss_function_scale, convexity, mu), ndt_weight / (n_cells k)) (:392), the GNC
+  // schedule of :382-397 with gnc_steps, the manifold when optimize_on_manifold (and not the analytic functors), and the rejection gate
+  // of :408-422.  The motion-model and IMU factors of the reference's joint problem are host-side factors outside this path: a caller
+  // that needs them keeps ceres and plugs NdtCostFunction in instead.  trans: prior in, estimate out (untouched when rejected).
+  // Batched: problem b = moving map b against map b of every entry of fixed_ndts.  Returns accepted[b].
+  std::vector<char> estimateTransformsNDT(std::vector<SE2d>& trans, const std::vector<const Map*>& fixed_ndts, const Map& moving_ndts) const;
+  bool estimateTransformNDT(SE2d& trans, const std::vector<const Map*>& fixed_ndts, const Map& moving_ndt) const;
   // Matcher::estimateLoopConstraint (ndt_matcher.cpp:426-493), B = 1
   double estimateLoopConstraint(SE2d& trans, const Map& old_ndt, Map& new_ndt, int max_gnc_steps, bool use_intensity_as_dimension,
                                 double scale) const;
@@ -220,6 +229,11 @@ RANDT_API int randt_hostapi_bnb(int device, const randt_grid_params* gp, const f
                                 uint32_t n_moving, double convexity, double scale, double window_linear, double window_angular,
                                 double linear_step, double max_px_range, double cost_threshold, int n_iter, double* pose_io4, double* min_cost,
                                 uint32_t* n_evaluated);
+RANDT_API int randt_hostapi_odometry(int device, const randt_grid_params* gp, const float* const* fixed_pts4, const uint32_t* n_fixed_pts,
+                                     const double* fixed_pose4 /*[n_fixed][4]: each fixed scan is voxelised, then moved by its pose*/,
+                                     uint32_t n_fixed, const float* moving_pts4, uint32_t n_moving, int k, double loss_function_scale,
+                                     double convexity, double divisor, int gnc_steps, double ndt_weight, int optimize_on_manifold,
+                                     double reject_translation, double reject_rotation, double* pose_io4, int* accepted);
 RANDT_API int randt_hostapi_export(int device, const randt_grid_params* gp, const float* pts4, uint32_t n_pts, double* mean3 /*[cap][3]*/,
                                    double* cov6 /*[cap][6]*/, uint32_t cap, uint32_t* n_cells);
 RANDT_API const char* randt_hostapi_last_error(void);

@@ -230,6 +230,92 @@ std::unique_ptr<NdtCostFunction> Matcher::addNDTFactor(const SE2d& initial_guess
   return std::unique_ptr<NdtCostFunction>(new NdtCostFunction(*ctx_, prob, variant(use_intensity_as_dimension)));
 }
 
+std::vector<char> Matcher::estimateTransformsNDT(std::vector<SE2d>& trans, const std::vector<const Map*>& fixed_ndts, const Map& moving_ndts) const {
+  const uint32_t B = moving_ndts.n_maps();
+  if (fixed_ndts.empty()) throw Error(RANDT_E_INVALID, "estimateTransformsNDT: no fixed map");
+  if (trans.size() != B) throw Error(RANDT_E_INVALID, "estimateTransformsNDT: one prior per moving map");
+  for (const Map* f : fixed_ndts) if (!f || f->n_maps() != B) throw Error(RANDT_E_INVALID, "estimateTransformsNDT: batch sizes differ");
+  const bool use_intensity = parameters_.use_intensity_as_dimension;
+  const int k = parameters_.n_results_kd_lookup;
+  struct Problems { std::vector<randt_problem*> v; ~Problems() { for (randt_problem* p : v) randt_problem_destroy(p); } } probs;
+  for (const Map* f : fixed_ndts) probs.v.push_back(associate(trans.data(), *f, moving_ndts, use_intensity, k));
+  randt_problem* prob = probs.v[0];
+  if (probs.v.size() > 1) {
+    // one residual-block list per state: the blocks of fixed map 0, then those of fixed map 1, ... (estimateTransformCeres appends
+    // the ids addNDTFactor returns map after map).  The moving cells are shared, the fixed tables are laid one after the other.
+    std::vector<float> cells_m, cells_f;
+    std::vector<std::vector<uint32_t>> pm(probs.v.size()), pf(probs.v.size()), so(probs.v.size());
+    uint32_t n_m = 0, f_base = 0;
+    for (size_t i = 0; i < probs.v.size(); ++i) {
+      uint32_t S = 0, P = 0, nm = 0, nf = 0;
+      ctx_->check(randt_problem_info(probs.v[i], &S, &P, &nm, &nf));
+      pm[i].resize(P); pf[i].resize(P); so[i].resize((size_t)S + 1);
+      ctx_->check(randt_problem_download(ctx_->get(), probs.v[i], pm[i].data(), pf[i].data(), so[i].data()));
+      std::vector<float> cm((size_t)nm * 12), cf((size_t)nf * 12);
+      ctx_->check(randt_problem_download_cells(ctx_->get(), probs.v[i], cm.data(), cf.data()));
+      if (i == 0) { cells_m = cm; n_m = nm; }
+      cells_f.insert(cells_f.end(), cf.begin(), cf.end());
+      for (uint32_t& j : pf[i]) j += f_base;
+      f_base += nf;
+    }
+    std::vector<uint32_t> pair_m, pair_f, seg_off((size_t)B + 1, 0);
+    for (uint32_t b = 0; b < B; ++b) {
+      for (size_t i = 0; i < probs.v.size(); ++i) {
+        pair_m.insert(pair_m.end(), pm[i].begin() + so[i][b], pm[i].begin() + so[i][b + 1]);
+        pair_f.insert(pair_f.end(), pf[i].begin() + so[i][b], pf[i].begin() + so[i][b + 1]);
+      }
+      seg_off[b + 1] = (uint32_t)pair_m.size();
+    }
+    randt_problem* merged = nullptr;
+    ctx_->check(randt_problem_create(ctx_->get(), cells_m.data(), n_m, cells_f.data(), f_base, pair_m.data(), pair_f.data(), (uint32_t)pair_m.size(),
+                                     seg_off.data(), B, &merged));
+    probs.v.push_back(merged);
+    prob = merged;
+  }
+  const int var = variant(use_intensity);
+  const int np = var <= RANDT_VAR_SE2_XY ? 4 : 3;
+  std::vector<double> poses((size_t)B * np), result((size_t)B * RANDT_REG_STRIDE);
+  for (uint32_t b = 0; b < B; ++b) {
+    if (np == 4) std::memcpy(&poses[4 * b], trans[b].v, 4 * sizeof(double));
+    else { poses[3 * b] = trans[b].v[2]; poses[3 * b + 1] = trans[b].v[3]; poses[3 * b + 2] = trans[b].angle(); }
+  }
+  // n_cells counts the moving map's cells (ndt_matcher.cpp:372), once, whatever the number of fixed maps.  One weight per call: for a
+  // batch the mean over its moving maps (the reference has one stream).
+  const double n_cells = (double)moving_ndts.get_n_cells() / (double)B;
+  randt_loss loss;
+  loss.kind = RANDT_LOSS_BARRON; loss.scale = parameters_.loss_function_scale; loss.alpha = parameters_.loss_function_convexity; loss.mu = 1.0;
+  loss.weight = parameters_.ndt_weight / (n_cells * (double)k);
+  randt_solver_options opt;
+  randt_solver_options_default(&opt);
+  opt.max_num_iterations = parameters_.max_iteration;
+  opt.use_manifold = (parameters_.optimize_on_manifold && !parameters_.use_analytic_expressions_for_optimization) ? 1 : 0;
+  opt.gnc_loss_scale = parameters_.loss_function_scale;
+  opt.gnc_divisor = parameters_.gnc_control_parameter_divisor;
+  opt.gnc_max_steps = parameters_.gnc_steps;
+  ctx_->check(randt_register_batch(ctx_->get(), prob, var, poses.data(), &loss, &opt, result.data()));
+  std::vector<char> accepted(B, 1);
+  for (uint32_t b = 0; b < B; ++b) {
+    SE2d est;
+    if (np == 4) std::memcpy(est.v, &poses[4 * b], 4 * sizeof(double));
+    else est = SE2d(poses[3 * b + 2], poses[3 * b], poses[3 * b + 1]);
+    // reject an estimate that strays too far from the prior (ndt_matcher.cpp:408-411); no residual block at all is a failure too
+    double da = est.angle() - trans[b].angle();
+    da = std::atan2(std::sin(da), std::cos(da));
+    const bool stray = std::fabs(est.v[2] - trans[b].v[2]) > parameters_.pose_reject_translation ||
+                       std::fabs(est.v[3] - trans[b].v[3]) > parameters_.pose_reject_translation || std::fabs(da) > parameters_.pose_reject_rotation;
+    if (stray || result[(size_t)b * RANDT_REG_STRIDE + RANDT_REG_STATUS] != 0.0) accepted[b] = 0;
+    else trans[b] = est;
+  }
+  return accepted;
+}
+
+bool Matcher::estimateTransformNDT(SE2d& trans, const std::vector<const Map*>& fixed_ndts, const Map& moving_ndt) const {
+  std::vector<SE2d> t(1, trans);
+  const std::vector<char> ok = estimateTransformsNDT(t, fixed_ndts, moving_ndt);
+  trans = t[0];
+  return ok[0] != 0;
+}
+
 std::vector<double> Matcher::estimateLoopConstraints(std::vector<SE2d>& trans, const Map& old_ndts, Map& new_ndts, int max_gnc_steps,
                                                      bool use_intensity_as_dimension, double scale) const {
   const uint32_t B = old_ndts.n_maps();
@@ -412,6 +498,40 @@ int randt_hostapi_cost_function(int device, const randt_grid_params* gp, const f
     double* jac[1] = {jacobian};
     if (!base->Evaluate(params, residuals, jacobian ? jac : nullptr)) throw randt::Error(RANDT_E_NONFINITE, "Evaluate returned false");
     if (max_raw) *max_raw = cf->maxRawResidual(pose4);
+  });
+}
+
+int randt_hostapi_odometry(int device, const randt_grid_params* gp, const float* const* fixed_pts4, const uint32_t* n_fixed_pts, const double* fixed_pose4,
+                           uint32_t n_fixed, const float* moving_pts4, uint32_t n_moving, int k, double loss_function_scale, double convexity,
+                           double divisor, int gnc_steps, double ndt_weight, int optimize_on_manifold, double reject_translation,
+                           double reject_rotation, double* pose_io4, int* accepted) {
+  return guarded([&] {
+    randt::Context ctx(device);
+    const randt::NDTMapParameters mp = map_params(*gp);
+    std::vector<std::unique_ptr<randt::Map>> fixed;
+    std::vector<const randt::Map*> fixed_ptr;
+    for (uint32_t i = 0; i < n_fixed; ++i) {
+      fixed.emplace_back(new randt::Map(ctx, mp));
+      const uint32_t off[2] = {0, n_fixed_pts[i]};
+      fixed.back()->addClusters(fixed_pts4[i], off, 1);
+      randt::SE2d T;
+      std::memcpy(T.v, fixed_pose4 + 4 * i, 4 * sizeof(double));
+      fixed.back()->transformMap(&T);
+      fixed_ptr.push_back(fixed.back().get());
+    }
+    randt::Map moving(ctx, mp);
+    const uint32_t mo[2] = {0, n_moving};
+    moving.addClusters(moving_pts4, mo, 1);
+    randt::NDTMatcherParameters p;
+    p.n_results_kd_lookup = k; p.loss_function_scale = loss_function_scale; p.loss_function_convexity = convexity;
+    p.gnc_control_parameter_divisor = divisor; p.gnc_steps = gnc_steps; p.ndt_weight = ndt_weight; p.optimize_on_manifold = optimize_on_manifold != 0;
+    p.pose_reject_translation = reject_translation; p.pose_reject_rotation = reject_rotation;
+    randt::Matcher m(ctx);
+    m.initialize(p);
+    randt::SE2d t;
+    std::memcpy(t.v, pose_io4, 4 * sizeof(double));
+    *accepted = m.estimateTransformNDT(t, fixed_ptr, moving) ? 1 : 0;
+    std::memcpy(pose_io4, t.v, 4 * sizeof(double));
   });
 }
 

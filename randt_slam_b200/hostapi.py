@@ -19,7 +19,7 @@ def lib():
         capi.lib()   # librandt_gpu.so first (the host library links against it)
         L = C.CDLL(LIB_PATH)
         L.randt_hostapi_last_error.restype = C.c_char_p
-        for name in ("randt_hostapi_loop_constraints", "randt_hostapi_cost_function", "randt_hostapi_bnb", "randt_hostapi_export"):
+        for name in ("randt_hostapi_loop_constraints", "randt_hostapi_cost_function", "randt_hostapi_bnb", "randt_hostapi_export", "randt_hostapi_odometry"):
             getattr(L, name).restype = C.c_int
         _lib = L
     return _lib
@@ -80,3 +80,20 @@ def export_normal_distributions(gp, pts, device=0):
     mean = np.zeros((cap, 3)); cov = np.zeros((cap, 6)); n = C.c_uint32(0)
     _check(lib().randt_hostapi_export(C.c_int(device), C.byref(gp), _pf(pts), C.c_uint32(len(pts)), _pf(mean), _pf(cov), C.c_uint32(cap), C.byref(n)))
     return mean[: n.value].copy(), cov[: n.value].copy()
+
+
+def odometry(gp, fixed_scans, fixed_poses, moving_pts, prior, k, loss_function_scale, convexity, divisor, gnc_steps, ndt_weight,
+             optimize_on_manifold=True, reject_translation=5.0, reject_rotation=2.0, device=0):
+    """Matcher::estimateTransformNDT: every fixed scan is voxelised and moved by its pose (a stand-in for a submap), the moving scan is
+    registered against all of them at once -> (pose [4], accepted)"""
+    fs = [np.ascontiguousarray(f, np.float32) for f in fixed_scans]
+    ptrs = (C.c_void_p * len(fs))(*[f.ctypes.data for f in fs])
+    n_pts = np.array([len(f) for f in fs], np.uint32)
+    fp = np.ascontiguousarray(fixed_poses, np.float64).reshape(len(fs), 4)
+    m = np.ascontiguousarray(moving_pts, np.float32)
+    pose = np.ascontiguousarray(prior, np.float64).copy(); ok = C.c_int(0)
+    _check(lib().randt_hostapi_odometry(C.c_int(device), C.byref(gp), ptrs, _pf(n_pts), _pf(fp), C.c_uint32(len(fs)), _pf(m), C.c_uint32(len(m)),
+                                        C.c_int(k), C.c_double(loss_function_scale), C.c_double(convexity), C.c_double(divisor), C.c_int(gnc_steps),
+                                        C.c_double(ndt_weight), C.c_int(int(optimize_on_manifold)), C.c_double(reject_translation),
+                                        C.c_double(reject_rotation), _pf(pose), C.byref(ok)))
+    return pose, bool(ok.value)

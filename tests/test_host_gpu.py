@@ -104,3 +104,41 @@ def test_export_normal_distributions_wire_format(oracle):
     assert np.array_equal(mean, v[:, :3].astype(np.float64))
     c = v[:, 3:].reshape(-1, 3, 3).astype(np.float64)
     assert np.array_equal(cov, np.stack([c[:, 0, 0], c[:, 0, 1], c[:, 0, 2], c[:, 1, 1], c[:, 1, 2], c[:, 2, 2]], 1))
+
+
+@pytest.mark.parametrize("n_fixed", [1, 2])
+def test_estimate_transform_ndt_matches_oracle(oracle, n_fixed):
+    """the NDT part of Matcher::estimateTransformCeres: blocks against every fixed map (current submap + the previous one while they
+    overlap), ScaledLoss(Barron, ndt_weight / (n_cells k)), GNC, SE2 manifold; and the rejection gate (ndt_matcher.cpp:408-422)"""
+    p = P.OXFORD
+    k = p.n_results_nn_lookup
+    fixed_pose = [(0.0, 0.0, 0.0), (0.5, 0.1, 0.01)][:n_fixed]
+    fixed = [H.make_scan(p, 90, fp, 11 + i) for i, fp in enumerate(fixed_pose)]
+    fixed_se2 = np.stack([synth.pose_to_se2(*fp) for fp in fixed_pose])
+    moving = H.make_scan(p, 90, (0.9, -0.3, 0.03), 21)
+    prior = synth.pose_to_se2(0.8, -0.2, 0.02)
+    args = (k, p.loss_function_scale, p.loss_function_convexity, p.gnc_control_parameter_divisor, p.gnc_steps, p.ndt_weight)
+    pose, ok = hostapi.odometry(capi.grid_params(p), fixed, fixed_se2, moving, prior, *args)
+    assert ok
+    # oracle: the same blocks, fixed tables one after the other
+    mv = oracle.voxelize(moving, *H.vox_args(p))
+    f_cells, im_all, jf_all, base = [], [], [], 0
+    for pts, T in zip(fixed, fixed_se2):
+        v = oracle.voxelize(pts, *H.vox_args(p))
+        cells = oracle.transform_cells(v["cells"], *T.astype(np.float32))
+        slot = v["slot"]          # Map::transformMap moves the cells, not grid_indizes_ (ndt_map.cpp:177-182): lookups use the old slots
+        im, jf = oracle.associate(cells, slot, p.size_x, p.size_y, p.resolution, p.max_neighbor_linf_distance, mv["cells"], prior, k)
+        f_cells.append(cells); im_all.append(im); jf_all.append(jf + base); base += len(cells)
+    w = p.ndt_weight / (len(mv["cells"]) * k)
+    o = oracle.loop_constraint(np.concatenate(f_cells), np.full(p.size_x * p.size_y, -1, np.int32), p.size_x, p.size_y, p.resolution,
+                               p.max_neighbor_linf_distance, mv["cells"], prior, k, matcher_loss_scale=p.loss_function_scale,
+                               loop_scale=p.loss_function_scale, alpha=p.loss_function_convexity, divisor=p.gnc_control_parameter_divisor,
+                               max_gnc_steps=p.gnc_steps, on_manifold=True, loss_weight=w,
+                               pairs=(np.concatenate(im_all).astype(np.uint32), np.concatenate(jf_all).astype(np.uint32)))
+    assert o["status"] == 0 and len(np.concatenate(im_all)) > 50 * n_fixed
+    assert np.max(np.abs(pose - o["pose"])) < 1e-7
+    est = (pose[2], pose[3], np.arctan2(pose[1], pose[0]))
+    assert abs(est[0] - 0.9) < 0.3 and abs(est[1] + 0.3) < 0.3 and abs(est[2] - 0.03) < 0.02
+    # the gate: an estimate further than pose_reject_translation from the prior is refused and the prior comes back untouched
+    pose_r, ok_r = hostapi.odometry(capi.grid_params(p), fixed, fixed_se2, moving, prior, *args, reject_translation=1e-4)
+    assert not ok_r and np.array_equal(pose_r, prior)
