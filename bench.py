@@ -345,7 +345,7 @@ def main():
     # pipelined host-buffer calls (randt_eval_fused_async): every step uploads its own pinned poses and lands its own records in pinned
     # host memory; the host runs at most two steps ahead of the device
     E2E_DEPTH = 4
-    h_ring = [(capi.PinnedArray((S, 4)), capi.PinnedArray((S, capi.FUSED_STRIDE))) for _ in range(E2E_DEPTH)]
+    h_ring = [(capi.PinnedArray((S, 4)), capi.PinnedArray((S, capi.PACKED_STRIDE))) for _ in range(E2E_DEPTH)]
     for hp, _ in h_ring:
         hp.a[...] = poses
     ev_ring = [torch.cuda.Event() for _ in range(E2E_DEPTH)]
@@ -355,7 +355,7 @@ def main():
             j = i % E2E_DEPTH
             if i >= E2E_DEPTH:
                 ev_ring[(i - 2) % E2E_DEPTH].synchronize()   # step i-2 has left the stream => the records of step i-4 are in host memory
-            prob.eval_fused_async(h_ring[j][0].a, h_ring[j][1].a, loss)
+            prob.eval_fused_async(h_ring[j][0].a, h_ring[j][1].a, loss, packed=True)
             ev_ring[j].record(stream)
         ctx.sync()
 
@@ -399,7 +399,7 @@ def main():
         run_e2e_pipelined(args.steps)
         barrier()
         e2e_s = time.perf_counter() - t0
-        e2e_bits_equal = all(bool(np.array_equal(h_ring[j][1].a, h_out_np)) for j in range(E2E_DEPTH))
+        e2e_bits_equal = all(bool(np.array_equal(h_ring[j][1].a, capi.pack_fused(h_out_np))) for j in range(E2E_DEPTH))
         # ---- registrations: every problem of the batch solved to convergence (GNC + LM), K3 + K4, device resident ----
         reg = None
         if args.reg_steps > 0:
@@ -586,15 +586,16 @@ def main():
                        "mode": "fused (r, J, Barron corrector, per-pose J^T J / J^T r)", "resident_bytes_per_gpu": resident,
                        "l2_policy": "inputs larger than L2 (%.0f MB resident vs 126 MB), no flush" % (resident / 1e6),
                        "preset": p.name, "parallelism": "problems sharded across ranks, no data-path collective" if world > 1 else "single GPU"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(S * 32), "d2h_bytes_per_step": int(S * 192),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(S * 32), "d2h_bytes_per_step": int(S * 8 * capi.PACKED_STRIDE),
                     "ms_per_step": e2e_ms_all / args.steps, "in_flight": E2E_DEPTH,
                     "blocking_value": pairs_all * args.steps / (e2e_sync_ms_all * 1e-3), "blocking_ms_per_step": e2e_sync_ms_all / args.steps,
                     "results_equal_blocking_call": e2e_bits_equal,
                     "api": "randt_eval_fused_async (host pointers, wall clock): every step uploads its own pinned poses (copy stream, two device "
-                           "slots) and its per-pose records are copied out to the caller's pinned result buffer (second copy stream) while "
-                           "the next step's kernel runs; four host buffer sets, the host waits for step i-2 to leave the stream before "
-                           "reusing the buffers of step i-4; PCIe-bound (3.67 MB per step).  blocking_value: the same through "
-                           "randt_eval_fused, one step at a time, K3 storing straight into the pinned result buffer"},
+                           "slots) and its per-pose records — packed: H's upper triangle, g, cost, max r, sum r^2, n = 144 B — are copied out to "
+                           "the caller's pinned result buffer (second copy stream) while the next step's kernel runs; four host buffer "
+                           "sets, the host waits for step i-2 to leave the stream before reusing the buffers of step i-4.  blocking_value: "
+                           "the same through randt_eval_fused, one step at a time, K3 storing the full 192 B records straight into the "
+                           "pinned result buffer"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
                          "traffic": measured_traffic(Pn), "peak_source": pk_src, "kernel": "k3_fused_kernel<0,BARRON_M2,true>",

@@ -87,6 +87,13 @@ enum {
   RANDT_FUSED_N = 23,      /* residual blocks in the segment */
   RANDT_FUSED_STRIDE = 24
 };
+/* the same record without the redundant half of the symmetric H: 18 float64 (what randt_eval_fused_async can ship over PCIe) */
+enum {
+  RANDT_PACKED_H = 0,      /* [10] upper triangle of the 4x4, row by row: 00 01 02 03 11 12 13 22 23 33 */
+  RANDT_PACKED_G = 10,     /* [4] */
+  RANDT_PACKED_COST = 14, RANDT_PACKED_MAXR = 15, RANDT_PACKED_SUMSQ = 16, RANDT_PACKED_N = 17,
+  RANDT_PACKED_STRIDE = 18
+};
 
 typedef struct randt_ctx randt_ctx;
 typedef struct randt_map randt_map;          /* a batch of B NDT maps resident on the device */
@@ -200,9 +207,11 @@ RANDT_API int randt_eval_fused(randt_ctx* ctx, const randt_problem* p, int varia
 /* Enqueue-only form for a caller that scores one pose set after another (the BnB levels of ndt_matcher.cpp:560-576, pose grids):
  * poses, mu_per_seg and out must be pinned host memory (randt_host_alloc); the upload of call i+1 and the copy-out of call i-1 overlap
  * the kernel of call i (two copy streams, two device slots each way).  The buffers of a call may be read / reused after
- * randt_ctx_sync(), or once call i+2 has left the context's stream; give the calls in flight their own buffers. */
+ * randt_ctx_sync(), or once call i+2 has left the context's stream; give the calls in flight their own buffers.
+ * packed != 0: `out` receives RANDT_PACKED_STRIDE doubles per segment (layout RANDT_PACKED_*) instead of RANDT_FUSED_STRIDE — the
+ * copy-out is what bounds a pipelined step, and a quarter of the full record is the mirrored half of H. */
 RANDT_API int randt_eval_fused_async(randt_ctx* ctx, const randt_problem* p, int variant, const double* poses, const randt_loss* loss,
-                                     const double* mu_per_seg, int want_jac, double* out);
+                                     const double* mu_per_seg, int want_jac, int packed, double* out);
 RANDT_API int randt_eval_fused_dev(randt_ctx* ctx, const randt_problem* p, int variant, const double* d_poses, const randt_loss* loss,
                                    const double* d_mu_per_seg, int want_jac, double* d_out);
 /* Cost of ONE segment's pair list at many candidate poses (the inner loop of Matcher::estimateTransformGlobalBNB,

@@ -16,6 +16,13 @@ LOSS_NONE, LOSS_BARRON, LOSS_WELSCH = 0, 1, 2
 LOOKUP_MAHALANOBIS, LOOKUP_EUCLID = 0, 1
 FUSED_STRIDE = 24
 FUSED_H, FUSED_G, FUSED_COST, FUSED_MAXR, FUSED_SUMSQ, FUSED_N = 0, 16, 20, 21, 22, 23   # RANDT_FUSED_* of include/randt_gpu.h
+PACKED_STRIDE = 18                                                                       # RANDT_PACKED_*: H upper triangle (10), g (4), cost, max r, sum r^2, n
+_PACKED_SRC = [0, 1, 2, 3, 5, 6, 7, 10, 11, 15, 16, 17, 18, 19, 20, 21, 22, 23]
+
+
+def pack_fused(full):
+    """[S, 24] records -> [S, 18] (what randt_eval_fused_async(packed=1) delivers)"""
+    return np.ascontiguousarray(np.asarray(full)[..., _PACKED_SRC])
 E_INVALID, E_CUDA, E_CAPACITY, E_NONFINITE, E_NOMEM = -1, -2, -3, -4, -5
 
 
@@ -112,7 +119,7 @@ _SIGS = {
     "randt_eval_emit": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "randt_eval_emit_dev": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "randt_eval_fused": (_i, [_vp, _vp, _i, _vp, C.POINTER(Loss), _vp, _i, _vp]),
-    "randt_eval_fused_async": (_i, [_vp, _vp, _i, _vp, C.POINTER(Loss), _vp, _i, _vp]),
+    "randt_eval_fused_async": (_i, [_vp, _vp, _i, _vp, C.POINTER(Loss), _vp, _i, _i, _vp]),
     "randt_eval_fused_dev": (_i, [_vp, _vp, _i, _vp, C.POINTER(Loss), _vp, _i, _vp]),
     "randt_sweep_costs": (_i, [_vp, _vp, _u32, _i, _vp, _u32, C.POINTER(Loss), _vp]),
     "randt_solver_options_default": (None, [_vp]),
@@ -345,15 +352,15 @@ class Problem:
         self.ctx._check(lib().randt_eval_fused(self.ctx._h, self._h, int(variant), _ptr(poses), lp, _ptr(mu), int(want_jac), _ptr(out)))
         return out
 
-    def eval_fused_async(self, poses, out, loss=None, mu_per_seg=None, want_jac=True, variant=VAR_SE2_INTENSITY):
-        """enqueue-only evaluation: `poses`, `mu_per_seg` and `out` are float64 arrays in pinned host memory (pinned_array);
-        valid after Context.sync()"""
+    def eval_fused_async(self, poses, out, loss=None, mu_per_seg=None, want_jac=True, variant=VAR_SE2_INTENSITY, packed=False):
+        """enqueue-only evaluation: `poses`, `mu_per_seg` and `out` ([S, 24], or [S, 18] when packed) are float64 arrays in pinned host
+        memory (PinnedArray); valid after Context.sync()"""
         for a in (poses, out, mu_per_seg):
             if a is not None and not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous):
                 raise TypeError("eval_fused_async needs C-contiguous float64 arrays")
         lp = C.byref(loss) if loss is not None else None
         self.ctx._check(lib().randt_eval_fused_async(self.ctx._h, self._h, int(variant), _ptr(poses), lp, _ptr(mu_per_seg), int(want_jac),
-                                                     _ptr(out)))
+                                                     int(packed), _ptr(out)))
 
     def eval_fused_dev(self, d_poses, d_out, loss=None, d_mu=None, want_jac=True, variant=VAR_SE2_INTENSITY):
         lp = C.byref(loss) if loss is not None else None

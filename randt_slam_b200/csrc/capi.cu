@@ -904,7 +904,7 @@ int randt_eval_fused(randt_ctx* ctx, const randt_problem* cp, int variant, const
 // kernel of call i, and the records of call i leave on a third stream while the kernel of call i+1 runs.  randt_ctx_sync() orders the
 // host with all results; short of that, the records of call i are in host memory once call i+2 has left the context's stream.
 int randt_eval_fused_async(randt_ctx* ctx, const randt_problem* cp, int variant, const double* poses, const randt_loss* loss,
-                           const double* mu_per_seg, int want_jac, double* out) {
+                           const double* mu_per_seg, int want_jac, int packed, double* out) {
   if (!ctx || !cp || !poses || !out) return fail(ctx, RANDT_E_INVALID, "randt_eval_fused_async: null argument");
   if (check_variant(ctx, variant)) return RANDT_E_INVALID;
   randt_problem* p = const_cast<randt_problem*>(cp);
@@ -947,7 +947,7 @@ int randt_eval_fused_async(randt_ctx* ctx, const randt_problem* cp, int variant,
   CK(cudaStreamWaitEvent(ctx->stream, r.ev_in[slot], 0));
   // Records go to a device slot and leave on a third stream: a DMA copy moves the 192 S bytes at the full PCIe rate while the next
   // call's kernel runs (stores from the kernel straight into mapped host memory, as the blocking call does, reach ~3/4 of that rate).
-  const size_t n_out = (size_t)p->S * RANDT_FUSED_STRIDE;
+  const size_t n_full = (size_t)p->S * RANDT_FUSED_STRIDE, n_pack = packed ? (size_t)p->S * RANDT_PACKED_STRIDE : 0, n_out = n_full + n_pack;
   CK(cudaStreamWaitEvent(ctx->stream, r.ev_d2h[slot], 0));     // the copy-out of two calls ago has drained this slot
   if (r.oring_cap[slot] < n_out) {
     if (r.oring[slot]) CK(cudaFreeAsync(r.oring[slot], ctx->stream));
@@ -958,9 +958,16 @@ int randt_eval_fused_async(randt_ctx* ctx, const randt_problem* cp, int variant,
   double* d_out = r.oring[slot];
   int rc = randt_eval_fused_dev(ctx, p, variant, d_in, loss, mu_per_seg ? d_in + n_pose : nullptr, want_jac, d_out);
   if (rc) return rc;
+  const double* d_ship = d_out; size_t n_ship = n_full;
+  if (packed) {
+    int nl = 0;
+    CK(launch_pack_fused(d_out, p->S, d_out + n_full, ctx->stream, &nl));
+    ctx->launches += nl;
+    d_ship = d_out + n_full; n_ship = n_pack;
+  }
   CK(cudaEventRecord(r.ev_done[slot], ctx->stream));
   CK(cudaStreamWaitEvent(r.copy_out, r.ev_done[slot], 0));
-  CK(cudaMemcpyAsync(out, d_out, n_out * sizeof(double), cudaMemcpyDeviceToHost, r.copy_out));
+  CK(cudaMemcpyAsync(out, d_ship, n_ship * sizeof(double), cudaMemcpyDeviceToHost, r.copy_out));
   CK(cudaEventRecord(r.ev_d2h[slot], r.copy_out));             // randt_ctx_sync() waits for the copy-out stream as well
   return RANDT_OK;
 }

@@ -931,6 +931,25 @@ cudaError_t launch_build_duo_records(const float4* cells_m, const float4* cells_
   return cudaGetLastError();
 }
 
+// 24-double records -> 18-double records (RANDT_PACKED_*): the upper triangle of H, then g, cost, max r, sum r^2, n
+__global__ void __launch_bounds__(256) pack_fused_kernel(const double* __restrict__ full, uint32_t n_segments, double* __restrict__ packed) {
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_segments * (uint32_t)RANDT_PACKED_STRIDE) return;
+  const uint32_t s = e / RANDT_PACKED_STRIDE, j = e - s * RANDT_PACKED_STRIDE;
+  // source index of packed entry j, 5 bits each: 0 1 2 3 5 6 7 10 11 15 | 16..23
+  constexpr unsigned long long lo = 0ull | (1ull << 5) | (2ull << 10) | (3ull << 15) | (5ull << 20) | (6ull << 25) | (7ull << 30) | (10ull << 35) |
+                                    (11ull << 40) | (15ull << 45);
+  const uint32_t src = j < 10u ? (uint32_t)((lo >> (5u * j)) & 31ull) : j + 6u;
+  packed[e] = full[(size_t)s * RANDT_FUSED_STRIDE + src];
+}
+cudaError_t launch_pack_fused(const double* d_full, uint32_t n_segments, double* d_packed, cudaStream_t s, int* n_launches) {
+  if (n_segments == 0) return cudaSuccess;
+  const uint32_t n = n_segments * (uint32_t)RANDT_PACKED_STRIDE;
+  pack_fused_kernel<<<(n + 255u) / 256u, 256, 0, s>>>(d_full, n_segments, d_packed);
+  if (n_launches) *n_launches += 1;
+  return cudaGetLastError();
+}
+
 cudaError_t launch_eval_fused(const DeviceProblem& p, int variant, const double* d_poses, const LossParams& lp, const double* d_mu,
                               bool want_jac, double* d_out, unsigned long long* d_bad, cudaStream_t s, int* n_launches) {
   if (p.n_chunks == 0) return cudaSuccess;
