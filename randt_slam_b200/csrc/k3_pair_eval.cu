@@ -559,6 +559,27 @@ __device__ __forceinline__ void accumulate_duo(const PoseConst& kc, const LossCo
     loss_eval<LOSS>(dd[j], lc, wgt[j], hrho[j], wd[j]);
   }
   const bool use1 = two && ok[1];
+  // Nearly every duo is complete and well-conditioned: when that holds for all lanes that are here, the sums are updated without the
+  // per-accumulator selects of the general path (a warp-uniform branch).
+  if (__all_sync(__activemask(), ok[0] && use1)) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (WANT_JAC) {
+        int q = 0;
+#pragma unroll
+        for (int a = 0; a < NB; ++a) {
+          const double wa = wd[j] * N[j][a];
+#pragma unroll
+          for (int b2 = a; b2 < NB; ++b2) { acc[q] = fma(wa, N[j][b2], acc[q]); ++q; }
+          acc[NH + a] = fma(wgt[j], N[j][a], acc[NH + a]);
+        }
+      }
+      acc[NJ] += hrho[j];
+      acc[NJ + 1] += dd[j];
+    }
+    max_dd = fmax(max_dd, fmax(dd[0], dd[1]));
+    return;
+  }
   n_bad += (ok[0] ? 0u : 1u) + ((two && !ok[1]) ? 1u : 0u);
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
