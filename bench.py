@@ -512,6 +512,36 @@ def main():
                    "kept_points_per_scan": kept // len(raws), "cells_per_scan": cells // len(raws),
                    "what": "randt_filter_scan (K6, device in/out) + randt_voxelize (K1) per scan, wall clock incl. the two small D2H syncs; "
                            "the Oxford sensor delivers 4 scans/s"}
+            # the same for a batch of scans per call (several sequences side by side / a backlog): randt_filter_scans -> randt_voxelize
+            n_batch = 8 * len(raws)
+            d_raw_b = torch.cat(raws * 8).contiguous()
+            d_pts_b = torch.zeros((n_az * 64 * n_batch, 4), dtype=torch.float32, device="cuda:%d" % local)
+
+            def pre_batch():
+                off_b = ctx.filter_scans_dev(d_raw_b.data_ptr(), n_batch, n_az, n_bins, fpar, d_pts_b.data_ptr(), d_pts_b.shape[0])
+                t1 = time.perf_counter()
+                m = ctx.voxelize(d_pts_b.data_ptr(), off_b, gp, pts_on_device=True)
+                nc = m.info()[1]
+                m.close()
+                return int(off_b[-1]), nc, t1
+            pre_batch()
+            barrier()
+            t_f = t_all = 0.0
+            for _ in range(reps):
+                t0 = time.perf_counter()
+                kept_b, cells_b, t1 = pre_batch()
+                t2 = time.perf_counter()
+                t_f += t1 - t0; t_all += t2 - t0
+            t_f /= reps; t_all /= reps
+            raw_bytes = 16.0 * n_az * n_bins * n_batch
+            pk_, _ = peaks()
+            pre["batched"] = {"scans_per_call": n_batch, "scans_per_s": n_batch / t_all, "ms_per_call": t_all * 1e3,
+                              "filter_ms_per_call": t_f * 1e3, "filter_gbs": raw_bytes / t_f / 1e9, "filter_frac_of_hbm_peak": raw_bytes / t_f / 1e9 / pk_["hbm_gbs"],
+                              "raw_bytes_per_call": int(raw_bytes), "kept_points_per_call": kept_b, "cells_per_call": int(cells_b),
+                              "same_points_as_per_scan": bool(kept_b == 8 * kept),
+                              "what": "randt_filter_scans (K6 over %d scans, device in/out) + randt_voxelize (K1) per call, wall clock incl. the host "
+                                      "syncs; filter_gbs = raw bytes / wall time of the filter call" % n_batch}
+            del d_raw_b, d_pts_b
         # ---- construction-time stages: K1 voxelise and K2 associate on resident batches ----
         stages = None
         if args.pre_scans > 0:

@@ -136,6 +136,13 @@ typedef struct randt_filter_params {
 } randt_filter_params;
 RANDT_API int randt_filter_scan(randt_ctx* ctx, const float* raw4, uint32_t n_azimuths, uint32_t n_bins, const randt_filter_params* params,
                                 int raw_on_device, float* out4, int out_on_device, uint32_t cap, uint32_t* n_out);
+/* The same for n_scans scans of one shape laid back to back in raw4 (several sequences replayed side by side, or a backlog of one):
+ * every scan is filtered independently, exactly as randt_filter_scan would; out4 receives the kept points scan after scan and
+ * scan_off[n_scans + 1] (host) their offsets — together the input of randt_voxelize().  cap: capacity of out4 in points over all scans
+ * (RANDT_E_CAPACITY: scan_off[n_scans] then holds the required count). */
+RANDT_API int randt_filter_scans(randt_ctx* ctx, const float* raw4, uint32_t n_scans, uint32_t n_azimuths, uint32_t n_bins,
+                                 const randt_filter_params* params, int raw_on_device, float* out4, int out_on_device, uint32_t cap,
+                                 uint32_t* scan_off);
 
 /* ---- K1: voxelisation ---------------------------------------------------------------------------------
  * Replaces Grid::cluster (R/src/radar_preprocessing/grid.cpp:7-14), ClusterGenerator::labelClouds

@@ -102,6 +102,7 @@ _SIGS = {
     "randt_memcpy_h2d": (_i, [_vp, _vp, _vp, C.c_size_t]),
     "randt_memcpy_d2h": (_i, [_vp, _vp, _vp, C.c_size_t]),
     "randt_filter_scan": (_i, [_vp, _vp, _u32, _u32, C.POINTER(FilterParams), _i, _vp, _i, _u32, C.POINTER(_u32)]),
+    "randt_filter_scans": (_i, [_vp, _vp, _u32, _u32, _u32, C.POINTER(FilterParams), _i, _vp, _i, _u32, _vp]),
     "randt_voxelize": (_i, [_vp, _vp, _vp, _u32, C.POINTER(GridParams), _i, C.POINTER(_vp)]),
     "randt_map_upload": (_i, [_vp, _vp, _vp, _vp, _u32, _vp, C.POINTER(GridParams), C.POINTER(_vp)]),
     "randt_map_info": (_i, [_vp, C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_u32)]),
@@ -226,6 +227,23 @@ class Context:
         n = C.c_uint32(0)
         self._check(lib().randt_filter_scan(self._h, _ptr(d_raw), int(n_azimuths), int(n_bins), C.byref(fp), 1, _ptr(d_out), 1, int(cap), C.byref(n)))
         return int(n.value)
+
+    def filter_scans(self, raw4, n_scans, n_azimuths, n_bins, fp, cap=None):
+        """n_scans scans of one shape back to back -> (float32 [n, 4] kept points scan after scan, uint32 [n_scans + 1] offsets)"""
+        raw4 = _f32(raw4, (-1, 4))
+        assert len(raw4) == n_scans * n_azimuths * n_bins
+        cap = int(cap if cap is not None else max(16, len(raw4)))
+        out = np.zeros((cap, 4), np.float32); off = np.zeros(n_scans + 1, np.uint32)
+        self._check(lib().randt_filter_scans(self._h, _ptr(raw4), int(n_scans), int(n_azimuths), int(n_bins), C.byref(fp), 0, _ptr(out), 0, cap,
+                                             _ptr(off)))
+        return out[: off[-1]].copy(), off
+
+    def filter_scans_dev(self, d_raw, n_scans, n_azimuths, n_bins, fp, d_out, cap):
+        """device pointers in and out (ints); returns the uint32 [n_scans + 1] offsets (host)"""
+        off = np.zeros(n_scans + 1, np.uint32)
+        self._check(lib().randt_filter_scans(self._h, _ptr(d_raw), int(n_scans), int(n_azimuths), int(n_bins), C.byref(fp), 1, _ptr(d_out), 1,
+                                             int(cap), _ptr(off)))
+        return off
 
     # ---- K1 ----
     def voxelize(self, pts, scan_off, gp, pts_on_device=False):

@@ -530,6 +530,54 @@ int randt_filter_scan(randt_ctx* ctx, const float* raw4, uint32_t n_az, uint32_t
   return RANDT_OK;
 }
 
+int randt_filter_scans(randt_ctx* ctx, const float* raw4, uint32_t n_scans, uint32_t n_az, uint32_t n_bins, const randt_filter_params* fp,
+                       int raw_on_device, float* out4, int out_on_device, uint32_t cap, uint32_t* scan_off) {
+  if (!ctx || !fp || !scan_off || (!raw4 && n_scans && n_az && n_bins) || (!out4 && cap)) return fail(ctx, RANDT_E_INVALID, "randt_filter_scans: null argument");
+  if ((unsigned long long)n_az * n_bins > 0x7fffffffull) return fail(ctx, RANDT_E_CAPACITY, "randt_filter_scans: scan too large");
+  if ((unsigned long long)n_scans * n_az > 0x7fffffffull || n_scans > 65535u) return fail(ctx, RANDT_E_CAPACITY, "randt_filter_scans: too many scans per call");
+  CK(cudaSetDevice(ctx->device));
+  StreamScope scope__(ctx->stream);
+  for (uint32_t i = 0; i <= n_scans; ++i) scan_off[i] = 0;
+  if (n_scans == 0) return RANDT_OK;
+  const size_t n = (size_t)n_scans * n_az * n_bins;
+  float4 *d_raw = nullptr, *d_out = nullptr; uint32_t *d_peak = nullptr, *d_cnt = nullptr, *d_off = nullptr, *d_bs = nullptr; float* d_angle = nullptr;
+  int* d_status = nullptr;
+  bool own_raw = false, own_out = false;
+  int nl = 0;
+  auto cleanup = [&]() {
+    if (own_raw) dev_free(d_raw); if (own_out) dev_free(d_out);
+    dev_free(d_peak); dev_free(d_cnt); dev_free(d_off); dev_free(d_bs); dev_free(d_angle); dev_free(d_status);
+  };
+  cudaError_t e = cudaSuccess;
+  if (raw_on_device) d_raw = const_cast<float4*>(reinterpret_cast<const float4*>(raw4));
+  else { own_raw = true; e = dev_alloc(&d_raw, n); if (e == cudaSuccess && n) e = cudaMemcpyAsync(d_raw, raw4, n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream); }
+  if (out_on_device) d_out = reinterpret_cast<float4*>(out4);
+  else if (e == cudaSuccess) { own_out = true; e = dev_alloc(&d_out, cap); }
+  if (e == cudaSuccess) e = dev_alloc(&d_peak, (size_t)n_scans * n_az);
+  if (e == cudaSuccess) e = dev_alloc(&d_angle, (size_t)n_scans * n_az);
+  if (e == cudaSuccess) e = dev_alloc(&d_cnt, n_scans);
+  if (e == cudaSuccess) e = dev_alloc(&d_off, (size_t)n_scans + 1);
+  if (e == cudaSuccess) e = dev_alloc(&d_bs, n_scans / 1024 + 2);
+  if (e == cudaSuccess) e = dev_alloc(&d_status, n_scans);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_status, 0, (size_t)n_scans * sizeof(int), ctx->stream);
+  if (e == cudaSuccess) e = launch_filter_scans(d_raw, n_scans, n_az, n_bins, *fp, d_peak, d_angle, d_out, cap, d_cnt, d_off, d_bs, d_status, ctx->stream, &nl);
+  std::vector<int> h_status(n_scans, 0);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h_status.data(), d_status, (size_t)n_scans * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(scan_off, d_off, ((size_t)n_scans + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  bool bad_shape = false;
+  for (uint32_t i = 0; i < n_scans; ++i) bad_shape = bad_shape || h_status[i] == 1;
+  const bool over = scan_off[n_scans] > cap;
+  if (e == cudaSuccess && !out_on_device && !bad_shape && !over && scan_off[n_scans])
+    e = cudaMemcpy(out4, d_out, (size_t)scan_off[n_scans] * sizeof(float4), cudaMemcpyDeviceToHost);
+  cleanup();
+  if (e != cudaSuccess) return fail(ctx, RANDT_E_CUDA, "randt_filter_scans", e);
+  ctx->launches += nl;
+  if (bad_shape) return fail(ctx, RANDT_E_INVALID, "randt_filter_scans: a scan is not organised by azimuth (the reference's angle rule cuts it elsewhere)");
+  if (over) return fail(ctx, RANDT_E_CAPACITY, "randt_filter_scans: output capacity too small");
+  return RANDT_OK;
+}
+
 int randt_map_upload(randt_ctx* ctx, const float* cells, const uint32_t* npts, const uint32_t* cell_off, uint32_t n_maps, const int32_t* slot,
                      const randt_grid_params* gp, randt_map** out) {
   if (!ctx || !out || !gp || !cell_off) return fail(ctx, RANDT_E_INVALID, "randt_map_upload: null argument");

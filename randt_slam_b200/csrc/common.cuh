@@ -165,6 +165,9 @@ cudaError_t launch_cs_divergence(const float4* cells_f, const uint32_t* off_f, c
 int cs_divergence_split();
 
 // k6_filter_scan.cu
+cudaError_t launch_filter_scans(const float4* d_raw, uint32_t n_scans, uint32_t n_az, uint32_t n_bins, const randt_filter_params& fp, uint32_t* d_peak,
+                                float* d_angle, float4* d_out, uint32_t cap, uint32_t* d_counts, uint32_t* d_scan_off, uint32_t* d_block_sums,
+                                int* d_status, cudaStream_t s, int* n_launches);
 cudaError_t launch_filter_scan(const float4* d_raw, uint32_t n_az, uint32_t n_bins, const randt_filter_params& fp, uint32_t* d_peak, float* d_angle,
                                float4* d_out, uint32_t cap, uint32_t* d_n_out, int* d_status, cudaStream_t s, int* n_launches);
 

@@ -38,7 +38,8 @@ __device__ __forceinline__ float hypot_ref(float x, float y) { return (float)sqr
 __global__ void __launch_bounds__(kRowThreads) k6_row_peak_kernel(const float4* __restrict__ raw, uint32_t n_az, uint32_t n_bins, float min_d,
                                                                   float max_d, uint32_t* __restrict__ peak_idx, float* __restrict__ row_angle,
                                                                   int* __restrict__ status) {
-  const uint32_t row = blockIdx.x;
+  const uint32_t row = blockIdx.x, scan = blockIdx.y;          // a batch of scans: one grid row per scan, per-scan outputs
+  raw += (size_t)scan * n_az * n_bins; peak_idx += (size_t)scan * n_az; row_angle += (size_t)scan * n_az; status += scan;
   const float4* p = raw + (size_t)row * n_bins;
   const float4 first = __ldg(p);
   const float x0 = first.x, y0 = first.y;
@@ -93,9 +94,16 @@ __global__ void __launch_bounds__(kRowThreads) k6_row_peak_kernel(const float4* 
 
 struct FilterDev { float min_d, max_d, min_i; double beam_thr; float tf[12]; };
 
+// MODE 0: one scan, count and write in one pass (n_out[0] = kept points).  A batch (one CTA per scan) takes two passes around an
+// exclusive scan of the per-scan counts: MODE 1 counts into n_out[scan], MODE 2 writes scan `scan` at out[scan_off[scan] ...].
+template <int MODE>
 __global__ void __launch_bounds__(1024) k6_runs_kernel(const float4* __restrict__ raw, uint32_t n_az, uint32_t n_bins, FilterDev f,
                                                        const uint32_t* __restrict__ peak_idx, const float* __restrict__ row_angle,
-                                                       float4* __restrict__ out, uint32_t cap, uint32_t* __restrict__ n_out, int* __restrict__ status) {
+                                                       float4* __restrict__ out, uint32_t cap, uint32_t* __restrict__ n_out,
+                                                       const uint32_t* __restrict__ scan_off, int* __restrict__ status) {
+  const uint32_t scan = blockIdx.x;
+  raw += (size_t)scan * n_az * n_bins; peak_idx += (size_t)scan * n_az; row_angle += (size_t)scan * n_az; status += scan; n_out += scan;
+  const uint32_t w_base = MODE == 2 ? scan_off[scan] : 0u;
   // the reference's cut rule between consecutive rows: |angle(first of row r+1) - angle(first of row r)| must exceed 1e-4
   __shared__ uint32_t s_scan[1024];
   __shared__ uint32_t s_carry;
@@ -149,8 +157,8 @@ __global__ void __launch_bounds__(1024) k6_runs_kernel(const float4* __restrict_
       __syncthreads();
     }
     const uint32_t incl = s_scan[threadIdx.x], total = s_scan[blockDim.x - 1];
-    uint32_t w = s_carry + incl - cnt;
-    if (peak != kNoPeak) {
+    uint32_t w = w_base + s_carry + incl - cnt;
+    if (MODE != 1 && peak != kNoPeak) {
       for (uint32_t j = lo; j <= hi; ++j) {
         const float4 v = __ldg(raw + j);
         const float dist = hypot_ref(v.x, v.y);
@@ -172,7 +180,7 @@ __global__ void __launch_bounds__(1024) k6_runs_kernel(const float4* __restrict_
     if (threadIdx.x == 0) s_carry += total;
     __syncthreads();
   }
-  if (threadIdx.x == 0) { *n_out = s_carry; if (s_carry > cap) atomicExch(status, 2); }
+  if (threadIdx.x == 0 && MODE != 2) { *n_out = s_carry; if (MODE == 0 && s_carry > cap) atomicExch(status, 2); }
 }
 
 }  // namespace
@@ -183,8 +191,27 @@ cudaError_t launch_filter_scan(const float4* d_raw, uint32_t n_az, uint32_t n_bi
   FilterDev f; f.min_d = fp.min_range; f.max_d = fp.max_range; f.min_i = fp.min_intensity; f.beam_thr = fp.beam_distance_increment_threshold;
   for (int i = 0; i < 12; ++i) f.tf[i] = fp.sensor_to_base[i];
   k6_row_peak_kernel<<<n_az, kRowThreads, 0, s>>>(d_raw, n_az, n_bins, f.min_d, f.max_d, d_peak, d_angle, d_status);
-  k6_runs_kernel<<<1, 1024, 0, s>>>(d_raw, n_az, n_bins, f, d_peak, d_angle, d_out, cap, d_n_out, d_status);
+  k6_runs_kernel<0><<<1, 1024, 0, s>>>(d_raw, n_az, n_bins, f, d_peak, d_angle, d_out, cap, d_n_out, nullptr, d_status);
   if (n_launches) *n_launches += 2;
+  return cudaGetLastError();
+}
+
+// n_scans scans of the same shape, back to back in d_raw.  d_peak / d_angle: [n_scans * n_az]; d_counts: [n_scans]; d_scan_off: [n_scans + 1]
+// (exclusive scan of the counts, the offsets randt_voxelize takes); d_block_sums: >= n_scans / 1024 + 2; d_status: [n_scans].
+cudaError_t launch_filter_scans(const float4* d_raw, uint32_t n_scans, uint32_t n_az, uint32_t n_bins, const randt_filter_params& fp, uint32_t* d_peak,
+                                float* d_angle, float4* d_out, uint32_t cap, uint32_t* d_counts, uint32_t* d_scan_off, uint32_t* d_block_sums,
+                                int* d_status, cudaStream_t s, int* n_launches) {
+  if (n_scans == 0) return cudaMemsetAsync(d_scan_off, 0, sizeof(uint32_t), s);
+  if (n_az == 0 || n_bins == 0) return cudaMemsetAsync(d_scan_off, 0, ((size_t)n_scans + 1) * sizeof(uint32_t), s);
+  FilterDev f; f.min_d = fp.min_range; f.max_d = fp.max_range; f.min_i = fp.min_intensity; f.beam_thr = fp.beam_distance_increment_threshold;
+  for (int i = 0; i < 12; ++i) f.tf[i] = fp.sensor_to_base[i];
+  k6_row_peak_kernel<<<dim3(n_az, n_scans), kRowThreads, 0, s>>>(d_raw, n_az, n_bins, f.min_d, f.max_d, d_peak, d_angle, d_status);
+  k6_runs_kernel<1><<<n_scans, 1024, 0, s>>>(d_raw, n_az, n_bins, f, d_peak, d_angle, d_out, cap, d_counts, nullptr, d_status);
+  if (n_launches) *n_launches += 2;
+  cudaError_t e = launch_exclusive_scan_u32(d_counts, d_scan_off, n_scans, d_block_sums, s, n_launches);
+  if (e != cudaSuccess) return e;
+  k6_runs_kernel<2><<<n_scans, 1024, 0, s>>>(d_raw, n_az, n_bins, f, d_peak, d_angle, d_out, cap, d_counts, d_scan_off, d_status);
+  if (n_launches) *n_launches += 1;
   return cudaGetLastError();
 }
 

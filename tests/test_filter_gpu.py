@@ -99,3 +99,46 @@ def test_filter_scan_threshold_bands_take_the_exact_path(oracle, gpu_ctx):
     with pytest.raises(capi.RandtError) as e:
         gpu_ctx.filter_scan(raw.reshape(-1, 4), n_az, n_bins, capi.filter_params(p))
     assert e.value.code == capi.E_INVALID
+
+
+def test_filter_scans_batch_equals_scan_by_scan(oracle, gpu_ctx):
+    """randt_filter_scans: a batch of scans (incl. one whose first azimuth is empty and one that keeps nothing) gives, scan after scan,
+    exactly what randt_filter_scan / the oracle give for each, plus the offsets randt_voxelize takes"""
+    p = P.OXFORD
+    n_az, n_bins, B = 96, 500, 7
+    raws = []
+    for b in range(B):
+        r = synth.make_raw_scan(synth.scene_for(p, 30 + b), (0.1 * b, -0.05 * b, 0.01 * b), p, 40 + b, n_azimuth=n_az, n_bins=n_bins,
+                                bin_size=0.2).reshape(n_az, n_bins, 4)
+        if b == 2:
+            r[0, :, 3] = 0.0
+        if b == 4:
+            r[:, :, 3] = 0.0      # nothing above any gate: only the reference's "point 0" rule can fire, and its point fails the gates
+        raws.append(r.reshape(-1, 4))
+    fp = capi.filter_params(p, TF)
+    pts, off = gpu_ctx.filter_scans(np.concatenate(raws), B, n_az, n_bins, fp)
+    assert off[0] == 0 and off[-1] == len(pts) and (np.diff(off.astype(np.int64)) >= 0).all()
+    for b in range(B):
+        want, _ = oracle_filter(oracle, raws[b], p, TF)
+        one = gpu_ctx.filter_scan(raws[b], n_az, n_bins, fp)
+        got = pts[off[b]:off[b + 1]]
+        assert got.shape == want.shape, b
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), b
+        assert np.array_equal(one.view(np.uint32), want.view(np.uint32)), b
+    assert off[5] == off[4]                         # the silent scan keeps nothing
+    # straight into the voxeliser: same maps as voxelising every filtered scan on its own
+    gp = capi.grid_params(p)
+    m = gpu_ctx.voxelize(pts, off, gp).download()
+    for b in (0, 3, 6):
+        v = oracle.voxelize(pts[off[b]:off[b + 1]], *H.vox_args(p))
+        a, z = m["cell_off"][b], m["cell_off"][b + 1]
+        assert np.array_equal(m["cells"][a:z].view(np.uint32), v["cells"].view(np.uint32))
+    # capacity over the whole batch, and a malformed scan anywhere in the batch
+    with pytest.raises(capi.RandtError) as e:
+        gpu_ctx.filter_scans(np.concatenate(raws), B, n_az, n_bins, fp, cap=int(off[-1]) - 1)
+    assert e.value.code == capi.E_CAPACITY
+    bad = [r.copy() for r in raws]
+    bad[5].reshape(n_az, n_bins, 4)[3, 250:] = bad[5].reshape(n_az, n_bins, 4)[4, 250:]
+    with pytest.raises(capi.RandtError) as e:
+        gpu_ctx.filter_scans(np.concatenate(bad), B, n_az, n_bins, fp)
+    assert e.value.code == capi.E_INVALID
