@@ -221,6 +221,25 @@ __device__ __forceinline__ bool on_candidate(const randt_solver_options& o, cons
   return true;
 }
 
+// The per-segment state lives in memory word-major ([word][segment], 53 x 8 bytes per segment): thread s of a warp reads word i of 32
+// neighbouring segments from one 256-byte run instead of 32 sectors 424 bytes apart.
+constexpr int kStateWords = (int)(sizeof(LmState) / 8);
+static_assert(sizeof(LmState) % 8 == 0, "LmState is moved as 8-byte words");
+__device__ __forceinline__ void load_state(const LmState* __restrict__ base, uint32_t S, uint32_t s, LmState& st) {
+  const unsigned long long* mem = reinterpret_cast<const unsigned long long*>(base);
+  unsigned long long w[kStateWords];
+#pragma unroll
+  for (int i = 0; i < kStateWords; ++i) w[i] = mem[(size_t)i * S + s];
+  memcpy(&st, w, sizeof(LmState));
+}
+__device__ __forceinline__ void store_state(LmState* __restrict__ base, uint32_t S, uint32_t s, const LmState& st) {
+  unsigned long long* mem = reinterpret_cast<unsigned long long*>(base);
+  unsigned long long w[kStateWords];
+  memcpy(w, &st, sizeof(LmState));
+#pragma unroll
+  for (int i = 0; i < kStateWords; ++i) mem[(size_t)i * S + s] = w[i];
+}
+
 __global__ void __launch_bounds__(128) k4_init_kernel(uint32_t S, int np, const double* __restrict__ poses0, LmState* __restrict__ state,
                                                       double* __restrict__ eval_pose, double* __restrict__ mu, uint32_t* __restrict__ active,
                                                       double* __restrict__ rec, uint32_t* __restrict__ n_active) {
@@ -232,7 +251,7 @@ __global__ void __launch_bounds__(128) k4_init_kernel(uint32_t S, int np, const 
   for (int i = 0; i < np; ++i) { st.x[i] = poses0[(size_t)s * np + i]; eval_pose[(size_t)s * np + i] = st.x[i]; }
   st.phase = PH_INIT;
   st.mu = 1.0;
-  state[s] = st;
+  store_state(state, S, s, st);
   mu[s] = 1.0;
   active[s] = 1u;
   for (int i = 0; i < RANDT_FUSED_STRIDE; ++i) rec[(size_t)s * RANDT_FUSED_STRIDE + i] = 0.0;   // segments without pairs get no K3 record
@@ -251,7 +270,8 @@ __global__ void __launch_bounds__(64) k4_lm_step_kernel(uint32_t S, randt_solver
   typedef Dims<NP, MANIFOLD> D;
   constexpr int np = NP;
   const double* rec = rec_all + (size_t)s * RANDT_FUSED_STRIDE;
-  LmState st = state[s];
+  LmState st;
+  load_state(state, S, s, st);
   bool solve_ended = false, need_start = false;
   if (st.phase == PH_INIT) {
     st.n_blocks = (uint32_t)rec[RANDT_FUSED_N];
@@ -300,7 +320,7 @@ __global__ void __launch_bounds__(64) k4_lm_step_kernel(uint32_t S, randt_solver
     r[RANDT_REG_STATUS] = (double)st.status;
     r[RANDT_REG_TERMINATION] = (double)st.termination;
   }
-  state[s] = st;
+  store_state(state, S, s, st);
 }
 
 // ---- re-planning the K3 schedule for the segments that are still active ------------------------------------------------
