@@ -219,6 +219,11 @@ RANDT_API int randt_eval_fused(randt_ctx* ctx, const randt_problem* p, int varia
  * copy-out is what bounds a pipelined step, and a quarter of the full record is the mirrored half of H. */
 RANDT_API int randt_eval_fused_async(randt_ctx* ctx, const randt_problem* p, int variant, const double* poses, const randt_loss* loss,
                                      const double* mu_per_seg, int want_jac, int packed, double* out);
+/* Completion of individual async calls: randt_ctx_async_count() = number of randt_eval_fused_async calls issued on this context so far
+ * (the ticket of the latest one); randt_ctx_wait_async(ticket) returns once that call's records are in host memory and its input
+ * buffers may be reused (it may wait for a later call of the same parity: calls complete in order). */
+RANDT_API uint64_t randt_ctx_async_count(const randt_ctx* ctx);
+RANDT_API int randt_ctx_wait_async(randt_ctx* ctx, uint64_t ticket);
 RANDT_API int randt_eval_fused_dev(randt_ctx* ctx, const randt_problem* p, int variant, const double* d_poses, const randt_loss* loss,
                                    const double* d_mu_per_seg, int want_jac, double* d_out);
 /* Cost of ONE segment's pair list at many candidate poses (the inner loop of Matcher::estimateTransformGlobalBNB,

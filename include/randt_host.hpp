@@ -236,5 +236,9 @@ RANDT_API int randt_hostapi_odometry(int device, const randt_grid_params* gp, co
                                      double reject_translation, double reject_rotation, double* pose_io4, int* accepted);
 RANDT_API int randt_hostapi_export(int device, const randt_grid_params* gp, const float* pts4, uint32_t n_pts, double* mean3 /*[cap][3]*/,
                                    double* cov6 /*[cap][6]*/, uint32_t cap, uint32_t* n_cells);
+/* `steps` pipelined evaluations through randt_eval_fused_async from a C++ caller (what bench.py times as e2e): step i uses the i-th of
+ * `depth` caller-owned pinned buffer sets (poses [S][np] in, records out); a set is reused once its previous call has delivered. */
+RANDT_API int randt_hostapi_eval_async_loop(randt_ctx* ctx, const randt_problem* problem, int variant, const randt_loss* loss, double* const* poses_ring,
+                                            double* const* out_ring, uint32_t depth, uint32_t steps, int packed);
 RANDT_API const char* randt_hostapi_last_error(void);
 }

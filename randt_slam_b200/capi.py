@@ -120,6 +120,8 @@ _SIGS = {
     "randt_eval_emit": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "randt_eval_emit_dev": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "randt_eval_fused": (_i, [_vp, _vp, _i, _vp, C.POINTER(Loss), _vp, _i, _vp]),
+    "randt_ctx_async_count": (_u64, [_vp]),
+    "randt_ctx_wait_async": (_i, [_vp, _u64]),
     "randt_eval_fused_async": (_i, [_vp, _vp, _i, _vp, C.POINTER(Loss), _vp, _i, _i, _vp]),
     "randt_eval_fused_dev": (_i, [_vp, _vp, _i, _vp, C.POINTER(Loss), _vp, _i, _vp]),
     "randt_sweep_costs": (_i, [_vp, _vp, _u32, _i, _vp, _u32, C.POINTER(Loss), _vp]),
@@ -244,6 +246,13 @@ class Context:
         self._check(lib().randt_filter_scans(self._h, _ptr(d_raw), int(n_scans), int(n_azimuths), int(n_bins), C.byref(fp), 1, _ptr(d_out), 1,
                                              int(cap), _ptr(off)))
         return off
+
+    def async_count(self):
+        """ticket of the latest eval_fused_async call on this context"""
+        return int(lib().randt_ctx_async_count(self._h))
+
+    def wait_async(self, ticket):
+        self._check(lib().randt_ctx_wait_async(self._h, C.c_uint64(int(ticket))))
 
     # ---- K1 ----
     def voxelize(self, pts, scan_off, gp, pts_on_device=False):

@@ -30,7 +30,9 @@ struct StreamRef {
   cudaStream_t copy = nullptr;
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
   double* ring[2] = {nullptr, nullptr}; size_t ring_cap[2] = {0, 0}; uint64_t ring_n = 0;
+  const void* known_pinned[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; unsigned known_n = 0;   // buffers already checked
   cudaStream_t copy_out = nullptr; cudaEvent_t ev_d2h[2] = {nullptr, nullptr};
+  cudaEvent_t ev_call[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // delivery of call t: ev_call[t & 7]
   double* oring[2] = {nullptr, nullptr}; size_t oring_cap[2] = {0, 0};
   ~StreamRef() {
     cudaSetDevice(device);
@@ -39,6 +41,7 @@ struct StreamRef {
     if (own && stream) cudaStreamSynchronize(stream);
     for (int i = 0; i < 2; ++i) {
       if (ev_d2h[i]) cudaEventDestroy(ev_d2h[i]);
+      for (int q = i; q < 8; q += 2) if (ev_call[q]) cudaEventDestroy(ev_call[q]);
       if (oring[i]) cudaFree(oring[i]);
       if (ev_in[i]) cudaEventDestroy(ev_in[i]);
       if (ev_done[i]) cudaEventDestroy(ev_done[i]);
@@ -324,7 +327,7 @@ DeviceProblem view(const randt_problem* p) {
   DeviceProblem d;
   d.cells_m = p->cells_m; d.cells_f = p->cells_f; d.pairs = p->pairs; d.duos = p->duos; d.duo_recs = p->duo_recs; d.duo_p0 = p->duo_p0; d.seg_off = p->seg_off; d.chunks = p->chunks; d.n_chunks = p->n_chunks; d.warp_off = p->warp_off; d.n_warps = p->n_warps;
   d.seg_first_tile = p->seg_first_tile; d.n_segments = p->S; d.n_pairs = p->P; d.partials = p->partials; d.seg_counters = p->seg_counters;
-  d.seg_active = nullptr; d.plan_static = 1u;
+  d.seg_active = nullptr; d.plan_static = 1u; d.out_packed = 0u;
   return d;
 }
 
@@ -903,8 +906,17 @@ int randt_eval_emit(randt_ctx* ctx, const randt_problem* cp, int variant, const 
   return RANDT_OK;
 }
 
+namespace {
+int eval_fused_dev_impl(randt_ctx* ctx, const randt_problem* p, int variant, const double* d_poses, const randt_loss* loss,
+                        const double* d_mu_per_seg, int want_jac, double* d_out, bool packed);
+}
 int randt_eval_fused_dev(randt_ctx* ctx, const randt_problem* p, int variant, const double* d_poses, const randt_loss* loss,
                          const double* d_mu_per_seg, int want_jac, double* d_out) {
+  return eval_fused_dev_impl(ctx, p, variant, d_poses, loss, d_mu_per_seg, want_jac, d_out, false);
+}
+namespace {
+int eval_fused_dev_impl(randt_ctx* ctx, const randt_problem* p, int variant, const double* d_poses, const randt_loss* loss,
+                        const double* d_mu_per_seg, int want_jac, double* d_out, bool packed) {
   if (!ctx || !p || !d_poses || !d_out) return fail(ctx, RANDT_E_INVALID, "randt_eval_fused_dev: null argument");
   if (check_variant(ctx, variant)) return RANDT_E_INVALID;
   LossParams lp;
@@ -912,14 +924,16 @@ int randt_eval_fused_dev(randt_ctx* ctx, const randt_problem* p, int variant, co
   CK(cudaSetDevice(ctx->device));
   StreamScope scope__(ctx->stream);
   // segments without pairs produce no tile: clear their records up front
-  if (p->has_empty_segment) CK(cudaMemsetAsync(d_out, 0, (size_t)p->S * RANDT_FUSED_STRIDE * sizeof(double), ctx->stream));
+  if (p->has_empty_segment) CK(cudaMemsetAsync(d_out, 0, (size_t)p->S * (packed ? RANDT_PACKED_STRIDE : RANDT_FUSED_STRIDE) * sizeof(double), ctx->stream));
   int nl = 0;
   DeviceProblem v = view(p);
   v.chunks = p->chunks_full; v.n_chunks = p->n_chunks_full; v.warp_off = p->warp_off_full;   // every segment is evaluated: packed schedule
+  v.out_packed = packed ? 1u : 0u;
   CK(launch_eval_fused(v, variant, d_poses, lp, d_mu_per_seg, want_jac != 0, d_out, ctx->d_bad, ctx->stream, &nl));
   ctx->launches += nl;
   return RANDT_OK;
 }
+}  // namespace
 
 int randt_eval_fused(randt_ctx* ctx, const randt_problem* cp, int variant, const double* poses, const randt_loss* loss,
                      const double* mu_per_seg, int want_jac, double* out) {
@@ -957,17 +971,19 @@ int randt_eval_fused_async(randt_ctx* ctx, const randt_problem* cp, int variant,
   if (check_variant(ctx, variant)) return RANDT_E_INVALID;
   randt_problem* p = const_cast<randt_problem*>(cp);
   CK(cudaSetDevice(ctx->device));
-  auto pinned_dev_ptr = [](const void* h) -> void* {
-    cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, h) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) return at.devicePointer;
-    cudaGetLastError();
-    return nullptr;
-  };
-  double* out_dev = static_cast<double*>(pinned_dev_ptr(out));
-  if (!out_dev || !pinned_dev_ptr(poses) || (mu_per_seg && !pinned_dev_ptr(mu_per_seg)))
-    return fail(ctx, RANDT_E_INVALID, "randt_eval_fused_async: poses, mu_per_seg and out must be pinned host memory (randt_host_alloc)");
-  if (p->S == 0) return RANDT_OK;
   StreamRef& r = *ctx->sref;
+  // a pageable buffer would turn the copies synchronous: insist on pinned memory (checked once per buffer: callers cycle through a few;
+  // a stale entry after the caller freed and reallocated the address only costs that synchronous copy)
+  auto is_pinned = [&r](const void* h) -> bool {
+    for (const void* k : r.known_pinned) if (k == h) return true;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, h) == cudaSuccess && at.type == cudaMemoryTypeHost) { r.known_pinned[r.known_n++ & 7u] = h; return true; }
+    cudaGetLastError();
+    return false;
+  };
+  if (!is_pinned(out) || !is_pinned(poses) || (mu_per_seg && !is_pinned(mu_per_seg)))
+    return fail(ctx, RANDT_E_INVALID, "randt_eval_fused_async: poses, mu_per_seg and out must be pinned host memory (randt_host_alloc)");
+  if (p->S == 0) { r.ring_n++; return RANDT_OK; }      // nothing to do, but the call still has a ticket
   if (!r.copy) {
     CK(cudaStreamCreateWithFlags(&r.copy, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&r.copy_out, cudaStreamNonBlocking));
@@ -976,6 +992,7 @@ int randt_eval_fused_async(randt_ctx* ctx, const randt_problem* cp, int variant,
       CK(cudaEventCreateWithFlags(&r.ev_done[i], cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&r.ev_d2h[i], cudaEventDisableTiming));
     }
+    for (int i = 0; i < 8; ++i) CK(cudaEventCreateWithFlags(&r.ev_call[i], cudaEventDisableTiming));
   }
   const int np = np_of(variant);
   const int slot = (int)(r.ring_n++ & 1);
@@ -995,7 +1012,7 @@ int randt_eval_fused_async(randt_ctx* ctx, const randt_problem* cp, int variant,
   CK(cudaStreamWaitEvent(ctx->stream, r.ev_in[slot], 0));
   // Records go to a device slot and leave on a third stream: a DMA copy moves the 192 S bytes at the full PCIe rate while the next
   // call's kernel runs (stores from the kernel straight into mapped host memory, as the blocking call does, reach ~3/4 of that rate).
-  const size_t n_full = (size_t)p->S * RANDT_FUSED_STRIDE, n_pack = packed ? (size_t)p->S * RANDT_PACKED_STRIDE : 0, n_out = n_full + n_pack;
+  const size_t n_out = (size_t)p->S * (packed ? RANDT_PACKED_STRIDE : RANDT_FUSED_STRIDE);   // K3 writes either layout itself
   CK(cudaStreamWaitEvent(ctx->stream, r.ev_d2h[slot], 0));     // the copy-out of two calls ago has drained this slot
   if (r.oring_cap[slot] < n_out) {
     if (r.oring[slot]) CK(cudaFreeAsync(r.oring[slot], ctx->stream));
@@ -1004,19 +1021,26 @@ int randt_eval_fused_async(randt_ctx* ctx, const randt_problem* cp, int variant,
     r.oring_cap[slot] = n_out;
   }
   double* d_out = r.oring[slot];
-  int rc = randt_eval_fused_dev(ctx, p, variant, d_in, loss, mu_per_seg ? d_in + n_pose : nullptr, want_jac, d_out);
+  int rc = eval_fused_dev_impl(ctx, p, variant, d_in, loss, mu_per_seg ? d_in + n_pose : nullptr, want_jac, d_out, packed != 0);
   if (rc) return rc;
-  const double* d_ship = d_out; size_t n_ship = n_full;
-  if (packed) {
-    int nl = 0;
-    CK(launch_pack_fused(d_out, p->S, d_out + n_full, ctx->stream, &nl));
-    ctx->launches += nl;
-    d_ship = d_out + n_full; n_ship = n_pack;
-  }
+  const double* d_ship = d_out; const size_t n_ship = n_out;
   CK(cudaEventRecord(r.ev_done[slot], ctx->stream));
   CK(cudaStreamWaitEvent(r.copy_out, r.ev_done[slot], 0));
   CK(cudaMemcpyAsync(out, d_ship, n_ship * sizeof(double), cudaMemcpyDeviceToHost, r.copy_out));
   CK(cudaEventRecord(r.ev_d2h[slot], r.copy_out));             // randt_ctx_sync() waits for the copy-out stream as well
+  CK(cudaEventRecord(r.ev_call[r.ring_n & 7u], r.copy_out));   // ring_n is this call's ticket (randt_ctx_wait_async)
+  return RANDT_OK;
+}
+
+uint64_t randt_ctx_async_count(const randt_ctx* ctx) { return (ctx && ctx->sref) ? ctx->sref->ring_n : 0; }
+
+int randt_ctx_wait_async(randt_ctx* ctx, uint64_t ticket) {
+  if (!ctx) return RANDT_E_INVALID;
+  StreamRef& r = *ctx->sref;
+  if (ticket == 0 || ticket > r.ring_n) return fail(ctx, RANDT_E_INVALID, "randt_ctx_wait_async: no such call");
+  if (!r.copy_out) return RANDT_OK;
+  // the event belongs to call `ticket`, or — if the caller ran more than eight calls ahead — to a later call, which completes after it
+  CK(cudaEventSynchronize(r.ev_call[ticket & 7u]));
   return RANDT_OK;
 }
 

@@ -57,6 +57,7 @@ struct DeviceProblem {
   uint32_t n_chunks;
   const uint32_t* warp_off;  // [n_warps+1]
   uint32_t n_warps;
+  uint32_t out_packed;       // FUSED only: 1 = write RANDT_PACKED_STRIDE-double records (upper triangle of H) instead of RANDT_FUSED_STRIDE
   uint32_t plan_static;      // 1: chunks / warp_off are the problem's immutable schedule; 0: produced by a preceding kernel (solver re-plan)
   const uint32_t* seg_first_tile;  // [S+1]
   uint32_t n_segments;
@@ -84,7 +85,6 @@ cudaError_t launch_permute_duos(const Duo* in, const uint32_t* tile_rec_begin, c
                                 Duo* out, cudaStream_t s, int* n_launches);
 cudaError_t launch_build_duo_records(const float4* cells_m, const float4* cells_f, const Duo* duos, uint32_t n_duos, DuoRec* recs,
                                      uint32_t* duo_p0, cudaStream_t s, int* n_launches);
-cudaError_t launch_pack_fused(const double* d_full, uint32_t n_segments, double* d_packed, cudaStream_t s, int* n_launches);
 cudaError_t launch_sweep_costs(const DeviceProblem& p, uint32_t pair_begin, uint32_t pair_end, int variant, const double* d_poses,
                                uint32_t n_poses, const LossParams& lp, double* d_cost, cudaStream_t s, int* n_launches);
 

@@ -333,8 +333,8 @@ __device__ __forceinline__ double warp_max_nonneg(double v) {
 // that owns it (`mine` = the caller's own slot total; owner(slot) maps a slot to its lane), scales it, and the warp stores the
 // record with one coalesced 8-byte-per-lane store.  Slots: [NH upper triangle (i <= j, row-major)] [NB gradient] [cost] [sum dd].
 template <int VARIANT, bool WANT_JAC, typename OwnerFn>
-__device__ __forceinline__ void write_segment_out(double mine, double max_dd, const PoseConst& k, uint32_t n_pairs, double* __restrict__ out,
-                                                  int lane, OwnerFn owner) {
+__device__ __forceinline__ void write_segment_out(double mine, double max_dd, const PoseConst& k, uint32_t n_pairs, double* __restrict__ out_base,
+                                                  uint32_t seg, uint32_t packed, int lane, OwnerFn owner) {
   constexpr int NB = VarTraits<VARIANT>::NB;
   constexpr int NH = NB * (NB + 1) / 2;
   constexpr int NJ = WANT_JAC ? NH + NB : 0;
@@ -365,7 +365,14 @@ __device__ __forceinline__ void write_segment_out(double mine, double max_dd, co
   double val = f * v;
   if (e == 21) val = max_dd > 0.0 ? max_dd * rsqrt_fast(max_dd) : 0.0;   // max raw residual
   if (e == 23) val = (double)n_pairs;
-  if (e < RANDT_FUSED_STRIDE) out[e] = val;
+  if (!packed) {
+    if (e < RANDT_FUSED_STRIDE) out_base[(size_t)seg * RANDT_FUSED_STRIDE + e] = val;
+  } else {
+    // RANDT_PACKED_*: of H only row <= column (index in the row-major upper triangle), everything after H moves up by six
+    const int r = e >> 2, c = e & 3;
+    const int pk = e < 16 ? r * 4 - (r * (r - 1)) / 2 + (c - r) : e - 6;
+    if (e < RANDT_FUSED_STRIDE && (e >= 16 || c >= r)) out_base[(size_t)seg * RANDT_PACKED_STRIDE + pk] = val;
+  }
 }
 
 // ---- the software-pipelined tile stream of one warp ------------------------------------------------------------------
@@ -500,7 +507,7 @@ __device__ __forceinline__ void finish_tile(const DeviceProblem& P, const double
   const uint32_t bad = __reduce_add_sync(kFull, n_bad);
   const uint32_t n_pairs_seg = P.seg_off[seg + 1] - P.seg_off[seg];
   if (solo) {
-    write_segment_out<VARIANT, WANT_JAC>(mine, mx, kc, n_pairs_seg, out + (size_t)seg * RANDT_FUSED_STRIDE, lane, [](int sl) { return 2 * sl; });
+    write_segment_out<VARIANT, WANT_JAC>(mine, mx, kc, n_pairs_seg, out, seg, P.out_packed, lane, [](int sl) { return 2 * sl; });
     if (lane == 0 && bad) atomicAdd(bad_counter, (unsigned long long)bad);
   } else {
     // partial record of this tile: [NS sums][max dd][bad], one entry per lane
@@ -526,7 +533,7 @@ __device__ __forceinline__ void finish_tile(const DeviceProblem& P, const double
       }
       const double mx_all = __shfl_sync(kFull, v, NS);
       const double bad_all = __shfl_sync(kFull, v, NS + 1);
-      write_segment_out<VARIANT, WANT_JAC>(v, mx_all, kc, n_pairs_seg, out + (size_t)seg * RANDT_FUSED_STRIDE, lane, [](int sl) { return sl; });
+      write_segment_out<VARIANT, WANT_JAC>(v, mx_all, kc, n_pairs_seg, out, seg, P.out_packed, lane, [](int sl) { return sl; });
       if (lane == 0) {
         if (bad_all != 0.0) atomicAdd(bad_counter, (unsigned long long)bad_all);
         P.seg_counters[seg] = 0u;   // re-arm for the next launch
@@ -948,25 +955,6 @@ cudaError_t launch_build_duo_records(const float4* cells_m, const float4* cells_
   if (n_duos == 0) return cudaSuccess;
   const uint64_t n = (uint64_t)n_duos * 9u;
   build_duo_records_kernel<<<(unsigned)((n + 255u) / 256u), 256, 0, s>>>(cells_m, cells_f, duos, n_duos, reinterpret_cast<float4*>(recs), duo_p0);
-  if (n_launches) *n_launches += 1;
-  return cudaGetLastError();
-}
-
-// 24-double records -> 18-double records (RANDT_PACKED_*): the upper triangle of H, then g, cost, max r, sum r^2, n
-__global__ void __launch_bounds__(256) pack_fused_kernel(const double* __restrict__ full, uint32_t n_segments, double* __restrict__ packed) {
-  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n_segments * (uint32_t)RANDT_PACKED_STRIDE) return;
-  const uint32_t s = e / RANDT_PACKED_STRIDE, j = e - s * RANDT_PACKED_STRIDE;
-  // source index of packed entry j, 5 bits each: 0 1 2 3 5 6 7 10 11 15 | 16..23
-  constexpr unsigned long long lo = 0ull | (1ull << 5) | (2ull << 10) | (3ull << 15) | (5ull << 20) | (6ull << 25) | (7ull << 30) | (10ull << 35) |
-                                    (11ull << 40) | (15ull << 45);
-  const uint32_t src = j < 10u ? (uint32_t)((lo >> (5u * j)) & 31ull) : j + 6u;
-  packed[e] = full[(size_t)s * RANDT_FUSED_STRIDE + src];
-}
-cudaError_t launch_pack_fused(const double* d_full, uint32_t n_segments, double* d_packed, cudaStream_t s, int* n_launches) {
-  if (n_segments == 0) return cudaSuccess;
-  const uint32_t n = n_segments * (uint32_t)RANDT_PACKED_STRIDE;
-  pack_fused_kernel<<<(n + 255u) / 256u, 256, 0, s>>>(d_full, n_segments, d_packed);
   if (n_launches) *n_launches += 1;
   return cudaGetLastError();
 }

@@ -535,6 +535,24 @@ int randt_hostapi_odometry(int device, const randt_grid_params* gp, const float*
   });
 }
 
+int randt_hostapi_eval_async_loop(randt_ctx* ctx, const randt_problem* problem, int variant, const randt_loss* loss, double* const* poses_ring,
+                                  double* const* out_ring, uint32_t depth, uint32_t steps, int packed) {
+  return guarded([&] {
+    if (!ctx || !problem || !poses_ring || !out_ring || depth < 1) throw randt::Error(RANDT_E_INVALID, "eval_async_loop: needs buffer sets");
+    auto check = [&](int rc) { if (rc != RANDT_OK) throw randt::Error(rc, randt_last_error(ctx)); };
+    std::vector<uint64_t> ticket(depth, 0);
+    for (uint32_t i = 0; i < steps; ++i) {
+      const uint32_t j = i % depth;
+      // buffer set j is reused: the call that had it (step i - depth) must have delivered.  The device slots are ordered by events inside
+      // the library, so the host may run up to `depth` steps ahead and the next upload is never waiting for the host.
+      if (ticket[j]) check(randt_ctx_wait_async(ctx, ticket[j]));
+      check(randt_eval_fused_async(ctx, problem, variant, poses_ring[j], loss, nullptr, 1, packed, out_ring[j]));
+      ticket[j] = randt_ctx_async_count(ctx);
+    }
+    check(randt_ctx_sync(ctx));
+  });
+}
+
 int randt_hostapi_export(int device, const randt_grid_params* gp, const float* pts4, uint32_t n_pts, double* mean3, double* cov6, uint32_t cap,
                          uint32_t* n_cells) {
   return guarded([&] {

@@ -19,7 +19,7 @@ def lib():
         capi.lib()   # librandt_gpu.so first (the host library links against it)
         L = C.CDLL(LIB_PATH)
         L.randt_hostapi_last_error.restype = C.c_char_p
-        for name in ("randt_hostapi_loop_constraints", "randt_hostapi_cost_function", "randt_hostapi_bnb", "randt_hostapi_export", "randt_hostapi_odometry"):
+        for name in ("randt_hostapi_loop_constraints", "randt_hostapi_cost_function", "randt_hostapi_bnb", "randt_hostapi_export", "randt_hostapi_odometry", "randt_hostapi_eval_async_loop"):
             getattr(L, name).restype = C.c_int
         _lib = L
     return _lib
@@ -97,3 +97,11 @@ def odometry(gp, fixed_scans, fixed_poses, moving_pts, prior, k, loss_function_s
                                         C.c_double(ndt_weight), C.c_int(int(optimize_on_manifold)), C.c_double(reject_translation),
                                         C.c_double(reject_rotation), _pf(pose), C.byref(ok)))
     return pose, bool(ok.value)
+
+
+def eval_async_loop(ctx, prob, loss, poses_ring, out_ring, steps, packed=True, variant=0):
+    """`steps` pipelined randt_eval_fused_async calls issued from C++ over caller-owned pinned buffer sets (capi.PinnedArray)"""
+    d = len(poses_ring)
+    pp = (C.c_void_p * d)(*[a.ctypes.data for a in poses_ring]); oo = (C.c_void_p * d)(*[a.ctypes.data for a in out_ring])
+    _check(lib().randt_hostapi_eval_async_loop(ctx._h, prob._h, C.c_int(variant), C.byref(loss) if loss is not None else None, pp, oo, C.c_uint32(d),
+                                               C.c_uint32(int(steps)), C.c_int(int(packed))))

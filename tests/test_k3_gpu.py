@@ -217,6 +217,14 @@ def test_fused_async_pipeline_matches_the_blocking_call(oracle, gpu_ctx, with_em
             ho.a[...] = -1.0
         for i, (hp, hm, ho) in enumerate(bufs):
             prob.eval_fused_async(hp.a, ho.a, loss, mu_per_seg=hm.a if i % 2 else None, packed=bool(i % 2))
+        # tickets: every call can be waited for on its own (calls complete in order)
+        t_last = gpu_ctx.async_count()
+        gpu_ctx.wait_async(t_last - 3)
+        assert not np.any(bufs[n_calls - 4][2].a == -1.0)
+        gpu_ctx.wait_async(t_last)
+        assert not np.any(bufs[n_calls - 1][2].a == -1.0)
+        with pytest.raises(capi.RandtError):
+            gpu_ctx.wait_async(t_last + 1)
         gpu_ctx.sync()
         for i, (hp, hm, ho) in enumerate(bufs):
             want = prob.eval_fused(hp.a.copy(), loss, mu_per_seg=hm.a.copy() if i % 2 else None)
