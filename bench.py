@@ -237,7 +237,8 @@ def run_reference(args, p, loss):
 
 
 def workload_name(p):
-    return "configs[1]/[3]: Oxford-shape scan (400 beams, ~5k pts) vs 10-scan submap, %s params, SE(2)+intensity, batched independent problems" % p.name
+    shape = "Oxford-shape scan (400 beams, ~5k pts)" if p.max_range >= 50.0 else "%s-shape scan (400 beams)" % p.name
+    return "configs[1]/[3]: %s vs 10-scan submap, %s params, SE(2)+intensity, batched independent problems" % (shape, p.name)
 
 
 def build_host_workload(p, n_problems, seed0):
@@ -299,10 +300,14 @@ def main():
     ap.add_argument("--reg-cpu-sample", type=int, default=48, help="registrations the oracle solves for the CPU comparison")
     ap.add_argument("--pre-scans", type=int, default=8, help="raw Oxford-size scans in the preprocessing leg (0 disables it)")
     ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--preset", choices=sorted(P.PRESETS), default="oxford",
+                    help="shipped parameter file the scans, maps and losses follow (SURVEY §8d C2 fixes oxford for the headline workload: an "
+                         "Oxford-shape scan against parameters_oxford.yaml; BASELINE.json's configs[1] words it 'indoor params' — "
+                         "`--preset indoor` runs that reading: 400-beam indoor-shape scans, 0.5 m cells, k = 4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    p = P.OXFORD
+    p = P.PRESETS[args.preset]
 
     from randt_slam_b200 import capi
     # loss exactly as estimateLoopConstraint sets it (ndt_matcher.cpp:479): Barron(loop_closure_scale, alpha, mu), weight 1
