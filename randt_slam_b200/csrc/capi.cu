@@ -392,6 +392,8 @@ void randt_ctx_destroy(randt_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->sref && ctx->sref->copy) cudaStreamSynchronize(ctx->sref->copy);           // async evaluations still uploading / delivering
+  if (ctx->sref && ctx->sref->copy_out) cudaStreamSynchronize(ctx->sref->copy_out);
   dev_free(ctx->d_bad);
   delete ctx;      // the stream itself goes with the last object that was created on this context (StreamRef)
 }
