@@ -69,7 +69,10 @@ struct DeviceProblem {
 
 constexpr int kTileDuos = 256;    // most duos per tile (one warp owns a tile)
 constexpr int kMinTileDuos = 32;  // tile length for small problems
-constexpr int kK3Threads = 128;   // threads per CTA in the pair-evaluation kernels
+#ifndef RANDT_K3_THREADS
+#define RANDT_K3_THREADS 128
+#endif
+constexpr int kK3Threads = RANDT_K3_THREADS;   // threads per CTA in the pair-evaluation kernels
 #ifndef RANDT_K3_MIN_CTAS
 #define RANDT_K3_MIN_CTAS 4       // CTAs per SM the K3 register allocation is bounded for
 #endif
