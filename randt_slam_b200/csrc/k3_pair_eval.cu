@@ -17,13 +17,14 @@
 // FUSED mode never forms r or J: with w = weight*rho'(dd), H += (w/dd) N N^T, g += w N, cost += weight*rho(dd)/2, and for
 // the shipped alpha = -2 loss w/dd and rho come from ONE reciprocal.  fp64 pipe: ~110 instructions per pair (was 193).
 //
-// Work decomposition (B200: 148 SMs, fp64 64 lanes/clk/SM — the co-limiter next to HBM).  The frozen pair list is cut into
-// tiles that never straddle a segment (= pose); ONE WARP owns a tile: lanes stride the tile's pairs (coalesced uint2 pair
-// loads, 3 x float4 gathers per cell), partial sums stay in registers, a butterfly (transposing) shuffle reduction folds
-// them in a fixed order (deterministic), lane 0 writes the 24-double record.  No shared memory, no block barrier.  Each warp
-// walks its tiles as one software-pipelined stream of 32-pair chunks — pair indices are fetched two chunks ahead, the
-// cell gathers and the next tile's pose one chunk ahead — so HBM latency overlaps the fp64 work of the current chunk.
-// Segments longer than one tile are folded by the last warp to finish (ticket counter), in tile order.
+// Work decomposition (B200: 148 SMs, fp64 64 lanes/clk/SM — the co-limiter next to HBM).  Pairs are grouped into duos (two pairs
+// that share their moving cell, one lane each) and the duos of a segment (= pose) into tiles; ONE WARP owns a tile.  The host assigns
+// tiles to the 148 x 16 resident warps of a persistent grid (longest-processing-time first) and lays the duo records — moving cell
+// and both fixed cells inlined, 144 B — out in that order, so a warp streams ONE contiguous range: every chunk of 32 records is a
+// single bulk copy (TMA, cp.async.bulk + mbarrier) into a two-stage shared-memory ring, described by a 16-byte chunk descriptor.
+// Partial sums stay in registers; at a tile's end they are transposed through the just-consumed stage buffer and added in a fixed
+// order (deterministic), and lanes e < 24 write the record.  Segments longer than one tile are folded by the last warp to finish
+// (ticket counter), in tile order.  Launches chain with programmatic dependent launch (the schedule is fetched before the wait).
 #include <math.h>
 
 #include "common.cuh"
@@ -376,12 +377,11 @@ __device__ __forceinline__ void write_segment_out(double mine, double max_dd, co
 }
 
 // ---- the software-pipelined tile stream of one warp ------------------------------------------------------------------
-// Every warp walks tiles w, w + n_warps, ... as a stream of 32-duo chunks (a lane owns one duo = up to two pairs that share
-// their moving cell).  A chunk's inputs are staged in shared memory by cp.async (LDGSTS): 9 x 16 B per lane for the three
-// cells, plus (first chunk of a tile, lane 0) the pose and mu of the tile's segment and the chunk's descriptor.  kStages
-// chunks are in flight per warp, so registers hold nothing but the accumulators while HBM latency is covered; each lane reads
-// back only what it copied itself (no cross-lane hazard on the cell slots).  The two pairs of a duo are evaluated as two
-// independent instruction streams (ILP for the half-rate fp64 pipe).
+// Every warp walks its chunk list (P.warp_off) as a stream of 32-duo chunks (a lane owns one duo = up to two pairs that share their
+// moving cell).  Lane 0 issues ONE bulk copy per chunk (32 x 144 B, completion on the stage's mbarrier) and, for the first chunk of a
+// tile, cp.async copies of the tile's pose and mu.  kStages chunks are in flight per warp, so registers hold nothing but the
+// accumulators while HBM latency is covered.  The two pairs of a duo are evaluated as two independent instruction streams (ILP for
+// the half-rate fp64 pipe).
 constexpr int kWarpsPerCta = kK3Threads / 32;
 #ifndef RANDT_K3_STAGES
 #define RANDT_K3_STAGES 2
