@@ -1,6 +1,7 @@
 // C-ABI layer: contexts, device-resident maps and problems, and the extern "C" entry points declared in include/randt_gpu.h.
-// Host code only orchestrates (allocation, small prefix sums over per-map counts, tile lists); all per-point / per-cell /
-// per-pair work runs in the kernels of k1_voxelize.cu, k2_associate.cu and k3_pair_eval.cu.
+// Host code only orchestrates (stream-ordered allocation, the per-map offsets, the tile schedule and chunk lists, the polling of the
+// batched solver, the copy pipeline of the async evaluation); all per-point / per-cell / per-pair / per-registration work runs in the
+// kernels of k1_voxelize.cu, k2_associate.cu, k3_pair_eval.cu, k4_lm_step.cu, k5_cs_divergence.cu and k6_filter_scan.cu.
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>

@@ -9,8 +9,8 @@
 //
 // One CTA per scan.  Points are read with coalesced float4 loads; labels are binned with a STABLE parallel counting sort
 // (each warp owns a contiguous slice of the scan, per-warp histograms in shared memory, warp-level __match_any_sync ranking)
-// so that every cell sees its points in original order; one thread per occupied label then accumulates the two passes
-// sequentially in float32.  Kept cells are written in ascending-label order into a per-scan padded region and compacted
+// so that every cell sees its points in original order; one warp per kept cell then accumulates the two passes in float32 in exactly
+// that order (coalesced loads of 32 points, the sequential sum carried through shuffles).  Kept cells are written in ascending-label order into a per-scan padded region and compacted
 // across the batch by a second kernel.
 #include <float.h>
 
