@@ -69,3 +69,24 @@ def test_version_and_error_paths_without_a_gpu(built_lib):
         # the product path fails loudly without a device: no CPU fallback
         with pytest.raises(capi.RandtError):
             capi.Context(0)
+
+
+def test_record_layout_constants_match_the_header():
+    """RANDT_FUSED_* / RANDT_PACKED_* / RANDT_REG_* enumerators in include/randt_gpu.h == the constants the Python bindings index with"""
+    src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    enums = {k: int(v) for k, v in re.findall(r"\b(RANDT_(?:FUSED|PACKED|REG)_[A-Z_]+)\s*=\s*(\d+)", src)}
+    assert enums["RANDT_FUSED_STRIDE"] == capi.FUSED_STRIDE == 24
+    assert (enums["RANDT_FUSED_H"], enums["RANDT_FUSED_G"], enums["RANDT_FUSED_COST"], enums["RANDT_FUSED_MAXR"], enums["RANDT_FUSED_SUMSQ"],
+            enums["RANDT_FUSED_N"]) == (capi.FUSED_H, capi.FUSED_G, capi.FUSED_COST, capi.FUSED_MAXR, capi.FUSED_SUMSQ, capi.FUSED_N)
+    assert enums["RANDT_PACKED_STRIDE"] == capi.PACKED_STRIDE == 18
+    # packed = upper triangle of the 4x4 H row by row, then everything after H
+    want = [4 * r + c for r in range(4) for c in range(r, 4)] + list(range(16, 24))
+    assert capi._PACKED_SRC == want
+    assert (enums["RANDT_PACKED_G"], enums["RANDT_PACKED_COST"], enums["RANDT_PACKED_MAXR"], enums["RANDT_PACKED_SUMSQ"], enums["RANDT_PACKED_N"]) == \
+        (want.index(16), want.index(20), want.index(21), want.index(22), want.index(23))
+    import numpy as np
+    full = np.arange(48, dtype=np.float64).reshape(2, 24)
+    assert np.array_equal(capi.pack_fused(full)[1], full[1][want])
+    if "RANDT_REG_STRIDE" in enums:
+        assert enums["RANDT_REG_STRIDE"] == capi.REG_STRIDE
+        assert enums["RANDT_REG_SCORE"] == capi.REG_SCORE and enums["RANDT_REG_STATUS"] == capi.REG_STATUS
