@@ -240,5 +240,13 @@ RANDT_API int randt_hostapi_export(int device, const randt_grid_params* gp, cons
  * `depth` caller-owned pinned buffer sets (poses [S][np] in, records out); a set is reused once its previous call has delivered. */
 RANDT_API int randt_hostapi_eval_async_loop(randt_ctx* ctx, const randt_problem* problem, int variant, const randt_loss* loss, double* const* poses_ring,
                                             double* const* out_ring, uint32_t depth, uint32_t steps, int packed);
+/* The K3 work schedule (randt_slam_b200/csrc/schedule.hpp: tiles, longest-processing-time assignment to `max_warps` warps, chunk plans A and
+ * B) for the given per-segment duo offsets, without a device: what tests/test_schedule_cpu.py checks.  counts[5] = tiles, warps, chunks
+ * of plan A, chunks of plan B, records; a NULL output array is skipped; arrays must hold cap_tiles (+1) / cap_chunks / max_warps+1 /
+ * n_segments+1 entries (RANDT_E_CAPACITY otherwise, counts still filled).  tiles4 / plan_*4: 4 x uint32 per entry (seg, begin, end, part /
+ * duo_begin, meta, seg, part). */
+RANDT_API int randt_hostapi_build_schedule(const uint32_t* duo_off, uint32_t n_segments, uint32_t max_warps, uint32_t* counts, uint32_t* tiles4,
+                                           uint32_t cap_tiles, uint32_t* plan_a4, uint32_t* plan_b4, uint32_t cap_chunks, uint32_t* woff_a,
+                                           uint32_t* woff_b, uint32_t* tile_rec_begin, uint32_t* tile_duo_begin, uint32_t* first);
 RANDT_API const char* randt_hostapi_last_error(void);
 }

@@ -40,7 +40,8 @@ def _newer(target, deps):
 def build_all(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "nvcc")
     os.makedirs(OBJ, exist_ok=True)
-    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "..", "include", "randt_gpu.h"), os.path.abspath(__file__)]
+    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "schedule.hpp"), os.path.join(HERE, "..", "include", "randt_gpu.h"),
+               os.path.abspath(__file__)]
     jobs = []
     for src, extra in UNITS.items():
         s = os.path.join(CSRC, src)
@@ -62,7 +63,7 @@ def build_all(force=False, verbose=False):
     if force or jobs or _newer(LIB, objs):
         run([nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart_static", "-lpthread", "-ldl", "-lrt"])
     # host layer: plain C++17 over the C-ABI (no CUDA headers), linked against librandt_gpu.so next to it
-    if force or _newer(HOST_LIB, [HOST_SRC, HOST_HDR, LIB]):
+    if force or _newer(HOST_LIB, [HOST_SRC, HOST_HDR, LIB, os.path.join(CSRC, "schedule.hpp")]):
         cxx = os.environ.get("CXX", "g++")
         run([cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-Wall", "-o", HOST_LIB, HOST_SRC,
              "-L" + HERE, "-lrandt_gpu", "-Wl,-rpath,$ORIGIN"])

@@ -179,106 +179,14 @@ int finish_problem(randt_ctx* ctx, randt_problem* p) {
     fprintf(stderr, "[randt] finish_problem %-18s %8.1f us\n", what, std::chrono::duration<double, std::micro>(t - t_prev).count());
     t_prev = t;
   };
-  std::vector<Tile> tiles;
-  std::vector<uint32_t> first(p->S + 1, 0);
-  // one warp owns a tile.  Big batches: tiles of up to kTileDuos duos (a whole ~200-pair registration per warp, no partials);
-  // small problems: shorter tiles so that the pairs still spread over the SMs (each extra tile costs one partial record).
-  uint32_t tile_duos = (p->n_duos / (uint32_t)(kSmCount * 4) + 31u) / 32u * 32u;
-  tile_duos = std::max<uint32_t>(kMinTileDuos, std::min<uint32_t>(tile_duos, kTileDuos));
-  for (uint32_t s = 0; s < p->S; ++s) {
-    first[s] = (uint32_t)tiles.size();
-    uint32_t part = 0;
-    for (uint32_t b = p->h_duo_off[s]; b < p->h_duo_off[s + 1]; b += tile_duos) {
-      Tile t; t.seg = s; t.begin = b; t.end = std::min(p->h_duo_off[s + 1], b + tile_duos); t.part = part++;
-      tiles.push_back(t);
-    }
-  }
-  first[p->S] = (uint32_t)tiles.size();
-  lap("tiles");
-  // Balanced static schedule: longest-processing-time assignment of tiles to the resident warps of the persistent grid (a tile
-  // costs its duos plus a fixed prologue/reduce/emit overhead).  Registration problems differ in size, and one warp walks only ~7
-  // of them per launch at the bench size, so round-robin striding leaves warps (and whole SMs) idle at the tail.
-  const uint32_t n_warps = std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)kK3MaxWarps, (uint32_t)tiles.size()));
-  // (tile costs are small integers: counting sort and a bucket queue make this linear in the number of tiles)
-  const uint32_t T = (uint32_t)tiles.size();
-  std::vector<uint32_t> mine_off(n_warps + 1, 0), mine(T);    // tiles of warp w, ascending: mine[mine_off[w] .. mine_off[w + 1])
-  {
-    auto cost = [&](uint32_t t) { return (tiles[t].end - tiles[t].begin) + 24u; };
-    const uint32_t max_cost = tile_duos + 24u;
-    std::vector<uint32_t> bucket(max_cost + 2, 0), order(T), warp_of(T);
-    for (uint32_t t = 0; t < T; ++t) ++bucket[max_cost - cost(t) + 1];
-    for (uint32_t c = 0; c <= max_cost; ++c) bucket[c + 1] += bucket[c];
-    for (uint32_t t = 0; t < T; ++t) order[bucket[max_cost - cost(t)]++] = t;      // descending cost, ties in tile order
-    // least-loaded warp through a bucket queue over the (integer) loads: the minimum load never decreases, and greedy assignment
-    // keeps every load below average + max_cost
-    uint64_t total = 0;
-    for (uint32_t t = 0; t < T; ++t) total += cost(t);
-    const uint32_t n_loads = (uint32_t)(total / n_warps) + 2u * max_cost + 2u;
-    std::vector<int32_t> head(n_loads, -1), next(n_warps, -1);
-    for (uint32_t w = n_warps; w-- > 0;) { next[w] = head[0]; head[0] = (int32_t)w; }
-    uint32_t cur = 0;
-    for (uint32_t t : order) {
-      while (head[cur] < 0) ++cur;
-      const uint32_t w = (uint32_t)head[cur];
-      head[cur] = next[w];
-      warp_of[t] = w; ++mine_off[w + 1];
-      const uint32_t nl = cur + cost(t);
-      next[w] = head[nl]; head[nl] = (int32_t)w;
-    }
-    for (uint32_t w = 0; w < n_warps; ++w) mine_off[w + 1] += mine_off[w];
-    std::vector<uint32_t> fill(mine_off.begin(), mine_off.end() - 1);
-    for (uint32_t t = 0; t < T; ++t) mine[fill[warp_of[t]]++] = t;
-  }
-  lap("lpt");
-  // Records are laid out in schedule order (warp after warp, tile after tile), so that a warp streams one contiguous range and the
-  // tail of one tile and the head of the next can share a chunk.  Two chunk lists over the same records:
-  //   plan A (full evaluation): consecutive solo tiles of a warp are packed — the last, partly filled chunk of a tile takes the first
-  //           duos of the next tile (kChunkSplit), which keeps the lanes busy when problems are only ~3 chunks long;
-  //   plan B (solver with active flags, EMIT): every chunk belongs to one tile.
-  std::vector<uint32_t> tile_rec_begin, tile_duo_begin;
-  tile_rec_begin.reserve(tiles.size() + 1); tile_duo_begin.reserve(tiles.size());
-  std::vector<ChunkDesc> planA, planB;
-  planA.reserve(p->n_duos / 32 + tiles.size() + 1); planB.reserve(p->n_duos / 32 + tiles.size() + 1);
-  std::vector<uint32_t> woffA(n_warps + 1, 0), woffB(n_warps + 1, 0);
-  uint32_t rec = 0;
-  for (uint32_t w = 0; w < n_warps; ++w) {
-    bool open = false;      // the last chunk of plan A ends a solo tile, is not split yet and has free lanes
-    for (uint32_t q = mine_off[w]; q < mine_off[w + 1]; ++q) {
-      const uint32_t t = mine[q];
-      const Tile& tl = tiles[t];
-      const bool solo = first[tl.seg + 1] - first[tl.seg] == 1u;
-      const uint32_t len = tl.end - tl.begin, rb = rec;
-      tile_rec_begin.push_back(rb); tile_duo_begin.push_back(tl.begin);
-      rec += len;
-      const uint32_t part = first[tl.seg] + tl.part;
-      for (uint32_t o = 0; o < len; o += 32u) {
-        ChunkDesc c;
-        c.duo_begin = rb + o; c.seg = tl.seg; c.part = part;
-        c.meta = std::min(32u, len - o) | (o == 0 ? kChunkFirst : 0u) | (o + 32u >= len ? kChunkLast : 0u) | (solo ? kChunkSolo : 0u);
-        planB.push_back(c);
-      }
-      uint32_t o = 0;
-      if (solo && open) {   // this tile starts in the free lanes of the previous tile's last chunk
-        ChunkDesc& pc = planA.back();
-        const uint32_t n_old = pc.meta & kChunkCountMask, take = std::min(32u - n_old, len);
-        pc.meta = (pc.meta & ~kChunkCountMask) | (n_old + take) | kChunkSplit | (n_old << kChunkSplitShift) | (take == len ? kChunkNewLast : 0u);
-        pc.part = tl.seg;
-        o = take;
-      }
-      open = false;
-      for (; o < len; o += 32u) {
-        ChunkDesc c;
-        c.duo_begin = rb + o; c.seg = tl.seg; c.part = part;
-        const uint32_t n = std::min(32u, len - o);
-        c.meta = n | (o == 0 ? kChunkFirst : 0u) | (o + 32u >= len ? kChunkLast : 0u) | (solo ? kChunkSolo : 0u);
-        planA.push_back(c);
-        open = solo && (o + 32u >= len) && n < 32u;
-      }
-    }
-    woffA[w + 1] = (uint32_t)planA.size(); woffB[w + 1] = (uint32_t)planB.size();
-  }
-  tile_rec_begin.push_back(rec);
-  lap("chunk plans");
+  Schedule sch;
+  build_schedule(p->h_duo_off.data(), p->S, (uint32_t)kK3MaxWarps, sch);     // schedule.hpp: tiles, LPT assignment, plan A / plan B
+  const std::vector<Tile>& tiles = sch.tiles;
+  const std::vector<uint32_t>& first = sch.first;
+  const std::vector<ChunkDesc>&planA = sch.planA, &planB = sch.planB;
+  const std::vector<uint32_t>&woffA = sch.woffA, &woffB = sch.woffB, &tile_rec_begin = sch.tile_rec_begin, &tile_duo_begin = sch.tile_duo_begin;
+  const uint32_t n_warps = sch.n_warps;
+  lap("schedule");
   p->n_warps = n_warps;
   p->n_chunks = (uint32_t)planB.size(); p->n_chunks_full = (uint32_t)planA.size();
   p->n_tiles = (uint32_t)tiles.size();

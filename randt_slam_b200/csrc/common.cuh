@@ -8,9 +8,10 @@
 
 #include "../../include/randt_gpu.h"
 
+#include "schedule.hpp"
+
 namespace randt {
 
-constexpr int kSmCount = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
 
 struct LossParams {  // host-evaluated constants of the loss that do not depend on mu
   int kind;
@@ -30,20 +31,6 @@ constexpr uint32_t kNoCell = 0xffffffffu;
 // pair is marked by the bit pattern kNoSecondPair in the first float of the third cell (a NaN payload no arithmetic produces).
 struct __align__(16) DuoRec { float4 v[9]; };
 constexpr uint32_t kNoSecondPair = 0xffffffffu;
-
-// A work tile: duos [begin, end) of segment `seg`; `part` = index of the tile inside its segment.  One warp owns a tile.
-struct Tile { uint32_t seg, begin, end, part; };
-// What the kernels walk: a tile cut into chunks of <= 32 duos (one per lane).  meta: bits 0..5 = duos in the chunk (0 marks the end of
-// a warp's list), kChunkFirst / kChunkLast = first / last chunk of its tile, kChunkSolo = the tile is its segment's only tile.
-// part = index of the tile's partial record (seg_first_tile[seg] + tile.part), used when a segment spans several tiles.
-struct __align__(16) ChunkDesc { uint32_t duo_begin, meta, seg, part; };
-constexpr uint32_t kChunkCountMask = 0x3fu, kChunkFirst = 0x100u, kChunkLast = 0x200u, kChunkSolo = 0x400u;
-// Split chunks (full-evaluation schedule only): lanes [0, sp) finish one solo tile (segment `seg`, which therefore has kChunkLast) and
-// lanes [sp, count) start the next solo tile of the same warp, whose segment is carried in `part`; sp sits in bits 16..21.
-// kChunkNewLast: that second tile also ends inside this chunk.  The record table is laid out in schedule order so that the two
-// tiles' records are adjacent.
-constexpr uint32_t kChunkSplit = 0x800u, kChunkNewLast = 0x1000u;
-constexpr int kChunkSplitShift = 16;
 
 struct DeviceProblem {
   const float4* cells_m;   // 3 x float4 per cell
@@ -67,8 +54,6 @@ struct DeviceProblem {
   const uint32_t* seg_active;  // [S] or NULL: segments with a zero flag are skipped by the fused kernel (batched solver)
 };
 
-constexpr int kTileDuos = 256;    // most duos per tile (one warp owns a tile)
-constexpr int kMinTileDuos = 32;  // tile length for small problems
 #ifndef RANDT_K3_THREADS
 #define RANDT_K3_THREADS 128
 #endif

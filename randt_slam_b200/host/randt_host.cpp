@@ -10,6 +10,8 @@
 #include <array>
 #include <tuple>
 
+#include "../csrc/schedule.hpp"   // the K3 schedule builder (plain C++), exposed for the CPU tests
+
 namespace randt {
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -550,6 +552,29 @@ int randt_hostapi_eval_async_loop(randt_ctx* ctx, const randt_problem* problem, 
       ticket[j] = randt_ctx_async_count(ctx);
     }
     check(randt_ctx_sync(ctx));
+  });
+}
+
+int randt_hostapi_build_schedule(const uint32_t* duo_off, uint32_t n_segments, uint32_t max_warps, uint32_t* counts, uint32_t* tiles4, uint32_t cap_tiles,
+                                 uint32_t* plan_a4, uint32_t* plan_b4, uint32_t cap_chunks, uint32_t* woff_a, uint32_t* woff_b,
+                                 uint32_t* tile_rec_begin, uint32_t* tile_duo_begin, uint32_t* first) {
+  return guarded([&] {
+    if (!duo_off || !counts || max_warps == 0) throw randt::Error(RANDT_E_INVALID, "build_schedule: null argument");
+    randt::Schedule sch;
+    randt::build_schedule(duo_off, n_segments, max_warps, sch);
+    counts[0] = (uint32_t)sch.tiles.size(); counts[1] = sch.n_warps; counts[2] = (uint32_t)sch.planA.size(); counts[3] = (uint32_t)sch.planB.size();
+    counts[4] = sch.tile_rec_begin.back();
+    if (sch.tiles.size() > cap_tiles || sch.planA.size() > cap_chunks || sch.planB.size() > cap_chunks)
+      throw randt::Error(RANDT_E_CAPACITY, "build_schedule: output arrays too small");
+    static_assert(sizeof(randt::Tile) == 16 && sizeof(randt::ChunkDesc) == 16, "4 x uint32 records");
+    if (tiles4 && !sch.tiles.empty()) std::memcpy(tiles4, sch.tiles.data(), sch.tiles.size() * 16);
+    if (plan_a4 && !sch.planA.empty()) std::memcpy(plan_a4, sch.planA.data(), sch.planA.size() * 16);
+    if (plan_b4 && !sch.planB.empty()) std::memcpy(plan_b4, sch.planB.data(), sch.planB.size() * 16);
+    if (woff_a) std::memcpy(woff_a, sch.woffA.data(), sch.woffA.size() * 4);
+    if (woff_b) std::memcpy(woff_b, sch.woffB.data(), sch.woffB.size() * 4);
+    if (tile_rec_begin) std::memcpy(tile_rec_begin, sch.tile_rec_begin.data(), sch.tile_rec_begin.size() * 4);
+    if (tile_duo_begin && !sch.tile_duo_begin.empty()) std::memcpy(tile_duo_begin, sch.tile_duo_begin.data(), sch.tile_duo_begin.size() * 4);
+    if (first) std::memcpy(first, sch.first.data(), sch.first.size() * 4);
   });
 }
 

@@ -19,7 +19,7 @@ def lib():
         capi.lib()   # librandt_gpu.so first (the host library links against it)
         L = C.CDLL(LIB_PATH)
         L.randt_hostapi_last_error.restype = C.c_char_p
-        for name in ("randt_hostapi_loop_constraints", "randt_hostapi_cost_function", "randt_hostapi_bnb", "randt_hostapi_export", "randt_hostapi_odometry", "randt_hostapi_eval_async_loop"):
+        for name in ("randt_hostapi_loop_constraints", "randt_hostapi_cost_function", "randt_hostapi_bnb", "randt_hostapi_export", "randt_hostapi_odometry", "randt_hostapi_eval_async_loop", "randt_hostapi_build_schedule"):
             getattr(L, name).restype = C.c_int
         _lib = L
     return _lib
@@ -105,3 +105,20 @@ def eval_async_loop(ctx, prob, loss, poses_ring, out_ring, steps, packed=True, v
     pp = (C.c_void_p * d)(*[a.ctypes.data for a in poses_ring]); oo = (C.c_void_p * d)(*[a.ctypes.data for a in out_ring])
     _check(lib().randt_hostapi_eval_async_loop(ctx._h, prob._h, C.c_int(variant), C.byref(loss) if loss is not None else None, pp, oo, C.c_uint32(d),
                                                C.c_uint32(int(steps)), C.c_int(int(packed))))
+
+
+def build_schedule(duo_off, max_warps):
+    """The K3 schedule for per-segment duo offsets (no device needed) -> dict of numpy arrays"""
+    duo_off = np.ascontiguousarray(duo_off, np.uint32)
+    S = len(duo_off) - 1
+    n_duos = int(duo_off[-1])
+    cap_t = n_duos // 32 + S + 2; cap_c = n_duos // 32 + 2 * cap_t + 2
+    counts = np.zeros(5, np.uint32)
+    tiles = np.zeros((cap_t, 4), np.uint32); pa = np.zeros((cap_c, 4), np.uint32); pb = np.zeros((cap_c, 4), np.uint32)
+    wa = np.zeros(max_warps + 1, np.uint32); wb = np.zeros(max_warps + 1, np.uint32)
+    trb = np.zeros(cap_t + 1, np.uint32); tdb = np.zeros(cap_t, np.uint32); first = np.zeros(S + 1, np.uint32)
+    _check(lib().randt_hostapi_build_schedule(_pf(duo_off), C.c_uint32(S), C.c_uint32(int(max_warps)), _pf(counts), _pf(tiles), C.c_uint32(cap_t), _pf(pa),
+                                              _pf(pb), C.c_uint32(cap_c), _pf(wa), _pf(wb), _pf(trb), _pf(tdb), _pf(first)))
+    nt, nw, na, nb, nr = (int(c) for c in counts)
+    return dict(tiles=tiles[:nt], n_warps=nw, plan_a=pa[:na], plan_b=pb[:nb], woff_a=wa[: nw + 1], woff_b=wb[: nw + 1], tile_rec_begin=trb[: nt + 1],
+                tile_duo_begin=tdb[:nt], first=first, n_records=nr)
