@@ -90,3 +90,49 @@ def test_record_layout_constants_match_the_header():
     if "RANDT_REG_STRIDE" in enums:
         assert enums["RANDT_REG_STRIDE"] == capi.REG_STRIDE
         assert enums["RANDT_REG_SCORE"] == capi.REG_SCORE and enums["RANDT_REG_STATUS"] == capi.REG_STATUS
+
+
+def test_header_is_plain_c_and_every_symbol_links_from_c(built_lib, tmp_path):
+    """the drop-in boundary is a C ABI: include/randt_gpu.h compiles as C99 (-pedantic), and a C translation unit that takes the address
+    of every declared entry point links against librandt_gpu.so"""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no gcc")
+    syms = declared_symbols()
+    src = tmp_path / "abi.c"
+    src.write_text('#include "randt_gpu.h"\n#include <stdio.h>\nint main(void) {\n  const void* f[] = {%s};\n'
+                   '  printf("%%d %%d\\n", (int)(sizeof(f) / sizeof(f[0])), randt_version());\n  return 0;\n}\n'
+                   % ", ".join("(const void*)%s" % s_ for s_ in syms))
+    exe = tmp_path / "abi"
+    lib_dir = os.path.dirname(built_lib)
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                        "-L", lib_dir, "-lrandt_gpu", "-Wl,-rpath," + lib_dir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-fsyntax-only", "-x", "c", HEADER], capture_output=True, text=True)
+    assert r.returncode == 0 and not r.stderr.strip(), r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.split() == [str(len(syms)), "100"]
+
+
+def test_host_layer_compiles_against_a_ceres_cost_function(tmp_path):
+    """include/randt_host.hpp derives NdtCostFunction from <ceres/cost_function.h> when that header exists (it does not in this image):
+    the branch is compiled here against a header with Ceres 2.1.0's CostFunction interface, so Evaluate's signature, the protected
+    setters and the deleted copy are all what a real ceres::Problem expects"""
+    import shutil
+    import subprocess
+    gxx = shutil.which("g++")
+    if not gxx:
+        pytest.skip("no g++")
+    fake = os.path.join(ROOT, "tests", "fake_ceres")
+    host = os.path.join(ROOT, "randt_slam_b200", "host", "randt_host.cpp")
+    r = subprocess.run([gxx, "-std=c++17", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I", fake, host], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    probe = tmp_path / "probe.cpp"
+    probe.write_text('#include "randt_host.hpp"\n#include <type_traits>\n'
+                     'static_assert(std::is_base_of<ceres::CostFunction, randt::NdtCostFunction>::value, "derives from ceres");\n'
+                     'static_assert(!std::is_abstract<randt::NdtCostFunction>::value, "Evaluate is overridden");\n'
+                     'static_assert(!std::is_copy_constructible<randt::NdtCostFunction>::value, "ceres forbids copies");\nint main() { return 0; }\n')
+    r = subprocess.run([gxx, "-std=c++17", "-fsyntax-only", "-I", fake, "-I", os.path.join(ROOT, "include"), str(probe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
