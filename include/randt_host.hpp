@@ -11,7 +11,7 @@
 //   randt::SE2d             <- Sophus::SE2d (storage order [cos, sin, tx, ty], group product, exp / log of the rotation)
 //
 // No Eigen / Sophus / Ceres / PCL / ROS types appear here (none exist in this image); INTEGRATION.md shows the few lines that
-// adapt them in the reference tree.  Every method throws randt::Error (std::runtime_error) on a C-ABI failure — there is no CPU
+// adapt them in the reference tree.  The classes are exported from librandt_host.so (link with -lrandt_host -lrandt_gpu).  Every method throws randt::Error (std::runtime_error) on a C-ABI failure — there is no CPU
 // fallback.
 #pragma once
 #include <cstddef>
@@ -52,13 +52,13 @@ class CostFunction {
 
 namespace randt {
 
-struct Error : std::runtime_error {
+struct RANDT_API Error : std::runtime_error {
   int code;
   Error(int c, const std::string& what) : std::runtime_error(what), code(c) {}
 };
 
 // Sophus::SE2d stand-in: unit complex number + translation, data() in Sophus' storage order.
-struct SE2d {
+struct RANDT_API SE2d {
   double v[4] = {1.0, 0.0, 0.0, 0.0};   // cos, sin, tx, ty
   SE2d() {}
   SE2d(double theta, double tx, double ty);
@@ -71,7 +71,7 @@ struct SE2d {
 
 // The parameter fields of the reference this path reads (R/include/ndt_slam/ndt_slam_parameters.h:17-50,56-84), already derived as
 // NDTSlam::readParameters leaves them (size in cells after the int /= resolution; n_clusters = int((2 max_range / resolution)^2)).
-struct NDTMapParameters {
+struct RANDT_API NDTMapParameters {
   double resolution = 1.0;
   int size_x = 50, size_y = 50;
   double max_neighbour_manhattan_distance = 4.0;
@@ -98,7 +98,7 @@ struct NDTMatcherParameters {
   int csm_n_iter = 2;
 };
 
-class Context {
+class RANDT_API Context {
  public:
   explicit Context(int device = 0, void* cuda_stream = nullptr);
   ~Context();
@@ -113,7 +113,7 @@ class Context {
 };
 
 // A batch of B independent NDT maps resident on the device (B = 1 is the reference's Map).
-class Map {
+class RANDT_API Map {
  public:
   Map(Context& ctx, const NDTMapParameters& p, uint32_t n_maps = 1);   // Map::initialize: empty maps
   ~Map();
@@ -157,7 +157,7 @@ class Map {
 // extra entry sqrt(2 (sum rho/2 - sum rho' r^2/2)) with a zero Jacobian, so that 1/2 |residuals|^2 equals the robustified cost ceres
 // would report for the P blocks, and J^T J / J^T r equal what ceres accumulates with its per-block Corrector (exact for rho'' <= 0,
 // i.e. every Barron alpha < 2 and Welsch).  With no loss set the residuals and Jacobians are the raw ones and the extra entry is 0.
-class NdtCostFunction : public ceres::CostFunction {
+class RANDT_API NdtCostFunction : public ceres::CostFunction {
  public:
   NdtCostFunction(Context& ctx, randt_problem* problem /*takes ownership*/, int variant);
   ~NdtCostFunction() override;
@@ -177,7 +177,7 @@ class NdtCostFunction : public ceres::CostFunction {
   mutable std::vector<double> r_, J_;
 };
 
-class Matcher {
+class RANDT_API Matcher {
  public:
   explicit Matcher(Context& ctx) : ctx_(&ctx) {}
   void initialize(const NDTMatcherParameters& parameters) { parameters_ = parameters; }

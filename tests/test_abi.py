@@ -136,3 +136,24 @@ def test_host_layer_compiles_against_a_ceres_cost_function(tmp_path):
                      'static_assert(!std::is_copy_constructible<randt::NdtCostFunction>::value, "ceres forbids copies");\nint main() { return 0; }\n')
     r = subprocess.run([gxx, "-std=c++17", "-fsyntax-only", "-I", fake, "-I", os.path.join(ROOT, "include"), str(probe)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_cpp_example_links_against_the_exported_host_classes(built_lib, tmp_path):
+    """examples/local_fuser_flow.cpp (the reference's per-scan flow on include/randt_host.hpp) compiles, links against librandt_host.so /
+    librandt_gpu.so, and — without a GPU — fails loudly instead of falling back to anything"""
+    import shutil
+    import subprocess
+    gxx = shutil.which("g++")
+    if not gxx:
+        pytest.skip("no g++")
+    lib_dir = os.path.dirname(built_lib)
+    exe = tmp_path / "flow"
+    r = subprocess.run([gxx, "-std=c++17", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "local_fuser_flow.cpp"),
+                        "-L", lib_dir, "-lrandt_host", "-lrandt_gpu", "-Wl,-rpath," + lib_dir, "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    import torch
+    if torch.cuda.is_available():
+        assert out.returncode == 0 and "cells exported" in out.stdout, out.stdout + out.stderr
+    else:
+        assert out.returncode == 1 and "randt error" in out.stderr and "CUDA" in out.stderr
