@@ -65,7 +65,10 @@ def build_all(force=False, verbose=False):
     # host layer: plain C++17 over the C-ABI (no CUDA headers), linked against librandt_gpu.so next to it
     if force or _newer(HOST_LIB, [HOST_SRC, HOST_HDR, LIB, os.path.join(CSRC, "schedule.hpp")]):
         cxx = os.environ.get("CXX", "g++")
-        run([cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-Wall", "-o", HOST_LIB, HOST_SRC,
+        # RANDT_HOST_CXXFLAGS: e.g. "-I/usr/include/eigen3 -I<ceres>/include" so that the host layer is compiled against the real
+        # ceres/cost_function.h of the tree it is going to be linked into
+        run([cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-Wall"] + os.environ.get("RANDT_HOST_CXXFLAGS", "").split() +
+            ["-o", HOST_LIB, HOST_SRC,
              "-L" + HERE, "-lrandt_gpu", "-Wl,-rpath,$ORIGIN"])
     return LIB
 
