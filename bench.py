@@ -700,9 +700,20 @@ def main():
                 c1, cN, cit = cpu_registrations(p, host, poses, min(args.reg_cpu_sample, S), threads)
                 line["registrations"]["cpu_baseline"] = {"value": cN, "single_thread_value": c1, "cores": threads, "kind": "port", "mean_iterations": cit,
                                                          "sample": "first %d problems" % min(args.reg_cpu_sample, S)}
+            # BASELINE.md B3 (informational): the closed form (what a hand-optimised CPU path would evaluate) on one thread,
+            # residual + Jacobian per pair without loss or accumulation
+            P_s = int(host["seg"][n_s])
+            cf_reps = 0; t0 = time.perf_counter()
+            while time.perf_counter() - t0 < 1.0:
+                for s_ in range(min(n_s, 64)):
+                    a_, b_ = int(host["seg"][s_]), int(host["seg"][s_ + 1])
+                    O.eval_pairs(0, host["cells_m"], host["cells_f"], host["pm"][a_:b_], host["pf"][a_:b_], poses[s_], 1)
+                cf_reps += 1
+            cf_rate = cf_reps * int(host["seg"][min(n_s, 64)]) / (time.perf_counter() - t0)
             line["cpu_baseline"] = {"value": vN, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": "first %d problems (%d pairs) x %d passes, Jet<4> autodiff + corrector + J^T J" % (n_s, int(host["seg"][n_s]), reps),
-                                    "single_thread_value": v1, "gpu_vs_oracle_max_rel_err_on_sample": err}
+                                    "sample": "first %d problems (%d pairs) x %d passes, Jet<4> autodiff + corrector + J^T J" % (n_s, P_s, reps),
+                                    "single_thread_value": v1, "closed_form_single_thread_value": cf_rate,
+                                    "gpu_vs_oracle_max_rel_err_on_sample": err}
         emit(line)
     if world > 1:
         dist.destroy_process_group()
