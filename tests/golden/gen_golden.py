@@ -212,10 +212,53 @@ def gen_merge(seed=13):
     return cases
 
 
+def gen_fused(seed=17):
+    """Per-pose robustified normal equations as ceres accumulates them for P residual blocks that share one pose, each block with
+    ScaledLoss(rho, weight) and the Corrector of the rho'' <= 0 branch (residual and Jacobian row scaled by sqrt(weight rho')):
+    H = sum weight rho'(r^2) J^T J,  g = sum weight rho'(r^2) r J^T,  cost = 1/2 sum weight rho(r^2);  plus max r and sum r^2."""
+    rng = np.random.default_rng(seed)
+    cases = []
+    for (variant, kind, a, alpha, mu, weight, n_pairs) in [(0, "barron", 1.0, -2.0, 1.0, 1.0, 7), (0, "barron", 2.0, -1.0, 1.21, 0.37, 9),
+                                                             (2, "welsch", 1.5, 0.0, 2.0, 1.0, 6), (1, "barron", 1.5, -1.5, 1.0, 2.5, 5),
+                                                             (3, "none", 1.0, 2.0, 1.0, 1.0, 4)]:
+        th = rng.uniform(-0.4, 0.4); tx, ty = rng.uniform(-1, 1, 2)
+        params = [math.cos(th), math.sin(th), tx, ty] if variant <= 1 else [tx, ty, th]
+        pm = [mp.mpf(p) for p in params]
+        n = len(params)
+        H = [[mp.mpf(0)] * n for _ in range(n)]; g = [mp.mpf(0)] * n; cost = mp.mpf(0); max_r = mp.mpf(0); sum_sq = mp.mpf(0)
+        cells_m, cells_f = [], []
+        for _ in range(n_pairs):
+            cm = random_cell(rng); cf = random_cell(rng)
+            x = math.cos(th) * float(cm[0]) - math.sin(th) * float(cm[1]) + tx
+            y = math.sin(th) * float(cm[0]) + math.cos(th) * float(cm[1]) + ty
+            cf[0] = np.float32(x + rng.normal(0, 0.5)); cf[1] = np.float32(y + rng.normal(0, 0.5)); cf[2] = np.float32(float(cm[2]) + rng.normal(0, 10))
+            r = residual(variant, pm, cm, cf); J = jacobian(variant, pm, cm, cf)
+            sq = r * r
+            if kind == "barron":
+                rho = barron(sq, mp.mpf(a), mp.mpf(alpha), mp.mpf(mu))
+            elif kind == "welsch":
+                rho = welsch(sq, mp.mpf(a), mp.mpf(mu))
+            else:
+                rho = (sq, mp.mpf(1), mp.mpf(0))
+            assert rho[2] <= 0
+            w1 = mp.mpf(weight) * rho[1]
+            for i in range(n):
+                g[i] += w1 * r * J[i]
+                for j in range(n):
+                    H[i][j] += w1 * J[i] * J[j]
+            cost += mp.mpf(weight) * rho[0] / 2
+            max_r = max(max_r, r); sum_sq += sq
+            cells_m.append([float(v) for v in cm]); cells_f.append([float(v) for v in cf])
+        cases.append(dict(variant=variant, kind=kind, a=a, alpha=alpha, mu=mu, weight=weight, params=[float(p) for p in params], cells_m=cells_m,
+                          cells_f=cells_f, H=[[float(v) for v in row] for row in H], g=[float(v) for v in g], cost=float(cost), max_r=float(max_r),
+                          sum_sq=float(sum_sq)))
+    return cases
+
+
 def main():
     data = dict(
         note="generated by tests/golden/gen_golden.py (mpmath %s, 50 digits); independent of oracle/ and of the CUDA kernels" % mp.__version__,
-        pairs=gen_pairs(), losses=gen_losses(), labels=gen_labels(), cell_stats=gen_cell_stats(), merges=gen_merge())
+        pairs=gen_pairs(), losses=gen_losses(), labels=gen_labels(), cell_stats=gen_cell_stats(), merges=gen_merge(), fused=gen_fused())
     with open(os.path.join(HERE, "ndt_golden.json"), "w") as f:
         json.dump(data, f, indent=0)
     print("wrote", os.path.join(HERE, "ndt_golden.json"), {k: len(v) for k, v in data.items() if isinstance(v, list)})

@@ -57,6 +57,24 @@ def test_golden_losses(oracle, golden):
         assert np.allclose(rho_w, 0.37 * rho, rtol=1e-15, atol=0)
 
 
+def test_golden_fused_normal_equations(oracle, golden):
+    """per-pose robustified normal equations (ScaledLoss + Corrector, rho'' <= 0) of a handful of blocks, all four functors and three losses,
+    against the 50-digit evaluation: H, g 1e-9 of their largest entry, cost / max r / sum r^2 1e-10"""
+    assert len(golden["fused"]) >= 5
+    for c in golden["fused"]:
+        kind = {"barron": oracle.LOSS_BARRON, "welsch": oracle.LOSS_WELSCH, "none": oracle.LOSS_NONE}[c["kind"]]
+        cm = np.array(c["cells_m"], np.float32); cf = np.array(c["cells_f"], np.float32)
+        idx = np.arange(len(cm), dtype=np.uint32)
+        out = oracle.fused(c["variant"], cm, cf, idx, idx, np.array(c["params"]), (kind, c["a"], c["alpha"], c["mu"], c["weight"]))
+        n = len(c["params"])
+        H = np.array(c["H"]); g = np.array(c["g"])
+        assert np.max(np.abs(out["H"][:n, :n] - H)) <= 1e-9 * np.abs(H).max(), (c["variant"], c["kind"])
+        assert np.max(np.abs(out["g"][:n] - g)) <= 1e-9 * np.abs(g).max()
+        assert abs(out["cost"] - c["cost"]) <= 1e-10 * abs(c["cost"])
+        assert abs(out["max_r"] - c["max_r"]) <= 1e-10 * c["max_r"] and abs(out["sum_sq"] - c["sum_sq"]) <= 1e-10 * c["sum_sq"]
+        assert out["n"] == len(cm)
+
+
 def test_golden_labels(oracle, golden):
     for c in golden["labels"]:
         assert oracle.n_clusters(c["max_range"], c["resolution"]) == c["n_clusters"]
