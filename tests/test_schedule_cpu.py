@@ -10,6 +10,15 @@ import pytest
 
 from randt_slam_b200 import hostapi
 
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _libraries_built():
+    """the schedule builder is reached through librandt_host.so: make sure it exists (nvcc / g++ cross-compile without a GPU)"""
+    from randt_slam_b200 import build
+    build.build_all()
+
+
 COUNT, FIRST, LAST, SOLO, SPLIT, NEWLAST, SPLIT_SHIFT = 0x3F, 0x100, 0x200, 0x400, 0x800, 0x1000, 16
 MAX_WARPS = 148 * 4 * 4
 
