@@ -106,11 +106,13 @@ def build_problem(ctx, capi, p, n_problems, seed0):
 
 def measured_traffic(pairs):
     """dram__bytes_read.sum + dram__bytes_write.sum of one K3 fused launch from the committed `ncu --set full` capture of this very
-    workload (profiles/r01_k3_fused_*_ncu_summary.txt, newest); None when the capture was taken on a different batch size."""
+    workload (profiles/r*_k3_fused_*_ncu_summary.txt: the `final` capture of the latest round, else the last by name); None when no
+    capture was taken on this batch size."""
     import glob
     import re
     best = None
-    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r01_k3_fused_*_ncu_summary.txt"))):
+    paths = glob.glob(os.path.join(ROOT, "profiles", "r*_k3_fused_*_ncu_summary.txt"))
+    for path in sorted(paths, key=lambda q: (os.path.basename(q).split("_")[0], "_final_" in os.path.basename(q), os.path.basename(q))):
         txt = open(path).read()
         m_pairs = re.search(r"([\d ]+) pairs per launch", txt)
         rd = re.search(r"dram__bytes_read\.sum\s+Mbyte\s+([\d.]+)", txt); wr = re.search(r"dram__bytes_write\.sum\s+Mbyte\s+([\d.]+)", txt)

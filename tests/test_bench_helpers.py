@@ -1,0 +1,45 @@
+"""bench.py's bookkeeping that needs no GPU: the algorithmic-byte formula of SURVEY §8d, the DRAM traffic figure taken from the committed
+ncu capture, the workload naming, and the committed bench line itself (contract keys, roofline arithmetic)."""
+import json
+import os
+
+import bench
+from randt_slam_b200 import params as P
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_algorithmic_bytes_formula():
+    st = dict(n_m=1000, n_f_referenced=3000, pairs=2000, segments=10)
+    assert bench.algorithmic_bytes(st) == 48 * (1000 + 3000) + 8 * 2000 + 32 * 10 + 192 * 10
+
+
+def test_traffic_comes_from_the_final_capture():
+    t = bench.measured_traffic(2941151)
+    txt = open(os.path.join(ROOT, "profiles", "r01_k3_fused_final_ncu_summary.txt")).read()
+    import re
+    rd = float(re.search(r"dram__bytes_read\.sum\s+Mbyte\s+([\d.]+)", txt).group(1)); wr = float(re.search(r"dram__bytes_write\.sum\s+Mbyte\s+([\d.]+)", txt).group(1))
+    assert abs(t - (rd + wr) * 1e6) < 1.0
+    assert bench.measured_traffic(12345) is None
+
+
+def test_workload_names():
+    assert "Oxford-shape" in bench.workload_name(P.OXFORD) and "oxford params" in bench.workload_name(P.OXFORD)
+    assert "indoor params" in bench.workload_name(P.INDOOR)
+
+
+def test_committed_bench_line_keeps_the_contract():
+    d = json.load(open(os.path.join(ROOT, "profiles", "r01_bench_final.json")))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config",
+              "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
+        assert k in d, k
+    assert d["metric"] == bench.METRIC and d["unit"] == bench.UNIT and d["vs_baseline"] is None and d["warmup"] >= 3
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and r["frac"] >= 0.60
+    assert abs(r["achieved"] - r["algorithmic_bytes_per_launch"] / (r["kernel_ms"] * 1e-3) / 1e9) < 1e-6 * r["achieved"]
+    assert abs(d["value"] - d["config"]["pairs_per_gpu"] * d["steps"] / (d["ms_per_step"] * d["steps"] * 1e-3)) < 1e-6 * d["value"]
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] < d["value"] and e["results_equal_blocking_call"]
+    c = d["cpu_baseline"]
+    assert c["kind"] == "port" and c["cores"] >= 1 and d["value"] / c["single_thread_value"] >= 100      # north_star: >= 100x one CPU thread
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
