@@ -168,3 +168,16 @@ def test_split_chunks_actually_pack_small_problems():
     sc = hostapi.build_schedule(offsets(rng.integers(60, 130, 16384)), MAX_WARPS)
     assert len(sc["plan_a"]) < 0.9 * len(sc["plan_b"])
     assert ((sc["plan_a"][:, 1] & SPLIT) != 0).sum() > 1000
+
+
+def test_schedule_randomised_shapes():
+    """hypothesis: arbitrary mixes of empty / tiny / chunk-aligned / multi-tile segments and any warp count keep every invariant"""
+    hyp = pytest.importorskip("hypothesis")
+    st = pytest.importorskip("hypothesis.strategies")
+    sizes = st.lists(st.one_of(st.integers(0, 3), st.integers(28, 36), st.integers(60, 70), st.integers(250, 262), st.integers(0, 1500)), min_size=0, max_size=60)
+
+    @hyp.settings(max_examples=60, deadline=None)
+    @hyp.given(sizes, st.integers(1, 64))
+    def check(sz, max_warps):
+        test_schedule_invariants("random", np.array(sz, np.int64), max_warps)
+    check()
