@@ -165,8 +165,14 @@ RANDT_API int randt_map_info(const randt_map* map, uint32_t* n_maps, uint32_t* n
 RANDT_API int randt_map_download(randt_ctx* ctx, const randt_map* map, float* cells, uint32_t* npts, int32_t* labels,
                                  uint32_t* cell_off, int32_t* slot);
 /* Map::transformMap / Cell::transformCell (R/src/ndt_representation/ndt_map.cpp:177-182, ndt_cell.cpp:117-123).
- * trans: float32 [n_maps][4] = (cos, sin, tx, ty) on the host.  The slot table is NOT updated (neither is the reference's). */
+ * trans: float32 [n_maps][4] = (cos, sin, tx, ty) of the Eigen::Affine2f the caller holds, on the host.  Means move by the affine as given;
+ * covariances by Eigen's Transform::rotation() of it (the SVD polar factor, as transformCell computes it: equal to the linear part only up
+ * to float rounding).  The slot table is NOT updated (neither is the reference's). */
 RANDT_API int randt_map_transform(randt_ctx* ctx, randt_map* map, const float* trans);
+/* The same for poses held as Sophus::SE2d: poses float64 [n_maps][4] = [cos, sin, tx, ty]; the affine is
+ * Eigen::Affine2f(pose.cast<float>().matrix()) as the reference builds it (R/src/local_fuser/local_fuser.cpp:175,280,338): Sophus' cast
+ * re-normalises the float unit complex. */
+RANDT_API int randt_map_transform_se2d(randt_ctx* ctx, randt_map* map, const double* poses);
 /* Map::mergeMapCell + Cell::operator+= (R/src/ndt_representation/ndt_map.cpp:191-207, ndt_cell.h:133-142): merge moving map b
  * into fixed map b for every b.  `fixed` is rebuilt in place (cell order: existing cells, then appended cells in moving order). */
 RANDT_API int randt_map_merge(randt_ctx* ctx, randt_map* fixed, const randt_map* moving);

@@ -249,27 +249,147 @@ inline void voxelize(const Pt4* pts, size_t n, size_t n_clusters, float max_rang
 }
 
 // ------------------------------------------------------------------------------------------
-// a5  Cell::transformCell / Map::transformMap   R/src/ndt_representation/ndt_cell.cpp:117-123, ndt_map.cpp:177-182
-// float32.  trans = [[c,-s,tx],[s,c,ty]].  The reference obtains the 3x3 rotation through
-// Eigen's Transform::rotation() (an SVD polar factor of the linear part); for a proper rotation
-// that is R itself up to a few float ulps, and the oracle uses R directly (documented deviation).
+// Sophus 1.22.10 SE2d::cast<float>() (sophus/se2.hpp:cast, so2.hpp: SO2(complex) constructor -> normalize()):
+// the unit complex is cast to float and re-normalised (length = hypot(re, im); complex /= length), the translation is cast.
+// This is what every `Eigen::Affine2f(x.cast<float>().matrix())` in the reference holds
+// (R/src/ndt_registration/ndt_matcher.cpp:208, R/src/local_fuser/local_fuser.cpp:175,280,338).  out = (re, im, tx, ty).
 // ------------------------------------------------------------------------------------------
+inline void se2d_cast_float(const double pose[4], float out[4]) {
+  float re = static_cast<float>(pose[0]), im = static_cast<float>(pose[1]);
+  const float length = std::hypot(re, im);   // glibc hypotf: (float)sqrt((double)re*re + (double)im*im)
+  re /= length; im /= length;
+  out[0] = re; out[1] = im; out[2] = static_cast<float>(pose[2]); out[3] = static_cast<float>(pose[3]);
+}
+
+// ------------------------------------------------------------------------------------------
+// Eigen 3.3.7 Transform<float,3,Affine>::rotation() of the lift Cell::transformCell builds (ndt_cell.cpp:118-122):
+// linear part L = [[c,-s,0],[s,c,0],[0,0,1]].  rotation() = computeRotationScaling(&R, 0) (Geometry/Transform.h): JacobiSVD<Matrix3f>
+// (two-sided Jacobi, SVD/JacobiSVD.h compute() + real_2x2_jacobi_svd + Jacobi.h makeJacobi / apply_rotation_in_the_plane),
+// x = det(U V^T), U.col(0) /= x, R = U V^T.  R equals L only up to float rounding (and differs from it for about half of all angles).
+// ------------------------------------------------------------------------------------------
+namespace eig3f {
+struct Rot { float c, s; };
+inline bool make_jacobi(float x, float y, float z, Rot& r) {
+  const float deno = 2.0f * std::fabs(y);
+  if (deno < std::numeric_limits<float>::min()) { r.c = 1.0f; r.s = 0.0f; return false; }
+  const float tau = (x - z) / deno;
+  const float w = std::sqrt(tau * tau + 1.0f);
+  float t;
+  if (tau > 0.0f) t = 1.0f / (tau + w); else t = 1.0f / (tau - w);
+  const float sign_t = t > 0.0f ? 1.0f : -1.0f;
+  const float n = 1.0f / std::sqrt(t * t + 1.0f);
+  r.s = -sign_t * (y / std::fabs(y)) * std::fabs(t) * n;
+  r.c = n;
+  return true;
+}
+// apply_rotation_in_the_plane on rows p, q (applyOnTheLeft) / columns p, q with the transposed rotation (applyOnTheRight)
+inline void rot_rows(float m[3][3], int p, int q, Rot j, int ncols = 3) {
+  if (j.c == 1.0f && j.s == 0.0f) return;
+  for (int k = 0; k < ncols; ++k) { const float xi = m[p][k], yi = m[q][k]; m[p][k] = j.c * xi + j.s * yi; m[q][k] = -j.s * xi + j.c * yi; }
+}
+inline void rot_cols(float m[3][3], int p, int q, Rot j) {
+  const float c = j.c, s = -j.s;     // j.transpose()
+  if (c == 1.0f && s == 0.0f) return;
+  for (int k = 0; k < 3; ++k) { const float xi = m[k][p], yi = m[k][q]; m[k][p] = c * xi + s * yi; m[k][q] = -s * xi + c * yi; }
+}
+inline float det3(const float m[3][3]) {
+  auto h = [&](int a, int b, int c) { return m[0][a] * (m[1][b] * m[2][c] - m[1][c] * m[2][b]); };
+  return h(0, 1, 2) - h(1, 0, 2) + h(2, 0, 1);
+}
+inline void jacobi_svd3(const float a[3][3], float U[3][3], float V[3][3], float sv[3]) {
+  const float precision = 2.0f * std::numeric_limits<float>::epsilon();
+  const float consider_as_zero = std::numeric_limits<float>::min();
+  float scale = 0.0f;
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) scale = std::max(scale, std::fabs(a[i][j]));
+  if (scale == 0.0f) scale = 1.0f;
+  float w[3][3];
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { w[i][j] = a[i][j] / scale; U[i][j] = V[i][j] = (i == j) ? 1.0f : 0.0f; }
+  float max_diag = 0.0f;
+  for (int i = 0; i < 3; ++i) max_diag = std::max(max_diag, std::fabs(w[i][i]));
+  bool finished = false;
+  while (!finished) {
+    finished = true;
+    for (int p = 1; p < 3; ++p)
+      for (int q = 0; q < p; ++q) {
+        const float threshold = std::max(consider_as_zero, precision * max_diag);
+        if (std::fabs(w[p][q]) > threshold || std::fabs(w[q][p]) > threshold) {
+          finished = false;
+          // real_2x2_jacobi_svd
+          float m[3][3] = {{w[p][p], w[p][q], 0.f}, {w[q][p], w[q][q], 0.f}, {0.f, 0.f, 0.f}};
+          Rot rot1;
+          const float t = m[0][0] + m[1][1];
+          const float d = m[1][0] - m[0][1];
+          if (std::fabs(d) < std::numeric_limits<float>::min()) { rot1.s = 0.0f; rot1.c = 1.0f; }
+          else { const float u = t / d; const float tmp = std::sqrt(1.0f + u * u); rot1.s = 1.0f / tmp; rot1.c = u / tmp; }
+          rot_rows(m, 0, 1, rot1, 2);
+          Rot j_right;
+          make_jacobi(m[0][0], m[0][1], m[1][1], j_right);
+          const Rot jrt = {j_right.c, -j_right.s};
+          const Rot j_left = {rot1.c * jrt.c - rot1.s * jrt.s, rot1.c * jrt.s + rot1.s * jrt.c};   // rot1 * j_right.transpose()
+          rot_rows(w, p, q, j_left);
+          const Rot jlt = {j_left.c, -j_left.s};
+          rot_cols(U, p, q, jlt);
+          rot_cols(w, p, q, j_right);
+          rot_cols(V, p, q, j_right);
+          max_diag = std::max(max_diag, std::max(std::fabs(w[p][p]), std::fabs(w[q][q])));
+        }
+      }
+  }
+  for (int i = 0; i < 3; ++i) {
+    sv[i] = std::fabs(w[i][i]);
+    if (w[i][i] < 0.0f) for (int k = 0; k < 3; ++k) U[k][i] = -U[k][i];
+  }
+  for (int i = 0; i < 3; ++i) sv[i] = sv[i] * scale;
+  for (int i = 0; i < 3; ++i) {      // descending sort, first maximum wins
+    int pos = 0; float best = sv[i];
+    for (int k = 1; k < 3 - i; ++k) if (sv[i + k] > best) { best = sv[i + k]; pos = k; }
+    if (best == 0.0f) break;
+    if (pos) {
+      pos += i;
+      std::swap(sv[i], sv[pos]);
+      for (int k = 0; k < 3; ++k) { std::swap(U[k][pos], U[k][i]); std::swap(V[k][pos], V[k][i]); }
+    }
+  }
+}
+// 3x3 float product, coefficient = x0 + (x1 + x2)  (Eigen's unrolled reduction of three terms)
+inline void mul3(const float A[3][3], const float B[3][3], float C[3][3]) {
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) C[i][j] = A[i][0] * B[0][j] + (A[i][1] * B[1][j] + A[i][2] * B[2][j]);
+}
+inline void transpose3(const float A[3][3], float T[3][3]) { for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) T[i][j] = A[j][i]; }
+}  // namespace eig3f
+
+inline void affine_rotation_f(float c, float s, float R[3][3]) {
+  const float L[3][3] = {{c, -s, 0.f}, {s, c, 0.f}, {0.f, 0.f, 1.f}};
+  float U[3][3], V[3][3], Vt[3][3], UVt[3][3], sv[3];
+  eig3f::jacobi_svd3(L, U, V, sv);
+  eig3f::transpose3(V, Vt);
+  eig3f::mul3(U, Vt, UVt);
+  const float x = eig3f::det3(UVt);
+  for (int k = 0; k < 3; ++k) U[k][0] = U[k][0] / x;
+  eig3f::mul3(U, Vt, R);
+}
+
+// ------------------------------------------------------------------------------------------
+// a5  Cell::transformCell / Map::transformMap   R/src/ndt_representation/ndt_cell.cpp:117-123, ndt_map.cpp:177-182
+// float32.  trans = [[c,-s,tx],[s,c,ty]] (the Affine2f the caller built).  mean <- trans_3d * mean (translation + linear * mean, the
+// linear part as given); cov <- R cov R^T with R = trans_3d.rotation(), Eigen's SVD polar factor of the linear part (above).
+// ------------------------------------------------------------------------------------------
+inline void transform_cell(Cell12& cell, float c, float s, float tx, float ty, const float R[3][3]) {
+  const float x = cell.mu[0], y = cell.mu[1], in = cell.mu[2];
+  cell.mu[0] = tx + (c * x + ((-s) * y + 0.f * in));
+  cell.mu[1] = ty + (s * x + (c * y + 0.f * in));
+  cell.mu[2] = 0.f + (0.f * x + (0.f * y + 1.f * in));
+  float S[3][3], T[3][3], Rt[3][3], O[3][3];
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) S[i][j] = cell.cov[i * 3 + j];
+  eig3f::mul3(R, S, T);
+  eig3f::transpose3(R, Rt);
+  eig3f::mul3(T, Rt, O);
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) cell.cov[i * 3 + j] = O[i][j];
+}
 inline void transform_cell(Cell12& cell, float c, float s, float tx, float ty) {
-  const float R[3][3] = {{c, -s, 0.f}, {s, c, 0.f}, {0.f, 0.f, 1.f}};
-  const float x = cell.mu[0], y = cell.mu[1];
-  cell.mu[0] = tx + (R[0][0] * x + R[0][1] * y);
-  cell.mu[1] = ty + (R[1][0] * x + R[1][1] * y);
-  float T[3][3];
-  for (int i = 0; i < 3; ++i)
-    for (int j = 0; j < 3; ++j) {
-      if (i < 2) T[i][j] = R[i][0] * cell.cov[0 * 3 + j] + R[i][1] * cell.cov[1 * 3 + j];
-      else       T[i][j] = cell.cov[2 * 3 + j];
-    }
-  for (int i = 0; i < 3; ++i)
-    for (int j = 0; j < 3; ++j) {
-      if (j < 2) cell.cov[i * 3 + j] = T[i][0] * R[j][0] + T[i][1] * R[j][1];
-      else       cell.cov[i * 3 + j] = T[i][2];
-    }
+  float R[3][3];
+  affine_rotation_f(c, s, R);
+  transform_cell(cell, c, s, tx, ty, R);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -391,12 +511,16 @@ struct PairList {
   std::vector<uint32_t> im, jf;
 };
 inline void associate(const NdtMap& fixed, const NdtMap& moving, const double pose[4], int k, int metric, PairList& out) {
-  const float c = (float)pose[0], s = (float)pose[1], tx = (float)pose[2], ty = (float)pose[3];
+  float a[4];
+  se2d_cast_float(pose, a);        // initial_guess.cast<float>() (ndt_matcher.cpp:208,213)
+  const float c = a[0], s = a[1], tx = a[2], ty = a[3];
+  float R[3][3];
+  affine_rotation_f(c, s, R);
   std::vector<uint32_t> nn;
   for (size_t i = 0; i < moving.cells.size(); ++i) {
     Cell12 q = moving.cells[i];
     if (metric == LOOKUP_MAHALANOBIS_INTENSITY) {
-      transform_cell(q, c, s, tx, ty);
+      transform_cell(q, c, s, tx, ty, R);
     } else {
       // initial_guess.cast<float>() * mean_xy  (Sophus SE2f * point = R p + t)
       const float x = q.mu[0], y = q.mu[1];
@@ -730,8 +854,8 @@ inline double cs_divergence(const Cell12* fixed, size_t nf, const Cell12* moving
 // RadarPreprocessor::filterScan   R/src/radar_preprocessing/radar_preprocessor.cpp:45-125   
 // Restated sequentially as written.  The two `while(true)` walks leave closer_idx / further_idx uninitialised when their
 // size_t wrap-around guard fires first (UB in the reference); the oracle defines them as the position reached.
-// tf: row-major 3x4 of initial_transform_radar_baselink (Affine3f); pcl::transformPointCloud's SSE path evaluates each row as
-// (x c0 + y c1) + (z c2 + c3).
+// tf: row-major 3x4 of initial_transform_radar_baselink (Affine3f); pcl::transformPointCloud's SSE2 path (PCL 1.10
+// detail::Transformer<float>::se3: _mm_add_ps(p0, _mm_add_ps(p1, _mm_add_ps(p2, c[3])))) evaluates each row as x c0 + (y c1 + (z c2 + c3)).
 // ------------------------------------------------------------------------------------------
 struct FilterParams { float min_distance, max_distance, min_intensity; double beam_thr; float tf[12]; };
 inline void filter_scan(const Pt4* raw, size_t n, const FilterParams& fp, std::vector<Pt4>& out, std::vector<size_t>* peaks = nullptr) {
@@ -773,9 +897,9 @@ inline void filter_scan(const Pt4* raw, size_t n, const FilterParams& fp, std::v
       const float dist = std::hypot(raw[j].x, raw[j].y);
       if (dist > fp.min_distance && dist < fp.max_distance && raw[j].i > fp.min_intensity) {
         Pt4 o;
-        o.x = (raw[j].x * fp.tf[0] + raw[j].y * fp.tf[1]) + (raw[j].z * fp.tf[2] + fp.tf[3]);
-        o.y = (raw[j].x * fp.tf[4] + raw[j].y * fp.tf[5]) + (raw[j].z * fp.tf[6] + fp.tf[7]);
-        o.z = (raw[j].x * fp.tf[8] + raw[j].y * fp.tf[9]) + (raw[j].z * fp.tf[10] + fp.tf[11]);
+        o.x = raw[j].x * fp.tf[0] + (raw[j].y * fp.tf[1] + (raw[j].z * fp.tf[2] + fp.tf[3]));
+        o.y = raw[j].x * fp.tf[4] + (raw[j].y * fp.tf[5] + (raw[j].z * fp.tf[6] + fp.tf[7]));
+        o.z = raw[j].x * fp.tf[8] + (raw[j].y * fp.tf[9] + (raw[j].z * fp.tf[10] + fp.tf[11]));
         o.i = raw[j].i;
         out.push_back(o);
       }

@@ -71,9 +71,13 @@ int orc_voxelize(const float* pts4, size_t n, size_t n_clusters, float max_range
   return nc;
 }
 
+void orc_se2d_cast_float(const double* pose, float* out4) { se2d_cast_float(pose, out4); }
+void orc_affine_rotation(float c, float s, float* R9) { float R[3][3]; affine_rotation_f(c, s, R); for (int i = 0; i < 9; ++i) R9[i] = R[i / 3][i % 3]; }
 void orc_transform_cells(float* cells, size_t n, float c, float s, float tx, float ty) {
   Cell12* cc = reinterpret_cast<Cell12*>(cells);
-  for (size_t i = 0; i < n; ++i) transform_cell(cc[i], c, s, tx, ty);
+  float R[3][3];
+  affine_rotation_f(c, s, R);
+  for (size_t i = 0; i < n; ++i) transform_cell(cc[i], c, s, tx, ty, R);
 }
 
 // in-place merge of a moving map into a fixed map (arrays have capacity cap_f); returns new fixed cell count or -needed

@@ -73,6 +73,8 @@ def _sig(L):
     L.orc_cell_from_points.restype = i; L.orc_cell_from_points.argtypes = [pf, sz, i, pf]
     L.orc_voxelize.restype = i
     L.orc_voxelize.argtypes = [pf, sz, sz, f, i, i, i, d, d, pf, pu, pi, pi, i, C.POINTER(i)]
+    L.orc_se2d_cast_float.restype = None; L.orc_se2d_cast_float.argtypes = [pd, pf]
+    L.orc_affine_rotation.restype = None; L.orc_affine_rotation.argtypes = [f, f, pf]
     L.orc_transform_cells.restype = None; L.orc_transform_cells.argtypes = [pf, sz, f, f, f, f]
     L.orc_merge_map_cell.restype = i; L.orc_merge_map_cell.argtypes = [pf, pu, i, i, pi, i, i, d, pf, pu, i]
     L.orc_associate.restype = i; L.orc_associate.argtypes = [pf, i, pi, i, i, d, d, pf, i, pd, i, i, pu, pu, i]
@@ -149,6 +151,20 @@ def voxelize(pts, n_clusters_, max_range, min_points, size_x, size_y, res, max_l
                            _p(slot, C.c_int32), cap, C.byref(dropped))
     assert n >= 0
     return dict(cells=cells[:n].copy(), npts=npts[:n].copy(), labels=labels[:n].copy(), slot=slot, dropped=dropped.value)
+
+
+def se2d_cast_float(pose):
+    """Sophus SE2d::cast<float>() restated -> float32 (re, im, tx, ty): what Eigen::Affine2f(pose.cast<float>().matrix()) holds"""
+    pose = _f64(pose); out = np.zeros(4, np.float32)
+    lib().orc_se2d_cast_float(_p(pose, C.c_double), _p(out, C.c_float))
+    return out
+
+
+def affine_rotation(c, s):
+    """Eigen Transform<float,3,Affine>::rotation() of the lift of [[c,-s],[s,c]] restated -> [3, 3] float32"""
+    out = np.zeros(9, np.float32)
+    lib().orc_affine_rotation(float(c), float(s), _p(out, C.c_float))
+    return out.reshape(3, 3)
 
 
 def transform_cells(cells, c, s, tx, ty):

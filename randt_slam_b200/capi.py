@@ -108,6 +108,7 @@ _SIGS = {
     "randt_map_info": (_i, [_vp, C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_u32)]),
     "randt_map_download": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "randt_map_transform": (_i, [_vp, _vp, _vp]),
+    "randt_map_transform_se2d": (_i, [_vp, _vp, _vp]),
     "randt_map_merge": (_i, [_vp, _vp, _vp]),
     "randt_map_destroy": (None, [_vp]),
     "randt_cs_divergence": (_i, [_vp, _vp, _vp, _vp]),
@@ -322,6 +323,12 @@ class Map:
         trans = _f32(trans, (-1, 4))
         assert len(trans) == self.info()[0]
         self.ctx._check(lib().randt_map_transform(self.ctx._h, self._h, _ptr(trans)))
+
+    def transform_se2d(self, poses):
+        """Map::transformMap(Eigen::Affine2f(pose.cast<float>().matrix())) for float64 [B, 4] Sophus SE2d poses"""
+        poses = _f64(poses).reshape(-1, 4)
+        assert len(poses) == self.info()[0]
+        self.ctx._check(lib().randt_map_transform_se2d(self.ctx._h, self._h, _ptr(poses)))
 
     def merge(self, moving):
         self.ctx._check(lib().randt_map_merge(self.ctx._h, self._h, moving._h))

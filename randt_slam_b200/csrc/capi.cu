@@ -553,20 +553,34 @@ int randt_map_download(randt_ctx* ctx, const randt_map* m, float* cells, uint32_
   return RANDT_OK;
 }
 
-int randt_map_transform(randt_ctx* ctx, randt_map* m, const float* trans) {
-  if (!ctx || !m || !trans) return fail(ctx, RANDT_E_INVALID, "randt_map_transform: null argument");
+namespace {
+// in: host float32 [B][4] (cos, sin, tx, ty) when from_se2d == 0, host float64 [B][4] Sophus SE2d storage otherwise
+int map_transform_impl(randt_ctx* ctx, randt_map* m, const void* in, int from_se2d) {
   CK(cudaSetDevice(ctx->device));
   StreamScope scope__(ctx->stream);
-  float4* d_t = nullptr;
-  CK(dev_alloc(&d_t, m->B));
+  const size_t in_bytes = (size_t)m->B * 4 * (from_se2d ? sizeof(double) : sizeof(float));
+  unsigned char* d_in = nullptr; float4* d_aff = nullptr;
+  CK(dev_alloc(&d_in, in_bytes));
+  cudaError_t e = dev_alloc(&d_aff, (size_t)m->B * 4);
   int nl = 0;
-  cudaError_t e = cudaMemcpyAsync(d_t, trans, (size_t)m->B * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess) e = launch_transform_cells(m->cells, m->cell_off, m->B, m->max_per_map, d_t, ctx->stream, &nl);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, in, in_bytes, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = launch_prepare_affine(d_in, from_se2d, m->B, d_aff, ctx->stream, &nl);
+  if (e == cudaSuccess) e = launch_transform_cells(m->cells, m->cell_off, m->B, m->max_per_map, d_aff, ctx->stream, &nl);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  dev_free(d_t);
+  dev_free(d_in); dev_free(d_aff);
   if (e != cudaSuccess) return fail(ctx, RANDT_E_CUDA, "randt_map_transform", e);
   ctx->launches += nl;
   return RANDT_OK;
+}
+}  // namespace
+
+int randt_map_transform(randt_ctx* ctx, randt_map* m, const float* trans) {
+  if (!ctx || !m || !trans) return fail(ctx, RANDT_E_INVALID, "randt_map_transform: null argument");
+  return map_transform_impl(ctx, m, trans, 0);
+}
+int randt_map_transform_se2d(randt_ctx* ctx, randt_map* m, const double* poses) {
+  if (!ctx || !m || !poses) return fail(ctx, RANDT_E_INVALID, "randt_map_transform_se2d: null argument");
+  return map_transform_impl(ctx, m, poses, 1);
 }
 
 int randt_map_merge(randt_ctx* ctx, randt_map* F, const randt_map* M) {
@@ -653,14 +667,14 @@ int randt_associate(randt_ctx* ctx, const randt_map* F, const randt_map* M, cons
   randt_problem* p = new (std::nothrow) randt_problem();
   if (!p) return RANDT_E_NOMEM;
   p->device = ctx->device; p->sref = ctx->sref; p->S = B; p->n_m = n_m; p->n_f = F->n_cells;
-  float4* d_pose = nullptr; uint32_t *d_nn = nullptr, *d_cnt = nullptr, *d_scan = nullptr, *d_bs = nullptr, *d_cnt2 = nullptr, *d_scan2 = nullptr, *d_offs = nullptr;
+  float4* d_pose = nullptr; double* d_pose0 = nullptr; uint32_t *d_nn = nullptr, *d_cnt = nullptr, *d_scan = nullptr, *d_bs = nullptr, *d_cnt2 = nullptr, *d_scan2 = nullptr, *d_offs = nullptr;
   int rc = RANDT_OK; int nl = 0;
-  auto cleanup = [&]() { dev_free(d_pose); dev_free(d_nn); dev_free(d_cnt); dev_free(d_scan); dev_free(d_bs); dev_free(d_cnt2); dev_free(d_scan2); dev_free(d_offs); };
+  auto cleanup = [&]() { dev_free(d_pose); dev_free(d_pose0); dev_free(d_nn); dev_free(d_cnt); dev_free(d_scan); dev_free(d_bs); dev_free(d_cnt2); dev_free(d_scan2); dev_free(d_offs); };
 #define CKA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rc = fail(ctx, RANDT_E_CUDA, #call, e__); cleanup(); free_problem(p); return rc; } } while (0)
-  std::vector<float4> h_pose(B);
-  for (uint32_t b = 0; b < B; ++b) h_pose[b] = make_float4((float)pose0[4 * b], (float)pose0[4 * b + 1], (float)pose0[4 * b + 2], (float)pose0[4 * b + 3]);
-  CKA(dev_alloc(&d_pose, B));
-  if (B) CKA(cudaMemcpyAsync(d_pose, h_pose.data(), (size_t)B * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+  // initial_guess.cast<float>() and the rotation its transformCell applies, once per map on the device (AffineRec)
+  CKA(dev_alloc(&d_pose, (size_t)B * 4)); CKA(dev_alloc(&d_pose0, (size_t)B * 4));
+  if (B) CKA(cudaMemcpyAsync(d_pose0, pose0, (size_t)B * 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CKA(launch_prepare_affine(d_pose0, 1, B, d_pose, ctx->stream, &nl));
   CKA(dev_alloc(&d_nn, (size_t)n_m * k)); CKA(dev_alloc(&d_cnt, n_m)); CKA(dev_alloc(&d_scan, (size_t)n_m + 1)); CKA(dev_alloc(&d_bs, n_m / 1024 + 2));
   CKA(launch_associate(F->cells, F->cell_off, F->slot, M->cells, M->cell_off, B, n_m, M->max_per_map, geom, d_pose, k, metric, d_nn, d_cnt, ctx->stream, &nl));
   CKA(launch_exclusive_scan_u32(d_cnt, d_scan, n_m, d_bs, ctx->stream, &nl));

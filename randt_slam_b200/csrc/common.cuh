@@ -122,7 +122,10 @@ cudaError_t launch_compact_cells(const float4* d_cells_p, const uint32_t* d_npts
                                  uint32_t* d_npts, int32_t* d_labels, cudaStream_t s, int* n_launches);
 cudaError_t launch_build_slots(const float4* d_cells, const uint32_t* d_cell_off, uint32_t n_maps, uint32_t max_per_map,
                                const MapGeomDev& geom, int32_t* d_slot, cudaStream_t s, int* n_launches);
-cudaError_t launch_transform_cells(float4* d_cells, const uint32_t* d_cell_off, uint32_t n_maps, uint32_t max_per_map, const float4* d_trans,
+// AffineRec: 4 x float4 per map = (c, s, tx, ty) | (R00 R01 R02 R10) | (R11 R12 R20 R21) | (R22 0 0 0): the reference's Eigen::Affine2f and the
+// Eigen Transform::rotation() of its 3-D lift (what Cell::transformCell rotates covariances with)
+cudaError_t launch_prepare_affine(const void* d_in, int from_se2d, uint32_t n_maps, float4* d_aff, cudaStream_t s, int* n_launches);
+cudaError_t launch_transform_cells(float4* d_cells, const uint32_t* d_cell_off, uint32_t n_maps, uint32_t max_per_map, const float4* d_aff,
                                    cudaStream_t s, int* n_launches);
 cudaError_t launch_merge_maps(const float4* f_cells, const uint32_t* f_npts, const uint32_t* f_off, int32_t* f_slot, const float4* m_cells,
                               const uint32_t* m_npts, const uint32_t* m_off, uint32_t n_maps, const MapGeomDev& geom, const uint32_t* o_off,
@@ -169,5 +172,33 @@ __host__ __device__ inline uint32_t coord_to_index(const MapGeomDev& g, float x,
   const uint32_t my = to_u32_trunc(((double)y - g.off_y) / g.res);
   return my * (uint32_t)g.size_x + mx;
 }
+
+#ifdef __CUDACC__
+// Cell::transformCell (R/src/ndt_representation/ndt_cell.cpp:117-123) on the 3 x float4 cell layout.  Only meaningful in translation units
+// compiled with -fmad=false (k1, k2): every product / sum is a separate IEEE operation in Eigen's order, x0 + (x1 + x2) per coefficient.
+struct CellRaw { float4 a, b, c; };
+__device__ __forceinline__ void transform_cell_affine(CellRaw& q, const float4* __restrict__ aff) {
+  const float4 A = __ldg(aff), R0 = __ldg(aff + 1), R1 = __ldg(aff + 2), R2 = __ldg(aff + 3);
+  const float c = A.x, s = A.y;
+  const float R[3][3] = {{R0.x, R0.y, R0.z}, {R0.w, R1.x, R1.y}, {R1.z, R1.w, R2.x}};
+  const float S[3][3] = {{q.a.w, q.b.x, q.b.y}, {q.b.z, q.b.w, q.c.x}, {q.c.y, q.c.z, q.c.w}};
+  const float x = q.a.x, y = q.a.y, in = q.a.z;
+  const float mx = A.z + (c * x + ((-s) * y + 0.f * in));
+  const float my = A.w + (s * x + (c * y + 0.f * in));
+  const float mi = 0.f + (0.f * x + (0.f * y + 1.f * in));
+  float T[3][3], O[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) T[i][j] = R[i][0] * S[0][j] + (R[i][1] * S[1][j] + R[i][2] * S[2][j]);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) O[i][j] = T[i][0] * R[j][0] + (T[i][1] * R[j][1] + T[i][2] * R[j][2]);
+  q.a = make_float4(mx, my, mi, O[0][0]);
+  q.b = make_float4(O[0][1], O[0][2], O[1][0], O[1][1]);
+  q.c = make_float4(O[1][2], O[2][0], O[2][1], O[2][2]);
+}
+#endif
 
 }  // namespace randt

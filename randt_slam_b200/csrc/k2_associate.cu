@@ -23,27 +23,6 @@ __device__ __forceinline__ CellF load_cell_f(const float4* __restrict__ tab, uin
   return o;
 }
 
-// Cell::transformCell with trans = [[c,-s,tx],[s,c,ty]] (float)
-__device__ __forceinline__ void transform_cell_f(CellF& q, float c, float s, float tx, float ty) {
-  const float ns = -s;
-  const float x = q.mu[0], y = q.mu[1];
-  q.mu[0] = tx + (c * x + ns * y);
-  q.mu[1] = ty + (s * x + c * y);
-  float T[3][3];
-#pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    T[0][j] = c * q.cov[j] + ns * q.cov[3 + j];
-    T[1][j] = s * q.cov[j] + c * q.cov[3 + j];
-    T[2][j] = q.cov[6 + j];
-  }
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    q.cov[i * 3 + 0] = T[i][0] * c + T[i][1] * ns;
-    q.cov[i * 3 + 1] = T[i][0] * s + T[i][1] * c;
-    q.cov[i * 3 + 2] = T[i][2];
-  }
-}
-
 // (v^T inv(m)) v with Eigen's cofactor inverse evaluation order (float)
 __device__ __forceinline__ float inv3_quadform_f(const float m[9], const float v[3]) {
 #define M_(r, c) m[(r) * 3 + (c)]
@@ -77,11 +56,16 @@ __global__ void __launch_bounds__(128) k2_associate_kernel(const float4* __restr
   const uint32_t m0 = cell_off_m[b], m1 = cell_off_m[b + 1];
   const uint32_t i = m0 + blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m1) return;
-  const float4 T = __ldg(pose_f + b);   // (c, s, tx, ty)
-  CellF q = load_cell_f(cells_m, i);
+  const float4 T = __ldg(pose_f + 4 * (size_t)b);   // AffineRec: (c, s, tx, ty) of initial_guess.cast<float>(), then its Eigen rotation()
+  CellF q;
   if (metric == RANDT_LOOKUP_MAHALANOBIS_INTENSITY) {
-    transform_cell_f(q, T.x, T.y, T.z, T.w);
+    CellRaw raw;
+    raw.a = __ldg(cells_m + 3 * (size_t)i); raw.b = __ldg(cells_m + 3 * (size_t)i + 1); raw.c = __ldg(cells_m + 3 * (size_t)i + 2);
+    transform_cell_affine(raw, pose_f + 4 * (size_t)b);
+    q.mu[0] = raw.a.x; q.mu[1] = raw.a.y; q.mu[2] = raw.a.z;
+    q.cov[0] = raw.a.w; q.cov[1] = raw.b.x; q.cov[2] = raw.b.y; q.cov[3] = raw.b.z; q.cov[4] = raw.b.w; q.cov[5] = raw.c.x; q.cov[6] = raw.c.y; q.cov[7] = raw.c.z; q.cov[8] = raw.c.w;
   } else {
+    q = load_cell_f(cells_m, i);
     const float x = q.mu[0], y = q.mu[1];
     q.mu[0] = (T.x * x - T.y * y) + T.z;
     q.mu[1] = (T.y * x + T.x * y) + T.w;

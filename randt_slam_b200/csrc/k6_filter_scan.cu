@@ -164,11 +164,11 @@ __global__ void __launch_bounds__(1024) k6_runs_kernel(const float4* __restrict_
         const float dist = hypot_ref(v.x, v.y);
         if (dist > f.min_d && dist < f.max_d && v.w > f.min_i) {
           if (w < cap) {
-            // pcl::transformPointCloud (Affine3f, SSE path): (x c0 + y c1) + (z c2 + c3) per output row
             float4 o;
-            o.x = (v.x * f.tf[0] + v.y * f.tf[1]) + (v.z * f.tf[2] + f.tf[3]);
-            o.y = (v.x * f.tf[4] + v.y * f.tf[5]) + (v.z * f.tf[6] + f.tf[7]);
-            o.z = (v.x * f.tf[8] + v.y * f.tf[9]) + (v.z * f.tf[10] + f.tf[11]);
+            // pcl::detail::Transformer<float>::se3 (PCL 1.10, SSE2): p0 + (p1 + (p2 + c3)), pk = src[k] * column k
+            o.x = v.x * f.tf[0] + (v.y * f.tf[1] + (v.z * f.tf[2] + f.tf[3]));
+            o.y = v.x * f.tf[4] + (v.y * f.tf[5] + (v.z * f.tf[6] + f.tf[7]));
+            o.z = v.x * f.tf[8] + (v.y * f.tf[9] + (v.z * f.tf[10] + f.tf[11]));
             o.w = v.w;
             out[w] = o;
           }

@@ -73,10 +73,11 @@ void Map::addClusters(const float* pts4, const uint32_t* scan_off, uint32_t n_sc
   host_valid_ = false;
 }
 void Map::transformMap(const SE2d* trans) {
+  // Eigen::Affine2f(trans.cast<float>().matrix()) — the cast (with Sophus' re-normalisation) happens on the device
   const uint32_t B = n_maps();
-  std::vector<float> t(4 * (size_t)B);
-  for (uint32_t b = 0; b < B; ++b) for (int i = 0; i < 4; ++i) t[4 * b + i] = (float)trans[b].v[i];   // Sophus -> Affine2f cast
-  ctx_->check(randt_map_transform(ctx_->get(), map_, t.data()));
+  std::vector<double> t(4 * (size_t)B);
+  for (uint32_t b = 0; b < B; ++b) for (int i = 0; i < 4; ++i) t[4 * b + i] = trans[b].v[i];
+  ctx_->check(randt_map_transform_se2d(ctx_->get(), map_, t.data()));
   host_valid_ = false;
 }
 void Map::mergeMapCell(const Map& moving) {
