@@ -153,7 +153,8 @@ def test_loss_in_the_fused_normal_equations_equals_reference_loss(gpu_ctx):
     for ci, (a, alpha, mu) in enumerate(G["loss_cases"]):
         rho_fix, drho_fix = barron(a, alpha, mu, G["loss_s"])
         ref = G["loss_barron"][ci]
-        assert np.allclose(rho_fix, ref[:, 0], rtol=1e-13, atol=1e-300) and np.allclose(drho_fix, ref[:, 1], rtol=1e-13, atol=1e-300)
+        # (rho = pre (pow(..) - 1) cancels for tiny s: an ulp of pow is a large relative error of rho there, hence the absolute floor)
+        assert np.allclose(rho_fix, ref[:, 0], rtol=1e-12, atol=1e-13 * a * a * mu) and np.allclose(drho_fix, ref[:, 1], rtol=1e-12, atol=0)
         rho, drho = barron(a, alpha, mu, s)
         for weight in (1.0, 0.37):
             out = capi.unpack_fused(prob.eval_fused(pose, capi.make_loss(capi.LOSS_BARRON, a, alpha, mu, weight)))
