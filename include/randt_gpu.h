@@ -199,6 +199,9 @@ RANDT_API int randt_problem_create(randt_ctx* ctx, const float* cells_m, uint32_
                                    const uint32_t* pair_m, const uint32_t* pair_f, uint32_t n_pairs, const uint32_t* seg_off,
                                    uint32_t n_segments, randt_problem** out);
 RANDT_API int randt_problem_info(const randt_problem* p, uint32_t* n_segments, uint32_t* n_pairs, uint32_t* n_m, uint32_t* n_f);
+/* how K3 holds the problem in HBM: records of record_bytes each (one per duo = two pairs sharing their moving cell), of which
+ * n_overflow needed a full-precision side record; any pointer may be NULL */
+RANDT_API int randt_problem_layout(const randt_problem* p, uint32_t* n_duos, uint32_t* record_bytes, uint32_t* n_overflow);
 /* any pointer may be NULL */
 RANDT_API int randt_problem_download(randt_ctx* ctx, const randt_problem* p, uint32_t* pair_m, uint32_t* pair_f, uint32_t* seg_off);
 /* the snapshotted cell tables: cells_m [n_m][12], cells_f [n_f][12]; either may be NULL */

@@ -115,6 +115,7 @@ _SIGS = {
     "randt_associate": (_i, [_vp, _vp, _vp, _vp, _i, _i, C.POINTER(_vp)]),
     "randt_problem_create": (_i, [_vp, _vp, _u32, _vp, _u32, _vp, _vp, _u32, _vp, _u32, C.POINTER(_vp)]),
     "randt_problem_info": (_i, [_vp, C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_u32)]),
+    "randt_problem_layout": (_i, [_vp, C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_u32)]),
     "randt_problem_download": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "randt_problem_download_cells": (_i, [_vp, _vp, _vp, _vp]),
     "randt_problem_destroy": (None, [_vp]),
@@ -357,6 +358,12 @@ class Problem:
             self.close()
         except Exception:
             pass
+
+    def layout(self):
+        """-> (n_duos, record_bytes, n_overflow): the record table K3 streams"""
+        d, b, o = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        lib().randt_problem_layout(self._h, C.byref(d), C.byref(b), C.byref(o))
+        return d.value, b.value, o.value
 
     def download(self):
         pm = np.zeros(self.n_pairs, np.uint32); pf = np.zeros(self.n_pairs, np.uint32); off = np.zeros(self.n_segments + 1, np.uint32)

@@ -89,6 +89,7 @@ struct randt_problem {
   uint2* pairs = nullptr;
   Duo* duos = nullptr; uint32_t n_duos = 0;
   DuoRec* duo_recs = nullptr; uint32_t* duo_p0 = nullptr;
+  DuoRecFull* duo_overflow = nullptr; uint32_t n_overflow = 0;   // full-precision records of the duos the compact form cannot hold
   std::vector<uint32_t> h_duo_off;   // [S+1] duo offsets per segment
   uint32_t n_tiles = 0;
   ChunkDesc* chunks = nullptr; uint32_t n_chunks = 0;             // plan B: one tile per chunk (solver, EMIT)
@@ -160,7 +161,7 @@ void free_map(randt_map* m) {
 }
 void free_problem(randt_problem* p) {
   if (!p) return;
-  dev_free(p->cells_m); dev_free(p->cells_f); dev_free(p->pairs); dev_free(p->duos); dev_free(p->duo_recs); dev_free(p->duo_p0); dev_free(p->chunks); dev_free(p->warp_off); dev_free(p->chunks_full); dev_free(p->warp_off_full); dev_free(p->seg_first_tile); dev_free(p->seg_off);
+  dev_free(p->cells_m); dev_free(p->cells_f); dev_free(p->pairs); dev_free(p->duos); dev_free(p->duo_recs); dev_free(p->duo_p0); dev_free(p->duo_overflow); dev_free(p->chunks); dev_free(p->warp_off); dev_free(p->chunks_full); dev_free(p->warp_off_full); dev_free(p->seg_first_tile); dev_free(p->seg_off);
   dev_free(p->partials); dev_free(p->seg_counters); dev_free(p->d_poses); dev_free(p->d_out); dev_free(p->d_mu); dev_free(p->d_r);
   dev_free(p->d_J); dev_free(p->d_sweep);
   dev_free(p->lm_state); dev_free(p->lm_eval_pose); dev_free(p->lm_mu); dev_free(p->lm_rec); dev_free(p->lm_poses); dev_free(p->lm_result);
@@ -210,8 +211,20 @@ int finish_problem(randt_ctx* ctx, randt_problem* p) {
     if (e == cudaSuccess && !tile_duo_begin.empty())
       e = cudaMemcpyAsync(d_tdb, tile_duo_begin.data(), tile_duo_begin.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = launch_permute_duos(p->duos, d_trb, d_tdb, (uint32_t)tiles.size(), p->n_duos, d_stream, ctx->stream, &nl);
-    if (e == cudaSuccess) e = launch_build_duo_records(p->cells_m, p->cells_f, d_stream, p->n_duos, p->duo_recs, p->duo_p0, ctx->stream, &nl);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    // compact records; the few duos that do not fit go to an overflow table sized by a first guess and, if that was too small, rebuilt
+    uint32_t* d_novf = nullptr; uint32_t h_novf = 0, ovf_cap = std::max<uint32_t>(64u, p->n_duos / 512u);
+    if (e == cudaSuccess) e = dev_alloc(&d_novf, 1);
+    for (int attempt = 0; attempt < 2 && e == cudaSuccess; ++attempt) {
+      e = dev_alloc(&p->duo_overflow, ovf_cap);
+      if (e == cudaSuccess) e = cudaMemsetAsync(d_novf, 0, sizeof(uint32_t), ctx->stream);
+      if (e == cudaSuccess) e = launch_build_duo_records(p->cells_m, p->cells_f, d_stream, p->n_duos, p->duo_recs, p->duo_p0, p->duo_overflow, ovf_cap, d_novf, ctx->stream, &nl);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(&h_novf, d_novf, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+      if (e != cudaSuccess || h_novf <= ovf_cap) break;
+      dev_free(p->duo_overflow); p->duo_overflow = nullptr; ovf_cap = h_novf;
+    }
+    p->n_overflow = h_novf;
+    dev_free(d_novf);
     lap("uploads + records");
     dev_free(d_trb); dev_free(d_tdb); dev_free(d_stream);
     if (e != cudaSuccess) return fail(ctx, RANDT_E_CUDA, "finish_problem: record table", e);
@@ -234,7 +247,7 @@ int finish_problem(randt_ctx* ctx, randt_problem* p) {
 
 DeviceProblem view(const randt_problem* p) {
   DeviceProblem d;
-  d.cells_m = p->cells_m; d.cells_f = p->cells_f; d.pairs = p->pairs; d.duos = p->duos; d.duo_recs = p->duo_recs; d.duo_p0 = p->duo_p0; d.seg_off = p->seg_off; d.chunks = p->chunks; d.n_chunks = p->n_chunks; d.warp_off = p->warp_off; d.n_warps = p->n_warps;
+  d.cells_m = p->cells_m; d.cells_f = p->cells_f; d.pairs = p->pairs; d.duos = p->duos; d.duo_recs = p->duo_recs; d.duo_overflow = p->duo_overflow; d.duo_p0 = p->duo_p0; d.seg_off = p->seg_off; d.chunks = p->chunks; d.n_chunks = p->n_chunks; d.warp_off = p->warp_off; d.n_warps = p->n_warps;
   d.seg_first_tile = p->seg_first_tile; d.n_segments = p->S; d.n_pairs = p->P; d.partials = p->partials; d.seg_counters = p->seg_counters;
   d.seg_active = nullptr; d.plan_static = 1u; d.out_packed = 0u;
   return d;
@@ -763,6 +776,14 @@ int randt_problem_info(const randt_problem* p, uint32_t* n_segments, uint32_t* n
   if (n_pairs) *n_pairs = p->P;
   if (n_m) *n_m = p->n_m;
   if (n_f) *n_f = p->n_f;
+  return RANDT_OK;
+}
+
+int randt_problem_layout(const randt_problem* p, uint32_t* n_duos, uint32_t* record_bytes, uint32_t* n_overflow) {
+  if (!p) return RANDT_E_INVALID;
+  if (n_duos) *n_duos = p->n_duos;
+  if (record_bytes) *record_bytes = (uint32_t)sizeof(DuoRec);
+  if (n_overflow) *n_overflow = p->n_overflow;
   return RANDT_OK;
 }
 

@@ -27,17 +27,26 @@ struct LossParams {  // host-evaluated constants of the loss that do not depend 
 // the moving cell is loaded, converted and rotated once for both pairs.
 struct Duo { uint32_t im, jf0, jf1, p0; };   // moving cell, fixed cell of pair p0, fixed cell of pair p0 + 1 (kNoCell: none), first pair
 constexpr uint32_t kNoCell = 0xffffffffu;
-// What K3 streams: the duo with its three cells inlined (moving, fixed of pair p0, fixed of pair p0 + 1), 144 B.  A missing second
-// pair is marked by the bit pattern kNoSecondPair in the first float of the third cell (a NaN payload no arithmetic produces).
-struct __align__(16) DuoRec { float4 v[9]; };
-constexpr uint32_t kNoSecondPair = 0xffffffffu;
+// What K3 streams: the duo with its three cells inlined (moving, fixed of pair p0, fixed of pair p0 + 1) in the COMPACT form, 112 B.
+// K3 only ever uses the symmetric part of a covariance, i.e. per off-diagonal couple (a, b) the fp64 sum s = (double)a + (double)b.  A
+// cell is therefore stored as 9 floats — mean (x, y, i), diagonal (S00, S11, S22) and hs = float(s) rounded toward zero for the couples
+// (01,10), (02,20), (12,21) — plus a 2-bit code per couple: s has at most 26 significant bits (a and b are a few float-ulps apart), so
+// the bits of s are the bits of (double)hs with the code OR-ed in at bit 27.  The encoding is verified bit for bit when the table is
+// built; a duo with a couple that does not fit (exponents far apart: an off-diagonal that is rounding noise around zero) is flagged
+// kRecEscape and its word 0 indexes a full-precision record (9 x float4 = the three cells as stored) in the overflow table.
+//   words 9 c + 0..8 : cell c = (mx, my, mi, S00, S11, S22, hs01, hs02, hs12), c = 0 moving, 1 fixed of p0, 2 fixed of p0 + 1
+//   word 27          : bits 2 e, 2 e + 1 = code of couple e = 3 c + j;  kRecNoSecond: the duo has one pair only;  kRecEscape
+struct __align__(16) DuoRec { float4 v[7]; };
+struct __align__(16) DuoRecFull { float4 v[9]; };
+constexpr uint32_t kRecEscape = 0x80000000u, kRecNoSecond = 0x40000000u;
 
 struct DeviceProblem {
   const float4* cells_m;   // 3 x float4 per cell
   const float4* cells_f;
   const uint2* pairs;      // (im, jf), reference residual-block order
   const Duo* duos;         // the same pairs grouped two by two (shared moving cell)
-  const DuoRec* duo_recs;  // [n_duos] record-major table K3 streams with bulk copies
+  const DuoRec* duo_recs;  // [n_duos] record-major table K3 streams with bulk copies (compact form)
+  const DuoRecFull* duo_overflow;  // full-precision records of the (rare) duos flagged kRecEscape
   const uint32_t* duo_p0;  // [n_duos] first pair of each duo (EMIT output rows)
   const uint32_t* seg_off; // [S+1] pair offsets per segment
   const ChunkDesc* chunks; // in the balanced order: warp w owns chunks [warp_off[w], warp_off[w+1])
@@ -71,8 +80,11 @@ cudaError_t launch_eval_emit(const DeviceProblem& p, int variant, const double* 
                              unsigned long long* d_bad, cudaStream_t s, int* n_launches);
 cudaError_t launch_permute_duos(const Duo* in, const uint32_t* tile_rec_begin, const uint32_t* tile_duo_begin, uint32_t n_tiles, uint32_t n_duos,
                                 Duo* out, cudaStream_t s, int* n_launches);
+// d_n_overflow: device counter (zeroed by the caller) of the duos that needed a full record; records beyond overflow_cap are dropped
+// (the caller re-runs with a larger table when the count exceeds the capacity)
 cudaError_t launch_build_duo_records(const float4* cells_m, const float4* cells_f, const Duo* duos, uint32_t n_duos, DuoRec* recs,
-                                     uint32_t* duo_p0, cudaStream_t s, int* n_launches);
+                                     uint32_t* duo_p0, DuoRecFull* overflow, uint32_t overflow_cap, uint32_t* d_n_overflow, cudaStream_t s,
+                                     int* n_launches);
 cudaError_t launch_sweep_costs(const DeviceProblem& p, uint32_t pair_begin, uint32_t pair_end, int variant, const double* d_poses,
                                uint32_t n_poses, const LossParams& lp, double* d_cost, cudaStream_t s, int* n_launches);
 

@@ -20,7 +20,7 @@
 // Work decomposition (B200: 148 SMs, fp64 64 lanes/clk/SM — the co-limiter next to HBM).  Pairs are grouped into duos (two pairs
 // that share their moving cell, one lane each) and the duos of a segment (= pose) into tiles; ONE WARP owns a tile.  The host assigns
 // tiles to the 148 x 16 resident warps of a persistent grid (longest-processing-time first) and lays the duo records — moving cell
-// and both fixed cells inlined, 144 B — out in that order, so a warp streams ONE contiguous range: every chunk of 32 records is a
+// and both fixed cells inlined in the compact 112-byte form of common.cuh — out in that order, so a warp streams ONE contiguous range: every chunk of 32 records is a
 // single bulk copy (TMA, cp.async.bulk + mbarrier) into a two-stage shared-memory ring, described by a 16-byte chunk descriptor.
 // Partial sums stay in registers; at a tile's end they are transposed through the just-consumed stage buffer and added in a fixed
 // order (deterministic), and lanes e < 24 write the record.  Segments longer than one tile are folded by the last warp to finish
@@ -52,6 +52,29 @@ struct LossConst {
 };
 
 struct RawCell { float4 a, b, c; };   // mean (x, y, i) + row-major 3x3 covariance, as stored (12 floats)
+// What the arithmetic consumes of a cell: mean, diagonal, and the fp64 sums of the off-diagonal couples (twice the symmetric part)
+struct CellC { float mx, my, mi, s00, s11, s22; double b2, e2, f2; };   // b2 = S01 + S10, e2 = S02 + S20, f2 = S12 + S21
+__device__ __forceinline__ CellC cellc_from_raw(const RawCell& m) {
+  CellC c;
+  c.mx = m.a.x; c.my = m.a.y; c.mi = m.a.z; c.s00 = m.a.w; c.s11 = m.b.w; c.s22 = m.c.w;
+  c.b2 = (double)m.b.x + (double)m.b.z; c.e2 = (double)m.b.y + (double)m.c.y; c.f2 = (double)m.c.x + (double)m.c.z;
+  return c;
+}
+// compact record couple -> fp64 sum: the bits of (double)hs with the 2-bit code at bits 27..28 (common.cuh: DuoRec)
+constexpr uint32_t kCodeMask = 0x18000000u;
+__device__ __forceinline__ double sym_decode(float hs, uint32_t code_at_27) {
+  const double d = (double)hs;
+  return __hiloint2double(__double2hiint(d), __double2loint(d) | (int)(code_at_27 & kCodeMask));
+}
+// the inverse, verified bit for bit: false when s = (double)a + (double)b is not (double)float_rz(s) | code << 27 with code < 4
+__device__ __forceinline__ bool sym_encode(float a, float b, float& hs, uint32_t& code) {
+  const double s = (double)a + (double)b;
+  hs = __double2float_rz(s);
+  const unsigned long long sb = (unsigned long long)__double_as_longlong(s), db = (unsigned long long)__double_as_longlong((double)hs);
+  const unsigned long long c = (sb - db) >> 27;
+  code = (uint32_t)(c & 3ull);
+  return c < 4ull && (db | (c << 27)) == sb;
+}
 
 // 1/x for a normal, finite, non-zero x: MUFU.RCP64H seed (2^-23) + two Newton steps.  No slow path: callers guarantee or
 // tolerate garbage-in-garbage-out (degenerate pairs are caught by the validity test on dd).
@@ -90,9 +113,9 @@ struct Moving {
   double xr, yr;                          // R mu_m (no translation)
 };
 template <int VARIANT>
-__device__ __forceinline__ void moving_part(const PoseConst& k, const RawCell& m, Moving& o) {
-  o.mx = m.a.x; o.my = m.a.y; o.S00 = m.a.w; o.S11 = m.b.w;
-  const double b2 = (double)m.b.x + (double)m.b.z;              // 2 * sym(S01)
+__device__ __forceinline__ void moving_part(const PoseConst& k, const CellC& m, Moving& o) {
+  o.mx = m.mx; o.my = m.my; o.S00 = m.s00; o.S11 = m.s11;
+  const double b2 = m.b2;                                       // 2 * sym(S01)
   o.bh = 0.5 * b2;
   o.M00 = fma(k.cc, o.S00, fma(k.ss, o.S11, -k.cs * b2));
   o.M11 = fma(k.n2, o.S00 + o.S11, -o.M00);
@@ -100,29 +123,29 @@ __device__ __forceinline__ void moving_part(const PoseConst& k, const RawCell& m
   o.xr = fma(k.c, o.mx, -k.s * o.my);
   o.yr = fma(k.s, o.mx, k.c * o.my);
   if (VARIANT == 0 || VARIANT == 2) {
-    const double e2 = (double)m.b.y + (double)m.c.y;            // 2 * sym(S02)
-    const double f2 = (double)m.c.x + (double)m.c.z;            // 2 * sym(S12)
+    const double e2 = m.e2;                                     // 2 * sym(S02)
+    const double f2 = m.f2;                                     // 2 * sym(S12)
     o.M02 = fma(k.ch, e2, -k.sh * f2);
     o.M12 = fma(k.sh, e2, k.ch * f2);
-    o.mi = m.a.z; o.S22 = m.c.w;
+    o.mi = m.mi; o.S22 = m.s22;
   } else {
     o.M02 = 0.0; o.M12 = 0.0; o.mi = 0.0; o.S22 = 0.0;
   }
 }
 // dd = d^T B^-1 d and (WANT_JAC) the basis numerators N[] = r * dr/d(basis), in the basis order of VarTraits.
 template <int VARIANT, bool WANT_JAC>
-__device__ __forceinline__ double fixed_part(const PoseConst& k, const Moving& mv, const RawCell& f, double* __restrict__ N) {
-  const double d0 = (mv.xr + k.tx) - (double)f.a.x;
-  const double d1 = (mv.yr + k.ty) - (double)f.a.y;
-  const double B00 = mv.M00 + (double)f.a.w;
-  const double B11 = mv.M11 + (double)f.b.w;
-  const double B01 = fma(0.5, (double)f.b.x + (double)f.b.z, mv.M01);
+__device__ __forceinline__ double fixed_part(const PoseConst& k, const Moving& mv, const CellC& f, double* __restrict__ N) {
+  const double d0 = (mv.xr + k.tx) - (double)f.mx;
+  const double d1 = (mv.yr + k.ty) - (double)f.my;
+  const double B00 = mv.M00 + (double)f.s00;
+  const double B11 = mv.M11 + (double)f.s11;
+  const double B01 = fma(0.5, f.b2, mv.M01);
   double q0, q1, q2 = 0.0, dd;
   if (VARIANT == 0 || VARIANT == 2) {
-    const double d2 = mv.mi - (double)f.a.z;
-    const double B22 = mv.S22 + (double)f.c.w;
-    const double B02 = fma(0.5, (double)f.b.y + (double)f.c.y, mv.M02);
-    const double B12 = fma(0.5, (double)f.c.x + (double)f.c.z, mv.M12);
+    const double d2 = mv.mi - (double)f.mi;
+    const double B22 = mv.S22 + (double)f.s22;
+    const double B02 = fma(0.5, f.e2, mv.M02);
+    const double B12 = fma(0.5, f.f2, mv.M12);
     const double C00 = fma(B11, B22, -B12 * B12);
     const double C01 = fma(B02, B12, -B01 * B22);
     const double C02 = fma(B01, B12, -B02 * B11);
@@ -165,8 +188,8 @@ __device__ __forceinline__ double fixed_part(const PoseConst& k, const Moving& m
 template <int VARIANT, bool WANT_JAC>
 __device__ __forceinline__ double pair_core(const PoseConst& k, const RawCell& m, const RawCell& f, double* __restrict__ N) {
   Moving mv;
-  moving_part<VARIANT>(k, m, mv);
-  return fixed_part<VARIANT, WANT_JAC>(k, mv, f, N);
+  moving_part<VARIANT>(k, cellc_from_raw(m), mv);
+  return fixed_part<VARIANT, WANT_JAC>(k, mv, cellc_from_raw(f), N);
 }
 
 __device__ __forceinline__ bool dd_valid(double dd) { return (dd >= 0.0) && (dd < 1.0e300); }   // false for NaN, inf, negative
@@ -389,12 +412,40 @@ constexpr int kWarpsPerCta = kK3Threads / 32;
 constexpr int kStages = RANDT_K3_STAGES;
 constexpr int kMinCtas = RANDT_K3_MIN_CTAS;   // CTAs per SM the register allocation is bounded for
 
-struct __align__(128) StageBuf {
-  float4 rec[32][9];       // the chunk's duo records (144 B each, see DuoRec in common.cuh), landed by ONE bulk copy
+constexpr int kRecF4 = (int)(sizeof(DuoRec) / sizeof(float4));   // float4 per compact record (7)
+// SCRATCH_BYTES: what the tile epilogue needs of the record area when it is reused as reduction scratch (NS * 34 doubles)
+template <int SCRATCH_BYTES>
+struct __align__(128) StageBufT {
+  static constexpr int kAreaF4 = (SCRATCH_BYTES > 32 * (int)sizeof(DuoRec) ? SCRATCH_BYTES : 32 * (int)sizeof(DuoRec)) / 16;
+  float4 rec[kAreaF4];     // the chunk's duo records (112 B each, see DuoRec in common.cuh), landed by ONE bulk copy
   double pose[2][4];       // [0]: pose of the tile at lane 0 (valid for the first chunk of a tile); [1]: pose of the tile that starts
   double mu[2];            //      inside a split chunk; mu likewise
   unsigned long long bar;  // mbarrier the bulk copy completes on
 };
+
+// One lane's duo out of the landed chunk: seven conflict-free LDS.128, then the couples' sums are rebuilt from their codes.  A duo
+// flagged kRecEscape fetches its three cells as stored from the overflow table instead (rare: divergent global loads).
+__device__ __forceinline__ void load_duo(const float4* __restrict__ rec, int lane, const DuoRecFull* __restrict__ ovf, CellC& m, CellC& f0,
+                                         CellC& f1, bool& two) {
+  const float4* r = rec + lane * kRecF4;
+  const float4 v0 = r[0], v1 = r[1], v2 = r[2], v3 = r[3], v4 = r[4], v5 = r[5], v6 = r[6];
+  const uint32_t w = __float_as_uint(v6.w);
+  two = (w & kRecNoSecond) == 0u;
+  if ((w & kRecEscape) == 0u) {
+    m.mx = v0.x; m.my = v0.y; m.mi = v0.z; m.s00 = v0.w; m.s11 = v1.x; m.s22 = v1.y;
+    m.b2 = sym_decode(v1.z, w << 27); m.e2 = sym_decode(v1.w, w << 25); m.f2 = sym_decode(v2.x, w << 23);
+    f0.mx = v2.y; f0.my = v2.z; f0.mi = v2.w; f0.s00 = v3.x; f0.s11 = v3.y; f0.s22 = v3.z;
+    f0.b2 = sym_decode(v3.w, w << 21); f0.e2 = sym_decode(v4.x, w << 19); f0.f2 = sym_decode(v4.y, w << 17);
+    f1.mx = v4.z; f1.my = v4.w; f1.mi = v5.x; f1.s00 = v5.y; f1.s11 = v5.z; f1.s22 = v5.w;
+    f1.b2 = sym_decode(v6.x, w << 15); f1.e2 = sym_decode(v6.y, w << 13); f1.f2 = sym_decode(v6.z, w << 11);
+  } else {
+    const float4* q = ovf[__float_as_uint(v0.x)].v;
+    RawCell c;
+    c.a = __ldg(q + 0); c.b = __ldg(q + 1); c.c = __ldg(q + 2); m = cellc_from_raw(c);
+    c.a = __ldg(q + 3); c.b = __ldg(q + 4); c.c = __ldg(q + 5); f0 = cellc_from_raw(c);
+    c.a = __ldg(q + 6); c.b = __ldg(q + 7); c.c = __ldg(q + 8); f1 = cellc_from_raw(c);
+  }
+}
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
@@ -448,39 +499,43 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 // bulk (TMA) copy of the chunk's duo records plus, for the first chunk of a tile, 16-byte cp.async copies of the segment's pose
 // and mu.  No per-chunk index arithmetic, no gathers, no LSU traffic for the cell data.
 struct WarpQueue {
-  ChunkDesc* q;        // [32] in shared memory
-  uint32_t c_base, c_end, act_mask;
-  __device__ __forceinline__ uint4 load_desc(const DeviceProblem& P, int lane) const {   // (duo_begin, meta, seg, part); meta 0 past the end
-    const uint32_t idx = c_base + (uint32_t)lane;
+  ChunkDesc* q;        // [64] in shared memory: two halves of 32; chunk j of the warp's list sits in q[j & 63]
+  uint32_t c_begin, c_end, act[2];
+  __device__ __forceinline__ uint4 load_desc(const DeviceProblem& P, uint32_t block, int lane) const {   // (duo_begin, meta, seg, part); meta 0 past the end
+    const uint32_t idx = c_begin + block * 32u + (uint32_t)lane;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
     if (idx < c_end) v = __ldg(reinterpret_cast<const uint4*>(P.chunks) + idx);
     return v;
   }
-  __device__ __forceinline__ void publish(const DeviceProblem& P, uint4 v, int lane) {      // active flags, queue, warp barrier
+  __device__ __forceinline__ void publish(const DeviceProblem& P, uint4 v, uint32_t block, int lane) {   // active flags, queue, warp barrier
     uint32_t on = 0;
     if (v.y & kChunkCountMask) on = P.seg_active ? P.seg_active[v.z] : 1u;
-    *reinterpret_cast<uint4*>(&q[lane]) = v;
-    act_mask = __ballot_sync(kFull, on != 0u);
+    *reinterpret_cast<uint4*>(&q[(block & 1u) * 32u + (uint32_t)lane]) = v;
+    const uint32_t mask = __ballot_sync(kFull, on != 0u);
+    if (block & 1u) act[1] = mask; else act[0] = mask;
     __syncwarp();
   }
-  __device__ __forceinline__ void refill(const DeviceProblem& P, int lane) { publish(P, load_desc(P, lane), lane); }
-  __device__ __forceinline__ ChunkDesc get(int j) const {
-    const uint4 v = *reinterpret_cast<const uint4*>(&q[j]);
+  // Block b (chunks 32 b .. 32 b + 31) replaces block b - 2 in its half: by the time chunk 32 b is staged, the chunk being consumed is
+  // at most kStages - 1 <= 32 behind it, i.e. in block b - 1 or later.
+  __device__ __forceinline__ void refill(const DeviceProblem& P, uint32_t block, int lane) { publish(P, load_desc(P, block, lane), block, lane); }
+  __device__ __forceinline__ ChunkDesc get(uint32_t j) const {
+    const uint4 v = *reinterpret_cast<const uint4*>(&q[j & 63u]);
     ChunkDesc d; d.duo_begin = v.x; d.meta = v.y; d.seg = v.z; d.part = v.w;
     return d;
   }
+  __device__ __forceinline__ bool live(uint32_t j) const { return (((j & 32u) ? act[1] : act[0]) >> (j & 31u)) & 1u; }
 };
 
-template <int NP>
-__device__ __forceinline__ void stage_issue(const DeviceProblem& P, const WarpQueue& wq, int j, int lane, StageBuf* sb,
+template <int NP, typename SB>
+__device__ __forceinline__ void stage_issue(const DeviceProblem& P, const WarpQueue& wq, uint32_t j, int lane, SB* sb,
                                             const double* __restrict__ poses, const double* __restrict__ mu_per_seg) {
-  if (lane == 0 && ((wq.act_mask >> j) & 1u)) {
+  if (lane == 0 && wq.live(j)) {
     const ChunkDesc d = wq.get(j);
     const uint32_t n_here = d.meta & kChunkCountMask;
     if (n_here) {
       const uint32_t bytes = n_here * (uint32_t)sizeof(DuoRec);
       mbar_expect_tx(&sb->bar, bytes);
-      bulk_g2s(&sb->rec[0][0], P.duo_recs + d.duo_begin, bytes, &sb->bar);
+      bulk_g2s(&sb->rec[0], P.duo_recs + d.duo_begin, bytes, &sb->bar);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         if (d.meta & (h == 0 ? kChunkFirst : kChunkSplit)) {
@@ -544,16 +599,14 @@ __device__ __forceinline__ void finish_tile(const DeviceProblem& P, const double
 
 // One lane's duo (two pairs sharing their moving cell) added into `acc` (H upper triangle, g, cost, sum dd), max dd, bad count.
 template <int VARIANT, int LOSS, bool WANT_JAC, int NS>
-__device__ __forceinline__ void accumulate_duo(const PoseConst& kc, const LossConst& lc, const StageBuf* sb, int lane, double* acc, double& max_dd,
-                                               uint32_t& n_bad) {
+__device__ __forceinline__ void accumulate_duo(const PoseConst& kc, const LossConst& lc, const float4* __restrict__ rec, const DuoRecFull* __restrict__ ovf,
+                                               int lane, double* acc, double& max_dd, uint32_t& n_bad) {
   constexpr int NB = VarTraits<VARIANT>::NB;
   constexpr int NH = NB * (NB + 1) / 2;
   constexpr int NJ = WANT_JAC ? NH + NB : 0;
-  RawCell m, f[2];
-  m.a = sb->rec[lane][0]; m.b = sb->rec[lane][1]; m.c = sb->rec[lane][2];
-  f[0].a = sb->rec[lane][3]; f[0].b = sb->rec[lane][4]; f[0].c = sb->rec[lane][5];
-  f[1].a = sb->rec[lane][6]; f[1].b = sb->rec[lane][7]; f[1].c = sb->rec[lane][8];
-  const bool two = __float_as_uint(f[1].a.x) != kNoSecondPair;
+  CellC m, f[2];
+  bool two;
+  load_duo(rec, lane, ovf, m, f[0], f[1], two);
   Moving mv;
   moving_part<VARIANT>(kc, m, mv);
   double dd[2], N[2][4], wgt[2], hrho[2], wd[2];
@@ -617,15 +670,17 @@ __global__ void __launch_bounds__(kK3Threads, kMinCtas) k3_fused_kernel(DevicePr
   constexpr int NH = NB * (NB + 1) / 2;
   constexpr int NJ = WANT_JAC ? NH + NB : 0;     // additive slots: H, g, then cost, sum dd
   constexpr int NS = NJ + 2;
+  using StageBuf = StageBufT<NS * 34 * 8>;
   __shared__ StageBuf stage_all[kWarpsPerCta][kStages];
   const int lane = threadIdx.x & 31;
   const int warp = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0);
   const uint32_t w = blockIdx.x * kWarpsPerCta + warp;
   if (w >= P.n_warps) return;
   StageBuf* stage = stage_all[warp];
-  __shared__ ChunkDesc queue_all[kWarpsPerCta][32];
+  __shared__ ChunkDesc queue_all[kWarpsPerCta][64];
   WarpQueue wq;
   wq.q = queue_all[warp];
+  wq.act[0] = 0u; wq.act[1] = 0u;
   griddep_launch_dependents();
   if (lane == 0) {
 #pragma unroll
@@ -636,14 +691,14 @@ __global__ void __launch_bounds__(kK3Threads, kMinCtas) k3_fused_kernel(DevicePr
   // after griddep_wait(); the static schedule of a problem is immutable, so its first descriptors are fetched while the
   // previous grid is still draining.
   if (!P.plan_static) griddep_wait();
-  wq.c_base = P.warp_off[w]; wq.c_end = P.warp_off[w + 1];
-  const uint4 v_first = wq.load_desc(P, lane);
+  wq.c_begin = P.warp_off[w]; wq.c_end = P.warp_off[w + 1];
+  const uint4 v_first = wq.load_desc(P, 0u, lane);
   if (P.plan_static) griddep_wait();
-  if (wq.c_base >= wq.c_end) return;
-  wq.publish(P, v_first, lane);        // includes the warp barrier that publishes the mbarrier init
+  if (wq.c_begin >= wq.c_end) return;
+  wq.publish(P, v_first, 0u, lane);    // includes the warp barrier that publishes the mbarrier init
   // prologue: chunks 0 .. kStages-2 in flight (a warp owns at least one chunk; kStages - 1 <= 31 descriptors are in the queue)
 #pragma unroll
-  for (int s = 0; s < kStages - 1; ++s) stage_issue<NP>(P, wq, s, lane, &stage[s], poses, mu_per_seg);
+  for (int s = 0; s < kStages - 1; ++s) stage_issue<NP>(P, wq, (uint32_t)s, lane, &stage[s], poses, mu_per_seg);
   uint32_t phase_bits = 0u;     // bit s: parity the next completion of stage s's barrier will have
 
   // Pose and loss constants of the tile(s) in flight live in shared memory (two slots per warp: a split chunk carries the tail of
@@ -655,15 +710,16 @@ __global__ void __launch_bounds__(kK3Threads, kMinCtas) k3_fused_kernel(DevicePr
   double acc[NS]; double max_dd = 0.0; uint32_t n_bad = 0;
 #pragma unroll
   for (int e = 0; e < NS; ++e) acc[e] = 0.0;
-  int slot = 0, jj = 0;
+  int slot = 0;
+  uint32_t jj = 0;              // index of the chunk being consumed in the warp's list
   while (true) {
     const ChunkDesc cm = wq.get(jj);
     const uint32_t n_here = cm.meta & kChunkCountMask;
     if (n_here == 0u) break;                                  // past the warp's last chunk
-    const bool live = (wq.act_mask >> jj) & 1u;               // false: chunk of an inactive segment (nothing was copied)
+    const bool live = wq.live(jj);                            // false: chunk of an inactive segment (nothing was copied)
     // ---- stage chunk j + kStages - 1 ----
-    int jn = jj + kStages - 1;
-    if (jn >= 32) { wq.c_base += 32u; wq.refill(P, lane); jn -= 32; jj -= 32; }   // cm is already in registers
+    const uint32_t jn = jj + (uint32_t)(kStages - 1);
+    if ((jn & 31u) == 0u) wq.refill(P, jn >> 5, lane);        // first chunk of a new block of 32 descriptors
     int islot = slot + kStages - 1; if (islot >= kStages) islot -= kStages;
     stage_issue<NP>(P, wq, jn, lane, &stage[islot], poses, mu_per_seg);
     // ---- chunk j has landed ----
@@ -683,10 +739,10 @@ __global__ void __launch_bounds__(kK3Threads, kMinCtas) k3_fused_kernel(DevicePr
       }
       __syncwarp();
     }
-    double* scratch = reinterpret_cast<double*>(&sb->rec[0][0]);
+    double* scratch = reinterpret_cast<double*>(&sb->rec[0]);
     if (!split) {
       const PoseConst& kc = kc_all[warp][ts]; const LossConst& lc = lc_all[warp][ts];
-      if (live && (uint32_t)lane < n_here) accumulate_duo<VARIANT, LOSS, WANT_JAC, NS>(kc, lc, sb, lane, acc, max_dd, n_bad);
+      if (live && (uint32_t)lane < n_here) accumulate_duo<VARIANT, LOSS, WANT_JAC, NS>(kc, lc, sb->rec, P.duo_overflow, lane, acc, max_dd, n_bad);
       if (live && (cm.meta & kChunkLast)) {
         finish_tile<VARIANT, WANT_JAC, NS>(P, acc, max_dd, n_bad, cm.seg, (cm.meta & kChunkSolo) != 0u, cm.part, kc, scratch, out, bad_counter, lane);
 #pragma unroll
@@ -701,7 +757,7 @@ __global__ void __launch_bounds__(kK3Threads, kMinCtas) k3_fused_kernel(DevicePr
       double c[NS]; double mc = 0.0; uint32_t cb = 0;
 #pragma unroll
       for (int e = 0; e < NS; ++e) c[e] = 0.0;
-      if ((uint32_t)lane < n_here) accumulate_duo<VARIANT, LOSS, WANT_JAC, NS>(kc_all[warp][my], lc_all[warp][my], sb, lane, c, mc, cb);
+      if ((uint32_t)lane < n_here) accumulate_duo<VARIANT, LOSS, WANT_JAC, NS>(kc_all[warp][my], lc_all[warp][my], sb->rec, P.duo_overflow, lane, c, mc, cb);
       double vals[NS];
 #pragma unroll
       for (int e = 0; e < NS; ++e) vals[e] = acc[e] + (mine_new ? 0.0 : c[e]);
@@ -756,35 +812,38 @@ template <int VARIANT, bool WANT_JAC>
 __global__ void __launch_bounds__(kK3Threads, kMinCtas) k3_emit_kernel(DeviceProblem P, const double* __restrict__ poses, double* __restrict__ r_out,
                                                                       double* __restrict__ J_out, unsigned long long* __restrict__ bad_counter) {
   constexpr int NP = VarTraits<VARIANT>::NP;
+  using StageBuf = StageBufT<0>;
   __shared__ StageBuf stage_all[kWarpsPerCta][kStages];
   const int lane = threadIdx.x & 31;
   const int warp = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0);
   const uint32_t w = blockIdx.x * kWarpsPerCta + warp;
   if (w >= P.n_warps) return;
   StageBuf* stage = stage_all[warp];
-  __shared__ ChunkDesc queue_all[kWarpsPerCta][32];
+  __shared__ ChunkDesc queue_all[kWarpsPerCta][64];
   WarpQueue wq;
   wq.q = queue_all[warp];
-  wq.c_base = P.warp_off[w]; wq.c_end = P.warp_off[w + 1];
-  if (wq.c_base >= wq.c_end) return;
+  wq.act[0] = 0u; wq.act[1] = 0u;
+  wq.c_begin = P.warp_off[w]; wq.c_end = P.warp_off[w + 1];
+  if (wq.c_begin >= wq.c_end) return;
   if (lane == 0) {
 #pragma unroll
     for (int s = 0; s < kStages; ++s) mbar_init(&stage[s].bar, 1u);
     fence_mbar_init();
   }
-  wq.refill(P, lane);
+  wq.refill(P, 0u, lane);
 #pragma unroll
-  for (int s = 0; s < kStages - 1; ++s) stage_issue<NP>(P, wq, s, lane, &stage[s], poses, nullptr);
+  for (int s = 0; s < kStages - 1; ++s) stage_issue<NP>(P, wq, (uint32_t)s, lane, &stage[s], poses, nullptr);
   PoseConst kc;
   uint32_t n_bad = 0, phase_bits = 0u;
-  int slot = 0, jj = 0;
+  int slot = 0;
+  uint32_t jj = 0;
   while (true) {
     const ChunkDesc cm = wq.get(jj);
     const uint32_t n_here = cm.meta & kChunkCountMask;
     if (n_here == 0u) break;
-    const bool live = (wq.act_mask >> jj) & 1u;
-    int jn = jj + kStages - 1;
-    if (jn >= 32) { wq.c_base += 32u; wq.refill(P, lane); jn -= 32; jj -= 32; }
+    const bool live = wq.live(jj);
+    const uint32_t jn = jj + (uint32_t)(kStages - 1);
+    if ((jn & 31u) == 0u) wq.refill(P, jn >> 5, lane);
     int islot = slot + kStages - 1; if (islot >= kStages) islot -= kStages;
     stage_issue<NP>(P, wq, jn, lane, &stage[islot], poses, nullptr);
     cp_async_wait<kStages - 1>();
@@ -793,18 +852,16 @@ __global__ void __launch_bounds__(kK3Threads, kMinCtas) k3_emit_kernel(DevicePro
     if (live) { mbar_wait(&sb->bar, (phase_bits >> slot) & 1u); phase_bits ^= 1u << slot; }
     if ((cm.meta & kChunkFirst) && live) make_pose_const<VARIANT>(sb->pose[0], kc);
     if (live && (uint32_t)lane < n_here) {
-      RawCell m, f0, f1;
-      m.a = sb->rec[lane][0]; m.b = sb->rec[lane][1]; m.c = sb->rec[lane][2];
-      f0.a = sb->rec[lane][3]; f0.b = sb->rec[lane][4]; f0.c = sb->rec[lane][5];
+      CellC m, f0, f1;
+      bool two;
+      load_duo(sb->rec, lane, P.duo_overflow, m, f0, f1, two);
       const uint32_t p0 = __ldg(P.duo_p0 + cm.duo_begin + lane);     // first pair of the duo: where its rows go in r / J
       Moving mv;
       moving_part<VARIANT>(kc, m, mv);
       double N[4] = {0.0, 0.0, 0.0, 0.0};
       const double dd0 = fixed_part<VARIANT, WANT_JAC>(kc, mv, f0, N);
       emit_one<VARIANT, WANT_JAC>(kc, p0, dd0, N, r_out, J_out, n_bad);
-      f1.a = sb->rec[lane][6];
-      if (__float_as_uint(f1.a.x) != kNoSecondPair) {
-        f1.b = sb->rec[lane][7]; f1.c = sb->rec[lane][8];
+      if (two) {
         const double dd1 = fixed_part<VARIANT, WANT_JAC>(kc, mv, f1, N);
         emit_one<VARIANT, WANT_JAC>(kc, p0 + 1u, dd1, N, r_out, J_out, n_bad);
       }
@@ -862,22 +919,49 @@ __global__ void __launch_bounds__(kSweepThreads) k3_sweep_kernel(DeviceProblem P
   if (active) cost_out[pi] = cost;
 }
 
-// Record-major duo table: record d = [moving cell | fixed cell of pair p0 | fixed cell of pair p0+1 (or the kNoSecondPair marker)],
-// 9 x float4 = 144 B, so that the 32 duos of a chunk are one contiguous 4608-byte block that a single bulk copy can land.
-__global__ void __launch_bounds__(256) build_duo_records_kernel(const float4* __restrict__ cells_m, const float4* __restrict__ cells_f,
-                                                                const Duo* __restrict__ duos, uint32_t n_duos, float4* __restrict__ recs,
-                                                                uint32_t* __restrict__ duo_p0) {
-  const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= (uint64_t)n_duos * 9u) return;
-  const uint32_t d = (uint32_t)(e / 9u), j = (uint32_t)(e - (uint64_t)d * 9u);
+// Record-major duo table in the compact form (common.cuh: DuoRec): record d = [moving cell | fixed cell of pair p0 | fixed cell of pair
+// p0 + 1] as 3 x 9 floats + the code word, 112 B, so that the 32 duos of a chunk are one contiguous 3584-byte block that a single bulk
+// copy lands.  One thread per duo; a duo whose couples do not fit the encoding goes to the overflow table as stored.
+__global__ void __launch_bounds__(128) build_duo_records_kernel(const float4* __restrict__ cells_m, const float4* __restrict__ cells_f,
+                                                                const Duo* __restrict__ duos, uint32_t n_duos, DuoRec* __restrict__ recs,
+                                                                uint32_t* __restrict__ duo_p0, DuoRecFull* __restrict__ overflow, uint32_t overflow_cap,
+                                                                uint32_t* __restrict__ n_overflow) {
+  const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= n_duos) return;
   const Duo du = duos[d];
-  float4 v;
-  if (j < 3) v = __ldg(cells_m + 3 * (size_t)du.im + j);
-  else if (j < 6) v = __ldg(cells_f + 3 * (size_t)du.jf0 + (j - 3));
-  else if (du.jf1 != kNoCell) v = __ldg(cells_f + 3 * (size_t)du.jf1 + (j - 6));
-  else { const float mk = __uint_as_float(kNoSecondPair); v = make_float4(mk, mk, mk, mk); }
-  recs[e] = v;
-  if (j == 0) duo_p0[d] = du.p0;
+  const bool two = du.jf1 != kNoCell;
+  RawCell c[3];
+  c[0].a = __ldg(cells_m + 3 * (size_t)du.im); c[0].b = __ldg(cells_m + 3 * (size_t)du.im + 1); c[0].c = __ldg(cells_m + 3 * (size_t)du.im + 2);
+  c[1].a = __ldg(cells_f + 3 * (size_t)du.jf0); c[1].b = __ldg(cells_f + 3 * (size_t)du.jf0 + 1); c[1].c = __ldg(cells_f + 3 * (size_t)du.jf0 + 2);
+  c[2] = c[1];                                  // a missing second pair repeats the first (finite values; kRecNoSecond keeps it out of the sums)
+  if (two) { c[2].a = __ldg(cells_f + 3 * (size_t)du.jf1); c[2].b = __ldg(cells_f + 3 * (size_t)du.jf1 + 1); c[2].c = __ldg(cells_f + 3 * (size_t)du.jf1 + 2); }
+  float o[28];
+  uint32_t w = two ? 0u : kRecNoSecond;
+  bool fits = true;
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    o[9 * q + 0] = c[q].a.x; o[9 * q + 1] = c[q].a.y; o[9 * q + 2] = c[q].a.z;
+    o[9 * q + 3] = c[q].a.w; o[9 * q + 4] = c[q].b.w; o[9 * q + 5] = c[q].c.w;
+    uint32_t code;
+    fits = sym_encode(c[q].b.x, c[q].b.z, o[9 * q + 6], code) && fits; w |= code << (2 * (3 * q + 0));
+    fits = sym_encode(c[q].b.y, c[q].c.y, o[9 * q + 7], code) && fits; w |= code << (2 * (3 * q + 1));
+    fits = sym_encode(c[q].c.x, c[q].c.z, o[9 * q + 8], code) && fits; w |= code << (2 * (3 * q + 2));
+  }
+  if (!fits) {
+    const uint32_t idx = atomicAdd(n_overflow, 1u);
+    if (idx < overflow_cap) {
+      float4* q = overflow[idx].v;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { q[3 * i] = c[i].a; q[3 * i + 1] = c[i].b; q[3 * i + 2] = c[i].c; }
+    }
+    o[0] = __uint_as_float(idx);
+    w = (w & kRecNoSecond) | kRecEscape;
+  }
+  o[27] = __uint_as_float(w);
+  float4* dst = recs[d].v;
+#pragma unroll
+  for (int i = 0; i < 7; ++i) dst[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+  duo_p0[d] = du.p0;
 }
 
 int loss_code(const LossParams& lp) {
@@ -951,10 +1035,10 @@ cudaError_t launch_permute_duos(const Duo* in, const uint32_t* tile_rec_begin, c
 }
 
 cudaError_t launch_build_duo_records(const float4* cells_m, const float4* cells_f, const Duo* duos, uint32_t n_duos, DuoRec* recs,
-                                     uint32_t* duo_p0, cudaStream_t s, int* n_launches) {
+                                     uint32_t* duo_p0, DuoRecFull* overflow, uint32_t overflow_cap, uint32_t* d_n_overflow, cudaStream_t s,
+                                     int* n_launches) {
   if (n_duos == 0) return cudaSuccess;
-  const uint64_t n = (uint64_t)n_duos * 9u;
-  build_duo_records_kernel<<<(unsigned)((n + 255u) / 256u), 256, 0, s>>>(cells_m, cells_f, duos, n_duos, reinterpret_cast<float4*>(recs), duo_p0);
+  build_duo_records_kernel<<<(n_duos + 127u) / 128u, 128, 0, s>>>(cells_m, cells_f, duos, n_duos, recs, duo_p0, overflow, overflow_cap, d_n_overflow);
   if (n_launches) *n_launches += 1;
   return cudaGetLastError();
 }

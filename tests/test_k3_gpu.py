@@ -293,3 +293,46 @@ def test_fused_one_very_long_segment(oracle, gpu_ctx):
     assert o["n"][0] == P_
     assert H.rel_err(o["H"][0], fo["H"]) < 1e-9 and H.rel_err(o["g"][0], fo["g"]) < 1e-9
     assert abs(o["cost"][0] - fo["cost"]) <= 1e-10 * fo["cost"]
+
+
+def test_compact_records_hold_asymmetric_cells_and_overflow(oracle, gpu_ctx):
+    """K3 streams 112-byte records that carry, per off-diagonal couple (a, b) of a covariance, float_rz(a + b) and a 2-bit code (common.cuh).
+    Covariances that are asymmetric at float-ulp level (what V L V^-1 and R S R^T leave behind) must be held exactly; a couple whose two
+    entries are far apart in exponent (rounding noise around zero) cannot be and must take the full-precision overflow record."""
+    rng = np.random.default_rng(77)
+    cm = H.random_cells(rng, 300); cf = H.random_cells(rng, 700)
+    for c in (cm, cf):
+        for i, j in ((4, 6), (5, 9), (8, 10)):
+            steps = rng.integers(-3, 4, len(c))
+            v = c[:, j].copy()
+            for _ in range(3):
+                up = steps > 0; dn = steps < 0
+                v[up] = np.nextafter(v[up], np.float32(np.inf)); v[dn] = np.nextafter(v[dn], np.float32(-np.inf))
+                steps -= np.sign(steps)
+            c[:, j] = v
+    esc_m = np.array([5, 77, 201]); esc_f = np.array([0, 13, 400, 699])
+    cm[esc_m, 4] = 1.0e-12; cm[esc_m, 6] = 3.1e-17
+    cf[esc_f, 5] = -2.5e-11; cf[esc_f, 9] = 7.7e-16
+    im = np.repeat(np.arange(300, dtype=np.uint32), 3)                    # three neighbours per moving cell: duos of 2 + 1
+    jf = rng.integers(0, 700, len(im)).astype(np.uint32)
+    jf[:8] = [0, 13, 400, 699, 0, 13, 400, 699]
+    seg = [0, 450, len(im)]
+    poses = np.stack([synth.pose_to_se2(0.3, -0.2, 0.05), synth.pose_to_se2(-0.4, 0.1, -0.3)])
+    prob = gpu_ctx.problem_create(cm, cf, im, jf, seg)
+    n_duos, rec_bytes, n_ovf = prob.layout()
+    assert rec_bytes == 112 and n_duos == 600
+    touched = np.isin(im, esc_m) | np.isin(jf, esc_f)
+    want_ovf = len(np.unique((np.arange(len(im)) // 3 * 2 + (np.arange(len(im)) % 3) // 2)[touched]))
+    assert n_ovf == want_ovf and 0 < n_ovf < n_duos // 4
+    r, J = prob.eval_emit(poses)
+    loss = LOSSES[1]
+    out = capi.unpack_fused(prob.eval_fused(poses, loss))
+    for s in range(2):
+        a, b = seg[s], seg[s + 1]
+        ro, Jo = oracle.eval_pairs(0, cm, cf, im[a:b], jf[a:b], poses[s], 0)
+        assert np.max(np.abs(r[a:b] - ro) / ro) < TOL
+        assert rowwise(J[a:b], Jo) < 1e-8
+        fo = oracle.fused(0, cm, cf, im[a:b], jf[a:b], poses[s], loss_tuple(loss), True)
+        assert abs(out["cost"][s] - fo["cost"]) < TOL * abs(fo["cost"])
+        assert H.rel_err(out["H"][s], fo["H"]) < 1e-8 and H.rel_err(out["g"][s], fo["g"]) < 1e-8
+    assert gpu_ctx.take_bad_pairs() == 0
