@@ -27,6 +27,8 @@
 // (ticket counter), in tile order.  Launches chain with programmatic dependent launch (the schedule is fetched before the wait).
 #include <math.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace randt {
@@ -354,48 +356,61 @@ __device__ __forceinline__ double warp_max_nonneg(double v) {
 }
 
 // Write the 24-double record of one segment cooperatively: lane e < 24 fetches the basis total its entry depends on from the lane
-// that owns it (`mine` = the caller's own slot total; owner(slot) maps a slot to its lane), scales it, and the warp stores the
-// record with one coalesced 8-byte-per-lane store.  Slots: [NH upper triangle (i <= j, row-major)] [NB gradient] [cost] [sum dd].
-template <int VARIANT, bool WANT_JAC, typename OwnerFn>
-__device__ __forceinline__ void write_segment_out(double mine, double max_dd, const PoseConst& k, uint32_t n_pairs, double* __restrict__ out_base,
-                                                  uint32_t seg, uint32_t packed, int lane, OwnerFn owner) {
+// that owns it, scales it, and the warp stores the record with one coalesced 8-byte-per-lane store.
+// Slots: [NH upper triangle (i <= j, row-major)] [NB gradient] [cost] [sum dd].  What entry e needs does not depend on the tile, so
+// every lane derives it once per kernel (out_map) and keeps it packed in one register:
+//   bits 0..4 slot | 5..6 row factor | 7..8 column factor (0: 1, 1: ja, 2: jb, 3: 0) | 9..13 index in the packed layout | 14 stored in the
+//   packed layout | 15 entry scales a slot total (else: max r, n, or nothing)
+template <int VARIANT, bool WANT_JAC>
+__device__ __forceinline__ uint32_t out_map(int lane) {
   constexpr int NB = VarTraits<VARIANT>::NB;
   constexpr int NH = NB * (NB + 1) / 2;
   constexpr int NJ = WANT_JAC ? NH + NB : 0;
   const int e = lane;
   // entry e: H (e < 16: row r = e / 4, column c = e % 4), g (16..19), cost (20), max r (21), sum r^2 (22), n (23)
-  int slot = 0; double f = 0.0;
+  int slot = 0, fr = 3, fc = 0, scaled = 0;
   if (e < 20) {
     if (WANT_JAC) {
       const int r = e < 16 ? (e >> 2) : (e - 16), c = e & 3;
-      int tr, tc; double fr, fc;
+      int tr, tc, sr, sc;
       if (VARIANT == 0) {   // ambient (c, s, tx, ty) from the tangent basis (theta, x, y): d theta/d c = ja, d theta/d s = jb
         tr = r < 2 ? 0 : r - 1; tc = c < 2 ? 0 : c - 1;
-        fr = r == 0 ? k.ja : (r == 1 ? k.jb : 1.0); fc = c == 0 ? k.ja : (c == 1 ? k.jb : 1.0);
+        sr = r == 0 ? 1 : (r == 1 ? 2 : 0); sc = c == 0 ? 1 : (c == 1 ? 2 : 0);
       } else {
-        tr = r; tc = c; fr = r < NB ? 1.0 : 0.0; fc = c < NB ? 1.0 : 0.0;
+        tr = r; tc = c; sr = r < NB ? 0 : 3; sc = c < NB ? 0 : 3;
         if (tr >= NB) tr = 0;
         if (tc >= NB) tc = 0;
       }
       if (e < 16) {
         const int i = tr < tc ? tr : tc, j = tr < tc ? tc : tr;
         slot = i * NB - (i * (i - 1)) / 2 + (j - i);
-        f = fr * fc;
-      } else { slot = NH + tr; f = fr; }
+        fr = sr; fc = sc;
+      } else { slot = NH + tr; fr = sr; fc = 0; }
+      scaled = 1;
     }
-  } else if (e == 20) { slot = NJ; f = 1.0; }
-  else if (e == 22) { slot = NJ + 1; f = 1.0; }
-  const double v = __shfl_sync(kFull, mine, owner(slot));
-  double val = f * v;
+  } else if (e == 20) { slot = NJ; fr = 0; fc = 0; scaled = 1; }
+  else if (e == 22) { slot = NJ + 1; fr = 0; fc = 0; scaled = 1; }
+  // RANDT_PACKED_*: of H only row <= column (index in the row-major upper triangle), everything after H moves up by six
+  const int r = e >> 2, c = e & 3;
+  const int pk = e < 16 ? r * 4 - (r * (r - 1)) / 2 + (c - r) : e - 6;
+  const int in_packed = (e < RANDT_FUSED_STRIDE && (e >= 16 || c >= r)) ? 1 : 0;
+  return (uint32_t)slot | ((uint32_t)fr << 5) | ((uint32_t)fc << 7) | ((uint32_t)(pk & 31) << 9) | ((uint32_t)in_packed << 14) | ((uint32_t)scaled << 15);
+}
+__device__ __forceinline__ double out_factor(uint32_t sel, double ja, double jb) {
+  return sel == 0u ? 1.0 : (sel == 1u ? ja : (sel == 2u ? jb : 0.0));
+}
+// `mine` = the caller's own slot total; slot s is owned by lane s * owner_mul
+__device__ __forceinline__ void write_segment_out(double mine, double max_dd, double ja, double jb, uint32_t n_pairs, double* __restrict__ out_base,
+                                                  uint32_t seg, uint32_t packed, int lane, uint32_t omap, int owner_mul) {
+  const int e = lane;
+  const double v = __shfl_sync(kFull, mine, (int)(omap & 31u) * owner_mul);
+  double val = (omap & 0x8000u) ? v * (out_factor((omap >> 5) & 3u, ja, jb) * out_factor((omap >> 7) & 3u, ja, jb)) : 0.0;
   if (e == 21) val = max_dd > 0.0 ? max_dd * rsqrt_fast(max_dd) : 0.0;   // max raw residual
   if (e == 23) val = (double)n_pairs;
   if (!packed) {
     if (e < RANDT_FUSED_STRIDE) out_base[(size_t)seg * RANDT_FUSED_STRIDE + e] = val;
-  } else {
-    // RANDT_PACKED_*: of H only row <= column (index in the row-major upper triangle), everything after H moves up by six
-    const int r = e >> 2, c = e & 3;
-    const int pk = e < 16 ? r * 4 - (r * (r - 1)) / 2 + (c - r) : e - 6;
-    if (e < RANDT_FUSED_STRIDE && (e >= 16 || c >= r)) out_base[(size_t)seg * RANDT_PACKED_STRIDE + pk] = val;
+  } else if (omap & 0x4000u) {
+    out_base[(size_t)seg * RANDT_PACKED_STRIDE + ((omap >> 9) & 31u)] = val;
   }
 }
 
@@ -420,6 +435,7 @@ struct __align__(128) StageBufT {
   float4 rec[kAreaF4];     // the chunk's duo records (112 B each, see DuoRec in common.cuh), landed by ONE bulk copy
   double pose[2][4];       // [0]: pose of the tile at lane 0 (valid for the first chunk of a tile); [1]: pose of the tile that starts
   double mu[2];            //      inside a split chunk; mu likewise
+  uint32_t segoff[2][2];   // seg_off[seg], seg_off[seg + 1] of those tiles (pairs of the segment, entry 23 of its record)
   unsigned long long bar;  // mbarrier the bulk copy completes on
 };
 
@@ -450,6 +466,10 @@ __device__ __forceinline__ void load_duo(const float4* __restrict__ rec, int lan
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
   const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
@@ -526,7 +546,7 @@ struct WarpQueue {
   __device__ __forceinline__ bool live(uint32_t j) const { return (((j & 32u) ? act[1] : act[0]) >> (j & 31u)) & 1u; }
 };
 
-template <int NP, typename SB>
+template <int NP, bool WANT_SEGOFF, typename SB>
 __device__ __forceinline__ void stage_issue(const DeviceProblem& P, const WarpQueue& wq, uint32_t j, int lane, SB* sb,
                                             const double* __restrict__ poses, const double* __restrict__ mu_per_seg) {
   if (lane == 0 && wq.live(j)) {
@@ -544,6 +564,7 @@ __device__ __forceinline__ void stage_issue(const DeviceProblem& P, const WarpQu
           if (NP == 4) { cp_async16(&sb->pose[h][0], ps); cp_async16(&sb->pose[h][2], ps + 2); }
           else { cp_async8(&sb->pose[h][0], ps); cp_async8(&sb->pose[h][1], ps + 1); cp_async8(&sb->pose[h][2], ps + 2); }
           if (mu_per_seg) cp_async8(&sb->mu[h], mu_per_seg + sg);
+          if (WANT_SEGOFF) { cp_async4(&sb->segoff[h][0], P.seg_off + sg); cp_async4(&sb->segoff[h][1], P.seg_off + sg + 1); }
         }
       }
     }
@@ -555,14 +576,13 @@ __device__ __forceinline__ void stage_issue(const DeviceProblem& P, const WarpQu
 // segment's record — directly when the tile is its segment's only one, else as a partial that the last tile to finish folds.
 template <int VARIANT, bool WANT_JAC, int NS>
 __device__ __forceinline__ void finish_tile(const DeviceProblem& P, const double* vals, double max_dd, uint32_t n_bad, uint32_t seg, bool solo,
-                                            uint32_t part_slot, const PoseConst& kc, double* scratch, double* __restrict__ out,
-                                            unsigned long long* __restrict__ bad_counter, int lane) {
+                                            uint32_t part_slot, const PoseConst& kc, uint32_t n_pairs_seg, uint32_t omap, double* scratch,
+                                            double* __restrict__ out, unsigned long long* __restrict__ bad_counter, int lane) {
   const double mine = smem_reduce<NS>(vals, scratch, lane);   // slot s total: lanes 2s, 2s+1
   const double mx = warp_max_nonneg(max_dd);
   const uint32_t bad = __reduce_add_sync(kFull, n_bad);
-  const uint32_t n_pairs_seg = P.seg_off[seg + 1] - P.seg_off[seg];
   if (solo) {
-    write_segment_out<VARIANT, WANT_JAC>(mine, mx, kc, n_pairs_seg, out, seg, P.out_packed, lane, [](int sl) { return 2 * sl; });
+    write_segment_out(mine, mx, kc.ja, kc.jb, n_pairs_seg, out, seg, P.out_packed, lane, omap, 2);
     if (lane == 0 && bad) atomicAdd(bad_counter, (unsigned long long)bad);
   } else {
     // partial record of this tile: [NS sums][max dd][bad], one entry per lane
@@ -588,7 +608,7 @@ __device__ __forceinline__ void finish_tile(const DeviceProblem& P, const double
       }
       const double mx_all = __shfl_sync(kFull, v, NS);
       const double bad_all = __shfl_sync(kFull, v, NS + 1);
-      write_segment_out<VARIANT, WANT_JAC>(v, mx_all, kc, n_pairs_seg, out, seg, P.out_packed, lane, [](int sl) { return sl; });
+      write_segment_out(v, mx_all, kc.ja, kc.jb, n_pairs_seg, out, seg, P.out_packed, lane, omap, 1);
       if (lane == 0) {
         if (bad_all != 0.0) atomicAdd(bad_counter, (unsigned long long)bad_all);
         P.seg_counters[seg] = 0u;   // re-arm for the next launch
@@ -671,12 +691,13 @@ __global__ void __launch_bounds__(kK3Threads, kMinCtas) k3_fused_kernel(DevicePr
   constexpr int NJ = WANT_JAC ? NH + NB : 0;     // additive slots: H, g, then cost, sum dd
   constexpr int NS = NJ + 2;
   using StageBuf = StageBufT<NS * 34 * 8>;
-  __shared__ StageBuf stage_all[kWarpsPerCta][kStages];
+  extern __shared__ __align__(128) unsigned char k3_dyn_smem[];       // [kWarpsPerCta][kStages] stage buffers
   const int lane = threadIdx.x & 31;
   const int warp = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0);
   const uint32_t w = blockIdx.x * kWarpsPerCta + warp;
   if (w >= P.n_warps) return;
-  StageBuf* stage = stage_all[warp];
+  StageBuf* stage = reinterpret_cast<StageBuf*>(k3_dyn_smem) + warp * kStages;
+  const uint32_t omap = out_map<VARIANT, WANT_JAC>(lane);
   __shared__ ChunkDesc queue_all[kWarpsPerCta][64];
   WarpQueue wq;
   wq.q = queue_all[warp];
@@ -698,7 +719,7 @@ __global__ void __launch_bounds__(kK3Threads, kMinCtas) k3_fused_kernel(DevicePr
   wq.publish(P, v_first, 0u, lane);    // includes the warp barrier that publishes the mbarrier init
   // prologue: chunks 0 .. kStages-2 in flight (a warp owns at least one chunk; kStages - 1 <= 31 descriptors are in the queue)
 #pragma unroll
-  for (int s = 0; s < kStages - 1; ++s) stage_issue<NP>(P, wq, (uint32_t)s, lane, &stage[s], poses, mu_per_seg);
+  for (int s = 0; s < kStages - 1; ++s) stage_issue<NP, true>(P, wq, (uint32_t)s, lane, &stage[s], poses, mu_per_seg);
   uint32_t phase_bits = 0u;     // bit s: parity the next completion of stage s's barrier will have
 
   // Pose and loss constants of the tile(s) in flight live in shared memory (two slots per warp: a split chunk carries the tail of
@@ -706,6 +727,7 @@ __global__ void __launch_bounds__(kK3Threads, kMinCtas) k3_fused_kernel(DevicePr
   // ~26 fewer live registers per thread.
   __shared__ PoseConst kc_all[kWarpsPerCta][2];
   __shared__ LossConst lc_all[kWarpsPerCta][2];
+  __shared__ uint32_t np_all[kWarpsPerCta][2];     // pairs of the segment(s) in flight
   int ts = 0;
   double acc[NS]; double max_dd = 0.0; uint32_t n_bad = 0;
 #pragma unroll
@@ -721,7 +743,7 @@ __global__ void __launch_bounds__(kK3Threads, kMinCtas) k3_fused_kernel(DevicePr
     const uint32_t jn = jj + (uint32_t)(kStages - 1);
     if ((jn & 31u) == 0u) wq.refill(P, jn >> 5, lane);        // first chunk of a new block of 32 descriptors
     int islot = slot + kStages - 1; if (islot >= kStages) islot -= kStages;
-    stage_issue<NP>(P, wq, jn, lane, &stage[islot], poses, mu_per_seg);
+    stage_issue<NP, true>(P, wq, jn, lane, &stage[islot], poses, mu_per_seg);
     // ---- chunk j has landed ----
     cp_async_wait<kStages - 1>();
     __syncwarp();
@@ -736,6 +758,7 @@ __global__ void __launch_bounds__(kK3Threads, kMinCtas) k3_fused_kernel(DevicePr
         make_pose_const<VARIANT>(sb->pose[lane], k0);
         make_loss_const(lp, mu_per_seg ? sb->mu[lane] : lp.mu, l0);
         kc_all[warp][ts ^ lane] = k0; lc_all[warp][ts ^ lane] = l0;
+        np_all[warp][ts ^ lane] = sb->segoff[lane][1] - sb->segoff[lane][0];
       }
       __syncwarp();
     }
@@ -744,7 +767,7 @@ __global__ void __launch_bounds__(kK3Threads, kMinCtas) k3_fused_kernel(DevicePr
       const PoseConst& kc = kc_all[warp][ts]; const LossConst& lc = lc_all[warp][ts];
       if (live && (uint32_t)lane < n_here) accumulate_duo<VARIANT, LOSS, WANT_JAC, NS>(kc, lc, sb->rec, P.duo_overflow, lane, acc, max_dd, n_bad);
       if (live && (cm.meta & kChunkLast)) {
-        finish_tile<VARIANT, WANT_JAC, NS>(P, acc, max_dd, n_bad, cm.seg, (cm.meta & kChunkSolo) != 0u, cm.part, kc, scratch, out, bad_counter, lane);
+        finish_tile<VARIANT, WANT_JAC, NS>(P, acc, max_dd, n_bad, cm.seg, (cm.meta & kChunkSolo) != 0u, cm.part, kc, np_all[warp][ts], omap, scratch, out, bad_counter, lane);
 #pragma unroll
         for (int e = 0; e < NS; ++e) acc[e] = 0.0;
         max_dd = 0.0; n_bad = 0;
@@ -762,12 +785,12 @@ __global__ void __launch_bounds__(kK3Threads, kMinCtas) k3_fused_kernel(DevicePr
 #pragma unroll
       for (int e = 0; e < NS; ++e) vals[e] = acc[e] + (mine_new ? 0.0 : c[e]);
       finish_tile<VARIANT, WANT_JAC, NS>(P, vals, fmax(max_dd, mine_new ? 0.0 : mc), n_bad + (mine_new ? 0u : cb), cm.seg, true, 0u, kc_all[warp][ts],
-                                         scratch, out, bad_counter, lane);
+                                         np_all[warp][ts], omap, scratch, out, bad_counter, lane);
 #pragma unroll
       for (int e = 0; e < NS; ++e) acc[e] = mine_new ? c[e] : 0.0;
       max_dd = mine_new ? mc : 0.0; n_bad = mine_new ? cb : 0u;
       if (cm.meta & kChunkNewLast) {      // the second tile is shorter than the rest of the chunk: it ends here too
-        finish_tile<VARIANT, WANT_JAC, NS>(P, acc, max_dd, n_bad, cm.part, true, 0u, kc_all[warp][ts ^ 1], scratch, out, bad_counter, lane);
+        finish_tile<VARIANT, WANT_JAC, NS>(P, acc, max_dd, n_bad, cm.part, true, 0u, kc_all[warp][ts ^ 1], np_all[warp][ts ^ 1], omap, scratch, out, bad_counter, lane);
 #pragma unroll
         for (int e = 0; e < NS; ++e) acc[e] = 0.0;
         max_dd = 0.0; n_bad = 0;
@@ -813,12 +836,12 @@ __global__ void __launch_bounds__(kK3Threads, kMinCtas) k3_emit_kernel(DevicePro
                                                                       double* __restrict__ J_out, unsigned long long* __restrict__ bad_counter) {
   constexpr int NP = VarTraits<VARIANT>::NP;
   using StageBuf = StageBufT<0>;
-  __shared__ StageBuf stage_all[kWarpsPerCta][kStages];
+  extern __shared__ __align__(128) unsigned char k3_dyn_smem[];
   const int lane = threadIdx.x & 31;
   const int warp = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0);
   const uint32_t w = blockIdx.x * kWarpsPerCta + warp;
   if (w >= P.n_warps) return;
-  StageBuf* stage = stage_all[warp];
+  StageBuf* stage = reinterpret_cast<StageBuf*>(k3_dyn_smem) + warp * kStages;
   __shared__ ChunkDesc queue_all[kWarpsPerCta][64];
   WarpQueue wq;
   wq.q = queue_all[warp];
@@ -832,7 +855,7 @@ __global__ void __launch_bounds__(kK3Threads, kMinCtas) k3_emit_kernel(DevicePro
   }
   wq.refill(P, 0u, lane);
 #pragma unroll
-  for (int s = 0; s < kStages - 1; ++s) stage_issue<NP>(P, wq, (uint32_t)s, lane, &stage[s], poses, nullptr);
+  for (int s = 0; s < kStages - 1; ++s) stage_issue<NP, false>(P, wq, (uint32_t)s, lane, &stage[s], poses, nullptr);
   PoseConst kc;
   uint32_t n_bad = 0, phase_bits = 0u;
   int slot = 0;
@@ -845,7 +868,7 @@ __global__ void __launch_bounds__(kK3Threads, kMinCtas) k3_emit_kernel(DevicePro
     const uint32_t jn = jj + (uint32_t)(kStages - 1);
     if ((jn & 31u) == 0u) wq.refill(P, jn >> 5, lane);
     int islot = slot + kStages - 1; if (islot >= kStages) islot -= kStages;
-    stage_issue<NP>(P, wq, jn, lane, &stage[islot], poses, nullptr);
+    stage_issue<NP, false>(P, wq, jn, lane, &stage[islot], poses, nullptr);
     cp_async_wait<kStages - 1>();
     __syncwarp();
     StageBuf* sb = &stage[slot];
@@ -974,18 +997,42 @@ int loss_code(const LossParams& lp) {
 
 inline int stream_grid(uint32_t n_warps) { return (int)((n_warps + kWarpsPerCta - 1) / kWarpsPerCta); }
 
-template <int VARIANT, int LOSS>
-cudaError_t launch_fused_vl(const DeviceProblem& p, const double* d_poses, const LossParams& lp, const double* d_mu, bool want_jac,
-                            double* d_out, unsigned long long* bad, cudaStream_t s) {
+// the stage ring lives in dynamic shared memory (three stages of four warps exceed the 48 KB static limit)
+// (the attribute is per device: `done` remembers, per kernel instantiation, on which devices it has been set)
+template <typename K>
+cudaError_t allow_smem(K kernel, size_t bytes, std::atomic<unsigned long long>& done) {
+  if (bytes <= 32u * 1024u) return cudaSuccess;      // static + dynamic stay below the 48 KB that need no opt-in
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+  return e;
+}
+template <int VARIANT, int LOSS, bool WANT_JAC>
+cudaError_t launch_fused_vlj(const DeviceProblem& p, const double* d_poses, const LossParams& lp, const double* d_mu, double* d_out,
+                             unsigned long long* bad, cudaStream_t s) {
+  constexpr int NB = VarTraits<VARIANT>::NB;
+  constexpr int NS = (WANT_JAC ? NB * (NB + 1) / 2 + NB : 0) + 2;
+  constexpr size_t smem = (size_t)kWarpsPerCta * kStages * sizeof(StageBufT<NS * 34 * 8>);
+  static std::atomic<unsigned long long> smem_done{0ull};
+  if (cudaError_t rc = allow_smem(k3_fused_kernel<VARIANT, LOSS, WANT_JAC>, smem, smem_done)) return rc;
   const int grid = stream_grid(p.n_warps);
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kK3Threads); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kK3Threads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  if (want_jac) return cudaLaunchKernelEx(&cfg, k3_fused_kernel<VARIANT, LOSS, true>, p, d_poses, lp, d_mu, d_out, bad);
-  return cudaLaunchKernelEx(&cfg, k3_fused_kernel<VARIANT, LOSS, false>, p, d_poses, lp, d_mu, d_out, bad);
+  return cudaLaunchKernelEx(&cfg, k3_fused_kernel<VARIANT, LOSS, WANT_JAC>, p, d_poses, lp, d_mu, d_out, bad);
+}
+template <int VARIANT, int LOSS>
+cudaError_t launch_fused_vl(const DeviceProblem& p, const double* d_poses, const LossParams& lp, const double* d_mu, bool want_jac,
+                            double* d_out, unsigned long long* bad, cudaStream_t s) {
+  if (want_jac) return launch_fused_vlj<VARIANT, LOSS, true>(p, d_poses, lp, d_mu, d_out, bad, s);
+  return launch_fused_vlj<VARIANT, LOSS, false>(p, d_poses, lp, d_mu, d_out, bad, s);
 }
 template <int VARIANT>
 cudaError_t launch_fused_v(const DeviceProblem& p, const double* d_poses, const LossParams& lp, const double* d_mu, bool want_jac,
@@ -1062,9 +1109,12 @@ cudaError_t launch_eval_emit(const DeviceProblem& p, int variant, const double* 
                              unsigned long long* d_bad, cudaStream_t s, int* n_launches) {
   if (p.n_chunks == 0) return cudaSuccess;
   const int grid = stream_grid(p.n_warps);
+  constexpr size_t smem = (size_t)kWarpsPerCta * kStages * sizeof(StageBufT<0>);
 #define RANDT_EMIT(V)                                                                                              \
-  if (d_J) k3_emit_kernel<V, true><<<grid, kK3Threads, 0, s>>>(p, d_poses, d_r, d_J, d_bad);             \
-  else     k3_emit_kernel<V, false><<<grid, kK3Threads, 0, s>>>(p, d_poses, d_r, d_J, d_bad);
+  if (d_J) { static std::atomic<unsigned long long> dn_{0ull}; if (cudaError_t rc_ = allow_smem(k3_emit_kernel<V, true>, smem, dn_)) return rc_;   \
+             k3_emit_kernel<V, true><<<grid, kK3Threads, smem, s>>>(p, d_poses, d_r, d_J, d_bad); }             \
+  else     { static std::atomic<unsigned long long> dn_{0ull}; if (cudaError_t rc_ = allow_smem(k3_emit_kernel<V, false>, smem, dn_)) return rc_;  \
+             k3_emit_kernel<V, false><<<grid, kK3Threads, smem, s>>>(p, d_poses, d_r, d_J, d_bad); }
   switch (variant) {
     case 0: RANDT_EMIT(0) break;
     case 1: RANDT_EMIT(1) break;

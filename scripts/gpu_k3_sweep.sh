@@ -1,9 +1,12 @@
-# rebuild K3 with different pipeline depths / occupancy targets on the GPU box and bench each (tuning aid)
+# K3 tuning aid: rebuild with other pipeline depths / CTAs per SM on the box and bench each (the default build runs the parity tests first)
+set -x
 mkdir -p gpurun_out
-: > gpurun_out/k3_sweep.txt
-for cfg in ${K3_CFGS:-"2 4 128" "3 5 96"}; do
-  set -- $cfg
-  RANDT_NVCC_FLAGS="-DRANDT_K3_STAGES=$1 -DRANDT_K3_MIN_CTAS=$2 -DRANDT_K3_THREADS=${3:-128}" python -m randt_slam_b200.build --force > gpurun_out/k3_sweep_build.log 2>&1 || tail -5 gpurun_out/k3_sweep_build.log
-  v=$(timeout 300 python bench.py --steps 300 --warmup 10 --no-cpu-baseline --reg-steps 0 --pre-scans 0 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value']/1e9, d['ms_per_step'], d['roofline']['frac'])")
-  echo "stages=$1 min_ctas=$2 threads=${3:-128} : Gpairs/s ms frac = $v" | tee -a gpurun_out/k3_sweep.txt
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+for cfg in "${@:-2:4}"; do
+  st=${cfg%%:*}; ct=${cfg##*:}
+  RANDT_NVCC_FLAGS="-DRANDT_K3_STAGES=$st -DRANDT_K3_MIN_CTAS=$ct" python -c "from randt_slam_b200 import build; build.build_all(force=True)" || continue
+  timeout 300 python -m pytest tests/test_k3_gpu.py tests/test_fullsize_gpu.py -m gpu -x -q 2>&1 | tail -2
+  timeout 300 python bench.py --no-cpu-baseline --reg-steps 0 --pre-scans 0 > gpurun_out/sweep_${st}_${ct}.json 2> gpurun_out/sweep_${st}_${ct}.err
+  python -c "
+import json; d=json.load(open('gpurun_out/sweep_${st}_${ct}.json')); print('SWEEP stages=$st ctas=$ct VALUE %.2f G pairs/s  %.2f us  frac %.3f  e2e %.2f' % (d['value']/1e9, d['ms_per_step']*1e3, d['roofline']['frac'], d['e2e']['value']/1e9))"
 done
