@@ -264,7 +264,10 @@ typedef struct randt_solver_options {
   double gnc_loss_scale;                      /* ndt_matcher/loss_function_scale (the scale in mu0, ndt_matcher.cpp:386,473) */
   double gnc_divisor;                         /* ndt_matcher/gnc_control_parameter_divisor */
   int32_t gnc_max_steps;                      /* gnc_steps / loop_closure gnc steps */
-  int32_t poll_interval;                      /* LM iterations between host polls of the active-segment counter (0: default) */
+  int32_t poll_interval;                      /* >= 0: registrations of up to 1024 pairs are solved start to finish by the persistent kernel (one
+                                                 warp each, one launch for the batch); longer ones step through one evaluation + one
+                                                 solver launch per LM iteration, the host polling the active count every poll_interval
+                                                 iterations (0: default 4).  < 0: the stepwise path for every registration (diagnostic). */
 } randt_solver_options;
 RANDT_API void randt_solver_options_default(randt_solver_options* o);
 

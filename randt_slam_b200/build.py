@@ -22,6 +22,7 @@ COMMON = EXTRA + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xco
 UNITS = {
     "k3_pair_eval.cu": [],
     "k4_lm_step.cu": [],
+    "k7_solve.cu": [],
     "k2_associate.cu": ["-fmad=false"],
     "k1_voxelize.cu": ["-fmad=false"],
     "k5_cs_divergence.cu": ["-fmad=false"],
@@ -40,7 +41,7 @@ def _newer(target, deps):
 def build_all(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "nvcc")
     os.makedirs(OBJ, exist_ok=True)
-    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "schedule.hpp"), os.path.join(HERE, "..", "include", "randt_gpu.h"),
+    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "schedule.hpp"), os.path.join(CSRC, "k3_device.cuh"), os.path.join(CSRC, "k4_device.cuh"), os.path.join(HERE, "..", "include", "randt_gpu.h"),
                os.path.abspath(__file__)]
     jobs = []
     for src, extra in UNITS.items():

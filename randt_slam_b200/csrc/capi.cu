@@ -97,6 +97,8 @@ struct randt_problem {
   uint32_t *warp_off = nullptr, *warp_off_full = nullptr; uint32_t n_warps = 0;
   uint32_t* seg_first_tile = nullptr;
   uint32_t* seg_off = nullptr;
+  uint32_t *seg_duo_off = nullptr, *rec_of_tile = nullptr; uint32_t tile_duos = 0;   // what the persistent solver walks
+  uint32_t *solve_items = nullptr, *solve_counter = nullptr; uint32_t n_solve_items = 0; bool solve_all = true;   // segments short enough for it
   double* partials = nullptr;
   uint32_t* seg_counters = nullptr;
   std::vector<uint32_t> h_seg_off;
@@ -161,7 +163,7 @@ void free_map(randt_map* m) {
 }
 void free_problem(randt_problem* p) {
   if (!p) return;
-  dev_free(p->cells_m); dev_free(p->cells_f); dev_free(p->pairs); dev_free(p->duos); dev_free(p->duo_recs); dev_free(p->duo_p0); dev_free(p->duo_overflow); dev_free(p->chunks); dev_free(p->warp_off); dev_free(p->chunks_full); dev_free(p->warp_off_full); dev_free(p->seg_first_tile); dev_free(p->seg_off);
+  dev_free(p->cells_m); dev_free(p->cells_f); dev_free(p->pairs); dev_free(p->duos); dev_free(p->duo_recs); dev_free(p->duo_p0); dev_free(p->duo_overflow); dev_free(p->chunks); dev_free(p->warp_off); dev_free(p->chunks_full); dev_free(p->warp_off_full); dev_free(p->seg_first_tile); dev_free(p->seg_off); dev_free(p->seg_duo_off); dev_free(p->rec_of_tile); dev_free(p->solve_items); dev_free(p->solve_counter);
   dev_free(p->partials); dev_free(p->seg_counters); dev_free(p->d_poses); dev_free(p->d_out); dev_free(p->d_mu); dev_free(p->d_r);
   dev_free(p->d_J); dev_free(p->d_sweep);
   dev_free(p->lm_state); dev_free(p->lm_eval_pose); dev_free(p->lm_mu); dev_free(p->lm_rec); dev_free(p->lm_poses); dev_free(p->lm_result);
@@ -237,6 +239,18 @@ int finish_problem(randt_ctx* ctx, randt_problem* p) {
   CK(dev_alloc(&p->d_poses, (size_t)p->S * 4));
   CK(dev_alloc(&p->d_out, (size_t)p->S * RANDT_FUSED_STRIDE));
   CK(dev_alloc(&p->d_mu, p->S));
+  // persistent solver (K7): every tile's record offset by tile id, the duo offsets, and the list of segments one warp can take
+  p->tile_duos = sch.tile_duos;
+  std::vector<uint32_t> items;
+  for (uint32_t s = 0; s < p->S; ++s) if (p->h_duo_off[s + 1] - p->h_duo_off[s] <= kSolveMaxDuos) items.push_back(s);
+  p->n_solve_items = (uint32_t)items.size(); p->solve_all = items.size() == p->S;
+  CK(dev_alloc(&p->seg_duo_off, p->h_duo_off.size())); CK(dev_alloc(&p->rec_of_tile, sch.rec_of_tile.size())); CK(dev_alloc(&p->solve_counter, 1));
+  CK(cudaMemcpyAsync(p->seg_duo_off, p->h_duo_off.data(), p->h_duo_off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  if (!sch.rec_of_tile.empty()) CK(cudaMemcpyAsync(p->rec_of_tile, sch.rec_of_tile.data(), sch.rec_of_tile.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  if (!p->solve_all) {
+    CK(dev_alloc(&p->solve_items, items.size()));
+    if (!items.empty()) CK(cudaMemcpyAsync(p->solve_items, items.data(), items.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  }
   CK(cudaMemcpyAsync(p->seg_first_tile, first.data(), first.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(p->seg_off, p->h_seg_off.data(), p->h_seg_off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemsetAsync(p->seg_counters, 0, std::max<size_t>(1, p->S) * sizeof(uint32_t), ctx->stream));
@@ -1043,6 +1057,19 @@ int randt_register_batch_dev(randt_ctx* ctx, const randt_problem* cp, int varian
   const uint32_t S = p->S;
   const int np = np_of(variant);
   if (S == 0) return RANDT_OK;
+  int nl = 0;
+  // Registrations one warp can take (<= kSolveMaxDuos duos) are solved start to finish by the persistent kernel K7 in ONE launch; the
+  // rest (and everything, when poll_interval < 0) goes through the stepwise loop: one K3 fused launch + one K4 launch per LM iteration.
+  const bool stepwise_only = opt->poll_interval < 0;
+  const uint32_t n_k7 = stepwise_only ? 0u : p->n_solve_items;
+  if (n_k7) {
+    SolveLayout L;
+    L.seg_duo_off = p->seg_duo_off; L.tile_rec_begin = p->rec_of_tile; L.tile_duos = p->tile_duos;
+    L.items = p->solve_all ? nullptr : p->solve_items; L.n_items = n_k7; L.next_item = p->solve_counter;
+    CK(cudaMemsetAsync(p->solve_counter, 0, sizeof(uint32_t), ctx->stream));
+    CK(launch_solve_persistent(view(p), L, variant, opt->use_manifold, lp, *opt, d_poses, d_poses, d_result, ctx->d_bad, ctx->stream, &nl));
+    if (n_k7 == S) { ctx->launches += nl; return RANDT_OK; }
+  }
   if (!p->lm_state) {
     CK(dev_alloc(&p->lm_state, S)); CK(dev_alloc(&p->lm_eval_pose, (size_t)S * 4)); CK(dev_alloc(&p->lm_mu, S));
     CK(dev_alloc(&p->lm_rec, (size_t)S * RANDT_FUSED_STRIDE)); CK(dev_alloc(&p->lm_active, S)); CK(dev_alloc(&p->lm_n_active, 1));
@@ -1054,8 +1081,18 @@ int randt_register_batch_dev(randt_ctx* ctx, const randt_problem* cp, int varian
     CK(cudaHostAlloc(reinterpret_cast<void**>(&sr.h_n_active), 2 * sizeof(uint32_t), cudaHostAllocDefault));
     CK(cudaEventCreateWithFlags(&sr.ev[0], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&sr.ev[1], cudaEventDisableTiming));
   }
-  int nl = 0;
   CK(launch_lm_init(S, np, d_poses, p->lm_state, p->lm_eval_pose, p->lm_mu, p->lm_active, p->lm_rec, p->lm_n_active, ctx->stream, &nl));
+  uint32_t planned_for = S;     // active segments when the schedule in use was made
+  if (n_k7) {
+    // only the long registrations are left: everything K7 solved starts out inactive
+    std::vector<uint32_t> mask(S, 0u);
+    uint32_t n_left = 0;
+    for (uint32_t s = 0; s < S; ++s) if (p->h_duo_off[s + 1] - p->h_duo_off[s] > kSolveMaxDuos) { mask[s] = 1u; ++n_left; }
+    CK(cudaMemcpyAsync(p->lm_active, mask.data(), (size_t)S * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(p->lm_n_active, &n_left, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    planned_for = S;
+  }
   DeviceProblem v = view(p);
   v.seg_active = p->lm_active;
   const int poll = opt->poll_interval > 0 ? opt->poll_interval : 4;
@@ -1065,7 +1102,6 @@ int randt_register_batch_dev(randt_ctx* ctx, const randt_problem* cp, int varian
   // GPU never waits for the host (the price: up to one group of no-op launches after the last segment has finished).
   bool done = false;
   const auto t_solver0 = std::chrono::steady_clock::now();
-  uint32_t planned_for = S;     // active segments when the schedule in use was made
   const long long n_groups = (cap + poll - 1) / poll;
   for (long long g = 0; g < n_groups && !done; ++g) {
     for (int i = 0; i < poll; ++i) {

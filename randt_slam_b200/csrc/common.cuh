@@ -162,6 +162,20 @@ cudaError_t launch_lm_step(uint32_t S, int np, int use_manifold, const randt_sol
 cudaError_t launch_replan(const ChunkDesc* chunks, uint32_t n_chunks, const uint32_t* active, uint32_t n_warps, uint32_t* flags, uint32_t* scan,
                           uint32_t* block_sums, ChunkDesc* kept, uint32_t* warp_off, cudaStream_t s, int* n_launches);
 
+// k7_solve.cu — persistent solver: one warp per registration, the whole GNC + LM solve in one launch
+constexpr uint32_t kSolveMaxDuos = 512;   // registrations up to this many duos (1024 pairs) are solved by one warp
+struct SolveLayout {
+  const uint32_t* seg_duo_off;     // [S+1] duo offsets per segment
+  const uint32_t* tile_rec_begin;  // [n_tiles] record offset of every tile, tiles in segment order
+  uint32_t tile_duos;              // duos per full tile (multiple of 32)
+  const uint32_t* items;           // [n_items] segments to solve, or NULL = segments 0 .. n_items-1
+  uint32_t n_items;
+  uint32_t* next_item;             // device counter, zero at launch
+};
+cudaError_t launch_solve_persistent(const DeviceProblem& p, const SolveLayout& L, int variant, int use_manifold, const LossParams& lp,
+                                    const randt_solver_options& o, const double* d_poses0, double* d_poses_out, double* d_result,
+                                    unsigned long long* d_bad, cudaStream_t s, int* n_launches);
+
 // k5_cs_divergence.cu
 cudaError_t launch_cs_divergence(const float4* cells_f, const uint32_t* off_f, const float4* cells_m, const uint32_t* off_m, uint32_t n_maps,
                                  double* d_partials, uint32_t* d_tickets, double* d_out, cudaStream_t s, int* n_launches);

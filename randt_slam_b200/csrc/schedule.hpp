@@ -31,10 +31,12 @@ struct Schedule {
   std::vector<Tile> tiles;                       // segment after segment
   std::vector<uint32_t> first;                   // [S+1] first tile of every segment
   uint32_t n_warps = 0;
+  uint32_t tile_duos = 0;                        // duos per tile (a multiple of 32; a segment's last tile may be shorter)
   std::vector<ChunkDesc> planA, planB;           // plan A: split chunks allowed (full evaluation); plan B: one tile per chunk (solver, EMIT)
   std::vector<uint32_t> woffA, woffB;            // [n_warps+1] chunk ranges of every warp in the two plans
   std::vector<uint32_t> tile_rec_begin;          // [n_tiles+1] record offsets of the tiles in schedule order (warp after warp)
   std::vector<uint32_t> tile_duo_begin;          // [n_tiles]   where each of those tiles starts in the segment-ordered duo list
+  std::vector<uint32_t> rec_of_tile;             // [n_tiles]   record offset of tile t, tiles in SEGMENT order (what the persistent solver walks)
 };
 
 // duo_off: [S+1] duo offsets per segment; max_warps: resident warps of the persistent grid (kK3MaxWarps)
@@ -48,6 +50,7 @@ inline void build_schedule(const uint32_t* duo_off, uint32_t S, uint32_t max_war
   // small problems: shorter tiles so that the pairs still spread over the SMs (each extra tile costs one partial record).
   uint32_t tile_duos = (n_duos / (uint32_t)(kSmCount * 4) + 31u) / 32u * 32u;
   tile_duos = std::max<uint32_t>(kMinTileDuos, std::min<uint32_t>(tile_duos, kTileDuos));
+  out.tile_duos = tile_duos;
   for (uint32_t s = 0; s < S; ++s) {
     first[s] = (uint32_t)tiles.size();
     uint32_t part = 0;
@@ -99,6 +102,7 @@ inline void build_schedule(const uint32_t* duo_off, uint32_t S, uint32_t max_war
   //   plan B (solver with active flags, EMIT): every chunk belongs to one tile.
   std::vector<uint32_t>& tile_rec_begin = out.tile_rec_begin; std::vector<uint32_t>& tile_duo_begin = out.tile_duo_begin;
   tile_rec_begin.clear(); tile_duo_begin.clear();
+  out.rec_of_tile.assign(tiles.size(), 0u);
   tile_rec_begin.reserve(tiles.size() + 1); tile_duo_begin.reserve(tiles.size());
   std::vector<ChunkDesc>& planA = out.planA; std::vector<ChunkDesc>& planB = out.planB;
   planA.clear(); planB.clear();
@@ -114,6 +118,7 @@ inline void build_schedule(const uint32_t* duo_off, uint32_t S, uint32_t max_war
       const bool solo = first[tl.seg + 1] - first[tl.seg] == 1u;
       const uint32_t len = tl.end - tl.begin, rb = rec;
       tile_rec_begin.push_back(rb); tile_duo_begin.push_back(tl.begin);
+      out.rec_of_tile[t] = rb;
       rec += len;
       const uint32_t part = first[tl.seg] + tl.part;
       for (uint32_t o = 0; o < len; o += 32u) {
