@@ -32,11 +32,11 @@ sys.path.insert(0, ROOT)
 
 from randt_slam_b200 import params as P  # noqa: E402
 from randt_slam_b200 import synth  # noqa: E402
+from randt_slam_b200 import workloads as W  # noqa: E402
+from randt_slam_b200.workloads import POOL, SUBMAP_SCANS, pool_scans  # noqa: E402
 
 METRIC = "ndt_cell_pair_residual_jacobian_evals_per_s"
 UNIT = "pairs/s"
-POOL = 16                 # distinct synthetic scenes
-SUBMAP_SCANS = 10
 DEFAULT_PROBLEMS = 16384  # per GPU; ~22 KB of tables each -> ~360 MB resident, > 126 MB L2
 
 
@@ -46,21 +46,6 @@ def peaks():
             return json.load(f), "measured"
     except OSError:
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
-
-
-def pool_scans(p, seed0):
-    """POOL scenes x (SUBMAP_SCANS keyframe scans + 1 moving scan), numpy only."""
-    kw = synth.preset_scan_kwargs(p)
-    sub, mov, sub_pose, true_pose = [], [], [], []
-    for j in range(POOL):
-        sc = synth.scene_for(p, seed0 + j)
-        rng = np.random.default_rng(seed0 * 1000 + j)
-        for i in range(SUBMAP_SCANS):
-            pose = (0.5 * i, 0.0, 0.0)
-            sub.append(synth.make_scan(sc, pose, p, seed0 * 100 + j * 20 + i, **kw)); sub_pose.append(pose)
-        tp = (2.5 + rng.uniform(-1, 1), rng.uniform(-1, 1), rng.uniform(-0.05, 0.05))
-        mov.append(synth.make_scan(sc, tp, p, seed0 * 100 + j * 20 + 19, **kw)); true_pose.append(tp)
-    return sub, sub_pose, mov, true_pose
 
 
 def build_problem(ctx, capi, p, n_problems, seed0):
@@ -212,10 +197,10 @@ def run_reference(args, p, loss):
     from randt_slam_b200 import capi
     # the workload is built with the product kernels when a GPU is present (identical inputs to the product arm);
     # otherwise (CPU-only container) with the oracle's own voxeliser.  Either way only the oracle is timed.
-    n_sample = args.ref_problems
-    host, poses = build_host_workload(p, n_sample, args.seed)
+    n_sample = min(args.ref_problems, args.problems)
+    host, poses = build_host_workload(p, args.problems, args.seed)      # the GPU arm's problem set (same seeds, same construction rules)
     threads = O.hw_threads()
-    P_ = int(host["seg"][n_sample])
+    P_ = int(host["seg"][n_sample]); P_all = int(host["seg"][args.problems])
     for _ in range(args.warmup):
         cpu_fused(host, poses, loss, n_sample, threads, 1)
     t0 = time.perf_counter()
@@ -228,9 +213,11 @@ def run_reference(args, p, loss):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": workload_name(p), "problems_per_step": n_sample, "pairs_per_step": P_, "preset": p.name},
+        "config": {"workload": workload_name(p), "problems_per_gpu": args.problems, "pairs_per_gpu": P_all, "k": p.n_results_nn_lookup,
+                   "mode": "fused (r, J, Barron corrector, per-pose J^T J / J^T r)", "preset": p.name,
+                   "step": "bounded sample: the first %d problems (%d pairs) of the workload per step" % (n_sample, P_)},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": "%d problems (%d pairs) per step, Jet<4> autodiff + Barron corrector + J^T J accumulation" % (n_sample, P_)},
+                         "sample": "first %d of %d problems (%d pairs) per step, Jet<4> autodiff + Barron corrector + J^T J accumulation" % (n_sample, args.problems, P_)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "registrations": {"value": regN, "unit": "registrations/s", "single_thread_value": reg1, "cores": threads, "mean_iterations": reg_it,
                           "what": "Matcher::estimateLoopConstraint restated (GNC + ceres-LM, Jet<4> evaluation), oxford loop-closure parameters"},
@@ -274,6 +261,108 @@ def build_host_workload(p, n_problems, seed0):
     return host, poses
 
 
+def run_configs(args, ctx, capi, stream, rank, world, local, barrier):
+    """Sub-records for the BASELINE configs that are not the headline workload: c0 (plumbing case), c2 (2 k x 8 k shape), c3 (the literal
+    256-registration batch, sharded over the ranks: strong scaling) and c4 (sequence replay, rank 0; a single drive does not shard)."""
+    import hashlib
+    import torch
+    import torch.distributed as dist
+    from randt_slam_b200 import shard
+    dev = "cuda:%d" % local
+    out = {}
+    pk, _ = peaks()
+    oracle = None
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import oracle_py as oracle
+    # ---- c0 ----
+    if rank == 0:
+        out["c0"] = W.run_c0(ctx, capi, oracle)
+    # ---- c2: configs[2] shape with the reference's SE(2) + intensity functor and kNN pair list ----
+    if args.c2_problems > 0:
+        prob, poses, host = W.build_c2(ctx, capi, args.c2_problems)
+        host["F"].close(); host["M"].close()
+        S, Pn = prob.n_segments, prob.n_pairs
+        loss = W.c2_loss(capi)
+        d_poses = torch.from_numpy(poses).to(dev); d_out = torch.zeros((S, capi.FUSED_STRIDE), dtype=torch.float64, device=dev)
+        for _ in range(5):
+            prob.eval_fused_dev(d_poses.data_ptr(), d_out.data_ptr(), loss)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_rep = 50
+        e0.record(stream)
+        for _ in range(n_rep):
+            prob.eval_fused_dev(d_poses.data_ptr(), d_out.data_ptr(), loss)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1) / n_rep
+        stc = dict(n_m=int(prob.n_m), n_f_referenced=int(len(np.unique(host["pf"]))), pairs=int(Pn), segments=int(S))
+        alg = algorithmic_bytes(stc)
+        rec = {"workload": "configs[2] shape: %d problems of 2 k moving x 8 k fixed cells, 0.5 m, k = 4, outdoor loss (alpha = -1), reference SE(2) + intensity "
+                           "functor, kNN pair list (reference semantics)" % S,
+               "se3_imu": "not run: the reference is strictly SE(2) (SURVEY fact 2); there is no reference implementation or oracle for an SE(3)/IMU variant",
+               "pairs_per_gpu": int(Pn), "pairs_per_problem": Pn / S, "ms_per_step": ms, "pairs_per_s_per_gpu": Pn / (ms * 1e-3),
+               "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                            "frac": alg / (ms * 1e-3) / 1e9 / pk["hbm_gbs"], "algorithmic_bytes_per_launch": alg, "bytes_per_pair": alg / Pn},
+               "finite": bool(torch.isfinite(d_out).all().item())}
+        if oracle is not None:      # parity spot check: first problem against the oracle
+            a, b = int(host["seg"][0]), int(host["seg"][1])
+            fo = oracle.fused(0, host["cells_m"], host["cells_f"], host["pm"][a:b], host["pf"][a:b], poses[0], (loss.kind, loss.scale, loss.alpha, loss.mu, loss.weight), True)
+            g = capi.unpack_fused(d_out[0].cpu().numpy())
+            rec["gpu_vs_oracle_max_rel_err_first_problem"] = float(max(np.max(np.abs(g["H"] - fo["H"])) / np.max(np.abs(fo["H"])), abs(g["cost"] - fo["cost"]) / abs(fo["cost"])))
+        prob.close()
+        del d_poses, d_out
+        out["c2"] = rec
+    # ---- c3: the literal batch, strong scaling ----
+    if args.c3_batch > 0:
+        batch = W.literal_batch(P.OXFORD, n=args.c3_batch, seed=40, scenes=16)
+        begin, end = shard.partition(batch["n"], world)[rank]
+        W.solve_literal_block(ctx, capi, batch, begin, end)                 # warm-up (allocations, first launches)
+        barrier()
+        rows, dt = W.solve_literal_block(ctx, capi, batch, begin, end)      # dt: this rank's randt_register_batch call (host poses in, poses + records out)
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        table = shard.gather_results(rows, begin, batch["n"], rank, world, device=torch.device("cuda", local))    # the job's only exchange (NCCL all_gather)
+        if rank == 0:
+            makespan = float(t[0])
+            th = np.arctan2(table[:, 1], table[:, 0])
+            ok = (np.hypot(table[:, 2] - batch["truth"][:, 0], table[:, 3] - batch["truth"][:, 1]) < 0.3) & (np.abs(th - batch["truth"][:, 2]) < 0.02)
+            out["c3"] = {"workload": "configs[3]: %d independent keyframe-pair registrations (estimateLoopConstraint semantics, oxford loop-closure parameters), "
+                                     "contiguous blocks over %d rank(s), one all_gather of the result rows" % (batch["n"], world),
+                         "scaling": "strong", "registrations": batch["n"], "n_gpus": world, "makespan_ms": makespan * 1e3,
+                         "registrations_per_s": batch["n"] / makespan, "mean_iterations": float(table[:, 5].mean()), "max_iterations": float(table[:, 5].max()),
+                         "failed": int((table[:, 6] != 0).sum()), "within_0.3m_0.02rad_of_truth": int(ok.sum()),
+                         "table_sha256": hashlib.sha256(np.ascontiguousarray(table[:, :7]).tobytes()).hexdigest(),
+                         "what": "makespan = max over ranks of the wall time of one randt_register_batch call on the rank's block (host initial guesses in, poses + result "
+                                 "records out); table_sha256 covers [cos, sin, tx, ty, score, iterations, status] of all registrations and must not depend on n_gpus"}
+    # ---- c4: sequence replay (a single drive has a scan -> scan dependency: replicas only) ----
+    if args.replay_scans > 1 and rank == 0:
+        p4 = P.OXFORD
+        t0 = time.perf_counter()
+        truth, scans = W.make_loop_drive(p4, 300, args.replay_scans)
+        t_gen = time.perf_counter() - t0
+        W.device_replay(ctx, capi, p4, scans[:12])                          # warm-up
+        l0 = ctx.launch_count
+        poses_g, dt, its = W.device_replay(ctx, capi, p4, scans)
+        launches = ctx.launch_count - l0
+        est = np.stack([poses_g[:, 2], poses_g[:, 3], np.unwrap(np.arctan2(poses_g[:, 1], poses_g[:, 0]))], 1)
+        err = np.hypot(est[:, 0] - truth[:, 0], est[:, 1] - truth[:, 1])
+        rec = {"workload": "configs[4]: one synthetic drive of %d Oxford-shape scans (~5 k filtered points each) around a 30 m circle, per scan: K1 voxelise -> K2 "
+                           "associate against the submap -> K7 GNC + LM registration -> every 2nd scan transform + merge into the submap" % len(scans),
+               "scans": len(scans), "scans_per_s": (len(scans) - 1) / dt, "ms_per_scan": dt * 1e3 / (len(scans) - 1), "kernel_launches_per_scan": launches / (len(scans) - 1),
+               "mean_lm_iterations_per_scan": its, "max_position_error_m": float(err.max()), "final_position_error_m": float(err[-1]),
+               "sensor_rate_hz": 4.02, "scan_generation_s": t_gen, "n_gpus_used": 1,
+               "note": "replicas only: a drive is a chain of dependent scans; NDT-only odometry without the reference's motion-model / IMU factors (host side)"}
+        if oracle is not None and args.replay_oracle_scans > 1:
+            n_o = min(args.replay_oracle_scans, len(scans))
+            poses_o, dto = W.oracle_replay(oracle, p4, scans[:n_o])
+            rec["cpu_baseline"] = {"scans_per_s": (n_o - 1) / dto, "cores": 1, "kind": "port", "sample": "first %d scans of the drive" % n_o,
+                                   "max_abs_pose_difference_vs_device": float(np.max(np.abs(poses_o - poses_g[:n_o])))}
+        out["c4"] = rec
+    barrier()
+    return out
+
+
 _OUT = None
 
 
@@ -295,13 +384,18 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--problems", type=int, default=DEFAULT_PROBLEMS, help="independent registration problems per GPU per step")
-    ap.add_argument("--ref-problems", type=int, default=2048, help="problems per step of the CPU reference arm (bounded sample)")
+    ap.add_argument("--ref-problems", type=int, default=2048, help="problems each step of the CPU reference arm evaluates (bounded sample of the --problems workload)")
     ap.add_argument("--cpu-sample", type=int, default=1024, help="problems in the cpu_baseline sample")
     ap.add_argument("--reg-steps", type=int, default=3, help="timed full-batch GNC+LM registration solves (0 disables the registrations leg)")
     ap.add_argument("--reg-streams", type=int, default=3, help="independent batches solved concurrently (own context/stream/thread each) in the pipelined leg; 0 disables")
     ap.add_argument("--reg-cpu-sample", type=int, default=48, help="registrations the oracle solves for the CPU comparison")
     ap.add_argument("--pre-scans", type=int, default=8, help="raw Oxford-size scans in the preprocessing leg (0 disables it)")
     ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--no-configs", action="store_true", help="skip the configs leg (c0, c2, c3, c4 sub-records)")
+    ap.add_argument("--c2-problems", type=int, default=384, help="configs[2]-shaped problems (2 k x 8 k cells) evaluated per step in the c2 sub-record")
+    ap.add_argument("--c3-batch", type=int, default=256, help="registrations of the literal configs[3] batch (sharded over the ranks)")
+    ap.add_argument("--replay-scans", type=int, default=8609, help="scans of the configs[4] replay (Oxford sequence length); rank 0 only")
+    ap.add_argument("--replay-oracle-scans", type=int, default=300, help="prefix of the drive the CPU oracle chain replays for comparison")
     ap.add_argument("--preset", choices=sorted(P.PRESETS), default="oxford",
                     help="shipped parameter file the scans, maps and losses follow (SURVEY §8d C2 fixes oxford for the headline workload: an "
                          "Oxford-shape scan against parameters_oxford.yaml; BASELINE.json's configs[1] words it 'indoor params' — "
@@ -328,7 +422,7 @@ def main():
     torch.cuda.set_device(local)
     stream = torch.cuda.Stream(device=local)
     ctx = capi.Context(local, stream=stream.cuda_stream)
-    prob, poses, st, host = build_problem(ctx, capi, p, args.problems, args.seed + 100 * rank)
+    prob, poses, st, host = build_problem(ctx, capi, p, args.problems, args.seed)     # the same shard shape on every rank: equal pair counts
     S, Pn = st["segments"], st["pairs"]
     resident = 48 * (st["n_m"] + st["n_f"]) + 8 * Pn + 16 * prob.n_segments + 224 * S
 
@@ -565,7 +659,7 @@ def main():
         # ---- construction-time stages: K1 voxelise and K2 associate on resident batches ----
         stages = None
         if args.pre_scans > 0:
-            sub_, _, mov_, _ = pool_scans(p, args.seed + 100 * rank)
+            sub_, _, mov_, _ = pool_scans(p, args.seed)
             base = sub_[:POOL] + mov_
             reps_ = 8                                        # 256 scans per call
             pts_np = np.concatenate(base * reps_)
@@ -601,6 +695,7 @@ def main():
                                         "finite": bool(np.isfinite(cs_all).all()), "what": "randt_cs_divergence (K5), maps resident: all-pairs 3x3 inverse + det + exp"},
                       "associate": {"queries_per_s": st["n_m"] / t_as, "ms_per_call": t_as * 1e3, "queries_per_call": st["n_m"],
                                     "what": "randt_associate (K2 + pair/duo compaction + record table + schedule), maps resident"}}
+        configs = None if args.no_configs else run_configs(args, ctx, capi, stream, rank, world, local, barrier)
     bad = ctx.take_bad_pairs()
 
     t_ms = torch.tensor([ms, e2e_s * 1e3, reg["ms_per_batch"] if reg else 0.0, reg["e2e_ms_per_batch"] if reg else 0.0, e2e_sync_s * 1e3], dtype=torch.float64,
@@ -616,6 +711,13 @@ def main():
             rows[:, 5] = reg["rows"][:, capi.REG_ITERATIONS]; rows[:, 6] = reg["rows"][:, capi.REG_STATUS]
             table = shard.gather_results(rows, rank * S, world * S, rank, world, device=torch.device("cuda", local))   # NCCL all_gather
             assert table.shape[0] == world * S and not np.isnan(table[:, 4]).any()
+    per_rank = None
+    if world > 1:
+        mine = torch.tensor([ms, e2e_s * 1e3, reg["ms_per_batch"] if reg else 0.0], dtype=torch.float64, device="cuda:%d" % local)
+        gathered = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        per_rank = {"ms_per_step": [float(g[0]) / args.steps for g in gathered], "e2e_ms_per_step": [float(g[1]) / args.steps for g in gathered],
+                    "registrations_ms_per_batch": [float(g[2]) for g in gathered]}
     ms_all, e2e_ms_all, reg_ms_all, reg_e2e_ms_all, e2e_sync_ms_all = (float(t_ms[i]) for i in range(5))
     seg_all = float(tot[1])
     pairs_all = float(tot[0])
@@ -651,8 +753,12 @@ def main():
                          "traffic": measured_traffic(Pn), "peak_source": pk_src, "kernel": "k3_fused_kernel<0,BARRON_M2,true>",
                          "algorithmic_bytes_per_launch": alg, "kernel_ms": kern_ms},
             "clocks": clocks,
+            "per_rank": per_rank,
             "degenerate_pairs": bad,
         }
+        if configs is not None:
+            configs["c1"] = {"workload": workload_name(p), "see": "the top-level value / e2e / roofline / registrations of this line"}
+            line["configs"] = configs
         if pre:
             line["preprocess"] = pre
         if stages:

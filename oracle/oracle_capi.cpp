@@ -191,6 +191,13 @@ double orc_fused_batch(int variant, const float* cells_m, const float* cells_f, 
 }
 
 // Matcher::estimateLoopConstraint restated.  out = pose[4], score, gnc_solves, total_iterations, total_evals, mu_first ; returns status
+// ceres tolerances for the next orc_loop_constraint calls of this thread (<= 0: ceres' defaults): lets a test remove the slack the
+// default function_tolerance leaves when two implementations are compared at their stopping points
+static thread_local double g_function_tol = 0.0, g_parameter_tol = 0.0, g_gradient_tol = 0.0;
+void orc_set_tolerances(double function_tol, double parameter_tol, double gradient_tol) {
+  g_function_tol = function_tol; g_parameter_tol = parameter_tol; g_gradient_tol = gradient_tol;
+}
+
 int orc_loop_constraint(const float* f_cells, int n_f, const int32_t* f_slot, int size_x, int size_y, double res, double max_linf,
                         const float* m_cells, int n_m, const double* pose4, int k, int metric, int variant,
                         double matcher_loss_scale, double loop_scale, double alpha, double divisor, int max_gnc_steps,
@@ -199,6 +206,9 @@ int orc_loop_constraint(const float* f_cells, int n_f, const int32_t* f_slot, in
   NdtMap F = view_map(f_cells, nullptr, n_f, f_slot, size_x, size_y, res, max_linf);
   NdtMap M = view_map(m_cells, nullptr, n_m, nullptr, size_x, size_y, res, max_linf);
   LmOptions opt; opt.max_num_iterations = max_iterations;
+  if (g_function_tol > 0.0) opt.function_tolerance = g_function_tol;
+  if (g_parameter_tol > 0.0) opt.parameter_tolerance = g_parameter_tol;
+  if (g_gradient_tol > 0.0) opt.gradient_tolerance = g_gradient_tol;
   PairList pl;
   if (im_in && P_in > 0) { pl.im.assign(im_in, im_in + P_in); pl.jf.assign(jf_in, jf_in + P_in); }
   LoopConstraintResult R = loop_constraint(F, M, pose4, k, metric, variant, matcher_loss_scale, loop_scale, alpha, divisor,

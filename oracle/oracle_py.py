@@ -259,17 +259,22 @@ def fused_batch(variant, cells_m, cells_f, im, jf, seg_off, poses, loss=(LOSS_NO
 
 def loop_constraint(f_cells, f_slot, size_x, size_y, res, max_linf, m_cells, pose, k, metric=LOOKUP_MAHALANOBIS,
                     variant=VAR_SE2_INTENSITY, matcher_loss_scale=1.0, loop_scale=1.0, alpha=-2.0, divisor=1.1, max_gnc_steps=2,
-                    max_iterations=200, on_manifold=False, loss_weight=1.0, pairs=None):
+                    max_iterations=200, on_manifold=False, loss_weight=1.0, pairs=None, tolerances=None):
+    """tolerances: (function, parameter, gradient) overriding ceres' defaults (1e-6, 1e-8, 1e-10) for this call"""
     fc = _f32(f_cells).reshape(-1, 12); mc = _f32(m_cells).reshape(-1, 12); fs = _i32(f_slot); pose = _f64(pose)
     out = np.zeros(9, np.float64)
     if pairs is not None:
         im, jf = _u32(pairs[0]), _u32(pairs[1]); pim, pjf, P = _p(im, C.c_uint32), _p(jf, C.c_uint32), len(im)
     else:
         pim, pjf, P = None, None, 0
+    if tolerances is not None:
+        lib().orc_set_tolerances(C.c_double(tolerances[0]), C.c_double(tolerances[1]), C.c_double(tolerances[2]))
     st = lib().orc_loop_constraint(_p(fc, C.c_float), len(fc), _p(fs, C.c_int32), size_x, size_y, float(res), float(max_linf),
                                    _p(mc, C.c_float), len(mc), _p(pose, C.c_double), int(k), int(metric), int(variant),
                                    float(matcher_loss_scale), float(loop_scale), float(alpha), float(divisor), int(max_gnc_steps),
                                    int(max_iterations), int(on_manifold), float(loss_weight), pim, pjf, P, _p(out, C.c_double))
+    if tolerances is not None:
+        lib().orc_set_tolerances(C.c_double(0.0), C.c_double(0.0), C.c_double(0.0))
     return dict(pose=out[:4].copy(), score=out[4], gnc_solves=int(out[5]), iterations=int(out[6]), evals=int(out[7]),
                 mu_first=out[8], status=st)
 
