@@ -19,25 +19,28 @@
 namespace randt {
 namespace {
 
-constexpr int kVoxThreads = 256;
+constexpr int kVoxThreads = 1024;  // most threads of the one CTA a scan gets: 32 warps shorten every block-wide phase (the bin scans, the slot-table
+                                   // clear) of a lone scan; batches launch 512 so that two scans share an SM (56 registers per thread)
 constexpr int kVoxWarps = kVoxThreads / 32;
+constexpr int kVoxCountWarps = 8;  // warps that own a slice of the scan in the stable counting sort (one 16-bit histogram each)
 
-__device__ __forceinline__ uint32_t block_scan_excl(uint32_t v, uint32_t* warp_sums, uint32_t* total) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  uint32_t x = v;
+// exclusive block scan of a 64-bit value (two 32-bit counters packed: both are scanned in one pass)
+__device__ __forceinline__ unsigned long long block_scan_excl(unsigned long long v, unsigned long long* warp_sums, unsigned long long* total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, n_warps = (int)(blockDim.x >> 5);
+  unsigned long long x = v;
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+  for (int o = 1; o < 32; o <<= 1) { const unsigned long long y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
   if (lane == 31) warp_sums[w] = x;
   __syncthreads();
   if (w == 0) {
-    uint32_t s = (lane < kVoxWarps) ? warp_sums[lane] : 0u;
+    unsigned long long s = (lane < n_warps) ? warp_sums[lane] : 0ull;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
+    for (int o = 1; o < 32; o <<= 1) { const unsigned long long y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
     warp_sums[lane] = s;
   }
   __syncthreads();
-  const uint32_t base = (w > 0) ? warp_sums[w - 1] : 0u;
-  *total = warp_sums[kVoxWarps - 1];
+  const unsigned long long base = (w > 0) ? warp_sums[w - 1] : 0ull;
+  *total = warp_sums[n_warps - 1];
   __syncthreads();
   return base + x - v;
 }
@@ -103,32 +106,40 @@ struct CellOut { float mu[3]; float cov[9]; };
 
 // Cell::updateCell for a fresh cell: two sequential float32 passes over the cell's points (ndt_cell.cpp:43-65), then the
 // xy eigenvalue floor and the +1e-6 on the intensity variance (ndt_cell.cpp:102-112).
-// One WARP per cell: the 32 lanes fetch 32 points at a time (index, then point: two memory round trips per 32 points instead of
-// per point), and every lane then adds the 32 values in point order through shuffles — all lanes carry the same running sums, so
-// the order (and with it every rounding) is exactly the reference's sequential loop.
-__device__ void cell_stats_warp(const float4* __restrict__ pts, const uint32_t* __restrict__ order, uint32_t n, int lane, CellOut& o) {
-  constexpr unsigned kAll = 0xffffffffu;
+// One THREAD per cell: the stable counting sort has laid the cell's points (x, y, intensity) out contiguously in scan order, so the
+// thread streams its own run — eight independent loads in flight, then eight adds in point order: the order (and with it every
+// rounding) is exactly the reference's sequential loop, and the 32 lanes of a warp work on 32 cells at once.
+__device__ void cell_stats_thread(const float4* __restrict__ sp, uint32_t n, CellOut& o) {
   float sx = 0.f, sy = 0.f, si = 0.f;
-  for (uint32_t k0 = 0; k0 < n; k0 += 32) {
-    const uint32_t m = min(32u, n - k0);
-    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-    if ((uint32_t)lane < m) p = __ldg(pts + order[k0 + lane]);
-    for (uint32_t j = 0; j < m; ++j) {
-      sx += __shfl_sync(kAll, p.x, (int)j); sy += __shfl_sync(kAll, p.y, (int)j); si += __shfl_sync(kAll, p.w, (int)j);
-    }
+  uint32_t k = 0;
+  for (; k + 8 <= n; k += 8) {
+    float4 p[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) p[j] = sp[k + j];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sx += p[j].x; sy += p[j].y; si += p[j].z; }
   }
+  for (; k < n; ++k) { const float4 p = sp[k]; sx += p.x; sy += p.y; si += p.z; }
   const float nf = (float)n;
   const float mx = sx / nf, my = sy / nf, mz = si / nf;
   float c00 = 0.f, c11 = 0.f, c22 = 0.f, c01 = 0.f, c02 = 0.f, c12 = 0.f;
-  for (uint32_t k0 = 0; k0 < n; k0 += 32) {
-    const uint32_t m = min(32u, n - k0);
-    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-    if ((uint32_t)lane < m) p = __ldg(pts + order[k0 + lane]);
-    for (uint32_t j = 0; j < m; ++j) {
-      const float dx = __shfl_sync(kAll, p.x, (int)j) - mx, dy = __shfl_sync(kAll, p.y, (int)j) - my, di = __shfl_sync(kAll, p.w, (int)j) - mz;
+  k = 0;
+  for (; k + 8 <= n; k += 8) {
+    float4 p[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) p[j] = sp[k + j];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float dx = p[j].x - mx, dy = p[j].y - my, di = p[j].z - mz;
       c00 += dx * dx; c11 += dy * dy; c22 += di * di;
       c01 += dx * dy; c02 += dx * di; c12 += dy * di;
     }
+  }
+  for (; k < n; ++k) {
+    const float4 p = sp[k];
+    const float dx = p.x - mx, dy = p.y - my, di = p.z - mz;
+    c00 += dx * dx; c11 += dy * dy; c22 += di * di;
+    c01 += dx * dy; c02 += dx * di; c12 += dy * di;
   }
   o.mu[0] = mx; o.mu[1] = my; o.mu[2] = mz;
   o.cov[0] = c00 / nf; o.cov[1] = c01 / nf; o.cov[2] = c02 / nf;
@@ -150,18 +161,20 @@ __device__ void cell_stats_warp(const float4* __restrict__ pts, const uint32_t* 
 
 // per-scan status codes: VOX_* in common.cuh
 
-// dynamic shared memory: uint32 bin_start[span_cap] | uint32 bin_rank[span_cap] | uint16 whist[n_cnt_warps][span_cap]
+// dynamic shared memory: uint32 bin_start[span_cap] | uint32 bin_keep[span_cap] | uint16 whist[n_cnt_warps][span_cap]
+//   bin_keep[bin] = index of the bin's cell among the kept cells of the scan, or kNotKept
+constexpr uint32_t kNotKept = 0xffffffffu;
 __global__ void __launch_bounds__(kVoxThreads) k1_voxelize_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ scan_off,
                                                                  int row, float label_res, int min_points, MapGeomDev geom,
                                                                  uint32_t span_cap, int n_cnt_warps, uint32_t cell_cap, float4* __restrict__ cells_out,
                                                                  uint32_t* __restrict__ npts_out, int32_t* __restrict__ labels_out,
                                                                  uint32_t* __restrict__ cell_count, int32_t* __restrict__ slot_out,
-                                                                 int32_t* __restrict__ labels_scratch, uint32_t* __restrict__ order, int* __restrict__ status) {
+                                                                 int32_t* __restrict__ labels_scratch, float4* __restrict__ sorted, int* __restrict__ status) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* bin_start = reinterpret_cast<uint32_t*>(smem_raw);
-  uint32_t* bin_rank = bin_start + span_cap;
-  unsigned short* whist = reinterpret_cast<unsigned short*>(bin_rank + span_cap);
-  __shared__ uint32_t warp_sums[32];
+  uint32_t* bin_keep = bin_start + span_cap;
+  unsigned short* whist = reinterpret_cast<unsigned short*>(bin_keep + span_cap);
+  __shared__ unsigned long long warp_sums[32];
   __shared__ int s_min[kVoxWarps], s_max[kVoxWarps];
   __shared__ int s_lab_min, s_lab_max;
 
@@ -169,14 +182,21 @@ __global__ void __launch_bounds__(kVoxThreads) k1_voxelize_kernel(const float4* 
   const uint32_t p0 = scan_off[b], p1 = scan_off[b + 1];
   const uint32_t n = p1 - p0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t n_thr = blockDim.x; const int n_warps = (int)(blockDim.x >> 5);
   int32_t* __restrict__ slot = slot_out + (size_t)b * geom.n_slots;
-  for (uint32_t e = tid; e < geom.n_slots; e += kVoxThreads) slot[e] = -1;
+  {
+    // the slot table starts out empty (-1): 16-byte stores where the table is aligned for them
+    int4* s4 = reinterpret_cast<int4*>(slot);
+    const uint32_t n4 = ((reinterpret_cast<uintptr_t>(slot) & 15u) == 0u) ? geom.n_slots / 4u : 0u;
+    for (uint32_t e = tid; e < n4; e += n_thr) s4[e] = make_int4(-1, -1, -1, -1);
+    for (uint32_t e = n4 * 4u + tid; e < geom.n_slots; e += n_thr) slot[e] = -1;
+  }
   if (tid == 0) { cell_count[b] = 0; status[b] = VOX_OK; }
   if (n == 0) return;
 
   // ---- phase 0: labels (Grid::cluster), min/max label ----
   int lmin = INT_MAX, lmax = INT_MIN;
-  for (uint32_t e = tid; e < n; e += kVoxThreads) {
+  for (uint32_t e = tid; e < n; e += n_thr) {
     const float4 p = __ldg(pts + p0 + e);
     const int lab = (int)(p.x / label_res) + row * (int)(p.y / label_res);   // C++ float->int conversion truncates toward zero
     labels_scratch[p0 + e] = lab;
@@ -185,11 +205,14 @@ __global__ void __launch_bounds__(kVoxThreads) k1_voxelize_kernel(const float4* 
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, o)); lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o)); }
   if (lane == 0) { s_min[warp] = lmin; s_max[warp] = lmax; }
+  // per-warp histograms cleared while the labels settle
+  for (uint32_t e = tid; e < (uint32_t)n_cnt_warps * span_cap / 2u; e += n_thr) reinterpret_cast<uint32_t*>(whist)[e] = 0u;
   __syncthreads();
-  if (tid == 0) {
-    int a = s_min[0], z = s_max[0];
-    for (int w = 1; w < kVoxWarps; ++w) { a = min(a, s_min[w]); z = max(z, s_max[w]); }
-    s_lab_min = a; s_lab_max = z;
+  if (warp == 0) {
+    int a = lane < n_warps ? s_min[lane] : INT_MAX, z = lane < n_warps ? s_max[lane] : INT_MIN;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a = min(a, __shfl_xor_sync(0xffffffffu, a, o)); z = max(z, __shfl_xor_sync(0xffffffffu, z, o)); }
+    if (lane == 0) { s_lab_min = a; s_lab_max = z; }
   }
   __syncthreads();
   const int lab_min = s_lab_min;
@@ -200,8 +223,6 @@ __global__ void __launch_bounds__(kVoxThreads) k1_voxelize_kernel(const float4* 
   // ---- phase 1: per-warp histograms over contiguous slices (stable counting sort, pass 1) ----
   const uint32_t slice = (n + n_cnt_warps - 1) / n_cnt_warps;
   if (slice > 65535u) { if (tid == 0) status[b] = VOX_SPAN; return; }
-  for (uint32_t e = tid; e < (uint32_t)n_cnt_warps * span_cap; e += kVoxThreads) whist[e] = 0;
-  __syncthreads();
   if (warp < n_cnt_warps) {
     const uint32_t s0 = warp * slice, s1 = min(n, s0 + slice);
     unsigned short* h = whist + (size_t)warp * span_cap;
@@ -216,18 +237,24 @@ __global__ void __launch_bounds__(kVoxThreads) k1_voxelize_kernel(const float4* 
   }
   __syncthreads();
 
-  // ---- phase 2: totals per bin -> exclusive scan (bin_start) and rank of occupied bins (ascending label = cluster id) ----
-  uint32_t carry_pts = 0, carry_occ = 0;
-  for (uint32_t base = 0; base < span; base += kVoxThreads) {
+  // ---- phase 2: totals per bin -> exclusive scans: points before the bin (bin_start) and kept cells before the bin (ascending label =
+  //      cluster order; keep test count > min_points, Cell::addPointCloud) — both counters in one 64-bit scan ----
+  unsigned long long carry = 0ull;
+  for (uint32_t base = 0; base < span; base += n_thr) {
     const uint32_t bin = base + tid;
     uint32_t tot = 0;
     if (bin < span) for (int w = 0; w < n_cnt_warps; ++w) tot += whist[(size_t)w * span_cap + bin];
-    uint32_t t_pts, t_occ;
-    const uint32_t ex_pts = block_scan_excl(tot, warp_sums, &t_pts);
-    const uint32_t ex_occ = block_scan_excl(tot > 0 ? 1u : 0u, warp_sums, &t_occ);
+    const bool keep = tot > 0u && (long long)tot > (long long)min_points;
+    unsigned long long total;
+    const unsigned long long ex = carry + block_scan_excl((unsigned long long)tot | ((unsigned long long)(keep ? 1u : 0u) << 32), warp_sums, &total);
     if (bin < span) {
-      bin_start[bin] = carry_pts + ex_pts;
-      bin_rank[bin] = carry_occ + ex_occ;
+      bin_start[bin] = (uint32_t)ex;
+      const uint32_t ci = (uint32_t)(ex >> 32);
+      bin_keep[bin] = keep ? ci : kNotKept;
+      if (keep) {
+        if (ci < cell_cap) { npts_out[(size_t)b * cell_cap + ci] = tot; labels_out[(size_t)b * cell_cap + ci] = (int32_t)bin + lab_min; }
+        else status[b] = VOX_CELL_CAP;
+      }
       // turn per-warp counts into per-warp offsets inside the bin
       uint32_t run = 0;
       for (int w = 0; w < n_cnt_warps; ++w) {
@@ -237,11 +264,12 @@ __global__ void __launch_bounds__(kVoxThreads) k1_voxelize_kernel(const float4* 
       }
       if (run > 65535u) status[b] = VOX_SPAN;   // a single cell with > 65535 points does not fit the 16-bit offsets
     }
-    carry_pts += t_pts; carry_occ += t_occ;
+    carry += total;
   }
   __syncthreads();
+  const uint32_t n_keep = min((uint32_t)(carry >> 32), cell_cap);
 
-  // ---- phase 3: stable scatter of point indices ----
+  // ---- phase 3: stable scatter of the points (x, y, intensity) of kept cells into cell-major, scan-ordered runs ----
   if (warp < n_cnt_warps) {
     const uint32_t s0 = warp * slice, s1 = min(n, s0 + slice);
     unsigned short* h = whist + (size_t)warp * span_cap;
@@ -254,52 +282,31 @@ __global__ void __launch_bounds__(kVoxThreads) k1_voxelize_kernel(const float4* 
       uint32_t off = 0;
       if (act && leader == lane) { off = h[bin]; h[bin] = (unsigned short)(off + __popc(peers)); }
       off = __shfl_sync(0xffffffffu, off, leader);
-      if (act) order[p0 + bin_start[bin] + off + __popc(peers & ((1u << lane) - 1u))] = p0 + e;
+      if (act && bin_keep[bin] != kNotKept) {
+        const float4 p = __ldg(pts + p0 + e);
+        sorted[p0 + bin_start[bin] + off + __popc(peers & ((1u << lane) - 1u))] = make_float4(p.x, p.y, p.w, 0.f);
+      }
       __syncwarp();
     }
   }
   __syncthreads();
 
-  // ---- phase 4a: keep test (count > min_points), kept clusters numbered in ascending label order ----
-  uint32_t carry_keep = 0;
-  for (uint32_t base = 0; base < span; base += kVoxThreads) {
-    const uint32_t bin = base + tid;
-    uint32_t cnt = 0;
-    if (bin < span) cnt = ((bin + 1 < span) ? bin_start[bin + 1] : n) - bin_start[bin];
-    const bool keep = (bin < span) && cnt > 0 && ((long long)cnt > (long long)min_points);
-    uint32_t t_keep;
-    const uint32_t ex = block_scan_excl(keep ? 1u : 0u, warp_sums, &t_keep);
-    if (keep) {
-      const uint32_t ci = carry_keep + ex;
-      if (ci < cell_cap) {
-        npts_out[(size_t)b * cell_cap + ci] = cnt;
-        labels_out[(size_t)b * cell_cap + ci] = (int32_t)bin + lab_min;
-      } else {
-        status[b] = VOX_CELL_CAP;
-      }
-    }
-    carry_keep += t_keep;
-  }
-  __syncthreads();
-  // ---- phase 4b: one warp per kept cell: sequential float32 statistics, slot table ----
-  const uint32_t n_keep = min(carry_keep, cell_cap);
-  for (uint32_t ci = warp; ci < n_keep; ci += kVoxWarps) {
+  // ---- phase 4: one thread per kept cell: sequential float32 statistics, slot table ----
+  for (uint32_t ci = tid; ci < n_keep; ci += n_thr) {
     const uint32_t bin = (uint32_t)(labels_out[(size_t)b * cell_cap + ci] - lab_min);
     const uint32_t cnt = npts_out[(size_t)b * cell_cap + ci];
     CellOut o;
-    cell_stats_warp(pts, order + p0 + bin_start[bin], cnt, lane, o);
-    if (lane == 0) {
-      const uint32_t s = coord_to_index(geom, o.mu[0], o.mu[1]);
-      float4* dst = cells_out + 3 * ((size_t)b * cell_cap + ci);
-      dst[0] = make_float4(o.mu[0], o.mu[1], o.mu[2], o.cov[0]);
-      dst[1] = make_float4(o.cov[1], o.cov[2], o.cov[3], o.cov[4]);
-      dst[2] = make_float4(o.cov[5], o.cov[6], o.cov[7], o.cov[8]);
-      // the reference would throw (vector::at) for a mean outside the map; flagged instead, cell kept without a slot
-      if (s < geom.n_slots) atomicMax(&slot[s], (int32_t)ci);   // "later cluster wins" == largest kept index
-      else status[b] = VOX_OUT_OF_MAP;
-    }
+    cell_stats_thread(sorted + p0 + bin_start[bin], cnt, o);
+    const uint32_t s = coord_to_index(geom, o.mu[0], o.mu[1]);
+    float4* dst = cells_out + 3 * ((size_t)b * cell_cap + ci);
+    dst[0] = make_float4(o.mu[0], o.mu[1], o.mu[2], o.cov[0]);
+    dst[1] = make_float4(o.cov[1], o.cov[2], o.cov[3], o.cov[4]);
+    dst[2] = make_float4(o.cov[5], o.cov[6], o.cov[7], o.cov[8]);
+    // the reference would throw (vector::at) for a mean outside the map; flagged instead, cell kept without a slot
+    if (s < geom.n_slots) atomicMax(&slot[s], (int32_t)ci);   // "later cluster wins" == largest kept index
+    else status[b] = VOX_OUT_OF_MAP;
   }
-  if (tid == 0) cell_count[b] = min(carry_keep, cell_cap);
+  if (tid == 0) cell_count[b] = n_keep;
 }
 
 __global__ void k1_compact_cells_kernel(const float4* __restrict__ cells_p, const uint32_t* __restrict__ npts_p, const int32_t* __restrict__ labels_p,
@@ -522,7 +529,7 @@ __global__ void merge_maps_kernel(const float4* __restrict__ f_cells, const uint
 cudaError_t launch_voxelize(const float4* d_pts, const uint32_t* d_scan_off, uint32_t n_scans, uint32_t max_pts_per_scan,
                             const randt_grid_params& gp, const MapGeomDev& geom, uint32_t cell_cap_per_scan, float4* d_cells_p,
                             uint32_t* d_npts_p, int32_t* d_labels_p, uint32_t* d_cell_count, int32_t* d_slot, int32_t* d_labels_scratch,
-                            uint32_t* d_order, int* d_status, cudaStream_t s, int* n_launches) {
+                            float4* d_sorted, int* d_status, cudaStream_t s, int* n_launches) {
   if (n_scans == 0) return cudaSuccess;
   const int row = static_cast<int>(sqrt((double)(size_t)gp.n_clusters));
   if (row <= 0) return cudaErrorInvalidValue;
@@ -533,16 +540,18 @@ cudaError_t launch_voxelize(const float4* d_pts, const uint32_t* d_scan_off, uin
   const size_t smem_max = 220 * 1024;
   if ((size_t)span_cap * (8 + 2) > smem_max) span_cap = (uint32_t)(smem_max / 10 / 256 * 256);
   int n_cnt_warps = (int)((smem_max - (size_t)span_cap * 8) / ((size_t)span_cap * 2));
-  if (n_cnt_warps > kVoxWarps) n_cnt_warps = kVoxWarps;
+  if (n_cnt_warps > kVoxCountWarps) n_cnt_warps = kVoxCountWarps;
   if (n_cnt_warps < 1) n_cnt_warps = 1;
   // small scans do not need all counting warps (fewer histograms to clear and fold)
   while (n_cnt_warps > 1 && (max_pts_per_scan + n_cnt_warps - 1) / n_cnt_warps < 256) n_cnt_warps >>= 1;
   const size_t smem = (size_t)span_cap * 8 + (size_t)n_cnt_warps * span_cap * 2;
-  cudaError_t e = cudaFuncSetAttribute(k1_voxelize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaSuccess;
+  if (smem > 48u * 1024u) e = cudaFuncSetAttribute(k1_voxelize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k1_voxelize_kernel<<<n_scans, kVoxThreads, smem, s>>>(d_pts, d_scan_off, row, label_res, gp.min_points, geom, span_cap, n_cnt_warps,
+  const int threads = n_scans > (uint32_t)kSmCount ? 512 : kVoxThreads;     // a batch: two scans per SM; a lone scan: all 32 warps
+  k1_voxelize_kernel<<<n_scans, threads, smem, s>>>(d_pts, d_scan_off, row, label_res, gp.min_points, geom, span_cap, n_cnt_warps,
                                                         cell_cap_per_scan, d_cells_p, d_npts_p, d_labels_p, d_cell_count, d_slot,
-                                                        d_labels_scratch, d_order, d_status);
+                                                        d_labels_scratch, d_sorted, d_status);
   if (n_launches) *n_launches += 1;
   return cudaGetLastError();
 }
