@@ -371,6 +371,9 @@ int randt_voxelize(randt_ctx* ctx, const float* pts4, const uint32_t* scan_off, 
   *out = nullptr;
   if (gp->n_clusters <= 0 || gp->size_x <= 0 || gp->size_y <= 0 || !(gp->resolution > 0) || !(gp->max_range > 0))
     return fail(ctx, RANDT_E_INVALID, "randt_voxelize: bad grid parameters");
+  for (uint32_t b = 0; b < n_scans; ++b)
+    if (scan_off[b + 1] >= scan_off[b] && scan_off[b + 1] - scan_off[b] > 16384u)
+      return fail(ctx, RANDT_E_CAPACITY, "randt_voxelize: more than 16384 points in one scan (a scan is sorted in shared memory; the shipped sensors deliver ~3-5 k filtered points)");
   CK(cudaSetDevice(ctx->device));
   StreamScope scope__(ctx->stream);
   const uint32_t B = n_scans;
@@ -384,12 +387,12 @@ int randt_voxelize(randt_ctx* ctx, const float* pts4, const uint32_t* scan_off, 
   if (!m) return RANDT_E_NOMEM;
   m->device = ctx->device; m->sref = ctx->sref; m->gp = *gp; m->geom = make_geom(*gp); m->B = B;
   float4* d_pts = nullptr; bool own_pts = false;
-  uint32_t *d_scan_off = nullptr, *d_cnt = nullptr, *d_npts_p = nullptr; float4* d_sorted = nullptr;
+  uint32_t *d_scan_off = nullptr, *d_cnt = nullptr, *d_npts_p = nullptr;
   int32_t *d_labels_scratch = nullptr, *d_labels_p = nullptr; float4* d_cells_p = nullptr; int* d_status = nullptr;
   int rc = RANDT_OK;
   auto cleanup = [&]() {
     if (own_pts) dev_free(d_pts);
-    dev_free(d_scan_off); dev_free(d_cnt); dev_free(d_sorted); dev_free(d_npts_p); dev_free(d_labels_scratch); dev_free(d_labels_p);
+    dev_free(d_scan_off); dev_free(d_cnt); dev_free(d_npts_p); dev_free(d_labels_scratch); dev_free(d_labels_p);
     dev_free(d_cells_p); dev_free(d_status);
   };
 #define CKV(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rc = fail(ctx, RANDT_E_CUDA, #call, e__); cleanup(); free_map(m); return rc; } } while (0)
@@ -397,13 +400,13 @@ int randt_voxelize(randt_ctx* ctx, const float* pts4, const uint32_t* scan_off, 
   else { CKV(dev_alloc(&d_pts, n_pts)); own_pts = true; if (n_pts) CKV(cudaMemcpyAsync(d_pts, pts4, (size_t)n_pts * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream)); }
   CKV(dev_alloc(&d_scan_off, B + 1));
   CKV(cudaMemcpyAsync(d_scan_off, scan_off, (size_t)(B + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-  CKV(dev_alloc(&d_cnt, B)); CKV(dev_alloc(&d_sorted, n_pts)); CKV(dev_alloc(&d_labels_scratch, n_pts));
+  CKV(dev_alloc(&d_cnt, B)); CKV(dev_alloc(&d_labels_scratch, n_pts));
   CKV(dev_alloc(&d_cells_p, (size_t)B * cell_cap * 3)); CKV(dev_alloc(&d_npts_p, (size_t)B * cell_cap)); CKV(dev_alloc(&d_labels_p, (size_t)B * cell_cap));
   CKV(dev_alloc(&d_status, B));
   CKV(dev_alloc(&m->slot, (size_t)B * m->geom.n_slots));
   int nl = 0;
   CKV(launch_voxelize(d_pts, d_scan_off, B, max_pts, *gp, m->geom, cell_cap, d_cells_p, d_npts_p, d_labels_p, d_cnt, m->slot, d_labels_scratch,
-                      d_sorted, d_status, ctx->stream, &nl));
+                      d_status, ctx->stream, &nl));
   std::vector<uint32_t> h_cnt(B); std::vector<int> h_status(B);
   if (B) { CKV(cudaMemcpyAsync(h_cnt.data(), d_cnt, B * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
            CKV(cudaMemcpyAsync(h_status.data(), d_status, B * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream)); }

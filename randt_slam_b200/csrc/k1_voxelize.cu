@@ -106,38 +106,19 @@ struct CellOut { float mu[3]; float cov[9]; };
 
 // Cell::updateCell for a fresh cell: two sequential float32 passes over the cell's points (ndt_cell.cpp:43-65), then the
 // xy eigenvalue floor and the +1e-6 on the intensity variance (ndt_cell.cpp:102-112).
-// One THREAD per cell: the stable counting sort has laid the cell's points (x, y, intensity) out contiguously in scan order, so the
-// thread streams its own run — eight independent loads in flight, then eight adds in point order: the order (and with it every
-// rounding) is exactly the reference's sequential loop, and the 32 lanes of a warp work on 32 cells at once.
-__device__ void cell_stats_thread(const float4* __restrict__ sp, uint32_t n, CellOut& o) {
+// One THREAD per cell: the stable counting sort has laid the cell's points (x, y, intensity) out contiguously in scan order in SHARED
+// memory, so the thread walks its own run at shared-memory latency, adding in point order: the order (and with it every rounding) is
+// exactly the reference's sequential loop, and the 32 lanes of a warp work on 32 cells at once.
+__device__ void cell_stats_thread(const float* __restrict__ px, const float* __restrict__ py, const float* __restrict__ pi, uint32_t n, CellOut& o) {
   float sx = 0.f, sy = 0.f, si = 0.f;
-  uint32_t k = 0;
-  for (; k + 8 <= n; k += 8) {
-    float4 p[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) p[j] = sp[k + j];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { sx += p[j].x; sy += p[j].y; si += p[j].z; }
-  }
-  for (; k < n; ++k) { const float4 p = sp[k]; sx += p.x; sy += p.y; si += p.z; }
+#pragma unroll 4
+  for (uint32_t k = 0; k < n; ++k) { sx += px[k]; sy += py[k]; si += pi[k]; }
   const float nf = (float)n;
   const float mx = sx / nf, my = sy / nf, mz = si / nf;
   float c00 = 0.f, c11 = 0.f, c22 = 0.f, c01 = 0.f, c02 = 0.f, c12 = 0.f;
-  k = 0;
-  for (; k + 8 <= n; k += 8) {
-    float4 p[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) p[j] = sp[k + j];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float dx = p[j].x - mx, dy = p[j].y - my, di = p[j].z - mz;
-      c00 += dx * dx; c11 += dy * dy; c22 += di * di;
-      c01 += dx * dy; c02 += dx * di; c12 += dy * di;
-    }
-  }
-  for (; k < n; ++k) {
-    const float4 p = sp[k];
-    const float dx = p.x - mx, dy = p.y - my, di = p.z - mz;
+#pragma unroll 4
+  for (uint32_t k = 0; k < n; ++k) {
+    const float dx = px[k] - mx, dy = py[k] - my, di = pi[k] - mz;
     c00 += dx * dx; c11 += dy * dy; c22 += di * di;
     c01 += dx * dy; c02 += dx * di; c12 += dy * di;
   }
@@ -161,19 +142,23 @@ __device__ void cell_stats_thread(const float4* __restrict__ sp, uint32_t n, Cel
 
 // per-scan status codes: VOX_* in common.cuh
 
-// dynamic shared memory: uint32 bin_start[span_cap] | uint32 bin_keep[span_cap] | uint16 whist[n_cnt_warps][span_cap]
-//   bin_keep[bin] = index of the bin's cell among the kept cells of the scan, or kNotKept
+// dynamic shared memory: uint32 bin_start[span_cap] | uint32 bin_keep[span_cap] | uint16 whist[n_cnt_warps][span_cap] | float sx[pt_cap] sy[pt_cap] si[pt_cap]
+//   bin_start[bin] = kept points before the bin (where the bin's run starts in sx / sy / si)
+//   bin_keep[bin]  = index of the bin's cell among the kept cells of the scan, or kNotKept
 constexpr uint32_t kNotKept = 0xffffffffu;
 __global__ void __launch_bounds__(kVoxThreads) k1_voxelize_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ scan_off,
                                                                  int row, float label_res, int min_points, MapGeomDev geom,
                                                                  uint32_t span_cap, int n_cnt_warps, uint32_t cell_cap, float4* __restrict__ cells_out,
                                                                  uint32_t* __restrict__ npts_out, int32_t* __restrict__ labels_out,
                                                                  uint32_t* __restrict__ cell_count, int32_t* __restrict__ slot_out,
-                                                                 int32_t* __restrict__ labels_scratch, float4* __restrict__ sorted, int* __restrict__ status) {
+                                                                 int32_t* __restrict__ labels_scratch, uint32_t pt_cap, int* __restrict__ status) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* bin_start = reinterpret_cast<uint32_t*>(smem_raw);
   uint32_t* bin_keep = bin_start + span_cap;
   unsigned short* whist = reinterpret_cast<unsigned short*>(bin_keep + span_cap);
+  float* sx = reinterpret_cast<float*>(whist + (size_t)n_cnt_warps * span_cap);
+  float* sy = sx + pt_cap;
+  float* si = sy + pt_cap;
   __shared__ unsigned long long warp_sums[32];
   __shared__ int s_min[kVoxWarps], s_max[kVoxWarps];
   __shared__ int s_lab_min, s_lab_max;
@@ -193,6 +178,7 @@ __global__ void __launch_bounds__(kVoxThreads) k1_voxelize_kernel(const float4* 
   }
   if (tid == 0) { cell_count[b] = 0; status[b] = VOX_OK; }
   if (n == 0) return;
+  if (n > pt_cap) { if (tid == 0) status[b] = VOX_SPAN; return; }
 
   // ---- phase 0: labels (Grid::cluster), min/max label ----
   int lmin = INT_MAX, lmax = INT_MIN;
@@ -246,7 +232,7 @@ __global__ void __launch_bounds__(kVoxThreads) k1_voxelize_kernel(const float4* 
     if (bin < span) for (int w = 0; w < n_cnt_warps; ++w) tot += whist[(size_t)w * span_cap + bin];
     const bool keep = tot > 0u && (long long)tot > (long long)min_points;
     unsigned long long total;
-    const unsigned long long ex = carry + block_scan_excl((unsigned long long)tot | ((unsigned long long)(keep ? 1u : 0u) << 32), warp_sums, &total);
+    const unsigned long long ex = carry + block_scan_excl((unsigned long long)(keep ? tot : 0u) | ((unsigned long long)(keep ? 1u : 0u) << 32), warp_sums, &total);
     if (bin < span) {
       bin_start[bin] = (uint32_t)ex;
       const uint32_t ci = (uint32_t)(ex >> 32);
@@ -269,7 +255,7 @@ __global__ void __launch_bounds__(kVoxThreads) k1_voxelize_kernel(const float4* 
   __syncthreads();
   const uint32_t n_keep = min((uint32_t)(carry >> 32), cell_cap);
 
-  // ---- phase 3: stable scatter of the points (x, y, intensity) of kept cells into cell-major, scan-ordered runs ----
+  // ---- phase 3: stable scatter of the points (x, y, intensity) of kept cells into cell-major, scan-ordered runs in shared memory ----
   if (warp < n_cnt_warps) {
     const uint32_t s0 = warp * slice, s1 = min(n, s0 + slice);
     unsigned short* h = whist + (size_t)warp * span_cap;
@@ -284,19 +270,22 @@ __global__ void __launch_bounds__(kVoxThreads) k1_voxelize_kernel(const float4* 
       off = __shfl_sync(0xffffffffu, off, leader);
       if (act && bin_keep[bin] != kNotKept) {
         const float4 p = __ldg(pts + p0 + e);
-        sorted[p0 + bin_start[bin] + off + __popc(peers & ((1u << lane) - 1u))] = make_float4(p.x, p.y, p.w, 0.f);
+        const uint32_t at = bin_start[bin] + off + __popc(peers & ((1u << lane) - 1u));
+        sx[at] = p.x; sy[at] = p.y; si[at] = p.w;
       }
       __syncwarp();
     }
   }
   __syncthreads();
 
+  if (tid == 0) cell_count[b] = n_keep;
   // ---- phase 4: one thread per kept cell: sequential float32 statistics, slot table ----
   for (uint32_t ci = tid; ci < n_keep; ci += n_thr) {
     const uint32_t bin = (uint32_t)(labels_out[(size_t)b * cell_cap + ci] - lab_min);
     const uint32_t cnt = npts_out[(size_t)b * cell_cap + ci];
+    const uint32_t at = bin_start[bin];
     CellOut o;
-    cell_stats_thread(sorted + p0 + bin_start[bin], cnt, o);
+    cell_stats_thread(sx + at, sy + at, si + at, cnt, o);
     const uint32_t s = coord_to_index(geom, o.mu[0], o.mu[1]);
     float4* dst = cells_out + 3 * ((size_t)b * cell_cap + ci);
     dst[0] = make_float4(o.mu[0], o.mu[1], o.mu[2], o.cov[0]);
@@ -306,7 +295,6 @@ __global__ void __launch_bounds__(kVoxThreads) k1_voxelize_kernel(const float4* 
     if (s < geom.n_slots) atomicMax(&slot[s], (int32_t)ci);   // "later cluster wins" == largest kept index
     else status[b] = VOX_OUT_OF_MAP;
   }
-  if (tid == 0) cell_count[b] = n_keep;
 }
 
 __global__ void k1_compact_cells_kernel(const float4* __restrict__ cells_p, const uint32_t* __restrict__ npts_p, const int32_t* __restrict__ labels_p,
@@ -529,7 +517,7 @@ __global__ void merge_maps_kernel(const float4* __restrict__ f_cells, const uint
 cudaError_t launch_voxelize(const float4* d_pts, const uint32_t* d_scan_off, uint32_t n_scans, uint32_t max_pts_per_scan,
                             const randt_grid_params& gp, const MapGeomDev& geom, uint32_t cell_cap_per_scan, float4* d_cells_p,
                             uint32_t* d_npts_p, int32_t* d_labels_p, uint32_t* d_cell_count, int32_t* d_slot, int32_t* d_labels_scratch,
-                            float4* d_sorted, int* d_status, cudaStream_t s, int* n_launches) {
+                            int* d_status, cudaStream_t s, int* n_launches) {
   if (n_scans == 0) return cudaSuccess;
   const int row = static_cast<int>(sqrt((double)(size_t)gp.n_clusters));
   if (row <= 0) return cudaErrorInvalidValue;
@@ -538,20 +526,26 @@ cudaError_t launch_voxelize(const float4* d_pts, const uint32_t* d_scan_off, uin
   const long long bound = (long long)(row + 4) * (long long)(row + 4);
   uint32_t span_cap = (uint32_t)((bound + 255) / 256 * 256);
   const size_t smem_max = 220 * 1024;
-  if ((size_t)span_cap * (8 + 2) > smem_max) span_cap = (uint32_t)(smem_max / 10 / 256 * 256);
-  int n_cnt_warps = (int)((smem_max - (size_t)span_cap * 8) / ((size_t)span_cap * 2));
-  if (n_cnt_warps > kVoxCountWarps) n_cnt_warps = kVoxCountWarps;
-  if (n_cnt_warps < 1) n_cnt_warps = 1;
-  // small scans do not need all counting warps (fewer histograms to clear and fold)
-  while (n_cnt_warps > 1 && (max_pts_per_scan + n_cnt_warps - 1) / n_cnt_warps < 256) n_cnt_warps >>= 1;
-  const size_t smem = (size_t)span_cap * 8 + (size_t)n_cnt_warps * span_cap * 2;
+  const uint32_t pt_cap = (max_pts_per_scan + 31u) / 32u * 32u;        // the kept points of a scan are staged in shared memory
+  const size_t fixed = (size_t)pt_cap * 12;
+  if (fixed + 1024 > smem_max) return cudaErrorInvalidValue;           // > 18 k points in one scan (randt_voxelize refuses such scans)
+  if ((size_t)span_cap * (8 + 2) + fixed > smem_max) span_cap = (uint32_t)((smem_max - fixed) / 10 / 256 * 256);
+  if (span_cap == 0) return cudaErrorInvalidValue;
+  // counting warps: each owns a contiguous slice of the scan and a 16-bit histogram.  As many as leave room for a second CTA on the
+  // SM when the batch has more scans than SMs; small scans do not need all of them (fewer histograms to clear and fold).
+  const size_t budget = n_scans > (uint32_t)kSmCount ? (size_t)110 * 1024 : smem_max;
+  int n_cnt_warps = kVoxCountWarps;
+  while (n_cnt_warps > 1 && ((size_t)span_cap * 8 + (size_t)n_cnt_warps * span_cap * 2 + fixed > budget ||
+                             (max_pts_per_scan + n_cnt_warps - 1) / n_cnt_warps < 256)) n_cnt_warps >>= 1;
+  const size_t smem = (size_t)span_cap * 8 + (size_t)n_cnt_warps * span_cap * 2 + fixed;
+  if (smem > smem_max) return cudaErrorInvalidValue;
   cudaError_t e = cudaSuccess;
   if (smem > 48u * 1024u) e = cudaFuncSetAttribute(k1_voxelize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int threads = n_scans > (uint32_t)kSmCount ? 512 : kVoxThreads;     // a batch: two scans per SM; a lone scan: all 32 warps
   k1_voxelize_kernel<<<n_scans, threads, smem, s>>>(d_pts, d_scan_off, row, label_res, gp.min_points, geom, span_cap, n_cnt_warps,
-                                                        cell_cap_per_scan, d_cells_p, d_npts_p, d_labels_p, d_cell_count, d_slot,
-                                                        d_labels_scratch, d_sorted, d_status);
+                                                    cell_cap_per_scan, d_cells_p, d_npts_p, d_labels_p, d_cell_count, d_slot,
+                                                    d_labels_scratch, pt_cap, d_status);
   if (n_launches) *n_launches += 1;
   return cudaGetLastError();
 }
