@@ -280,7 +280,6 @@ def run_configs(args, ctx, capi, stream, rank, world, local, barrier):
     # ---- c2: configs[2] shape with the reference's SE(2) + intensity functor and kNN pair list ----
     if args.c2_problems > 0:
         prob, poses, host = W.build_c2(ctx, capi, args.c2_problems)
-        host["F"].close(); host["M"].close()
         S, Pn = prob.n_segments, prob.n_pairs
         loss = W.c2_loss(capi)
         d_poses = torch.from_numpy(poses).to(dev); d_out = torch.zeros((S, capi.FUSED_STRIDE), dtype=torch.float64, device=dev)
@@ -309,6 +308,34 @@ def run_configs(args, ctx, capi, stream, rank, world, local, barrier):
             fo = oracle.fused(0, host["cells_m"], host["cells_f"], host["pm"][a:b], host["pf"][a:b], poses[0], (loss.kind, loss.scale, loss.alpha, loss.mu, loss.weight), True)
             g = capi.unpack_fused(d_out[0].cpu().numpy())
             rec["gpu_vs_oracle_max_rel_err_first_problem"] = float(max(np.max(np.abs(g["H"] - fo["H"])) / np.max(np.abs(fo["H"])), abs(g["cost"] - fo["cost"]) / abs(fo["cost"])))
+        # all-pairs variant (K8): every moving cell against every fixed cell of its map pair, N_m x N_f = 16 M pairs per problem; inputs are
+        # cache resident, so this one is bound by the fp64 pipe: reported in pairs/s and fp64 flop/s (~200 flop per pair closed form)
+        n_ap = min(S, args.c2_allpairs_problems)
+        if n_ap > 0:
+            gp = capi.grid_params(P.C3)
+            nm_, nf_ = int(host["m_off"][1]), int(host["f_off"][1])
+            Fa = ctx.map_upload(host["cells_f"][:n_ap * nf_], host["f_off"][:n_ap + 1], gp); Ma = ctx.map_upload(host["cells_m"][:n_ap * nm_], host["m_off"][:n_ap + 1], gp)
+            d_oa = torch.zeros((n_ap, capi.FUSED_STRIDE), dtype=torch.float64, device=dev)
+            for _ in range(2):
+                Fa.eval_allpairs_dev(Ma, d_poses.data_ptr(), d_oa.data_ptr(), loss)
+            barrier()
+            n_rep = 5
+            e0.record(stream)
+            for _ in range(n_rep):
+                Fa.eval_allpairs_dev(Ma, d_poses.data_ptr(), d_oa.data_ptr(), loss)
+            e1.record(stream)
+            barrier()
+            ms_ap = e0.elapsed_time(e1) / n_rep
+            pairs_ap = float(n_ap) * nm_ * nf_
+            FLOP_PER_PAIR = 2 * 62 + 36          # measured op mix of the per-pair closed form: ~62 DFMA (2 flop) + ~36 DMUL / DADD
+            rec["all_pairs"] = {"workload": "%d problems x (%d moving x %d fixed cells) = %.3g pairs per step, no neighbour search, no window" % (n_ap, nm_, nf_, pairs_ap),
+                                "bound": "fp64 pipe (inputs cache resident: %.2f MB of cells per problem)" % (48 * (nm_ + nf_) / 1e6),
+                                "ms_per_step": ms_ap, "pairs_per_s_per_gpu": pairs_ap / (ms_ap * 1e-3), "fp64_flops_per_pair": FLOP_PER_PAIR,
+                                "fp64_tflops": pairs_ap * FLOP_PER_PAIR / (ms_ap * 1e-3) / 1e12, "pairs_used_first_problem": float(d_oa[0, capi.FUSED_STRIDE - 1].item()),
+                                "finite": bool(torch.isfinite(d_oa).all().item())}
+            Fa.close(); Ma.close()
+            del d_oa
+        host["F"].close(); host["M"].close()
         prob.close()
         del d_poses, d_out
         out["c2"] = rec
@@ -363,6 +390,59 @@ def run_configs(args, ctx, capi, stream, rank, world, local, barrier):
     return out
 
 
+def pin_rank_to_local_cores(local, world):
+    """One process per GPU on one host: give every rank its own slice of the cores its GPU is attached to (nvidia-smi topo: CPU affinity
+    of the GPU), so that the rank's caller thread, its copy-completion waits and torch's helper threads do not migrate across NUMA nodes
+    or pile onto the cores of another rank.  -> description for the bench line (None when nothing was changed)."""
+    if world <= 1 or not hasattr(os, "sched_setaffinity"):
+        return None
+    try:
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+    except (OSError, subprocess.SubprocessError):
+        return None
+    aff = {}
+    for ln in out.splitlines():
+        f = ln.split()
+        if f and f[0].startswith("GPU") and f[0][3:].isdigit():
+            spec = next((x for x in f[1:] if x[0].isdigit() and ("-" in x or "," in x) and not x.endswith("%")), None)
+            if spec:
+                cpus = []
+                for part in spec.split(","):
+                    a, _, b = part.partition("-")
+                    cpus.extend(range(int(a), int(b or a) + 1))
+                aff[int(f[0][3:])] = cpus
+    if local not in aff:
+        return None
+    allowed = sorted(set(aff[local]) & set(os.sched_getaffinity(0)))
+    peers = sorted(g for g in aff if g < world and aff[g] == aff[local])
+    if not allowed or local not in peers:
+        return None
+    per = max(1, len(allowed) // len(peers))
+    i = peers.index(local)
+    mine = allowed[i * per:(i + 1) * per] or allowed
+    try:
+        os.sched_setaffinity(0, mine)
+    except OSError:
+        return None
+    return {"gpu_cpu_affinity": "%d-%d" % (aff[local][0], aff[local][-1]), "ranks_sharing_it": len(peers), "cores_of_this_rank": "%d-%d" % (mine[0], mine[-1])}
+
+
+def d2h_bandwidth_probe(torch, dist, local, world, barrier, mb=64, reps=8):
+    """every rank copies `mb` MB device -> pinned host at the same time; -> this rank's GB/s (the ranks' sum is what the host side sustains)"""
+    d = torch.empty(mb * 1024 * 1024, dtype=torch.uint8, device="cuda:%d" % local)
+    h = torch.empty(mb * 1024 * 1024, dtype=torch.uint8).pin_memory()
+    h.copy_(d, non_blocking=True); torch.cuda.synchronize()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        h.copy_(d, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    return mb * 1024 * 1024 * reps / (e0.elapsed_time(e1) * 1e-3) / 1e9
+
+
 _OUT = None
 
 
@@ -393,6 +473,7 @@ def main():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--no-configs", action="store_true", help="skip the configs leg (c0, c2, c3, c4 sub-records)")
     ap.add_argument("--c2-problems", type=int, default=384, help="configs[2]-shaped problems (2 k x 8 k cells) evaluated per step in the c2 sub-record")
+    ap.add_argument("--c2-allpairs-problems", type=int, default=16, help="problems of the c2 all-pairs variant (16 M pairs each)")
     ap.add_argument("--c3-batch", type=int, default=256, help="registrations of the literal configs[3] batch (sharded over the ranks)")
     ap.add_argument("--replay-scans", type=int, default=8609, help="scans of the configs[4] replay (Oxford sequence length); rank 0 only")
     ap.add_argument("--replay-oracle-scans", type=int, default=300, help="prefix of the drive the CPU oracle chain replays for comparison")
@@ -416,6 +497,7 @@ def main():
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    pinned_to = pin_rank_to_local_cores(local, world)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -713,11 +795,14 @@ def main():
             assert table.shape[0] == world * S and not np.isnan(table[:, 4]).any()
     per_rank = None
     if world > 1:
-        mine = torch.tensor([ms, e2e_s * 1e3, reg["ms_per_batch"] if reg else 0.0], dtype=torch.float64, device="cuda:%d" % local)
+        d2h_gbs = d2h_bandwidth_probe(torch, dist, local, world, barrier)
+        mine = torch.tensor([ms, e2e_s * 1e3, reg["ms_per_batch"] if reg else 0.0, d2h_gbs], dtype=torch.float64, device="cuda:%d" % local)
         gathered = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(gathered, mine)
         per_rank = {"ms_per_step": [float(g[0]) / args.steps for g in gathered], "e2e_ms_per_step": [float(g[1]) / args.steps for g in gathered],
-                    "registrations_ms_per_batch": [float(g[2]) for g in gathered]}
+                    "registrations_ms_per_batch": [float(g[2]) for g in gathered],
+                    "concurrent_d2h_gbs": [float(g[3]) for g in gathered], "concurrent_d2h_gbs_sum": float(sum(float(g[3]) for g in gathered)),
+                    "cpu_pinning_rank0": pinned_to}
     ms_all, e2e_ms_all, reg_ms_all, reg_e2e_ms_all, e2e_sync_ms_all = (float(t_ms[i]) for i in range(5))
     seg_all = float(tot[1])
     pairs_all = float(tot[0])

@@ -235,6 +235,16 @@ RANDT_API uint64_t randt_ctx_async_count(const randt_ctx* ctx);
 RANDT_API int randt_ctx_wait_async(randt_ctx* ctx, uint64_t ticket);
 RANDT_API int randt_eval_fused_dev(randt_ctx* ctx, const randt_problem* p, int variant, const double* d_poses, const randt_loss* loss,
                                    const double* d_mu_per_seg, int want_jac, double* d_out);
+/* All-pairs evaluation (K8): every moving cell of map b against every fixed cell of map b — optionally only pairs whose fixed mean lies
+ * within `window` metres (L-infinity) of the transformed moving mean; window <= 0: all N_m x N_f pairs — with the same functor, loss
+ * corrector and per-pose reduction as randt_eval_fused (record layout RANDT_FUSED_*, entry n = pairs used).  The reference keeps only the k
+ * nearest fixed cells per moving cell (Matcher::addNDTFactor, ndt_matcher.cpp:183-288); this is the "every overlapping submap cell" reading
+ * of the cost (BASELINE.json north_star), a cache-resident, fp64-bound workload.  poses [n_maps][np], out [n_maps][24]. */
+RANDT_API int randt_eval_allpairs(randt_ctx* ctx, const randt_map* fixed, const randt_map* moving, int variant, const double* poses,
+                                  const randt_loss* loss, double window, double* out);
+RANDT_API int randt_eval_allpairs_dev(randt_ctx* ctx, const randt_map* fixed, const randt_map* moving, int variant, const double* d_poses,
+                                      const randt_loss* loss, double window, double* d_out);
+
 /* Cost of ONE segment's pair list at many candidate poses (the inner loop of Matcher::estimateTransformGlobalBNB,
  * ndt_matcher.cpp:560-576): cost[i] = sum over the pairs of segment `seg` of 0.5 * rho(r^2) at poses[i]. */
 RANDT_API int randt_sweep_costs(randt_ctx* ctx, const randt_problem* p, uint32_t seg, int variant, const double* poses, uint32_t n_poses,

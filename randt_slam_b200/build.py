@@ -23,6 +23,7 @@ UNITS = {
     "k3_pair_eval.cu": [],
     "k4_lm_step.cu": [],
     "k7_solve.cu": [],
+    "k8_allpairs.cu": [],
     "k2_associate.cu": ["-fmad=false"],
     "k1_voxelize.cu": ["-fmad=false"],
     "k5_cs_divergence.cu": ["-fmad=false"],

@@ -115,6 +115,8 @@ _SIGS = {
     "randt_associate": (_i, [_vp, _vp, _vp, _vp, _i, _i, C.POINTER(_vp)]),
     "randt_problem_create": (_i, [_vp, _vp, _u32, _vp, _u32, _vp, _vp, _u32, _vp, _u32, C.POINTER(_vp)]),
     "randt_problem_info": (_i, [_vp, C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_u32)]),
+    "randt_eval_allpairs": (_i, [_vp, _vp, _vp, _i, _vp, _vp, C.c_double, _vp]),
+    "randt_eval_allpairs_dev": (_i, [_vp, _vp, _vp, _i, _vp, _vp, C.c_double, _vp]),
     "randt_problem_layout": (_i, [_vp, C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_u32)]),
     "randt_problem_download": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "randt_problem_download_cells": (_i, [_vp, _vp, _vp, _vp]),
@@ -333,6 +335,20 @@ class Map:
 
     def merge(self, moving):
         self.ctx._check(lib().randt_map_merge(self.ctx._h, self._h, moving._h))
+
+    def eval_allpairs(self, moving, poses, loss=None, window=0.0, variant=VAR_SE2_INTENSITY):
+        """K8: self = fixed maps; every moving cell against every fixed cell (within `window` m, <= 0: all) -> fused records [B, 24]"""
+        B = self.info()[0]
+        npar = 4 if variant <= 1 else 3
+        poses = _f64(poses).reshape(B, npar)
+        out = np.zeros((B, FUSED_STRIDE), np.float64)
+        lp = C.byref(loss) if loss is not None else None
+        self.ctx._check(lib().randt_eval_allpairs(self.ctx._h, self._h, moving._h, int(variant), _ptr(poses), lp, float(window), _ptr(out)))
+        return out
+
+    def eval_allpairs_dev(self, moving, d_poses, d_out, loss=None, window=0.0, variant=VAR_SE2_INTENSITY):
+        lp = C.byref(loss) if loss is not None else None
+        self.ctx._check(lib().randt_eval_allpairs_dev(self.ctx._h, self._h, moving._h, int(variant), C.c_void_p(d_poses), lp, float(window), C.c_void_p(d_out)))
 
     def cs_divergence(self, moving):
         """Map::calculateCSDivergence for every map pair of the batch -> float64 [B]"""

@@ -1013,6 +1013,57 @@ int randt_ctx_wait_async(randt_ctx* ctx, uint64_t ticket) {
   return RANDT_OK;
 }
 
+// K8: all pairs of (moving cell, fixed cell) of every map pair of the batch, within `window` metres (L-infinity, <= 0: unbounded) of
+// the transformed moving mean.  d_poses [B][np], d_out [B][RANDT_FUSED_STRIDE] on the device.
+int randt_eval_allpairs_dev(randt_ctx* ctx, const randt_map* F, const randt_map* M, int variant, const double* d_poses, const randt_loss* loss,
+                            double window, double* d_out) {
+  if (!ctx || !F || !M || !d_poses || !d_out) return fail(ctx, RANDT_E_INVALID, "randt_eval_allpairs: null argument");
+  if (check_variant(ctx, variant)) return RANDT_E_INVALID;
+  if (F->B != M->B) return fail(ctx, RANDT_E_INVALID, "randt_eval_allpairs: fixed and moving batches differ in size");
+  LossParams lp;
+  if (int rc = make_loss(ctx, loss, &lp)) return rc;
+  CK(cudaSetDevice(ctx->device));
+  StreamScope scope__(ctx->stream);
+  const uint32_t B = F->B;
+  if (B == 0) return RANDT_OK;
+  uint32_t tm, tf;
+  allpairs_tiles(M->max_per_map, F->max_per_map, &tm, &tf);
+  double* d_part = nullptr; uint32_t* d_tick = nullptr;
+  int nl = 0;
+  cudaError_t e = dev_alloc(&d_part, (size_t)B * tm * tf * kMaxAcc);
+  if (e == cudaSuccess) e = dev_alloc(&d_tick, B);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_tick, 0, (size_t)B * sizeof(uint32_t), ctx->stream);
+  if (e == cudaSuccess) e = launch_allpairs(F->cells, F->cell_off, F->max_per_map, M->cells, M->cell_off, M->max_per_map, B, variant, d_poses, lp, window,
+                                            d_part, d_tick, d_out, ctx->d_bad, ctx->stream, &nl);
+  dev_free(d_part); dev_free(d_tick);
+  if (e != cudaSuccess) return fail(ctx, RANDT_E_CUDA, "randt_eval_allpairs", e);
+  ctx->launches += nl;
+  return RANDT_OK;
+}
+
+int randt_eval_allpairs(randt_ctx* ctx, const randt_map* F, const randt_map* M, int variant, const double* poses, const randt_loss* loss,
+                        double window, double* out) {
+  if (!ctx || !F || !M || !poses || !out) return fail(ctx, RANDT_E_INVALID, "randt_eval_allpairs: null argument");
+  if (check_variant(ctx, variant)) return RANDT_E_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  StreamScope scope__(ctx->stream);
+  const uint32_t B = F->B;
+  if (B == 0) return RANDT_OK;
+  const int np = np_of(variant);
+  double *d_p = nullptr, *d_o = nullptr;
+  CK(dev_alloc(&d_p, (size_t)B * np));
+  cudaError_t e = dev_alloc(&d_o, (size_t)B * RANDT_FUSED_STRIDE);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_p, poses, (size_t)B * np * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+  int rc = RANDT_OK;
+  if (e == cudaSuccess) rc = randt_eval_allpairs_dev(ctx, F, M, variant, d_p, loss, window, d_o);
+  if (e == cudaSuccess && rc == RANDT_OK) e = cudaMemcpyAsync(out, d_o, (size_t)B * RANDT_FUSED_STRIDE * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess && rc == RANDT_OK) e = cudaStreamSynchronize(ctx->stream);
+  dev_free(d_p); dev_free(d_o);
+  if (rc != RANDT_OK) return rc;
+  if (e != cudaSuccess) return fail(ctx, RANDT_E_CUDA, "randt_eval_allpairs", e);
+  return RANDT_OK;
+}
+
 int randt_sweep_costs(randt_ctx* ctx, const randt_problem* cp, uint32_t seg, int variant, const double* poses, uint32_t n_poses,
                       const randt_loss* loss, double* cost) {
   if (!ctx || !cp || !poses || !cost) return fail(ctx, RANDT_E_INVALID, "randt_sweep_costs: null argument");

@@ -176,6 +176,12 @@ cudaError_t launch_solve_persistent(const DeviceProblem& p, const SolveLayout& L
                                     const randt_solver_options& o, const double* d_poses0, double* d_poses_out, double* d_result,
                                     unsigned long long* d_bad, cudaStream_t s, int* n_launches);
 
+// k8_allpairs.cu — every moving cell against every fixed cell (optionally within an L-infinity window), fused normal equations per map pair
+void allpairs_tiles(uint32_t max_m, uint32_t max_f, uint32_t* tiles_m, uint32_t* tiles_f);
+cudaError_t launch_allpairs(const float4* cells_f, const uint32_t* off_f, uint32_t max_f, const float4* cells_m, const uint32_t* off_m, uint32_t max_m,
+                            uint32_t n_maps, int variant, const double* d_poses, const LossParams& lp, double window, double* d_partials,
+                            uint32_t* d_tickets, double* d_out, unsigned long long* d_bad, cudaStream_t s, int* n_launches);
+
 // k5_cs_divergence.cu
 cudaError_t launch_cs_divergence(const float4* cells_f, const uint32_t* off_f, const float4* cells_m, const uint32_t* off_m, uint32_t n_maps,
                                  double* d_partials, uint32_t* d_tickets, double* d_out, cudaStream_t s, int* n_launches);
