@@ -300,6 +300,11 @@ RANDT_API int randt_register_batch(randt_ctx* ctx, const randt_problem* p, int v
                                    const randt_solver_options* opt, double* result);
 RANDT_API int randt_register_batch_dev(randt_ctx* ctx, const randt_problem* p, int variant, double* d_poses, const randt_loss* loss,
                                        const randt_solver_options* opt, double* d_result);
+/* randt_register_batch with one ScaledLoss weight per registration (host [n_segments]; NULL = loss->weight for all): the odometry weight
+ * ndt_weight / (n_cells k) depends on the moving scan's own cell count (ndt_matcher.cpp:367,392), so a batch of scans solved together
+ * gives each scan exactly the weight it would get alone.  Needs registrations of <= 1024 pairs (the persistent solver). */
+RANDT_API int randt_register_batch_weighted(randt_ctx* ctx, const randt_problem* p, int variant, double* poses, const randt_loss* loss,
+                                            const double* weight_per_seg, const randt_solver_options* opt, double* result);
 
 #ifdef __cplusplus
 }

@@ -115,6 +115,7 @@ _SIGS = {
     "randt_associate": (_i, [_vp, _vp, _vp, _vp, _i, _i, C.POINTER(_vp)]),
     "randt_problem_create": (_i, [_vp, _vp, _u32, _vp, _u32, _vp, _vp, _u32, _vp, _u32, C.POINTER(_vp)]),
     "randt_problem_info": (_i, [_vp, C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_u32)]),
+    "randt_register_batch_weighted": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "randt_eval_allpairs": (_i, [_vp, _vp, _vp, _i, _vp, _vp, C.c_double, _vp]),
     "randt_eval_allpairs_dev": (_i, [_vp, _vp, _vp, _i, _vp, _vp, C.c_double, _vp]),
     "randt_problem_layout": (_i, [_vp, C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_u32)]),
@@ -427,13 +428,17 @@ class Problem:
     def eval_emit_dev(self, d_poses, d_r, d_J, variant=VAR_SE2_INTENSITY):
         self.ctx._check(lib().randt_eval_emit_dev(self.ctx._h, self._h, int(variant), _ptr(d_poses), _ptr(d_r), _ptr(d_J)))
 
-    def register_batch(self, poses, loss, opt, variant=VAR_SE2_INTENSITY):
-        """GNC + LM for every segment at once -> (poses [S, np], result [S, REG_STRIDE])"""
+    def register_batch(self, poses, loss, opt, variant=VAR_SE2_INTENSITY, weights=None):
+        """GNC + LM for every segment at once -> (poses [S, np], result [S, REG_STRIDE]); weights: one ScaledLoss weight per segment"""
         npar = 4 if variant <= 1 else 3
         poses = _f64(poses).reshape(self.n_segments, npar).copy()
         result = np.zeros((self.n_segments, REG_STRIDE), np.float64)
         lp = C.byref(loss) if loss is not None else None
-        self.ctx._check(lib().randt_register_batch(self.ctx._h, self._h, int(variant), _ptr(poses), lp, C.byref(opt), _ptr(result)))
+        if weights is None:
+            self.ctx._check(lib().randt_register_batch(self.ctx._h, self._h, int(variant), _ptr(poses), lp, C.byref(opt), _ptr(result)))
+        else:
+            w = _f64(weights).reshape(self.n_segments)
+            self.ctx._check(lib().randt_register_batch_weighted(self.ctx._h, self._h, int(variant), _ptr(poses), lp, _ptr(w), C.byref(opt), _ptr(result)))
         return poses, result
 
     def register_batch_dev(self, d_poses, d_result, loss, opt, variant=VAR_SE2_INTENSITY):

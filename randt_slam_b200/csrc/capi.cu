@@ -25,6 +25,7 @@ struct StreamRef {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own = false;
+  cudaMemPool_t pool = nullptr;              // this context's own stream-ordered pool (release threshold: never trim)
   uint32_t* h_n_active = nullptr;            // pinned [2]
   cudaEvent_t ev[2] = {nullptr, nullptr};
   // input pipeline of randt_eval_fused_async: a copy stream and a two-slot device ring for the poses of the calls in flight
@@ -53,6 +54,7 @@ struct StreamRef {
     if (h_n_active) cudaFreeHost(h_n_active);
     if (ev[0]) cudaEventDestroy(ev[0]);
     if (ev[1]) cudaEventDestroy(ev[1]);
+    if (pool) cudaMemPoolDestroy(pool);      // every map / problem that allocated from it held a reference to this object
     if (own && stream) cudaStreamDestroy(stream);
   }
 };
@@ -73,6 +75,7 @@ struct randt_map {
   randt_grid_params gp{};
   MapGeomDev geom{};
   uint32_t B = 0, n_cells = 0, max_per_map = 0;
+  bool has_npts = true;          // false: uploaded without point counts (cannot take part in a merge)
   float4* cells = nullptr;       // [n_cells][3]
   uint32_t* npts = nullptr;      // [n_cells]
   int32_t* labels = nullptr;     // [n_cells] voxel labels (voxelised maps only)
@@ -106,6 +109,7 @@ struct randt_problem {
   // scratch for the host-pointer entry points
   double *d_poses = nullptr, *d_out = nullptr, *d_mu = nullptr, *d_r = nullptr, *d_J = nullptr;
   double* d_sweep = nullptr; size_t sweep_cap = 0;
+  double* lm_weight = nullptr;   // [S] per-registration loss weights (randt_register_batch_weighted)
   // workspace of the batched solver (randt_register_batch), allocated on first use
   LmState* lm_state = nullptr; double *lm_eval_pose = nullptr, *lm_mu = nullptr, *lm_rec = nullptr, *lm_poses = nullptr, *lm_result = nullptr;
   uint32_t *lm_active = nullptr, *lm_n_active = nullptr;
@@ -135,15 +139,17 @@ int fail(randt_ctx* ctx, int code, const char* what, cudaError_t e = cudaSuccess
 // calls (voxelise, associate, merge) are made of.  Outside a call (the destroy functions) plain cudaFree is used, which is valid
 // for pool memory as well.
 thread_local cudaStream_t t_stream = nullptr;
+thread_local cudaMemPool_t t_pool = nullptr;
 thread_local bool t_in_call = false;
 struct StreamScope {
-  cudaStream_t prev; bool prev_in;
-  explicit StreamScope(cudaStream_t s) : prev(t_stream), prev_in(t_in_call) { t_stream = s; t_in_call = true; }
-  ~StreamScope() { t_stream = prev; t_in_call = prev_in; }
+  cudaStream_t prev; cudaMemPool_t prev_pool; bool prev_in;
+  StreamScope(cudaStream_t s, cudaMemPool_t pool) : prev(t_stream), prev_pool(t_pool), prev_in(t_in_call) { t_stream = s; t_pool = pool; t_in_call = true; }
+  ~StreamScope() { t_stream = prev; t_pool = prev_pool; t_in_call = prev_in; }
 };
 template <typename T>
 cudaError_t dev_alloc(T** p, size_t n) {
   *p = nullptr; if (n == 0) n = 1;
+  if (t_in_call && t_pool) return cudaMallocFromPoolAsync(reinterpret_cast<void**>(p), n * sizeof(T), t_pool, t_stream);
   if (t_in_call) return cudaMallocAsync(reinterpret_cast<void**>(p), n * sizeof(T), t_stream);
   return cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T));
 }
@@ -165,7 +171,7 @@ void free_problem(randt_problem* p) {
   if (!p) return;
   dev_free(p->cells_m); dev_free(p->cells_f); dev_free(p->pairs); dev_free(p->duos); dev_free(p->duo_recs); dev_free(p->duo_p0); dev_free(p->duo_overflow); dev_free(p->chunks); dev_free(p->warp_off); dev_free(p->chunks_full); dev_free(p->warp_off_full); dev_free(p->seg_first_tile); dev_free(p->seg_off); dev_free(p->seg_duo_off); dev_free(p->rec_of_tile); dev_free(p->solve_items); dev_free(p->solve_counter);
   dev_free(p->partials); dev_free(p->seg_counters); dev_free(p->d_poses); dev_free(p->d_out); dev_free(p->d_mu); dev_free(p->d_r);
-  dev_free(p->d_J); dev_free(p->d_sweep);
+  dev_free(p->d_J); dev_free(p->d_sweep); dev_free(p->lm_weight);
   dev_free(p->lm_state); dev_free(p->lm_eval_pose); dev_free(p->lm_mu); dev_free(p->lm_rec); dev_free(p->lm_poses); dev_free(p->lm_result);
   dev_free(p->lm_active); dev_free(p->lm_n_active);
   dev_free(p->lm_chunks); dev_free(p->lm_flags); dev_free(p->lm_scan); dev_free(p->lm_bs); dev_free(p->lm_warp_off);
@@ -311,10 +317,14 @@ int randt_ctx_create(int device, void* stream, randt_ctx** out) {
     }
   }
   if (e == cudaSuccess) {
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    // a pool of this context's own (the device's default pool and its release threshold belong to the host application)
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned; props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice; props.location.id = device;
+    e = cudaMemPoolCreate(&ctx->sref->pool, &props);
+    if (e == cudaSuccess) {
       unsigned long long keep = ~0ull;     // never trim: the per-scan calls reuse the same few buffers
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      e = cudaMemPoolSetAttribute(ctx->sref->pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
   }
   if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_bad), sizeof(unsigned long long));
@@ -375,7 +385,7 @@ int randt_voxelize(randt_ctx* ctx, const float* pts4, const uint32_t* scan_off, 
     if (scan_off[b + 1] >= scan_off[b] && scan_off[b + 1] - scan_off[b] > 16384u)
       return fail(ctx, RANDT_E_CAPACITY, "randt_voxelize: more than 16384 points in one scan (a scan is sorted in shared memory; the shipped sensors deliver ~3-5 k filtered points)");
   CK(cudaSetDevice(ctx->device));
-  StreamScope scope__(ctx->stream);
+  StreamScope scope__(ctx->stream, ctx->sref->pool);
   const uint32_t B = n_scans;
   if (scan_off[0] != 0) return fail(ctx, RANDT_E_INVALID, "randt_voxelize: scan_off[0] must be 0");
   const uint32_t n_pts = scan_off[B];
@@ -447,7 +457,7 @@ int randt_filter_scan(randt_ctx* ctx, const float* raw4, uint32_t n_az, uint32_t
   if (!ctx || !fp || !n_out || (!raw4 && n_az && n_bins) || (!out4 && cap)) return fail(ctx, RANDT_E_INVALID, "randt_filter_scan: null argument");
   if ((unsigned long long)n_az * n_bins > 0x7fffffffull) return fail(ctx, RANDT_E_CAPACITY, "randt_filter_scan: scan too large");
   CK(cudaSetDevice(ctx->device));
-  StreamScope scope__(ctx->stream);
+  StreamScope scope__(ctx->stream, ctx->sref->pool);
   *n_out = 0;
   const size_t n = (size_t)n_az * n_bins;
   float4 *d_raw = nullptr, *d_out = nullptr; uint32_t *d_peak = nullptr, *d_n = nullptr; float* d_angle = nullptr; int* d_status = nullptr;
@@ -486,7 +496,7 @@ int randt_filter_scans(randt_ctx* ctx, const float* raw4, uint32_t n_scans, uint
   if ((unsigned long long)n_az * n_bins > 0x7fffffffull) return fail(ctx, RANDT_E_CAPACITY, "randt_filter_scans: scan too large");
   if ((unsigned long long)n_scans * n_az > 0x7fffffffull || n_scans > 65535u) return fail(ctx, RANDT_E_CAPACITY, "randt_filter_scans: too many scans per call");
   CK(cudaSetDevice(ctx->device));
-  StreamScope scope__(ctx->stream);
+  StreamScope scope__(ctx->stream, ctx->sref->pool);
   for (uint32_t i = 0; i <= n_scans; ++i) scan_off[i] = 0;
   if (n_scans == 0) return RANDT_OK;
   const size_t n = (size_t)n_scans * n_az * n_bins;
@@ -534,7 +544,7 @@ int randt_map_upload(randt_ctx* ctx, const float* cells, const uint32_t* npts, c
   *out = nullptr;
   if (gp->size_x <= 0 || gp->size_y <= 0 || !(gp->resolution > 0)) return fail(ctx, RANDT_E_INVALID, "randt_map_upload: bad map geometry");
   CK(cudaSetDevice(ctx->device));
-  StreamScope scope__(ctx->stream);
+  StreamScope scope__(ctx->stream, ctx->sref->pool);
   randt_map* m = new (std::nothrow) randt_map();
   if (!m) return RANDT_E_NOMEM;
   m->device = ctx->device; m->sref = ctx->sref; m->gp = *gp; m->geom = make_geom(*gp); m->B = n_maps;
@@ -551,7 +561,7 @@ int randt_map_upload(randt_ctx* ctx, const float* cells, const uint32_t* npts, c
   CKM(dev_alloc(&m->slot, (size_t)n_maps * m->geom.n_slots));
   if (m->n_cells) CKM(cudaMemcpyAsync(m->cells, cells, (size_t)m->n_cells * 48, cudaMemcpyHostToDevice, ctx->stream));
   if (npts && m->n_cells) CKM(cudaMemcpyAsync(m->npts, npts, (size_t)m->n_cells * 4, cudaMemcpyHostToDevice, ctx->stream));
-  else CKM(cudaMemsetAsync(m->npts, 0, std::max<size_t>(1, m->n_cells) * 4, ctx->stream));
+  else { CKM(cudaMemsetAsync(m->npts, 0, std::max<size_t>(1, m->n_cells) * 4, ctx->stream)); m->has_npts = m->n_cells == 0; }
   CKM(cudaMemcpyAsync(m->cell_off, cell_off, (size_t)(n_maps + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
   if (slot) CKM(cudaMemcpyAsync(m->slot, slot, (size_t)n_maps * m->geom.n_slots * 4, cudaMemcpyHostToDevice, ctx->stream));
   else {
@@ -576,7 +586,7 @@ int randt_map_info(const randt_map* m, uint32_t* n_maps, uint32_t* n_cells_total
 int randt_map_download(randt_ctx* ctx, const randt_map* m, float* cells, uint32_t* npts, int32_t* labels, uint32_t* cell_off, int32_t* slot) {
   if (!ctx || !m) return fail(ctx, RANDT_E_INVALID, "randt_map_download: null argument");
   CK(cudaSetDevice(ctx->device));
-  StreamScope scope__(ctx->stream);
+  StreamScope scope__(ctx->stream, ctx->sref->pool);
   if (cells && m->n_cells) CK(cudaMemcpyAsync(cells, m->cells, (size_t)m->n_cells * 48, cudaMemcpyDeviceToHost, ctx->stream));
   if (npts && m->n_cells) CK(cudaMemcpyAsync(npts, m->npts, (size_t)m->n_cells * 4, cudaMemcpyDeviceToHost, ctx->stream));
   if (labels) {
@@ -593,7 +603,7 @@ namespace {
 // in: host float32 [B][4] (cos, sin, tx, ty) when from_se2d == 0, host float64 [B][4] Sophus SE2d storage otherwise
 int map_transform_impl(randt_ctx* ctx, randt_map* m, const void* in, int from_se2d) {
   CK(cudaSetDevice(ctx->device));
-  StreamScope scope__(ctx->stream);
+  StreamScope scope__(ctx->stream, ctx->sref->pool);
   const size_t in_bytes = (size_t)m->B * 4 * (from_se2d ? sizeof(double) : sizeof(float));
   unsigned char* d_in = nullptr; float4* d_aff = nullptr;
   CK(dev_alloc(&d_in, in_bytes));
@@ -622,8 +632,10 @@ int randt_map_transform_se2d(randt_ctx* ctx, randt_map* m, const double* poses) 
 int randt_map_merge(randt_ctx* ctx, randt_map* F, const randt_map* M) {
   if (!ctx || !F || !M) return fail(ctx, RANDT_E_INVALID, "randt_map_merge: null argument");
   if (F->B != M->B || !same_geom(F->gp, M->gp)) return fail(ctx, RANDT_E_INVALID, "randt_map_merge: batch size / geometry mismatch");
+  if (!F->has_npts || !M->has_npts)
+    return fail(ctx, RANDT_E_INVALID, "randt_map_merge: a map was uploaded without point counts (Cell::operator+= weights by n - 1, ndt_cell.h:133-142)");
   CK(cudaSetDevice(ctx->device));
-  StreamScope scope__(ctx->stream);
+  StreamScope scope__(ctx->stream, ctx->sref->pool);
   const uint32_t B = F->B;
   uint32_t cap = 1;
   for (uint32_t b = 0; b < B; ++b) cap = std::max(cap, (F->h_cell_off[b + 1] - F->h_cell_off[b]) + (M->h_cell_off[b + 1] - M->h_cell_off[b]));
@@ -658,7 +670,7 @@ int randt_cs_divergence(randt_ctx* ctx, const randt_map* F, const randt_map* M, 
   if (!ctx || !F || !M || !out) return fail(ctx, RANDT_E_INVALID, "randt_cs_divergence: null argument");
   if (F->B != M->B) return fail(ctx, RANDT_E_INVALID, "randt_cs_divergence: fixed and moving batches differ in size");
   CK(cudaSetDevice(ctx->device));
-  StreamScope scope__(ctx->stream);
+  StreamScope scope__(ctx->stream, ctx->sref->pool);
   const uint32_t B = F->B;
   if (B == 0) return RANDT_OK;
   double *d_part = nullptr, *d_out = nullptr; uint32_t* d_tick = nullptr;
@@ -680,7 +692,7 @@ void randt_map_destroy(randt_map* m) {
   if (!m) return;
   cudaSetDevice(m->device);
   std::shared_ptr<StreamRef> sr = m->sref;      // keeps the stream alive until the frees are queued
-  if (sr && sr->own) { StreamScope scope__(sr->stream); free_map(m); }
+  if (sr && sr->own) { StreamScope scope__(sr->stream, sr->pool); free_map(m); }
   else free_map(m);                             // borrowed stream (may be gone by now): cudaFree
 }
 
@@ -698,7 +710,7 @@ int randt_associate(randt_ctx* ctx, const randt_map* F, const randt_map* M, cons
   if (2 * (geom.r_stop > 0 ? geom.r_stop - 1 : 0) + 1 > geom.size_x)
     return fail(ctx, RANDT_E_CAPACITY, "randt_associate: search window wider than the map (duplicate window slots are not supported)");
   CK(cudaSetDevice(ctx->device));
-  StreamScope scope__(ctx->stream);
+  StreamScope scope__(ctx->stream, ctx->sref->pool);
   const uint32_t B = F->B, n_m = M->n_cells;
   randt_problem* p = new (std::nothrow) randt_problem();
   if (!p) return RANDT_E_NOMEM;
@@ -758,7 +770,7 @@ int randt_problem_create(randt_ctx* ctx, const float* cells_m, uint32_t n_m, con
   for (uint32_t s = 0; s < n_segments; ++s) if (seg_off[s + 1] < seg_off[s]) return fail(ctx, RANDT_E_INVALID, "randt_problem_create: seg_off not monotone");
   for (uint32_t i = 0; i < n_pairs; ++i) if (pair_m[i] >= n_m || pair_f[i] >= n_f) return fail(ctx, RANDT_E_INVALID, "randt_problem_create: pair index out of range");
   CK(cudaSetDevice(ctx->device));
-  StreamScope scope__(ctx->stream);
+  StreamScope scope__(ctx->stream, ctx->sref->pool);
   randt_problem* p = new (std::nothrow) randt_problem();
   if (!p) return RANDT_E_NOMEM;
   p->device = ctx->device; p->sref = ctx->sref; p->S = n_segments; p->P = n_pairs; p->n_m = n_m; p->n_f = n_f;
@@ -813,7 +825,7 @@ int randt_problem_layout(const randt_problem* p, uint32_t* n_duos, uint32_t* rec
 int randt_problem_download(randt_ctx* ctx, const randt_problem* p, uint32_t* pair_m, uint32_t* pair_f, uint32_t* seg_off) {
   if (!ctx || !p) return fail(ctx, RANDT_E_INVALID, "randt_problem_download: null argument");
   CK(cudaSetDevice(ctx->device));
-  StreamScope scope__(ctx->stream);
+  StreamScope scope__(ctx->stream, ctx->sref->pool);
   if ((pair_m || pair_f) && p->P) {
     std::vector<uint2> h(p->P);
     CK(cudaMemcpyAsync(h.data(), p->pairs, (size_t)p->P * sizeof(uint2), cudaMemcpyDeviceToHost, ctx->stream));
@@ -828,7 +840,7 @@ int randt_problem_download(randt_ctx* ctx, const randt_problem* p, uint32_t* pai
 int randt_problem_download_cells(randt_ctx* ctx, const randt_problem* p, float* cells_m, float* cells_f) {
   if (!ctx || !p) return fail(ctx, RANDT_E_INVALID, "randt_problem_download_cells: null argument");
   CK(cudaSetDevice(ctx->device));
-  StreamScope scope__(ctx->stream);
+  StreamScope scope__(ctx->stream, ctx->sref->pool);
   if (cells_m && p->n_m) CK(cudaMemcpyAsync(cells_m, p->cells_m, (size_t)p->n_m * 48, cudaMemcpyDeviceToHost, ctx->stream));
   if (cells_f && p->n_f) CK(cudaMemcpyAsync(cells_f, p->cells_f, (size_t)p->n_f * 48, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -839,7 +851,7 @@ void randt_problem_destroy(randt_problem* p) {
   if (!p) return;
   cudaSetDevice(p->device);
   std::shared_ptr<StreamRef> sr = p->sref;
-  if (sr && sr->own) { StreamScope scope__(sr->stream); free_problem(p); }
+  if (sr && sr->own) { StreamScope scope__(sr->stream, sr->pool); free_problem(p); }
   else free_problem(p);
 }
 
@@ -850,7 +862,7 @@ int randt_eval_emit_dev(randt_ctx* ctx, const randt_problem* p, int variant, con
   if (!ctx || !p || !d_poses || !d_r) return fail(ctx, RANDT_E_INVALID, "randt_eval_emit_dev: null argument");
   if (check_variant(ctx, variant)) return RANDT_E_INVALID;
   CK(cudaSetDevice(ctx->device));
-  StreamScope scope__(ctx->stream);
+  StreamScope scope__(ctx->stream, ctx->sref->pool);
   int nl = 0;
   CK(launch_eval_emit(view(p), variant, d_poses, d_r, d_J, ctx->d_bad, ctx->stream, &nl));
   ctx->launches += nl;
@@ -862,7 +874,7 @@ int randt_eval_emit(randt_ctx* ctx, const randt_problem* cp, int variant, const 
   if (check_variant(ctx, variant)) return RANDT_E_INVALID;
   randt_problem* p = const_cast<randt_problem*>(cp);
   CK(cudaSetDevice(ctx->device));
-  StreamScope scope__(ctx->stream);
+  StreamScope scope__(ctx->stream, ctx->sref->pool);
   const int np = np_of(variant);
   if (!p->d_r) CK(dev_alloc(&p->d_r, p->P));
   if (J && !p->d_J) CK(dev_alloc(&p->d_J, (size_t)p->P * 4));
@@ -891,7 +903,7 @@ int eval_fused_dev_impl(randt_ctx* ctx, const randt_problem* p, int variant, con
   LossParams lp;
   if (int rc = make_loss(ctx, loss, &lp)) return rc;
   CK(cudaSetDevice(ctx->device));
-  StreamScope scope__(ctx->stream);
+  StreamScope scope__(ctx->stream, ctx->sref->pool);
   // segments without pairs produce no tile: clear their records up front
   if (p->has_empty_segment) CK(cudaMemsetAsync(d_out, 0, (size_t)p->S * (packed ? RANDT_PACKED_STRIDE : RANDT_FUSED_STRIDE) * sizeof(double), ctx->stream));
   int nl = 0;
@@ -910,7 +922,7 @@ int randt_eval_fused(randt_ctx* ctx, const randt_problem* cp, int variant, const
   if (check_variant(ctx, variant)) return RANDT_E_INVALID;
   randt_problem* p = const_cast<randt_problem*>(cp);
   CK(cudaSetDevice(ctx->device));
-  StreamScope scope__(ctx->stream);
+  StreamScope scope__(ctx->stream, ctx->sref->pool);
   const int np = np_of(variant);
   CK(cudaMemcpyAsync(p->d_poses, poses, (size_t)p->S * np * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   if (mu_per_seg) CK(cudaMemcpyAsync(p->d_mu, mu_per_seg, (size_t)p->S * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -952,7 +964,11 @@ int randt_eval_fused_async(randt_ctx* ctx, const randt_problem* cp, int variant,
   };
   if (!is_pinned(out) || !is_pinned(poses) || (mu_per_seg && !is_pinned(mu_per_seg)))
     return fail(ctx, RANDT_E_INVALID, "randt_eval_fused_async: poses, mu_per_seg and out must be pinned host memory (randt_host_alloc)");
-  if (p->S == 0) { r.ring_n++; return RANDT_OK; }      // nothing to do, but the call still has a ticket
+  if (p->S == 0) {      // nothing to do, but the call still has a ticket (delivered as soon as everything before it is)
+    if (r.copy_out) CK(cudaEventRecord(r.ev_call[(r.ring_n + 1) & 7u], r.copy_out));
+    r.ring_n++;
+    return RANDT_OK;
+  }
   if (!r.copy) {
     CK(cudaStreamCreateWithFlags(&r.copy, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&r.copy_out, cudaStreamNonBlocking));
@@ -964,14 +980,15 @@ int randt_eval_fused_async(randt_ctx* ctx, const randt_problem* cp, int variant,
     for (int i = 0; i < 8; ++i) CK(cudaEventCreateWithFlags(&r.ev_call[i], cudaEventDisableTiming));
   }
   const int np = np_of(variant);
-  const int slot = (int)(r.ring_n++ & 1);
+  const uint64_t ticket = r.ring_n + 1;      // committed only once every step below has been enqueued: a failed call has no ticket
+  const int slot = (int)(r.ring_n & 1);
   const size_t n_pose = (size_t)p->S * np, need = n_pose + (mu_per_seg ? p->S : 0);
   // the slot is free once the kernel that read it two calls ago has finished
   CK(cudaStreamWaitEvent(r.copy, r.ev_done[slot], 0));
   if (r.ring_cap[slot] < need) {
     if (r.ring[slot]) CK(cudaFreeAsync(r.ring[slot], r.copy));
     r.ring[slot] = nullptr; r.ring_cap[slot] = 0;
-    CK(cudaMallocAsync(reinterpret_cast<void**>(&r.ring[slot]), need * sizeof(double), r.copy));
+    CK(cudaMallocFromPoolAsync(reinterpret_cast<void**>(&r.ring[slot]), need * sizeof(double), r.pool, r.copy));
     r.ring_cap[slot] = need;
   }
   double* d_in = r.ring[slot];
@@ -986,7 +1003,7 @@ int randt_eval_fused_async(randt_ctx* ctx, const randt_problem* cp, int variant,
   if (r.oring_cap[slot] < n_out) {
     if (r.oring[slot]) CK(cudaFreeAsync(r.oring[slot], ctx->stream));
     r.oring[slot] = nullptr; r.oring_cap[slot] = 0;
-    CK(cudaMallocAsync(reinterpret_cast<void**>(&r.oring[slot]), n_out * sizeof(double), ctx->stream));
+    CK(cudaMallocFromPoolAsync(reinterpret_cast<void**>(&r.oring[slot]), n_out * sizeof(double), r.pool, ctx->stream));
     r.oring_cap[slot] = n_out;
   }
   double* d_out = r.oring[slot];
@@ -997,7 +1014,8 @@ int randt_eval_fused_async(randt_ctx* ctx, const randt_problem* cp, int variant,
   CK(cudaStreamWaitEvent(r.copy_out, r.ev_done[slot], 0));
   CK(cudaMemcpyAsync(out, d_ship, n_ship * sizeof(double), cudaMemcpyDeviceToHost, r.copy_out));
   CK(cudaEventRecord(r.ev_d2h[slot], r.copy_out));             // randt_ctx_sync() waits for the copy-out stream as well
-  CK(cudaEventRecord(r.ev_call[r.ring_n & 7u], r.copy_out));   // ring_n is this call's ticket (randt_ctx_wait_async)
+  CK(cudaEventRecord(r.ev_call[ticket & 7u], r.copy_out));     // delivery of this call (randt_ctx_wait_async)
+  r.ring_n = ticket;
   return RANDT_OK;
 }
 
@@ -1023,7 +1041,7 @@ int randt_eval_allpairs_dev(randt_ctx* ctx, const randt_map* F, const randt_map*
   LossParams lp;
   if (int rc = make_loss(ctx, loss, &lp)) return rc;
   CK(cudaSetDevice(ctx->device));
-  StreamScope scope__(ctx->stream);
+  StreamScope scope__(ctx->stream, ctx->sref->pool);
   const uint32_t B = F->B;
   if (B == 0) return RANDT_OK;
   uint32_t tm, tf;
@@ -1046,7 +1064,7 @@ int randt_eval_allpairs(randt_ctx* ctx, const randt_map* F, const randt_map* M, 
   if (!ctx || !F || !M || !poses || !out) return fail(ctx, RANDT_E_INVALID, "randt_eval_allpairs: null argument");
   if (check_variant(ctx, variant)) return RANDT_E_INVALID;
   CK(cudaSetDevice(ctx->device));
-  StreamScope scope__(ctx->stream);
+  StreamScope scope__(ctx->stream, ctx->sref->pool);
   const uint32_t B = F->B;
   if (B == 0) return RANDT_OK;
   const int np = np_of(variant);
@@ -1073,7 +1091,7 @@ int randt_sweep_costs(randt_ctx* ctx, const randt_problem* cp, uint32_t seg, int
   LossParams lp;
   if (int rc = make_loss(ctx, loss, &lp)) return rc;
   CK(cudaSetDevice(ctx->device));
-  StreamScope scope__(ctx->stream);
+  StreamScope scope__(ctx->stream, ctx->sref->pool);
   const int np = np_of(variant);
   const size_t need = (size_t)n_poses * (np + 1);
   if (p->sweep_cap < need) { dev_free(p->d_sweep); p->d_sweep = nullptr; p->sweep_cap = 0; CK(dev_alloc(&p->d_sweep, need)); p->sweep_cap = need; }
@@ -1100,8 +1118,17 @@ void randt_solver_options_default(randt_solver_options* o) {
   o->gnc_loss_scale = 1.0; o->gnc_divisor = 1.1; o->gnc_max_steps = 2; o->poll_interval = 0;
 }
 
+namespace {
+int register_batch_impl(randt_ctx* ctx, const randt_problem* cp, int variant, double* d_poses, const randt_loss* loss, const double* d_weight_per_seg,
+                        const randt_solver_options* opt, double* d_result);
+}
 int randt_register_batch_dev(randt_ctx* ctx, const randt_problem* cp, int variant, double* d_poses, const randt_loss* loss,
                              const randt_solver_options* opt, double* d_result) {
+  return register_batch_impl(ctx, cp, variant, d_poses, loss, nullptr, opt, d_result);
+}
+namespace {
+int register_batch_impl(randt_ctx* ctx, const randt_problem* cp, int variant, double* d_poses, const randt_loss* loss, const double* d_weight_per_seg,
+                        const randt_solver_options* opt, double* d_result) {
   if (!ctx || !cp || !d_poses || !opt || !d_result) return fail(ctx, RANDT_E_INVALID, "randt_register_batch: null argument");
   if (check_variant(ctx, variant)) return RANDT_E_INVALID;
   if (!(opt->gnc_divisor > 1.0) || !(opt->gnc_loss_scale > 0.0) || opt->gnc_max_steps < 1 || opt->max_num_iterations < 0 ||
@@ -1113,7 +1140,7 @@ int randt_register_batch_dev(randt_ctx* ctx, const randt_problem* cp, int varian
   if (int rc = make_loss(ctx, &l0, &lp)) return rc;
   randt_problem* p = const_cast<randt_problem*>(cp);
   CK(cudaSetDevice(ctx->device));
-  StreamScope scope__(ctx->stream);
+  StreamScope scope__(ctx->stream, ctx->sref->pool);
   const uint32_t S = p->S;
   const int np = np_of(variant);
   if (S == 0) return RANDT_OK;
@@ -1122,12 +1149,14 @@ int randt_register_batch_dev(randt_ctx* ctx, const randt_problem* cp, int varian
   // rest (and everything, when poll_interval < 0) goes through the stepwise loop: one K3 fused launch + one K4 launch per LM iteration.
   const bool stepwise_only = opt->poll_interval < 0;
   const uint32_t n_k7 = stepwise_only ? 0u : p->n_solve_items;
+  if (d_weight_per_seg && n_k7 != S)
+    return fail(ctx, RANDT_E_INVALID, "randt_register_batch_weighted: per-registration weights need the persistent solver (registrations of <= 1024 pairs, poll_interval >= 0)");
   if (n_k7) {
     SolveLayout L;
     L.seg_duo_off = p->seg_duo_off; L.tile_rec_begin = p->rec_of_tile; L.tile_duos = p->tile_duos;
     L.items = p->solve_all ? nullptr : p->solve_items; L.n_items = n_k7; L.next_item = p->solve_counter;
     CK(cudaMemsetAsync(p->solve_counter, 0, sizeof(uint32_t), ctx->stream));
-    CK(launch_solve_persistent(view(p), L, variant, opt->use_manifold, lp, *opt, d_poses, d_poses, d_result, ctx->d_bad, ctx->stream, &nl));
+    CK(launch_solve_persistent(view(p), L, variant, opt->use_manifold, lp, d_weight_per_seg, *opt, d_poses, d_poses, d_result, ctx->d_bad, ctx->stream, &nl));
     if (n_k7 == S) { ctx->launches += nl; return RANDT_OK; }
   }
   if (!p->lm_state) {
@@ -1193,20 +1222,30 @@ int randt_register_batch_dev(randt_ctx* ctx, const randt_problem* cp, int varian
   if (!done) return fail(ctx, RANDT_E_NONFINITE, "randt_register_batch: iteration cap reached with active segments (non-finite evaluations?)");
   return RANDT_OK;
 }
+}  // namespace
 
 int randt_register_batch(randt_ctx* ctx, const randt_problem* cp, int variant, double* poses, const randt_loss* loss,
                          const randt_solver_options* opt, double* result) {
+  return randt_register_batch_weighted(ctx, cp, variant, poses, loss, nullptr, opt, result);
+}
+
+int randt_register_batch_weighted(randt_ctx* ctx, const randt_problem* cp, int variant, double* poses, const randt_loss* loss,
+                                  const double* weight_per_seg, const randt_solver_options* opt, double* result) {
   if (!ctx || !cp || !poses || !opt || !result) return fail(ctx, RANDT_E_INVALID, "randt_register_batch: null argument");
   if (check_variant(ctx, variant)) return RANDT_E_INVALID;
   randt_problem* p = const_cast<randt_problem*>(cp);
   CK(cudaSetDevice(ctx->device));
-  StreamScope scope__(ctx->stream);
+  StreamScope scope__(ctx->stream, ctx->sref->pool);
   const uint32_t S = p->S;
   const int np = np_of(variant);
   if (S == 0) return RANDT_OK;
   if (!p->lm_poses) { CK(dev_alloc(&p->lm_poses, (size_t)S * 4)); CK(dev_alloc(&p->lm_result, (size_t)S * RANDT_REG_STRIDE)); }
   CK(cudaMemcpyAsync(p->lm_poses, poses, (size_t)S * np * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  int rc = randt_register_batch_dev(ctx, p, variant, p->lm_poses, loss, opt, p->lm_result);
+  if (weight_per_seg) {
+    if (!p->lm_weight) CK(dev_alloc(&p->lm_weight, S));
+    CK(cudaMemcpyAsync(p->lm_weight, weight_per_seg, (size_t)S * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  int rc = register_batch_impl(ctx, p, variant, p->lm_poses, loss, weight_per_seg ? p->lm_weight : nullptr, opt, p->lm_result);
   if (rc) return rc;
   CK(cudaMemcpyAsync(poses, p->lm_poses, (size_t)S * np * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(result, p->lm_result, (size_t)S * RANDT_REG_STRIDE * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

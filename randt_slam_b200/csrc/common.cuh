@@ -173,7 +173,7 @@ struct SolveLayout {
   uint32_t* next_item;             // device counter, zero at launch
 };
 cudaError_t launch_solve_persistent(const DeviceProblem& p, const SolveLayout& L, int variant, int use_manifold, const LossParams& lp,
-                                    const randt_solver_options& o, const double* d_poses0, double* d_poses_out, double* d_result,
+                                    const double* d_weight_per_seg /* [S] ScaledLoss weight per registration, or NULL: lp.weight */, const randt_solver_options& o, const double* d_poses0, double* d_poses_out, double* d_result,
                                     unsigned long long* d_bad, cudaStream_t s, int* n_launches);
 
 // k8_allpairs.cu — every moving cell against every fixed cell (optionally within an L-infinity window), fused normal equations per map pair

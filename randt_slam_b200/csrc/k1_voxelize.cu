@@ -493,7 +493,7 @@ __global__ void merge_maps_kernel(const float4* __restrict__ f_cells, const uint
       const float bcov[9] = {A.w, Bq.x, Bq.y, Bq.z, Bq.w, Cq.x, Cq.y, Cq.z, Cq.w};
       const uint32_t na = o_npts[o0 + idx], nb = m_npts[m0 + i];
       // operator+= (ndt_cell.h:133-142): unsigned / size_t weights converted to float, (na*nb)/(na+nb) is integer division
-      const float w1 = (float)(na - 1u);
+      const float w1 = (float)((unsigned long long)na - 1ull);
       const float w2 = (float)((unsigned long long)nb - 1ull);
       const float w3 = (float)(((unsigned long long)na * (unsigned long long)nb) / ((unsigned long long)na + (unsigned long long)nb));
       const float d[3] = {amu[0] - bmu[0], amu[1] - bmu[1], amu[2] - bmu[2]};

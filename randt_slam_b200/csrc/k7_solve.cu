@@ -41,8 +41,9 @@ struct __align__(128) SolveWarp {
 
 template <int VARIANT, int LOSS, bool MANIFOLD>
 __global__ void __launch_bounds__(kK7Warps * 32, kK7MinCtas)
-k7_solve_kernel(DeviceProblem P, SolveLayout L, LossParams lp, randt_solver_options o, const double* __restrict__ poses0,
-                double* __restrict__ poses_out, double* __restrict__ result, unsigned long long* __restrict__ bad_counter) {
+k7_solve_kernel(DeviceProblem P, SolveLayout L, LossParams lp, const double* __restrict__ weight_per_seg, randt_solver_options o,
+                const double* __restrict__ poses0, double* __restrict__ poses_out, double* __restrict__ result,
+                unsigned long long* __restrict__ bad_counter) {
   constexpr int NB = VarTraits<VARIANT>::NB;
   constexpr int NP = VarTraits<VARIANT>::NP;
   constexpr int NH = NB * (NB + 1) / 2;
@@ -73,6 +74,8 @@ k7_solve_kernel(DeviceProblem P, SolveLayout L, LossParams lp, randt_solver_opti
     const uint32_t first_tile = P.seg_first_tile[seg];
     const uint32_t n_pairs_seg = P.seg_off[seg + 1] - P.seg_off[seg];
     const bool resident = n_chunks <= (uint32_t)kK7Bufs;
+    LossParams lps = lp;                       // ScaledLoss weight of this registration (ndt_weight / (n_cells k) differs per scan)
+    if (weight_per_seg) lps.weight = weight_per_seg[seg];
     const uint32_t ahead = resident ? (uint32_t)kK7Bufs : (uint32_t)(kK7Bufs - 1);
     auto issue = [&](uint32_t c) {           // lane 0: chunk c of this registration -> buffer c % kK7Bufs
       const uint32_t n_here = min(32u, nd - (c << 5));
@@ -101,7 +104,7 @@ k7_solve_kernel(DeviceProblem P, SolveLayout L, LossParams lp, randt_solver_opti
         if (load) for (uint32_t c = 0; c < min(n_chunks, ahead); ++c) issue(c);
         PoseConst k0; LossConst l0;
         make_pose_const<VARIANT>(w.eval_pose, k0);
-        make_loss_const(lp, w.mu, l0);
+        make_loss_const(lps, w.mu, l0);
         w.kc = k0; w.lc = l0;
       }
       __syncwarp();
@@ -162,8 +165,8 @@ int k7_loss_code(const LossParams& lp) {
 }
 
 template <int VARIANT, int LOSS, bool MANIFOLD>
-cudaError_t launch_solve_vlm(const DeviceProblem& p, const SolveLayout& L, const LossParams& lp, const randt_solver_options& o, const double* poses0,
-                             double* poses_out, double* result, unsigned long long* bad, cudaStream_t s) {
+cudaError_t launch_solve_vlm(const DeviceProblem& p, const SolveLayout& L, const LossParams& lp, const double* wps, const randt_solver_options& o,
+                             const double* poses0, double* poses_out, double* result, unsigned long long* bad, cudaStream_t s) {
   constexpr int NB = VarTraits<VARIANT>::NB;
   constexpr int NS = NB * (NB + 1) / 2 + NB + 2;
   constexpr size_t smem = (size_t)kK7Warps * sizeof(SolveWarp<NS>);
@@ -171,36 +174,36 @@ cudaError_t launch_solve_vlm(const DeviceProblem& p, const SolveLayout& L, const
   if (cudaError_t rc = k7_allow_smem(k7_solve_kernel<VARIANT, LOSS, MANIFOLD>, smem, done)) return rc;
   const uint32_t max_ctas = (uint32_t)(kSmCount * kK7MinCtas);
   const uint32_t grid = std::max(1u, std::min(max_ctas, (L.n_items + kK7Warps - 1u) / kK7Warps));
-  k7_solve_kernel<VARIANT, LOSS, MANIFOLD><<<grid, kK7Warps * 32, smem, s>>>(p, L, lp, o, poses0, poses_out, result, bad);
+  k7_solve_kernel<VARIANT, LOSS, MANIFOLD><<<grid, kK7Warps * 32, smem, s>>>(p, L, lp, wps, o, poses0, poses_out, result, bad);
   return cudaGetLastError();
 }
 template <int VARIANT, bool MANIFOLD>
-cudaError_t launch_solve_vm(const DeviceProblem& p, const SolveLayout& L, const LossParams& lp, const randt_solver_options& o, const double* poses0,
-                            double* poses_out, double* result, unsigned long long* bad, cudaStream_t s) {
+cudaError_t launch_solve_vm(const DeviceProblem& p, const SolveLayout& L, const LossParams& lp, const double* wps, const randt_solver_options& o,
+                            const double* poses0, double* poses_out, double* result, unsigned long long* bad, cudaStream_t s) {
   switch (k7_loss_code(lp)) {
-    case L_NONE: return launch_solve_vlm<VARIANT, L_NONE, MANIFOLD>(p, L, lp, o, poses0, poses_out, result, bad, s);
-    case L_WELSCH: return launch_solve_vlm<VARIANT, L_WELSCH, MANIFOLD>(p, L, lp, o, poses0, poses_out, result, bad, s);
-    case L_BARRON_M2: return launch_solve_vlm<VARIANT, L_BARRON_M2, MANIFOLD>(p, L, lp, o, poses0, poses_out, result, bad, s);
-    case L_BARRON_M1: return launch_solve_vlm<VARIANT, L_BARRON_M1, MANIFOLD>(p, L, lp, o, poses0, poses_out, result, bad, s);
-    default: return launch_solve_vlm<VARIANT, L_BARRON, MANIFOLD>(p, L, lp, o, poses0, poses_out, result, bad, s);
+    case L_NONE: return launch_solve_vlm<VARIANT, L_NONE, MANIFOLD>(p, L, lp, wps, o, poses0, poses_out, result, bad, s);
+    case L_WELSCH: return launch_solve_vlm<VARIANT, L_WELSCH, MANIFOLD>(p, L, lp, wps, o, poses0, poses_out, result, bad, s);
+    case L_BARRON_M2: return launch_solve_vlm<VARIANT, L_BARRON_M2, MANIFOLD>(p, L, lp, wps, o, poses0, poses_out, result, bad, s);
+    case L_BARRON_M1: return launch_solve_vlm<VARIANT, L_BARRON_M1, MANIFOLD>(p, L, lp, wps, o, poses0, poses_out, result, bad, s);
+    default: return launch_solve_vlm<VARIANT, L_BARRON, MANIFOLD>(p, L, lp, wps, o, poses0, poses_out, result, bad, s);
   }
 }
 
 }  // namespace
 
 cudaError_t launch_solve_persistent(const DeviceProblem& p, const SolveLayout& L, int variant, int use_manifold, const LossParams& lp,
-                                    const randt_solver_options& o, const double* d_poses0, double* d_poses_out, double* d_result,
+                                    const double* d_weight_per_seg, const randt_solver_options& o, const double* d_poses0, double* d_poses_out, double* d_result,
                                     unsigned long long* d_bad, cudaStream_t s, int* n_launches) {
   if (L.n_items == 0) return cudaSuccess;
   cudaError_t e;
   // the manifold only exists for the 4-parameter SE2 pose blocks (variants 0 and 1), as in K4
   switch (variant) {
-    case 0: e = use_manifold ? launch_solve_vm<0, true>(p, L, lp, o, d_poses0, d_poses_out, d_result, d_bad, s)
-                             : launch_solve_vm<0, false>(p, L, lp, o, d_poses0, d_poses_out, d_result, d_bad, s); break;
-    case 1: e = use_manifold ? launch_solve_vm<1, true>(p, L, lp, o, d_poses0, d_poses_out, d_result, d_bad, s)
-                             : launch_solve_vm<1, false>(p, L, lp, o, d_poses0, d_poses_out, d_result, d_bad, s); break;
-    case 2: e = launch_solve_vm<2, false>(p, L, lp, o, d_poses0, d_poses_out, d_result, d_bad, s); break;
-    case 3: e = launch_solve_vm<3, false>(p, L, lp, o, d_poses0, d_poses_out, d_result, d_bad, s); break;
+    case 0: e = use_manifold ? launch_solve_vm<0, true>(p, L, lp, d_weight_per_seg, o, d_poses0, d_poses_out, d_result, d_bad, s)
+                             : launch_solve_vm<0, false>(p, L, lp, d_weight_per_seg, o, d_poses0, d_poses_out, d_result, d_bad, s); break;
+    case 1: e = use_manifold ? launch_solve_vm<1, true>(p, L, lp, d_weight_per_seg, o, d_poses0, d_poses_out, d_result, d_bad, s)
+                             : launch_solve_vm<1, false>(p, L, lp, d_weight_per_seg, o, d_poses0, d_poses_out, d_result, d_bad, s); break;
+    case 2: e = launch_solve_vm<2, false>(p, L, lp, d_weight_per_seg, o, d_poses0, d_poses_out, d_result, d_bad, s); break;
+    case 3: e = launch_solve_vm<3, false>(p, L, lp, d_weight_per_seg, o, d_poses0, d_poses_out, d_result, d_bad, s); break;
     default: return cudaErrorInvalidValue;
   }
   if (n_launches) *n_launches += 1;

@@ -282,12 +282,14 @@ std::vector<char> Matcher::estimateTransformsNDT(std::vector<SE2d>& trans, const
     if (np == 4) std::memcpy(&poses[4 * b], trans[b].v, 4 * sizeof(double));
     else { poses[3 * b] = trans[b].v[2]; poses[3 * b + 1] = trans[b].v[3]; poses[3 * b + 2] = trans[b].angle(); }
   }
-  // n_cells counts the moving map's cells (ndt_matcher.cpp:372), once, whatever the number of fixed maps.  One weight per call: for a
-  // batch the mean over its moving maps (the reference has one stream).
-  const double n_cells = (double)moving_ndts.get_n_cells() / (double)B;
+  // n_cells counts the moving map's cells (ndt_matcher.cpp:372), once, whatever the number of fixed maps: every registration of the
+  // batch gets the weight its own scan would get alone
+  const std::vector<uint32_t>& m_off = moving_ndts.cellOffsets();
+  std::vector<double> weights(B);
+  for (uint32_t b = 0; b < B; ++b) weights[b] = parameters_.ndt_weight / ((double)(m_off[b + 1] - m_off[b]) * (double)k);
   randt_loss loss;
   loss.kind = RANDT_LOSS_BARRON; loss.scale = parameters_.loss_function_scale; loss.alpha = parameters_.loss_function_convexity; loss.mu = 1.0;
-  loss.weight = parameters_.ndt_weight / (n_cells * (double)k);
+  loss.weight = 1.0;
   randt_solver_options opt;
   randt_solver_options_default(&opt);
   opt.max_num_iterations = parameters_.max_iteration;
@@ -295,7 +297,7 @@ std::vector<char> Matcher::estimateTransformsNDT(std::vector<SE2d>& trans, const
   opt.gnc_loss_scale = parameters_.loss_function_scale;
   opt.gnc_divisor = parameters_.gnc_control_parameter_divisor;
   opt.gnc_max_steps = parameters_.gnc_steps;
-  ctx_->check(randt_register_batch(ctx_->get(), prob, var, poses.data(), &loss, &opt, result.data()));
+  ctx_->check(randt_register_batch_weighted(ctx_->get(), prob, var, poses.data(), &loss, weights.data(), &opt, result.data()));
   std::vector<char> accepted(B, 1);
   for (uint32_t b = 0; b < B; ++b) {
     SE2d est;

@@ -119,6 +119,25 @@ def test_register_batch_vector_variant_and_scaled_loss(oracle, gpu_ctx):
     assert abs(out3[0, 2] - math.atan2(out[0, 1], out[0, 0])) < 1e-3
 
 
+def test_weighted_batch_equals_single_registrations(oracle, gpu_ctx):
+    """the odometry weight ndt_weight / (n_cells k) depends on each scan's own cell count (ndt_matcher.cpp:367,392): a batch solved with
+    per-registration weights gives every registration the bits it gets alone with that weight as loss->weight"""
+    p = P.OXFORD
+    guesses = [(0.5, -0.3, 0.02), (0.2, -0.1, 0.0), (0.9, -0.6, 0.05)]
+    cases, cm, cf, pm, pf, seg, poses = build_batch(oracle, p, [41, 42, 43], guesses)
+    w = np.array([p.ndt_weight / (len(c["moving"]["cells"]) * p.n_results_nn_lookup) for c in cases])
+    assert len(set(w)) == 3
+    opt = capi.solver_options(use_manifold=1, gnc_loss_scale=p.loss_function_scale, gnc_divisor=p.gnc_control_parameter_divisor, gnc_max_steps=p.gnc_steps)
+    prob = gpu_ctx.problem_create(cm, cf, pm, pf, seg)
+    out, res = prob.register_batch(poses, capi.make_loss(capi.LOSS_BARRON, p.loss_function_scale, p.loss_function_convexity, 1.0, 1.0), opt, weights=w)
+    for j, c in enumerate(cases):
+        solo = gpu_ctx.problem_create(c["moving"]["cells"], c["fixed"]["cells"], c["im"], c["jf"], [0, len(c["im"])])
+        o, r = solo.register_batch(c["pose0"][None], capi.make_loss(capi.LOSS_BARRON, p.loss_function_scale, p.loss_function_convexity, 1.0, w[j]), opt)
+        assert np.array_equal(o[0], out[j]) and np.array_equal(r[0], res[j])
+    with pytest.raises(capi.RandtError):     # the stepwise path has one weight per call
+        prob.register_batch(poses, None, capi.solver_options(poll_interval=-1), weights=w)
+
+
 def test_register_batch_rejects_bad_options(gpu_ctx):
     cm = np.zeros((1, 12), np.float32); cm[0, 3:] = np.eye(3).reshape(9)
     prob = gpu_ctx.problem_create(cm, cm, [0], [0], [0, 1])
