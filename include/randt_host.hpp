@@ -67,7 +67,23 @@ struct RANDT_API SE2d {
   double angle() const;                  // so2().log()
   SE2d operator*(const SE2d& o) const;   // group product with Sophus' conditional renormalisation of the complex number
   void matrix3f(float out[9]) const;     // column-major 3x3 homogeneous matrix as floats (what the BnB search de-duplicates on)
+  static SE2d exp(double ux, double uy, double theta);   // Sophus::SE2d::exp of the screw (ux, uy, theta)
 };
+
+// rc::navigation::ndt::State (R/include/ndt_slam/trajectory_representation.h:12-22): a window state in both representations
+struct RANDT_API State {
+  SE2d pose;
+  double pos[2] = {0.0, 0.0};
+  double rot = 0.0;
+  double lin_vel[2] = {0.0, 0.0};
+  double rot_vel = 0.0;
+  double lin_acc[2] = {0.0, 0.0};
+  double imu_bias = 0.0;
+  double stamp = 0.0;
+};
+// predict / predictSE2 (R/include/ndt_registration/ceres_residuals.h:25-85): constant-acceleration motion model over max(dt, 0.2 s)
+RANDT_API void predict(const State& old_state, double raw_dt, State& new_state);      // vector representation (pos, rot)
+RANDT_API void predictSE2(const State& old_state, double raw_dt, State& new_state);   // Lie-group representation (pose)
 
 // The parameter fields of the reference this path reads (R/include/ndt_slam/ndt_slam_parameters.h:17-50,56-84), already derived as
 // NDTSlam::readParameters leaves them (size in cells after the int /= resolution; n_clusters = int((2 max_range / resolution)^2)).
@@ -94,6 +110,7 @@ struct NDTMatcherParameters {
   bool use_intensity_as_dimension = true;
   bool optimize_on_manifold = true;
   bool lookup_mahalanobis = true;
+  bool use_constant_velocity_model = true;
   double csm_window_linear = 4.5, csm_window_angular = 0.45, csm_linear_step = 0.4, csm_cost_threshold = 0.82, csm_max_px_accurate_range = 4.0;
   int csm_n_iter = 2;
 };
@@ -181,6 +198,13 @@ class RANDT_API Matcher {
  public:
   explicit Matcher(Context& ctx) : ctx_(&ctx) {}
   void initialize(const NDTMatcherParameters& parameters) { parameters_ = parameters; }
+  // Matcher::resetMatcher (ndt_matcher.cpp:18-20): forget the relative IMU constraints collected by predictTransform
+  void resetMatcher() { imu_constraints_.clear(); }
+  // Matcher::predictTransform (ndt_matcher.cpp:22-59): append the motion-model prediction of the last state at `stamp` to the trajectory
+  // (vector model when the analytic functors or the vector parametrisation are configured, SE(2) model otherwise; the predicted state
+  // carries zero acceleration) and remember the IMU yaw guess of the step.  Both representations of the new state agree.
+  void predictTransform(const double& initial_angle_guess, const double& stamp, std::vector<State>& trajectory);
+  const std::vector<double>& imuConstraints() const { return imu_constraints_; }
   // association half of Matcher::addNDTFactor for a batch: problem b pairs moving map b with fixed map b at initial_guess[b]
   randt_problem* associate(const SE2d* initial_guess, const Map& fixed_ndt, const Map& moving_ndt, bool use_intensity_as_dimension,
                            int n_neighbours) const;
@@ -211,6 +235,8 @@ class RANDT_API Matcher {
  private:
   Context* ctx_;
   NDTMatcherParameters parameters_;
+  std::vector<double> imu_constraints_;
+  State X_next_;
 };
 
 }  // namespace randt
@@ -248,5 +274,7 @@ RANDT_API int randt_hostapi_eval_async_loop(randt_ctx* ctx, const randt_problem*
 RANDT_API int randt_hostapi_build_schedule(const uint32_t* duo_off, uint32_t n_segments, uint32_t max_warps, uint32_t* counts, uint32_t* tiles4,
                                            uint32_t cap_tiles, uint32_t* plan_a4, uint32_t* plan_b4, uint32_t cap_chunks, uint32_t* woff_a,
                                            uint32_t* woff_b, uint32_t* tile_rec_begin, uint32_t* tile_duo_begin, uint32_t* first);
+/* predict (se2_model == 0) / predictSE2 (se2_model != 0) on one state: state12 = [cos, sin, tx, ty, pos_x, pos_y, rot, vx, vy, omega, ax, ay] in and out */
+RANDT_API void randt_hostapi_predict(int se2_model, const double* state12, double raw_dt, double* out12);
 RANDT_API const char* randt_hostapi_last_error(void);
 }

@@ -29,6 +29,70 @@ SE2d SE2d::operator*(const SE2d& o) const {
   r.v[3] = v[3] + (v[1] * o.v[2] + v[0] * o.v[3]);
   return r;
 }
+SE2d SE2d::exp(double ux, double uy, double theta) {
+  // Sophus::SE2::exp: SO2::exp(theta), translation = V(theta) * (ux, uy) with the small-angle series below Constants<double>::epsilon()
+  const double s = std::sin(theta), c = std::cos(theta);
+  double sbt, omcbt;   // sin(theta) / theta, (1 - cos(theta)) / theta
+  if (std::fabs(theta) < 1e-10) {
+    const double t2 = theta * theta;
+    sbt = 1.0 - (1.0 / 6.0) * t2;
+    omcbt = 0.5 * theta - (1.0 / 24.0) * theta * t2;
+  } else { sbt = s / theta; omcbt = (1.0 - c) / theta; }
+  SE2d r;
+  r.v[0] = c; r.v[1] = s;
+  r.v[2] = sbt * ux - omcbt * uy;
+  r.v[3] = omcbt * ux + sbt * uy;
+  return r;
+}
+
+namespace {
+// NormalizeAngle (R/include/ndt_registration/state_manifold.h:17-23)
+double normalize_angle(double a) { const double two_pi = 2.0 * M_PI; return a - two_pi * std::floor((a + M_PI) / two_pi); }
+}  // namespace
+
+void predict(const State& o, double raw_dt, State& n) {
+  const double dt = std::max(raw_dt, 0.2);          // identical stamps happen (driver hiccups): ceres_residuals.h:38
+  const double rot = normalize_angle(o.rot + 0.5 * dt * o.rot_vel);
+  const double sy = std::sin(rot), cy = std::cos(rot);
+  const double dx = o.lin_vel[0] * dt + 0.5 * o.lin_acc[0] * dt * dt, dy = o.lin_vel[1] * dt + 0.5 * o.lin_acc[1] * dt * dt;
+  State r = o;
+  r.rot = normalize_angle(o.rot + dt * o.rot_vel);
+  r.pos[0] = o.pos[0] + (cy * dx - sy * dy);
+  r.pos[1] = o.pos[1] + (sy * dx + cy * dy);
+  r.lin_vel[0] = o.lin_vel[0] + dt * o.lin_acc[0];
+  r.lin_vel[1] = o.lin_vel[1] + dt * o.lin_acc[1];
+  n.pos[0] = r.pos[0]; n.pos[1] = r.pos[1]; n.rot = r.rot;
+  n.lin_vel[0] = r.lin_vel[0]; n.lin_vel[1] = r.lin_vel[1]; n.rot_vel = o.rot_vel; n.lin_acc[0] = o.lin_acc[0]; n.lin_acc[1] = o.lin_acc[1];
+}
+
+void predictSE2(const State& o, double raw_dt, State& n) {
+  const double dt = std::max(raw_dt, 0.2);
+  // screw = (v dt + dt a / 2, omega dt): the reference's SE(2) model integrates the acceleration with dt / 2, not dt^2 / 2 (ceres_residuals.h:77-79)
+  const SE2d step = SE2d::exp(o.lin_vel[0] * dt + 0.5 * dt * o.lin_acc[0], o.lin_vel[1] * dt + 0.5 * dt * o.lin_acc[1], o.rot_vel * dt);
+  n.pose = o.pose * step;
+  n.lin_vel[0] = o.lin_vel[0] + dt * o.lin_acc[0];
+  n.lin_vel[1] = o.lin_vel[1] + dt * o.lin_acc[1];
+  n.rot_vel = o.rot_vel; n.lin_acc[0] = o.lin_acc[0]; n.lin_acc[1] = o.lin_acc[1];
+}
+
+void Matcher::predictTransform(const double& initial_angle_guess, const double& stamp, std::vector<State>& trajectory) {
+  if (trajectory.empty()) return;
+  State last_state = trajectory.back();
+  X_next_.stamp = stamp;
+  last_state.lin_acc[0] = 0.0; last_state.lin_acc[1] = 0.0;
+  const double dt = stamp - trajectory.back().stamp;
+  if (parameters_.use_analytic_expressions_for_optimization || !parameters_.optimize_on_manifold) {
+    predict(last_state, dt, X_next_);
+    X_next_.pose = SE2d(X_next_.rot, X_next_.pos[0], X_next_.pos[1]);     // both representations hold the same information
+  } else {
+    predictSE2(last_state, dt, X_next_);
+    X_next_.pos[0] = X_next_.pose.v[2]; X_next_.pos[1] = X_next_.pose.v[3];
+    X_next_.rot = X_next_.pose.angle();
+  }
+  trajectory.push_back(X_next_);
+  imu_constraints_.push_back(initial_angle_guess);
+}
+
 void SE2d::matrix3f(float out[9]) const {
   const float m[9] = {(float)v[0], (float)v[1], 0.f, (float)-v[1], (float)v[0], 0.f, (float)v[2], (float)v[3], 1.f};
   std::memcpy(out, m, sizeof(m));
@@ -579,6 +643,16 @@ int randt_hostapi_build_schedule(const uint32_t* duo_off, uint32_t n_segments, u
     if (tile_duo_begin && !sch.tile_duo_begin.empty()) std::memcpy(tile_duo_begin, sch.tile_duo_begin.data(), sch.tile_duo_begin.size() * 4);
     if (first) std::memcpy(first, sch.first.data(), sch.first.size() * 4);
   });
+}
+
+void randt_hostapi_predict(int se2_model, const double* s, double raw_dt, double* out) {
+  randt::State a, b;
+  std::memcpy(a.pose.v, s, 4 * sizeof(double));
+  a.pos[0] = s[4]; a.pos[1] = s[5]; a.rot = s[6]; a.lin_vel[0] = s[7]; a.lin_vel[1] = s[8]; a.rot_vel = s[9]; a.lin_acc[0] = s[10]; a.lin_acc[1] = s[11];
+  b = a;
+  if (se2_model) randt::predictSE2(a, raw_dt, b); else randt::predict(a, raw_dt, b);
+  std::memcpy(out, b.pose.v, 4 * sizeof(double));
+  out[4] = b.pos[0]; out[5] = b.pos[1]; out[6] = b.rot; out[7] = b.lin_vel[0]; out[8] = b.lin_vel[1]; out[9] = b.rot_vel; out[10] = b.lin_acc[0]; out[11] = b.lin_acc[1];
 }
 
 int randt_hostapi_export(int device, const randt_grid_params* gp, const float* pts4, uint32_t n_pts, double* mean3, double* cov6, uint32_t cap,

@@ -122,3 +122,12 @@ def build_schedule(duo_off, max_warps):
     nt, nw, na, nb, nr = (int(c) for c in counts)
     return dict(tiles=tiles[:nt], n_warps=nw, plan_a=pa[:na], plan_b=pb[:nb], woff_a=wa[: nw + 1], woff_b=wb[: nw + 1], tile_rec_begin=trb[: nt + 1],
                 tile_duo_begin=tdb[:nt], first=first, n_records=nr)
+
+
+def predict(state12, raw_dt, se2_model):
+    """randt::predict / randt::predictSE2 on one state [cos, sin, tx, ty, pos_x, pos_y, rot, vx, vy, omega, ax, ay] -> predicted state"""
+    s = np.ascontiguousarray(state12, np.float64).reshape(12)
+    out = np.zeros(12, np.float64)
+    lib().randt_hostapi_predict.restype = None
+    lib().randt_hostapi_predict(C.c_int(int(se2_model)), _pf(s), C.c_double(float(raw_dt)), _pf(out))
+    return out
