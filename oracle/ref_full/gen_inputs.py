@@ -1,0 +1,66 @@
+#!/usr/bin/env python
+"""Writes tests/golden/ref_full_inputs.json: the seeded inputs the full-reference harness (oracle/ref_full/gen_fixtures.cpp) evaluates with
+the reference's own headers on a machine that has its dependencies (Eigen 3.3.7, Ceres 2.1.0, Sophus 1.22.10: /root/reference/Dockerfile).
+Inputs are generated here (numpy, CPU oracle for the cell tables and pair lists) so that the C++ side needs no generator of its own.
+usage: python oracle/ref_full/gen_inputs.py"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import oracle_py as O  # noqa: E402
+from randt_slam_b200 import params as P, synth  # noqa: E402
+from tests import helpers as H  # noqa: E402
+
+
+def main():
+    rng = np.random.default_rng(2024)
+    cm = H.random_cells(rng, 48); cf = H.random_cells(rng, 48)
+    cf[:, :2] = cm[:, :2] + rng.normal(0, 0.3, (48, 2)).astype(np.float32)          # residuals of O(1)
+    poses4 = [synth.pose_to_se2(*rng.uniform(-1, 1, 3) * [0.5, 0.5, 0.3]).tolist() for _ in range(4)]
+    poses4[1] = (np.array(poses4[1]) * [1.002, 1.002, 1, 1]).tolist()                  # un-normalised complex part (raw ambient block)
+    poses3 = rng.uniform(-1, 1, (4, 3)).tolist()
+    regs = []
+    p = P.OXFORD
+    for seed, guess in ((3, (0.5, -0.3, 0.02)), (4, (0.2, -0.1, 0.0)), (5, (0.9, -0.6, 0.05))):
+        c = H.make_registration_case(O, p, seed=seed, n_fixed_scans=4, true_pose=(0.6, -0.4, 0.03), guess=guess)
+        regs.append(dict(cells_m=c["moving"]["cells"].astype(np.float64).tolist(), cells_f=c["fixed"]["cells"].astype(np.float64).tolist(),
+                         pair_m=c["im"].tolist(), pair_f=c["jf"].tolist(), pose0=c["pose0"].tolist()))
+    doc = dict(
+        note="cells are float32 values written as doubles: [mean x, y, i, cov row-major 9]; poses4 = Sophus SE2d::data() order [cos, sin, tx, ty]",
+        pairs=dict(cells_m=cm.astype(np.float64).tolist(), cells_f=cf.astype(np.float64).tolist()),
+        poses4=poses4, poses3=poses3,
+        loss=dict(s=[0.0, 1e-6, 0.03, 0.5, 1.0, 4.0, 37.5, 900.0], settings=[[1.0, -2.0, 1.0], [2.0, -1.0, 3.3], [2.0, -1.5, 1.21], [1.5, 0.03, 1.0], [1.5, 1.0, 2.0], [1.5, 2.5, 2.0]]),
+        registrations=regs,
+        solver=dict(loss_function_scale=p.loss_function_scale, loop_closure_scale=p.loop_closure_scale, convexity=p.loss_function_convexity,
+                    divisor=p.gnc_control_parameter_divisor, loop_closure_gnc_steps=p.loop_closure_gnc_steps, gnc_steps=p.gnc_steps, max_iteration=p.max_iteration))
+    out = os.path.join(ROOT, "tests", "golden", "ref_full_inputs.json")
+    with open(out, "w") as f:
+        json.dump(doc, f)
+    print(out, os.path.getsize(out), "bytes")
+    # the same as whitespace-separated text (what the C++ harness reads: no JSON parser needed there)
+    txt = os.path.join(ROOT, "tests", "golden", "ref_full_inputs.txt")
+    r17 = lambda v: " ".join("%.17g" % x for x in v)
+    with open(txt, "w") as f:
+        f.write("pairs %d\n" % len(cm))
+        for a, b in zip(doc["pairs"]["cells_m"], doc["pairs"]["cells_f"]):
+            f.write(r17(a) + " " + r17(b) + "\n")
+        f.write("poses4 %d\n" % len(poses4)); [f.write(r17(q) + "\n") for q in poses4]
+        f.write("poses3 %d\n" % len(poses3)); [f.write(r17(q) + "\n") for q in poses3]
+        f.write("loss_s %d\n%s\n" % (len(doc["loss"]["s"]), r17(doc["loss"]["s"])))
+        f.write("loss_settings %d\n" % len(doc["loss"]["settings"])); [f.write(r17(q) + "\n") for q in doc["loss"]["settings"]]
+        sv = doc["solver"]
+        f.write("solver %s\n" % r17([sv["loss_function_scale"], sv["loop_closure_scale"], sv["convexity"], sv["divisor"], sv["loop_closure_gnc_steps"], sv["gnc_steps"], sv["max_iteration"]]))
+        f.write("registrations %d\n" % len(regs))
+        for g in regs:
+            f.write("registration %d %d %d\n" % (len(g["cells_m"]), len(g["cells_f"]), len(g["pair_m"])))
+            [f.write(r17(c) + "\n") for c in g["cells_m"]]; [f.write(r17(c) + "\n") for c in g["cells_f"]]
+            f.write(" ".join(str(i) for i in g["pair_m"]) + "\n" + " ".join(str(i) for i in g["pair_f"]) + "\n" + r17(g["pose0"]) + "\n")
+    print(txt, os.path.getsize(txt), "bytes")
+
+
+if __name__ == "__main__":
+    main()
