@@ -306,6 +306,16 @@ RANDT_API int randt_register_batch_dev(randt_ctx* ctx, const randt_problem* p, i
 RANDT_API int randt_register_batch_weighted(randt_ctx* ctx, const randt_problem* p, int variant, double* poses, const randt_loss* loss,
                                             const double* weight_per_seg, const randt_solver_options* opt, double* result);
 
+/* One scan of a live stream in one call (the per-scan chain of LocalFuser::processScan, R/src/local_fuser/local_fuser.cpp:95-190, for the
+ * parts that are on this path): voxelise the filtered scan (K1) -> associate it with the submap at pose_io (K2, addNDTFactor) ->
+ * GNC + LM registration (K7; loss ScaledLoss(Barron(loss->scale, loss->alpha, mu), ndt_weight / (n_cells k)), ndt_matcher.cpp:392) ->
+ * if insert_keyframe != 0: transformMap by the estimate + mergeMapCell into the submap (local_fuser.cpp:164-190).  An EMPTY submap
+ * (created by randt_map_upload with no cells) takes the scan as its first keyframe at pose_io.  pose_io [4]: prior in, estimate out;
+ * result [RANDT_REG_STRIDE] (may be NULL); n_cells_out: cells of the scan (may be NULL).  pts4 is host memory. */
+RANDT_API int randt_scan_step(randt_ctx* ctx, randt_map* submap, const float* pts4, uint32_t n_pts, const randt_grid_params* gp, int k, int metric,
+                              const randt_loss* loss, double ndt_weight, const randt_solver_options* opt, int insert_keyframe, double* pose_io,
+                              double* result, uint32_t* n_cells_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -116,6 +116,7 @@ _SIGS = {
     "randt_problem_create": (_i, [_vp, _vp, _u32, _vp, _u32, _vp, _vp, _u32, _vp, _u32, C.POINTER(_vp)]),
     "randt_problem_info": (_i, [_vp, C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_u32)]),
     "randt_register_batch_weighted": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "randt_scan_step": (_i, [_vp, _vp, _vp, _u32, _vp, _i, _i, _vp, C.c_double, _vp, _i, _vp, _vp, _vp]),
     "randt_eval_allpairs": (_i, [_vp, _vp, _vp, _i, _vp, _vp, C.c_double, _vp]),
     "randt_eval_allpairs_dev": (_i, [_vp, _vp, _vp, _i, _vp, _vp, C.c_double, _vp]),
     "randt_problem_layout": (_i, [_vp, C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_u32)]),
@@ -350,6 +351,18 @@ class Map:
     def eval_allpairs_dev(self, moving, d_poses, d_out, loss=None, window=0.0, variant=VAR_SE2_INTENSITY):
         lp = C.byref(loss) if loss is not None else None
         self.ctx._check(lib().randt_eval_allpairs_dev(self.ctx._h, self._h, moving._h, int(variant), C.c_void_p(d_poses), lp, float(window), C.c_void_p(d_out)))
+
+    def scan_step(self, pts, gp, k, loss, ndt_weight, opt, insert_keyframe, pose, metric=None):
+        """randt_scan_step on this (single) submap: voxelise -> associate -> register -> optional keyframe merge.  -> (pose [4], result [REG_STRIDE], n_cells)"""
+        pts = _f32(pts).reshape(-1, 4)
+        pose = _f64(pose).reshape(4).copy()
+        res = np.zeros(REG_STRIDE, np.float64)
+        nc = C.c_uint32()
+        lp = C.byref(loss) if loss is not None else None
+        self.ctx._check(lib().randt_scan_step(self.ctx._h, self._h, _ptr(pts), C.c_uint32(len(pts)), C.byref(gp), int(k),
+                                              int(LOOKUP_MAHALANOBIS if metric is None else metric), lp, float(ndt_weight), C.byref(opt), int(insert_keyframe),
+                                              _ptr(pose), _ptr(res), C.byref(nc)))
+        return pose, res, nc.value
 
     def cs_divergence(self, moving):
         """Map::calculateCSDivergence for every map pair of the batch -> float64 [B]"""

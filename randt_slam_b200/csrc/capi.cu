@@ -647,7 +647,7 @@ int randt_map_merge(randt_ctx* ctx, randt_map* F, const randt_map* M) {
 #define CKG(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rc = fail(ctx, RANDT_E_CUDA, #call, e__); cleanup(); dev_free(n_cells); dev_free(n_npts); dev_free(n_off); return rc; } } while (0)
   CKG(dev_alloc(&o_cells, (size_t)B * cap * 3)); CKG(dev_alloc(&o_npts, (size_t)B * cap)); CKG(dev_alloc(&o_cnt, B)); CKG(dev_alloc(&d_ooff, B + 1));
   CKG(cudaMemcpyAsync(d_ooff, h_ooff.data(), (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
-  CKG(launch_merge_maps(F->cells, F->npts, F->cell_off, F->slot, M->cells, M->npts, M->cell_off, B, F->geom, d_ooff, o_cells, o_npts, o_cnt, ctx->stream, &nl));
+  CKG(launch_merge_maps(F->cells, F->npts, F->cell_off, F->slot, M->cells, M->npts, M->cell_off, B, F->geom, d_ooff, o_cells, o_npts, o_cnt, M->max_per_map, ctx->stream, &nl));
   std::vector<uint32_t> h_cnt(B);
   if (B) CKG(cudaMemcpyAsync(h_cnt.data(), o_cnt, (size_t)B * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CKG(cudaStreamSynchronize(ctx->stream));
@@ -1251,6 +1251,38 @@ int randt_register_batch_weighted(randt_ctx* ctx, const randt_problem* cp, int v
   CK(cudaMemcpyAsync(result, p->lm_result, (size_t)S * RANDT_REG_STRIDE * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return RANDT_OK;
+}
+
+// the per-scan chain as one call: see randt_gpu.h
+int randt_scan_step(randt_ctx* ctx, randt_map* submap, const float* pts4, uint32_t n_pts, const randt_grid_params* gp, int k, int metric,
+                    const randt_loss* loss, double ndt_weight, const randt_solver_options* opt, int insert_keyframe, double* pose_io, double* result,
+                    uint32_t* n_cells_out) {
+  if (!ctx || !submap || !gp || !opt || !pose_io || (!pts4 && n_pts)) return fail(ctx, RANDT_E_INVALID, "randt_scan_step: null argument");
+  if (submap->B != 1) return fail(ctx, RANDT_E_INVALID, "randt_scan_step: the submap must be a single map");
+  const uint32_t off[2] = {0u, n_pts};
+  randt_map* scan = nullptr;
+  int rc = randt_voxelize(ctx, pts4, off, 1, gp, 0, &scan);
+  if (rc != RANDT_OK) return rc;
+  if (n_cells_out) *n_cells_out = scan->n_cells;
+  double res[RANDT_REG_STRIDE] = {0};
+  if (submap->n_cells > 0) {
+    randt_problem* prob = nullptr;
+    rc = randt_associate(ctx, submap, scan, pose_io, k, metric, &prob);
+    if (rc == RANDT_OK) {
+      randt_loss l; l.kind = RANDT_LOSS_NONE; l.scale = 1.0; l.alpha = 2.0; l.mu = 1.0; l.weight = 1.0;
+      if (loss) l = *loss;
+      if (ndt_weight > 0.0 && scan->n_cells > 0) l.weight = ndt_weight / ((double)scan->n_cells * (double)k);
+      rc = randt_register_batch(ctx, prob, 0, pose_io, &l, opt, res);
+    }
+    randt_problem_destroy(prob);
+  }
+  if (rc == RANDT_OK && (insert_keyframe || submap->n_cells == 0)) {
+    rc = randt_map_transform_se2d(ctx, scan, pose_io);
+    if (rc == RANDT_OK) rc = randt_map_merge(ctx, submap, scan);
+  }
+  randt_map_destroy(scan);
+  if (result) memcpy(result, res, sizeof(res));
+  return rc;
 }
 
 }  // extern "C"

@@ -141,7 +141,7 @@ cudaError_t launch_transform_cells(float4* d_cells, const uint32_t* d_cell_off, 
                                    cudaStream_t s, int* n_launches);
 cudaError_t launch_merge_maps(const float4* f_cells, const uint32_t* f_npts, const uint32_t* f_off, int32_t* f_slot, const float4* m_cells,
                               const uint32_t* m_npts, const uint32_t* m_off, uint32_t n_maps, const MapGeomDev& geom, const uint32_t* o_off,
-                              float4* o_cells, uint32_t* o_npts, uint32_t* o_count, cudaStream_t s, int* n_launches);
+                              float4* o_cells, uint32_t* o_npts, uint32_t* o_count, uint32_t max_m_per_map, cudaStream_t s, int* n_launches);
 
 // k4_lm_step.cu — per-segment state of the batched GNC + LM solver
 struct LmState {

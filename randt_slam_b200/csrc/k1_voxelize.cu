@@ -457,59 +457,93 @@ __global__ void transform_cells_kernel(float4* __restrict__ cells, const uint32_
   p[0] = q.a; p[1] = q.b; p[2] = q.c;
 }
 
-// Map::mergeMapCell + Cell::operator+=.  One warp per map; lane 0 walks the moving cells in order (the recursion is
-// sequential by construction: a mover may create the cell the next mover merges into).  Output region of map b has room for
-// n_f(b) + n_m(b) cells; the fixed slot table is updated in place.
-__global__ void merge_maps_kernel(const float4* __restrict__ f_cells, const uint32_t* __restrict__ f_npts, const uint32_t* __restrict__ f_off,
+// Cell::operator+= (ndt_cell.h:133-142) of the cell (bmu, bcov, nb) into the accumulated cell (amu, acov, na): unsigned / size_t weights
+// converted to float, (na * nb) / (na + nb) in integer arithmetic, population covariances weighted by n - 1.
+__device__ __forceinline__ void merge_cell(float* amu, float* acov, uint32_t& na, const float* bmu, const float* bcov, uint32_t nb) {
+  const float w1 = (float)((unsigned long long)na - 1ull);
+  const float w2 = (float)((unsigned long long)nb - 1ull);
+  const float w3 = (float)(((unsigned long long)na * (unsigned long long)nb) / ((unsigned long long)na + (unsigned long long)nb));
+  const float d[3] = {amu[0] - bmu[0], amu[1] - bmu[1], amu[2] - bmu[2]};
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) acov[r * 3 + c] = (w1 * acov[r * 3 + c] + w2 * bcov[r * 3 + c]) + w3 * (d[r] * d[c]);
+  const float n1 = (float)na, n2 = (float)(unsigned long long)nb, nn = (float)((unsigned long long)na + (unsigned long long)nb);
+  for (int r = 0; r < 3; ++r) amu[r] = ((amu[r] * n1) + (bmu[r] * n2)) / nn;
+  const uint32_t nsum = na + nb;
+  const float dn = (float)(nsum - 1u);
+  for (int e = 0; e < 9; ++e) acov[e] /= dn;
+  na = nsum;
+}
+__device__ __forceinline__ void load_cell(const float4* __restrict__ p, float* mu, float* cov) {
+  const float4 A = p[0], B = p[1], Cq = p[2];
+  mu[0] = A.x; mu[1] = A.y; mu[2] = A.z;
+  cov[0] = A.w; cov[1] = B.x; cov[2] = B.y; cov[3] = B.z; cov[4] = B.w; cov[5] = Cq.x; cov[6] = Cq.y; cov[7] = Cq.z; cov[8] = Cq.w;
+}
+
+// Map::mergeMapCell + Cell::operator+=, one CTA per map.  The reference walks the moving cells in order; a mover either merges into
+// the cell its slot holds or founds a new cell there (which later movers of the same slot then merge into).  Movers that target
+// DIFFERENT slots never interact, so the walk splits into independent chains — all movers of one slot, in mover order — and one
+// thread runs each chain with the reference's arithmetic; new cells are numbered in the order their founders appear.  Bit-identical
+// to the sequential walk.  Output region of map b has room for n_f(b) + n_m(b) cells; the fixed slot table is updated in place.
+// dynamic shared memory: uint32 target[nm_cap] (slot of every mover, 0xffffffff: outside the map)
+constexpr int kMergeThreads = 256;
+__global__ void __launch_bounds__(kMergeThreads) merge_maps_kernel(const float4* __restrict__ f_cells, const uint32_t* __restrict__ f_npts, const uint32_t* __restrict__ f_off,
                                   int32_t* __restrict__ f_slot, const float4* __restrict__ m_cells, const uint32_t* __restrict__ m_npts,
                                   const uint32_t* __restrict__ m_off, MapGeomDev geom, const uint32_t* __restrict__ o_off, float4* __restrict__ o_cells,
                                   uint32_t* __restrict__ o_npts, uint32_t* __restrict__ o_count) {
+  extern __shared__ uint32_t target[];
+  __shared__ unsigned long long warp_sums[32];
   const uint32_t b = blockIdx.x;
   const uint32_t f0 = f_off[b], nf = f_off[b + 1] - f0, m0 = m_off[b], nm = m_off[b + 1] - m0, o0 = o_off[b];
-  // copy the existing fixed cells (all lanes)
-  for (uint32_t e = threadIdx.x; e < nf * 3; e += blockDim.x) o_cells[3 * (size_t)o0 + e] = f_cells[3 * (size_t)f0 + e];
-  for (uint32_t e = threadIdx.x; e < nf; e += blockDim.x) o_npts[o0 + e] = f_npts[f0 + e];
-  __syncthreads();
-  if (threadIdx.x != 0) return;
-  int32_t* slot = f_slot + (size_t)b * geom.n_slots;
-  uint32_t count = nf;
-  for (uint32_t i = 0; i < nm; ++i) {
-    const float4 A = m_cells[3 * (size_t)(m0 + i)], Bq = m_cells[3 * (size_t)(m0 + i) + 1], Cq = m_cells[3 * (size_t)(m0 + i) + 2];
+  const int tid = threadIdx.x;
+  // copy the existing fixed cells (all threads)
+  for (uint32_t e = tid; e < nf * 3; e += kMergeThreads) o_cells[3 * (size_t)o0 + e] = f_cells[3 * (size_t)f0 + e];
+  for (uint32_t e = tid; e < nf; e += kMergeThreads) o_npts[o0 + e] = f_npts[f0 + e];
+  for (uint32_t i = tid; i < nm; i += kMergeThreads) {
+    const float4 A = m_cells[3 * (size_t)(m0 + i)];
     const uint32_t s = coord_to_index(geom, A.x, A.y);
-    if (s >= geom.n_slots) continue;
-    const int32_t idx = slot[s];
-    if (idx < 0) {
-      float4* dst = o_cells + 3 * (size_t)(o0 + count);
-      dst[0] = A; dst[1] = Bq; dst[2] = Cq;
-      o_npts[o0 + count] = m_npts[m0 + i];
-      slot[s] = (int32_t)count;
-      ++count;
-    } else {
+    target[i] = s < geom.n_slots ? s : 0xffffffffu;
+  }
+  __syncthreads();
+  int32_t* slot = f_slot + (size_t)b * geom.n_slots;
+  unsigned long long carry = 0ull;
+  for (uint32_t base = 0; base < nm; base += kMergeThreads) {
+    const uint32_t i = base + tid;
+    bool head = false, founds = false;
+    uint32_t s = 0xffffffffu;
+    if (i < nm) {
+      s = target[i];
+      head = s != 0xffffffffu;
+      for (uint32_t j = 0; head && j < i; ++j) head = target[j] != s;       // the first mover of its slot runs the slot's chain
+      founds = head && slot[s] < 0;
+    }
+    unsigned long long total;
+    const uint32_t rank = (uint32_t)(carry + block_scan_excl(founds ? 1ull : 0ull, warp_sums, &total));
+    carry += total;
+    if (head) {
+      float amu[3], acov[9], bmu[3], bcov[9];
+      uint32_t na, idx, j0;
+      if (founds) {
+        idx = nf + rank;
+        load_cell(m_cells + 3 * (size_t)(m0 + i), amu, acov); na = m_npts[m0 + i];
+        j0 = i + 1;
+      } else {
+        idx = (uint32_t)slot[s];
+        load_cell(o_cells + 3 * (size_t)(o0 + idx), amu, acov); na = o_npts[o0 + idx];
+        j0 = i;
+      }
+      for (uint32_t j = j0; j < nm; ++j) {
+        if (target[j] != s) continue;
+        load_cell(m_cells + 3 * (size_t)(m0 + j), bmu, bcov);
+        merge_cell(amu, acov, na, bmu, bcov, m_npts[m0 + j]);
+      }
       float4* dst = o_cells + 3 * (size_t)(o0 + idx);
-      const float4 FA = dst[0], FB = dst[1], FC = dst[2];
-      float amu[3] = {FA.x, FA.y, FA.z};
-      float acov[9] = {FA.w, FB.x, FB.y, FB.z, FB.w, FC.x, FC.y, FC.z, FC.w};
-      const float bmu[3] = {A.x, A.y, A.z};
-      const float bcov[9] = {A.w, Bq.x, Bq.y, Bq.z, Bq.w, Cq.x, Cq.y, Cq.z, Cq.w};
-      const uint32_t na = o_npts[o0 + idx], nb = m_npts[m0 + i];
-      // operator+= (ndt_cell.h:133-142): unsigned / size_t weights converted to float, (na*nb)/(na+nb) is integer division
-      const float w1 = (float)((unsigned long long)na - 1ull);
-      const float w2 = (float)((unsigned long long)nb - 1ull);
-      const float w3 = (float)(((unsigned long long)na * (unsigned long long)nb) / ((unsigned long long)na + (unsigned long long)nb));
-      const float d[3] = {amu[0] - bmu[0], amu[1] - bmu[1], amu[2] - bmu[2]};
-      for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) acov[r * 3 + c] = (w1 * acov[r * 3 + c] + w2 * bcov[r * 3 + c]) + w3 * (d[r] * d[c]);
-      const float n1 = (float)na, n2 = (float)(unsigned long long)nb, nn = (float)((unsigned long long)na + (unsigned long long)nb);
-      for (int r = 0; r < 3; ++r) amu[r] = ((amu[r] * n1) + (bmu[r] * n2)) / nn;
-      const uint32_t nsum = na + nb;
-      const float dn = (float)(nsum - 1u);
-      for (int e = 0; e < 9; ++e) acov[e] /= dn;
       dst[0] = make_float4(amu[0], amu[1], amu[2], acov[0]);
       dst[1] = make_float4(acov[1], acov[2], acov[3], acov[4]);
       dst[2] = make_float4(acov[5], acov[6], acov[7], acov[8]);
-      o_npts[o0 + idx] = nsum;
+      o_npts[o0 + idx] = na;
+      if (founds) slot[s] = (int32_t)idx;
     }
   }
-  o_count[b] = count;
+  if (tid == 0) o_count[b] = nf + (uint32_t)carry;
 }
 
 }  // namespace
@@ -587,9 +621,12 @@ cudaError_t launch_transform_cells(float4* d_cells, const uint32_t* d_cell_off, 
 
 cudaError_t launch_merge_maps(const float4* f_cells, const uint32_t* f_npts, const uint32_t* f_off, int32_t* f_slot, const float4* m_cells,
                               const uint32_t* m_npts, const uint32_t* m_off, uint32_t n_maps, const MapGeomDev& geom, const uint32_t* o_off,
-                              float4* o_cells, uint32_t* o_npts, uint32_t* o_count, cudaStream_t s, int* n_launches) {
+                              float4* o_cells, uint32_t* o_npts, uint32_t* o_count, uint32_t max_m_per_map, cudaStream_t s, int* n_launches) {
   if (n_maps == 0) return cudaSuccess;
-  merge_maps_kernel<<<n_maps, 64, 0, s>>>(f_cells, f_npts, f_off, f_slot, m_cells, m_npts, m_off, geom, o_off, o_cells, o_npts, o_count);
+  const size_t smem = (size_t)std::max(1u, max_m_per_map) * sizeof(uint32_t);
+  if (smem > 200u * 1024u) return cudaErrorInvalidValue;       // > 51 200 moving cells in one map
+  if (smem > 48u * 1024u) { cudaError_t e = cudaFuncSetAttribute(merge_maps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; }
+  merge_maps_kernel<<<n_maps, kMergeThreads, smem, s>>>(f_cells, f_npts, f_off, f_slot, m_cells, m_npts, m_off, geom, o_off, o_cells, o_npts, o_count);
   if (n_launches) *n_launches += 1;
   return cudaGetLastError();
 }

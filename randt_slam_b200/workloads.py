@@ -291,22 +291,15 @@ def device_replay(ctx, capi, p, scans, keyframe_every=2, submap_keyframes=None):
     opt = odometry_solver(capi, p)
     n = len(scans)
     poses = np.zeros((n, 4)); poses[0] = synth.pose_to_se2(0, 0, 0)
-    sub = ctx.voxelize(scans[0], [0, len(scans[0])], gp)
+    loss = capi.make_loss(capi.LOSS_BARRON, p.loss_function_scale, p.loss_function_convexity, 1.0, 1.0)
+    sub = ctx.map_upload(np.zeros((0, 12), np.float32), np.zeros(2, np.uint32), gp)
+    sub.scan_step(scans[0], gp, k, loss, p.ndt_weight, opt, True, poses[0])          # the first scan founds the submap
     iters = 0.0
     ctx.sync()
     t0 = time.perf_counter()
     for i in range(1, n):
-        mv = ctx.voxelize(scans[i], [0, len(scans[i])], gp)
-        guess = poses[i - 1:i]
-        prob = ctx.associate(sub, mv, guess, k)
-        loss = capi.make_loss(capi.LOSS_BARRON, p.loss_function_scale, p.loss_function_convexity, 1.0, p.ndt_weight / (mv.info()[1] * k))
-        pose, res = prob.register_batch(guess, loss, opt)
-        poses[i] = pose[0]
-        iters += float(res[0, capi.REG_ITERATIONS])
-        if i % keyframe_every == 0:
-            mv.transform(pose.astype(np.float32))
-            sub.merge(mv)
-        mv.close(); prob.close()
+        poses[i], res, _ = sub.scan_step(scans[i], gp, k, loss, p.ndt_weight, opt, i % keyframe_every == 0, poses[i - 1])     # one C-ABI call per scan
+        iters += float(res[capi.REG_ITERATIONS])
     ctx.sync()
     dt = time.perf_counter() - t0
     sub.close()
@@ -321,7 +314,9 @@ def oracle_replay(O, p, scans, keyframe_every=2):
     poses = np.zeros((n, 4)); poses[0] = synth.pose_to_se2(0, 0, 0)
     t0 = time.perf_counter()
     v0 = O.voxelize(scans[0], *va)
-    cells, npts, slot = v0["cells"], v0["npts"], v0["slot"]
+    # the first scan founds the submap as a keyframe at the identity (transformMap + mergeMapCell into the empty map, like every later one)
+    cells, npts, slot = O.merge_map_cell(np.zeros((0, 12), np.float32), np.zeros(0, np.uint32), np.full(p.size_x * p.size_y, -1, np.int32), p.size_x, p.size_y,
+                                         p.resolution, O.transform_cells(v0["cells"], 1.0, 0.0, 0.0, 0.0), v0["npts"])
     for i in range(1, n):
         v = O.voxelize(scans[i], *va)
         w = p.ndt_weight / (len(v["cells"]) * k)
