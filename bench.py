@@ -771,8 +771,27 @@ def main():
             nf_ = np.diff(host["f_off"]).astype(np.float64); nm_ = np.diff(host["m_off"]).astype(np.float64)
             cs_terms = float(np.sum(nf_ * nm_ + nf_ * (nf_ - 1) / 2 + nm_ * (nm_ - 1) / 2))
             Fm.close(); Mm.close()
+            pk_s, _ = peaks()
+            vox_bytes = 16 * len(pts_np) + 52 * int(n_cells_vox)          # 16 N_pts + 48 N_cells + 4 N_cells
+            # the same on 4096 scans per call (16 x the 256-scan batch)
+            pts_big = d_pts_all.repeat(16, 1).contiguous()
+            lens = np.diff(off_np.astype(np.int64))
+            off_big = np.concatenate([[0], np.cumsum(np.tile(lens, 16))]).astype(np.uint32)
+            ctx.voxelize(pts_big.data_ptr(), off_big, gp_, pts_on_device=True).close()
+            barrier(); t0 = time.perf_counter()
+            for _ in range(3):
+                mbig = ctx.voxelize(pts_big.data_ptr(), off_big, gp_, pts_on_device=True)
+                n_cells_big = mbig.info()[1]; mbig.close()
+            barrier(); t_big = (time.perf_counter() - t0) / 3
+            big_bytes = 16 * int(pts_big.shape[0]) + 52 * int(n_cells_big)
+            del pts_big
             stages = {"voxelize": {"points_per_s": len(pts_np) / t_vox, "scans_per_s": (len(off_np) - 1) / t_vox, "ms_per_call": t_vox * 1e3, "scans_per_call": len(off_np) - 1,
-                                   "points_per_call": int(len(pts_np)), "cells_per_call": int(n_cells_vox), "what": "randt_voxelize (K1), points resident, incl. per-call allocation and count readback"},
+                                   "points_per_call": int(len(pts_np)), "cells_per_call": int(n_cells_vox), "what": "randt_voxelize (K1), points resident, incl. per-call allocation and count readback",
+                                   "roofline": {"bound": "hbm", "achieved": vox_bytes / t_vox / 1e9, "peak": pk_s["hbm_gbs"], "unit": "GB/s", "frac": vox_bytes / t_vox / 1e9 / pk_s["hbm_gbs"],
+                                                "algorithmic_bytes_per_call": vox_bytes, "timing": "wall clock of the whole randt_voxelize call (allocation, K1, count readback, compaction)"},
+                                   "scans_4096": {"ms_per_call": t_big * 1e3, "points_per_s": 16 * len(pts_np) / t_big, "cells_per_call": int(n_cells_big),
+                                                  "roofline": {"bound": "hbm", "achieved": big_bytes / t_big / 1e9, "peak": pk_s["hbm_gbs"], "unit": "GB/s",
+                                                               "frac": big_bytes / t_big / 1e9 / pk_s["hbm_gbs"], "algorithmic_bytes_per_call": big_bytes}}},
                       "cs_divergence": {"map_pairs_per_s": S / t_cs, "gaussian_overlaps_per_s": cs_terms / t_cs, "ms_per_call": t_cs * 1e3, "map_pairs_per_call": S,
                                         "finite": bool(np.isfinite(cs_all).all()), "what": "randt_cs_divergence (K5), maps resident: all-pairs 3x3 inverse + det + exp"},
                       "associate": {"queries_per_s": st["n_m"] / t_as, "ms_per_call": t_as * 1e3, "queries_per_call": st["n_m"],
