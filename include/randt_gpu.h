@@ -92,7 +92,8 @@ enum {
   RANDT_PACKED_H = 0,      /* [10] upper triangle of the 4x4, row by row: 00 01 02 03 11 12 13 22 23 33 */
   RANDT_PACKED_G = 10,     /* [4] */
   RANDT_PACKED_COST = 14, RANDT_PACKED_MAXR = 15, RANDT_PACKED_SUMSQ = 16, RANDT_PACKED_N = 17,
-  RANDT_PACKED_STRIDE = 18
+  RANDT_PACKED_STRIDE = 18,
+  RANDT_CORE_STRIDE = 15   /* packed == 2: the first 15 entries of the packed record (H upper triangle, g, cost) — what one LM iteration consumes */
 };
 
 typedef struct randt_ctx randt_ctx;
@@ -224,7 +225,8 @@ RANDT_API int randt_eval_fused(randt_ctx* ctx, const randt_problem* p, int varia
  * poses, mu_per_seg and out must be pinned host memory (randt_host_alloc); the upload of call i+1 and the copy-out of call i-1 overlap
  * the kernel of call i (two copy streams, two device slots each way).  The buffers of a call may be read / reused after
  * randt_ctx_sync(), or once call i+2 has left the context's stream; give the calls in flight their own buffers.
- * packed != 0: `out` receives RANDT_PACKED_STRIDE doubles per segment (layout RANDT_PACKED_*) instead of RANDT_FUSED_STRIDE — the
+ * packed == 1: `out` receives RANDT_PACKED_STRIDE doubles per segment (layout RANDT_PACKED_*) instead of RANDT_FUSED_STRIDE; packed == 2:
+ * RANDT_CORE_STRIDE doubles (the packed record without max r, sum r^2, n: the normal equations and the cost, 120 bytes) — the
  * copy-out is what bounds a pipelined step, and a quarter of the full record is the mirrored half of H. */
 RANDT_API int randt_eval_fused_async(randt_ctx* ctx, const randt_problem* p, int variant, const double* poses, const randt_loss* loss,
                                      const double* mu_per_seg, int want_jac, int packed, double* out);

@@ -16,6 +16,7 @@ LOSS_NONE, LOSS_BARRON, LOSS_WELSCH = 0, 1, 2
 LOOKUP_MAHALANOBIS, LOOKUP_EUCLID = 0, 1
 FUSED_STRIDE = 24
 FUSED_H, FUSED_G, FUSED_COST, FUSED_MAXR, FUSED_SUMSQ, FUSED_N = 0, 16, 20, 21, 22, 23   # RANDT_FUSED_* of include/randt_gpu.h
+CORE_STRIDE = 15                                                                         # RANDT_CORE_STRIDE: packed == 2 (H upper triangle, g, cost)
 PACKED_STRIDE = 18                                                                       # RANDT_PACKED_*: H upper triangle (10), g (4), cost, max r, sum r^2, n
 _PACKED_SRC = [0, 1, 2, 3, 5, 6, 7, 10, 11, 15, 16, 17, 18, 19, 20, 21, 22, 23]
 

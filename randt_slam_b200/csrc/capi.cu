@@ -889,27 +889,29 @@ int randt_eval_emit(randt_ctx* ctx, const randt_problem* cp, int variant, const 
 
 namespace {
 int eval_fused_dev_impl(randt_ctx* ctx, const randt_problem* p, int variant, const double* d_poses, const randt_loss* loss,
-                        const double* d_mu_per_seg, int want_jac, double* d_out, bool packed);
+                        const double* d_mu_per_seg, int want_jac, double* d_out, int packed);
+inline size_t out_stride(int packed) { return packed == 1 ? RANDT_PACKED_STRIDE : (packed == 2 ? RANDT_CORE_STRIDE : RANDT_FUSED_STRIDE); }
 }
 int randt_eval_fused_dev(randt_ctx* ctx, const randt_problem* p, int variant, const double* d_poses, const randt_loss* loss,
                          const double* d_mu_per_seg, int want_jac, double* d_out) {
-  return eval_fused_dev_impl(ctx, p, variant, d_poses, loss, d_mu_per_seg, want_jac, d_out, false);
+  return eval_fused_dev_impl(ctx, p, variant, d_poses, loss, d_mu_per_seg, want_jac, d_out, 0);
 }
 namespace {
 int eval_fused_dev_impl(randt_ctx* ctx, const randt_problem* p, int variant, const double* d_poses, const randt_loss* loss,
-                        const double* d_mu_per_seg, int want_jac, double* d_out, bool packed) {
+                        const double* d_mu_per_seg, int want_jac, double* d_out, int packed) {
   if (!ctx || !p || !d_poses || !d_out) return fail(ctx, RANDT_E_INVALID, "randt_eval_fused_dev: null argument");
+  if (packed < 0 || packed > 2) return fail(ctx, RANDT_E_INVALID, "randt_eval_fused: packed must be 0, 1 or 2");
   if (check_variant(ctx, variant)) return RANDT_E_INVALID;
   LossParams lp;
   if (int rc = make_loss(ctx, loss, &lp)) return rc;
   CK(cudaSetDevice(ctx->device));
   StreamScope scope__(ctx->stream, ctx->sref->pool);
   // segments without pairs produce no tile: clear their records up front
-  if (p->has_empty_segment) CK(cudaMemsetAsync(d_out, 0, (size_t)p->S * (packed ? RANDT_PACKED_STRIDE : RANDT_FUSED_STRIDE) * sizeof(double), ctx->stream));
+  if (p->has_empty_segment) CK(cudaMemsetAsync(d_out, 0, (size_t)p->S * out_stride(packed) * sizeof(double), ctx->stream));
   int nl = 0;
   DeviceProblem v = view(p);
   v.chunks = p->chunks_full; v.n_chunks = p->n_chunks_full; v.warp_off = p->warp_off_full;   // every segment is evaluated: packed schedule
-  v.out_packed = packed ? 1u : 0u;
+  v.out_packed = (uint32_t)packed;
   CK(launch_eval_fused(v, variant, d_poses, lp, d_mu_per_seg, want_jac != 0, d_out, ctx->d_bad, ctx->stream, &nl));
   ctx->launches += nl;
   return RANDT_OK;
@@ -998,7 +1000,8 @@ int randt_eval_fused_async(randt_ctx* ctx, const randt_problem* cp, int variant,
   CK(cudaStreamWaitEvent(ctx->stream, r.ev_in[slot], 0));
   // Records go to a device slot and leave on a third stream: a DMA copy moves the 192 S bytes at the full PCIe rate while the next
   // call's kernel runs (stores from the kernel straight into mapped host memory, as the blocking call does, reach ~3/4 of that rate).
-  const size_t n_out = (size_t)p->S * (packed ? RANDT_PACKED_STRIDE : RANDT_FUSED_STRIDE);   // K3 writes either layout itself
+  if (packed < 0 || packed > 2) return fail(ctx, RANDT_E_INVALID, "randt_eval_fused_async: packed must be 0, 1 or 2");
+  const size_t n_out = (size_t)p->S * out_stride(packed);   // K3 writes the layout itself
   CK(cudaStreamWaitEvent(ctx->stream, r.ev_d2h[slot], 0));     // the copy-out of two calls ago has drained this slot
   if (r.oring_cap[slot] < n_out) {
     if (r.oring[slot]) CK(cudaFreeAsync(r.oring[slot], ctx->stream));
@@ -1007,7 +1010,7 @@ int randt_eval_fused_async(randt_ctx* ctx, const randt_problem* cp, int variant,
     r.oring_cap[slot] = n_out;
   }
   double* d_out = r.oring[slot];
-  int rc = eval_fused_dev_impl(ctx, p, variant, d_in, loss, mu_per_seg ? d_in + n_pose : nullptr, want_jac, d_out, packed != 0);
+  int rc = eval_fused_dev_impl(ctx, p, variant, d_in, loss, mu_per_seg ? d_in + n_pose : nullptr, want_jac, d_out, packed);
   if (rc) return rc;
   const double* d_ship = d_out; const size_t n_ship = n_out;
   CK(cudaEventRecord(r.ev_done[slot], ctx->stream));
@@ -1259,26 +1262,39 @@ int randt_scan_step(randt_ctx* ctx, randt_map* submap, const float* pts4, uint32
                     uint32_t* n_cells_out) {
   if (!ctx || !submap || !gp || !opt || !pose_io || (!pts4 && n_pts)) return fail(ctx, RANDT_E_INVALID, "randt_scan_step: null argument");
   if (submap->B != 1) return fail(ctx, RANDT_E_INVALID, "randt_scan_step: the submap must be a single map");
+  static const bool trace = getenv("RANDT_DEBUG_TIMING") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!trace) return;
+    auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "[randt] scan_step %-12s %8.1f us\n", what, std::chrono::duration<double, std::micro>(t - t_prev).count());
+    t_prev = t;
+  };
   const uint32_t off[2] = {0u, n_pts};
   randt_map* scan = nullptr;
   int rc = randt_voxelize(ctx, pts4, off, 1, gp, 0, &scan);
   if (rc != RANDT_OK) return rc;
+  lap("voxelize");
   if (n_cells_out) *n_cells_out = scan->n_cells;
   double res[RANDT_REG_STRIDE] = {0};
   if (submap->n_cells > 0) {
     randt_problem* prob = nullptr;
     rc = randt_associate(ctx, submap, scan, pose_io, k, metric, &prob);
+    lap("associate");
     if (rc == RANDT_OK) {
       randt_loss l; l.kind = RANDT_LOSS_NONE; l.scale = 1.0; l.alpha = 2.0; l.mu = 1.0; l.weight = 1.0;
       if (loss) l = *loss;
       if (ndt_weight > 0.0 && scan->n_cells > 0) l.weight = ndt_weight / ((double)scan->n_cells * (double)k);
       rc = randt_register_batch(ctx, prob, 0, pose_io, &l, opt, res);
+      lap("register");
     }
     randt_problem_destroy(prob);
+    lap("destroy");
   }
   if (rc == RANDT_OK && (insert_keyframe || submap->n_cells == 0)) {
     rc = randt_map_transform_se2d(ctx, scan, pose_io);
     if (rc == RANDT_OK) rc = randt_map_merge(ctx, submap, scan);
+    lap("keyframe");
   }
   randt_map_destroy(scan);
   if (result) memcpy(result, res, sizeof(res));

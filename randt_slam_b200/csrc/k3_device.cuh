@@ -172,9 +172,10 @@ __device__ __forceinline__ double pair_core(const PoseConst& k, const RawCell& m
 __device__ __forceinline__ bool dd_valid(double dd) { return (dd >= 0.0) && (dd < 1.0e300); }   // false for NaN, inf, negative
 
 // ---- loss: w = weight*rho'(s), hrho = weight*rho(s)/2, wd = w/s (finite garbage when s == 0: it only multiplies N = 0) ----
-template <int LOSS>
+// POS: the caller guarantees s > 0 (the select-free fast path)
+template <int LOSS, bool POS = false>
 __device__ __forceinline__ void loss_eval(double s, const LossConst& k, double& w, double& hrho, double& wd) {
-  const bool pos = s > 0.0;
+  const bool pos = POS || s > 0.0;
   if (LOSS == L_BARRON_M2) {                    // alpha = -2: rho = pre (1/u - 1), rho' = pre e ts / u^2, u = s ts + 1
     const double u = fma(s, k.ts, 1.0);
     const double v = (u * u) * s;
@@ -385,7 +386,9 @@ __device__ __forceinline__ void write_segment_out(double mine, double max_dd, do
   if (!packed) {
     if (e < RANDT_FUSED_STRIDE) out_base[(size_t)seg * RANDT_FUSED_STRIDE + e] = val;
   } else if (omap & 0x4000u) {
-    out_base[(size_t)seg * RANDT_PACKED_STRIDE + ((omap >> 9) & 31u)] = val;
+    const uint32_t pk = (omap >> 9) & 31u;
+    if (packed == 1u) out_base[(size_t)seg * RANDT_PACKED_STRIDE + pk] = val;
+    else if (pk < (uint32_t)RANDT_CORE_STRIDE) out_base[(size_t)seg * RANDT_CORE_STRIDE + pk] = val;     // packed == 2: H, g, cost only
   }
 }
 
@@ -609,14 +612,13 @@ __device__ __forceinline__ void accumulate_duo(const PoseConst& kc, const LossCo
 #pragma unroll
   for (int j = 0; j < 2; ++j) dd[j] = fixed_part<VARIANT, WANT_JAC>(kc, mv, f[j], N[j]);
 #pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    ok[j] = dd_valid(dd[j]);
-    loss_eval<LOSS>(dd[j], lc, wgt[j], hrho[j], wd[j]);
-  }
+  for (int j = 0; j < 2; ++j) ok[j] = dd_valid(dd[j]);
   const bool use1 = two && ok[1];
-  // Nearly every duo is complete and well-conditioned: when that holds for all lanes that are here, the sums are updated without the
-  // per-accumulator selects of the general path (a warp-uniform branch).
-  if (__all_sync(__activemask(), ok[0] && use1)) {
+  // Nearly every duo is complete, well-conditioned and off the r = 0 corner: when that holds for all lanes that are here, loss and sums
+  // run without the guards and per-accumulator selects of the general path (a warp-uniform branch).
+  if (__all_sync(__activemask(), ok[0] && use1 && dd[0] > 0.0 && dd[1] > 0.0)) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) loss_eval<LOSS, true>(dd[j], lc, wgt[j], hrho[j], wd[j]);
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       if (WANT_JAC) {
@@ -635,6 +637,8 @@ __device__ __forceinline__ void accumulate_duo(const PoseConst& kc, const LossCo
     max_dd = fmax(max_dd, fmax(dd[0], dd[1]));
     return;
   }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) loss_eval<LOSS>(dd[j], lc, wgt[j], hrho[j], wd[j]);
   n_bad += (ok[0] ? 0u : 1u) + ((two && !ok[1]) ? 1u : 0u);
 #pragma unroll
   for (int j = 0; j < 2; ++j) {

@@ -135,13 +135,16 @@ __global__ void __launch_bounds__(kK3Threads, kMinCtas) k3_fused_kernel(DevicePr
 #pragma unroll
       for (int e = 0; e < NS; ++e) c[e] = 0.0;
       if ((uint32_t)lane < n_here) accumulate_duo<VARIANT, LOSS, WANT_JAC, NS>(kc_all[warp][my], lc_all[warp][my], sb->rec, P.duo_overflow, lane, c, mc, cb);
+      // lanes of the finishing tile add their duo to its sums, lanes of the starting tile keep theirs for the next: 0/1 masks instead of
+      // per-accumulator selects (the private sums are finite: degenerate pairs never enter them)
+      const double m_old = mine_new ? 0.0 : 1.0, m_new = mine_new ? 1.0 : 0.0;
       double vals[NS];
 #pragma unroll
-      for (int e = 0; e < NS; ++e) vals[e] = acc[e] + (mine_new ? 0.0 : c[e]);
+      for (int e = 0; e < NS; ++e) vals[e] = fma(c[e], m_old, acc[e]);
       finish_tile<VARIANT, WANT_JAC, NS>(P, vals, fmax(max_dd, mine_new ? 0.0 : mc), n_bad + (mine_new ? 0u : cb), cm.seg, true, 0u, kc_all[warp][ts],
                                          np_all[warp][ts], omap, scratch, out, bad_counter, lane);
 #pragma unroll
-      for (int e = 0; e < NS; ++e) acc[e] = mine_new ? c[e] : 0.0;
+      for (int e = 0; e < NS; ++e) acc[e] = fma(c[e], m_new, 0.0);      // (+0 addend: a negative private sum times 0 must not leave -0)
       max_dd = mine_new ? mc : 0.0; n_bad = mine_new ? cb : 0u;
       if (cm.meta & kChunkNewLast) {      // the second tile is shorter than the rest of the chunk: it ends here too
         finish_tile<VARIANT, WANT_JAC, NS>(P, acc, max_dd, n_bad, cm.part, true, 0u, kc_all[warp][ts ^ 1], np_all[warp][ts ^ 1], omap, scratch, out, bad_counter, lane);
