@@ -16,7 +16,7 @@ def test_algorithmic_bytes_formula():
 
 def test_traffic_comes_from_the_final_capture():
     t = bench.measured_traffic(2941151)
-    txt = open(os.path.join(ROOT, "profiles", "r01_k3_fused_final_ncu_summary.txt")).read()
+    txt = open(os.path.join(ROOT, "profiles", "r02_k3_fused_final_ncu_summary.txt")).read()     # the latest round's `final` capture wins
     import re
     rd = float(re.search(r"dram__bytes_read\.sum\s+Mbyte\s+([\d.]+)", txt).group(1)); wr = float(re.search(r"dram__bytes_write\.sum\s+Mbyte\s+([\d.]+)", txt).group(1))
     assert abs(t - (rd + wr) * 1e6) < 1.0
@@ -26,6 +26,26 @@ def test_traffic_comes_from_the_final_capture():
 def test_workload_names():
     assert "Oxford-shape" in bench.workload_name(P.OXFORD) and "oxford params" in bench.workload_name(P.OXFORD)
     assert "indoor params" in bench.workload_name(P.INDOOR)
+
+
+def test_round2_bench_line_carries_every_config():
+    d = json.load(open(os.path.join(ROOT, "profiles", "r02_bench_final.json")))
+    assert d["metric"] == bench.METRIC and d["roofline"]["frac"] >= 0.60 and d["gpu_launches"] == d["steps"]
+    # DRAM traffic of the dominant kernel no longer exceeds its algorithmic bytes (round 1: 1.25 x)
+    assert d["roofline"]["traffic"] <= 1.05 * d["roofline"]["algorithmic_bytes_per_launch"]
+    c = d["configs"]
+    assert set(c) >= {"c0", "c1", "c2", "c3", "c4"}
+    assert c["c0"]["max_rel_err_r_vs_oracle"] < 1e-9 and c["c2"]["gpu_vs_oracle_max_rel_err_first_problem"] < 1e-9
+    assert c["c2"]["all_pairs"]["pairs_used_first_problem"] == 2000 * 8000 and "not run" in c["c2"]["se3_imu"]
+    assert c["c3"]["registrations"] == 256 and c["c3"]["failed"] == 0 and c["c3"]["scaling"] == "strong" and len(c["c3"]["table_sha256"]) == 64
+    assert c["c4"]["scans"] == 8609 and c["c4"]["scans_per_s"] > 3 * c["c4"]["cpu_baseline"]["scans_per_s"] * 0.9
+    r = d["registrations"]
+    assert r["launches_per_batch"] == 1 and r["failed"] == 0 and r["value"] > 2.5e6
+    e = d["e2e"]
+    assert e["d2h_bytes_per_step"] == d["config"]["problems_per_gpu"] * 8 * 15 and e["results_equal_blocking_call"]
+    # the literal batch gives the same table on 1, 2, 4 and 8 GPUs
+    s = json.load(open(os.path.join(ROOT, "profiles", "r02_scaling_1_2_4_8.json")))
+    assert len({s[n]["configs_c3"]["table_sha256"] for n in ("1", "2", "4", "8")}) == 1
 
 
 def test_committed_bench_line_keeps_the_contract():
