@@ -212,13 +212,23 @@ __global__ void __launch_bounds__(kVoxThreads) k1_voxelize_kernel(const float4* 
   if (warp < n_cnt_warps) {
     const uint32_t s0 = warp * slice, s1 = min(n, s0 + slice);
     unsigned short* h = whist + (size_t)warp * span_cap;
-    for (uint32_t base = s0; base < s1; base += 32) {
-      const uint32_t e = base + lane;
-      const bool act = e < s1;
-      const uint32_t bin = act ? (uint32_t)(labels_scratch[p0 + e] - lab_min) : 0xffffffffu;
-      const unsigned peers = __match_any_sync(0xffffffffu, bin);
-      if (act && (__ffs(peers) - 1) == lane) h[bin] = (unsigned short)(h[bin] + __popc(peers));
-      __syncwarp();
+    // the slice is walked 32 points at a time in scan order (each step updates the histogram the next one reads), but the labels of
+    // eight steps are fetched up front: the global-memory latency is paid once per eight steps instead of once per step
+    for (uint32_t base = s0; base < s1; base += 32u * 8u) {
+      uint32_t bins[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const uint32_t e = base + 32u * (uint32_t)u + lane;
+        bins[u] = e < s1 ? (uint32_t)(labels_scratch[p0 + e] - lab_min) : 0xffffffffu;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (base + 32u * (uint32_t)u >= s1) break;          // warp-uniform
+        const uint32_t bin = bins[u];
+        const unsigned peers = __match_any_sync(0xffffffffu, bin);
+        if (bin != 0xffffffffu && (__ffs(peers) - 1) == lane) h[bin] = (unsigned short)(h[bin] + __popc(peers));
+        __syncwarp();
+      }
     }
   }
   __syncthreads();
@@ -259,21 +269,31 @@ __global__ void __launch_bounds__(kVoxThreads) k1_voxelize_kernel(const float4* 
   if (warp < n_cnt_warps) {
     const uint32_t s0 = warp * slice, s1 = min(n, s0 + slice);
     unsigned short* h = whist + (size_t)warp * span_cap;
-    for (uint32_t base = s0; base < s1; base += 32) {
-      const uint32_t e = base + lane;
-      const bool act = e < s1;
-      const uint32_t bin = act ? (uint32_t)(labels_scratch[p0 + e] - lab_min) : 0xffffffffu;
-      const unsigned peers = __match_any_sync(0xffffffffu, bin);
-      const int leader = __ffs(peers) - 1;
-      uint32_t off = 0;
-      if (act && leader == lane) { off = h[bin]; h[bin] = (unsigned short)(off + __popc(peers)); }
-      off = __shfl_sync(0xffffffffu, off, leader);
-      if (act && bin_keep[bin] != kNotKept) {
-        const float4 p = __ldg(pts + p0 + e);
-        const uint32_t at = bin_start[bin] + off + __popc(peers & ((1u << lane) - 1u));
-        sx[at] = p.x; sy[at] = p.y; si[at] = p.w;
+    for (uint32_t base = s0; base < s1; base += 32u * 4u) {       // labels and points of four steps fetched up front (see phase 1)
+      uint32_t bins[4]; float4 pp[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t e = base + 32u * (uint32_t)u + lane;
+        const bool act = e < s1;
+        bins[u] = act ? (uint32_t)(labels_scratch[p0 + e] - lab_min) : 0xffffffffu;
+        pp[u] = act ? __ldg(pts + p0 + e) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      __syncwarp();
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (base + 32u * (uint32_t)u >= s1) break;          // warp-uniform
+        const uint32_t bin = bins[u];
+        const bool act = bin != 0xffffffffu;
+        const unsigned peers = __match_any_sync(0xffffffffu, bin);
+        const int leader = __ffs(peers) - 1;
+        uint32_t off = 0;
+        if (act && leader == lane) { off = h[bin]; h[bin] = (unsigned short)(off + __popc(peers)); }
+        off = __shfl_sync(0xffffffffu, off, leader);
+        if (act && bin_keep[bin] != kNotKept) {
+          const uint32_t at = bin_start[bin] + off + __popc(peers & ((1u << lane) - 1u));
+          sx[at] = pp[u].x; sy[at] = pp[u].y; si[at] = pp[u].w;
+        }
+        __syncwarp();
+      }
     }
   }
   __syncthreads();
