@@ -277,6 +277,30 @@ def run_configs(args, ctx, capi, stream, rank, world, local, barrier):
     # ---- c0 ----
     if rank == 0:
         out["c0"] = W.run_c0(ctx, capi, oracle)
+    # ---- c1 (indoor reading): BASELINE.json words configs[1] as "indoor params"; the headline follows SURVEY 8d (oxford parameters) ----
+    if args.c1_indoor_problems > 0 and args.preset != "indoor":
+        pi = P.PRESETS["indoor"]
+        prob_i, poses_i, st_i, _ = build_problem(ctx, capi, pi, args.c1_indoor_problems, args.seed)
+        loss_i = capi.make_loss(capi.LOSS_BARRON, pi.loop_closure_scale, pi.loss_function_convexity, 1.0, 1.0)
+        d_pi = torch.from_numpy(poses_i).to(dev); d_oi = torch.zeros((st_i["segments"], capi.FUSED_STRIDE), dtype=torch.float64, device=dev)
+        for _ in range(5):
+            prob_i.eval_fused_dev(d_pi.data_ptr(), d_oi.data_ptr(), loss_i)
+        barrier()
+        ei0, ei1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ei0.record(stream)
+        for _ in range(50):
+            prob_i.eval_fused_dev(d_pi.data_ptr(), d_oi.data_ptr(), loss_i)
+        ei1.record(stream)
+        barrier()
+        ms_i = ei0.elapsed_time(ei1) / 50
+        alg_i = algorithmic_bytes(st_i)
+        out["c1_indoor"] = {"workload": workload_name(pi), "problems_per_gpu": st_i["segments"], "pairs_per_gpu": st_i["pairs"], "k": pi.n_results_nn_lookup,
+                            "ms_per_step": ms_i, "pairs_per_s_per_gpu": st_i["pairs"] / (ms_i * 1e-3),
+                            "roofline": {"bound": "hbm", "achieved": alg_i / (ms_i * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                         "frac": alg_i / (ms_i * 1e-3) / 1e9 / pk["hbm_gbs"], "algorithmic_bytes_per_launch": alg_i, "bytes_per_pair": alg_i / st_i["pairs"]},
+                            "note": "same kernel, k = 4: every moving cell is shared by four pairs, so the algorithmic bytes per pair are lower; the pair rate is what the kernel is bound by"}
+        prob_i.close()
+        del d_pi, d_oi
     # ---- c2: configs[2] shape with the reference's SE(2) + intensity functor and kNN pair list ----
     if args.c2_problems > 0:
         prob, poses, host = W.build_c2(ctx, capi, args.c2_problems)
@@ -472,6 +496,7 @@ def main():
     ap.add_argument("--pre-scans", type=int, default=8, help="raw Oxford-size scans in the preprocessing leg (0 disables it)")
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--no-configs", action="store_true", help="skip the configs leg (c0, c2, c3, c4 sub-records)")
+    ap.add_argument("--c1-indoor-problems", type=int, default=16384, help="problems of the indoor-parameter reading of configs[1] (c1_indoor sub-record; 0 disables)")
     ap.add_argument("--c2-problems", type=int, default=384, help="configs[2]-shaped problems (2 k x 8 k cells) evaluated per step in the c2 sub-record")
     ap.add_argument("--c2-allpairs-problems", type=int, default=16, help="problems of the c2 all-pairs variant (16 M pairs each)")
     ap.add_argument("--c3-batch", type=int, default=256, help="registrations of the literal configs[3] batch (sharded over the ranks)")

@@ -135,6 +135,11 @@ typedef struct randt_filter_params {
   double beam_distance_increment_threshold;     /* radar_preprocessor/beam_distance_increment_threshold */
   float sensor_to_base[12];                     /* row-major 3x4 of initial_transform_radar_baselink (Eigen::Affine3f) */
 } randt_filter_params;
+/* pcl::PointXYZI records as PCL lays them out (32 bytes: x, y, z, 1 | intensity, 3 pad floats; what `cloud.points.data()` points at in
+ * RadarPreprocessor::filterScan's input, radar_preprocessor.cpp:45-51) -> the path's (x, y, 0, intensity) float4 points in DEVICE memory
+ * d_out4 (n * 16 bytes), ready for randt_filter_scan(raw_on_device = 1) or randt_voxelize(pts_on_device = 1): the caller hands the PCL
+ * buffer over as it is instead of repacking 1.2 M points per scan on the host.  pcl_points: host (on_device = 0) or device memory. */
+RANDT_API int randt_points_from_pcl_xyzi(randt_ctx* ctx, const void* pcl_points, uint32_t n, int on_device, float* d_out4);
 RANDT_API int randt_filter_scan(randt_ctx* ctx, const float* raw4, uint32_t n_azimuths, uint32_t n_bins, const randt_filter_params* params,
                                 int raw_on_device, float* out4, int out_on_device, uint32_t cap, uint32_t* n_out);
 /* The same for n_scans scans of one shape laid back to back in raw4 (several sequences replayed side by side, or a backlog of one):

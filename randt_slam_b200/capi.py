@@ -117,6 +117,7 @@ _SIGS = {
     "randt_problem_create": (_i, [_vp, _vp, _u32, _vp, _u32, _vp, _vp, _u32, _vp, _u32, C.POINTER(_vp)]),
     "randt_problem_info": (_i, [_vp, C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_u32)]),
     "randt_register_batch_weighted": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "randt_points_from_pcl_xyzi": (_i, [_vp, _vp, _u32, _i, _vp]),
     "randt_scan_step": (_i, [_vp, _vp, _vp, _u32, _vp, _i, _i, _vp, C.c_double, _vp, _i, _vp, _vp, _vp]),
     "randt_eval_allpairs": (_i, [_vp, _vp, _vp, _i, _vp, _vp, C.c_double, _vp]),
     "randt_eval_allpairs_dev": (_i, [_vp, _vp, _vp, _i, _vp, _vp, C.c_double, _vp]),
@@ -230,6 +231,11 @@ class Context:
         n = C.c_uint32(0)
         self._check(lib().randt_filter_scan(self._h, _ptr(raw4), int(n_azimuths), int(n_bins), C.byref(fp), 0, _ptr(out), 0, cap, C.byref(n)))
         return out[: n.value].copy()
+
+    def points_from_pcl_xyzi(self, pcl_points, d_out4):
+        """pcl::PointXYZI records (float32 [n, 8] host array: x, y, z, 1, intensity, pad x 3) -> float4 points at the device pointer d_out4"""
+        a = _f32(pcl_points, (-1, 8))
+        self._check(lib().randt_points_from_pcl_xyzi(self._h, _ptr(a), C.c_uint32(len(a)), 0, C.c_void_p(int(d_out4))))
 
     def filter_scan_dev(self, d_raw, n_azimuths, n_bins, fp, d_out, cap):
         """device pointers in and out (ints); returns the number of kept points"""

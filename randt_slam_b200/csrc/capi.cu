@@ -452,6 +452,28 @@ int randt_voxelize(randt_ctx* ctx, const float* pts4, const uint32_t* scan_off, 
   return RANDT_OK;
 }
 
+// pcl::PointXYZI records (32 bytes each, cloud.points.data()) -> the path's float4 points on the device
+int randt_points_from_pcl_xyzi(randt_ctx* ctx, const void* pcl_points, uint32_t n, int on_device, float* d_out4) {
+  if (!ctx || (!pcl_points && n) || (!d_out4 && n)) return fail(ctx, RANDT_E_INVALID, "randt_points_from_pcl_xyzi: null argument");
+  CK(cudaSetDevice(ctx->device));
+  StreamScope scope__(ctx->stream, ctx->sref->pool);
+  if (n == 0) return RANDT_OK;
+  const void* d_in = pcl_points; void* d_tmp = nullptr;
+  int nl = 0;
+  cudaError_t e = cudaSuccess;
+  if (!on_device) {
+    unsigned char* t = nullptr;
+    e = dev_alloc(&t, (size_t)n * 32);
+    d_tmp = t; d_in = t;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_tmp, pcl_points, (size_t)n * 32, cudaMemcpyHostToDevice, ctx->stream);
+  }
+  if (e == cudaSuccess) e = launch_pcl_xyzi_to_float4(d_in, n, reinterpret_cast<float4*>(d_out4), ctx->stream, &nl);
+  dev_free(d_tmp);
+  if (e != cudaSuccess) return fail(ctx, RANDT_E_CUDA, "randt_points_from_pcl_xyzi", e);
+  ctx->launches += nl;
+  return RANDT_OK;
+}
+
 int randt_filter_scan(randt_ctx* ctx, const float* raw4, uint32_t n_az, uint32_t n_bins, const randt_filter_params* fp, int raw_on_device,
                       float* out4, int out_on_device, uint32_t cap, uint32_t* n_out) {
   if (!ctx || !fp || !n_out || (!raw4 && n_az && n_bins) || (!out4 && cap)) return fail(ctx, RANDT_E_INVALID, "randt_filter_scan: null argument");

@@ -194,6 +194,8 @@ cudaError_t launch_filter_scans(const float4* d_raw, uint32_t n_scans, uint32_t 
 cudaError_t launch_filter_scan(const float4* d_raw, uint32_t n_az, uint32_t n_bins, const randt_filter_params& fp, uint32_t* d_peak, float* d_angle,
                                float4* d_out, uint32_t cap, uint32_t* d_n_out, int* d_status, cudaStream_t s, int* n_launches);
 
+cudaError_t launch_pcl_xyzi_to_float4(const void* d_in32, uint32_t n, float4* d_out, cudaStream_t s, int* n_launches);
+
 // static_cast<unsigned>(double) as x86-64 gcc defines it for negative inputs: truncate to int64, keep the low 32 bits
 __host__ __device__ inline uint32_t to_u32_trunc(double v) {
   if (!(v > -9.2e18 && v < 9.2e18)) return 0u;

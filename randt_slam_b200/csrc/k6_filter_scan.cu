@@ -185,6 +185,21 @@ __global__ void __launch_bounds__(1024) k6_runs_kernel(const float4* __restrict_
 
 }  // namespace
 
+// pcl::PointXYZI as PCL lays it out (32 bytes: x, y, z, 1.0f | intensity, 3 pad floats; pcl/impl/point_types.hpp) -> the path's float4
+// (x, y, 0, intensity): one thread per point, two 16-byte loads, one 16-byte store.  Lets the caller hand cloud.points.data() over as it is.
+__global__ void __launch_bounds__(256) pcl_xyzi_to_float4_kernel(const float4* __restrict__ in, uint32_t n, float4* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 a = __ldg(in + 2 * (size_t)i), b = __ldg(in + 2 * (size_t)i + 1);
+  out[i] = make_float4(a.x, a.y, 0.0f, b.x);
+}
+cudaError_t launch_pcl_xyzi_to_float4(const void* d_in32, uint32_t n, float4* d_out, cudaStream_t s, int* n_launches) {
+  if (n == 0) return cudaSuccess;
+  pcl_xyzi_to_float4_kernel<<<(n + 255u) / 256u, 256, 0, s>>>(static_cast<const float4*>(d_in32), n, d_out);
+  if (n_launches) *n_launches += 1;
+  return cudaGetLastError();
+}
+
 cudaError_t launch_filter_scan(const float4* d_raw, uint32_t n_az, uint32_t n_bins, const randt_filter_params& fp, uint32_t* d_peak, float* d_angle,
                                float4* d_out, uint32_t cap, uint32_t* d_n_out, int* d_status, cudaStream_t s, int* n_launches) {
   if (n_az == 0 || n_bins == 0) return cudaMemsetAsync(d_n_out, 0, sizeof(uint32_t), s);

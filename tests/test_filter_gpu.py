@@ -142,3 +142,24 @@ def test_filter_scans_batch_equals_scan_by_scan(oracle, gpu_ctx):
     with pytest.raises(capi.RandtError) as e:
         gpu_ctx.filter_scans(np.concatenate(bad), B, n_az, n_bins, fp)
     assert e.value.code == capi.E_INVALID
+
+
+def test_pcl_xyzi_records_feed_the_filter_unchanged(oracle, gpu_ctx):
+    """the reference's filterScan takes a pcl::PointCloud<PointXYZI> (32-byte records); randt_points_from_pcl_xyzi turns cloud.points.data()
+    into the path's float4 points on the device: filtering those equals filtering the host-repacked scan bit for bit"""
+    import torch
+    p = P.OXFORD
+    raw = synth.make_raw_scan(synth.scene_for(p, 9), (0.0, 0.0, 0.0), p, 9, n_azimuth=64, n_bins=500, bin_size=0.2)
+    n = len(raw)
+    pcl = np.zeros((n, 8), np.float32)
+    pcl[:, 0] = raw[:, 0]; pcl[:, 1] = raw[:, 1]; pcl[:, 2] = 0.37; pcl[:, 3] = 1.0      # z is ignored by the path, w = 1 as PCL sets it
+    pcl[:, 4] = raw[:, 3]; pcl[:, 5:] = np.float32(-7.0)                                  # padding holds garbage
+    d_pts = torch.zeros((n, 4), dtype=torch.float32, device="cuda")
+    d_out = torch.zeros((n, 4), dtype=torch.float32, device="cuda")
+    gpu_ctx.points_from_pcl_xyzi(pcl, d_pts.data_ptr())
+    fp = capi.filter_params(p)
+    kept = gpu_ctx.filter_scan_dev(d_pts.data_ptr(), 64, 500, fp, d_out.data_ptr(), n)
+    gpu_ctx.sync()
+    assert np.array_equal(d_pts.cpu().numpy(), raw)
+    want = gpu_ctx.filter_scan(raw, 64, 500, fp)
+    assert kept == len(want) and np.array_equal(d_out[:kept].cpu().numpy().view(np.uint32), want.view(np.uint32))
