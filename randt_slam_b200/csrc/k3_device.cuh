@@ -375,11 +375,18 @@ __device__ __forceinline__ uint32_t out_map(int lane) {
 __device__ __forceinline__ double out_factor(uint32_t sel, double ja, double jb) {
   return sel == 0u ? 1.0 : (sel == 1u ? ja : (sel == 2u ? jb : 0.0));
 }
-// `mine` = the caller's own slot total; slot s is owned by lane s * owner_mul
+// `mine` = the caller's own slot total; src_lane = the lane that owns the slot this lane's entry needs
+__device__ __forceinline__ void write_segment_out_from(double mine, double max_dd, double ja, double jb, uint32_t n_pairs, double* __restrict__ out_base,
+                                                       uint32_t seg, uint32_t packed, int lane, uint32_t omap, int src_lane);
+// slot s is owned by lane s * owner_mul (smem_reduce: 2, the partial fold: 1)
 __device__ __forceinline__ void write_segment_out(double mine, double max_dd, double ja, double jb, uint32_t n_pairs, double* __restrict__ out_base,
                                                   uint32_t seg, uint32_t packed, int lane, uint32_t omap, int owner_mul) {
+  write_segment_out_from(mine, max_dd, ja, jb, n_pairs, out_base, seg, packed, lane, omap, (int)(omap & 31u) * owner_mul);
+}
+__device__ __forceinline__ void write_segment_out_from(double mine, double max_dd, double ja, double jb, uint32_t n_pairs, double* __restrict__ out_base,
+                                                       uint32_t seg, uint32_t packed, int lane, uint32_t omap, int src_lane) {
   const int e = lane;
-  const double v = __shfl_sync(kFull, mine, (int)(omap & 31u) * owner_mul);
+  const double v = __shfl_sync(kFull, mine, src_lane);
   double val = (omap & 0x8000u) ? v * (out_factor((omap >> 5) & 3u, ja, jb) * out_factor((omap >> 7) & 3u, ja, jb)) : 0.0;
   if (e == 21) val = max_dd > 0.0 ? max_dd * rsqrt_fast(max_dd) : 0.0;   // max raw residual
   if (e == 23) val = (double)n_pairs;

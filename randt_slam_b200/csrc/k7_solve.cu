@@ -27,14 +27,19 @@ namespace randt {
 
 namespace {
 
-constexpr int kK7Warps = 4;      // warps per CTA
+#ifndef RANDT_K7_WARPS
+#define RANDT_K7_WARPS 4
+#endif
+constexpr int kK7Warps = RANDT_K7_WARPS;      // warps per CTA
 constexpr int kK7Bufs = 3;       // chunk buffers per warp
-constexpr int kK7MinCtas = 3;    // CTAs per SM (shared memory: ~15 KB per warp)
+#ifndef RANDT_K7_MIN_CTAS
+#define RANDT_K7_MIN_CTAS 4
+#endif
+constexpr int kK7MinCtas = RANDT_K7_MIN_CTAS;    // CTAs per SM (shared memory: ~11.6 KB per warp)
 
 template <int NS>
 struct __align__(128) SolveWarp {
   float4 rec[kK7Bufs][32 * kRecF4];     // the registration's duo records, chunk c in buffer c % kK7Bufs
-  double scratch[NS * 34];              // warp reduction scratch (smem_reduce)
   double out[RANDT_FUSED_STRIDE];       // record of the evaluation just made
   LmState st;                           // ceres state of the registration (lane 0)
   PoseConst kc; LossConst lc;           // constants of the evaluation in flight
@@ -64,6 +69,7 @@ k7_solve_kernel(DeviceProblem P, SolveLayout L, LossParams lp, const double* __r
   }
   __syncwarp();
   const uint32_t omap = out_map<VARIANT, true>(lane);
+  const int src_lane = bfly_owner<NS>((int)(omap & 31u));      // where the butterfly leaves the slot this lane's record entry needs
   uint32_t phase_bits = 0u;     // bit b: parity the next completion of buffer b's barrier will have
   const uint32_t cpt = L.tile_duos >> 5;     // chunks per full tile (tiles are multiples of 32 duos except a segment's last)
   while (true) {
@@ -126,10 +132,10 @@ k7_solve_kernel(DeviceProblem P, SolveLayout L, LossParams lp, const double* __r
         if ((uint32_t)lane < n_here) accumulate_duo<VARIANT, LOSS, true, NS>(w.kc, w.lc, &w.rec[b][0], P.duo_overflow, lane, acc, max_dd, n_bad);
         __syncwarp();
       }
-      const double mine = smem_reduce<NS>(acc, w.scratch, lane);     // slot s total: lanes 2 s, 2 s + 1
+      bfly_reduce<NS, 16>(acc, lane);             // fixed exchange pattern, no scratch: acc[0] = the 32-lane total of this lane's slot
       const double mx = warp_max_nonneg(max_dd);
       const uint32_t bad = __reduce_add_sync(kFull, n_bad);
-      write_segment_out(mine, mx, w.kc.ja, w.kc.jb, n_pairs_seg, w.out, 0u, 0u, lane, omap, 2);
+      write_segment_out_from(acc[0], mx, w.kc.ja, w.kc.jb, n_pairs_seg, w.out, 0u, 0u, lane, omap, src_lane);
       if (lane == 0 && bad) atomicAdd(bad_counter, (unsigned long long)bad);
       __syncwarp();
       first_eval = false;
