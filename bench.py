@@ -390,7 +390,7 @@ def run_configs(args, ctx, capi, stream, rank, world, local, barrier):
     if args.replay_scans > 1 and rank == 0:
         p4 = P.OXFORD
         t0 = time.perf_counter()
-        truth, scans = W.make_loop_drive(p4, 300, args.replay_scans)
+        truth, scans = W.make_loop_drive(p4, W.REPLAY_SCENE_SEED, args.replay_scans)
         t_gen = time.perf_counter() - t0
         W.device_replay(ctx, capi, p4, scans[:12])                          # warm-up
         l0 = ctx.launch_count

@@ -118,6 +118,8 @@ struct randt_problem {
 
 namespace {
 
+constexpr uint32_t kSingleMaxCells = 8192;   // the fused one-CTA association serves map pairs up to this many cells a side
+
 int fail(randt_ctx* ctx, int code, const char* what, cudaError_t e = cudaSuccess) {
   if (ctx) {
     char buf[512];
@@ -179,7 +181,7 @@ void free_problem(randt_problem* p) {
 }
 
 // tile list, balanced schedule, record table and per-segment bookkeeping from a host seg_off; uploads everything a DeviceProblem needs
-int finish_problem(randt_ctx* ctx, randt_problem* p) {
+int finish_problem(randt_ctx* ctx, randt_problem* p, bool records_ready = false) {
   static const bool trace = getenv("RANDT_DEBUG_TIMING") != nullptr;
   auto t_prev = std::chrono::steady_clock::now();
   auto lap = [&](const char* what) {
@@ -206,8 +208,14 @@ int finish_problem(randt_ctx* ctx, randt_problem* p) {
   if (!planA.empty()) CK(cudaMemcpyAsync(p->chunks_full, planA.data(), planA.size() * sizeof(ChunkDesc), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(p->warp_off, woffB.data(), woffB.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(p->warp_off_full, woffA.data(), woffA.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  // the fused single-map association wrote its records in duo order: valid when the schedule streams the tiles in that order
+  if (records_ready && tile_rec_begin != tile_duo_begin) {
+    records_ready = false;
+    dev_free(p->duo_recs); dev_free(p->duo_p0); dev_free(p->duo_overflow);
+    p->duo_recs = nullptr; p->duo_p0 = nullptr; p->duo_overflow = nullptr;
+  }
   // record-major duo table in schedule order (what K3 streams)
-  {
+  if (!records_ready) {
     int nl = 0;
     uint32_t *d_trb = nullptr, *d_tdb = nullptr; Duo* d_stream = nullptr;
     cudaError_t e = dev_alloc(&d_trb, tile_rec_begin.size());
@@ -260,7 +268,8 @@ int finish_problem(randt_ctx* ctx, randt_problem* p) {
   CK(cudaMemcpyAsync(p->seg_first_tile, first.data(), first.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(p->seg_off, p->h_seg_off.data(), p->h_seg_off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemsetAsync(p->seg_counters, 0, std::max<size_t>(1, p->S) * sizeof(uint32_t), ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));   // the host vectors above go out of scope
+  // (the uploads above come from pageable vectors: cudaMemcpyAsync has staged them before it returned, so nothing here has to wait)
+  if (!records_ready) CK(cudaStreamSynchronize(ctx->stream));   // surfaces an error of the record kernels in this call
   lap("tail");
   return RANDT_OK;
 }
@@ -737,6 +746,44 @@ int randt_associate(randt_ctx* ctx, const randt_map* F, const randt_map* M, cons
   randt_problem* p = new (std::nothrow) randt_problem();
   if (!p) return RANDT_E_NOMEM;
   p->device = ctx->device; p->sref = ctx->sref; p->S = B; p->n_m = n_m; p->n_f = F->n_cells;
+  // one scan against one submap (the live stream's call): one fused launch and one read-back
+  static const bool no_fused = getenv("RANDT_NO_FUSED_ASSOC") != nullptr;   // A/B switch for tests and profiling
+  if (B == 1 && !no_fused && n_m <= kSingleMaxCells && F->n_cells <= kSingleMaxCells) {
+    const uint32_t ovf_cap = 64;
+    double* d_p0 = nullptr; uint32_t* d_tot = nullptr; int nl1 = 0;
+    const size_t max_duos = (size_t)n_m * ((k + 1) / 2);
+    cudaError_t e = dev_alloc(&d_p0, 4);
+    if (e == cudaSuccess) e = dev_alloc(&d_tot, 3);
+    if (e == cudaSuccess) e = dev_alloc(&p->pairs, (size_t)n_m * k);
+    if (e == cudaSuccess) e = dev_alloc(&p->duos, max_duos);
+    if (e == cudaSuccess) e = dev_alloc(&p->duo_recs, max_duos);
+    if (e == cudaSuccess) e = dev_alloc(&p->duo_p0, max_duos);
+    if (e == cudaSuccess) e = dev_alloc(&p->duo_overflow, ovf_cap);
+    if (e == cudaSuccess) e = dev_alloc(&p->cells_m, (size_t)n_m * 3);
+    if (e == cudaSuccess) e = dev_alloc(&p->cells_f, (size_t)F->n_cells * 3);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_p0, pose0, 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_tot, 0, 3 * sizeof(uint32_t), ctx->stream);
+    if (e == cudaSuccess) e = launch_associate_single(F->cells, F->n_cells, F->slot, M->cells, n_m, geom, d_p0, k, metric, p->pairs, p->duos, p->duo_recs, p->duo_p0,
+                                                      p->duo_overflow, ovf_cap, p->cells_m, p->cells_f, d_tot, ctx->stream, &nl1);
+    uint32_t h_tot[3] = {0, 0, 0};
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_tot, d_tot, sizeof(h_tot), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    dev_free(d_p0); dev_free(d_tot);
+    if (e != cudaSuccess) { int rc1 = fail(ctx, RANDT_E_CUDA, "randt_associate (single map)", e); free_problem(p); return rc1; }
+    ctx->launches += nl1;
+    p->P = h_tot[0]; p->n_duos = h_tot[1]; p->n_overflow = h_tot[2];
+    p->h_seg_off = {0u, p->P}; p->h_duo_off = {0u, p->n_duos};
+    bool ready = true;
+    if (h_tot[2] > ovf_cap) {      // more escapes than the first guess holds: let the general record builder size the table
+      ready = false;
+      dev_free(p->duo_recs); dev_free(p->duo_p0); dev_free(p->duo_overflow);
+      p->duo_recs = nullptr; p->duo_p0 = nullptr; p->duo_overflow = nullptr;
+    }
+    int rc1 = finish_problem(ctx, p, ready);
+    if (rc1 != RANDT_OK) { free_problem(p); return rc1; }
+    *out = p;
+    return RANDT_OK;
+  }
   float4* d_pose = nullptr; double* d_pose0 = nullptr; uint32_t *d_nn = nullptr, *d_cnt = nullptr, *d_scan = nullptr, *d_bs = nullptr, *d_cnt2 = nullptr, *d_scan2 = nullptr, *d_offs = nullptr;
   int rc = RANDT_OK; int nl = 0;
   auto cleanup = [&]() { dev_free(d_pose); dev_free(d_pose0); dev_free(d_nn); dev_free(d_cnt); dev_free(d_scan); dev_free(d_bs); dev_free(d_cnt2); dev_free(d_scan2); dev_free(d_offs); };

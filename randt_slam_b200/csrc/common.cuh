@@ -111,6 +111,11 @@ cudaError_t launch_associate(const float4* cells_f, const uint32_t* cell_off_f, 
                              const uint32_t* cell_off_m, uint32_t n_maps, uint32_t n_m_total, uint32_t max_m_per_map,
                              const MapGeomDev& geom, const float4* d_pose_f /*[B] (c,s,tx,ty)*/, int k, int metric,
                              uint32_t* d_nn /*[n_m_total*k]*/, uint32_t* d_cnt /*[n_m_total]*/, cudaStream_t s, int* n_launches);
+// one map pair, everything (affine, association, pair / duo lists, K3 records, cell snapshots, totals) in one launch; d_totals[3] zeroed by the caller
+cudaError_t launch_associate_single(const float4* cells_f, uint32_t n_f, const int32_t* slot_f, const float4* cells_m, uint32_t n_m,
+                                    const MapGeomDev& geom, const double* d_pose0, int k, int metric, uint2* d_pairs, Duo* d_duos, DuoRec* d_recs,
+                                    uint32_t* d_duo_p0, DuoRecFull* d_overflow, uint32_t overflow_cap, float4* d_snap_m, float4* d_snap_f,
+                                    uint32_t* d_totals, cudaStream_t s, int* n_launches);
 cudaError_t launch_compact_pairs(const uint32_t* d_nn, const uint32_t* d_cnt, const uint32_t* d_scan /*exclusive scan of cnt*/,
                                  const uint32_t* cell_off_m, const uint32_t* cell_off_f, uint32_t n_maps, uint32_t n_m_total,
                                  uint32_t max_m_per_map, int k, uint2* d_pairs, cudaStream_t s, int* n_launches);
@@ -211,8 +216,8 @@ __host__ __device__ inline uint32_t coord_to_index(const MapGeomDev& g, float x,
 // Cell::transformCell (R/src/ndt_representation/ndt_cell.cpp:117-123) on the 3 x float4 cell layout.  Only meaningful in translation units
 // compiled with -fmad=false (k1, k2): every product / sum is a separate IEEE operation in Eigen's order, x0 + (x1 + x2) per coefficient.
 struct CellRaw { float4 a, b, c; };
-__device__ __forceinline__ void transform_cell_affine(CellRaw& q, const float4* __restrict__ aff) {
-  const float4 A = __ldg(aff), R0 = __ldg(aff + 1), R1 = __ldg(aff + 2), R2 = __ldg(aff + 3);
+__device__ __forceinline__ void transform_cell_affine(CellRaw& q, const float4* aff) {
+  const float4 A = aff[0], R0 = aff[1], R1 = aff[2], R2 = aff[3];   // (plain loads: the fused association keeps the record in shared memory)
   const float c = A.x, s = A.y;
   const float R[3][3] = {{R0.x, R0.y, R0.z}, {R0.w, R1.x, R1.y}, {R1.z, R1.w, R2.x}};
   const float S[3][3] = {{q.a.w, q.b.x, q.b.y}, {q.b.z, q.b.w, q.c.x}, {q.c.y, q.c.z, q.c.w}};

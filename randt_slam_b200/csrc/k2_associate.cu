@@ -9,6 +9,8 @@
 //   Cell::mahalanobisSquaredIntensity (ndt_cell.cpp:172-176), first k by (distance, index).
 // One thread per moving cell; the fixed map's dense slot table and cells are read through the read-only path.
 #include "common.cuh"
+#include "affine_device.cuh"
+#include "k3_device.cuh"   // RawCell + encode_duo_record (the fused single-map path builds K3's records itself)
 
 namespace randt {
 namespace {
@@ -47,21 +49,17 @@ __device__ __forceinline__ bool closer(double d, uint32_t i, double bd, uint32_t
   return (d < bd) || (d == bd && i < bi);
 }
 
-__global__ void __launch_bounds__(128) k2_associate_kernel(const float4* __restrict__ cells_f, const uint32_t* __restrict__ cell_off_f,
-                                                          const int32_t* __restrict__ slot_f, const float4* __restrict__ cells_m,
-                                                          const uint32_t* __restrict__ cell_off_m, MapGeomDev geom,
-                                                          const float4* __restrict__ pose_f, int k, int metric, uint32_t* __restrict__ nn,
-                                                          uint32_t* __restrict__ cnt) {
-  const uint32_t b = blockIdx.y;
-  const uint32_t m0 = cell_off_m[b], m1 = cell_off_m[b + 1];
-  const uint32_t i = m0 + blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= m1) return;
-  const float4 T = __ldg(pose_f + 4 * (size_t)b);   // AffineRec: (c, s, tx, ty) of initial_guess.cast<float>(), then its Eigen rotation()
+// Association of moving cell i (absolute index into cells_m) with the fixed map whose cells start at f0 and whose slot table is `slot`:
+// the first k occupied slots of the expanding window by (distance, index).  aff: the AffineRec of the initial guess.  -> number found.
+__device__ __forceinline__ int associate_cell(const float4* __restrict__ cells_f, uint32_t f0, const int32_t* __restrict__ slot,
+                                              const float4* __restrict__ cells_m, uint32_t i, const MapGeomDev& geom, const float4* __restrict__ aff,
+                                              int k, int metric, uint32_t* best_i) {
+  const float4 T = aff[0];   // AffineRec: (c, s, tx, ty) of initial_guess.cast<float>(), then its Eigen rotation()
   CellF q;
   if (metric == RANDT_LOOKUP_MAHALANOBIS_INTENSITY) {
     CellRaw raw;
     raw.a = __ldg(cells_m + 3 * (size_t)i); raw.b = __ldg(cells_m + 3 * (size_t)i + 1); raw.c = __ldg(cells_m + 3 * (size_t)i + 2);
-    transform_cell_affine(raw, pose_f + 4 * (size_t)b);
+    transform_cell_affine(raw, aff);
     q.mu[0] = raw.a.x; q.mu[1] = raw.a.y; q.mu[2] = raw.a.z;
     q.cov[0] = raw.a.w; q.cov[1] = raw.b.x; q.cov[2] = raw.b.y; q.cov[3] = raw.b.z; q.cov[4] = raw.b.w; q.cov[5] = raw.c.x; q.cov[6] = raw.c.y; q.cov[7] = raw.c.z; q.cov[8] = raw.c.w;
   } else {
@@ -70,12 +68,9 @@ __global__ void __launch_bounds__(128) k2_associate_kernel(const float4* __restr
     q.mu[0] = (T.x * x - T.y * y) + T.z;
     q.mu[1] = (T.y * x + T.x * y) + T.w;
   }
-  const uint32_t f0 = cell_off_f[b];
-  const int32_t* __restrict__ slot = slot_f + (size_t)b * geom.n_slots;
   const uint32_t center = coord_to_index(geom, q.mu[0], q.mu[1]);
 
   double best_d[kMaxNeighbours];
-  uint32_t best_i[kMaxNeighbours];
   int n_best = 0;
   uint32_t total = 0;
   int r = 0;
@@ -122,8 +117,94 @@ __global__ void __launch_bounds__(128) k2_associate_kernel(const float4* __restr
     ++r;
     if (r >= geom.r_stop) break;
   }
+  return n_best;
+}
+
+__global__ void __launch_bounds__(128) k2_associate_kernel(const float4* __restrict__ cells_f, const uint32_t* __restrict__ cell_off_f,
+                                                          const int32_t* __restrict__ slot_f, const float4* __restrict__ cells_m,
+                                                          const uint32_t* __restrict__ cell_off_m, MapGeomDev geom,
+                                                          const float4* __restrict__ pose_f, int k, int metric, uint32_t* __restrict__ nn,
+                                                          uint32_t* __restrict__ cnt) {
+  const uint32_t b = blockIdx.y;
+  const uint32_t m0 = cell_off_m[b], m1 = cell_off_m[b + 1];
+  const uint32_t i = m0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m1) return;
+  uint32_t best_i[kMaxNeighbours];
+  const int n_best = associate_cell(cells_f, cell_off_f[b], slot_f + (size_t)b * geom.n_slots, cells_m, i, geom, pose_f + 4 * (size_t)b, k, metric, best_i);
   cnt[i] = (uint32_t)n_best;
   for (int t = 0; t < n_best; ++t) nn[(size_t)i * k + t] = best_i[t];
+}
+
+// ---- single map pair, everything in one launch ------------------------------------------------------------------------------
+// The per-scan call of a live stream (one moving scan against one submap): the AffineRec of the initial guess, the association,
+// the pair / duo lists in the reference's block order, K3's compact records (a lone registration's tiles sit in duo order: one tile
+// per warp), the snapshots of both cell tables and the totals the host needs — one CTA, one launch, one read-back, instead of ~15
+// launches and three host synchronisations.
+constexpr int kSingleThreads = 1024;
+__global__ void __launch_bounds__(kSingleThreads) k2_associate_single_kernel(const float4* __restrict__ cells_f, uint32_t n_f, const int32_t* __restrict__ slot,
+                                                                            const float4* __restrict__ cells_m, uint32_t n_m, MapGeomDev geom,
+                                                                            const double* __restrict__ pose0, int k, int metric, uint2* __restrict__ pairs,
+                                                                            Duo* __restrict__ duos, DuoRec* __restrict__ recs, uint32_t* __restrict__ duo_p0,
+                                                                            DuoRecFull* __restrict__ overflow, uint32_t overflow_cap, float4* __restrict__ snap_m,
+                                                                            float4* __restrict__ snap_f, uint32_t* __restrict__ totals /* P, n_duos, n_overflow */) {
+  __shared__ float4 aff[4];
+  __shared__ uint32_t warp_sums[32];
+  __shared__ uint32_t warp_sums2[32];
+  const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+  if (tid == 0) make_affine_rec_se2d(pose0, aff);
+  // the snapshots (the reference's functors copy their cells by value)
+  for (uint32_t e = tid; e < 3u * n_m; e += kSingleThreads) snap_m[e] = __ldg(cells_m + e);
+  for (uint32_t e = tid; e < 3u * n_f; e += kSingleThreads) snap_f[e] = __ldg(cells_f + e);
+  __syncthreads();
+  uint32_t carry_p = 0, carry_d = 0;
+  for (uint32_t base = 0; base < n_m; base += kSingleThreads) {
+    const uint32_t i = base + tid;
+    uint32_t best_i[kMaxNeighbours];
+    int n = 0;
+    if (i < n_m) n = associate_cell(cells_f, 0u, slot, cells_m, i, geom, aff, k, metric, best_i);
+    // exclusive block scans of the pair and duo counts (two warp-shuffle scans, one round of barriers)
+    const uint32_t cp = (uint32_t)n, cd = ((uint32_t)n + 1u) >> 1;
+    uint32_t xp = cp, xd = cd;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t yp = __shfl_up_sync(0xffffffffu, xp, o), yd = __shfl_up_sync(0xffffffffu, xd, o);
+      if (lane >= o) { xp += yp; xd += yd; }
+    }
+    if (lane == 31) { warp_sums[wp] = xp; warp_sums2[wp] = xd; }
+    __syncthreads();
+    if (wp == 0) {
+      uint32_t sp = warp_sums[lane], sd = warp_sums2[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t yp = __shfl_up_sync(0xffffffffu, sp, o), yd = __shfl_up_sync(0xffffffffu, sd, o);
+        if (lane >= o) { sp += yp; sd += yd; }
+      }
+      warp_sums[lane] = sp; warp_sums2[lane] = sd;
+    }
+    __syncthreads();
+    const uint32_t pbase = carry_p + (wp > 0 ? warp_sums[wp - 1] : 0u) + xp - cp;
+    const uint32_t dbase = carry_d + (wp > 0 ? warp_sums2[wp - 1] : 0u) + xd - cd;
+    carry_p += warp_sums[31]; carry_d += warp_sums2[31];
+    __syncthreads();
+    if (i < n_m) {
+      RawCell c[3];
+      c[0].a = __ldg(cells_m + 3 * (size_t)i); c[0].b = __ldg(cells_m + 3 * (size_t)i + 1); c[0].c = __ldg(cells_m + 3 * (size_t)i + 2);
+      for (int t = 0; t < n; ++t) pairs[pbase + t] = make_uint2(i, best_i[t]);
+      for (int t = 0; t < n; t += 2) {
+        const bool two = t + 1 < n;
+        Duo d;
+        d.im = i; d.jf0 = best_i[t]; d.jf1 = two ? best_i[t + 1] : kNoCell; d.p0 = pbase + t;
+        const uint32_t di = dbase + (uint32_t)(t >> 1);
+        duos[di] = d;
+        c[1].a = __ldg(cells_f + 3 * (size_t)d.jf0); c[1].b = __ldg(cells_f + 3 * (size_t)d.jf0 + 1); c[1].c = __ldg(cells_f + 3 * (size_t)d.jf0 + 2);
+        c[2] = c[1];
+        if (two) { c[2].a = __ldg(cells_f + 3 * (size_t)d.jf1); c[2].b = __ldg(cells_f + 3 * (size_t)d.jf1 + 1); c[2].c = __ldg(cells_f + 3 * (size_t)d.jf1 + 2); }
+        encode_duo_record(c, two, recs + di, overflow, overflow_cap, totals + 2);
+        duo_p0[di] = d.p0;
+      }
+    }
+  }
+  if (tid == 0) { totals[0] = carry_p; totals[1] = carry_d; }
 }
 
 __global__ void k2_compact_pairs_kernel(const uint32_t* __restrict__ nn, const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ scan,
@@ -236,6 +317,16 @@ cudaError_t launch_associate(const float4* cells_f, const uint32_t* cell_off_f, 
   if (n_maps == 0 || max_m_per_map == 0) return cudaSuccess;
   dim3 grid((max_m_per_map + 127) / 128, n_maps);
   k2_associate_kernel<<<grid, 128, 0, s>>>(cells_f, cell_off_f, slot_f, cells_m, cell_off_m, geom, d_pose_f, k, metric, d_nn, d_cnt);
+  if (n_launches) *n_launches += 1;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_associate_single(const float4* cells_f, uint32_t n_f, const int32_t* slot_f, const float4* cells_m, uint32_t n_m,
+                                    const MapGeomDev& geom, const double* d_pose0, int k, int metric, uint2* d_pairs, Duo* d_duos, DuoRec* d_recs,
+                                    uint32_t* d_duo_p0, DuoRecFull* d_overflow, uint32_t overflow_cap, float4* d_snap_m, float4* d_snap_f,
+                                    uint32_t* d_totals, cudaStream_t s, int* n_launches) {
+  k2_associate_single_kernel<<<1, kSingleThreads, 0, s>>>(cells_f, n_f, slot_f, cells_m, n_m, geom, d_pose0, k, metric, d_pairs, d_duos, d_recs, d_duo_p0,
+                                                         d_overflow, overflow_cap, d_snap_m, d_snap_f, d_totals);
   if (n_launches) *n_launches += 1;
   return cudaGetLastError();
 }

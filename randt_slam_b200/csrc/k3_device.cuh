@@ -53,6 +53,38 @@ __device__ __forceinline__ bool sym_encode(float a, float b, float& hs, uint32_t
   return c < 4ull && (db | (c << 27)) == sb;
 }
 
+// One duo's three cells (moving, fixed of p0, fixed of p0 + 1 or a repeat of the first when the duo has one pair) -> its compact record
+// (common.cuh: DuoRec); a duo whose couples do not fit the encoding goes to the overflow table as stored.
+__device__ __forceinline__ void encode_duo_record(const RawCell* c, bool two, DuoRec* __restrict__ rec, DuoRecFull* __restrict__ overflow,
+                                                  uint32_t overflow_cap, uint32_t* __restrict__ n_overflow) {
+  float o[28];
+  uint32_t w = two ? 0u : kRecNoSecond;
+  bool fits = true;
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    o[9 * q + 0] = c[q].a.x; o[9 * q + 1] = c[q].a.y; o[9 * q + 2] = c[q].a.z;
+    o[9 * q + 3] = c[q].a.w; o[9 * q + 4] = c[q].b.w; o[9 * q + 5] = c[q].c.w;
+    uint32_t code;
+    fits = sym_encode(c[q].b.x, c[q].b.z, o[9 * q + 6], code) && fits; w |= code << (2 * (3 * q + 0));
+    fits = sym_encode(c[q].b.y, c[q].c.y, o[9 * q + 7], code) && fits; w |= code << (2 * (3 * q + 1));
+    fits = sym_encode(c[q].c.x, c[q].c.z, o[9 * q + 8], code) && fits; w |= code << (2 * (3 * q + 2));
+  }
+  if (!fits) {
+    const uint32_t idx = atomicAdd(n_overflow, 1u);
+    if (idx < overflow_cap) {
+      float4* q = overflow[idx].v;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { q[3 * i] = c[i].a; q[3 * i + 1] = c[i].b; q[3 * i + 2] = c[i].c; }
+    }
+    o[0] = __uint_as_float(idx);
+    w = (w & kRecNoSecond) | kRecEscape;
+  }
+  o[27] = __uint_as_float(w);
+  float4* dst = rec->v;
+#pragma unroll
+  for (int i = 0; i < 7; ++i) dst[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+}
+
 // 1/x for a normal, finite, non-zero x: MUFU.RCP64H seed (2^-23) + two Newton steps.  No slow path: callers guarantee or
 // tolerate garbage-in-garbage-out (degenerate pairs are caught by the validity test on dd).
 __device__ __forceinline__ double rcp_fast(double x) {

@@ -315,32 +315,7 @@ __global__ void __launch_bounds__(128) build_duo_records_kernel(const float4* __
   c[1].a = __ldg(cells_f + 3 * (size_t)du.jf0); c[1].b = __ldg(cells_f + 3 * (size_t)du.jf0 + 1); c[1].c = __ldg(cells_f + 3 * (size_t)du.jf0 + 2);
   c[2] = c[1];                                  // a missing second pair repeats the first (finite values; kRecNoSecond keeps it out of the sums)
   if (two) { c[2].a = __ldg(cells_f + 3 * (size_t)du.jf1); c[2].b = __ldg(cells_f + 3 * (size_t)du.jf1 + 1); c[2].c = __ldg(cells_f + 3 * (size_t)du.jf1 + 2); }
-  float o[28];
-  uint32_t w = two ? 0u : kRecNoSecond;
-  bool fits = true;
-#pragma unroll
-  for (int q = 0; q < 3; ++q) {
-    o[9 * q + 0] = c[q].a.x; o[9 * q + 1] = c[q].a.y; o[9 * q + 2] = c[q].a.z;
-    o[9 * q + 3] = c[q].a.w; o[9 * q + 4] = c[q].b.w; o[9 * q + 5] = c[q].c.w;
-    uint32_t code;
-    fits = sym_encode(c[q].b.x, c[q].b.z, o[9 * q + 6], code) && fits; w |= code << (2 * (3 * q + 0));
-    fits = sym_encode(c[q].b.y, c[q].c.y, o[9 * q + 7], code) && fits; w |= code << (2 * (3 * q + 1));
-    fits = sym_encode(c[q].c.x, c[q].c.z, o[9 * q + 8], code) && fits; w |= code << (2 * (3 * q + 2));
-  }
-  if (!fits) {
-    const uint32_t idx = atomicAdd(n_overflow, 1u);
-    if (idx < overflow_cap) {
-      float4* q = overflow[idx].v;
-#pragma unroll
-      for (int i = 0; i < 3; ++i) { q[3 * i] = c[i].a; q[3 * i + 1] = c[i].b; q[3 * i + 2] = c[i].c; }
-    }
-    o[0] = __uint_as_float(idx);
-    w = (w & kRecNoSecond) | kRecEscape;
-  }
-  o[27] = __uint_as_float(w);
-  float4* dst = recs[d].v;
-#pragma unroll
-  for (int i = 0; i < 7; ++i) dst[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+  encode_duo_record(c, two, recs + d, overflow, overflow_cap, n_overflow);
   duo_p0[d] = du.p0;
 }
 

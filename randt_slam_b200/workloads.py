@@ -261,6 +261,14 @@ def _scan_job(args):
     return synth.make_scan(synth.scene_for(p, scene_seed), pose, p, scan_seed, **synth.preset_scan_kwargs(p))
 
 
+# Scene of the replay drive.  With the Oxford preset's 3.5 m cells, odometry alone (no loop closure) loses half a cell in a single
+# step on many random scenes — the CPU oracle chain, i.e. the reference's algorithm, does so on 5 of 9 scenes tried (seeds 300-308;
+# seed 300: a 1.7 m step at scan 272 that it undoes at scan 456) — and past such a step a free-running chain is a chaotic function
+# of the last bits of its sums.  On this scene the oracle chain stays within 0.71 m of the ground truth over all 8 609 scans, so
+# "both chains track the same trajectory" is a statement about the implementations and not about the scene.
+REPLAY_SCENE_SEED = 304
+
+
 def make_loop_drive(p, seed, n_scans, radius=30.0, step=0.45, workers=None):
     """A drive of n_scans scans around a circle inside one synthetic scene (an 8 609-scan straight drive would leave any finite scene):
     0.45 m per scan like the Oxford vehicle at 4 Hz.  -> (truth [n,3], scans list).  Scans are generated by a process pool."""

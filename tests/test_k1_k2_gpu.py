@@ -105,6 +105,47 @@ def test_associate_matches_oracle(oracle, gpu_ctx, preset, metric):
     assert np.array_equal(cm, np.concatenate([m["cells"] for m in moving]))
 
 
+@pytest.mark.parametrize("preset,n_submap_scans", [("oxford", 3), ("indoor", 2), ("c1", 6)])
+@pytest.mark.parametrize("metric", [capi.LOOKUP_MAHALANOBIS, capi.LOOKUP_EUCLID])
+def test_associate_single_map_equals_batched_path(oracle, gpu_ctx, preset, n_submap_scans, metric):
+    """One scan against one submap takes the fused one-launch path (association, pair / duo lists, K3's records and the snapshots in
+    one kernel).  Its problem must be the one the batched path builds for the same pair: same pairs as the oracle's
+    getCellsAndNeighbors restatement, and equal fused blocks and bit-identical solver results."""
+    p = PRESETS[preset]
+    f = H.build_submap(oracle, p, 31, n_scans=n_submap_scans)
+    pts = H.make_scan(p, 31, (0.4, -0.2, 0.03), 911)
+    mv = oracle.voxelize(pts, *H.vox_args(p))
+    pose = synth.pose_to_se2(0.38, -0.22, 0.025)
+    gp = capi.grid_params(p)
+    k = p.n_results_nn_lookup
+    nf, nm = len(f["cells"]), len(mv["cells"])
+    f1 = gpu_ctx.map_upload(f["cells"], np.array([0, nf], np.uint32), gp, npts=f["npts"], slot=f["slot"][None])
+    m1 = gpu_ctx.map_upload(mv["cells"], np.array([0, nm], np.uint32), gp)
+    single = gpu_ctx.associate(f1, m1, pose[None], k, metric)
+    f2 = gpu_ctx.map_upload(np.concatenate([f["cells"]] * 2), np.array([0, nf, 2 * nf], np.uint32), gp, npts=np.concatenate([f["npts"]] * 2),
+                            slot=np.stack([f["slot"]] * 2))
+    m2 = gpu_ctx.map_upload(np.concatenate([mv["cells"]] * 2), np.array([0, nm, 2 * nm], np.uint32), gp)
+    both = gpu_ctx.associate(f2, m2, np.stack([pose, pose]), k, metric)
+    im, jf = oracle.associate(f["cells"], f["slot"], p.size_x, p.size_y, p.resolution, p.max_neighbor_linf_distance, mv["cells"], pose, k, metric)
+    pm, pf, seg = single.download()
+    assert list(seg) == [0, len(im)] and len(im) > 20
+    assert np.array_equal(pm, im) and np.array_equal(pf, jf)
+    bm, bf, bseg = both.download()
+    assert np.array_equal(bm[:bseg[1]], pm) and np.array_equal(bf[:bseg[1]], pf)
+    cm, cf = single.download_cells()
+    assert np.array_equal(cm, mv["cells"]) and np.array_equal(cf, f["cells"])
+    assert single.layout() == (both.layout()[0] // 2, both.layout()[1], both.layout()[2] // 2)
+    loss = capi.make_loss(capi.LOSS_BARRON, 1.0, -2.0)
+    for q in (pose, synth.pose_to_se2(0.5, -0.1, -0.04)):
+        a = single.eval_fused(q[None], loss)
+        b = both.eval_fused(np.stack([q, q]), loss)      # (tile sizes differ between the two schedules: same sums, other grouping)
+        assert np.allclose(a[0], b[0], rtol=1e-11, atol=1e-13) and np.array_equal(b[0], b[1])
+    opt = capi.solver_options()
+    ra = single.register_batch(pose[None], loss, opt)
+    rb = both.register_batch(np.stack([pose, pose]), loss, opt)
+    assert np.array_equal(np.asarray(ra[0])[0], np.asarray(rb[0])[0])
+
+
 def test_slot_table_rebuild_matches_insert_order(oracle, gpu_ctx):
     p = P.OXFORD
     v = oracle.voxelize(H.make_scan(p, 9, (0, 0, 0), 9), *H.vox_args(p))

@@ -23,7 +23,7 @@ N_SCANS = 8609
 
 @pytest.fixture(scope="module")
 def drive():
-    return W.make_loop_drive(P.OXFORD, 300, N_SCANS)
+    return W.make_loop_drive(P.OXFORD, W.REPLAY_SCENE_SEED, N_SCANS)
 
 
 def test_full_length_replay_tracks_and_matches_oracle_chain(oracle, gpu_ctx, drive):
@@ -32,7 +32,9 @@ def test_full_length_replay_tracks_and_matches_oracle_chain(oracle, gpu_ctx, dri
     poses_g, dt, its = W.device_replay(gpu_ctx, capi, p, scans)
     est = np.stack([poses_g[:, 2], poses_g[:, 3]], 1)
     err = np.hypot(est[:, 0] - truth[:, 0], est[:, 1] - truth[:, 1])
-    assert np.all(np.isfinite(poses_g)) and err.max() < 5.0, err.max()          # 20 laps of a 30 m circle: never lost
+    # 20 laps of a 30 m circle, odometry only (no loop closure), on the scene where the reference's algorithm itself tracks
+    # (workloads.REPLAY_SCENE_SEED: the oracle chain stays within 0.71 m over the whole drive)
+    assert np.all(np.isfinite(poses_g)) and err.max() < 1.5, err.max()
     assert abs(np.hypot(poses_g[:, 0], poses_g[:, 1]) - 1.0).max() < 1e-9      # manifold mode keeps the complex number normalised
     # the oracle chain over a prefix, free-running: same trajectory
     n_o = 600
