@@ -764,7 +764,7 @@ int randt_associate(randt_ctx* ctx, const randt_map* F, const randt_map* M, cons
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_p0, pose0, 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(d_tot, 0, 3 * sizeof(uint32_t), ctx->stream);
     if (e == cudaSuccess) e = launch_associate_single(F->cells, F->n_cells, F->slot, M->cells, n_m, geom, d_p0, k, metric, p->pairs, p->duos, p->duo_recs, p->duo_p0,
-                                                      p->duo_overflow, ovf_cap, p->cells_m, p->cells_f, d_tot, ctx->stream, &nl1);
+                                                      p->duo_overflow, ovf_cap, p->cells_m, p->cells_f, d_tot, nullptr, ctx->stream, &nl1);
     uint32_t h_tot[3] = {0, 0, 0};
     if (e == cudaSuccess) e = cudaMemcpyAsync(h_tot, d_tot, sizeof(h_tot), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
@@ -1325,6 +1325,69 @@ int randt_register_batch_weighted(randt_ctx* ctx, const randt_problem* cp, int v
   return RANDT_OK;
 }
 
+namespace {
+// One scan against one submap, association and solve back to back with no host round trip between them: the fused association
+// kernel leaves K3's records and a one-registration layout in device memory, K7 solves from them, and pose, result and the totals come
+// back in one copy.  Same kernels and the same arithmetic as randt_associate + randt_register_batch (which also build the pair lists
+// and the K3 schedule a caller may evaluate later; a scan step drops its problem at once and needs neither).
+// -> RANDT_OK with *handled = false when the pair does not qualify (too many duos for one warp, escapes beyond the table).
+int scan_associate_solve(randt_ctx* ctx, const randt_map* F, const randt_map* M, int k, int metric, const randt_loss* loss, const randt_solver_options* opt,
+                         double* pose_io, double* res, bool* handled) {
+  *handled = false;
+  static const bool no_fused = getenv("RANDT_NO_FUSED_ASSOC") != nullptr;
+  const uint32_t n_m = M->n_cells;
+  const size_t max_duos = (size_t)n_m * ((k + 1) / 2);
+  if (no_fused || opt->poll_interval < 0 || n_m == 0 || max_duos > kSolveMaxDuos || F->n_cells > kSingleMaxCells) return RANDT_OK;
+  if (k < 1 || k > kMaxNeighbours || (metric != RANDT_LOOKUP_MAHALANOBIS_INTENSITY && metric != RANDT_LOOKUP_EUCLID_XY)) return RANDT_OK;   // let randt_associate report it
+  if (!(opt->gnc_divisor > 1.0) || !(opt->gnc_loss_scale > 0.0) || opt->gnc_max_steps < 1 || opt->max_num_iterations < 0 ||
+      opt->max_num_consecutive_invalid_steps < 1 || !(opt->initial_trust_region_radius > 0.0)) return RANDT_OK;                          // let randt_register_batch report it
+  MapGeomDev geom = F->geom;
+  geom.r_stop = static_cast<int>(F->gp.max_linf / F->gp.resolution);
+  if (2 * (geom.r_stop > 0 ? geom.r_stop - 1 : 0) + 1 > geom.size_x) return RANDT_OK;
+  randt_loss l0 = *loss; l0.mu = 1.0;
+  LossParams lp;
+  if (int rc = make_loss(ctx, &l0, &lp)) return rc;
+  CK(cudaSetDevice(ctx->device));
+  StreamScope scope__(ctx->stream, ctx->sref->pool);
+  // one block: [pose 4 | result 8] doubles, [totals 3 | counter 1 | layout 6 | pad 2] words, records, escapes
+  constexpr uint32_t ovf_cap = 64;
+  constexpr size_t io_doubles = 4 + RANDT_REG_STRIDE, io_words = 12;
+  const size_t off_rec = (io_doubles * 8 + io_words * 4 + 127) & ~(size_t)127;
+  const size_t off_ovf = off_rec + ((max_duos * sizeof(DuoRec) + 127) & ~(size_t)127);
+  const size_t bytes = off_ovf + ovf_cap * sizeof(DuoRecFull);
+  unsigned char* blk = nullptr;
+  CK(dev_alloc(&blk, bytes));
+  double* d_pose = reinterpret_cast<double*>(blk); double* d_res = d_pose + 4;
+  uint32_t* d_words = reinterpret_cast<uint32_t*>(blk + io_doubles * 8);
+  uint32_t *d_tot = d_words, *d_counter = d_words + 3, *d_layout = d_words + 4;
+  DuoRec* d_recs = reinterpret_cast<DuoRec*>(blk + off_rec);
+  DuoRecFull* d_ovf = reinterpret_cast<DuoRecFull*>(blk + off_ovf);
+  int nl = 0;
+  struct { double pose[4]; double res[RANDT_REG_STRIDE]; uint32_t words[io_words]; } h;
+  cudaError_t e = cudaMemsetAsync(d_pose, 0, io_doubles * 8 + io_words * 4, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_pose, pose_io, 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = launch_associate_single(F->cells, F->n_cells, F->slot, M->cells, n_m, geom, d_pose, k, metric, nullptr, nullptr, d_recs, nullptr, d_ovf, ovf_cap,
+                                                    nullptr, nullptr, d_tot, d_layout, ctx->stream, &nl);
+  if (e == cudaSuccess) {
+    DeviceProblem v;
+    v.duo_recs = d_recs; v.duo_overflow = d_ovf; v.seg_off = d_layout; v.seg_first_tile = d_layout + 4; v.n_segments = 1;
+    SolveLayout L;
+    L.seg_duo_off = d_layout + 2; L.tile_rec_begin = d_layout + 5; L.tile_duos = kSolveMaxDuos; L.items = nullptr; L.n_items = 1; L.next_item = d_counter;
+    e = launch_solve_persistent(v, L, 0, opt->use_manifold, lp, nullptr, *opt, d_pose, d_pose, d_res, ctx->d_bad, ctx->stream, &nl);
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&h, blk, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  dev_free(blk);
+  if (e != cudaSuccess) return fail(ctx, RANDT_E_CUDA, "randt_scan_step (fused associate + solve)", e);
+  ctx->launches += nl;
+  if (h.words[2] > ovf_cap) return RANDT_OK;       // escapes beyond the table: the general path sizes it
+  memcpy(pose_io, h.pose, sizeof(h.pose));
+  memcpy(res, h.res, sizeof(h.res));
+  *handled = true;
+  return RANDT_OK;
+}
+}  // namespace
+
 // the per-scan chain as one call: see randt_gpu.h
 int randt_scan_step(randt_ctx* ctx, randt_map* submap, const float* pts4, uint32_t n_pts, const randt_grid_params* gp, int k, int metric,
                     const randt_loss* loss, double ndt_weight, const randt_solver_options* opt, int insert_keyframe, double* pose_io, double* result,
@@ -1347,18 +1410,23 @@ int randt_scan_step(randt_ctx* ctx, randt_map* submap, const float* pts4, uint32
   if (n_cells_out) *n_cells_out = scan->n_cells;
   double res[RANDT_REG_STRIDE] = {0};
   if (submap->n_cells > 0) {
-    randt_problem* prob = nullptr;
-    rc = randt_associate(ctx, submap, scan, pose_io, k, metric, &prob);
-    lap("associate");
-    if (rc == RANDT_OK) {
-      randt_loss l; l.kind = RANDT_LOSS_NONE; l.scale = 1.0; l.alpha = 2.0; l.mu = 1.0; l.weight = 1.0;
-      if (loss) l = *loss;
-      if (ndt_weight > 0.0 && scan->n_cells > 0) l.weight = ndt_weight / ((double)scan->n_cells * (double)k);
-      rc = randt_register_batch(ctx, prob, 0, pose_io, &l, opt, res);
-      lap("register");
+    randt_loss l; l.kind = RANDT_LOSS_NONE; l.scale = 1.0; l.alpha = 2.0; l.mu = 1.0; l.weight = 1.0;
+    if (loss) l = *loss;
+    if (ndt_weight > 0.0 && scan->n_cells > 0) l.weight = ndt_weight / ((double)scan->n_cells * (double)k);
+    bool handled = false;
+    rc = scan_associate_solve(ctx, submap, scan, k, metric, &l, opt, pose_io, res, &handled);
+    lap("assoc+solve");
+    if (rc == RANDT_OK && !handled) {
+      randt_problem* prob = nullptr;
+      rc = randt_associate(ctx, submap, scan, pose_io, k, metric, &prob);
+      lap("associate");
+      if (rc == RANDT_OK) {
+        rc = randt_register_batch(ctx, prob, 0, pose_io, &l, opt, res);
+        lap("register");
+      }
+      randt_problem_destroy(prob);
+      lap("destroy");
     }
-    randt_problem_destroy(prob);
-    lap("destroy");
   }
   if (rc == RANDT_OK && (insert_keyframe || submap->n_cells == 0)) {
     rc = randt_map_transform_se2d(ctx, scan, pose_io);

@@ -146,15 +146,18 @@ __global__ void __launch_bounds__(kSingleThreads) k2_associate_single_kernel(con
                                                                             const double* __restrict__ pose0, int k, int metric, uint2* __restrict__ pairs,
                                                                             Duo* __restrict__ duos, DuoRec* __restrict__ recs, uint32_t* __restrict__ duo_p0,
                                                                             DuoRecFull* __restrict__ overflow, uint32_t overflow_cap, float4* __restrict__ snap_m,
-                                                                            float4* __restrict__ snap_f, uint32_t* __restrict__ totals /* P, n_duos, n_overflow */) {
+                                                                            float4* __restrict__ snap_f, uint32_t* __restrict__ totals /* P, n_duos, n_overflow */,
+                                                                            uint32_t* __restrict__ layout /* or NULL: the one-registration layout K7 walks */) {
   __shared__ float4 aff[4];
   __shared__ uint32_t warp_sums[32];
   __shared__ uint32_t warp_sums2[32];
   const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
   if (tid == 0) make_affine_rec_se2d(pose0, aff);
   // the snapshots (the reference's functors copy their cells by value)
-  for (uint32_t e = tid; e < 3u * n_m; e += kSingleThreads) snap_m[e] = __ldg(cells_m + e);
-  for (uint32_t e = tid; e < 3u * n_f; e += kSingleThreads) snap_f[e] = __ldg(cells_f + e);
+  if (snap_m) {
+    for (uint32_t e = tid; e < 3u * n_m; e += kSingleThreads) snap_m[e] = __ldg(cells_m + e);
+    for (uint32_t e = tid; e < 3u * n_f; e += kSingleThreads) snap_f[e] = __ldg(cells_f + e);
+  }
   __syncthreads();
   uint32_t carry_p = 0, carry_d = 0;
   for (uint32_t base = 0; base < n_m; base += kSingleThreads) {
@@ -189,22 +192,26 @@ __global__ void __launch_bounds__(kSingleThreads) k2_associate_single_kernel(con
     if (i < n_m) {
       RawCell c[3];
       c[0].a = __ldg(cells_m + 3 * (size_t)i); c[0].b = __ldg(cells_m + 3 * (size_t)i + 1); c[0].c = __ldg(cells_m + 3 * (size_t)i + 2);
-      for (int t = 0; t < n; ++t) pairs[pbase + t] = make_uint2(i, best_i[t]);
+      if (pairs) for (int t = 0; t < n; ++t) pairs[pbase + t] = make_uint2(i, best_i[t]);
       for (int t = 0; t < n; t += 2) {
         const bool two = t + 1 < n;
         Duo d;
         d.im = i; d.jf0 = best_i[t]; d.jf1 = two ? best_i[t + 1] : kNoCell; d.p0 = pbase + t;
         const uint32_t di = dbase + (uint32_t)(t >> 1);
-        duos[di] = d;
+        if (duos) { duos[di] = d; duo_p0[di] = d.p0; }
         c[1].a = __ldg(cells_f + 3 * (size_t)d.jf0); c[1].b = __ldg(cells_f + 3 * (size_t)d.jf0 + 1); c[1].c = __ldg(cells_f + 3 * (size_t)d.jf0 + 2);
         c[2] = c[1];
         if (two) { c[2].a = __ldg(cells_f + 3 * (size_t)d.jf1); c[2].b = __ldg(cells_f + 3 * (size_t)d.jf1 + 1); c[2].c = __ldg(cells_f + 3 * (size_t)d.jf1 + 2); }
         encode_duo_record(c, two, recs + di, overflow, overflow_cap, totals + 2);
-        duo_p0[di] = d.p0;
       }
     }
   }
-  if (tid == 0) { totals[0] = carry_p; totals[1] = carry_d; }
+  if (tid == 0) {
+    totals[0] = carry_p; totals[1] = carry_d;
+    if (layout) {     // seg_off[2], seg_duo_off[2], seg_first_tile[1], tile_rec_begin[1]: one registration, one tile, records in duo order
+      layout[0] = 0u; layout[1] = carry_p; layout[2] = 0u; layout[3] = carry_d; layout[4] = 0u; layout[5] = 0u;
+    }
+  }
 }
 
 __global__ void k2_compact_pairs_kernel(const uint32_t* __restrict__ nn, const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ scan,
@@ -324,9 +331,9 @@ cudaError_t launch_associate(const float4* cells_f, const uint32_t* cell_off_f, 
 cudaError_t launch_associate_single(const float4* cells_f, uint32_t n_f, const int32_t* slot_f, const float4* cells_m, uint32_t n_m,
                                     const MapGeomDev& geom, const double* d_pose0, int k, int metric, uint2* d_pairs, Duo* d_duos, DuoRec* d_recs,
                                     uint32_t* d_duo_p0, DuoRecFull* d_overflow, uint32_t overflow_cap, float4* d_snap_m, float4* d_snap_f,
-                                    uint32_t* d_totals, cudaStream_t s, int* n_launches) {
+                                    uint32_t* d_totals, uint32_t* d_layout, cudaStream_t s, int* n_launches) {
   k2_associate_single_kernel<<<1, kSingleThreads, 0, s>>>(cells_f, n_f, slot_f, cells_m, n_m, geom, d_pose0, k, metric, d_pairs, d_duos, d_recs, d_duo_p0,
-                                                         d_overflow, overflow_cap, d_snap_m, d_snap_f, d_totals);
+                                                         d_overflow, overflow_cap, d_snap_m, d_snap_f, d_totals, d_layout);
   if (n_launches) *n_launches += 1;
   return cudaGetLastError();
 }

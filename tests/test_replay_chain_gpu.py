@@ -100,3 +100,38 @@ def test_every_step_matches_oracle_teacher_forced(oracle, gpu_ctx, drive):
             cells, npts, slot = oracle.merge_map_cell(cells, npts, slot, p.size_x, p.size_y, p.resolution, mc, v["npts"])
     assert tight >= 0.9 * (tight + loose), (tight, loose)
     print("teacher-forced: %d steps at 1e-6 with equal iteration counts, %d stopped at different iterates (same minimum at tight tolerances, poses within %.1e there), worst %.2e" % (tight, loose, worst_tight, worst))
+
+
+@pytest.mark.parametrize("preset", ["oxford", "indoor"])
+def test_scan_step_equals_the_separate_calls(gpu_ctx, preset):
+    """randt_scan_step associates and solves back to back on the device (no host round trip in between, no pair lists, no K3 schedule).
+    A user of the separate entry points (randt_voxelize -> randt_associate -> randt_register_batch -> randt_map_transform_se2d ->
+    randt_map_merge) must get the same bits: poses, solver records and the submap after every keyframe."""
+    p = P.PRESETS[preset]
+    gp = capi.grid_params(p)
+    k = p.n_results_nn_lookup
+    opt = W.odometry_solver(capi, p)
+    _, scans = W.make_loop_drive(p, W.REPLAY_SCENE_SEED, 40)
+    loss = capi.make_loss(capi.LOSS_BARRON, p.loss_function_scale, p.loss_function_convexity, 1.0, 1.0)
+    empty = lambda: gpu_ctx.map_upload(np.zeros((0, 12), np.float32), np.zeros(2, np.uint32), gp)
+    sub_a, sub_b = empty(), empty()
+    pose_a = synth.pose_to_se2(0, 0, 0)
+    pose_a, _, _ = sub_a.scan_step(scans[0], gp, k, loss, p.ndt_weight, opt, True, pose_a)
+    pose_b = synth.pose_to_se2(0, 0, 0)
+    m0 = gpu_ctx.voxelize(scans[0], [0, len(scans[0])], gp)
+    m0.transform_se2d(pose_b[None]); sub_b.merge(m0); m0.close()
+    for i in range(1, len(scans)):
+        pose_a, res_a, nc = sub_a.scan_step(scans[i], gp, k, loss, p.ndt_weight, opt, i % 2 == 0, pose_a)
+        M = gpu_ctx.voxelize(scans[i], [0, len(scans[i])], gp)
+        assert M.info()[1] == nc
+        prob = gpu_ctx.associate(sub_b, M, pose_b[None], k)
+        out, res_b = prob.register_batch(pose_b[None], capi.make_loss(capi.LOSS_BARRON, p.loss_function_scale, p.loss_function_convexity, 1.0, p.ndt_weight / (nc * k)), opt)
+        pose_b = out[0]
+        assert np.array_equal(pose_a, pose_b), i
+        assert np.array_equal(res_a, res_b[0]), i
+        if i % 2 == 0:
+            M.transform_se2d(pose_b[None]); sub_b.merge(M)
+        M.close(); prob.close()
+    ca, cb = sub_a.download(), sub_b.download()
+    assert np.array_equal(ca["cells"], cb["cells"]) and np.array_equal(ca["npts"], cb["npts"]) and np.array_equal(ca["slot"], cb["slot"])
+    sub_a.close(); sub_b.close()
