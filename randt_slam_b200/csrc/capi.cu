@@ -407,11 +407,11 @@ int randt_voxelize(randt_ctx* ctx, const float* pts4, const uint32_t* scan_off, 
   m->device = ctx->device; m->sref = ctx->sref; m->gp = *gp; m->geom = make_geom(*gp); m->B = B;
   float4* d_pts = nullptr; bool own_pts = false;
   uint32_t *d_scan_off = nullptr, *d_cnt = nullptr, *d_npts_p = nullptr;
-  int32_t *d_labels_scratch = nullptr, *d_labels_p = nullptr; float4* d_cells_p = nullptr; int* d_status = nullptr;
+  int32_t* d_labels_p = nullptr; float4* d_cells_p = nullptr; int* d_status = nullptr;
   int rc = RANDT_OK;
   auto cleanup = [&]() {
     if (own_pts) dev_free(d_pts);
-    dev_free(d_scan_off); dev_free(d_cnt); dev_free(d_npts_p); dev_free(d_labels_scratch); dev_free(d_labels_p);
+    dev_free(d_scan_off); dev_free(d_cnt); dev_free(d_npts_p); dev_free(d_labels_p);
     dev_free(d_cells_p); dev_free(d_status);
   };
 #define CKV(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rc = fail(ctx, RANDT_E_CUDA, #call, e__); cleanup(); free_map(m); return rc; } } while (0)
@@ -419,13 +419,12 @@ int randt_voxelize(randt_ctx* ctx, const float* pts4, const uint32_t* scan_off, 
   else { CKV(dev_alloc(&d_pts, n_pts)); own_pts = true; if (n_pts) CKV(cudaMemcpyAsync(d_pts, pts4, (size_t)n_pts * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream)); }
   CKV(dev_alloc(&d_scan_off, B + 1));
   CKV(cudaMemcpyAsync(d_scan_off, scan_off, (size_t)(B + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-  CKV(dev_alloc(&d_cnt, B)); CKV(dev_alloc(&d_labels_scratch, n_pts));
+  CKV(dev_alloc(&d_cnt, B));
   CKV(dev_alloc(&d_cells_p, (size_t)B * cell_cap * 3)); CKV(dev_alloc(&d_npts_p, (size_t)B * cell_cap)); CKV(dev_alloc(&d_labels_p, (size_t)B * cell_cap));
   CKV(dev_alloc(&d_status, B));
   CKV(dev_alloc(&m->slot, (size_t)B * m->geom.n_slots));
   int nl = 0;
-  CKV(launch_voxelize(d_pts, d_scan_off, B, max_pts, *gp, m->geom, cell_cap, d_cells_p, d_npts_p, d_labels_p, d_cnt, m->slot, d_labels_scratch,
-                      d_status, ctx->stream, &nl));
+  CKV(launch_voxelize(d_pts, d_scan_off, B, max_pts, *gp, m->geom, cell_cap, d_cells_p, d_npts_p, d_labels_p, d_cnt, m->slot, d_status, ctx->stream, &nl));
   std::vector<uint32_t> h_cnt(B); std::vector<int> h_status(B);
   if (B) { CKV(cudaMemcpyAsync(h_cnt.data(), d_cnt, B * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
            CKV(cudaMemcpyAsync(h_status.data(), d_status, B * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream)); }
@@ -452,7 +451,7 @@ int randt_voxelize(randt_ctx* ctx, const float* pts4, const uint32_t* scan_off, 
   } else {
     CKV(dev_alloc(&m->cells, (size_t)m->n_cells * 3)); CKV(dev_alloc(&m->npts, m->n_cells)); CKV(dev_alloc(&m->labels, m->n_cells));
     CKV(launch_compact_cells(d_cells_p, d_npts_p, d_labels_p, m->cell_off, B, cell_cap, m->max_per_map, m->cells, m->npts, m->labels, ctx->stream, &nl));
-    CKV(cudaStreamSynchronize(ctx->stream));
+    // (no wait: the padded buffers are released in stream order, and every later use of the map is queued on the same stream)
   }
 #undef CKV
   ctx->launches += nl;
@@ -784,6 +783,14 @@ int randt_associate(randt_ctx* ctx, const randt_map* F, const randt_map* M, cons
     *out = p;
     return RANDT_OK;
   }
+  static const bool trace = getenv("RANDT_DEBUG_TIMING") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!trace) return;
+    auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "[randt] associate %-18s %8.1f us\n", what, std::chrono::duration<double, std::micro>(t - t_prev).count());
+    t_prev = t;
+  };
   float4* d_pose = nullptr; double* d_pose0 = nullptr; uint32_t *d_nn = nullptr, *d_cnt = nullptr, *d_scan = nullptr, *d_bs = nullptr, *d_cnt2 = nullptr, *d_scan2 = nullptr, *d_offs = nullptr;
   int rc = RANDT_OK; int nl = 0;
   auto cleanup = [&]() { dev_free(d_pose); dev_free(d_pose0); dev_free(d_nn); dev_free(d_cnt); dev_free(d_scan); dev_free(d_bs); dev_free(d_cnt2); dev_free(d_scan2); dev_free(d_offs); };
@@ -814,7 +821,9 @@ int randt_associate(randt_ctx* ctx, const randt_map* F, const randt_map* M, cons
   if (F->n_cells) CKA(cudaMemcpyAsync(p->cells_f, F->cells, (size_t)F->n_cells * 48, cudaMemcpyDeviceToDevice, ctx->stream));
   std::vector<uint32_t> h_offs(2 * ((size_t)B + 1));
   CKA(cudaMemcpyAsync(h_offs.data(), d_offs, h_offs.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  lap("queued");
   CKA(cudaStreamSynchronize(ctx->stream));
+  lap("device done");
   p->h_seg_off.assign(h_offs.begin(), h_offs.begin() + B + 1);
   p->h_duo_off.assign(h_offs.begin() + B + 1, h_offs.end());
   p->P = p->h_seg_off[B]; p->n_duos = p->h_duo_off[B];

@@ -7,11 +7,14 @@
 //   Map::insertCluster               R/src/ndt_representation/ndt_map.cpp:238-245       keep n > min_points; slot table, later wins
 //   Cell::addPointCloud/updateCell   R/src/ndt_representation/ndt_cell.cpp:25-114       mean, population covariance, regularisation
 //
-// One CTA per scan.  Points are read with coalesced float4 loads; labels are binned with a STABLE parallel counting sort
-// (each warp owns a contiguous slice of the scan, per-warp histograms in shared memory, warp-level __match_any_sync ranking)
-// so that every cell sees its points in original order; one warp per kept cell then accumulates the two passes in float32 in exactly
-// that order (coalesced loads of 32 points, the sequential sum carried through shuffles).  Kept cells are written in ascending-label order into a per-scan padded region and compacted
-// across the batch by a second kernel.
+// One CTA per scan.  Labels are binned (bin = label - smallest label of the scan) with warp-aggregated shared-memory atomics
+// (__match_any_sync: one update per distinct bin of a 32-point step) that give every bin its point count and a 32-bit mask of the
+// parts of the scan its points lie in.  The STABLE sort the reference's order-dependent float32 sums need is then done cell by cell:
+// one warp per kept cell walks only the parts its mask names, ballots the points that carry its bin and writes them — in scan order —
+// into the cell's run of a cell-major copy of the scan in shared memory (a filtered radar scan is azimuth-major, so a cell's points
+// lie within a few beams of each other and a walk is one or two parts; any other point order works, only slower).  One THREAD per kept
+// cell then runs the reference's two sequential passes over its run.  Kept cells are written in ascending-label order into a per-scan
+// padded region and compacted across the batch by a second kernel.
 #include <float.h>
 
 #include "common.cuh"
@@ -20,10 +23,9 @@
 namespace randt {
 namespace {
 
-constexpr int kVoxThreads = 1024;  // most threads of the one CTA a scan gets: 32 warps shorten every block-wide phase (the bin scans, the slot-table
-                                   // clear) of a lone scan; batches launch 512 so that two scans share an SM (56 registers per thread)
+constexpr int kVoxThreads = 1024;  // most threads of the one CTA a scan gets: 32 warps shorten every block-wide phase of a lone scan (and
+                                   // leave its ~100 cell walks 3-4 to a warp); batches launch 512 so that two scans share an SM
 constexpr int kVoxWarps = kVoxThreads / 32;
-constexpr int kVoxCountWarps = 8;  // warps that own a slice of the scan in the stable counting sort (one 16-bit histogram each)
 
 // exclusive block scan of a 64-bit value (two 32-bit counters packed: both are scanned in one pass)
 __device__ __forceinline__ unsigned long long block_scan_excl(unsigned long long v, unsigned long long* warp_sums, unsigned long long* total) {
@@ -107,18 +109,37 @@ struct CellOut { float mu[3]; float cov[9]; };
 
 // Cell::updateCell for a fresh cell: two sequential float32 passes over the cell's points (ndt_cell.cpp:43-65), then the
 // xy eigenvalue floor and the +1e-6 on the intensity variance (ndt_cell.cpp:102-112).
-// One THREAD per cell: the stable counting sort has laid the cell's points (x, y, intensity) out contiguously in scan order in SHARED
-// memory, so the thread walks its own run at shared-memory latency, adding in point order: the order (and with it every rounding) is
-// exactly the reference's sequential loop, and the 32 lanes of a warp work on 32 cells at once.
+// One THREAD per cell: the cell's points (x, y, intensity) lie contiguously in scan order in SHARED memory, so the thread walks its
+// own run at shared-memory latency, adding in point order: the order (and with it every rounding) is exactly the reference's
+// sequential loop, and the 32 lanes of a warp work on 32 cells at once.  Eight points are fetched per round so that the loads do
+// not sit in the dependent chain of the sums.
 __device__ void cell_stats_thread(const float* __restrict__ px, const float* __restrict__ py, const float* __restrict__ pi, uint32_t n, CellOut& o) {
   float sx = 0.f, sy = 0.f, si = 0.f;
-#pragma unroll 4
-  for (uint32_t k = 0; k < n; ++k) { sx += px[k]; sy += py[k]; si += pi[k]; }
+  uint32_t k = 0;
+  for (; k + 8u <= n; k += 8u) {
+    float x[8], y[8], z[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { x[u] = px[k + u]; y[u] = py[k + u]; z[u] = pi[k + u]; }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { sx += x[u]; sy += y[u]; si += z[u]; }
+  }
+  for (; k < n; ++k) { sx += px[k]; sy += py[k]; si += pi[k]; }
   const float nf = (float)n;
   const float mx = sx / nf, my = sy / nf, mz = si / nf;
   float c00 = 0.f, c11 = 0.f, c22 = 0.f, c01 = 0.f, c02 = 0.f, c12 = 0.f;
-#pragma unroll 4
-  for (uint32_t k = 0; k < n; ++k) {
+  k = 0;
+  for (; k + 4u <= n; k += 4u) {
+    float x[4], y[4], z[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { x[u] = px[k + u]; y[u] = py[k + u]; z[u] = pi[k + u]; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float dx = x[u] - mx, dy = y[u] - my, di = z[u] - mz;
+      c00 += dx * dx; c11 += dy * dy; c22 += di * di;
+      c01 += dx * dy; c02 += dx * di; c12 += dy * di;
+    }
+  }
+  for (; k < n; ++k) {
     const float dx = px[k] - mx, dy = py[k] - my, di = pi[k] - mz;
     c00 += dx * dx; c11 += dy * dy; c22 += di * di;
     c01 += dx * dy; c02 += dx * di; c12 += dy * di;
@@ -143,23 +164,29 @@ __device__ void cell_stats_thread(const float* __restrict__ px, const float* __r
 
 // per-scan status codes: VOX_* in common.cuh
 
-// dynamic shared memory: uint32 bin_start[span_cap] | uint32 bin_keep[span_cap] | uint16 whist[n_cnt_warps][span_cap] | float sx[pt_cap] sy[pt_cap] si[pt_cap]
-//   bin_start[bin] = kept points before the bin (where the bin's run starts in sx / sy / si)
-//   bin_keep[bin]  = index of the bin's cell among the kept cells of the scan, or kNotKept
-constexpr uint32_t kNotKept = 0xffffffffu;
+// dynamic shared memory: uint32 mask[span_cap] | uint16 cnt[span_cap] | uint16 start[span_cap] | float sx[pt_cap] sy[pt_cap] si[pt_cap] | uint16 bins[pt_cap] | uint16 order[cell_cap]
+//   mask[bin]:  bit j set = the bin has points among the scan's points [j part, (j + 1) part)  (part = a whole number of 32-point steps)
+//   cnt[bin]:   the bin's point count (two 16-bit counters to a word, added to as one 32-bit atomic: a scan has at most 16 384 points,
+//               so a counter cannot carry into its neighbour)
+//   start[bin]: where the (kept) bin's run starts in sx / sy / si;  until the sort, the labels (int32) live in the sx array
+//   order[i]:   the kept cells by falling size class (so that the 32 cells a warp takes in phase 4 are about equally long)
 __global__ void __launch_bounds__(kVoxThreads) k1_voxelize_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ scan_off,
                                                                  int row, float label_res, int min_points, MapGeomDev geom,
-                                                                 uint32_t span_cap, int n_cnt_warps, uint32_t cell_cap, float4* __restrict__ cells_out,
+                                                                 uint32_t span_cap, uint32_t cell_cap, float4* __restrict__ cells_out,
                                                                  uint32_t* __restrict__ npts_out, int32_t* __restrict__ labels_out,
                                                                  uint32_t* __restrict__ cell_count, int32_t* __restrict__ slot_out,
-                                                                 int32_t* __restrict__ labels_scratch, uint32_t pt_cap, int* __restrict__ status) {
+                                                                 uint32_t pt_cap, int* __restrict__ status) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint32_t* bin_start = reinterpret_cast<uint32_t*>(smem_raw);
-  uint32_t* bin_keep = bin_start + span_cap;
-  unsigned short* whist = reinterpret_cast<unsigned short*>(bin_keep + span_cap);
-  float* sx = reinterpret_cast<float*>(whist + (size_t)n_cnt_warps * span_cap);
+  uint32_t* mask = reinterpret_cast<uint32_t*>(smem_raw);
+  uint32_t* cnt2 = mask + span_cap;                                         // span_cap / 2 words
+  unsigned short* start = reinterpret_cast<unsigned short*>(cnt2 + span_cap / 2u);
+  float* sx = reinterpret_cast<float*>(start + span_cap);
   float* sy = sx + pt_cap;
   float* si = sy + pt_cap;
+  unsigned short* bins = reinterpret_cast<unsigned short*>(si + pt_cap);
+  unsigned short* order = bins + pt_cap;
+  int* labs = reinterpret_cast<int*>(sx);
+  __shared__ uint32_t s_class[32], s_class_at[32];
   __shared__ unsigned long long warp_sums[32];
   __shared__ int s_min[kVoxWarps], s_max[kVoxWarps];
   __shared__ int s_lab_min, s_lab_max;
@@ -181,19 +208,26 @@ __global__ void __launch_bounds__(kVoxThreads) k1_voxelize_kernel(const float4* 
   if (n == 0) return;
   if (n > pt_cap) { if (tid == 0) status[b] = VOX_SPAN; return; }
 
-  // ---- phase 0: labels (Grid::cluster), min/max label ----
+  // ---- phase 0: labels (Grid::cluster), smallest / largest label ----
   int lmin = INT_MAX, lmax = INT_MIN;
-  for (uint32_t e = tid; e < n; e += n_thr) {
-    const float4 p = __ldg(pts + p0 + e);
-    const int lab = (int)(p.x / label_res) + row * (int)(p.y / label_res);   // C++ float->int conversion truncates toward zero
-    labels_scratch[p0 + e] = lab;
-    lmin = min(lmin, lab); lmax = max(lmax, lab);
+  for (uint32_t e = tid; e < n; e += 4u * n_thr) {        // four loads in flight per thread
+    float4 p[4];
+#pragma unroll
+    for (uint32_t u = 0; u < 4u; ++u) if (e + u * n_thr < n) p[u] = __ldg(pts + p0 + e + u * n_thr);
+#pragma unroll
+    for (uint32_t u = 0; u < 4u; ++u) {
+      if (e + u * n_thr < n) {
+        const int lab = (int)(p[u].x / label_res) + row * (int)(p[u].y / label_res);   // C++ float->int conversion truncates toward zero
+        labs[e + u * n_thr] = lab;
+        lmin = min(lmin, lab); lmax = max(lmax, lab);
+      }
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, o)); lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o)); }
   if (lane == 0) { s_min[warp] = lmin; s_max[warp] = lmax; }
-  // per-warp histograms cleared while the labels settle
-  for (uint32_t e = tid; e < (uint32_t)n_cnt_warps * span_cap / 2u; e += n_thr) reinterpret_cast<uint32_t*>(whist)[e] = 0u;
+  for (uint32_t e = tid; e < span_cap + span_cap / 2u; e += n_thr) mask[e] = 0u;      // mask and cnt2 are adjacent
+  if (tid < 32) s_class[tid] = 0u;
   __syncthreads();
   if (warp == 0) {
     int a = lane < n_warps ? s_min[lane] : INT_MAX, z = lane < n_warps ? s_max[lane] : INT_MIN;
@@ -206,114 +240,116 @@ __global__ void __launch_bounds__(kVoxThreads) k1_voxelize_kernel(const float4* 
   const long long span_ll = (long long)s_lab_max - (long long)lab_min + 1;
   if (span_ll > (long long)span_cap) { if (tid == 0) status[b] = VOX_SPAN; return; }
   const uint32_t span = (uint32_t)span_ll;
+  const uint32_t n_steps = (n + 31u) >> 5;
+  const uint32_t part_steps = (n_steps + 31u) >> 5;          // 32-point steps per mask bit
 
-  // ---- phase 1: per-warp histograms over contiguous slices (stable counting sort, pass 1) ----
-  const uint32_t slice = (n + n_cnt_warps - 1) / n_cnt_warps;
-  if (slice > 65535u) { if (tid == 0) status[b] = VOX_SPAN; return; }
-  if (warp < n_cnt_warps) {
-    const uint32_t s0 = warp * slice, s1 = min(n, s0 + slice);
-    unsigned short* h = whist + (size_t)warp * span_cap;
-    // the slice is walked 32 points at a time in scan order (each step updates the histogram the next one reads), but the labels of
-    // eight steps are fetched up front: the global-memory latency is paid once per eight steps instead of once per step
-    for (uint32_t base = s0; base < s1; base += 32u * 8u) {
-      uint32_t bins[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const uint32_t e = base + 32u * (uint32_t)u + lane;
-        bins[u] = e < s1 ? (uint32_t)(labels_scratch[p0 + e] - lab_min) : 0xffffffffu;
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        if (base + 32u * (uint32_t)u >= s1) break;          // warp-uniform
-        const uint32_t bin = bins[u];
-        const unsigned peers = __match_any_sync(0xffffffffu, bin);
-        if (bin != 0xffffffffu && (__ffs(peers) - 1) == lane) h[bin] = (unsigned short)(h[bin] + __popc(peers));
-        __syncwarp();
+  // ---- phase 1: bin of every point; per bin the point count and the parts of the scan it occurs in (one shared-memory update per
+  //      distinct bin of a 32-point step: points along a beam share their cell) ----
+  for (uint32_t e0 = (uint32_t)warp * 32u; e0 < n; e0 += n_thr) {
+    const uint32_t e = e0 + (uint32_t)lane;
+    const bool act = e < n;
+    uint32_t bin = 0xffffffffu;
+    if (act) bin = (uint32_t)(labs[e] - lab_min);
+    const unsigned peers = __match_any_sync(0xffffffffu, bin);
+    if (act) {
+      bins[e] = (unsigned short)bin;
+      if ((__ffs(peers) - 1) == lane) {
+        atomicAdd(&cnt2[bin >> 1], (uint32_t)__popc(peers) << (16u * (bin & 1u)));
+        atomicOr(&mask[bin], 1u << ((e0 >> 5) / part_steps));
       }
     }
   }
   __syncthreads();
 
-  // ---- phase 2: totals per bin -> exclusive scans: points before the bin (bin_start) and kept cells before the bin (ascending label =
-  //      cluster order; keep test count > min_points, Cell::addPointCloud) — both counters in one 64-bit scan ----
-  unsigned long long carry = 0ull;
-  for (uint32_t base = 0; base < span; base += n_thr) {
-    const uint32_t bin = base + tid;
-    uint32_t tot = 0;
-    if (bin < span) for (int w = 0; w < n_cnt_warps; ++w) tot += whist[(size_t)w * span_cap + bin];
-    const bool keep = tot > 0u && (long long)tot > (long long)min_points;
-    unsigned long long total;
-    const unsigned long long ex = carry + block_scan_excl((unsigned long long)(keep ? tot : 0u) | ((unsigned long long)(keep ? 1u : 0u) << 32), warp_sums, &total);
-    if (bin < span) {
-      bin_start[bin] = (uint32_t)ex;
+  // ---- phase 2: kept cells in ascending label (= cluster) order and where their runs start; keep test count > min_points
+  //      (Cell::addPointCloud).  Every thread owns a run of consecutive bins; one 64-bit block scan (kept cells | kept points) ----
+  const uint32_t per = (span + n_thr - 1u) / n_thr;
+  const uint32_t b0 = min(span, (uint32_t)tid * per), b1 = min(span, b0 + per);
+  unsigned long long mine_sum = 0ull;
+  for (uint32_t bin = b0; bin < b1; ++bin) {
+    const uint32_t tot = (cnt2[bin >> 1] >> (16u * (bin & 1u))) & 0xffffu;
+    if (tot > 0u && (long long)tot > (long long)min_points) mine_sum += (unsigned long long)tot | (1ull << 32);
+  }
+  unsigned long long total;
+  unsigned long long ex = block_scan_excl(mine_sum, warp_sums, &total);
+  for (uint32_t bin = b0; bin < b1; ++bin) {
+    const uint32_t tot = (cnt2[bin >> 1] >> (16u * (bin & 1u))) & 0xffffu;
+    if (tot > 0u && (long long)tot > (long long)min_points) {
       const uint32_t ci = (uint32_t)(ex >> 32);
-      bin_keep[bin] = keep ? ci : kNotKept;
-      if (keep) {
-        if (ci < cell_cap) { npts_out[(size_t)b * cell_cap + ci] = tot; labels_out[(size_t)b * cell_cap + ci] = (int32_t)bin + lab_min; }
-        else status[b] = VOX_CELL_CAP;
-      }
-      // turn per-warp counts into per-warp offsets inside the bin
-      uint32_t run = 0;
-      for (int w = 0; w < n_cnt_warps; ++w) {
-        const uint32_t c = whist[(size_t)w * span_cap + bin];
-        whist[(size_t)w * span_cap + bin] = (unsigned short)run;
-        run += c;
-      }
-      if (run > 65535u) status[b] = VOX_SPAN;   // a single cell with > 65535 points does not fit the 16-bit offsets
-    }
-    carry += total;
-  }
-  __syncthreads();
-  const uint32_t n_keep = min((uint32_t)(carry >> 32), cell_cap);
-
-  // ---- phase 3: stable scatter of the points (x, y, intensity) of kept cells into cell-major, scan-ordered runs in shared memory ----
-  if (warp < n_cnt_warps) {
-    const uint32_t s0 = warp * slice, s1 = min(n, s0 + slice);
-    unsigned short* h = whist + (size_t)warp * span_cap;
-    for (uint32_t base = s0; base < s1; base += 32u * 4u) {       // labels and points of four steps fetched up front (see phase 1)
-      uint32_t bins[4]; float4 pp[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const uint32_t e = base + 32u * (uint32_t)u + lane;
-        const bool act = e < s1;
-        bins[u] = act ? (uint32_t)(labels_scratch[p0 + e] - lab_min) : 0xffffffffu;
-        pp[u] = act ? __ldg(pts + p0 + e) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (base + 32u * (uint32_t)u >= s1) break;          // warp-uniform
-        const uint32_t bin = bins[u];
-        const bool act = bin != 0xffffffffu;
-        const unsigned peers = __match_any_sync(0xffffffffu, bin);
-        const int leader = __ffs(peers) - 1;
-        uint32_t off = 0;
-        if (act && leader == lane) { off = h[bin]; h[bin] = (unsigned short)(off + __popc(peers)); }
-        off = __shfl_sync(0xffffffffu, off, leader);
-        if (act && bin_keep[bin] != kNotKept) {
-          const uint32_t at = bin_start[bin] + off + __popc(peers & ((1u << lane) - 1u));
-          sx[at] = pp[u].x; sy[at] = pp[u].y; si[at] = pp[u].w;
-        }
-        __syncwarp();
-      }
+      start[bin] = (unsigned short)(uint32_t)ex;
+      if (ci < cell_cap) {
+        npts_out[(size_t)b * cell_cap + ci] = tot; labels_out[(size_t)b * cell_cap + ci] = (int32_t)bin + lab_min;
+        atomicAdd(&s_class[31 - __clz(tot)], 1u);       // size class = floor(log2(points))
+      } else status[b] = VOX_CELL_CAP;
+      ex += (unsigned long long)tot | (1ull << 32);
     }
   }
-  __syncthreads();
-
+  __syncthreads();          // (also: every thread has read its labels; the sx array is free for the sorted points)
+  const uint32_t n_keep = min((uint32_t)(total >> 32), cell_cap);
   if (tid == 0) cell_count[b] = n_keep;
-  // ---- phase 4: one thread per kept cell: sequential float32 statistics, slot table ----
-  for (uint32_t ci = tid; ci < n_keep; ci += n_thr) {
-    const uint32_t bin = (uint32_t)(labels_out[(size_t)b * cell_cap + ci] - lab_min);
-    const uint32_t cnt = npts_out[(size_t)b * cell_cap + ci];
-    const uint32_t at = bin_start[bin];
+  if (warp == 0) {       // where every size class starts in `order`, largest class first
+    const uint32_t mine_n = s_class[31 - lane];
+    uint32_t x = mine_n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    s_class_at[31 - lane] = x - mine_n;
+  }
+  __syncthreads();
+  for (uint32_t c = tid; c < n_keep; c += n_thr)
+    order[atomicAdd(&s_class_at[31 - __clz(npts_out[(size_t)b * cell_cap + c])], 1u)] = (unsigned short)c;
+
+  // ---- phase 3: stable sort, one warp per kept cell: walk the parts of the scan the cell occurs in, ballot the points that carry its
+  //      bin, write them in scan order into the cell's run ----
+  const unsigned lt = (1u << lane) - 1u;
+  for (uint32_t c = (uint32_t)warp; c < n_keep; c += (uint32_t)n_warps) {
+    const uint32_t bin = (uint32_t)(labels_out[(size_t)b * cell_cap + c] - lab_min);
+    const uint32_t cnt = npts_out[(size_t)b * cell_cap + c];
+    uint32_t at = start[bin], left = cnt;
+    unsigned m = mask[bin];
+    while (m != 0u && left != 0u) {
+      const uint32_t j = (uint32_t)__ffs(m) - 1u;
+      m &= m - 1u;
+      const uint32_t s_end = min(n_steps, (j + 1u) * part_steps);
+      for (uint32_t st = j * part_steps; st < s_end && left != 0u; st += 4u) {
+        // four steps per round: the point loads of all four are in flight before the first is stored
+        bool hit[4]; unsigned bal[4]; float4 p[4];
+#pragma unroll
+        for (uint32_t u = 0; u < 4u; ++u) {
+          const uint32_t e = ((st + u) << 5) + (uint32_t)lane;
+          hit[u] = (st + u) < s_end && e < n && bins[e] == (unsigned short)bin;
+          bal[u] = __ballot_sync(0xffffffffu, hit[u]);
+          if (hit[u]) p[u] = __ldg(pts + p0 + e);
+        }
+#pragma unroll
+        for (uint32_t u = 0; u < 4u; ++u) {
+          if (hit[u]) {
+            const uint32_t pos = at + (uint32_t)__popc(bal[u] & lt);
+            sx[pos] = p[u].x; sy[pos] = p[u].y; si[pos] = p[u].w;
+          }
+          const uint32_t k = (uint32_t)__popc(bal[u]);
+          at += k; left -= k;
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 4: one thread per kept cell: sequential float32 statistics, slot table.  Cells are taken 32 to a warp in falling size
+  //      class: a warp runs as long as its longest cell, and the fewest warps are busy (the code is issue-bound, not latency-bound) ----
+  for (uint32_t i = tid; i < n_keep; i += n_thr) {
+    const uint32_t c = order[i];
+    const uint32_t bin = (uint32_t)(labels_out[(size_t)b * cell_cap + c] - lab_min);
+    const uint32_t cnt = npts_out[(size_t)b * cell_cap + c];
+    const uint32_t at = start[bin];
     CellOut o;
     cell_stats_thread(sx + at, sy + at, si + at, cnt, o);
     const uint32_t s = coord_to_index(geom, o.mu[0], o.mu[1]);
-    float4* dst = cells_out + 3 * ((size_t)b * cell_cap + ci);
+    float4* dst = cells_out + 3 * ((size_t)b * cell_cap + c);
     dst[0] = make_float4(o.mu[0], o.mu[1], o.mu[2], o.cov[0]);
     dst[1] = make_float4(o.cov[1], o.cov[2], o.cov[3], o.cov[4]);
     dst[2] = make_float4(o.cov[5], o.cov[6], o.cov[7], o.cov[8]);
     // the reference would throw (vector::at) for a mean outside the map; flagged instead, cell kept without a slot
-    if (s < geom.n_slots) atomicMax(&slot[s], (int32_t)ci);   // "later cluster wins" == largest kept index
+    if (s < geom.n_slots) atomicMax(&slot[s], (int32_t)c);   // "later cluster wins" == largest kept index
     else status[b] = VOX_OUT_OF_MAP;
   }
 }
@@ -463,8 +499,8 @@ __global__ void __launch_bounds__(kMergeThreads) merge_maps_kernel(const float4*
 
 cudaError_t launch_voxelize(const float4* d_pts, const uint32_t* d_scan_off, uint32_t n_scans, uint32_t max_pts_per_scan,
                             const randt_grid_params& gp, const MapGeomDev& geom, uint32_t cell_cap_per_scan, float4* d_cells_p,
-                            uint32_t* d_npts_p, int32_t* d_labels_p, uint32_t* d_cell_count, int32_t* d_slot, int32_t* d_labels_scratch,
-                            int* d_status, cudaStream_t s, int* n_launches) {
+                            uint32_t* d_npts_p, int32_t* d_labels_p, uint32_t* d_cell_count, int32_t* d_slot, int* d_status, cudaStream_t s,
+                            int* n_launches) {
   if (n_scans == 0) return cudaSuccess;
   const int row = static_cast<int>(sqrt((double)(size_t)gp.n_clusters));
   if (row <= 0) return cudaErrorInvalidValue;
@@ -473,26 +509,21 @@ cudaError_t launch_voxelize(const float4* d_pts, const uint32_t* d_scan_off, uin
   const long long bound = (long long)(row + 4) * (long long)(row + 4);
   uint32_t span_cap = (uint32_t)((bound + 255) / 256 * 256);
   const size_t smem_max = 220 * 1024;
-  const uint32_t pt_cap = (max_pts_per_scan + 31u) / 32u * 32u;        // the kept points of a scan are staged in shared memory
-  const size_t fixed = (size_t)pt_cap * 12;
-  if (fixed + 1024 > smem_max) return cudaErrorInvalidValue;           // > 18 k points in one scan (randt_voxelize refuses such scans)
-  if ((size_t)span_cap * (8 + 2) + fixed > smem_max) span_cap = (uint32_t)((smem_max - fixed) / 10 / 256 * 256);
+  const uint32_t pt_cap = (max_pts_per_scan + 31u) / 32u * 32u;        // a scan is staged in shared memory: 14 bytes per point (+ 2 per cell)
+  const size_t fixed = (size_t)pt_cap * 14 + (((size_t)std::min(cell_cap_per_scan, pt_cap) * 2 + 15) & ~(size_t)15);
+  if (fixed + 1536 > smem_max) return cudaErrorInvalidValue;           // > 16 k points in one scan (randt_voxelize refuses such scans)
+  if ((size_t)span_cap * 8 + fixed > smem_max) span_cap = (uint32_t)((smem_max - fixed) / 8 / 256 * 256);
+  span_cap = std::min<uint32_t>(span_cap, 65280u);                     // bins are 16 bit (0xffff marks "no point")
   if (span_cap == 0) return cudaErrorInvalidValue;
-  // counting warps: each owns a contiguous slice of the scan and a 16-bit histogram.  As many as leave room for a second CTA on the
-  // SM when the batch has more scans than SMs; small scans do not need all of them (fewer histograms to clear and fold).
-  const size_t budget = n_scans > (uint32_t)kSmCount ? (size_t)110 * 1024 : smem_max;
-  int n_cnt_warps = kVoxCountWarps;
-  while (n_cnt_warps > 1 && ((size_t)span_cap * 8 + (size_t)n_cnt_warps * span_cap * 2 + fixed > budget ||
-                             (max_pts_per_scan + n_cnt_warps - 1) / n_cnt_warps < 256)) n_cnt_warps >>= 1;
-  const size_t smem = (size_t)span_cap * 8 + (size_t)n_cnt_warps * span_cap * 2 + fixed;
-  if (smem > smem_max) return cudaErrorInvalidValue;
-  cudaError_t e = cudaSuccess;
-  if (smem > 48u * 1024u) e = cudaFuncSetAttribute(k1_voxelize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  const int threads = n_scans > (uint32_t)kSmCount ? 512 : kVoxThreads;     // a batch: two scans per SM; a lone scan: all 32 warps
-  k1_voxelize_kernel<<<n_scans, threads, smem, s>>>(d_pts, d_scan_off, row, label_res, gp.min_points, geom, span_cap, n_cnt_warps,
-                                                    cell_cap_per_scan, d_cells_p, d_npts_p, d_labels_p, d_cell_count, d_slot,
-                                                    d_labels_scratch, pt_cap, d_status);
+  const size_t smem = (size_t)span_cap * 8 + fixed;
+  if (smem > 48u * 1024u) {
+    const cudaError_t e = cudaFuncSetAttribute(k1_voxelize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  const bool batch = n_scans > (uint32_t)kSmCount;
+  const int threads = batch ? 512 : kVoxThreads;     // (256 and 1024 threads per scan measured 20 % and 35 % slower on a 4096-scan batch)     // a batch: two (or more) scans per SM; a lone scan: all 32 warps
+  k1_voxelize_kernel<<<n_scans, threads, smem, s>>>(d_pts, d_scan_off, row, label_res, gp.min_points, geom, span_cap, cell_cap_per_scan, d_cells_p,
+                                                    d_npts_p, d_labels_p, d_cell_count, d_slot, pt_cap, d_status);
   if (n_launches) *n_launches += 1;
   return cudaGetLastError();
 }
