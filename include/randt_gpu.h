@@ -208,6 +208,12 @@ RANDT_API int randt_problem_info(const randt_problem* p, uint32_t* n_segments, u
 /* how K3 holds the problem in HBM: records of record_bytes each (one per duo = two pairs sharing their moving cell), of which
  * n_overflow needed a full-precision side record; any pointer may be NULL */
 RANDT_API int randt_problem_layout(const randt_problem* p, uint32_t* n_duos, uint32_t* record_bytes, uint32_t* n_overflow);
+/* the work schedule K3 walks (introspection; tests compare it with the host builder in csrc/schedule.hpp).  counts [5]: warps of the
+ * schedule, tiles, chunks of plan A (split chunks allowed), chunks of plan B, the warp budget the schedule was built for.  plan_a4 /
+ * plan_b4: the chunk descriptors as 4 x uint32 {duo_begin, meta, seg, part} (at most cap_chunks each); woff_a / woff_b: [warps + 1]
+ * chunk ranges per warp (at most cap_warps + 1 each); duo_off: [n_segments + 1].  Any pointer but counts may be NULL. */
+RANDT_API int randt_problem_schedule(randt_ctx* ctx, const randt_problem* p, uint32_t* counts, uint32_t* plan_a4, uint32_t* plan_b4,
+                                     uint32_t cap_chunks, uint32_t* woff_a, uint32_t* woff_b, uint32_t cap_warps, uint32_t* duo_off);
 /* any pointer may be NULL */
 RANDT_API int randt_problem_download(randt_ctx* ctx, const randt_problem* p, uint32_t* pair_m, uint32_t* pair_f, uint32_t* seg_off);
 /* the snapshotted cell tables: cells_m [n_m][12], cells_f [n_f][12]; either may be NULL */

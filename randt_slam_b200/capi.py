@@ -122,6 +122,7 @@ _SIGS = {
     "randt_eval_allpairs": (_i, [_vp, _vp, _vp, _i, _vp, _vp, C.c_double, _vp]),
     "randt_eval_allpairs_dev": (_i, [_vp, _vp, _vp, _i, _vp, _vp, C.c_double, _vp]),
     "randt_problem_layout": (_i, [_vp, C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_u32)]),
+    "randt_problem_schedule": (_i, [_vp, _vp, _vp, _vp, _vp, _u32, _vp, _vp, _u32, _vp]),
     "randt_problem_download": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "randt_problem_download_cells": (_i, [_vp, _vp, _vp, _vp]),
     "randt_problem_destroy": (None, [_vp]),
@@ -395,6 +396,16 @@ class Problem:
             self.close()
         except Exception:
             pass
+
+    def schedule(self):
+        """the work schedule K3 walks, as built on the device -> dict (same keys as hostapi.build_schedule where they apply)"""
+        counts = np.zeros(5, np.uint32)
+        self.ctx._check(lib().randt_problem_schedule(self.ctx._h, self._h, _ptr(counts), None, None, 0, None, None, 0, None))
+        nw, nt, na, nb, budget = (int(c) for c in counts)
+        pa = np.zeros((max(na, 1), 4), np.uint32); pb = np.zeros((max(nb, 1), 4), np.uint32)
+        wa = np.zeros(nw + 1, np.uint32); wb = np.zeros(nw + 1, np.uint32); doff = np.zeros(self.n_segments + 1, np.uint32)
+        self.ctx._check(lib().randt_problem_schedule(self.ctx._h, self._h, _ptr(counts), _ptr(pa), _ptr(pb), max(na, nb, 1), _ptr(wa), _ptr(wb), nw, _ptr(doff)))
+        return dict(n_warps=nw, n_tiles=nt, plan_a=pa[:na], plan_b=pb[:nb], woff_a=wa, woff_b=wb, duo_off=doff, warp_budget=budget)
 
     def layout(self):
         """-> (n_duos, record_bytes, n_overflow): the record table K3 streams"""

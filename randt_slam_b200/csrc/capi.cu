@@ -67,6 +67,11 @@ struct randt_ctx {
   std::string err;
   uint64_t launches = 0;
   unsigned long long* d_bad = nullptr;   // count of degenerate pairs seen by K3
+  // scratch of finish_problem / randt_associate, kept between calls: the schedule builder's vectors, a pinned staging block for the
+  // one upload a problem's schedule needs (stage_ev: that upload has left the block) and a pinned block for offset read-backs
+  Schedule sched;
+  uint32_t* h_stage = nullptr; size_t stage_cap = 0; cudaEvent_t stage_ev = nullptr; bool stage_busy = false;
+  uint32_t* h_offs = nullptr; size_t offs_cap = 0; cudaEvent_t offs_ev = nullptr;
 };
 
 struct randt_map {
@@ -102,6 +107,9 @@ struct randt_problem {
   uint32_t* seg_off = nullptr;
   uint32_t *seg_duo_off = nullptr, *rec_of_tile = nullptr; uint32_t tile_duos = 0;   // what the persistent solver walks
   uint32_t *solve_items = nullptr, *solve_counter = nullptr; uint32_t n_solve_items = 0; bool solve_all = true;   // segments short enough for it
+  uint32_t* sched_blob = nullptr;     // one allocation behind warp_off .. solve_items (views into it)
+  double* work_blob = nullptr;        // one allocation behind partials, d_poses, d_out, d_mu, seg_counters, solve_counter
+  unsigned char* assoc_blob = nullptr;
   double* partials = nullptr;
   uint32_t* seg_counters = nullptr;
   std::vector<uint32_t> h_seg_off;
@@ -171,16 +179,30 @@ void free_map(randt_map* m) {
 }
 void free_problem(randt_problem* p) {
   if (!p) return;
-  dev_free(p->cells_m); dev_free(p->cells_f); dev_free(p->pairs); dev_free(p->duos); dev_free(p->duo_recs); dev_free(p->duo_p0); dev_free(p->duo_overflow); dev_free(p->chunks); dev_free(p->warp_off); dev_free(p->chunks_full); dev_free(p->warp_off_full); dev_free(p->seg_first_tile); dev_free(p->seg_off); dev_free(p->seg_duo_off); dev_free(p->rec_of_tile); dev_free(p->solve_items); dev_free(p->solve_counter);
-  dev_free(p->partials); dev_free(p->seg_counters); dev_free(p->d_poses); dev_free(p->d_out); dev_free(p->d_mu); dev_free(p->d_r);
-  dev_free(p->d_J); dev_free(p->d_sweep); dev_free(p->lm_weight);
+  dev_free(p->cells_m); dev_free(p->cells_f); dev_free(p->pairs); dev_free(p->duos); dev_free(p->duo_recs); dev_free(p->duo_p0); dev_free(p->duo_overflow);
+  dev_free(p->chunks); dev_free(p->chunks_full);
+  dev_free(p->sched_blob);     // warp_off, warp_off_full, seg_first_tile, seg_off, seg_duo_off, rec_of_tile, solve_items
+  dev_free(p->work_blob);      // partials, d_poses, d_out, d_mu, seg_counters, solve_counter
+  dev_free(p->d_r); dev_free(p->d_J); dev_free(p->d_sweep); dev_free(p->lm_weight);
   dev_free(p->lm_state); dev_free(p->lm_eval_pose); dev_free(p->lm_mu); dev_free(p->lm_rec); dev_free(p->lm_poses); dev_free(p->lm_result);
   dev_free(p->lm_active); dev_free(p->lm_n_active);
   dev_free(p->lm_chunks); dev_free(p->lm_flags); dev_free(p->lm_scan); dev_free(p->lm_bs); dev_free(p->lm_warp_off);
   delete p;
 }
 
-// tile list, balanced schedule, record table and per-segment bookkeeping from a host seg_off; uploads everything a DeviceProblem needs
+// a pinned host block of the context, grown on demand
+int pinned_reserve(randt_ctx* ctx, uint32_t** buf, size_t* cap, size_t words) {
+  if (*cap >= words) return RANDT_OK;
+  if (*buf) { cudaFreeHost(*buf); *buf = nullptr; *cap = 0; }
+  const size_t want = std::max<size_t>(words + words / 2, 4096);
+  if (cudaHostAlloc(reinterpret_cast<void**>(buf), want * sizeof(uint32_t), cudaHostAllocDefault) != cudaSuccess) return fail(ctx, RANDT_E_NOMEM, "pinned staging block");
+  *cap = want;
+  return RANDT_OK;
+}
+
+// tile list, balanced schedule, record table and per-segment bookkeeping from the host offsets of a problem.  The host computes the
+// tile assignment only (schedule.hpp build_schedule_core, vectors reused between calls); everything the device needs goes up in ONE
+// copy from a pinned block, and the chunk lists of both plans are written by a kernel.
 int finish_problem(randt_ctx* ctx, randt_problem* p, bool records_ready = false) {
   static const bool trace = getenv("RANDT_DEBUG_TIMING") != nullptr;
   auto t_prev = std::chrono::steady_clock::now();
@@ -190,50 +212,61 @@ int finish_problem(randt_ctx* ctx, randt_problem* p, bool records_ready = false)
     fprintf(stderr, "[randt] finish_problem %-18s %8.1f us\n", what, std::chrono::duration<double, std::micro>(t - t_prev).count());
     t_prev = t;
   };
-  Schedule sch;
-  build_schedule(p->h_duo_off.data(), p->S, (uint32_t)kK3MaxWarps, sch);     // schedule.hpp: tiles, LPT assignment, plan A / plan B
-  const std::vector<Tile>& tiles = sch.tiles;
-  const std::vector<uint32_t>& first = sch.first;
-  const std::vector<ChunkDesc>&planA = sch.planA, &planB = sch.planB;
-  const std::vector<uint32_t>&woffA = sch.woffA, &woffB = sch.woffB, &tile_rec_begin = sch.tile_rec_begin, &tile_duo_begin = sch.tile_duo_begin;
-  const uint32_t n_warps = sch.n_warps;
+  Schedule& sch = ctx->sched;
+  const uint32_t S = p->S;
+  build_schedule_core(p->h_duo_off.data(), S, (uint32_t)kK3MaxWarps, sch);     // schedule.hpp: tiles, LPT assignment, record layout, chunk ranges
+  const uint32_t W = sch.n_warps, T = (uint32_t)sch.tiles.size();
   lap("schedule");
-  p->n_warps = n_warps;
-  p->n_chunks = (uint32_t)planB.size(); p->n_chunks_full = (uint32_t)planA.size();
-  p->n_tiles = (uint32_t)tiles.size();
-  for (uint32_t s = 0; s < p->S; ++s) if (p->h_seg_off[s + 1] == p->h_seg_off[s]) p->has_empty_segment = true;
-  CK(dev_alloc(&p->chunks, planB.size())); CK(dev_alloc(&p->chunks_full, planA.size()));
-  CK(dev_alloc(&p->warp_off, woffB.size())); CK(dev_alloc(&p->warp_off_full, woffA.size()));
-  if (!planB.empty()) CK(cudaMemcpyAsync(p->chunks, planB.data(), planB.size() * sizeof(ChunkDesc), cudaMemcpyHostToDevice, ctx->stream));
-  if (!planA.empty()) CK(cudaMemcpyAsync(p->chunks_full, planA.data(), planA.size() * sizeof(ChunkDesc), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(p->warp_off, woffB.data(), woffB.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(p->warp_off_full, woffA.data(), woffA.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  p->n_warps = W; p->n_tiles = T;
+  p->n_chunks = sch.woffB[W]; p->n_chunks_full = sch.woffA[W];
+  p->tile_duos = sch.tile_duos;
+  for (uint32_t s = 0; s < S; ++s) if (p->h_seg_off[s + 1] == p->h_seg_off[s]) p->has_empty_segment = true;
   // the fused single-map association wrote its records in duo order: valid when the schedule streams the tiles in that order
-  if (records_ready && tile_rec_begin != tile_duo_begin) {
+  if (records_ready && !std::equal(sch.tile_duo_begin.begin(), sch.tile_duo_begin.end(), sch.tile_rec_begin.begin())) {
     records_ready = false;
     dev_free(p->duo_recs); dev_free(p->duo_p0); dev_free(p->duo_overflow);
     p->duo_recs = nullptr; p->duo_p0 = nullptr; p->duo_overflow = nullptr;
   }
+  // segments the persistent solver (K7) takes: short enough for one warp
+  uint32_t n_items = 0;
+  for (uint32_t s = 0; s < S; ++s) if (p->h_duo_off[s + 1] - p->h_duo_off[s] <= kSolveMaxDuos) ++n_items;
+  p->n_solve_items = n_items; p->solve_all = n_items == S;
+  // ---- one staging block, one upload ----
+  const size_t o_tseg = 0, o_first = o_tseg + T, o_mine = o_first + S + 1, o_moff = o_mine + T, o_wrb = o_moff + W + 1, o_woffA = o_wrb + W,
+               o_woffB = o_woffA + W + 1, o_trb = o_woffB + W + 1, o_tdb = o_trb + T + 1, o_rot = o_tdb + T, o_soff = o_rot + T, o_doff = o_soff + S + 1,
+               o_items = o_doff + S + 1, words = o_items + (p->solve_all ? 0 : n_items);
+  if (ctx->stage_busy) { CK(cudaEventSynchronize(ctx->stage_ev)); ctx->stage_busy = false; }
+  if (int rc = pinned_reserve(ctx, &ctx->h_stage, &ctx->stage_cap, words)) return rc;
+  if (!ctx->stage_ev) CK(cudaEventCreateWithFlags(&ctx->stage_ev, cudaEventDisableTiming));
+  uint32_t* h = ctx->h_stage;
+  for (uint32_t t = 0; t < T; ++t) h[o_tseg + t] = sch.tiles[t].seg;
+  auto put = [&](size_t off, const std::vector<uint32_t>& v) { if (!v.empty()) memcpy(h + off, v.data(), v.size() * sizeof(uint32_t)); };
+  put(o_first, sch.first); put(o_mine, sch.mine); put(o_moff, sch.mine_off); put(o_wrb, sch.warp_rec_begin); put(o_woffA, sch.woffA); put(o_woffB, sch.woffB);
+  put(o_trb, sch.tile_rec_begin); put(o_tdb, sch.tile_duo_begin); put(o_rot, sch.rec_of_tile); put(o_soff, p->h_seg_off); put(o_doff, p->h_duo_off);
+  if (!p->solve_all) { uint32_t i = 0; for (uint32_t s = 0; s < S; ++s) if (p->h_duo_off[s + 1] - p->h_duo_off[s] <= kSolveMaxDuos) h[o_items + i++] = s; }
+  CK(dev_alloc(&p->sched_blob, words));
+  CK(cudaMemcpyAsync(p->sched_blob, h, words * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaEventRecord(ctx->stage_ev, ctx->stream)); ctx->stage_busy = true;
+  uint32_t* d = p->sched_blob;
+  p->seg_first_tile = d + o_first; p->warp_off_full = d + o_woffA; p->warp_off = d + o_woffB; p->rec_of_tile = d + o_rot; p->seg_off = d + o_soff;
+  p->seg_duo_off = d + o_doff; p->solve_items = p->solve_all ? nullptr : d + o_items;
+  int nl = 0;
+  CK(dev_alloc(&p->chunks, p->n_chunks)); CK(dev_alloc(&p->chunks_full, p->n_chunks_full));
+  CK(launch_emit_chunks(d + o_tseg, d + o_first, d + o_doff, sch.tile_duos, d + o_mine, d + o_moff, d + o_wrb, d + o_woffA, d + o_woffB, W, p->chunks_full, p->chunks,
+                        ctx->stream, &nl));
+  lap("upload + chunks");
   // record-major duo table in schedule order (what K3 streams)
   if (!records_ready) {
-    int nl = 0;
-    uint32_t *d_trb = nullptr, *d_tdb = nullptr; Duo* d_stream = nullptr;
-    cudaError_t e = dev_alloc(&d_trb, tile_rec_begin.size());
-    if (e == cudaSuccess) e = dev_alloc(&d_tdb, tile_duo_begin.size());
-    if (e == cudaSuccess) e = dev_alloc(&d_stream, p->n_duos);
-    if (e == cudaSuccess) e = dev_alloc(&p->duo_recs, p->n_duos);
-    if (e == cudaSuccess) e = dev_alloc(&p->duo_p0, p->n_duos);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_trb, tile_rec_begin.data(), tile_rec_begin.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess && !tile_duo_begin.empty())
-      e = cudaMemcpyAsync(d_tdb, tile_duo_begin.data(), tile_duo_begin.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = launch_permute_duos(p->duos, d_trb, d_tdb, (uint32_t)tiles.size(), p->n_duos, d_stream, ctx->stream, &nl);
     // compact records; the few duos that do not fit go to an overflow table sized by a first guess and, if that was too small, rebuilt
     uint32_t* d_novf = nullptr; uint32_t h_novf = 0, ovf_cap = std::max<uint32_t>(64u, p->n_duos / 512u);
+    cudaError_t e = dev_alloc(&p->duo_recs, p->n_duos);
+    if (e == cudaSuccess) e = dev_alloc(&p->duo_p0, p->n_duos);
     if (e == cudaSuccess) e = dev_alloc(&d_novf, 1);
     for (int attempt = 0; attempt < 2 && e == cudaSuccess; ++attempt) {
       e = dev_alloc(&p->duo_overflow, ovf_cap);
       if (e == cudaSuccess) e = cudaMemsetAsync(d_novf, 0, sizeof(uint32_t), ctx->stream);
-      if (e == cudaSuccess) e = launch_build_duo_records(p->cells_m, p->cells_f, d_stream, p->n_duos, p->duo_recs, p->duo_p0, p->duo_overflow, ovf_cap, d_novf, ctx->stream, &nl);
+      if (e == cudaSuccess) e = launch_build_duo_records(p->cells_m, p->cells_f, p->duos, p->n_duos, d + o_trb, d + o_tdb, T, p->duo_recs, p->duo_p0, p->duo_overflow,
+                                                         ovf_cap, d_novf, ctx->stream, &nl);
       if (e == cudaSuccess) e = cudaMemcpyAsync(&h_novf, d_novf, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
       if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
       if (e != cudaSuccess || h_novf <= ovf_cap) break;
@@ -241,35 +274,16 @@ int finish_problem(randt_ctx* ctx, randt_problem* p, bool records_ready = false)
     }
     p->n_overflow = h_novf;
     dev_free(d_novf);
-    lap("uploads + records");
-    dev_free(d_trb); dev_free(d_tdb); dev_free(d_stream);
+    lap("records");
     if (e != cudaSuccess) return fail(ctx, RANDT_E_CUDA, "finish_problem: record table", e);
-    ctx->launches += nl;
   }
-  CK(dev_alloc(&p->seg_first_tile, first.size()));
-  CK(dev_alloc(&p->seg_off, p->h_seg_off.size()));
-  CK(dev_alloc(&p->partials, (size_t)tiles.size() * kMaxAcc));
-  CK(dev_alloc(&p->seg_counters, p->S));
-  CK(dev_alloc(&p->d_poses, (size_t)p->S * 4));
-  CK(dev_alloc(&p->d_out, (size_t)p->S * RANDT_FUSED_STRIDE));
-  CK(dev_alloc(&p->d_mu, p->S));
-  // persistent solver (K7): every tile's record offset by tile id, the duo offsets, and the list of segments one warp can take
-  p->tile_duos = sch.tile_duos;
-  std::vector<uint32_t> items;
-  for (uint32_t s = 0; s < p->S; ++s) if (p->h_duo_off[s + 1] - p->h_duo_off[s] <= kSolveMaxDuos) items.push_back(s);
-  p->n_solve_items = (uint32_t)items.size(); p->solve_all = items.size() == p->S;
-  CK(dev_alloc(&p->seg_duo_off, p->h_duo_off.size())); CK(dev_alloc(&p->rec_of_tile, sch.rec_of_tile.size())); CK(dev_alloc(&p->solve_counter, 1));
-  CK(cudaMemcpyAsync(p->seg_duo_off, p->h_duo_off.data(), p->h_duo_off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-  if (!sch.rec_of_tile.empty()) CK(cudaMemcpyAsync(p->rec_of_tile, sch.rec_of_tile.data(), sch.rec_of_tile.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-  if (!p->solve_all) {
-    CK(dev_alloc(&p->solve_items, items.size()));
-    if (!items.empty()) CK(cudaMemcpyAsync(p->solve_items, items.data(), items.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-  }
-  CK(cudaMemcpyAsync(p->seg_first_tile, first.data(), first.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(p->seg_off, p->h_seg_off.data(), p->h_seg_off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemsetAsync(p->seg_counters, 0, std::max<size_t>(1, p->S) * sizeof(uint32_t), ctx->stream));
-  // (the uploads above come from pageable vectors: cudaMemcpyAsync has staged them before it returned, so nothing here has to wait)
-  if (!records_ready) CK(cudaStreamSynchronize(ctx->stream));   // surfaces an error of the record kernels in this call
+  ctx->launches += nl;
+  // ---- work arrays of the evaluation / solver entry points: one allocation ----
+  const size_t n_part = (size_t)T * kMaxAcc, n_dbl = n_part + (size_t)S * 4 + (size_t)S * RANDT_FUSED_STRIDE + S, n_cnt = (size_t)S + 2;
+  CK(dev_alloc(&p->work_blob, n_dbl + (n_cnt + 1) / 2));
+  p->partials = p->work_blob; p->d_poses = p->partials + n_part; p->d_out = p->d_poses + (size_t)S * 4; p->d_mu = p->d_out + (size_t)S * RANDT_FUSED_STRIDE;
+  p->seg_counters = reinterpret_cast<uint32_t*>(p->d_mu + S); p->solve_counter = p->seg_counters + S;
+  CK(cudaMemsetAsync(p->seg_counters, 0, n_cnt * sizeof(uint32_t), ctx->stream));
   lap("tail");
   return RANDT_OK;
 }
@@ -350,6 +364,10 @@ void randt_ctx_destroy(randt_ctx* ctx) {
   if (ctx->sref && ctx->sref->copy) cudaStreamSynchronize(ctx->sref->copy);           // async evaluations still uploading / delivering
   if (ctx->sref && ctx->sref->copy_out) cudaStreamSynchronize(ctx->sref->copy_out);
   dev_free(ctx->d_bad);
+  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+  if (ctx->h_offs) cudaFreeHost(ctx->h_offs);
+  if (ctx->stage_ev) cudaEventDestroy(ctx->stage_ev);
+  if (ctx->offs_ev) cudaEventDestroy(ctx->offs_ev);
   delete ctx;      // the stream itself goes with the last object that was created on this context (StreamRef)
 }
 
@@ -806,11 +824,16 @@ int randt_associate(randt_ctx* ctx, const randt_map* F, const randt_map* M, cons
   CKA(dev_alloc(&d_cnt2, n_m)); CKA(dev_alloc(&d_scan2, (size_t)n_m + 1));
   CKA(launch_duo_counts(d_cnt, n_m, d_cnt2, ctx->stream, &nl));
   CKA(launch_exclusive_scan_u32(d_cnt2, d_scan2, n_m, d_bs, ctx->stream, &nl));
-  // The host only needs the B+1 per-map offsets of both scans: gather them on the device and read them back once, after everything
-  // else of this call has been queued.  The pair / duo tables are sized by their bounds (k and ceil(k/2) per moving cell; nearly
-  // every cell finds its k neighbours), so no size has to come back before the compaction kernels run.
+  // The host only needs the B+1 per-map offsets of both scans: gather them on the device and start their copy into pinned memory
+  // now; the compaction kernels and the snapshots are queued behind it, and the host waits for the offsets only (it then builds the
+  // schedule while the device is still compacting).  The pair / duo tables are sized by their bounds (k and ceil(k/2) per moving
+  // cell; nearly every cell finds its k neighbours), so no size has to come back before the compaction kernels run.
   CKA(dev_alloc(&d_offs, 2 * ((size_t)B + 1)));
   CKA(launch_gather_offsets(d_scan, d_scan2, M->cell_off, B + 1, d_offs, ctx->stream, &nl));
+  if (pinned_reserve(ctx, &ctx->h_offs, &ctx->offs_cap, 2 * ((size_t)B + 1)) != RANDT_OK) { cleanup(); free_problem(p); return RANDT_E_NOMEM; }
+  if (!ctx->offs_ev) CKA(cudaEventCreateWithFlags(&ctx->offs_ev, cudaEventDisableTiming));
+  CKA(cudaMemcpyAsync(ctx->h_offs, d_offs, 2 * ((size_t)B + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CKA(cudaEventRecord(ctx->offs_ev, ctx->stream));
   CKA(dev_alloc(&p->pairs, (size_t)n_m * k));
   CKA(launch_compact_pairs(d_nn, d_cnt, d_scan, M->cell_off, F->cell_off, B, n_m, M->max_per_map, k, p->pairs, ctx->stream, &nl));
   CKA(dev_alloc(&p->duos, (size_t)n_m * ((k + 1) / 2)));
@@ -819,13 +842,11 @@ int randt_associate(randt_ctx* ctx, const randt_map* F, const randt_map* M, cons
   CKA(dev_alloc(&p->cells_m, (size_t)n_m * 3)); CKA(dev_alloc(&p->cells_f, (size_t)F->n_cells * 3));
   if (n_m) CKA(cudaMemcpyAsync(p->cells_m, M->cells, (size_t)n_m * 48, cudaMemcpyDeviceToDevice, ctx->stream));
   if (F->n_cells) CKA(cudaMemcpyAsync(p->cells_f, F->cells, (size_t)F->n_cells * 48, cudaMemcpyDeviceToDevice, ctx->stream));
-  std::vector<uint32_t> h_offs(2 * ((size_t)B + 1));
-  CKA(cudaMemcpyAsync(h_offs.data(), d_offs, h_offs.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
   lap("queued");
-  CKA(cudaStreamSynchronize(ctx->stream));
-  lap("device done");
-  p->h_seg_off.assign(h_offs.begin(), h_offs.begin() + B + 1);
-  p->h_duo_off.assign(h_offs.begin() + B + 1, h_offs.end());
+  CKA(cudaEventSynchronize(ctx->offs_ev));
+  lap("offsets back");
+  p->h_seg_off.assign(ctx->h_offs, ctx->h_offs + B + 1);
+  p->h_duo_off.assign(ctx->h_offs + B + 1, ctx->h_offs + 2 * ((size_t)B + 1));
   p->P = p->h_seg_off[B]; p->n_duos = p->h_duo_off[B];
 #undef CKA
   cleanup();
@@ -889,6 +910,23 @@ int randt_problem_info(const randt_problem* p, uint32_t* n_segments, uint32_t* n
   if (n_pairs) *n_pairs = p->P;
   if (n_m) *n_m = p->n_m;
   if (n_f) *n_f = p->n_f;
+  return RANDT_OK;
+}
+
+int randt_problem_schedule(randt_ctx* ctx, const randt_problem* p, uint32_t* counts, uint32_t* plan_a4, uint32_t* plan_b4, uint32_t cap_chunks, uint32_t* woff_a,
+                           uint32_t* woff_b, uint32_t cap_warps, uint32_t* duo_off) {
+  if (!ctx || !p || !counts) return fail(ctx, RANDT_E_INVALID, "randt_problem_schedule: null argument");
+  counts[0] = p->n_warps; counts[1] = p->n_tiles; counts[2] = p->n_chunks_full; counts[3] = p->n_chunks; counts[4] = (uint32_t)kK3MaxWarps;
+  if (((plan_a4 || plan_b4) && (p->n_chunks_full > cap_chunks || p->n_chunks > cap_chunks)) || ((woff_a || woff_b) && p->n_warps > cap_warps))
+    return fail(ctx, RANDT_E_CAPACITY, "randt_problem_schedule: output arrays too small");
+  CK(cudaSetDevice(ctx->device));
+  static_assert(sizeof(ChunkDesc) == 16, "4 x uint32 records");
+  if (plan_a4 && p->n_chunks_full) CK(cudaMemcpyAsync(plan_a4, p->chunks_full, (size_t)p->n_chunks_full * 16, cudaMemcpyDeviceToHost, ctx->stream));
+  if (plan_b4 && p->n_chunks) CK(cudaMemcpyAsync(plan_b4, p->chunks, (size_t)p->n_chunks * 16, cudaMemcpyDeviceToHost, ctx->stream));
+  if (woff_a) CK(cudaMemcpyAsync(woff_a, p->warp_off_full, ((size_t)p->n_warps + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (woff_b) CK(cudaMemcpyAsync(woff_b, p->warp_off, ((size_t)p->n_warps + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (duo_off) memcpy(duo_off, p->h_duo_off.data(), p->h_duo_off.size() * sizeof(uint32_t));
   return RANDT_OK;
 }
 

@@ -82,9 +82,14 @@ cudaError_t launch_permute_duos(const Duo* in, const uint32_t* tile_rec_begin, c
                                 Duo* out, cudaStream_t s, int* n_launches);
 // d_n_overflow: device counter (zeroed by the caller) of the duos that needed a full record; records beyond overflow_cap are dropped
 // (the caller re-runs with a larger table when the count exceeds the capacity)
-cudaError_t launch_build_duo_records(const float4* cells_m, const float4* cells_f, const Duo* duos, uint32_t n_duos, DuoRec* recs,
-                                     uint32_t* duo_p0, DuoRecFull* overflow, uint32_t overflow_cap, uint32_t* d_n_overflow, cudaStream_t s,
-                                     int* n_launches);
+// (tile_rec_begin / tile_duo_begin / n_tiles: the schedule-order permutation of the duos, or NULL: records in duo order)
+cudaError_t launch_build_duo_records(const float4* cells_m, const float4* cells_f, const Duo* duos, uint32_t n_duos, const uint32_t* tile_rec_begin,
+                                     const uint32_t* tile_duo_begin, uint32_t n_tiles, DuoRec* recs, uint32_t* duo_p0, DuoRecFull* overflow,
+                                     uint32_t overflow_cap, uint32_t* d_n_overflow, cudaStream_t s, int* n_launches);
+// the chunk lists of both plans from the tile assignment (schedule.hpp walk_warp, one thread per warp of the schedule)
+cudaError_t launch_emit_chunks(const uint32_t* tile_seg, const uint32_t* first, const uint32_t* duo_off, uint32_t tile_duos, const uint32_t* mine,
+                               const uint32_t* mine_off, const uint32_t* warp_rec_begin, const uint32_t* woffA, const uint32_t* woffB, uint32_t n_warps,
+                               ChunkDesc* planA, ChunkDesc* planB, cudaStream_t s, int* n_launches);
 cudaError_t launch_sweep_costs(const DeviceProblem& p, uint32_t pair_begin, uint32_t pair_end, int variant, const double* d_poses,
                                uint32_t n_poses, const LossParams& lp, double* d_cost, cudaStream_t s, int* n_launches);
 

@@ -303,12 +303,21 @@ __global__ void __launch_bounds__(kSweepThreads) k3_sweep_kernel(DeviceProblem P
 // p0 + 1] as 3 x 9 floats + the code word, 112 B, so that the 32 duos of a chunk are one contiguous 3584-byte block that a single bulk
 // copy lands.  One thread per duo; a duo whose couples do not fit the encoding goes to the overflow table as stored.
 __global__ void __launch_bounds__(128) build_duo_records_kernel(const float4* __restrict__ cells_m, const float4* __restrict__ cells_f,
-                                                                const Duo* __restrict__ duos, uint32_t n_duos, DuoRec* __restrict__ recs,
+                                                                const Duo* __restrict__ duos, uint32_t n_duos, const uint32_t* __restrict__ tile_rec_begin,
+                                                                const uint32_t* __restrict__ tile_duo_begin, uint32_t n_tiles, DuoRec* __restrict__ recs,
                                                                 uint32_t* __restrict__ duo_p0, DuoRecFull* __restrict__ overflow, uint32_t overflow_cap,
                                                                 uint32_t* __restrict__ n_overflow) {
   const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= n_duos) return;
-  const Duo du = duos[d];
+  // record d belongs to the tile t with tile_rec_begin[t] <= d < tile_rec_begin[t + 1] (tiles in the order the warps walk them) and
+  // is that tile's (d - tile_rec_begin[t])-th duo; without a tile table the records are in duo order
+  uint32_t src = d;
+  if (tile_rec_begin) {
+    uint32_t lo = 0, hi = n_tiles;          // largest t with tile_rec_begin[t] <= d
+    while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (tile_rec_begin[mid] <= d) lo = mid; else hi = mid; }
+    src = tile_duo_begin[lo] + (d - tile_rec_begin[lo]);
+  }
+  const Duo du = duos[src];
   const bool two = du.jf1 != kNoCell;
   RawCell c[3];
   c[0].a = __ldg(cells_m + 3 * (size_t)du.im); c[0].b = __ldg(cells_m + 3 * (size_t)du.im + 1); c[0].c = __ldg(cells_m + 3 * (size_t)du.im + 2);
@@ -317,6 +326,21 @@ __global__ void __launch_bounds__(128) build_duo_records_kernel(const float4* __
   if (two) { c[2].a = __ldg(cells_f + 3 * (size_t)du.jf1); c[2].b = __ldg(cells_f + 3 * (size_t)du.jf1 + 1); c[2].c = __ldg(cells_f + 3 * (size_t)du.jf1 + 2); }
   encode_duo_record(c, two, recs + d, overflow, overflow_cap, n_overflow);
   duo_p0[d] = du.p0;
+}
+
+// the chunk lists of the two plans, one thread per warp of the schedule (schedule.hpp walk_warp: the host only computed the assignment)
+__global__ void __launch_bounds__(128) emit_chunks_kernel(const uint32_t* __restrict__ tile_seg, const uint32_t* __restrict__ first,
+                                                          const uint32_t* __restrict__ duo_off, uint32_t tile_duos, const uint32_t* __restrict__ mine,
+                                                          const uint32_t* __restrict__ mine_off, const uint32_t* __restrict__ warp_rec_begin,
+                                                          const uint32_t* __restrict__ woffA, const uint32_t* __restrict__ woffB, uint32_t n_warps,
+                                                          ChunkDesc* __restrict__ planA, ChunkDesc* __restrict__ planB) {
+  const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n_warps) return;
+  ChunkDesc* a = planA + woffA[w];
+  ChunkDesc* b = planB + woffB[w];
+  uint32_t nA = 0, nB = 0;
+  walk_warp([=](uint32_t t) { return tile_from_seg(t, tile_seg[t], first, duo_off, tile_duos); }, first, mine, mine_off[w], mine_off[w + 1], warp_rec_begin[w],
+            [a](uint32_t i, const ChunkDesc& c) { a[i] = c; }, [b](uint32_t i, const ChunkDesc& c) { b[i] = c; }, [](uint32_t, uint32_t, uint32_t) {}, &nA, &nB);
 }
 
 int loss_code(const LossParams& lp) {
@@ -413,11 +437,21 @@ cudaError_t launch_permute_duos(const Duo* in, const uint32_t* tile_rec_begin, c
   return cudaGetLastError();
 }
 
-cudaError_t launch_build_duo_records(const float4* cells_m, const float4* cells_f, const Duo* duos, uint32_t n_duos, DuoRec* recs,
-                                     uint32_t* duo_p0, DuoRecFull* overflow, uint32_t overflow_cap, uint32_t* d_n_overflow, cudaStream_t s,
-                                     int* n_launches) {
+cudaError_t launch_build_duo_records(const float4* cells_m, const float4* cells_f, const Duo* duos, uint32_t n_duos, const uint32_t* tile_rec_begin,
+                                     const uint32_t* tile_duo_begin, uint32_t n_tiles, DuoRec* recs, uint32_t* duo_p0, DuoRecFull* overflow,
+                                     uint32_t overflow_cap, uint32_t* d_n_overflow, cudaStream_t s, int* n_launches) {
   if (n_duos == 0) return cudaSuccess;
-  build_duo_records_kernel<<<(n_duos + 127u) / 128u, 128, 0, s>>>(cells_m, cells_f, duos, n_duos, recs, duo_p0, overflow, overflow_cap, d_n_overflow);
+  build_duo_records_kernel<<<(n_duos + 127u) / 128u, 128, 0, s>>>(cells_m, cells_f, duos, n_duos, tile_rec_begin, tile_duo_begin, n_tiles, recs, duo_p0, overflow,
+                                                                  overflow_cap, d_n_overflow);
+  if (n_launches) *n_launches += 1;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_emit_chunks(const uint32_t* tile_seg, const uint32_t* first, const uint32_t* duo_off, uint32_t tile_duos, const uint32_t* mine,
+                               const uint32_t* mine_off, const uint32_t* warp_rec_begin, const uint32_t* woffA, const uint32_t* woffB, uint32_t n_warps,
+                               ChunkDesc* planA, ChunkDesc* planB, cudaStream_t s, int* n_launches) {
+  if (n_warps == 0) return cudaSuccess;
+  emit_chunks_kernel<<<(n_warps + 127u) / 128u, 128, 0, s>>>(tile_seg, first, duo_off, tile_duos, mine, mine_off, warp_rec_begin, woffA, woffB, n_warps, planA, planB);
   if (n_launches) *n_launches += 1;
   return cudaGetLastError();
 }

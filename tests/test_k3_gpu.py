@@ -336,3 +336,34 @@ def test_compact_records_hold_asymmetric_cells_and_overflow(oracle, gpu_ctx):
         assert abs(out["cost"][s] - fo["cost"]) < TOL * abs(fo["cost"])
         assert H.rel_err(out["H"][s], fo["H"]) < 1e-8 and H.rel_err(out["g"][s], fo["g"]) < 1e-8
     assert gpu_ctx.take_bad_pairs() == 0
+
+
+@pytest.mark.parametrize("shape", ["ragged", "bench-like", "few long", "one"])
+def test_device_built_schedule_equals_the_host_builder(oracle, gpu_ctx, shape):
+    """The host computes the tile assignment only; the chunk lists of both plans are written by a kernel running the same walk
+    (schedule.hpp walk_warp).  They must be the lists the all-host builder (which tests/test_schedule_cpu.py checks on the CPU) makes."""
+    from randt_slam_b200 import hostapi
+    rng = np.random.default_rng(5)
+    if shape == "ragged":
+        sizes = [1, 2, 31, 32, 33, 5, 63, 64, 65, 1, 1, 1, 40, 0, 255, 256, 257, 3, 600, 17, 96, 0, 700, 29, 30, 31, 32, 33, 34, 7]
+    elif shape == "bench-like":
+        sizes = list(rng.integers(60, 130, 3000))
+    elif shape == "few long":
+        sizes = list(rng.integers(2000, 9000, 12))
+    else:
+        sizes = [180]
+    k = 2
+    n_m = int(sum(sizes))
+    cm = H.random_cells(rng, max(n_m, 1), extent=6.0); cf = H.random_cells(rng, 64, extent=6.0)
+    im = np.repeat(np.arange(n_m, dtype=np.uint32), k)          # every moving cell once, with k neighbours: one duo each
+    jf = rng.integers(0, 64, n_m * k).astype(np.uint32)
+    seg = np.concatenate([[0], np.cumsum(np.asarray(sizes, np.int64) * k)]).astype(np.uint32)
+    prob = gpu_ctx.problem_create(cm, cf, im, jf, seg)
+    dev = prob.schedule()
+    assert list(np.diff(dev["duo_off"])) == list(sizes)
+    host = hostapi.build_schedule(dev["duo_off"], dev["warp_budget"])
+    assert dev["n_warps"] == host["n_warps"] and dev["n_tiles"] == len(host["tiles"])
+    assert np.array_equal(dev["woff_a"], host["woff_a"]) and np.array_equal(dev["woff_b"], host["woff_b"])
+    assert np.array_equal(dev["plan_a"], host["plan_a"])
+    assert np.array_equal(dev["plan_b"], host["plan_b"])
+    prob.close()
