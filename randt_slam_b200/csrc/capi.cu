@@ -433,8 +433,17 @@ int randt_voxelize(randt_ctx* ctx, const float* pts4, const uint32_t* scan_off, 
     dev_free(d_cells_p); dev_free(d_status);
   };
 #define CKV(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rc = fail(ctx, RANDT_E_CUDA, #call, e__); cleanup(); free_map(m); return rc; } } while (0)
+  static const bool trace = getenv("RANDT_DEBUG_TIMING") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!trace) return;
+    auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "[randt] voxelize %-18s %8.1f us\n", what, std::chrono::duration<double, std::micro>(t - t_prev).count());
+    t_prev = t;
+  };
   if (pts_on_device) d_pts = const_cast<float4*>(reinterpret_cast<const float4*>(pts4));
   else { CKV(dev_alloc(&d_pts, n_pts)); own_pts = true; if (n_pts) CKV(cudaMemcpyAsync(d_pts, pts4, (size_t)n_pts * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream)); }
+  lap("points h2d");
   CKV(dev_alloc(&d_scan_off, B + 1));
   CKV(cudaMemcpyAsync(d_scan_off, scan_off, (size_t)(B + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
   CKV(dev_alloc(&d_cnt, B));
@@ -443,10 +452,12 @@ int randt_voxelize(randt_ctx* ctx, const float* pts4, const uint32_t* scan_off, 
   CKV(dev_alloc(&m->slot, (size_t)B * m->geom.n_slots));
   int nl = 0;
   CKV(launch_voxelize(d_pts, d_scan_off, B, max_pts, *gp, m->geom, cell_cap, d_cells_p, d_npts_p, d_labels_p, d_cnt, m->slot, d_status, ctx->stream, &nl));
+  lap("queued");
   std::vector<uint32_t> h_cnt(B); std::vector<int> h_status(B);
   if (B) { CKV(cudaMemcpyAsync(h_cnt.data(), d_cnt, B * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
            CKV(cudaMemcpyAsync(h_status.data(), d_status, B * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream)); }
   CKV(cudaStreamSynchronize(ctx->stream));
+  lap("counts back");
   for (uint32_t b = 0; b < B; ++b) {
     if (h_status[b] == VOX_SPAN || h_status[b] == VOX_CELL_CAP) {
       cleanup(); free_map(m);
@@ -701,10 +712,16 @@ int randt_map_merge(randt_ctx* ctx, randt_map* F, const randt_map* M) {
   CKG(cudaStreamSynchronize(ctx->stream));
   std::vector<uint32_t> new_off(B + 1, 0); uint32_t max_per = 0;
   for (uint32_t b = 0; b < B; ++b) { new_off[b + 1] = new_off[b] + h_cnt[b]; max_per = std::max(max_per, h_cnt[b]); }
-  CKG(dev_alloc(&n_cells, (size_t)new_off[B] * 3)); CKG(dev_alloc(&n_npts, new_off[B])); CKG(dev_alloc(&n_off, B + 1));
+  CKG(dev_alloc(&n_off, B + 1));
   CKG(cudaMemcpyAsync(n_off, new_off.data(), (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
-  CKG(launch_compact_cells(o_cells, o_npts, nullptr, n_off, B, cap, max_per, n_cells, n_npts, nullptr, ctx->stream, &nl));
-  CKG(cudaStreamSynchronize(ctx->stream));
+  if (B == 1) {
+    // a single map's padded region already is its compact table: hand the buffers over (the keyframe insertion of a live stream)
+    n_cells = o_cells; n_npts = o_npts; o_cells = nullptr; o_npts = nullptr;
+  } else {
+    CKG(dev_alloc(&n_cells, (size_t)new_off[B] * 3)); CKG(dev_alloc(&n_npts, new_off[B]));
+    CKG(launch_compact_cells(o_cells, o_npts, nullptr, n_off, B, cap, max_per, n_cells, n_npts, nullptr, ctx->stream, &nl));
+    // (no wait: the padded buffers are released in stream order, and every later use of the map is queued on the same stream)
+  }
 #undef CKG
   cleanup();
   dev_free(F->cells); dev_free(F->npts); dev_free(F->cell_off); dev_free(F->labels);

@@ -2,6 +2,7 @@
 Prints the trajectory error against the ground truth of this run and saves the poses so two runs can be compared step by step."""
 import os, sys
 import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from randt_slam_b200 import capi, params as P, workloads as W
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 8609

@@ -49,6 +49,23 @@ def test_literal_256_batch_identical_for_1_2_4_8_ranks(gpu_ctx, batch):
     assert hashlib.sha256(t1[:, :7].tobytes()).hexdigest() == hashlib.sha256(tw[:, :7].tobytes()).hexdigest()
 
 
+def test_team_and_one_warp_solver_modes_give_identical_bits(gpu_ctx):
+    """Small batches are solved in team mode (a CTA of four warps shares one registration: three prepare pair terms, warp 0 adds them in
+    the one-warp kernel's order), larger ones with one warp per registration.  A 600-registration batch solved in one call (one-warp
+    mode) and in blocks of 150 (team mode) must give the same table, bit for bit."""
+    big = W.literal_batch(P.OXFORD, n=600, seed=41, scenes=16)
+    one = np.zeros((600, shard.ROW)); team = np.zeros((600, shard.ROW))
+    rows, _ = W.solve_literal_block(gpu_ctx, capi, big, 0, 600)
+    one[:] = rows
+    for begin in range(0, 600, 150):
+        rows, _ = W.solve_literal_block(gpu_ctx, capi, big, begin, begin + 150)
+        team[begin:begin + 150] = rows
+    assert np.array_equal(one[:, :7].view(np.uint64), team[:, :7].view(np.uint64))
+    # a lone registration (the per-scan call) as well
+    rows, _ = W.solve_literal_block(gpu_ctx, capi, big, 77, 78)
+    assert np.array_equal(rows[0, :7].view(np.uint64), one[77, :7].view(np.uint64))
+
+
 def test_literal_batch_matches_oracle(oracle, gpu_ctx, batch):
     """a sample of the batch against the CPU restatement of estimateLoopConstraint on the pair lists the device built.  Raw ambient pose
     block: at ceres' default function_tolerance two implementations may stop an iteration apart, so the comparison is made
