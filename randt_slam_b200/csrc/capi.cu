@@ -430,7 +430,7 @@ int randt_voxelize(randt_ctx* ctx, const float* pts4, const uint32_t* scan_off, 
   auto cleanup = [&]() {
     if (own_pts) dev_free(d_pts);
     dev_free(d_scan_off); dev_free(d_cnt); dev_free(d_npts_p); dev_free(d_labels_p);
-    dev_free(d_cells_p); dev_free(d_status);
+    dev_free(d_cells_p);
   };
 #define CKV(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rc = fail(ctx, RANDT_E_CUDA, #call, e__); cleanup(); free_map(m); return rc; } } while (0)
   static const bool trace = getenv("RANDT_DEBUG_TIMING") != nullptr;
@@ -446,17 +446,17 @@ int randt_voxelize(randt_ctx* ctx, const float* pts4, const uint32_t* scan_off, 
   lap("points h2d");
   CKV(dev_alloc(&d_scan_off, B + 1));
   CKV(cudaMemcpyAsync(d_scan_off, scan_off, (size_t)(B + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-  CKV(dev_alloc(&d_cnt, B));
+  CKV(dev_alloc(&d_cnt, 2 * (size_t)B)); d_status = reinterpret_cast<int*>(d_cnt + B);   // counts | status codes
   CKV(dev_alloc(&d_cells_p, (size_t)B * cell_cap * 3)); CKV(dev_alloc(&d_npts_p, (size_t)B * cell_cap)); CKV(dev_alloc(&d_labels_p, (size_t)B * cell_cap));
-  CKV(dev_alloc(&d_status, B));
   CKV(dev_alloc(&m->slot, (size_t)B * m->geom.n_slots));
   int nl = 0;
   CKV(launch_voxelize(d_pts, d_scan_off, B, max_pts, *gp, m->geom, cell_cap, d_cells_p, d_npts_p, d_labels_p, d_cnt, m->slot, d_status, ctx->stream, &nl));
   lap("queued");
-  std::vector<uint32_t> h_cnt(B); std::vector<int> h_status(B);
-  if (B) { CKV(cudaMemcpyAsync(h_cnt.data(), d_cnt, B * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-           CKV(cudaMemcpyAsync(h_status.data(), d_status, B * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream)); }
+  // counts and status codes sit side by side and come back in one copy into the context's pinned block
+  if (pinned_reserve(ctx, &ctx->h_offs, &ctx->offs_cap, 2 * (size_t)B + 2) != RANDT_OK) { cleanup(); free_map(m); return RANDT_E_NOMEM; }
+  if (B) CKV(cudaMemcpyAsync(ctx->h_offs, d_cnt, 2 * (size_t)B * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   CKV(cudaStreamSynchronize(ctx->stream));
+  const uint32_t* h_cnt = ctx->h_offs; const int* h_status = reinterpret_cast<const int*>(ctx->h_offs + B);
   lap("counts back");
   for (uint32_t b = 0; b < B; ++b) {
     if (h_status[b] == VOX_SPAN || h_status[b] == VOX_CELL_CAP) {
@@ -707,8 +707,9 @@ int randt_map_merge(randt_ctx* ctx, randt_map* F, const randt_map* M) {
   CKG(dev_alloc(&o_cells, (size_t)B * cap * 3)); CKG(dev_alloc(&o_npts, (size_t)B * cap)); CKG(dev_alloc(&o_cnt, B)); CKG(dev_alloc(&d_ooff, B + 1));
   CKG(cudaMemcpyAsync(d_ooff, h_ooff.data(), (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
   CKG(launch_merge_maps(F->cells, F->npts, F->cell_off, F->slot, M->cells, M->npts, M->cell_off, B, F->geom, d_ooff, o_cells, o_npts, o_cnt, M->max_per_map, ctx->stream, &nl));
-  std::vector<uint32_t> h_cnt(B);
-  if (B) CKG(cudaMemcpyAsync(h_cnt.data(), o_cnt, (size_t)B * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (pinned_reserve(ctx, &ctx->h_offs, &ctx->offs_cap, (size_t)B + 1) != RANDT_OK) { cleanup(); return RANDT_E_NOMEM; }
+  const uint32_t* h_cnt = ctx->h_offs;
+  if (B) CKG(cudaMemcpyAsync(ctx->h_offs, o_cnt, (size_t)B * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CKG(cudaStreamSynchronize(ctx->stream));
   std::vector<uint32_t> new_off(B + 1, 0); uint32_t max_per = 0;
   for (uint32_t b = 0; b < B; ++b) { new_off[b + 1] = new_off[b] + h_cnt[b]; max_per = std::max(max_per, h_cnt[b]); }
@@ -1427,7 +1428,9 @@ int scan_associate_solve(randt_ctx* ctx, const randt_map* F, const randt_map* M,
   DuoRec* d_recs = reinterpret_cast<DuoRec*>(blk + off_rec);
   DuoRecFull* d_ovf = reinterpret_cast<DuoRecFull*>(blk + off_ovf);
   int nl = 0;
-  struct { double pose[4]; double res[RANDT_REG_STRIDE]; uint32_t words[io_words]; } h;
+  struct Back { double pose[4]; double res[RANDT_REG_STRIDE]; uint32_t words[io_words]; };
+  if (int rc = pinned_reserve(ctx, &ctx->h_offs, &ctx->offs_cap, sizeof(Back) / sizeof(uint32_t))) { dev_free(blk); return rc; }
+  Back& h = *reinterpret_cast<Back*>(ctx->h_offs);
   cudaError_t e = cudaMemsetAsync(d_pose, 0, io_doubles * 8 + io_words * 4, ctx->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_pose, pose_io, 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = launch_associate_single(F->cells, F->n_cells, F->slot, M->cells, n_m, geom, d_pose, k, metric, nullptr, nullptr, d_recs, nullptr, d_ovf, ovf_cap,
@@ -1439,7 +1442,7 @@ int scan_associate_solve(randt_ctx* ctx, const randt_map* F, const randt_map* M,
     L.seg_duo_off = d_layout + 2; L.tile_rec_begin = d_layout + 5; L.tile_duos = kSolveMaxDuos; L.items = nullptr; L.n_items = 1; L.next_item = d_counter;
     e = launch_solve_persistent(v, L, 0, opt->use_manifold, lp, nullptr, *opt, d_pose, d_pose, d_res, ctx->d_bad, ctx->stream, &nl);
   }
-  if (e == cudaSuccess) e = cudaMemcpyAsync(&h, blk, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&h, blk, sizeof(Back), cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   dev_free(blk);
   if (e != cudaSuccess) return fail(ctx, RANDT_E_CUDA, "randt_scan_step (fused associate + solve)", e);

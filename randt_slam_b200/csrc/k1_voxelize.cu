@@ -169,13 +169,14 @@ __device__ void cell_stats_thread(const float* __restrict__ px, const float* __r
 //   cnt[bin]:   the bin's point count (two 16-bit counters to a word, added to as one 32-bit atomic: a scan has at most 16 384 points,
 //               so a counter cannot carry into its neighbour)
 //   start[bin]: where the (kept) bin's run starts in sx / sy / si;  until the sort, the labels (int32) live in the sx array
+//   (staged launches append float ox[pt_cap] oy[pt_cap] oi[pt_cap]: the scan in its original order)
 //   order[i]:   the kept cells by falling size class (so that the 32 cells a warp takes in phase 4 are about equally long)
 __global__ void __launch_bounds__(kVoxThreads) k1_voxelize_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ scan_off,
                                                                  int row, float label_res, int min_points, MapGeomDev geom,
                                                                  uint32_t span_cap, uint32_t cell_cap, float4* __restrict__ cells_out,
                                                                  uint32_t* __restrict__ npts_out, int32_t* __restrict__ labels_out,
                                                                  uint32_t* __restrict__ cell_count, int32_t* __restrict__ slot_out,
-                                                                 uint32_t pt_cap, int* __restrict__ status) {
+                                                                 uint32_t pt_cap, int staged, int* __restrict__ status) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* mask = reinterpret_cast<uint32_t*>(smem_raw);
   uint32_t* cnt2 = mask + span_cap;                                         // span_cap / 2 words
@@ -185,6 +186,11 @@ __global__ void __launch_bounds__(kVoxThreads) k1_voxelize_kernel(const float4* 
   float* si = sy + pt_cap;
   unsigned short* bins = reinterpret_cast<unsigned short*>(si + pt_cap);
   unsigned short* order = bins + pt_cap;
+  // staged (few scans, shared memory to spare): the scan itself also sits in shared memory, so the sort reads it at shared-memory
+  // latency instead of going back to L2 once per round
+  float* ox = reinterpret_cast<float*>(smem_raw + (((size_t)(reinterpret_cast<unsigned char*>(order + cell_cap) - smem_raw) + 15) & ~(size_t)15));
+  float* oy = ox + pt_cap;
+  float* oi = oy + pt_cap;
   int* labs = reinterpret_cast<int*>(sx);
   __shared__ uint32_t s_class[32], s_class_at[32];
   __shared__ unsigned long long warp_sums[32];
@@ -219,6 +225,7 @@ __global__ void __launch_bounds__(kVoxThreads) k1_voxelize_kernel(const float4* 
       if (e + u * n_thr < n) {
         const int lab = (int)(p[u].x / label_res) + row * (int)(p[u].y / label_res);   // C++ float->int conversion truncates toward zero
         labs[e + u * n_thr] = lab;
+        if (staged) { ox[e + u * n_thr] = p[u].x; oy[e + u * n_thr] = p[u].y; oi[e + u * n_thr] = p[u].w; }
         lmin = min(lmin, lab); lmax = max(lmax, lab);
       }
     }
@@ -318,7 +325,7 @@ __global__ void __launch_bounds__(kVoxThreads) k1_voxelize_kernel(const float4* 
           const uint32_t e = ((st + u) << 5) + (uint32_t)lane;
           hit[u] = (st + u) < s_end && e < n && bins[e] == (unsigned short)bin;
           bal[u] = __ballot_sync(0xffffffffu, hit[u]);
-          if (hit[u]) p[u] = __ldg(pts + p0 + e);
+          if (hit[u]) p[u] = staged ? make_float4(ox[e], oy[e], 0.f, oi[e]) : __ldg(pts + p0 + e);
         }
 #pragma unroll
         for (uint32_t u = 0; u < 4u; ++u) {
@@ -515,15 +522,17 @@ cudaError_t launch_voxelize(const float4* d_pts, const uint32_t* d_scan_off, uin
   if ((size_t)span_cap * 8 + fixed > smem_max) span_cap = (uint32_t)((smem_max - fixed) / 8 / 256 * 256);
   span_cap = std::min<uint32_t>(span_cap, 65280u);                     // bins are 16 bit (0xffff marks "no point")
   if (span_cap == 0) return cudaErrorInvalidValue;
-  const size_t smem = (size_t)span_cap * 8 + fixed;
+  const bool batch = n_scans > (uint32_t)kSmCount;
+  size_t smem = (size_t)span_cap * 8 + fixed;
+  const bool staged = !batch && smem + (size_t)pt_cap * 12 + 16 <= smem_max;
+  if (staged) smem += (size_t)pt_cap * 12 + 16;
   if (smem > 48u * 1024u) {
     const cudaError_t e = cudaFuncSetAttribute(k1_voxelize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  const bool batch = n_scans > (uint32_t)kSmCount;
   const int threads = batch ? 512 : kVoxThreads;     // (256 and 1024 threads per scan measured 20 % and 35 % slower on a 4096-scan batch)     // a batch: two (or more) scans per SM; a lone scan: all 32 warps
   k1_voxelize_kernel<<<n_scans, threads, smem, s>>>(d_pts, d_scan_off, row, label_res, gp.min_points, geom, span_cap, cell_cap_per_scan, d_cells_p,
-                                                    d_npts_p, d_labels_p, d_cell_count, d_slot, pt_cap, d_status);
+                                                    d_npts_p, d_labels_p, d_cell_count, d_slot, pt_cap, staged ? 1 : 0, d_status);
   if (n_launches) *n_launches += 1;
   return cudaGetLastError();
 }

@@ -11,7 +11,8 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k3_fused -s 3 -c 1 -o gpurun_out/r02_k3_fused_final -f python bench.py --steps 5 --warmup 3 --no-cpu-baseline --reg-steps 0 --pre-scans 0 --no-configs > gpurun_out/ncu_k3.log 2>&1; tail -1 gpurun_out/ncu_k3.log
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k7_solve -c 1 -o gpurun_out/r02_k7 -f python bench.py --steps 3 --warmup 3 --no-cpu-baseline --reg-steps 1 --reg-streams 0 --pre-scans 0 --no-configs > gpurun_out/ncu_k7.log 2>&1; tail -1 gpurun_out/ncu_k7.log
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k8_allpairs -s 2 -c 1 -o gpurun_out/r02_k8 -f python bench.py --steps 3 --warmup 3 --no-cpu-baseline --reg-steps 0 --pre-scans 0 --c3-batch 0 --replay-scans 0 > gpurun_out/ncu_k8.log 2>&1; tail -1 gpurun_out/ncu_k8.log
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k1_voxelize -s 2 -c 1 -o gpurun_out/r02_k1 -f python scripts/k1_profile.py 4096 > gpurun_out/ncu_k1.log 2>&1; tail -1 gpurun_out/ncu_k1.log
 M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed
-timeout 600 ncu --metrics $M --clock-control none --csv --log-file gpurun_out/r02_other_a.csv -k regex:"k1_|k2_|k5_|k6_|merge_maps|build_duo|permute_duos|transform_cells|prepare_affine" python bench.py --steps 3 --warmup 3 --no-cpu-baseline --reg-steps 0 --pre-scans 2 --c2-problems 0 --c3-batch 0 --replay-scans 12 > /dev/null 2> gpurun_out/other.err; tail -1 gpurun_out/other.err
+timeout 600 ncu --metrics $M --clock-control none --csv --log-file gpurun_out/r02_other_a.csv -k regex:"k1_|k2_|k5_|k6_|merge_maps|build_duo|emit_chunks|transform_cells|prepare_affine" python bench.py --steps 3 --warmup 3 --no-cpu-baseline --reg-steps 0 --pre-scans 2 --c2-problems 0 --c3-batch 0 --replay-scans 12 > /dev/null 2> gpurun_out/other.err; tail -1 gpurun_out/other.err
 python scripts/ncu_kernel_table.py gpurun_out/r02_other_a.csv > gpurun_out/r02_other_kernels_ncu.txt; cat gpurun_out/r02_other_kernels_ncu.txt
 ls -la gpurun_out | tail -20

@@ -135,3 +135,34 @@ def test_scan_step_equals_the_separate_calls(gpu_ctx, preset):
     ca, cb = sub_a.download(), sub_b.download()
     assert np.array_equal(ca["cells"], cb["cells"]) and np.array_equal(ca["npts"], cb["npts"]) and np.array_equal(ca["slot"], cb["slot"])
     sub_a.close(); sub_b.close()
+
+
+def test_scan_step_with_a_scan_that_yields_no_cells(gpu_ctx):
+    """A scan whose points all fall into cells with too few points has no NDT cells: the reference's matcher adds no residual blocks
+    ("WARNING: NO RESIDUALS ADDED!", ndt_matcher.cpp:454-456) and leaves the pose alone.  The composite must do the same — through
+    its fused path and through the separate calls — and carry on with the next scan."""
+    p = P.OXFORD
+    gp = capi.grid_params(p)
+    k = p.n_results_nn_lookup
+    opt = W.odometry_solver(capi, p)
+    _, scans = W.make_loop_drive(p, W.REPLAY_SCENE_SEED, 6)
+    loss = capi.make_loss(capi.LOSS_BARRON, p.loss_function_scale, p.loss_function_convexity, 1.0, 1.0)
+    sub = gpu_ctx.map_upload(np.zeros((0, 12), np.float32), np.zeros(2, np.uint32), gp)
+    pose, _, _ = sub.scan_step(scans[0], gp, k, loss, p.ndt_weight, opt, True, synth.pose_to_se2(0, 0, 0))
+    n_before = sub.info()[1]
+    sparse = scans[1][:: max(1, len(scans[1]) // 8)][:8].copy()           # eight scattered points: no cell reaches min_points
+    pose2, res, nc = sub.scan_step(sparse, gp, k, loss, p.ndt_weight, opt, True, pose)
+    assert nc == 0 and np.array_equal(pose2, pose)
+    assert res[capi.REG_STATUS] == 1 and res[capi.REG_ITERATIONS] == 0
+    assert sub.info()[1] == n_before                                       # nothing to merge
+    # the separate calls agree
+    M = gpu_ctx.voxelize(sparse, [0, len(sparse)], gp)
+    assert M.info()[1] == 0
+    prob = gpu_ctx.associate(sub, M, pose[None], k)
+    out, r = prob.register_batch(pose[None], loss, opt)
+    assert prob.n_pairs == 0 and np.array_equal(out[0], pose) and r[0, capi.REG_STATUS] == 1
+    M.close(); prob.close()
+    # and the stream carries on
+    pose3, res3, nc3 = sub.scan_step(scans[2], gp, k, loss, p.ndt_weight, opt, True, pose2)
+    assert nc3 > 20 and res3[capi.REG_STATUS] == 0 and np.all(np.isfinite(pose3))
+    sub.close()
