@@ -450,7 +450,11 @@ int randt_voxelize(randt_ctx* ctx, const float* pts4, const uint32_t* scan_off, 
   CKV(dev_alloc(&d_cells_p, (size_t)B * cell_cap * 3)); CKV(dev_alloc(&d_npts_p, (size_t)B * cell_cap)); CKV(dev_alloc(&d_labels_p, (size_t)B * cell_cap));
   CKV(dev_alloc(&m->slot, (size_t)B * m->geom.n_slots));
   int nl = 0;
-  CKV(launch_voxelize(d_pts, d_scan_off, B, max_pts, *gp, m->geom, cell_cap, d_cells_p, d_npts_p, d_labels_p, d_cnt, m->slot, d_status, ctx->stream, &nl));
+  unsigned short* d_bins = nullptr;
+  if (voxelize_needs_bins_scratch(max_pts, cell_cap, *gp)) CKV(dev_alloc(&d_bins, n_pts));
+  { const cudaError_t ev__ = launch_voxelize(d_pts, d_scan_off, B, max_pts, *gp, m->geom, cell_cap, d_cells_p, d_npts_p, d_labels_p, d_cnt, m->slot, d_bins, d_status, ctx->stream, &nl);
+    dev_free(d_bins);      // stream-ordered: released after the kernel
+    CKV(ev__); }
   lap("queued");
   // counts and status codes sit side by side and come back in one copy into the context's pinned block
   if (pinned_reserve(ctx, &ctx->h_offs, &ctx->offs_cap, 2 * (size_t)B + 2) != RANDT_OK) { cleanup(); free_map(m); return RANDT_E_NOMEM; }

@@ -139,8 +139,9 @@ cudaError_t launch_exclusive_scan_u32(const uint32_t* d_in, uint32_t* d_out /*[n
 enum { VOX_OK = 0, VOX_SPAN = 1, VOX_CELL_CAP = 2, VOX_OUT_OF_MAP = 3 };
 cudaError_t launch_voxelize(const float4* d_pts, const uint32_t* d_scan_off, uint32_t n_scans, uint32_t max_pts_per_scan,
                             const randt_grid_params& gp, const MapGeomDev& geom, uint32_t cell_cap_per_scan, float4* d_cells_p,
-                            uint32_t* d_npts_p, int32_t* d_labels_p, uint32_t* d_cell_count, int32_t* d_slot, int* d_status, cudaStream_t s,
-                            int* n_launches);
+                            uint32_t* d_npts_p, int32_t* d_labels_p, uint32_t* d_cell_count, int32_t* d_slot, unsigned short* d_bins_scratch /* n_points, or NULL */,
+                            int* d_status, cudaStream_t s, int* n_launches);
+bool voxelize_needs_bins_scratch(uint32_t max_pts_per_scan, uint32_t cell_cap_per_scan, const randt_grid_params& gp);
 cudaError_t launch_compact_cells(const float4* d_cells_p, const uint32_t* d_npts_p, const int32_t* d_labels_p, const uint32_t* d_cell_off,
                                  uint32_t n_scans, uint32_t cell_cap_per_scan, uint32_t max_cells_per_scan, float4* d_cells,
                                  uint32_t* d_npts, int32_t* d_labels, cudaStream_t s, int* n_launches);

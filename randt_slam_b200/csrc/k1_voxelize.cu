@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(kVoxThreads) k1_voxelize_kernel(const float4* 
                                                                  uint32_t span_cap, uint32_t cell_cap, float4* __restrict__ cells_out,
                                                                  uint32_t* __restrict__ npts_out, int32_t* __restrict__ labels_out,
                                                                  uint32_t* __restrict__ cell_count, int32_t* __restrict__ slot_out,
-                                                                 uint32_t pt_cap, int staged, int* __restrict__ status) {
+                                                                 uint32_t pt_cap, int staged, unsigned short* __restrict__ bins_scratch, int* __restrict__ status) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* mask = reinterpret_cast<uint32_t*>(smem_raw);
   uint32_t* cnt2 = mask + span_cap;                                         // span_cap / 2 words
@@ -184,8 +184,10 @@ __global__ void __launch_bounds__(kVoxThreads) k1_voxelize_kernel(const float4* 
   float* sx = reinterpret_cast<float*>(start + span_cap);
   float* sy = sx + pt_cap;
   float* si = sy + pt_cap;
-  unsigned short* bins = reinterpret_cast<unsigned short*>(si + pt_cap);
-  unsigned short* order = bins + pt_cap;
+  // (a scan too long for 14 bytes of shared memory per point keeps its bins in global scratch: bins_scratch != NULL)
+  unsigned short* smem_bins = reinterpret_cast<unsigned short*>(si + pt_cap);
+  unsigned short* bins = bins_scratch ? bins_scratch + scan_off[blockIdx.x] : smem_bins;
+  unsigned short* order = bins_scratch ? smem_bins : smem_bins + pt_cap;
   // staged (few scans, shared memory to spare): the scan itself also sits in shared memory, so the sort reads it at shared-memory
   // latency instead of going back to L2 once per round
   float* ox = reinterpret_cast<float*>(smem_raw + (((size_t)(reinterpret_cast<unsigned char*>(order + cell_cap) - smem_raw) + 15) & ~(size_t)15));
@@ -504,10 +506,21 @@ __global__ void __launch_bounds__(kMergeThreads) merge_maps_kernel(const float4*
 
 }  // namespace
 
+// a scan of this many points no longer fits its bins (2 bytes per point) into shared memory next to its sorted copy: the caller then
+// passes n_points x 2 bytes of global scratch
+bool voxelize_needs_bins_scratch(uint32_t max_pts_per_scan, uint32_t cell_cap_per_scan, const randt_grid_params& gp) {
+  const int row = static_cast<int>(sqrt((double)(size_t)gp.n_clusters));
+  const long long bound = (long long)(row + 4) * (long long)(row + 4);
+  const size_t span_cap = (size_t)((bound + 255) / 256 * 256);
+  const uint32_t pt_cap = (max_pts_per_scan + 31u) / 32u * 32u;
+  const size_t fixed = (size_t)pt_cap * 14 + (((size_t)std::min(cell_cap_per_scan, pt_cap) * 2 + 15) & ~(size_t)15);
+  return span_cap * 8 + fixed > (size_t)220 * 1024;
+}
+
 cudaError_t launch_voxelize(const float4* d_pts, const uint32_t* d_scan_off, uint32_t n_scans, uint32_t max_pts_per_scan,
                             const randt_grid_params& gp, const MapGeomDev& geom, uint32_t cell_cap_per_scan, float4* d_cells_p,
-                            uint32_t* d_npts_p, int32_t* d_labels_p, uint32_t* d_cell_count, int32_t* d_slot, int* d_status, cudaStream_t s,
-                            int* n_launches) {
+                            uint32_t* d_npts_p, int32_t* d_labels_p, uint32_t* d_cell_count, int32_t* d_slot, unsigned short* d_bins_scratch, int* d_status,
+                            cudaStream_t s, int* n_launches) {
   if (n_scans == 0) return cudaSuccess;
   const int row = static_cast<int>(sqrt((double)(size_t)gp.n_clusters));
   if (row <= 0) return cudaErrorInvalidValue;
@@ -517,14 +530,16 @@ cudaError_t launch_voxelize(const float4* d_pts, const uint32_t* d_scan_off, uin
   uint32_t span_cap = (uint32_t)((bound + 255) / 256 * 256);
   const size_t smem_max = 220 * 1024;
   const uint32_t pt_cap = (max_pts_per_scan + 31u) / 32u * 32u;        // a scan is staged in shared memory: 14 bytes per point (+ 2 per cell)
-  const size_t fixed = (size_t)pt_cap * 14 + (((size_t)std::min(cell_cap_per_scan, pt_cap) * 2 + 15) & ~(size_t)15);
-  if (fixed + 1536 > smem_max) return cudaErrorInvalidValue;           // > 16 k points in one scan (randt_voxelize refuses such scans)
+  const bool bins_global = voxelize_needs_bins_scratch(max_pts_per_scan, cell_cap_per_scan, gp);
+  if (bins_global && !d_bins_scratch) return cudaErrorInvalidValue;
+  const size_t fixed = (size_t)pt_cap * (bins_global ? 12 : 14) + (((size_t)std::min(cell_cap_per_scan, pt_cap) * 2 + 15) & ~(size_t)15);
+  if (fixed + 2048 > smem_max) return cudaErrorInvalidValue;           // > 18 k points in one scan (randt_voxelize refuses such scans)
   if ((size_t)span_cap * 8 + fixed > smem_max) span_cap = (uint32_t)((smem_max - fixed) / 8 / 256 * 256);
   span_cap = std::min<uint32_t>(span_cap, 65280u);                     // bins are 16 bit (0xffff marks "no point")
   if (span_cap == 0) return cudaErrorInvalidValue;
   const bool batch = n_scans > (uint32_t)kSmCount;
   size_t smem = (size_t)span_cap * 8 + fixed;
-  const bool staged = !batch && smem + (size_t)pt_cap * 12 + 16 <= smem_max;
+  const bool staged = !batch && !bins_global && smem + (size_t)pt_cap * 12 + 16 <= smem_max;
   if (staged) smem += (size_t)pt_cap * 12 + 16;
   if (smem > 48u * 1024u) {
     const cudaError_t e = cudaFuncSetAttribute(k1_voxelize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -532,7 +547,7 @@ cudaError_t launch_voxelize(const float4* d_pts, const uint32_t* d_scan_off, uin
   }
   const int threads = batch ? 512 : kVoxThreads;     // (256 and 1024 threads per scan measured 20 % and 35 % slower on a 4096-scan batch)     // a batch: two (or more) scans per SM; a lone scan: all 32 warps
   k1_voxelize_kernel<<<n_scans, threads, smem, s>>>(d_pts, d_scan_off, row, label_res, gp.min_points, geom, span_cap, cell_cap_per_scan, d_cells_p,
-                                                    d_npts_p, d_labels_p, d_cell_count, d_slot, pt_cap, staged ? 1 : 0, d_status);
+                                                    d_npts_p, d_labels_p, d_cell_count, d_slot, pt_cap, staged ? 1 : 0, bins_global ? d_bins_scratch : nullptr, d_status);
   if (n_launches) *n_launches += 1;
   return cudaGetLastError();
 }

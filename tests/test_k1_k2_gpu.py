@@ -62,6 +62,47 @@ def test_voxelize_device_pointer_and_large_batch(oracle, gpu_ctx):
         assert np.array_equal(d["cells"][a:z].view(np.uint32), ref[b % 4]["cells"].view(np.uint32))
 
 
+def _same_cells(d, b, v):
+    a, z = d["cell_off"][b], d["cell_off"][b + 1]
+    assert z - a == len(v["cells"])
+    assert np.array_equal(d["labels"][a:z], v["labels"]) and np.array_equal(d["npts"][a:z], v["npts"])
+    assert np.array_equal(d["slot"][b], v["slot"])
+    assert np.array_equal(d["cells"][a:z].view(np.uint32), v["cells"].view(np.uint32))
+
+
+@pytest.mark.parametrize("n_scans", [1, 200])       # a lone scan (staged in shared memory) and a batch (two scans per SM)
+def test_voxelize_any_point_order_and_extreme_cells(oracle, gpu_ctx, n_scans):
+    """K1 sorts cell by cell along the parts of the scan a cell occurs in; an azimuth-major scan keeps those walks short, but nothing may
+    depend on it.  Shuffled points (every cell occurs in every part), a scan that is one single cell, the largest scan the call
+    accepts (16 384 points), and a cell that straddles the end of the scan — all bit-identical to the oracle's sequential sums."""
+    p = P.OXFORD
+    rng = np.random.default_rng(9)
+    base = H.make_scan(p, 6, (0.2, 0.1, 0.05), 77)
+    shuffled = base[rng.permutation(len(base))]
+    one_cell = np.zeros((3000, 4), np.float32)
+    one_cell[:, 0] = 10.0 + rng.uniform(0, 1.0, 3000); one_cell[:, 1] = 20.0 + rng.uniform(0, 1.0, 3000); one_cell[:, 3] = rng.uniform(80, 200, 3000)
+    big = np.concatenate([base, base[::-1], shuffled, base])[:16384].copy()
+    big[:, :2] += rng.normal(0, 0.02, (len(big), 2)).astype(np.float32)
+    wrap = np.concatenate([base[len(base) // 2:], base[:len(base) // 2]])       # the scan starts in the middle of the sweep
+    cases = [shuffled, one_cell, big, wrap]
+    scans = [cases[i % len(cases)] for i in range(max(n_scans, len(cases)))] if n_scans > 1 else None
+    gp = capi.grid_params(p)
+    ref = [oracle.voxelize(c, *H.vox_args(p)) for c in cases]
+    assert len(ref[1]["cells"]) >= 1 and ref[1]["npts"].max() > 1000 and len(big) == 16384
+    if n_scans == 1:
+        for c, v in zip(cases, ref):
+            m = gpu_ctx.voxelize(c, [0, len(c)], gp)
+            _same_cells(m.download(want_labels=True), 0, v)
+            m.close()
+    else:
+        off = np.zeros(len(scans) + 1, np.uint32); off[1:] = np.cumsum([len(x) for x in scans])
+        m = gpu_ctx.voxelize(np.concatenate(scans), off, gp)
+        d = m.download(want_labels=True)
+        for b in range(len(scans)):
+            _same_cells(d, b, ref[b % len(cases)])
+        m.close()
+
+
 def test_voxelize_rejects_far_points(gpu_ctx):
     p = P.OXFORD
     pts = np.zeros((50, 4), np.float32); pts[:, 0] = 1e6; pts[:, 3] = 90
