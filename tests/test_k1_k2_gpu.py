@@ -187,6 +187,36 @@ def test_associate_single_map_equals_batched_path(oracle, gpu_ctx, preset, n_sub
     assert np.array_equal(np.asarray(ra[0])[0], np.asarray(rb[0])[0])
 
 
+@pytest.mark.parametrize("metric", [capi.LOOKUP_MAHALANOBIS, capi.LOOKUP_EUCLID])
+def test_associate_single_map_with_thousands_of_cells(oracle, gpu_ctx, metric):
+    """the one-CTA association walks a large moving map 1 024 cells at a time, carrying the pair / duo offsets from round to round:
+    3 000 moving against 6 000 fixed cells (drawn directly, slot table built on upload), against the oracle and the batched path"""
+    p = P.INDOOR
+    gp = capi.grid_params(p)
+    k = p.n_results_nn_lookup
+    rng = np.random.default_rng(77)
+    ext = 0.45 * p.size_x * p.resolution
+    cf = H.random_cells(rng, 6000, extent=ext); cm = H.random_cells(rng, 3000, extent=ext)
+    pose = synth.pose_to_se2(0.3, -0.2, 0.05)
+    F1 = gpu_ctx.map_upload(cf, np.array([0, 6000], np.uint32), gp)
+    M1 = gpu_ctx.map_upload(cm, np.array([0, 3000], np.uint32), gp)
+    slot = F1.download()["slot"][0]
+    single = gpu_ctx.associate(F1, M1, pose[None], k, metric)
+    pm, pf, seg = single.download()
+    im, jf = oracle.associate(cf, slot, p.size_x, p.size_y, p.resolution, p.max_neighbor_linf_distance, cm, pose, k, metric)
+    assert seg[1] == len(im) and len(im) > 3000
+    assert np.array_equal(pm, im) and np.array_equal(pf, jf)
+    F2 = gpu_ctx.map_upload(np.concatenate([cf, cf]), np.array([0, 6000, 12000], np.uint32), gp)
+    M2 = gpu_ctx.map_upload(np.concatenate([cm, cm]), np.array([0, 3000, 6000], np.uint32), gp)
+    both = gpu_ctx.associate(F2, M2, np.stack([pose, pose]), k, metric)
+    bm, bf, bseg = both.download()
+    assert np.array_equal(bm[:bseg[1]], pm) and np.array_equal(bf[:bseg[1]], pf)
+    loss = capi.make_loss(capi.LOSS_BARRON, 1.0, -2.0)
+    a = single.eval_fused(pose[None], loss); b = both.eval_fused(np.stack([pose, pose]), loss)
+    assert np.allclose(a[0], b[0], rtol=1e-11, atol=1e-13)
+    assert single.layout()[0] * 2 == both.layout()[0]
+
+
 def test_slot_table_rebuild_matches_insert_order(oracle, gpu_ctx):
     p = P.OXFORD
     v = oracle.voxelize(H.make_scan(p, 9, (0, 0, 0), 9), *H.vox_args(p))
