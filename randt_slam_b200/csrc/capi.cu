@@ -803,7 +803,7 @@ int randt_associate(randt_ctx* ctx, const randt_map* F, const randt_map* M, cons
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_p0, pose0, 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(d_tot, 0, 3 * sizeof(uint32_t), ctx->stream);
     if (e == cudaSuccess) e = launch_associate_single(F->cells, F->n_cells, F->slot, M->cells, n_m, geom, d_p0, k, metric, p->pairs, p->duos, p->duo_recs, p->duo_p0,
-                                                      p->duo_overflow, ovf_cap, p->cells_m, p->cells_f, d_tot, nullptr, ctx->stream, &nl1);
+                                                      p->duo_overflow, ovf_cap, p->cells_m, p->cells_f, d_tot, nullptr, nullptr, 0.0, nullptr, ctx->stream, &nl1);
     uint32_t h_tot[3] = {0, 0, 0};
     if (e == cudaSuccess) e = cudaMemcpyAsync(h_tot, d_tot, sizeof(h_tot), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
@@ -1395,67 +1395,127 @@ int randt_register_batch_weighted(randt_ctx* ctx, const randt_problem* cp, int v
 }
 
 namespace {
-// One scan against one submap, association and solve back to back with no host round trip between them: the fused association
-// kernel leaves K3's records and a one-registration layout in device memory, K7 solves from them, and pose, result and the totals come
-// back in one copy.  Same kernels and the same arithmetic as randt_associate + randt_register_batch (which also build the pair lists
-// and the K3 schedule a caller may evaluate later; a scan step drops its problem at once and needs neither).
-// -> RANDT_OK with *handled = false when the pair does not qualify (too many duos for one warp, escapes beyond the table).
-int scan_associate_solve(randt_ctx* ctx, const randt_map* F, const randt_map* M, int k, int metric, const randt_loss* loss, const randt_solver_options* opt,
-                         double* pose_io, double* res, bool* handled) {
-  *handled = false;
-  static const bool no_fused = getenv("RANDT_NO_FUSED_ASSOC") != nullptr;
-  const uint32_t n_m = M->n_cells;
-  const size_t max_duos = (size_t)n_m * ((k + 1) / 2);
-  if (no_fused || opt->poll_interval < 0 || n_m == 0 || max_duos > kSolveMaxDuos || F->n_cells > kSingleMaxCells) return RANDT_OK;
-  if (k < 1 || k > kMaxNeighbours || (metric != RANDT_LOOKUP_MAHALANOBIS_INTENSITY && metric != RANDT_LOOKUP_EUCLID_XY)) return RANDT_OK;   // let randt_associate report it
-  if (!(opt->gnc_divisor > 1.0) || !(opt->gnc_loss_scale > 0.0) || opt->gnc_max_steps < 1 || opt->max_num_iterations < 0 ||
-      opt->max_num_consecutive_invalid_steps < 1 || !(opt->initial_trust_region_radius > 0.0)) return RANDT_OK;                          // let randt_register_batch report it
+// One scan against one submap as ONE chain on the device: points up, K1, the fused association (which reads the scan's cell count from
+// where K1 left it and leaves K3's records, a one-registration layout and the scan's ScaledLoss weight in device memory), K7 — and one
+// copy back with pose, result, totals, cell count and K1's status.  One synchronisation; no pair lists, no K3 schedule.  Same kernels
+// and the same arithmetic as randt_voxelize + randt_associate + randt_register_batch.
+// -> *scan_out = the scan's map (for the keyframe insertion); *handled = false when the registration has to be redone through the
+//    general path (more duos than the persistent solver takes in a batch call, escapes beyond the table): the map is valid either way.
+int scan_chain(randt_ctx* ctx, const randt_map* F, const float* pts4, uint32_t n_pts, const randt_grid_params* gp, int k, int metric, const randt_loss* loss,
+               double ndt_weight, const randt_solver_options* opt, double* pose_io, double* res, randt_map** scan_out, bool* handled) {
+  *handled = false; *scan_out = nullptr;
   MapGeomDev geom = F->geom;
   geom.r_stop = static_cast<int>(F->gp.max_linf / F->gp.resolution);
-  if (2 * (geom.r_stop > 0 ? geom.r_stop - 1 : 0) + 1 > geom.size_x) return RANDT_OK;
   randt_loss l0 = *loss; l0.mu = 1.0;
   LossParams lp;
   if (int rc = make_loss(ctx, &l0, &lp)) return rc;
   CK(cudaSetDevice(ctx->device));
   StreamScope scope__(ctx->stream, ctx->sref->pool);
-  // one block: [pose 4 | result 8] doubles, [totals 3 | counter 1 | layout 6 | pad 2] words, records, escapes
+  static const bool trace = getenv("RANDT_DEBUG_TIMING") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!trace) return;
+    auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "[randt] scan_chain %-14s %8.1f us\n", what, std::chrono::duration<double, std::micro>(t - t_prev).count());
+    t_prev = t;
+  };
+  const uint32_t div = (uint32_t)std::max(gp->min_points, 0) + 1u;
+  const uint32_t cell_cap = std::max<uint32_t>(1, n_pts / div);
+  const size_t max_duos = (size_t)cell_cap * ((k + 1) / 2);
+  randt_map* m = new (std::nothrow) randt_map();
+  if (!m) return RANDT_E_NOMEM;
+  m->device = ctx->device; m->sref = ctx->sref; m->gp = *gp; m->geom = make_geom(*gp); m->B = 1;
+  // one block: [pose 4 | result 8 | weight 1 | pad 1] doubles, [totals 3 | counter 1 | layout 6 | cells 1 | status 1 | scan_off 2 | pad 2] words,
+  // records, escapes
   constexpr uint32_t ovf_cap = 64;
-  constexpr size_t io_doubles = 4 + RANDT_REG_STRIDE, io_words = 12;
+  constexpr size_t io_doubles = 4 + RANDT_REG_STRIDE + 2, io_words = 16;
   const size_t off_rec = (io_doubles * 8 + io_words * 4 + 127) & ~(size_t)127;
   const size_t off_ovf = off_rec + ((max_duos * sizeof(DuoRec) + 127) & ~(size_t)127);
   const size_t bytes = off_ovf + ovf_cap * sizeof(DuoRecFull);
-  unsigned char* blk = nullptr;
-  CK(dev_alloc(&blk, bytes));
-  double* d_pose = reinterpret_cast<double*>(blk); double* d_res = d_pose + 4;
+  unsigned char* blk = nullptr; float4* d_pts = nullptr; unsigned short* d_bins = nullptr;
+  struct Back { double pose[4]; double res[RANDT_REG_STRIDE]; double weight[2]; uint32_t words[io_words]; };
+  static_assert(sizeof(Back) == io_doubles * 8 + io_words * 4, "the read-back mirrors the head of the block");
+  int nl = 0;
+  cudaError_t e = dev_alloc(&blk, bytes);
+  if (e == cudaSuccess) e = dev_alloc(&d_pts, n_pts);
+  if (e == cudaSuccess) e = dev_alloc(&m->cells, (size_t)cell_cap * 3);
+  if (e == cudaSuccess) e = dev_alloc(&m->npts, cell_cap);
+  if (e == cudaSuccess) e = dev_alloc(&m->labels, cell_cap);
+  if (e == cudaSuccess) e = dev_alloc(&m->slot, m->geom.n_slots);
+  if (e == cudaSuccess) e = dev_alloc(&m->cell_off, 2);
+  if (e == cudaSuccess && voxelize_needs_bins_scratch(n_pts, cell_cap, *gp)) e = dev_alloc(&d_bins, n_pts);
+  if (e == cudaSuccess && pinned_reserve(ctx, &ctx->h_offs, &ctx->offs_cap, sizeof(Back) / sizeof(uint32_t)) != RANDT_OK) e = cudaErrorMemoryAllocation;
+  double* d_pose = reinterpret_cast<double*>(blk); double* d_res = d_pose + 4; double* d_weight = d_res + RANDT_REG_STRIDE;
   uint32_t* d_words = reinterpret_cast<uint32_t*>(blk + io_doubles * 8);
-  uint32_t *d_tot = d_words, *d_counter = d_words + 3, *d_layout = d_words + 4;
+  uint32_t *d_tot = d_words, *d_counter = d_words + 3, *d_layout = d_words + 4, *d_cnt = d_words + 10, *d_scan_off = d_words + 12;
+  int* d_status = reinterpret_cast<int*>(d_words + 11);
   DuoRec* d_recs = reinterpret_cast<DuoRec*>(blk + off_rec);
   DuoRecFull* d_ovf = reinterpret_cast<DuoRecFull*>(blk + off_ovf);
-  int nl = 0;
-  struct Back { double pose[4]; double res[RANDT_REG_STRIDE]; uint32_t words[io_words]; };
-  if (int rc = pinned_reserve(ctx, &ctx->h_offs, &ctx->offs_cap, sizeof(Back) / sizeof(uint32_t))) { dev_free(blk); return rc; }
   Back& h = *reinterpret_cast<Back*>(ctx->h_offs);
-  cudaError_t e = cudaMemsetAsync(d_pose, 0, io_doubles * 8 + io_words * 4, ctx->stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(d_pose, pose_io, 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess) e = launch_associate_single(F->cells, F->n_cells, F->slot, M->cells, n_m, geom, d_pose, k, metric, nullptr, nullptr, d_recs, nullptr, d_ovf, ovf_cap,
-                                                    nullptr, nullptr, d_tot, d_layout, ctx->stream, &nl);
+  if (e == cudaSuccess) {
+    // the head of the block goes up in one copy: pose, zeros, the loss weight for scans without ndt_weight, the scan's point range
+    memset(&h, 0, sizeof(Back));
+    memcpy(h.pose, pose_io, sizeof(h.pose));
+    h.weight[0] = lp.weight;
+    h.words[12] = 0u; h.words[13] = n_pts;
+    e = cudaMemcpyAsync(blk, &h, sizeof(Back), cudaMemcpyHostToDevice, ctx->stream);
+  }
+  if (e == cudaSuccess && n_pts) e = cudaMemcpyAsync(d_pts, pts4, (size_t)n_pts * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = launch_voxelize(d_pts, d_scan_off, 1, n_pts, *gp, m->geom, cell_cap, m->cells, m->npts, m->labels, d_cnt, m->slot, d_bins, d_status, ctx->stream, &nl);
+  if (e == cudaSuccess) e = launch_associate_single(F->cells, F->n_cells, F->slot, m->cells, 0u, geom, d_pose, k, metric, nullptr, nullptr, d_recs, nullptr, d_ovf, ovf_cap,
+                                                    nullptr, nullptr, d_tot, d_layout, d_cnt, ndt_weight > 0.0 ? ndt_weight : 0.0, ndt_weight > 0.0 ? d_weight : nullptr,
+                                                    ctx->stream, &nl);
   if (e == cudaSuccess) {
     DeviceProblem v;
     v.duo_recs = d_recs; v.duo_overflow = d_ovf; v.seg_off = d_layout; v.seg_first_tile = d_layout + 4; v.n_segments = 1;
     SolveLayout L;
-    L.seg_duo_off = d_layout + 2; L.tile_rec_begin = d_layout + 5; L.tile_duos = kSolveMaxDuos; L.items = nullptr; L.n_items = 1; L.next_item = d_counter;
-    e = launch_solve_persistent(v, L, 0, opt->use_manifold, lp, nullptr, *opt, d_pose, d_pose, d_res, ctx->d_bad, ctx->stream, &nl);
+    // one tile that covers any registration: the chunk index never leaves it
+    L.seg_duo_off = d_layout + 2; L.tile_rec_begin = d_layout + 5; L.tile_duos = 1u << 20; L.items = nullptr; L.n_items = 1; L.next_item = d_counter;
+    e = launch_solve_persistent(v, L, 0, opt->use_manifold, lp, d_weight, *opt, d_pose, d_pose, d_res, ctx->d_bad, ctx->stream, &nl);
   }
+  lap("queued");
   if (e == cudaSuccess) e = cudaMemcpyAsync(&h, blk, sizeof(Back), cudaMemcpyDeviceToHost, ctx->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  dev_free(blk);
-  if (e != cudaSuccess) return fail(ctx, RANDT_E_CUDA, "randt_scan_step (fused associate + solve)", e);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);      // (the pinned block is free again: the upload has long left it)
+  lap("result back");
+  dev_free(blk); dev_free(d_pts); dev_free(d_bins);
+  if (e != cudaSuccess) { free_map(m); return fail(ctx, RANDT_E_CUDA, "randt_scan_step (voxelise + associate + solve chain)", e); }
   ctx->launches += nl;
-  if (h.words[2] > ovf_cap) return RANDT_OK;       // escapes beyond the table: the general path sizes it
+  const int status = (int)h.words[11];
+  if (status == VOX_SPAN || status == VOX_CELL_CAP) {
+    free_map(m);
+    return fail(ctx, RANDT_E_CAPACITY, "randt_voxelize: label span / cell capacity exceeded (points far outside +-max_range?)");
+  }
+  if (status == VOX_OUT_OF_MAP) {
+    free_map(m);
+    return fail(ctx, RANDT_E_INVALID, "randt_voxelize: a cell mean falls outside the map (the reference throws std::out_of_range here)");
+  }
+  const uint32_t n_cells = h.words[10];
+  m->h_cell_off = {0u, n_cells}; m->n_cells = n_cells; m->max_per_map = n_cells;
+  if (cudaMemcpyAsync(m->cell_off, m->h_cell_off.data(), 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
+    free_map(m);
+    return fail(ctx, RANDT_E_CUDA, "randt_scan_step: cell offsets");
+  }
+  *scan_out = m;
+  // the general path solves registrations above kSolveMaxDuos stepwise (other summation order): keep the composite equal to it
+  if (h.words[2] > ovf_cap || h.words[1] > kSolveMaxDuos) return RANDT_OK;
   memcpy(pose_io, h.pose, sizeof(h.pose));
   memcpy(res, h.res, sizeof(h.res));
   *handled = true;
   return RANDT_OK;
+}
+
+// may the chain take this call?  (anything it cannot take is left to the separate entry points, which also report the errors)
+bool scan_chain_applies(const randt_map* F, uint32_t n_pts, const randt_grid_params* gp, int k, int metric, const randt_solver_options* opt) {
+  static const bool no_fused = getenv("RANDT_NO_FUSED_ASSOC") != nullptr;
+  if (no_fused || opt->poll_interval < 0 || F->n_cells == 0 || F->n_cells > kSingleMaxCells || n_pts == 0 || n_pts > 16384u) return false;
+  if (!same_geom(F->gp, *gp) || gp->n_clusters <= 0 || gp->size_x <= 0 || gp->size_y <= 0 || !(gp->resolution > 0) || !(gp->max_range > 0)) return false;
+  if (k < 1 || k > kMaxNeighbours || (metric != RANDT_LOOKUP_MAHALANOBIS_INTENSITY && metric != RANDT_LOOKUP_EUCLID_XY)) return false;
+  if (!(opt->gnc_divisor > 1.0) || !(opt->gnc_loss_scale > 0.0) || opt->gnc_max_steps < 1 || opt->max_num_iterations < 0 ||
+      opt->max_num_consecutive_invalid_steps < 1 || !(opt->initial_trust_region_radius > 0.0)) return false;
+  const int r_stop = static_cast<int>(F->gp.max_linf / F->gp.resolution);
+  if (2 * (r_stop > 0 ? r_stop - 1 : 0) + 1 > F->geom.size_x) return false;
+  const uint32_t cell_cap = std::max<uint32_t>(1, n_pts / ((uint32_t)std::max(gp->min_points, 0) + 1u));
+  return (size_t)cell_cap * ((k + 1) / 2) <= 16384u;
 }
 }  // namespace
 
@@ -1473,31 +1533,34 @@ int randt_scan_step(randt_ctx* ctx, randt_map* submap, const float* pts4, uint32
     fprintf(stderr, "[randt] scan_step %-12s %8.1f us\n", what, std::chrono::duration<double, std::micro>(t - t_prev).count());
     t_prev = t;
   };
-  const uint32_t off[2] = {0u, n_pts};
-  randt_map* scan = nullptr;
-  int rc = randt_voxelize(ctx, pts4, off, 1, gp, 0, &scan);
-  if (rc != RANDT_OK) return rc;
-  lap("voxelize");
-  if (n_cells_out) *n_cells_out = scan->n_cells;
+  randt_loss l; l.kind = RANDT_LOSS_NONE; l.scale = 1.0; l.alpha = 2.0; l.mu = 1.0; l.weight = 1.0;
+  if (loss) l = *loss;
   double res[RANDT_REG_STRIDE] = {0};
-  if (submap->n_cells > 0) {
-    randt_loss l; l.kind = RANDT_LOSS_NONE; l.scale = 1.0; l.alpha = 2.0; l.mu = 1.0; l.weight = 1.0;
-    if (loss) l = *loss;
+  randt_map* scan = nullptr;
+  int rc = RANDT_OK;
+  bool handled = false;
+  if (scan_chain_applies(submap, n_pts, gp, k, metric, opt)) {
+    rc = scan_chain(ctx, submap, pts4, n_pts, gp, k, metric, &l, ndt_weight, opt, pose_io, res, &scan, &handled);
+    if (rc != RANDT_OK) return rc;
+    lap("chain");
+  } else {
+    const uint32_t off[2] = {0u, n_pts};
+    rc = randt_voxelize(ctx, pts4, off, 1, gp, 0, &scan);
+    if (rc != RANDT_OK) return rc;
+    lap("voxelize");
+  }
+  if (n_cells_out) *n_cells_out = scan->n_cells;
+  if (submap->n_cells > 0 && !handled) {
     if (ndt_weight > 0.0 && scan->n_cells > 0) l.weight = ndt_weight / ((double)scan->n_cells * (double)k);
-    bool handled = false;
-    rc = scan_associate_solve(ctx, submap, scan, k, metric, &l, opt, pose_io, res, &handled);
-    lap("assoc+solve");
-    if (rc == RANDT_OK && !handled) {
-      randt_problem* prob = nullptr;
-      rc = randt_associate(ctx, submap, scan, pose_io, k, metric, &prob);
-      lap("associate");
-      if (rc == RANDT_OK) {
-        rc = randt_register_batch(ctx, prob, 0, pose_io, &l, opt, res);
-        lap("register");
-      }
-      randt_problem_destroy(prob);
-      lap("destroy");
+    randt_problem* prob = nullptr;
+    rc = randt_associate(ctx, submap, scan, pose_io, k, metric, &prob);
+    lap("associate");
+    if (rc == RANDT_OK) {
+      rc = randt_register_batch(ctx, prob, 0, pose_io, &l, opt, res);
+      lap("register");
     }
+    randt_problem_destroy(prob);
+    lap("destroy");
   }
   if (rc == RANDT_OK && (insert_keyframe || submap->n_cells == 0)) {
     rc = randt_map_transform_se2d(ctx, scan, pose_io);

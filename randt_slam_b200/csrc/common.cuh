@@ -119,10 +119,12 @@ cudaError_t launch_associate(const float4* cells_f, const uint32_t* cell_off_f, 
 // one map pair, everything (affine, association, pair / duo lists, K3 records, cell snapshots, totals) in one launch; d_totals[3] zeroed by
 // the caller.  d_pairs == NULL: records only (no pair / duo lists, no snapshots).  d_layout != NULL: also the 6-word layout
 // {seg_off[2], seg_duo_off[2], seg_first_tile, tile_rec_begin} that lets K7 solve this registration without a host round trip.
+// d_n_m != NULL: the moving map's size is read from the device (chained behind K1); d_weight != NULL: receives ndt_weight / (n_m k).
 cudaError_t launch_associate_single(const float4* cells_f, uint32_t n_f, const int32_t* slot_f, const float4* cells_m, uint32_t n_m,
                                     const MapGeomDev& geom, const double* d_pose0, int k, int metric, uint2* d_pairs, Duo* d_duos, DuoRec* d_recs,
                                     uint32_t* d_duo_p0, DuoRecFull* d_overflow, uint32_t overflow_cap, float4* d_snap_m, float4* d_snap_f,
-                                    uint32_t* d_totals, uint32_t* d_layout, cudaStream_t s, int* n_launches);
+                                    uint32_t* d_totals, uint32_t* d_layout, const uint32_t* d_n_m /* or NULL: n_m */, double ndt_weight,
+                                    double* d_weight /* or NULL */, cudaStream_t s, int* n_launches);
 cudaError_t launch_compact_pairs(const uint32_t* d_nn, const uint32_t* d_cnt, const uint32_t* d_scan /*exclusive scan of cnt*/,
                                  const uint32_t* cell_off_m, const uint32_t* cell_off_f, uint32_t n_maps, uint32_t n_m_total,
                                  uint32_t max_m_per_map, int k, uint2* d_pairs, cudaStream_t s, int* n_launches);

@@ -147,7 +147,13 @@ __global__ void __launch_bounds__(kSingleThreads) k2_associate_single_kernel(con
                                                                             Duo* __restrict__ duos, DuoRec* __restrict__ recs, uint32_t* __restrict__ duo_p0,
                                                                             DuoRecFull* __restrict__ overflow, uint32_t overflow_cap, float4* __restrict__ snap_m,
                                                                             float4* __restrict__ snap_f, uint32_t* __restrict__ totals /* P, n_duos, n_overflow */,
-                                                                            uint32_t* __restrict__ layout /* or NULL: the one-registration layout K7 walks */) {
+                                                                            uint32_t* __restrict__ layout /* or NULL: the one-registration layout K7 walks */,
+                                                                            const uint32_t* __restrict__ n_m_dev /* or NULL: the moving map's size, still on the device */,
+                                                                            double ndt_weight, double* __restrict__ weight_out) {
+  // chained behind K1 without a host round trip, the size of the moving map is read from where K1 left it, and the ScaledLoss
+  // weight of the scan, ndt_weight / (n_cells k) (ndt_matcher.cpp:392), is left for K7 next to the records
+  if (n_m_dev) n_m = *n_m_dev;
+  if (weight_out && threadIdx.x == 0 && n_m > 0u) *weight_out = ndt_weight / ((double)n_m * (double)k);
   __shared__ float4 aff[4];
   __shared__ uint32_t warp_sums[32];
   __shared__ uint32_t warp_sums2[32];
@@ -331,9 +337,10 @@ cudaError_t launch_associate(const float4* cells_f, const uint32_t* cell_off_f, 
 cudaError_t launch_associate_single(const float4* cells_f, uint32_t n_f, const int32_t* slot_f, const float4* cells_m, uint32_t n_m,
                                     const MapGeomDev& geom, const double* d_pose0, int k, int metric, uint2* d_pairs, Duo* d_duos, DuoRec* d_recs,
                                     uint32_t* d_duo_p0, DuoRecFull* d_overflow, uint32_t overflow_cap, float4* d_snap_m, float4* d_snap_f,
-                                    uint32_t* d_totals, uint32_t* d_layout, cudaStream_t s, int* n_launches) {
+                                    uint32_t* d_totals, uint32_t* d_layout, const uint32_t* d_n_m, double ndt_weight, double* d_weight, cudaStream_t s,
+                                    int* n_launches) {
   k2_associate_single_kernel<<<1, kSingleThreads, 0, s>>>(cells_f, n_f, slot_f, cells_m, n_m, geom, d_pose0, k, metric, d_pairs, d_duos, d_recs, d_duo_p0,
-                                                         d_overflow, overflow_cap, d_snap_m, d_snap_f, d_totals, d_layout);
+                                                         d_overflow, overflow_cap, d_snap_m, d_snap_f, d_totals, d_layout, d_n_m, ndt_weight, d_weight);
   if (n_launches) *n_launches += 1;
   return cudaGetLastError();
 }
