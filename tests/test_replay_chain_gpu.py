@@ -166,3 +166,37 @@ def test_scan_step_with_a_scan_that_yields_no_cells(gpu_ctx):
     pose3, res3, nc3 = sub.scan_step(scans[2], gp, k, loss, p.ndt_weight, opt, True, pose2)
     assert nc3 > 20 and res3[capi.REG_STATUS] == 0 and np.all(np.isfinite(pose3))
     sub.close()
+
+
+def test_scan_step_chain_hands_long_registrations_to_the_general_path(gpu_ctx):
+    """The chain solves on a four-warp team whatever the registration's length; the batch call solves registrations above 512 duos
+    stepwise (K3 + K4), in another summation order.  So that the composite always equals the separate calls, the chain's result is
+    dropped for such a scan and the registration is redone through the general path.  A fine clustering (16 384 clusters, cells kept
+    from 2 points on) makes scans of ~300 cells = ~600 duos at k = 4."""
+    p = P.INDOOR
+    gp = capi.GridParams(float(p.max_range), 16384, 1, int(p.size_x), int(p.size_y), float(p.resolution), float(p.max_neighbor_linf_distance))
+    k = p.n_results_nn_lookup
+    opt = W.odometry_solver(capi, p)
+    _, scans = W.make_loop_drive(p, W.REPLAY_SCENE_SEED, 8)
+    loss = capi.make_loss(capi.LOSS_BARRON, p.loss_function_scale, p.loss_function_convexity, 1.0, 1.0)
+    empty = lambda: gpu_ctx.map_upload(np.zeros((0, 12), np.float32), np.zeros(2, np.uint32), gp)
+    sub_a, sub_b = empty(), empty()
+    pose_a = synth.pose_to_se2(0, 0, 0)
+    pose_a, _, _ = sub_a.scan_step(scans[0], gp, k, loss, p.ndt_weight, opt, True, pose_a)
+    pose_b = synth.pose_to_se2(0, 0, 0)
+    m0 = gpu_ctx.voxelize(scans[0], [0, len(scans[0])], gp)
+    m0.transform_se2d(pose_b[None]); sub_b.merge(m0); m0.close()
+    longest = 0
+    for i in range(1, len(scans)):
+        pose_a, res_a, nc = sub_a.scan_step(scans[i], gp, k, loss, p.ndt_weight, opt, i % 2 == 0, pose_a)
+        M = gpu_ctx.voxelize(scans[i], [0, len(scans[i])], gp)
+        prob = gpu_ctx.associate(sub_b, M, pose_b[None], k)
+        longest = max(longest, prob.layout()[0])
+        out, res_b = prob.register_batch(pose_b[None], capi.make_loss(capi.LOSS_BARRON, p.loss_function_scale, p.loss_function_convexity, 1.0, p.ndt_weight / (nc * k)), opt)
+        pose_b = out[0]
+        assert np.array_equal(pose_a, pose_b) and np.array_equal(res_a, res_b[0]), i
+        if i % 2 == 0:
+            M.transform_se2d(pose_b[None]); sub_b.merge(M)
+        M.close(); prob.close()
+    assert longest > 512, longest          # the case this test is about did occur
+    sub_a.close(); sub_b.close()
