@@ -1019,6 +1019,19 @@ int randt_eval_emit(randt_ctx* ctx, const randt_problem* cp, int variant, const 
   CK(cudaMemcpyAsync(p->d_poses, poses, (size_t)p->S * np * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   int rc = randt_eval_emit_dev(ctx, p, variant, p->d_poses, p->d_r, J ? p->d_J : nullptr);
   if (rc) return rc;
+  // A single problem's residuals and Jacobian rows (the ceres::CostFunction::Evaluate shape: a few KB) come back through the
+  // context's pinned block: two copies into pageable memory would each be a blocking staged transfer (~10 us apiece on this host).
+  const size_t n_r = p->P, n_J = J ? (size_t)p->P * np : 0;
+  if ((n_r + n_J) * sizeof(double) <= ((size_t)1 << 20) && n_r) {
+    if (int rc2 = pinned_reserve(ctx, &ctx->h_offs, &ctx->offs_cap, 2 * (n_r + n_J))) return rc2;
+    double* h = reinterpret_cast<double*>(ctx->h_offs);
+    CK(cudaMemcpyAsync(h, p->d_r, n_r * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_J) CK(cudaMemcpyAsync(h + n_r, p->d_J, n_J * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    memcpy(r, h, n_r * sizeof(double));
+    if (n_J) memcpy(J, h + n_r, n_J * sizeof(double));
+    return RANDT_OK;
+  }
   if (p->P) CK(cudaMemcpyAsync(r, p->d_r, (size_t)p->P * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   if (J && p->P) CK(cudaMemcpyAsync(J, p->d_J, (size_t)p->P * np * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -1077,6 +1090,14 @@ int randt_eval_fused(randt_ctx* ctx, const randt_problem* cp, int variant, const
   }
   int rc = randt_eval_fused_dev(ctx, p, variant, p->d_poses, loss, mu_per_seg ? p->d_mu : nullptr, want_jac, d_out);
   if (rc) return rc;
+  const size_t n_out = (size_t)p->S * RANDT_FUSED_STRIDE;
+  if (p->S && !direct && n_out * sizeof(double) <= ((size_t)1 << 20)) {      // small result into pageable memory: through the pinned block
+    if (int rc2 = pinned_reserve(ctx, &ctx->h_offs, &ctx->offs_cap, 2 * n_out)) return rc2;
+    CK(cudaMemcpyAsync(ctx->h_offs, p->d_out, n_out * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    memcpy(out, ctx->h_offs, n_out * sizeof(double));
+    return RANDT_OK;
+  }
   if (p->S && !direct) CK(cudaMemcpyAsync(out, p->d_out, (size_t)p->S * RANDT_FUSED_STRIDE * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return RANDT_OK;
