@@ -804,8 +804,9 @@ int randt_associate(randt_ctx* ctx, const randt_map* F, const randt_map* M, cons
     if (e == cudaSuccess) e = cudaMemsetAsync(d_tot, 0, 3 * sizeof(uint32_t), ctx->stream);
     if (e == cudaSuccess) e = launch_associate_single(F->cells, F->n_cells, F->slot, M->cells, n_m, geom, d_p0, k, metric, p->pairs, p->duos, p->duo_recs, p->duo_p0,
                                                       p->duo_overflow, ovf_cap, p->cells_m, p->cells_f, d_tot, nullptr, nullptr, 0.0, nullptr, ctx->stream, &nl1);
-    uint32_t h_tot[3] = {0, 0, 0};
-    if (e == cudaSuccess) e = cudaMemcpyAsync(h_tot, d_tot, sizeof(h_tot), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && pinned_reserve(ctx, &ctx->h_offs, &ctx->offs_cap, 4) != RANDT_OK) e = cudaErrorMemoryAllocation;
+    uint32_t* h_tot = ctx->h_offs;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_tot, d_tot, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     dev_free(d_p0); dev_free(d_tot);
     if (e != cudaSuccess) { int rc1 = fail(ctx, RANDT_E_CUDA, "randt_associate (single map)", e); free_problem(p); return rc1; }
@@ -1409,6 +1410,16 @@ int randt_register_batch_weighted(randt_ctx* ctx, const randt_problem* cp, int v
   }
   int rc = register_batch_impl(ctx, p, variant, p->lm_poses, loss, weight_per_seg ? p->lm_weight : nullptr, opt, p->lm_result);
   if (rc) return rc;
+  const size_t n_po = (size_t)S * np, n_re = (size_t)S * RANDT_REG_STRIDE;
+  if ((n_po + n_re) * sizeof(double) <= ((size_t)1 << 20)) {       // small batches: both tables through the pinned block, one wait
+    if (int rc2 = pinned_reserve(ctx, &ctx->h_offs, &ctx->offs_cap, 2 * (n_po + n_re))) return rc2;
+    double* h = reinterpret_cast<double*>(ctx->h_offs);
+    CK(cudaMemcpyAsync(h, p->lm_poses, n_po * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h + n_po, p->lm_result, n_re * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    memcpy(poses, h, n_po * sizeof(double)); memcpy(result, h + n_po, n_re * sizeof(double));
+    return RANDT_OK;
+  }
   CK(cudaMemcpyAsync(poses, p->lm_poses, (size_t)S * np * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(result, p->lm_result, (size_t)S * RANDT_REG_STRIDE * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
