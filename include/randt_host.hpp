@@ -16,6 +16,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <deque>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -113,6 +114,21 @@ struct NDTMatcherParameters {
   bool use_constant_velocity_model = true;
   double csm_window_linear = 4.5, csm_window_angular = 0.45, csm_linear_step = 0.4, csm_cost_threshold = 0.82, csm_max_px_accurate_range = 4.0;
   int csm_n_iter = 2;
+  // the host factors of the joint window problem (ndt_slam_parameters.h:53-58,75): Eigen::Matrix<double,8,8> motion_sqrtI, entry (i, j)
+  // at [i * 8 + j] (NDTSlam::readParameters maps the yaml list column-major, ndt_slam.cpp:556 — the shipped matrices are diagonal)
+  double motion_sqrtI[64] = {1, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0,
+                             0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 1};
+  double covariance_scaling_factor = 25.0;
+  double weight_imu = 64.0, weight_imu_bias = 750000.1;
+  bool use_imu = false;
+};
+
+// what the last estimateTransformCeres call did (the reference keeps only total_optimization_time_; these are for tests and tracing)
+struct WindowSummary {
+  int status = 0;            // 0 solved, 1 nothing to solve (fewer than two states or no NDT residual block: the reference would read an empty vector)
+  int rejected = 0;          // the rejection gate of ndt_matcher.cpp:408-422 fired
+  int gnc_solves = 0, total_iterations = 0, n_free_states = 0, n_tangent = 0, evaluations = 0;
+  double final_cost = 0, mu_first = 0, max_residual = 0;
 };
 
 class RANDT_API Context {
@@ -211,6 +227,27 @@ class RANDT_API Matcher {
   // Matcher::addNDTFactor as one batched cost function (single map pair)
   std::unique_ptr<NdtCostFunction> addNDTFactor(const SE2d& initial_guess, const Map& fixed_ndt, const Map& moving_ndt,
                                                 bool use_intensity_as_dimension, int n_neighbours) const;
+  // Matcher::estimateTransformCeres (ndt_matcher.cpp:322-424), same arguments: the joint problem over the last smoothing_steps states of
+  // `trajectory` (the state before them is constant): per free state the NDT residual blocks of its scan (moving_ndts.end()[-i]) against
+  // every fixed map, associated at the state's pose; the motion-model factor between consecutive states (MotionModelFactorSE2 /
+  // MotionModelFactor, ceres_residuals.h:554-679); with use_imu the relative yaw factor (RotationalResidualSE2 / RotationalResidual,
+  // :307-370) and the IMU bias blocks; the acceleration blocks are constant under use_constant_velocity_model; GNC loop of :382-397 with
+  // ScaledLoss(Barron(scale, convexity, mu), ndt_weight / (n_cells k)), n_cells = the window's moving cells; ceres' trust-region
+  // Levenberg-Marquardt on the joint tangent space (Sophus::Manifold<SE2> for the poses when optimize_on_manifold), DENSE_QR replaced by
+  // the damped normal equations; afterwards the newest state's two representations are synchronised, the rejection gate of :408-422 is
+  // applied and `trans` returns the newest pose.  Every LM evaluation is ONE K3 launch over all window states (the normal equations of
+  // the NDT blocks per state) plus the 8 (+2) host residuals per factor.  The IMU constraint of the factor ending at trajectory.end()[-i]
+  // is imu_constraints_.end()[-i-1] as in the reference (:352), 0 where that reads before the first element.
+  void estimateTransformCeres(SE2d& trans, std::vector<State>& trajectory, const double& initial_angle_guess, const double& stamp,
+                              const std::deque<Map>& fixed_ndts, const std::deque<Map>& moving_ndts);
+  const WindowSummary& lastWindowSummary() const { return window_summary_; }
+  // ceres' convergence tolerances for the window solve (<= 0: Solver::Options defaults 1e-6 / 1e-8 / 1e-10)
+  void setWindowTolerances(double function_tolerance, double parameter_tolerance, double gradient_tolerance) {
+    window_tol_[0] = function_tolerance; window_tol_[1] = parameter_tolerance; window_tol_[2] = gradient_tolerance;
+  }
+  // the same with the IMU constraints given explicitly (imu[j] belongs to the factor ending at the j-th free state, oldest first)
+  void solveWindow(SE2d& trans, std::vector<State>& trajectory, const std::vector<const Map*>& fixed_ndts,
+                   const std::vector<const Map*>& moving_window, const std::vector<double>& imu);
   // The NDT part of Matcher::estimateTransformCeres (ndt_matcher.cpp:321-424) for the newest state of the window: residual blocks
   // of the moving scan against EVERY fixed map (the current submap, plus the previous one while they overlap: local_fuser.cpp:129-138)
   // in the reference's block order, loss ScaledLoss(Barron(loss_function_scale, convexity, mu), ndt_weight / (n_cells k)) (:392), the GNC
@@ -237,6 +274,8 @@ class RANDT_API Matcher {
   NDTMatcherParameters parameters_;
   std::vector<double> imu_constraints_;
   State X_next_;
+  WindowSummary window_summary_;
+  double window_tol_[3] = {0.0, 0.0, 0.0};
 };
 
 }  // namespace randt
@@ -276,5 +315,23 @@ RANDT_API int randt_hostapi_build_schedule(const uint32_t* duo_off, uint32_t n_s
                                            uint32_t* woff_b, uint32_t* tile_rec_begin, uint32_t* tile_duo_begin, uint32_t* first);
 /* predict (se2_model == 0) / predictSE2 (se2_model != 0) on one state: state12 = [cos, sin, tx, ty, pos_x, pos_y, rot, vx, vy, omega, ax, ay] in and out */
 RANDT_API void randt_hostapi_predict(int se2_model, const double* state12, double raw_dt, double* out12);
+/* The host factors of the window problem without a device (tests): the motion-model (+ IMU) factors over W + 1 states
+ * (states [(W + 1)][14]: cos, sin, tx, ty, pos_x, pos_y, rot, vx, vy, omega, ax, ay, imu_bias, stamp; the first one constant), evaluated
+ * at the states as given: cost, tangent gradient g [nt] and J^T J H [nt * nt] in the solver's parameter order (first state: lin_vel 2 |
+ * rot_vel 1 | lin_acc 2 unless constant velocity — only its pose and bias are constant, ndt_matcher.cpp:304-320; every later state: pose 3 |
+ * lin_vel 2 | rot_vel 1 | lin_acc 2 unless constant velocity | imu_bias 1 with use_imu).  params as in randt_hostapi_window_solve.
+ * Returns nt (or a negative error). */
+RANDT_API int randt_hostapi_window_factors(const double* states, uint32_t W, const double* imu, const double* params80, double* cost, double* g,
+                                           double* H);
+/* Matcher::estimateTransformCeres over scans given as points: fixed scan f is voxelised and moved by fixed_pose4[f] (one fixed map each);
+ * window scan w (oldest first, W of them) is voxelised as it is.  states [(W + 1)][14] in / out, trans4 in / out.  params80 [16 + 64]: k,
+ * gnc_steps, max_iteration, loss_scale, alpha, divisor, ndt_weight, manifold, constant_velocity, use_imu, weight_imu, weight_imu_bias,
+ * reject_translation, reject_rotation, use_intensity, (reserved), then covariance_scaling_factor * motion_sqrtI, entry (i, j) at [i * 8 + j].
+ * tolerances3 (may be NULL): function, parameter, gradient tolerance.  out10: status, rejected, gnc_solves, total_iterations, final_cost,
+ * mu_first, max_residual, n_tangent, evaluations, n_cells of the window. */
+RANDT_API int randt_hostapi_window_solve(int device, const randt_grid_params* gp, const float* const* fixed_pts4, const uint32_t* n_fixed_pts,
+                                         const double* fixed_pose4, uint32_t n_fixed, const float* const* window_pts4, const uint32_t* n_window_pts,
+                                         uint32_t W, double* states, const double* imu, const double* params80, const double* tolerances3,
+                                         double* trans4, double* out10);
 RANDT_API const char* randt_hostapi_last_error(void);
 }

@@ -7,6 +7,7 @@
 #include <atomic>
 
 #include "lm_oracle.h"
+#include "window_oracle.h"
 
 using namespace orc;
 
@@ -252,6 +253,68 @@ int orc_filter_scan(const float* raw4, size_t n, float min_d, float max_d, float
   if (out.size() > cap) return -1;
   std::memcpy(out4, out.data(), out.size() * sizeof(Pt4));
   return (int)out.size();
+}
+
+// ---- estimateTransformCeres window problem (window_oracle.h) ----------------------------------------------------------
+// params [16 + 64]: k, gnc_steps, max_iteration, loss_scale, alpha, divisor, ndt_weight, manifold, constant_velocity, use_imu, weight_imu,
+// weight_imu_bias, reject_translation, reject_rotation, variant, (reserved), then covariance_scaling_factor * motion_sqrtI row-major.
+// states [(W + 1)][14]: cos, sin, tx, ty, pos_x, pos_y, rot, vx, vy, omega, ax, ay, imu_bias, stamp — oldest (constant) state first.
+static void window_fill(WindowProblem& wp, const float* cells_m, const float* cells_f, const uint32_t* im, const uint32_t* jf, const uint32_t* seg_off,
+                        int W, const double* states, const double* imu, const double* params) {
+  WindowParams& P = wp.P;
+  P.k = (int)params[0]; P.gnc_steps = (int)params[1]; P.max_iteration = (int)params[2]; P.loss_scale = params[3]; P.alpha = params[4];
+  P.divisor = params[5]; P.ndt_weight = params[6]; P.manifold = params[7] != 0.0; P.constant_velocity = params[8] != 0.0;
+  P.use_imu = params[9] != 0.0; P.weight_imu = params[10]; P.weight_imu_bias = params[11]; P.reject_translation = params[12];
+  P.reject_rotation = params[13]; P.variant = (int)params[14];
+  for (int i = 0; i < 64; ++i) P.sqrtI[i] = params[16 + i];
+  wp.st.resize(W + 1);
+  for (int j = 0; j <= W; ++j) {
+    const double* s = states + (size_t)j * WSTATE_DOUBLES; WState& o = wp.st[j];
+    for (int i = 0; i < 4; ++i) o.pose[i] = s[i];
+    o.pos[0] = s[4]; o.pos[1] = s[5]; o.rot = s[6]; o.lin_vel[0] = s[7]; o.lin_vel[1] = s[8]; o.rot_vel = s[9];
+    o.lin_acc[0] = s[10]; o.lin_acc[1] = s[11]; o.imu_bias = s[12]; o.stamp = s[13];
+  }
+  wp.imu.assign(W, 0.0);
+  if (imu) for (int j = 0; j < W; ++j) wp.imu[j] = imu[j];
+  wp.cm = reinterpret_cast<const Cell12*>(cells_m); wp.cf = reinterpret_cast<const Cell12*>(cells_f);
+  wp.im = im; wp.jf = jf;
+  wp.seg_off.assign(seg_off, seg_off + W + 1);
+  wp.layout();
+}
+static void window_store(const WindowProblem& wp, double* states) {
+  for (size_t j = 0; j < wp.st.size(); ++j) {
+    double* s = states + j * WSTATE_DOUBLES; const WState& o = wp.st[j];
+    for (int i = 0; i < 4; ++i) s[i] = o.pose[i];
+    s[4] = o.pos[0]; s[5] = o.pos[1]; s[6] = o.rot; s[7] = o.lin_vel[0]; s[8] = o.lin_vel[1]; s[9] = o.rot_vel;
+    s[10] = o.lin_acc[0]; s[11] = o.lin_acc[1]; s[12] = o.imu_bias; s[13] = o.stamp;
+  }
+}
+// one evaluation of the whole problem at the given states: cost, tangent gradient [nt], tangent J^T J [nt * nt]; returns nt
+int orc_window_evaluate(const float* cells_m, const float* cells_f, const uint32_t* im, const uint32_t* jf, const uint32_t* seg_off, int W,
+                        const double* states, const double* imu, const double* params, int loss_kind, double mu, double weight, double* cost,
+                        double* g, double* H, double* max_raw) {
+  WindowProblem wp;
+  window_fill(wp, cells_m, cells_f, im, jf, seg_off, W, states, imu, params);
+  std::vector<double> x(wp.n_amb());
+  wp.pack(x.data());
+  Loss loss = make_loss(loss_kind, wp.P.loss_scale, wp.P.alpha, mu, weight);
+  wp.evaluate(x.data(), loss, cost, g, H, max_raw);
+  return wp.n_tan();
+}
+// out8: status, rejected, gnc_solves, total_iterations, final_cost, mu_first, max_residual, n_tangent
+int orc_window_solve(const float* cells_m, const float* cells_f, const uint32_t* im, const uint32_t* jf, const uint32_t* seg_off, int W,
+                     double* states, const double* imu, const double* params, size_t n_cells_total, double* trans4, double* out8) {
+  WindowProblem wp;
+  window_fill(wp, cells_m, cells_f, im, jf, seg_off, W, states, imu, params);
+  LmOptions opt; opt.max_num_iterations = wp.P.max_iteration;
+  if (g_function_tol > 0.0) opt.function_tolerance = g_function_tol;
+  if (g_parameter_tol > 0.0) opt.parameter_tolerance = g_parameter_tol;
+  if (g_gradient_tol > 0.0) opt.gradient_tolerance = g_gradient_tol;
+  const WindowResult R = window_solve(wp, trans4, opt, n_cells_total);
+  window_store(wp, states);
+  out8[0] = R.status; out8[1] = R.rejected; out8[2] = R.gnc_solves; out8[3] = R.total_iterations; out8[4] = R.final_cost; out8[5] = R.mu_first;
+  out8[6] = R.max_residual; out8[7] = R.n_tangent;
+  return R.status;
 }
 
 }  // extern "C"

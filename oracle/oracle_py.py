@@ -31,7 +31,7 @@ def _host_sig():
 
 def build(force=False):
     """Compile the C++ restatement (g++, seconds).  Safe to call repeatedly."""
-    srcs = [os.path.join(_HERE, f) for f in ("oracle_capi.cpp", "ndt_oracle.h", "lm_oracle.h", "jet.h", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("oracle_capi.cpp", "ndt_oracle.h", "lm_oracle.h", "window_oracle.h", "jet.h", "Makefile")]
     sig_path = os.path.join(_HERE, "_build", "host_sig.txt")
     sig = _host_sig()
     try:
@@ -94,6 +94,9 @@ def _sig(L):
     L.orc_filter_scan.restype = i; L.orc_filter_scan.argtypes = [pf, sz, f, f, f, d, pf, pf, sz, C.POINTER(sz)]
     L.orc_se2_plus.restype = None; L.orc_se2_plus.argtypes = [pd, pd, pd]
     L.orc_se2_plus_jacobian.restype = None; L.orc_se2_plus_jacobian.argtypes = [pd, pd]
+    L.orc_set_tolerances.restype = None; L.orc_set_tolerances.argtypes = [d, d, d]
+    L.orc_window_evaluate.restype = i; L.orc_window_evaluate.argtypes = [pf, pf, pu, pu, pu, i, pd, pd, pd, i, d, d, pd, pd, pd, pd]
+    L.orc_window_solve.restype = i; L.orc_window_solve.argtypes = [pf, pf, pu, pu, pu, i, pd, pd, pd, sz, pd, pd]
 
 
 def _f32(a):
@@ -325,3 +328,41 @@ def filter_scan(raw4, min_range, max_range, min_intensity, beam_thr, tf12=None):
                               _p(tf, C.c_float), _p(out, C.c_float), len(out), C.byref(npk))
     assert n >= 0
     return out[:n].copy(), int(npk.value)
+
+
+def window_evaluate(states14, params80, imu=None, cells_m=None, cells_f=None, im=None, jf=None, seg_off=None, loss_kind=LOSS_NONE, mu=1.0, weight=1.0):
+    """One evaluation of estimateTransformCeres' joint problem at the given states [(W + 1), 14] (window_oracle.h): cost, tangent gradient,
+    tangent J^T J, max raw NDT residual.  Without pair lists only the motion-model / IMU factors are evaluated."""
+    st = _f64(states14).reshape(-1, 14)
+    W = len(st) - 1
+    cm = _f32(cells_m if cells_m is not None else np.zeros((1, 12))); cf = _f32(cells_f if cells_f is not None else np.zeros((1, 12)))
+    im_ = _u32(im if im is not None else np.zeros(1)); jf_ = _u32(jf if jf is not None else np.zeros(1))
+    so = _u32(seg_off if seg_off is not None else np.zeros(W + 1))
+    imu_ = _f64(imu if imu is not None else np.zeros(max(W, 1)))
+    cap = 10 * (W + 1)
+    cost = np.zeros(1); g = np.zeros(cap); H = np.zeros(cap * cap); mr = np.zeros(1)
+    nt = lib().orc_window_evaluate(_p(cm, C.c_float), _p(cf, C.c_float), _p(im_, C.c_uint32), _p(jf_, C.c_uint32), _p(so, C.c_uint32), W,
+                                   _p(st, C.c_double), _p(imu_, C.c_double), _p(_f64(params80), C.c_double), int(loss_kind), float(mu), float(weight),
+                                   _p(cost, C.c_double), _p(g, C.c_double), _p(H, C.c_double), _p(mr, C.c_double))
+    return float(cost[0]), g[:nt].copy(), H[: nt * nt].reshape(nt, nt).copy(), float(mr[0])
+
+
+def window_solve(states14, params80, trans, cells_m, cells_f, im, jf, seg_off, n_cells_total, imu=None, tolerances=None):
+    """Matcher::estimateTransformCeres restated (window_oracle.h) on pre-associated pair lists (segment w = the blocks of window state w + 1)
+    -> (states [(W + 1), 14], trans [4], summary dict)"""
+    st = _f64(states14).reshape(-1, 14).copy()
+    W = len(st) - 1
+    t = _f64(trans).reshape(4).copy()
+    imu_ = _f64(imu if imu is not None else np.zeros(max(W, 1)))
+    out = np.zeros(8)
+    if tolerances is not None:
+        lib().orc_set_tolerances(C.c_double(tolerances[0]), C.c_double(tolerances[1]), C.c_double(tolerances[2]))
+    try:
+        lib().orc_window_solve(_p(_f32(cells_m), C.c_float), _p(_f32(cells_f), C.c_float), _p(_u32(im), C.c_uint32), _p(_u32(jf), C.c_uint32),
+                               _p(_u32(seg_off), C.c_uint32), W, _p(st, C.c_double), _p(imu_, C.c_double), _p(_f64(params80), C.c_double),
+                               C.c_size_t(int(n_cells_total)), _p(t, C.c_double), _p(out, C.c_double))
+    finally:
+        if tolerances is not None:
+            lib().orc_set_tolerances(C.c_double(0.0), C.c_double(0.0), C.c_double(0.0))
+    keys = ("status", "rejected", "gnc_solves", "total_iterations", "final_cost", "mu_first", "max_residual", "n_tangent")
+    return st, t, dict(zip(keys, out.tolist()))

@@ -14,6 +14,8 @@ OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "librandt_gpu.so")
 HOST_LIB = os.path.join(HERE, "librandt_host.so")       # C++ mirror of the reference's Map / Matcher surface (host/randt_host.cpp)
 HOST_SRC = os.path.join(HERE, "host", "randt_host.cpp")
+HOST_SRCS = [HOST_SRC, os.path.join(HERE, "host", "window_solver.cpp")]   # + the joint window problem of estimateTransformCeres
+HOST_DEPS = HOST_SRCS + [os.path.join(HERE, "host", "window_solver.hpp")]
 HOST_HDR = os.path.join(HERE, "..", "include", "randt_host.hpp")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -65,12 +67,12 @@ def build_all(force=False, verbose=False):
     if force or jobs or _newer(LIB, objs):
         run([nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart_static", "-lpthread", "-ldl", "-lrt"])
     # host layer: plain C++17 over the C-ABI (no CUDA headers), linked against librandt_gpu.so next to it
-    if force or _newer(HOST_LIB, [HOST_SRC, HOST_HDR, LIB, os.path.join(CSRC, "schedule.hpp")]):
+    if force or _newer(HOST_LIB, HOST_DEPS + [HOST_HDR, LIB, os.path.join(CSRC, "schedule.hpp")]):
         cxx = os.environ.get("CXX", "g++")
         # RANDT_HOST_CXXFLAGS: e.g. "-I/usr/include/eigen3 -I<ceres>/include" so that the host layer is compiled against the real
         # ceres/cost_function.h of the tree it is going to be linked into
         run([cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-Wall"] + os.environ.get("RANDT_HOST_CXXFLAGS", "").split() +
-            ["-o", HOST_LIB, HOST_SRC,
+            ["-o", HOST_LIB] + HOST_SRCS + [
              "-L" + HERE, "-lrandt_gpu", "-Wl,-rpath,$ORIGIN"])
     return LIB
 

@@ -11,6 +11,7 @@
 #include <tuple>
 
 #include "../csrc/schedule.hpp"   // the K3 schedule builder (plain C++), exposed for the CPU tests
+#include "window_solver.hpp"
 
 namespace randt {
 
@@ -426,6 +427,201 @@ double Matcher::estimateLoopConstraint(SE2d& trans, const Map& old_ndt, Map& new
   return s[0];
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Matcher::estimateTransformCeres: the joint window problem
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+// addMotionModelFactor (ndt_matcher.cpp:60-110) / addImuFactor (:144-181) over the blocks addMotionParameterBlock (:290-314) and
+// addImuParameterBlock (:316-320) registered; the acceleration blocks are constant under the constant-velocity model, the oldest
+// state's blocks are all constant
+struct WindowBlocks { int pose = -1, pos = -1, rot = -1, lin_vel = -1, rot_vel = -1, lin_acc = -1, imu_bias = -1; };
+
+WindowBlocks addMotionParameterBlock(window::JointProblem& problem, bool manifold, State& X, bool set_constant, bool constant_velocity) {
+  WindowBlocks b;
+  if (manifold) b.pose = problem.addParameterBlock(X.pose.data(), 4, true);
+  else { b.pos = problem.addParameterBlock(X.pos, 2, false); b.rot = problem.addParameterBlock(&X.rot, 1, false); }
+  b.lin_vel = problem.addParameterBlock(X.lin_vel, 2, false);
+  b.rot_vel = problem.addParameterBlock(&X.rot_vel, 1, false);
+  b.lin_acc = problem.addParameterBlock(X.lin_acc, 2, false);
+  if (constant_velocity) problem.setParameterBlockConstant(b.lin_acc);
+  if (set_constant) {
+    // the reference pins only the pose of the oldest state (:304-312) ...
+    if (manifold) problem.setParameterBlockConstant(b.pose);
+    else { problem.setParameterBlockConstant(b.pos); problem.setParameterBlockConstant(b.rot); }
+  }
+  return b;
+}
+
+void addMotionModelFactor(window::JointProblem& problem, bool manifold, const WindowBlocks& a, const WindowBlocks& b, double dt, const double* sqrtI) {
+  window::HostFactor f;
+  f.nres = 8;
+  if (manifold) {
+    f.blocks = {a.pose, a.lin_vel, a.rot_vel, a.lin_acc, b.pose, b.lin_vel, b.rot_vel, b.lin_acc};
+    f.eval = [dt, sqrtI](const window::D20* const* p, window::D20* r) { window::MotionModelFactorSE2(dt, sqrtI, p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], r); };
+  } else {
+    f.blocks = {a.pos, a.rot, a.lin_vel, a.rot_vel, a.lin_acc, b.pos, b.rot, b.lin_vel, b.rot_vel, b.lin_acc};
+    f.eval = [dt, sqrtI](const window::D20* const* p, window::D20* r) { window::MotionModelFactor(dt, sqrtI, p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], p[8], p[9], r); };
+  }
+  problem.addFactor(std::move(f));
+}
+
+void addImuFactor(window::JointProblem& problem, bool manifold, const WindowBlocks& a, const WindowBlocks& b, double imu_constraint, double weight_imu,
+                  double dt, double weight_imu_bias) {
+  window::HostFactor f;
+  f.nres = 2;
+  if (manifold) {
+    f.blocks = {a.pose, b.pose, a.imu_bias, b.imu_bias};
+    f.eval = [=](const window::D20* const* p, window::D20* r) { window::RotationalResidualSE2(imu_constraint, weight_imu, dt, weight_imu_bias, p[0], p[1], p[2], p[3], r); };
+  } else {
+    f.blocks = {a.rot, b.rot, a.imu_bias, b.imu_bias};
+    f.eval = [=](const window::D20* const* p, window::D20* r) { window::RotationalResidual(imu_constraint, weight_imu, dt, weight_imu_bias, p[0], p[1], p[2], p[3], r); };
+  }
+  problem.addFactor(std::move(f));
+}
+
+// registers the blocks and host factors of the window states[0 .. W] (states[0] constant); returns the blocks per state
+std::vector<WindowBlocks> buildWindowFactors(window::JointProblem& problem, const NDTMatcherParameters& p, bool manifold, State* const* states, int W,
+                                             const double* imu, const double* sqrtI_scaled) {
+  std::vector<WindowBlocks> blocks((size_t)W + 1);
+  blocks[0] = addMotionParameterBlock(problem, manifold, *states[0], true, p.use_constant_velocity_model);
+  if (p.use_imu) { blocks[0].imu_bias = problem.addParameterBlock(&states[0]->imu_bias, 1, false); problem.setParameterBlockConstant(blocks[0].imu_bias); }
+  for (int j = 1; j <= W; ++j) {
+    blocks[j] = addMotionParameterBlock(problem, manifold, *states[j], false, p.use_constant_velocity_model);
+    if (p.use_imu) blocks[j].imu_bias = problem.addParameterBlock(&states[j]->imu_bias, 1, false);
+    const double dt = states[j]->stamp - states[j - 1]->stamp;
+    addMotionModelFactor(problem, manifold, blocks[j - 1], blocks[j], dt, sqrtI_scaled);
+    if (p.use_imu) addImuFactor(problem, manifold, blocks[j - 1], blocks[j], imu[j - 1], p.weight_imu, dt, p.weight_imu_bias);
+  }
+  return blocks;
+}
+}  // namespace
+
+void Matcher::solveWindow(SE2d& trans, std::vector<State>& trajectory, const std::vector<const Map*>& fixed_ndts,
+                          const std::vector<const Map*>& moving_window, const std::vector<double>& imu) {
+  window_summary_ = WindowSummary();
+  const bool manifold = parameters_.optimize_on_manifold && !parameters_.use_analytic_expressions_for_optimization;
+  const bool use_intensity = parameters_.use_intensity_as_dimension;
+  const int k = parameters_.n_results_kd_lookup;
+  if (trajectory.size() < 2 || fixed_ndts.empty()) { window_summary_.status = 1; return; }
+  const size_t W = std::min(trajectory.size() - 1, (size_t)parameters_.smoothing_steps);   // ndt_matcher.cpp:343
+  if (moving_window.size() < W) throw Error(RANDT_E_INVALID, "estimateTransformCeres: fewer moving maps than window states");
+  if (parameters_.use_imu && imu.size() < W) throw Error(RANDT_E_INVALID, "estimateTransformCeres: one IMU constraint per window factor");
+  const double prior_translation[2] = {trans.v[2], trans.v[3]};
+  const double prior_rotation = trans.angle();
+
+  // ---- NDT residual blocks: per free state (oldest first), per fixed map, addNDTFactor at the state's own pose (:356-359)
+  struct Problems { std::vector<randt_problem*> v; ~Problems() { for (randt_problem* q : v) randt_problem_destroy(q); } } probs;
+  std::vector<float> cells_m, cells_f;
+  std::vector<uint32_t> pair_m, pair_f, seg_off(W + 1, 0);
+  size_t n_cells = 0;
+  for (size_t j = 1; j <= W; ++j) {
+    State& X = trajectory[trajectory.size() - 1 - W + j];
+    const Map& moving = *moving_window[moving_window.size() - W + (j - 1)];
+    if (moving.n_maps() != 1) throw Error(RANDT_E_INVALID, "estimateTransformCeres takes single maps");
+    const SE2d guess = X.pose;   // the association always starts from the Lie-group representation (:357), whatever is optimised
+    for (const Map* fixed : fixed_ndts) {
+      randt_problem* q = associate(&guess, *fixed, moving, use_intensity, k);
+      probs.v.push_back(q);
+      uint32_t S = 0, P = 0, nm = 0, nf = 0;
+      ctx_->check(randt_problem_info(q, &S, &P, &nm, &nf));
+      std::vector<uint32_t> pm(P), pf(P);
+      std::vector<float> cm((size_t)nm * 12), cf((size_t)nf * 12);
+      if (P) ctx_->check(randt_problem_download(ctx_->get(), q, pm.data(), pf.data(), nullptr));
+      ctx_->check(randt_problem_download_cells(ctx_->get(), q, nm ? cm.data() : nullptr, nf ? cf.data() : nullptr));
+      const uint32_t mb = (uint32_t)(cells_m.size() / 12), fb = (uint32_t)(cells_f.size() / 12);
+      for (uint32_t i = 0; i < P; ++i) { pair_m.push_back(pm[i] + mb); pair_f.push_back(pf[i] + fb); }
+      cells_m.insert(cells_m.end(), cm.begin(), cm.end());
+      cells_f.insert(cells_f.end(), cf.begin(), cf.end());
+    }
+    seg_off[j] = (uint32_t)pair_m.size();
+    n_cells += moving.get_n_cells();   // :361
+  }
+  if (pair_m.empty() || n_cells == 0) { window_summary_.status = 1; return; }
+  randt_problem* merged = nullptr;
+  ctx_->check(randt_problem_create(ctx_->get(), cells_m.data(), (uint32_t)(cells_m.size() / 12), cells_f.data(), (uint32_t)(cells_f.size() / 12),
+                                   pair_m.data(), pair_f.data(), (uint32_t)pair_m.size(), seg_off.data(), (uint32_t)W, &merged));
+  probs.v.push_back(merged);
+
+  // ---- parameter blocks and host factors
+  double sqrtI[64];
+  for (int i = 0; i < 64; ++i) sqrtI[i] = parameters_.covariance_scaling_factor * parameters_.motion_sqrtI[i];   // :67
+  window::JointProblem problem;
+  std::vector<State*> states(W + 1);
+  for (size_t j = 0; j <= W; ++j) states[j] = &trajectory[trajectory.size() - 1 - W + j];
+  const std::vector<WindowBlocks> blocks = buildWindowFactors(problem, parameters_, manifold, states.data(), (int)W, imu.data(), sqrtI);
+  window::NdtTerm term;
+  term.ctx = ctx_->get(); term.problem = merged; term.variant = variant(use_intensity); term.np = manifold ? 4 : 3;
+  for (size_t j = 1; j <= W; ++j) {
+    if (manifold) term.seg_blocks.push_back({blocks[j].pose});
+    else term.seg_blocks.push_back({blocks[j].pos, blocks[j].rot});
+  }
+  problem.setNdtTerm(term);
+  problem.finalize();
+
+  randt_solver_options opt;
+  randt_solver_options_default(&opt);
+  opt.max_num_iterations = parameters_.max_iteration;
+  if (window_tol_[0] > 0.0) opt.function_tolerance = window_tol_[0];
+  if (window_tol_[1] > 0.0) opt.parameter_tolerance = window_tol_[1];
+  if (window_tol_[2] > 0.0) opt.gradient_tolerance = window_tol_[2];
+
+  // ---- GNC loop (:382-397)
+  std::vector<double> x((size_t)problem.numAmbient());
+  problem.gather(x.data());
+  double raw_cost = 0.0, max_residual = 0.0;
+  if (!problem.evaluate(x.data(), nullptr, false, &raw_cost, nullptr, nullptr, &max_residual))
+    throw Error(RANDT_E_INVALID, std::string("estimateTransformCeres: evaluation failed: ") + randt_last_error(ctx_->get()));
+  double gnc_mu = 2.0 * std::pow(max_residual, 2) / std::pow(parameters_.loss_function_scale, 2);
+  gnc_mu = std::min(gnc_mu, std::pow(parameters_.gnc_control_parameter_divisor, parameters_.gnc_steps - 1));
+  window_summary_.mu_first = gnc_mu; window_summary_.max_residual = max_residual;
+  window_summary_.n_free_states = (int)W; window_summary_.n_tangent = problem.numTangent();
+  window::MinimizerSummary last;
+  do {
+    gnc_mu = std::max(gnc_mu, 1.0);
+    randt_loss loss;
+    loss.kind = RANDT_LOSS_BARRON; loss.scale = parameters_.loss_function_scale; loss.alpha = parameters_.loss_function_convexity; loss.mu = gnc_mu;
+    loss.weight = parameters_.ndt_weight / (double)(n_cells * (size_t)k);
+    last = window::minimize(problem, loss, opt, x.data());
+    window_summary_.gnc_solves++;
+    window_summary_.total_iterations += last.num_iterations;
+    gnc_mu /= parameters_.gnc_control_parameter_divisor;
+  } while (gnc_mu > 1.0 / std::sqrt(parameters_.gnc_control_parameter_divisor));
+  window_summary_.final_cost = last.final_cost;
+  window_summary_.evaluations = problem.evaluations();
+  problem.scatter(x.data());
+
+  // ---- both representations of the newest state (:399-406), rejection gate (:408-422)
+  State& newest = trajectory.back();
+  if (!manifold) newest.pose = SE2d(newest.rot, newest.pos[0], newest.pos[1]);
+  else { newest.pos[0] = newest.pose.v[2]; newest.pos[1] = newest.pose.v[3]; newest.rot = newest.pose.angle(); }
+  SE2d inv_rot; inv_rot.v[0] = newest.pose.v[0]; inv_rot.v[1] = -newest.pose.v[1];
+  const double rot_diff = (inv_rot * SE2d(prior_rotation, 0.0, 0.0)).angle();
+  if (std::fabs(newest.pose.v[2] - prior_translation[0]) > parameters_.pose_reject_translation ||
+      std::fabs(newest.pose.v[3] - prior_translation[1]) > parameters_.pose_reject_translation || std::fabs(rot_diff) > parameters_.pose_reject_rotation) {
+    const State& before = trajectory[trajectory.size() - 2];
+    window_summary_.rejected = 1;
+    newest.pos[0] = before.pos[0]; newest.pos[1] = before.pos[1]; newest.pose = before.pose; newest.rot = before.rot;
+    newest.lin_vel[0] = newest.lin_vel[1] = 0.0; newest.rot_vel = 0.0; newest.lin_acc[0] = newest.lin_acc[1] = 0.0;
+    newest.imu_bias = before.imu_bias;
+  }
+  trans = newest.pose;
+}
+
+void Matcher::estimateTransformCeres(SE2d& trans, std::vector<State>& trajectory, const double& /*initial_angle_guess*/, const double& /*stamp*/,
+                                     const std::deque<Map>& fixed_ndts, const std::deque<Map>& moving_ndts) {
+  std::vector<const Map*> fixed, moving;
+  for (const Map& m : fixed_ndts) fixed.push_back(&m);
+  for (const Map& m : moving_ndts) moving.push_back(&m);
+  const size_t W = trajectory.size() < 2 ? 0 : std::min(trajectory.size() - 1, (size_t)parameters_.smoothing_steps);
+  // the factor ending at trajectory.end()[-i] reads imu_constraints_.end()[-i-1] (:352); before the first element: 0
+  std::vector<double> imu(W, 0.0);
+  for (size_t i = 1; i <= W; ++i) {
+    const size_t back = i + 1;
+    if (back <= imu_constraints_.size()) imu[W - i] = imu_constraints_[imu_constraints_.size() - back];
+  }
+  solveWindow(trans, trajectory, fixed, moving, imu);
+}
+
 double Matcher::estimateTransformGlobalBNB(SE2d& trans, const Map& fixed_ndt, Map& moving_ndt, bool use_intensity_as_dimension, double scale,
                                            double search_window_size_linear, double search_window_size_angular) const {
   search_window_size_linear = std::min(search_window_size_linear, parameters_.csm_window_linear);
@@ -653,6 +849,96 @@ void randt_hostapi_predict(int se2_model, const double* s, double raw_dt, double
   if (se2_model) randt::predictSE2(a, raw_dt, b); else randt::predict(a, raw_dt, b);
   std::memcpy(out, b.pose.v, 4 * sizeof(double));
   out[4] = b.pos[0]; out[5] = b.pos[1]; out[6] = b.rot; out[7] = b.lin_vel[0]; out[8] = b.lin_vel[1]; out[9] = b.rot_vel; out[10] = b.lin_acc[0]; out[11] = b.lin_acc[1];
+}
+
+namespace {
+void state_from14(const double* s, randt::State& X) {
+  std::memcpy(X.pose.v, s, 4 * sizeof(double));
+  X.pos[0] = s[4]; X.pos[1] = s[5]; X.rot = s[6]; X.lin_vel[0] = s[7]; X.lin_vel[1] = s[8]; X.rot_vel = s[9];
+  X.lin_acc[0] = s[10]; X.lin_acc[1] = s[11]; X.imu_bias = s[12]; X.stamp = s[13];
+}
+void state_to14(const randt::State& X, double* s) {
+  std::memcpy(s, X.pose.v, 4 * sizeof(double));
+  s[4] = X.pos[0]; s[5] = X.pos[1]; s[6] = X.rot; s[7] = X.lin_vel[0]; s[8] = X.lin_vel[1]; s[9] = X.rot_vel;
+  s[10] = X.lin_acc[0]; s[11] = X.lin_acc[1]; s[12] = X.imu_bias; s[13] = X.stamp;
+}
+randt::NDTMatcherParameters matcher_params80(const double* q) {
+  randt::NDTMatcherParameters p;
+  p.n_results_kd_lookup = (int)q[0]; p.gnc_steps = (int)q[1]; p.max_iteration = (int)q[2]; p.loss_function_scale = q[3];
+  p.loss_function_convexity = q[4]; p.gnc_control_parameter_divisor = q[5]; p.ndt_weight = q[6]; p.optimize_on_manifold = q[7] != 0.0;
+  p.use_constant_velocity_model = q[8] != 0.0; p.use_imu = q[9] != 0.0; p.weight_imu = q[10]; p.weight_imu_bias = q[11];
+  p.pose_reject_translation = q[12]; p.pose_reject_rotation = q[13]; p.use_intensity_as_dimension = q[14] != 0.0;
+  p.covariance_scaling_factor = 1.0;   // the caller passes the scaled matrix
+  for (int i = 0; i < 64; ++i) p.motion_sqrtI[i] = q[16 + i];
+  return p;
+}
+}  // namespace
+
+int randt_hostapi_window_factors(const double* states, uint32_t W, const double* imu, const double* params80, double* cost, double* g, double* H) {
+  int nt = 0;
+  const int rc = guarded([&] {
+    const randt::NDTMatcherParameters p = matcher_params80(params80);
+    const bool manifold = p.optimize_on_manifold && !p.use_analytic_expressions_for_optimization;
+    std::vector<randt::State> st((size_t)W + 1);
+    std::vector<randt::State*> ptr((size_t)W + 1);
+    for (uint32_t j = 0; j <= W; ++j) { state_from14(states + 14 * (size_t)j, st[j]); ptr[j] = &st[j]; }
+    std::vector<double> zero(W, 0.0);
+    randt::window::JointProblem problem;
+    randt::buildWindowFactors(problem, p, manifold, ptr.data(), (int)W, imu ? imu : zero.data(), p.motion_sqrtI);
+    problem.finalize();
+    nt = problem.numTangent();
+    std::vector<double> x((size_t)problem.numAmbient());
+    problem.gather(x.data());
+    *cost = 0.0;
+    std::fill(g, g + nt, 0.0); std::fill(H, H + (size_t)nt * nt, 0.0);
+    problem.evaluateHostFactors(x.data(), true, cost, g, H);
+  });
+  return rc == RANDT_OK ? nt : rc;
+}
+
+int randt_hostapi_window_solve(int device, const randt_grid_params* gp, const float* const* fixed_pts4, const uint32_t* n_fixed_pts,
+                               const double* fixed_pose4, uint32_t n_fixed, const float* const* window_pts4, const uint32_t* n_window_pts, uint32_t W,
+                               double* states, const double* imu, const double* params80, const double* tolerances3, double* trans4, double* out10) {
+  return guarded([&] {
+    randt::Context ctx(device);
+    const randt::NDTMapParameters mp = map_params(*gp);
+    std::vector<std::unique_ptr<randt::Map>> maps;
+    std::vector<const randt::Map*> fixed, window;
+    for (uint32_t i = 0; i < n_fixed; ++i) {
+      maps.emplace_back(new randt::Map(ctx, mp));
+      const uint32_t off[2] = {0, n_fixed_pts[i]};
+      maps.back()->addClusters(fixed_pts4[i], off, 1);
+      randt::SE2d T;
+      std::memcpy(T.v, fixed_pose4 + 4 * i, 4 * sizeof(double));
+      maps.back()->transformMap(&T);
+      fixed.push_back(maps.back().get());
+    }
+    size_t n_cells = 0;
+    for (uint32_t w = 0; w < W; ++w) {
+      maps.emplace_back(new randt::Map(ctx, mp));
+      const uint32_t off[2] = {0, n_window_pts[w]};
+      maps.back()->addClusters(window_pts4[w], off, 1);
+      window.push_back(maps.back().get());
+      n_cells += maps.back()->get_n_cells();
+    }
+    randt::NDTMatcherParameters p = matcher_params80(params80);
+    p.smoothing_steps = (int)W;
+    randt::Matcher m(ctx);
+    m.initialize(p);
+    if (tolerances3) m.setWindowTolerances(tolerances3[0], tolerances3[1], tolerances3[2]);
+    std::vector<randt::State> trajectory((size_t)W + 1);
+    for (uint32_t j = 0; j <= W; ++j) state_from14(states + 14 * (size_t)j, trajectory[j]);
+    randt::SE2d t;
+    std::memcpy(t.v, trans4, 4 * sizeof(double));
+    std::vector<double> imu_v(W, 0.0);
+    if (imu) imu_v.assign(imu, imu + W);
+    m.solveWindow(t, trajectory, fixed, window, imu_v);
+    std::memcpy(trans4, t.v, 4 * sizeof(double));
+    for (uint32_t j = 0; j <= W; ++j) state_to14(trajectory[j], states + 14 * (size_t)j);
+    const randt::WindowSummary& ws = m.lastWindowSummary();
+    out10[0] = ws.status; out10[1] = ws.rejected; out10[2] = ws.gnc_solves; out10[3] = ws.total_iterations; out10[4] = ws.final_cost;
+    out10[5] = ws.mu_first; out10[6] = ws.max_residual; out10[7] = ws.n_tangent; out10[8] = ws.evaluations; out10[9] = (double)n_cells;
+  });
 }
 
 int randt_hostapi_export(int device, const randt_grid_params* gp, const float* pts4, uint32_t n_pts, double* mean3, double* cov6, uint32_t cap,

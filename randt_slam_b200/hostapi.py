@@ -19,7 +19,8 @@ def lib():
         capi.lib()   # librandt_gpu.so first (the host library links against it)
         L = C.CDLL(LIB_PATH)
         L.randt_hostapi_last_error.restype = C.c_char_p
-        for name in ("randt_hostapi_loop_constraints", "randt_hostapi_cost_function", "randt_hostapi_bnb", "randt_hostapi_export", "randt_hostapi_odometry", "randt_hostapi_eval_async_loop", "randt_hostapi_build_schedule"):
+        for name in ("randt_hostapi_loop_constraints", "randt_hostapi_cost_function", "randt_hostapi_bnb", "randt_hostapi_export", "randt_hostapi_odometry", "randt_hostapi_eval_async_loop", "randt_hostapi_build_schedule",
+                     "randt_hostapi_window_factors", "randt_hostapi_window_solve"):
             getattr(L, name).restype = C.c_int
         _lib = L
     return _lib
@@ -131,3 +132,48 @@ def predict(state12, raw_dt, se2_model):
     lib().randt_hostapi_predict.restype = None
     lib().randt_hostapi_predict(C.c_int(int(se2_model)), _pf(s), C.c_double(float(raw_dt)), _pf(out))
     return out
+
+
+def window_params(k=2, gnc_steps=2, max_iteration=200, loss_scale=1.0, alpha=-2.0, divisor=1.1, ndt_weight=5000.0, manifold=True,
+                  constant_velocity=True, use_imu=False, weight_imu=64.0, weight_imu_bias=750000.1, reject_translation=5.0, reject_rotation=2.0,
+                  use_intensity=True, covariance_scaling_factor=0.01, motion_sqrtI_diag=(1.0, 1.0, 10.0, 1.0, 3.0, 0.1, 20.0, 60.0)):
+    """The 16 + 64 doubles randt_hostapi_window_solve / window_factors (and the oracle's orc_window_*) read; defaults = parameters_oxford.yaml.
+    Slot 14 is use_intensity here and the functor variant (0 = SE2 + intensity ... 3 = vector xy) on the oracle side: see oracle_variant()."""
+    q = np.zeros(80, np.float64)
+    q[:15] = [k, gnc_steps, max_iteration, loss_scale, alpha, divisor, ndt_weight, float(manifold), float(constant_velocity), float(use_imu), weight_imu,
+              weight_imu_bias, reject_translation, reject_rotation, float(use_intensity)]
+    q[16:] = (covariance_scaling_factor * np.diag(np.asarray(motion_sqrtI_diag, np.float64))).reshape(64)
+    return q
+
+
+def window_factors(states14, params80, imu=None):
+    """The motion-model (+ IMU) factors of the window over states [(W + 1), 14], no device -> (cost, g [nt], H [nt, nt])"""
+    st = np.ascontiguousarray(states14, np.float64).reshape(-1, 14)
+    W = len(st) - 1
+    cap = 10 * (W + 1)
+    g = np.zeros(cap); H = np.zeros(cap * cap); cost = C.c_double(0)
+    im = None if imu is None else np.ascontiguousarray(imu, np.float64)
+    nt = lib().randt_hostapi_window_factors(_pf(st), C.c_uint32(W), _pf(im) if im is not None else None, _pf(np.ascontiguousarray(params80, np.float64)),
+                                            C.byref(cost), _pf(g), _pf(H))
+    if nt < 0:
+        _check(nt)
+    return cost.value, g[:nt].copy(), H[: nt * nt].reshape(nt, nt).copy()
+
+
+def window_solve(gp, fixed_scans, fixed_poses, window_scans, states14, params80, trans, imu=None, tolerances=None, device=0):
+    """Matcher::estimateTransformCeres (joint window problem) over scans given as points -> (states [(W + 1), 14], trans [4], summary dict)"""
+    fs = [np.ascontiguousarray(f, np.float32) for f in fixed_scans]
+    ws = [np.ascontiguousarray(w, np.float32) for w in window_scans]
+    fptr = (C.c_void_p * len(fs))(*[f.ctypes.data for f in fs]); wptr = (C.c_void_p * len(ws))(*[w.ctypes.data for w in ws])
+    nf = np.array([len(f) for f in fs], np.uint32); nw = np.array([len(w) for w in ws], np.uint32)
+    fp = np.ascontiguousarray(fixed_poses, np.float64).reshape(len(fs), 4)
+    st = np.ascontiguousarray(states14, np.float64).reshape(len(ws) + 1, 14).copy()
+    t = np.ascontiguousarray(trans, np.float64).reshape(4).copy()
+    im = None if imu is None else np.ascontiguousarray(imu, np.float64)
+    tol = None if tolerances is None else np.ascontiguousarray(tolerances, np.float64)
+    out = np.zeros(10)
+    _check(lib().randt_hostapi_window_solve(C.c_int(device), C.byref(gp), fptr, _pf(nf), _pf(fp), C.c_uint32(len(fs)), wptr, _pf(nw), C.c_uint32(len(ws)),
+                                            _pf(st), _pf(im) if im is not None else None, _pf(np.ascontiguousarray(params80, np.float64)),
+                                            _pf(tol) if tol is not None else None, _pf(t), _pf(out)))
+    keys = ("status", "rejected", "gnc_solves", "total_iterations", "final_cost", "mu_first", "max_residual", "n_tangent", "evaluations", "n_cells")
+    return st, t, dict(zip(keys, out.tolist()))

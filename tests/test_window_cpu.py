@@ -1,0 +1,200 @@
+"""The host factors of Matcher::estimateTransformCeres' joint window problem (R/src/ndt_registration/ndt_matcher.cpp:322-424): the
+motion-model factor (MotionModelFactorSE2 / MotionModelFactor, R/include/ndt_registration/ceres_residuals.h:554-679) and the relative IMU
+yaw factor (RotationalResidualSE2 / RotationalResidual, :307-370) as the product's host layer evaluates them (randt_slam_b200/host/
+window_solver.cpp, dual numbers + Sophus::Manifold<SE2>::PlusJacobian), against
+  * known answers (a window that follows the motion model exactly costs nothing; a hand-computed residual vector),
+  * an independent numpy restatement of the residuals differentiated by central differences along the solver's tangent directions,
+  * the CPU oracle (oracle/window_oracle.h).
+No device is needed: the NDT term is absent here (tests/test_window_gpu.py covers the whole solve)."""
+import math
+
+import numpy as np
+import pytest
+
+from randt_slam_b200 import hostapi
+
+DIAG = np.array([1.0, 1.0, 10.0, 1.0, 3.0, 0.1, 20.0, 60.0])
+
+
+# ---- independent restatement of the residuals (plain numpy, closed-form SE(2) exp / log) ---------------------------------------------
+def se2_exp(u):
+    th = u[2]
+    if abs(th) < 1e-10:
+        a, b = 1.0 - th * th / 6.0, 0.5 * th - th ** 3 / 24.0
+    else:
+        a, b = math.sin(th) / th, (1.0 - math.cos(th)) / th
+    return np.array([math.cos(th), math.sin(th), a * u[0] - b * u[1], b * u[0] + a * u[1]])
+
+
+def se2_mul(A, B):
+    return np.array([A[0] * B[0] - A[1] * B[1], A[0] * B[1] + A[1] * B[0], A[2] + A[0] * B[2] - A[1] * B[3], A[3] + A[1] * B[2] + A[0] * B[3]])
+
+
+def se2_inv(A):
+    c, s = A[0], -A[1]
+    return np.array([c, s, -(c * A[2] - s * A[3]), -(s * A[2] + c * A[3])])
+
+
+def se2_log(A):
+    th = math.atan2(A[1], A[0])
+    h = th / 2.0
+    f = 1.0 - th * th / 12.0 if abs(th) < 1e-4 else h / math.tan(h)   # theta/2 cot(theta/2)
+    return np.array([f * A[2] + h * A[3], -h * A[2] + f * A[3], th])
+
+
+def wrap(a):
+    return a - 2.0 * math.pi * math.floor((a + math.pi) / (2.0 * math.pi))
+
+
+def window_cost(st, sqrtI, manifold, use_imu, imu, weight_imu, weight_bias):
+    cost = 0.0
+    for j in range(1, len(st)):
+        a, b = st[j - 1], st[j]
+        raw_dt = b[13] - a[13]
+        dt = max(raw_dt, 0.2)
+        if manifold:
+            pred = se2_mul(a[:4], se2_exp([a[7] * dt + 0.5 * dt * a[10], a[8] * dt + 0.5 * dt * a[11], a[9] * dt]))
+            e_pose = se2_log(se2_mul(se2_inv(pred), b[:4]))
+        else:
+            mid = wrap(a[6] + 0.5 * dt * a[9])
+            dx, dy = a[7] * dt + 0.5 * a[10] * dt * dt, a[8] * dt + 0.5 * a[11] * dt * dt
+            e_pose = np.array([b[4] - (a[4] + math.cos(mid) * dx - math.sin(mid) * dy), b[5] - (a[5] + math.sin(mid) * dx + math.cos(mid) * dy),
+                               wrap(b[6] - wrap(a[6] + dt * a[9]))])
+        e = np.concatenate([e_pose, [b[7] - (a[7] + dt * a[10]), b[8] - (a[8] + dt * a[11]), b[9] - a[9], b[10] - a[10], b[11] - a[11]]])
+        r = sqrtI @ e
+        cost += 0.5 * float(r @ r)
+        if use_imu:
+            if manifold:
+                M1 = se2_mul(b[:4], se2_exp([0.0, 0.0, b[12] * raw_dt]))
+                yaw = se2_log(se2_mul(se2_inv(a[:4]), M1))[2]
+            else:
+                yaw = wrap(b[6] - a[6] + b[12] * raw_dt)
+            cost += 0.5 * (weight_imu * (imu[j - 1] - yaw)) ** 2 + 0.5 * (weight_bias * (b[12] - a[12])) ** 2
+    return cost
+
+
+def tangent_layout(W, manifold, cv, use_imu):
+    """(state, kind, component) per tangent column in the solver's order: the first state's pose and bias are constant"""
+    cols = []
+    for j in range(W + 1):
+        if j >= 1:
+            cols += [(j, "pose", c) for c in range(3)]
+        cols += [(j, "vel", 0), (j, "vel", 1), (j, "omega", 0)]
+        if not cv:
+            cols += [(j, "acc", 0), (j, "acc", 1)]
+        if use_imu and j >= 1:
+            cols.append((j, "bias", 0))
+    return cols
+
+
+def perturbed(st, col, h, manifold):
+    j, kind, c = col
+    s = st.copy()
+    if kind == "pose":
+        if manifold:
+            d = np.zeros(3); d[c] = h
+            s[j, :4] = se2_mul(s[j, :4], se2_exp(d))       # Sophus::Manifold<SE2>::Plus
+        else:
+            s[j, 4 + c] += h
+    elif kind == "vel":
+        s[j, 7 + c] += h
+    elif kind == "omega":
+        s[j, 9] += h
+    elif kind == "acc":
+        s[j, 10 + c] += h
+    else:
+        s[j, 12] += h
+    return s
+
+
+def make_states(W, rng, exact=False):
+    st = np.zeros((W + 1, 14))
+    th, x, y = 0.3, 1.0, -2.0
+    v = np.array([4.0, 0.3]); om = 0.12
+    for j in range(W + 1):
+        st[j, :4] = [math.cos(th), math.sin(th), x, y]; st[j, 4:7] = [x, y, th]
+        st[j, 7:9] = v; st[j, 9] = om; st[j, 13] = 0.25 * j
+        nxt = se2_mul(st[j, :4], se2_exp([v[0] * 0.25, v[1] * 0.25, om * 0.25]))
+        th, x, y = math.atan2(nxt[1], nxt[0]), nxt[2], nxt[3]
+    if not exact:
+        st[:, 7:9] += rng.normal(0, 0.2, (W + 1, 2)); st[:, 9] += rng.normal(0, 0.03, W + 1)
+        st[:, 10:12] = rng.normal(0, 0.3, (W + 1, 2)); st[:, 12] = rng.normal(0, 0.01, W + 1)
+        for j in range(W + 1):
+            d = rng.normal(0, [0.1, 0.1, 0.02])
+            st[j, :4] = se2_mul(st[j, :4], se2_exp(d))
+            st[j, 4:7] = [st[j, 2], st[j, 3], math.atan2(st[j, 1], st[j, 0])]
+    return st
+
+
+def test_a_window_that_follows_the_se2_motion_model_costs_nothing():
+    st = make_states(3, None, exact=True)
+    q = hostapi.window_params(manifold=True, constant_velocity=True, use_imu=False, covariance_scaling_factor=1.0)
+    cost, g, H = hostapi.window_factors(st, q)
+    assert cost < 1e-24 and np.max(np.abs(g)) < 1e-10
+    assert H.shape == (3 + 3 * 6, 3 + 3 * 6) and np.allclose(H, H.T) and np.all(np.linalg.eigvalsh(H) > -1e-9)
+
+
+def test_hand_computed_motion_residual():
+    """two states, identity pose, v = (2, 0), dt = 0.5 (above the 0.2 s clamp): the prediction is (1, 0, 0); the new state sits at
+    (1.3, -0.2, 0) with v = (2.5, 0.1), omega 0.2 -> e = (0.3, -0.2, 0, 0.5, 0.1, 0.2, 0, 0), residual = sqrtI e"""
+    st = np.zeros((2, 14))
+    st[0, :4] = [1, 0, 0, 0]; st[0, 7] = 2.0
+    st[1, :4] = [1, 0, 1.3, -0.2]; st[1, 4:6] = [1.3, -0.2]; st[1, 7:10] = [2.5, 0.1, 0.2]; st[1, 13] = 0.5
+    e = np.array([0.3, -0.2, 0.0, 0.5, 0.1, 0.2, 0.0, 0.0])
+    for manifold in (True, False):
+        q = hostapi.window_params(manifold=manifold, covariance_scaling_factor=0.5)
+        cost, g, H = hostapi.window_factors(st, q)
+        assert abs(cost - 0.5 * np.sum((0.5 * DIAG * e) ** 2)) < 1e-14
+    # identical stamps are clamped to 0.2 s (ceres_residuals.h:38,73): prediction (0.4, 0, 0)
+    st[1, 13] = 0.0
+    e[0] = 1.3 - 0.4
+    cost, _, _ = hostapi.window_factors(st, hostapi.window_params(covariance_scaling_factor=0.5))
+    assert abs(cost - 0.5 * np.sum((0.5 * DIAG * e) ** 2)) < 1e-14
+
+
+@pytest.mark.parametrize("manifold", [True, False])
+@pytest.mark.parametrize("cv", [True, False])
+@pytest.mark.parametrize("use_imu", [False, True])
+def test_gradient_and_gauss_newton_matrix_against_an_independent_restatement(manifold, cv, use_imu):
+    rng = np.random.default_rng(7 + 4 * manifold + 2 * cv + use_imu)
+    W = 3
+    st = make_states(W, rng)
+    imu = rng.normal(0.03, 0.01, W)
+    wi, wb = 64.0, 50.0
+    q = hostapi.window_params(manifold=manifold, constant_velocity=cv, use_imu=use_imu, weight_imu=wi, weight_imu_bias=wb, covariance_scaling_factor=0.3)
+    sqrtI = q[16:].reshape(8, 8)
+    cost, g, H = hostapi.window_factors(st, q, imu)
+    ref = window_cost(st, sqrtI, manifold, use_imu, imu, wi, wb)
+    assert abs(cost - ref) <= 1e-12 * ref
+    cols = tangent_layout(W, manifold, cv, use_imu)
+    assert len(cols) == len(g)
+    h = 1e-6
+    fd = np.array([(window_cost(perturbed(st, c, h, manifold), sqrtI, manifold, use_imu, imu, wi, wb) -
+                    window_cost(perturbed(st, c, -h, manifold), sqrtI, manifold, use_imu, imu, wi, wb)) / (2 * h) for c in cols])
+    assert np.max(np.abs(g - fd)) <= 2e-6 * max(1.0, np.max(np.abs(fd)))
+    # J^T J is the Gauss-Newton matrix: symmetric, positive semi-definite, and its quadratic model predicts the cost along a small step
+    assert np.allclose(H, H.T, rtol=0, atol=1e-9 * np.max(np.abs(H))) and np.min(np.linalg.eigvalsh(H)) > -1e-7 * np.max(np.abs(H))
+    d = rng.normal(0, 1e-4, len(g))
+    s = st.copy()
+    for c, dc in zip(cols, d):
+        s = perturbed(s, c, dc, manifold)
+    moved = window_cost(s, sqrtI, manifold, use_imu, imu, wi, wb)
+    model = cost + g @ d + 0.5 * d @ H @ d
+    assert abs(moved - model) <= 1e-3 * abs(moved - cost) + 1e-12 * cost
+
+
+@pytest.mark.parametrize("manifold", [True, False])
+@pytest.mark.parametrize("cv", [True, False])
+@pytest.mark.parametrize("use_imu", [False, True])
+def test_host_factors_equal_the_oracle(oracle, manifold, cv, use_imu):
+    rng = np.random.default_rng(100 + 4 * manifold + 2 * cv + use_imu)
+    for W in (1, 2, 3):
+        st = make_states(W, rng)
+        imu = rng.normal(0.0, 0.05, W)
+        q = hostapi.window_params(manifold=manifold, constant_velocity=cv, use_imu=use_imu, covariance_scaling_factor=25.0)
+        qo = q.copy(); qo[14] = 0 if manifold else 2      # the oracle reads the functor variant there
+        cost, g, H = hostapi.window_factors(st, q, imu)
+        co, go, Ho, _ = oracle.window_evaluate(st, qo, imu)
+        assert len(g) == len(go) == 3 + (0 if cv else 2) + W * (6 + (0 if cv else 2) + (1 if use_imu else 0))
+        assert abs(cost - co) <= 1e-13 * co
+        assert np.max(np.abs(g - go)) <= 1e-12 * np.max(np.abs(go)) and np.max(np.abs(H - Ho)) <= 1e-12 * np.max(np.abs(Ho))
