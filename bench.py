@@ -409,6 +409,33 @@ def run_configs(args, ctx, capi, stream, rank, world, local, barrier):
             poses_o, dto = W.oracle_replay(oracle, p4, scans[:n_o])
             rec["cpu_baseline"] = {"scans_per_s": (n_o - 1) / dto, "cores": 1, "kind": "port", "sample": "first %d scans of the drive" % n_o,
                                    "max_abs_pose_difference_vs_device": float(np.max(np.abs(poses_o - poses_g[:n_o])))}
+        if args.window_scans > 1:
+            # the same drive through the reference-shaped odometry: Matcher::predictTransform -> Matcher::estimateTransformCeres over the
+            # smoothing window (NDT blocks of 3 states in one K3 launch per LM evaluation + motion-model factors on the host) -> delayed
+            # keyframe insertion at the smoothed pose (LocalFuser::processScan, local_fuser.cpp:99-300)
+            from randt_slam_b200 import hostapi as HA
+            n_w = min(args.window_scans, len(scans))
+            q = W.window_odometry_params(HA, p4)
+            stamps = 0.2486 * np.arange(n_w)                                 # Oxford scan period
+            gp4 = capi.grid_params(p4)
+            HA.window_replay(gp4, scans[:12], stamps[:12], q)                # warm-up
+            poses_w, states_w, stats_w, tot = HA.window_replay(gp4, scans[:n_w], stamps, q)
+            est_w = np.stack([states_w[:, 2], states_w[:, 3]], 1)
+            err_w = np.hypot(est_w[:, 0] - truth[:n_w, 0], est_w[:, 1] - truth[:n_w, 1])
+            wrec = {"workload": "first %d scans of the drive through randt::Matcher::estimateTransformCeres (window of 3 states, SE(2) manifold, constant-velocity "
+                                "motion-model factors, parameters_oxford.yaml), keyframes inserted 4 scans late at their smoothed pose" % n_w,
+                    "scans": n_w, "scans_per_s": (n_w - 1) / tot["seconds"], "ms_per_scan": tot["seconds"] * 1e3 / (n_w - 1),
+                    "median_us_per_scan": float(np.median(stats_w[1:, 3])), "problem_setup_us_per_scan": tot["setup_seconds"] * 1e6 / (n_w - 1),
+                    "gnc_lm_loop_us_per_scan": tot["solve_seconds"] * 1e6 / (n_w - 1), "mean_lm_iterations_per_scan": float(stats_w[1:, 0].mean()),
+                    "mean_device_evaluations_per_scan": float(stats_w[1:, 1].mean()), "kernel_launches_per_scan": tot["launches"] / (n_w - 1),
+                    "rejected_estimates": int(stats_w[:, 2].sum()), "keyframes": tot["keyframes"], "max_position_error_m": float(err_w.max()),
+                    "final_speed_m_per_s": float(np.hypot(states_w[-1, 7], states_w[-1, 8])), "true_speed_m_per_s": 0.45 / 0.2486}
+            if oracle is not None and args.window_oracle_scans > 1:
+                n_o = min(args.window_oracle_scans, n_w)
+                o_poses, o_states, _, dto = W.oracle_window_replay(oracle, p4, scans[:n_o], stamps[:n_o], q)
+                wrec["cpu_baseline"] = {"scans_per_s": (n_o - 1) / dto, "cores": 1, "kind": "port", "sample": "first %d scans of the drive" % n_o,
+                                        "max_abs_pose_difference_vs_device": float(np.max(np.abs(o_poses - poses_w[:n_o])))}
+            rec["window_odometry"] = wrec
         out["c4"] = rec
     barrier()
     return out
@@ -501,6 +528,8 @@ def main():
     ap.add_argument("--c2-allpairs-problems", type=int, default=16, help="problems of the c2 all-pairs variant (16 M pairs each)")
     ap.add_argument("--c3-batch", type=int, default=256, help="registrations of the literal configs[3] batch (sharded over the ranks)")
     ap.add_argument("--replay-scans", type=int, default=8609, help="scans of the configs[4] replay (Oxford sequence length); rank 0 only")
+    ap.add_argument("--window-scans", type=int, default=1000, help="prefix of the drive replayed through estimateTransformCeres (window odometry); 0 skips it")
+    ap.add_argument("--window-oracle-scans", type=int, default=120, help="prefix of that the CPU oracle's window chain replays for comparison")
     ap.add_argument("--replay-oracle-scans", type=int, default=300, help="prefix of the drive the CPU oracle chain replays for comparison")
     ap.add_argument("--preset", choices=sorted(P.PRESETS), default="oxford",
                     help="shipped parameter file the scans, maps and losses follow (SURVEY §8d C2 fixes oxford for the headline workload: an "

@@ -129,6 +129,7 @@ struct WindowSummary {
   int rejected = 0;          // the rejection gate of ndt_matcher.cpp:408-422 fired
   int gnc_solves = 0, total_iterations = 0, n_free_states = 0, n_tangent = 0, evaluations = 0;
   double final_cost = 0, mu_first = 0, max_residual = 0;
+  double setup_us = 0, solve_us = 0;   // wall time of building the problem (associations, record table) and of the GNC / LM loop
 };
 
 class RANDT_API Context {
@@ -213,6 +214,9 @@ class RANDT_API NdtCostFunction : public ceres::CostFunction {
 class RANDT_API Matcher {
  public:
   explicit Matcher(Context& ctx) : ctx_(&ctx) {}
+  ~Matcher();
+  Matcher(const Matcher&) = delete;
+  Matcher& operator=(const Matcher&) = delete;
   void initialize(const NDTMatcherParameters& parameters) { parameters_ = parameters; }
   // Matcher::resetMatcher (ndt_matcher.cpp:18-20): forget the relative IMU constraints collected by predictTransform
   void resetMatcher() { imu_constraints_.clear(); }
@@ -240,6 +244,9 @@ class RANDT_API Matcher {
   // is imu_constraints_.end()[-i-1] as in the reference (:352), 0 where that reads before the first element.
   void estimateTransformCeres(SE2d& trans, std::vector<State>& trajectory, const double& initial_angle_guess, const double& stamp,
                               const std::deque<Map>& fixed_ndts, const std::deque<Map>& moving_ndts);
+  // the same over maps the caller keeps elsewhere (randt::Map is move-only; the reference copies its maps into the deques)
+  void estimateTransformCeres(SE2d& trans, std::vector<State>& trajectory, const double& initial_angle_guess, const double& stamp,
+                              const std::vector<const Map*>& fixed_ndts, const std::vector<const Map*>& moving_ndts);
   const WindowSummary& lastWindowSummary() const { return window_summary_; }
   // ceres' convergence tolerances for the window solve (<= 0: Solver::Options defaults 1e-6 / 1e-8 / 1e-10)
   void setWindowTolerances(double function_tolerance, double parameter_tolerance, double gradient_tolerance) {
@@ -276,6 +283,8 @@ class RANDT_API Matcher {
   State X_next_;
   WindowSummary window_summary_;
   double window_tol_[3] = {0.0, 0.0, 0.0};
+  double* window_staging_ = nullptr;   // pinned poses + records of one window evaluation (kept across calls)
+  size_t window_staging_cap_ = 0;
 };
 
 }  // namespace randt
@@ -333,5 +342,17 @@ RANDT_API int randt_hostapi_window_solve(int device, const randt_grid_params* gp
                                          const double* fixed_pose4, uint32_t n_fixed, const float* const* window_pts4, const uint32_t* n_window_pts,
                                          uint32_t W, double* states, const double* imu, const double* params80, const double* tolerances3,
                                          double* trans4, double* out10);
+/* LocalFuser::processScan in miniature (R/src/local_fuser/local_fuser.cpp:99-300, one submap, no submap roll-over): per scan voxelise ->
+ * Matcher::predictTransform -> Matcher::estimateTransformCeres against the submap over the window of the last smoothing_steps scans -> both
+ * pose representations of the window states -> keyframes (every insertion_step-th state) enter the submap insertion_delay = smoothing_steps + 1
+ * scans later at their smoothed pose (transformMap + mergeMapCell); the first scan initialises the trajectory (zero velocities) and the
+ * submap.  pts4 / scan_off: the scans back to back; stamps [n]; yaw [n] (relative IMU yaw per scan, may be NULL); params80 as in
+ * randt_hostapi_window_solve.  poses_out [n][4]: the estimate returned for each scan when it arrived; states_out [n][14]: the trajectory
+ * at the end (smoothed); stats_out [n][4]: total LM iterations, device evaluations, rejected, wall microseconds of the scan;
+ * totals [6]: wall seconds of the whole loop, submap cells at the end, kernel launches, keyframes merged, seconds spent building the window
+ * problems, seconds spent in their GNC / LM loops. */
+RANDT_API int randt_hostapi_window_replay(int device, const randt_grid_params* gp, const float* pts4, const uint32_t* scan_off, uint32_t n_scans,
+                                          const double* stamps, const double* yaw, const double* params80, int smoothing_steps, int insertion_step,
+                                          double* poses_out, double* states_out, double* stats_out, double* totals);
 RANDT_API const char* randt_hostapi_last_error(void);
 }

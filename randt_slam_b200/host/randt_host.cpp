@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <chrono>
 #include <cstring>
 #include <deque>
 #include <set>
@@ -496,9 +497,12 @@ std::vector<WindowBlocks> buildWindowFactors(window::JointProblem& problem, cons
 }
 }  // namespace
 
+Matcher::~Matcher() { randt_host_free(window_staging_); }
+
 void Matcher::solveWindow(SE2d& trans, std::vector<State>& trajectory, const std::vector<const Map*>& fixed_ndts,
                           const std::vector<const Map*>& moving_window, const std::vector<double>& imu) {
   window_summary_ = WindowSummary();
+  const std::chrono::steady_clock::time_point t_begin = std::chrono::steady_clock::now();
   const bool manifold = parameters_.optimize_on_manifold && !parameters_.use_analytic_expressions_for_optimization;
   const bool use_intensity = parameters_.use_intensity_as_dimension;
   const int k = parameters_.n_results_kd_lookup;
@@ -550,6 +554,15 @@ void Matcher::solveWindow(SE2d& trans, std::vector<State>& trajectory, const std
   for (size_t j = 0; j <= W; ++j) states[j] = &trajectory[trajectory.size() - 1 - W + j];
   const std::vector<WindowBlocks> blocks = buildWindowFactors(problem, parameters_, manifold, states.data(), (int)W, imu.data(), sqrtI);
   window::NdtTerm term;
+  const size_t staging = W * (4 + RANDT_FUSED_STRIDE);
+  if (window_staging_cap_ < staging) {
+    randt_host_free(window_staging_);
+    window_staging_cap_ = 0;
+    window_staging_ = static_cast<double*>(randt_host_alloc(sizeof(double) * staging));
+    if (!window_staging_) throw Error(RANDT_E_NOMEM, "estimateTransformCeres: no pinned host memory");
+    window_staging_cap_ = staging;
+  }
+  term.poses = window_staging_; term.records = window_staging_ + W * 4;
   term.ctx = ctx_->get(); term.problem = merged; term.variant = variant(use_intensity); term.np = manifold ? 4 : 3;
   for (size_t j = 1; j <= W; ++j) {
     if (manifold) term.seg_blocks.push_back({blocks[j].pose});
@@ -565,6 +578,8 @@ void Matcher::solveWindow(SE2d& trans, std::vector<State>& trajectory, const std
   if (window_tol_[1] > 0.0) opt.parameter_tolerance = window_tol_[1];
   if (window_tol_[2] > 0.0) opt.gradient_tolerance = window_tol_[2];
 
+  const std::chrono::steady_clock::time_point t_built = std::chrono::steady_clock::now();
+  window_summary_.setup_us = std::chrono::duration<double, std::micro>(t_built - t_begin).count();
   // ---- GNC loop (:382-397)
   std::vector<double> x((size_t)problem.numAmbient());
   problem.gather(x.data());
@@ -588,6 +603,7 @@ void Matcher::solveWindow(SE2d& trans, std::vector<State>& trajectory, const std
   } while (gnc_mu > 1.0 / std::sqrt(parameters_.gnc_control_parameter_divisor));
   window_summary_.final_cost = last.final_cost;
   window_summary_.evaluations = problem.evaluations();
+  window_summary_.solve_us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_built).count();
   problem.scatter(x.data());
 
   // ---- both representations of the newest state (:399-406), rejection gate (:408-422)
@@ -607,11 +623,16 @@ void Matcher::solveWindow(SE2d& trans, std::vector<State>& trajectory, const std
   trans = newest.pose;
 }
 
-void Matcher::estimateTransformCeres(SE2d& trans, std::vector<State>& trajectory, const double& /*initial_angle_guess*/, const double& /*stamp*/,
+void Matcher::estimateTransformCeres(SE2d& trans, std::vector<State>& trajectory, const double& initial_angle_guess, const double& stamp,
                                      const std::deque<Map>& fixed_ndts, const std::deque<Map>& moving_ndts) {
   std::vector<const Map*> fixed, moving;
   for (const Map& m : fixed_ndts) fixed.push_back(&m);
   for (const Map& m : moving_ndts) moving.push_back(&m);
+  estimateTransformCeres(trans, trajectory, initial_angle_guess, stamp, fixed, moving);
+}
+
+void Matcher::estimateTransformCeres(SE2d& trans, std::vector<State>& trajectory, const double& /*initial_angle_guess*/, const double& /*stamp*/,
+                                     const std::vector<const Map*>& fixed, const std::vector<const Map*>& moving) {
   const size_t W = trajectory.size() < 2 ? 0 : std::min(trajectory.size() - 1, (size_t)parameters_.smoothing_steps);
   // the factor ending at trajectory.end()[-i] reads imu_constraints_.end()[-i-1] (:352); before the first element: 0
   std::vector<double> imu(W, 0.0);
@@ -938,6 +959,83 @@ int randt_hostapi_window_solve(int device, const randt_grid_params* gp, const fl
     const randt::WindowSummary& ws = m.lastWindowSummary();
     out10[0] = ws.status; out10[1] = ws.rejected; out10[2] = ws.gnc_solves; out10[3] = ws.total_iterations; out10[4] = ws.final_cost;
     out10[5] = ws.mu_first; out10[6] = ws.max_residual; out10[7] = ws.n_tangent; out10[8] = ws.evaluations; out10[9] = (double)n_cells;
+  });
+}
+
+int randt_hostapi_window_replay(int device, const randt_grid_params* gp, const float* pts4, const uint32_t* scan_off, uint32_t n_scans,
+                                const double* stamps, const double* yaw, const double* params80, int smoothing_steps, int insertion_step,
+                                double* poses_out, double* states_out, double* stats_out, double* totals) {
+  return guarded([&] {
+    using clock = std::chrono::steady_clock;
+    randt::Context ctx(device);
+    const randt::NDTMapParameters mp = map_params(*gp);
+    randt::NDTMatcherParameters p = matcher_params80(params80);
+    p.smoothing_steps = smoothing_steps;
+    const bool manifold = p.optimize_on_manifold && !p.use_analytic_expressions_for_optimization;
+    const size_t insertion_delay = (size_t)smoothing_steps + 1;                  // ndt_slam.cpp:580
+    randt::Matcher matcher(ctx);
+    matcher.initialize(p);
+    std::vector<randt::State> trajectory;
+    std::deque<std::shared_ptr<randt::Map>> map_window, next_maps_to_insert;
+    std::shared_ptr<randt::Map> submap;      // _current_submap: becomes the first scan, then grows by mergeMapCell
+    randt::SE2d current_transform;
+    uint32_t keyframes = 0;
+    totals[4] = totals[5] = 0.0;
+    const uint64_t launches0 = ctx.launchCount();
+    const clock::time_point t_begin = clock::now();
+    for (uint32_t i = 0; i < n_scans; ++i) {
+      const clock::time_point t0 = clock::now();
+      std::shared_ptr<randt::Map> current_scan(new randt::Map(ctx, mp));
+      const uint32_t off[2] = {0, scan_off[i + 1] - scan_off[i]};
+      current_scan->addClusters(pts4 + 4 * (size_t)scan_off[i], off, 1);
+      double* st = stats_out + 4 * (size_t)i;
+      st[0] = st[1] = st[2] = 0.0;
+      if (submap && submap->get_n_cells() > 0) {
+        matcher.predictTransform(yaw ? yaw[i] : 0.0, stamps[i], trajectory);
+        map_window.push_back(current_scan);
+        std::vector<const randt::Map*> f_maps{submap.get()}, window;
+        for (const auto& m : map_window) window.push_back(m.get());
+        matcher.estimateTransformCeres(current_transform, trajectory, yaw ? yaw[i] : 0.0, stamps[i], f_maps, window);
+        const randt::WindowSummary& ws = matcher.lastWindowSummary();
+        st[0] = ws.total_iterations; st[1] = ws.evaluations; st[2] = ws.rejected;
+        totals[4] += ws.setup_us * 1e-6; totals[5] += ws.solve_us * 1e-6;
+        // write both pose representations (local_fuser.cpp:141-150)
+        for (size_t b = 1; b <= std::min((size_t)smoothing_steps, trajectory.size()); ++b) {
+          randt::State& X = trajectory[trajectory.size() - b];
+          if (!manifold) X.pose = randt::SE2d(X.rot, X.pos[0], X.pos[1]);
+          else { X.pos[0] = X.pose.v[2]; X.pos[1] = X.pose.v[3]; X.rot = X.pose.angle(); }
+        }
+        const size_t trajectory_size = trajectory.size();
+        if (map_window.size() >= (size_t)smoothing_steps) map_window.pop_front();
+        if (trajectory_size % (size_t)insertion_step == 0) next_maps_to_insert.push_back(current_scan);   // keyframe, pushed on the buffer
+        if (trajectory_size >= insertion_delay + (size_t)insertion_step && (trajectory_size - insertion_delay) % (size_t)insertion_step == 0 &&
+            !next_maps_to_insert.empty()) {
+          // the keyframe leaves the estimator: insert it at its smoothed pose (:164-190)
+          const randt::State& X_smoothed = trajectory[trajectory_size - insertion_delay - 1];
+          const randt::SE2d smoothed = manifold ? X_smoothed.pose : randt::SE2d(X_smoothed.rot, X_smoothed.pos[0], X_smoothed.pos[1]);
+          next_maps_to_insert.front()->transformMap(smoothed);
+          submap->mergeMapCell(*next_maps_to_insert.front());
+          next_maps_to_insert.pop_front();
+          ++keyframes;
+        }
+      } else {
+        // the first scan of the submap (:221-296)
+        randt::State initial_state;
+        initial_state.pose = current_transform;
+        initial_state.pos[0] = current_transform.v[2]; initial_state.pos[1] = current_transform.v[3]; initial_state.rot = current_transform.angle();
+        initial_state.stamp = stamps[i];
+        trajectory.push_back(initial_state);
+        current_scan->transformMap(current_transform);
+        submap = current_scan;               // mergeMapCell into the empty submap: every cell is appended as it is
+      }
+      std::memcpy(poses_out + 4 * (size_t)i, current_transform.v, 4 * sizeof(double));
+      st[3] = std::chrono::duration<double, std::micro>(clock::now() - t0).count();
+    }
+    totals[0] = std::chrono::duration<double>(clock::now() - t_begin).count();
+    totals[1] = submap ? (double)submap->get_n_cells() : 0.0;
+    totals[2] = (double)(ctx.launchCount() - launches0);
+    totals[3] = (double)keyframes;
+    for (uint32_t i = 0; i < n_scans && i < trajectory.size(); ++i) state_to14(trajectory[i], states_out + 14 * (size_t)i);
   });
 }
 

@@ -204,8 +204,8 @@ void JointProblem::finalize() {
     uint32_t S = 0, P = 0;
     randt_problem_info(ndt_.problem, &S, &P, nullptr, nullptr);
     ndt_blocks_ = P;
-    poses_.assign((size_t)S * ndt_.np, 0.0);
-    records_.assign((size_t)S * RANDT_FUSED_STRIDE, 0.0);
+    if (!ndt_.poses || !ndt_.records) throw Error(RANDT_E_INVALID, "window problem: the NDT term needs staging buffers");
+    (void)S;
   }
 }
 
@@ -281,16 +281,16 @@ bool JointProblem::evaluate(const double* x, const randt_loss* loss, bool want_j
     const int np = ndt_.np;
     for (size_t s = 0; s < S; ++s) {
       int o = 0;
-      for (int id : ndt_.seg_blocks[s]) { const double* v = blockValues(id, x); for (int c = 0; c < blocks_[id].size; ++c) poses_[s * np + o++] = v[c]; }
+      for (int id : ndt_.seg_blocks[s]) { const double* v = blockValues(id, x); for (int c = 0; c < blocks_[id].size; ++c) ndt_.poses[s * np + o++] = v[c]; }
     }
     randt_loss none;
     none.kind = RANDT_LOSS_NONE; none.scale = 1.0; none.alpha = 2.0; none.mu = 1.0; none.weight = 1.0;
     // ONE K3 launch: per window state the loss-corrected normal equations of all its residual blocks
-    if (randt_eval_fused(ndt_.ctx, ndt_.problem, ndt_.variant, poses_.data(), loss ? loss : &none, nullptr, want_jac ? 1 : 0, records_.data()) != RANDT_OK)
+    if (randt_eval_fused(ndt_.ctx, ndt_.problem, ndt_.variant, ndt_.poses, loss ? loss : &none, nullptr, want_jac ? 1 : 0, ndt_.records) != RANDT_OK)
       return false;
     double mr = 0.0;
     for (size_t s = 0; s < S; ++s) {
-      const double* rec = &records_[s * RANDT_FUSED_STRIDE];
+      const double* rec = &ndt_.records[s * RANDT_FUSED_STRIDE];
       *cost += rec[RANDT_FUSED_COST];
       if (rec[RANDT_FUSED_N] > 0.0) mr = std::max(mr, rec[RANDT_FUSED_MAXR]);
       if (!want_jac) continue;

@@ -48,6 +48,10 @@ struct NdtTerm {
   int variant = RANDT_VAR_SE2_INTENSITY;
   int np = 4;
   std::vector<std::vector<int>> seg_blocks;
+  // caller-owned staging for one evaluation: [S][np] poses and [S][RANDT_FUSED_STRIDE] records.  Pinned (randt_host_alloc) memory lets the
+  // poses go up without a staging copy and K3 store its records straight into host memory.
+  double* poses = nullptr;
+  double* records = nullptr;
 };
 
 class JointProblem {
@@ -76,7 +80,6 @@ class JointProblem {
   NdtTerm ndt_;
   int n_amb_ = 0, n_tan_ = 0, n_evals_ = 0;
   uint32_t ndt_blocks_ = 0;
-  std::vector<double> poses_, records_;
 };
 
 struct MinimizerSummary {

@@ -20,7 +20,7 @@ def lib():
         L = C.CDLL(LIB_PATH)
         L.randt_hostapi_last_error.restype = C.c_char_p
         for name in ("randt_hostapi_loop_constraints", "randt_hostapi_cost_function", "randt_hostapi_bnb", "randt_hostapi_export", "randt_hostapi_odometry", "randt_hostapi_eval_async_loop", "randt_hostapi_build_schedule",
-                     "randt_hostapi_window_factors", "randt_hostapi_window_solve"):
+                     "randt_hostapi_window_factors", "randt_hostapi_window_solve", "randt_hostapi_window_replay"):
             getattr(L, name).restype = C.c_int
         _lib = L
     return _lib
@@ -177,3 +177,20 @@ def window_solve(gp, fixed_scans, fixed_poses, window_scans, states14, params80,
                                             _pf(tol) if tol is not None else None, _pf(t), _pf(out)))
     keys = ("status", "rejected", "gnc_solves", "total_iterations", "final_cost", "mu_first", "max_residual", "n_tangent", "evaluations", "n_cells")
     return st, t, dict(zip(keys, out.tolist()))
+
+
+def window_replay(gp, scans, stamps, params80, smoothing_steps=3, insertion_step=2, yaw=None, device=0):
+    """LocalFuser::processScan in miniature over a drive: voxelise -> predictTransform -> estimateTransformCeres over the window -> delayed
+    keyframe insertion at the smoothed pose -> (poses [n, 4] as estimated on arrival, states [n, 14] at the end, stats [n, 4], totals dict)"""
+    sc = [np.ascontiguousarray(s, np.float32) for s in scans]
+    n = len(sc)
+    pts = np.ascontiguousarray(np.concatenate(sc), np.float32)
+    off = np.concatenate([[0], np.cumsum([len(s) for s in sc])]).astype(np.uint32)
+    st = np.ascontiguousarray(stamps, np.float64)
+    yw = None if yaw is None else np.ascontiguousarray(yaw, np.float64)
+    poses = np.zeros((n, 4)); states = np.zeros((n, 14)); stats = np.zeros((n, 4)); totals = np.zeros(6)
+    _check(lib().randt_hostapi_window_replay(C.c_int(device), C.byref(gp), _pf(pts), _pf(off), C.c_uint32(n), _pf(st), _pf(yw) if yw is not None else None,
+                                             _pf(np.ascontiguousarray(params80, np.float64)), C.c_int(int(smoothing_steps)), C.c_int(int(insertion_step)),
+                                             _pf(poses), _pf(states), _pf(stats), _pf(totals)))
+    return poses, states, stats, dict(seconds=totals[0], submap_cells=int(totals[1]), launches=int(totals[2]), keyframes=int(totals[3]),
+                                       setup_seconds=totals[4], solve_seconds=totals[5])

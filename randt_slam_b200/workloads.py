@@ -336,3 +336,89 @@ def oracle_replay(O, p, scans, keyframe_every=2):
             mc = O.transform_cells(v["cells"], *o["pose"].astype(np.float32))
             cells, npts, slot = O.merge_map_cell(cells, npts, slot, p.size_x, p.size_y, p.resolution, mc, v["npts"])
     return poses, time.perf_counter() - t0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# c4, reference-shaped: Matcher::estimateTransformCeres over the smoothing window (motion-model factors), scan by scan
+# ---------------------------------------------------------------------------------------------------------------
+def window_odometry_params(hostapi, p, covariance_scaling_factor=0.01, motion_sqrtI_diag=(1.0, 1.0, 10.0, 1.0, 3.0, 0.1, 20.0, 60.0)):
+    """parameters_oxford.yaml:60-87 for the joint window problem (SE(2) manifold, constant velocity, no IMU)"""
+    return hostapi.window_params(k=p.n_results_nn_lookup, gnc_steps=p.gnc_steps, max_iteration=p.max_iteration, loss_scale=p.loss_function_scale,
+                                 alpha=p.loss_function_convexity, divisor=p.gnc_control_parameter_divisor, ndt_weight=p.ndt_weight,
+                                 covariance_scaling_factor=covariance_scaling_factor, motion_sqrtI_diag=motion_sqrtI_diag)
+
+
+def _se2_exp(u):
+    th = u[2]
+    if abs(th) < 1e-10:
+        a, b = 1.0 - th * th / 6.0, 0.5 * th - th ** 3 / 24.0
+    else:
+        a, b = math.sin(th) / th, (1.0 - math.cos(th)) / th
+    return np.array([math.cos(th), math.sin(th), a * u[0] - b * u[1], b * u[0] + a * u[1]])
+
+
+def _se2_mul(A, B):
+    re, im = A[0] * B[0] - A[1] * B[1], A[0] * B[1] + A[1] * B[0]
+    n2 = re * re + im * im
+    if n2 != 1.0:
+        sc = 2.0 / (1.0 + n2); re *= sc; im *= sc
+    return np.array([re, im, A[2] + (A[0] * B[2] - A[1] * B[3]), A[3] + (A[1] * B[2] + A[0] * B[3])])
+
+
+def oracle_window_replay(oracle, p, scans, stamps, q, smoothing_steps=3, insertion_step=2):
+    """the same loop on the CPU oracle (LocalFuser::processScan, local_fuser.cpp:99-300, one submap)"""
+    va = (p.n_clusters, p.max_range, p.min_points_per_cell, p.size_x, p.size_y, p.resolution, p.max_neighbor_linf_distance)
+    k = p.n_results_nn_lookup
+    insertion_delay = smoothing_steps + 1
+    t_start = time.perf_counter()
+    traj, window, to_insert, poses = [], [], [], []
+    cells = npts = slot = None
+    cur = np.array([1.0, 0.0, 0.0, 0.0])
+    qo = q.copy(); qo[14] = 0
+    for i, pts in enumerate(scans):
+        v = oracle.voxelize(pts, *va)
+        if cells is not None:
+            last = traj[-1].copy()
+            dt = max(stamps[i] - last[13], 0.2)
+            nxt = last.copy()
+            nxt[:4] = _se2_mul(last[:4], _se2_exp([last[7] * dt, last[8] * dt, last[9] * dt]))    # predictSE2 with zero acceleration
+            nxt[4:6] = nxt[2:4]; nxt[6] = math.atan2(nxt[1], nxt[0]); nxt[10:12] = 0.0; nxt[12] = 0.0; nxt[13] = stamps[i]
+            traj.append(nxt)
+            window.append(v)
+            W = min(len(traj) - 1, smoothing_steps)
+            st = np.array(traj[-W - 1:])
+            cm, cf, im_all, jf_all, seg_off, n_cells, mb, fb = [], [], [], [], [0], 0, 0, 0
+            for j in range(1, W + 1):
+                mv = window[len(window) - W + (j - 1)]
+                n_cells += len(mv["cells"])
+                im, jf = oracle.associate(cells, slot, p.size_x, p.size_y, p.resolution, p.max_neighbor_linf_distance, mv["cells"], st[j, :4], k)
+                im_all.append(im + mb); jf_all.append(jf + fb); cm.append(mv["cells"]); cf.append(cells)
+                mb += len(mv["cells"]); fb += len(cells)
+                seg_off.append(sum(len(a) for a in im_all))
+            s_out, t_out, info = oracle.window_solve(st, qo, cur, np.concatenate(cm), np.concatenate(cf), np.concatenate(im_all).astype(np.uint32),
+                                                     np.concatenate(jf_all).astype(np.uint32), np.array(seg_off, np.uint32), n_cells)
+            if info["status"] != 0:
+                raise RuntimeError("oracle window solve: nothing to solve at scan %d" % i)
+            for j in range(W + 1):
+                traj[len(traj) - W - 1 + j] = s_out[j]
+            cur = t_out
+            for b in range(1, min(smoothing_steps, len(traj)) + 1):      # both representations of the window states
+                X = traj[-b]; X[4:6] = X[2:4]; X[6] = math.atan2(X[1], X[0])
+            n = len(traj)
+            if len(window) >= smoothing_steps:
+                window.pop(0)
+            if n % insertion_step == 0:
+                to_insert.append(v)
+            if n >= insertion_delay + insertion_step and (n - insertion_delay) % insertion_step == 0 and to_insert:
+                Xs = traj[n - insertion_delay - 1]
+                kf = to_insert.pop(0)
+                mc = oracle.transform_cells(kf["cells"], *Xs[:4].astype(np.float32))
+                cells, npts, slot = oracle.merge_map_cell(cells, npts, slot, p.size_x, p.size_y, p.resolution, mc, kf["npts"])
+        else:
+            s0 = np.zeros(14); s0[:4] = cur; s0[4:6] = cur[2:4]; s0[6] = math.atan2(cur[1], cur[0]); s0[13] = stamps[i]
+            traj.append(s0)
+            cells, npts, slot = oracle.transform_cells(v["cells"], *cur.astype(np.float32)), v["npts"], v["slot"]
+        poses.append(cur.copy())
+    return np.array(poses), np.array(traj), len(cells), time.perf_counter() - t_start
+
+

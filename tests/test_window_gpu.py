@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 from randt_slam_b200 import capi, hostapi, params as P, synth
+from randt_slam_b200 import workloads as W
 from tests import helpers as H
 
 pytestmark = pytest.mark.gpu
@@ -142,3 +143,26 @@ def test_window_without_ndt_blocks_is_reported(oracle):
     q = hostapi.window_params(k=p.n_results_nn_lookup)
     s1, t1, info = hostapi.window_solve(capi.grid_params(p), fixed, fixed_se2, far, st, q, st[-2, :4])
     assert info["status"] == 1 and np.array_equal(s1, st) and np.array_equal(t1, st[-2, :4])
+
+
+# ---- a drive through the window odometry, scan by scan -------------------------------------------------------------------------------
+def test_window_odometry_drive_matches_the_oracle_chain(oracle):
+    """14 scans of a curve through randt_hostapi_window_replay (predictTransform -> estimateTransformCeres over the 3-scan window ->
+    delayed keyframe insertion at the smoothed pose) and through the same loop on the oracle: both chains run free"""
+    p = P.OXFORD
+    n = 14
+    truth = [(0.9 * i, 0.015 * i * i, 0.008 * i) for i in range(n)]
+    scans = [H.make_scan(p, 130, truth[i], 600 + i) for i in range(n)]
+    stamps = 0.25 * np.arange(n)
+    q = W.window_odometry_params(hostapi, p)
+    poses, states, stats, totals = hostapi.window_replay(capi.grid_params(p), scans, stamps, q, smoothing_steps=3, insertion_step=2)
+    o_poses, o_states, o_cells, _ = W.oracle_window_replay(oracle, p, scans, stamps, q, 3, 2)
+    assert totals["keyframes"] == 5 and totals["submap_cells"] == o_cells      # trajectory sizes 6, 8, 10, 12, 14
+    # both chains run free at ceres' default tolerances (a solve stops where the relative cost change drops under 1e-6): observed 1e-5
+    assert np.max(np.abs(poses - o_poses)) < 1e-4, np.max(np.abs(poses - o_poses), axis=1)
+    assert np.max(np.abs(states - o_states)) < 1e-4
+    est = np.stack([states[:, 2], states[:, 3], np.arctan2(states[:, 1], states[:, 0])], 1)
+    assert np.max(np.abs(est[:, :2] - np.array(truth)[:, :2])) < 0.35 and np.max(np.abs(est[:, 2] - np.array(truth)[:, 2])) < 0.02
+    assert np.all(stats[1:, 1] >= 3) and np.all(stats[1:, 2] == 0)
+    # velocities were learnt from the motion-model factors: ~0.9 m per 0.25 s
+    assert abs(states[-1, 7] - 3.6) < 0.8
