@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdio>
 #include <random>
+#include <deque>
 #include <vector>
 
 #include "randt_host.hpp"
@@ -50,6 +51,27 @@ int main() {
       if (accepted && k % 2 == 0) {                          // insertion_step
         scan.transformMap(pose);
         submap.mergeMapCell(scan);
+      }
+    }
+
+    // the same scans through the reference's own odometry entry points: predictTransform + estimateTransformCeres over the smoothing
+    // window (NDT blocks of the window states + motion-model factors), local_fuser.cpp:125-138
+    {
+      std::vector<randt::State> trajectory(1);               // the submap's first state: identity, zero velocities, stamp 0
+      std::deque<randt::Map> f_maps, map_window;
+      f_maps.emplace_back(gpu, map_params);
+      f_maps.back().addClusters(toy_scan(0.0, 0.0, 0.0, 1));
+      randt::SE2d current_transform;
+      for (int k = 1; k <= 4; ++k) {
+        const double stamp = 0.25 * k;
+        matcher.predictTransform(/*yaw=*/0.0, stamp, trajectory);
+        map_window.emplace_back(gpu, map_params);
+        map_window.back().addClusters(toy_scan(0.15 * k, 0.02 * k, 0.01 * k, 10 + k));
+        matcher.estimateTransformCeres(current_transform, trajectory, 0.0, stamp, f_maps, map_window);
+        const randt::WindowSummary& ws = matcher.lastWindowSummary();
+        std::printf("window %d: x %.3f  y %.3f  theta %.4f  v %.3f  (%d states, %d LM iterations, %d K3 launches)\n", k, current_transform.v[2],
+                    current_transform.v[3], current_transform.angle(), trajectory.back().lin_vel[0], ws.n_free_states, ws.total_iterations, ws.evaluations);
+        if ((int)map_window.size() >= matcher.parameters().smoothing_steps) map_window.pop_front();
       }
     }
 
