@@ -204,6 +204,12 @@ RANDT_API int randt_associate(randt_ctx* ctx, const randt_map* fixed, const rand
 RANDT_API int randt_problem_create(randt_ctx* ctx, const float* cells_m, uint32_t n_m, const float* cells_f, uint32_t n_f,
                                    const uint32_t* pair_m, const uint32_t* pair_f, uint32_t n_pairs, const uint32_t* seg_off,
                                    uint32_t n_segments, randt_problem** out);
+/* Joins problems on the device (no host copy of their tables): part i contributes its cell snapshots, pairs and duos with shifted indices;
+ * its pairs go to segment seg_of_part[i] of the result (seg_of_part non-decreasing, every part a single-segment problem of this context's
+ * device).  This is how the residual blocks of several addNDTFactor calls become one problem: the blocks of every window state of
+ * Matcher::estimateTransformCeres (ndt_matcher.cpp:356-360: per state, one call per fixed map) -> one segment per state. */
+RANDT_API int randt_problem_concat(randt_ctx* ctx, const randt_problem* const* parts, uint32_t n_parts, const uint32_t* seg_of_part,
+                                   uint32_t n_segments, randt_problem** out);
 RANDT_API int randt_problem_info(const randt_problem* p, uint32_t* n_segments, uint32_t* n_pairs, uint32_t* n_m, uint32_t* n_f);
 /* how K3 holds the problem in HBM: records of record_bytes each (one per duo = two pairs sharing their moving cell), of which
  * n_overflow needed a full-precision side record; any pointer may be NULL */

@@ -116,6 +116,7 @@ _SIGS = {
     "randt_associate": (_i, [_vp, _vp, _vp, _vp, _i, _i, C.POINTER(_vp)]),
     "randt_problem_create": (_i, [_vp, _vp, _u32, _vp, _u32, _vp, _vp, _u32, _vp, _u32, C.POINTER(_vp)]),
     "randt_problem_info": (_i, [_vp, C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_u32)]),
+    "randt_problem_concat": (_i, [_vp, _vp, _u32, _vp, _u32, C.POINTER(_vp)]),
     "randt_register_batch_weighted": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "randt_points_from_pcl_xyzi": (_i, [_vp, _vp, _u32, _i, _vp]),
     "randt_scan_step": (_i, [_vp, _vp, _vp, _u32, _vp, _i, _i, _vp, C.c_double, _vp, _i, _vp, _vp, _vp]),
@@ -301,6 +302,14 @@ class Context:
         out = C.c_void_p()
         self._check(lib().randt_problem_create(self._h, _ptr(cells_m), len(cells_m), _ptr(cells_f), len(cells_f), _ptr(pair_m),
                                                _ptr(pair_f), len(pair_m), _ptr(seg_off), len(seg_off) - 1, C.byref(out)))
+        return Problem(self, out)
+
+    def problem_concat(self, parts, seg_of_part, n_segments):
+        """single-segment problems joined on the device: the pairs of part i go to segment seg_of_part[i] (non-decreasing)"""
+        hs = (C.c_void_p * len(parts))(*[q._h.value for q in parts])
+        so = _u32a(seg_of_part)
+        out = C.c_void_p()
+        self._check(lib().randt_problem_concat(self._h, hs, len(parts), _ptr(so), int(n_segments), C.byref(out)))
         return Problem(self, out)
 
 

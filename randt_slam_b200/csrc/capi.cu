@@ -927,6 +927,45 @@ int randt_problem_create(randt_ctx* ctx, const float* cells_m, uint32_t n_m, con
   return RANDT_OK;
 }
 
+int randt_problem_concat(randt_ctx* ctx, const randt_problem* const* parts, uint32_t n_parts, const uint32_t* seg_of_part, uint32_t n_segments,
+                         randt_problem** out) {
+  if (!ctx || !out || (n_parts && (!parts || !seg_of_part))) return fail(ctx, RANDT_E_INVALID, "randt_problem_concat: null argument");
+  *out = nullptr;
+  uint64_t n_m = 0, n_f = 0, n_p = 0, n_d = 0;
+  for (uint32_t i = 0; i < n_parts; ++i) {
+    const randt_problem* q = parts[i];
+    if (!q || q->S != 1 || q->device != ctx->device) return fail(ctx, RANDT_E_INVALID, "randt_problem_concat: parts must be single-segment problems of this device");
+    if (seg_of_part[i] >= n_segments || (i && seg_of_part[i] < seg_of_part[i - 1])) return fail(ctx, RANDT_E_INVALID, "randt_problem_concat: seg_of_part must be non-decreasing and below n_segments");
+    n_m += q->n_m; n_f += q->n_f; n_p += q->P; n_d += q->n_duos;
+  }
+  if (n_m > 0xffffffffull || n_f > 0xffffffffull || n_p > 0xffffffffull) return fail(ctx, RANDT_E_CAPACITY, "randt_problem_concat: joint tables exceed 32-bit indices");
+  CK(cudaSetDevice(ctx->device));
+  StreamScope scope__(ctx->stream, ctx->sref->pool);
+  randt_problem* p = new (std::nothrow) randt_problem();
+  if (!p) return RANDT_E_NOMEM;
+  p->device = ctx->device; p->sref = ctx->sref; p->S = n_segments; p->P = (uint32_t)n_p; p->n_m = (uint32_t)n_m; p->n_f = (uint32_t)n_f; p->n_duos = (uint32_t)n_d;
+  p->h_seg_off.assign((size_t)n_segments + 1, 0u); p->h_duo_off.assign((size_t)n_segments + 1, 0u);
+  int rc = RANDT_OK, nl = 0;
+#define CKC(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rc = fail(ctx, RANDT_E_CUDA, #call, e__); free_problem(p); return rc; } } while (0)
+  CKC(dev_alloc(&p->cells_m, (size_t)n_m * 3)); CKC(dev_alloc(&p->cells_f, (size_t)n_f * 3)); CKC(dev_alloc(&p->pairs, n_p)); CKC(dev_alloc(&p->duos, n_d));
+  uint32_t mb = 0, fb = 0, pb = 0, db = 0;
+  for (uint32_t i = 0; i < n_parts; ++i) {
+    const randt_problem* q = parts[i];
+    // the parts' tables were written on their creating context's stream; the parts of one caller share it (ordering is the caller's otherwise)
+    if (q->n_m) CKC(cudaMemcpyAsync(p->cells_m + 3 * (size_t)mb, q->cells_m, (size_t)q->n_m * 48, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (q->n_f) CKC(cudaMemcpyAsync(p->cells_f + 3 * (size_t)fb, q->cells_f, (size_t)q->n_f * 48, cudaMemcpyDeviceToDevice, ctx->stream));
+    CKC(launch_shift_part(q->pairs, q->P, q->duos, q->n_duos, mb, fb, pb, p->pairs + pb, p->duos + db, ctx->stream, &nl));
+    mb += q->n_m; fb += q->n_f; pb += q->P; db += q->n_duos;
+    for (uint32_t s = seg_of_part[i] + 1; s <= n_segments; ++s) { p->h_seg_off[s] = pb; p->h_duo_off[s] = db; }
+  }
+#undef CKC
+  ctx->launches += nl;
+  rc = finish_problem(ctx, p);
+  if (rc != RANDT_OK) { free_problem(p); return rc; }
+  *out = p;
+  return RANDT_OK;
+}
+
 int randt_problem_info(const randt_problem* p, uint32_t* n_segments, uint32_t* n_pairs, uint32_t* n_m, uint32_t* n_f) {
   if (!p) return RANDT_E_INVALID;
   if (n_segments) *n_segments = p->S;

@@ -132,6 +132,8 @@ cudaError_t launch_compact_duos(const uint32_t* d_nn, const uint32_t* d_cnt, con
                                 const uint32_t* cell_off_m, const uint32_t* cell_off_f, uint32_t n_maps, uint32_t n_m_total,
                                 uint32_t max_m_per_map, int k, Duo* d_duos, cudaStream_t s, int* n_launches);
 cudaError_t launch_duo_counts(const uint32_t* d_cnt, uint32_t n, uint32_t* d_cnt2, cudaStream_t s, int* n_launches);
+cudaError_t launch_shift_part(const uint2* pairs_in, uint32_t n_pairs, const Duo* duos_in, uint32_t n_duos, uint32_t m_base, uint32_t f_base,
+                              uint32_t p_base, uint2* pairs_out, Duo* duos_out, cudaStream_t s, int* n_launches);
 cudaError_t launch_gather_offsets(const uint32_t* d_scan, const uint32_t* d_scan2, const uint32_t* cell_off, uint32_t n_off, uint32_t* d_out,
                                   cudaStream_t s, int* n_launches);
 cudaError_t launch_exclusive_scan_u32(const uint32_t* d_in, uint32_t* d_out /*[n+1]*/, uint32_t n, uint32_t* d_block_sums, cudaStream_t s,

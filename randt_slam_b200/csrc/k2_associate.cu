@@ -321,6 +321,20 @@ __global__ void __launch_bounds__(kScanThreads) scan_add_kernel(uint32_t* __rest
   for (int e = 0; e < kScanItems; ++e) if (base + e < n) out[base + e] += add;
 }
 
+// randt_problem_concat: the pairs and duos of one part, shifted into the joint tables (moving / fixed cell indices by the rows already
+// there, pair indices by the pairs already there)
+__global__ void __launch_bounds__(256) shift_part_kernel(const uint2* __restrict__ pairs_in, uint32_t n_pairs, const Duo* __restrict__ duos_in, uint32_t n_duos,
+                                                         uint32_t m_base, uint32_t f_base, uint32_t p_base, uint2* __restrict__ pairs_out,
+                                                         Duo* __restrict__ duos_out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_pairs) { const uint2 v = pairs_in[i]; pairs_out[i] = make_uint2(v.x + m_base, v.y + f_base); }
+  if (i < n_duos) {
+    Duo d = duos_in[i];
+    d.im += m_base; d.jf0 += f_base; if (d.jf1 != kNoCell) d.jf1 += f_base; d.p0 += p_base;
+    duos_out[i] = d;
+  }
+}
+
 }  // namespace
 
 cudaError_t launch_associate(const float4* cells_f, const uint32_t* cell_off_f, const int32_t* slot_f, const float4* cells_m,
@@ -389,6 +403,15 @@ cudaError_t launch_exclusive_scan_u32(const uint32_t* d_in, uint32_t* d_out, uin
   scan_sums_kernel<<<1, kScanThreads, 0, s>>>(d_block_sums, n_blocks, d_out + n);
   scan_add_kernel<<<n_blocks, kScanThreads, 0, s>>>(d_out, n, d_block_sums);
   if (n_launches) *n_launches += 3;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_shift_part(const uint2* pairs_in, uint32_t n_pairs, const Duo* duos_in, uint32_t n_duos, uint32_t m_base, uint32_t f_base,
+                              uint32_t p_base, uint2* pairs_out, Duo* duos_out, cudaStream_t s, int* n_launches) {
+  const uint32_t n = n_pairs > n_duos ? n_pairs : n_duos;
+  if (n == 0) return cudaSuccess;
+  shift_part_kernel<<<(n + 255) / 256, 256, 0, s>>>(pairs_in, n_pairs, duos_in, n_duos, m_base, f_base, p_base, pairs_out, duos_out);
+  if (n_launches) ++*n_launches;
   return cudaGetLastError();
 }
 

@@ -515,9 +515,8 @@ void Matcher::solveWindow(SE2d& trans, std::vector<State>& trajectory, const std
 
   // ---- NDT residual blocks: per free state (oldest first), per fixed map, addNDTFactor at the state's own pose (:356-359)
   struct Problems { std::vector<randt_problem*> v; ~Problems() { for (randt_problem* q : v) randt_problem_destroy(q); } } probs;
-  std::vector<float> cells_m, cells_f;
-  std::vector<uint32_t> pair_m, pair_f, seg_off(W + 1, 0);
-  size_t n_cells = 0;
+  std::vector<uint32_t> seg_of_part;
+  size_t n_cells = 0, n_blocks = 0;
   for (size_t j = 1; j <= W; ++j) {
     State& X = trajectory[trajectory.size() - 1 - W + j];
     const Map& moving = *moving_window[moving_window.size() - W + (j - 1)];
@@ -526,24 +525,17 @@ void Matcher::solveWindow(SE2d& trans, std::vector<State>& trajectory, const std
     for (const Map* fixed : fixed_ndts) {
       randt_problem* q = associate(&guess, *fixed, moving, use_intensity, k);
       probs.v.push_back(q);
-      uint32_t S = 0, P = 0, nm = 0, nf = 0;
-      ctx_->check(randt_problem_info(q, &S, &P, &nm, &nf));
-      std::vector<uint32_t> pm(P), pf(P);
-      std::vector<float> cm((size_t)nm * 12), cf((size_t)nf * 12);
-      if (P) ctx_->check(randt_problem_download(ctx_->get(), q, pm.data(), pf.data(), nullptr));
-      ctx_->check(randt_problem_download_cells(ctx_->get(), q, nm ? cm.data() : nullptr, nf ? cf.data() : nullptr));
-      const uint32_t mb = (uint32_t)(cells_m.size() / 12), fb = (uint32_t)(cells_f.size() / 12);
-      for (uint32_t i = 0; i < P; ++i) { pair_m.push_back(pm[i] + mb); pair_f.push_back(pf[i] + fb); }
-      cells_m.insert(cells_m.end(), cm.begin(), cm.end());
-      cells_f.insert(cells_f.end(), cf.begin(), cf.end());
+      seg_of_part.push_back((uint32_t)(j - 1));
+      uint32_t P = 0;
+      ctx_->check(randt_problem_info(q, nullptr, &P, nullptr, nullptr));
+      n_blocks += P;
     }
-    seg_off[j] = (uint32_t)pair_m.size();
     n_cells += moving.get_n_cells();   // :361
   }
-  if (pair_m.empty() || n_cells == 0) { window_summary_.status = 1; return; }
+  if (n_blocks == 0 || n_cells == 0) { window_summary_.status = 1; return; }
+  // one problem, one segment per window state, joined on the device (cell snapshots, pairs and duos never visit the host)
   randt_problem* merged = nullptr;
-  ctx_->check(randt_problem_create(ctx_->get(), cells_m.data(), (uint32_t)(cells_m.size() / 12), cells_f.data(), (uint32_t)(cells_f.size() / 12),
-                                   pair_m.data(), pair_f.data(), (uint32_t)pair_m.size(), seg_off.data(), (uint32_t)W, &merged));
+  ctx_->check(randt_problem_concat(ctx_->get(), probs.v.data(), (uint32_t)probs.v.size(), seg_of_part.data(), (uint32_t)W, &merged));
   probs.v.push_back(merged);
 
   // ---- parameter blocks and host factors

@@ -166,3 +166,52 @@ def test_window_odometry_drive_matches_the_oracle_chain(oracle):
     assert np.all(stats[1:, 1] >= 3) and np.all(stats[1:, 2] == 0)
     # velocities were learnt from the motion-model factors: ~0.9 m per 0.25 s
     assert abs(states[-1, 7] - 3.6) < 0.8
+
+
+def test_problem_concat_equals_the_host_built_joint_problem(oracle, gpu_ctx):
+    """randt_problem_concat (device-side join of the per-state, per-fixed-map associations) == the same tables downloaded, joined on the
+    host and handed to randt_problem_create: pair lists, cell snapshots and the fused records, bit for bit"""
+    p = P.OXFORD
+    gp = capi.grid_params(p)
+    k = p.n_results_nn_lookup
+    rng = np.random.default_rng(3)
+    fixed, fixed_se2, window, st = make_case(p, 123, 2, 3, rng)
+    f_maps = []
+    for pts, T in zip(fixed, fixed_se2):
+        m = gpu_ctx.voxelize(pts, [0, len(pts)], gp); m.transform_se2d(T[None]); f_maps.append(m)
+    parts, seg_of_part = [], []
+    for j in range(3):
+        mv = gpu_ctx.voxelize(window[j], [0, len(window[j])], gp)
+        for fm in f_maps:
+            parts.append(gpu_ctx.associate(fm, mv, st[j + 1, :4][None], k)); seg_of_part.append(j)
+        mv.close()
+    joint = gpu_ctx.problem_concat(parts, seg_of_part, 3)
+    cm, cf, pm, pf, so, mb, fb = [], [], [], [], [0], 0, 0
+    for q, sg in zip(parts, seg_of_part):
+        a, b, _ = q.download(); m_, f_ = q.download_cells()
+        pm.append(a + mb); pf.append(b + fb); cm.append(m_); cf.append(f_); mb += len(m_); fb += len(f_)
+        if len(so) == sg + 1:
+            so.append(0)
+        so[sg + 1] = sum(len(x) for x in pm)
+    ref = gpu_ctx.problem_create(np.concatenate(cm), np.concatenate(cf), np.concatenate(pm), np.concatenate(pf), np.array(so, np.uint32))
+    assert joint.n_segments == 3 and joint.n_pairs == ref.n_pairs > 100
+    for x, y in zip(joint.download(), ref.download()):
+        assert np.array_equal(x, y)
+    for x, y in zip(joint.download_cells(), ref.download_cells()):
+        assert np.array_equal(x, y)
+    loss = capi.make_loss(capi.LOSS_BARRON, 1.0, -2.0, 1.3, 0.02)
+    poses = st[1:, :4].copy()
+    assert np.array_equal(joint.eval_fused(poses, loss), ref.eval_fused(poses, loss))
+    r0, J0 = joint.eval_emit(poses); r1, J1 = ref.eval_emit(poses)
+    assert np.array_equal(r0, r1) and np.array_equal(J0, J1)
+    # an empty segment in the middle (a window scan without cells) and misuse
+    gap = gpu_ctx.problem_concat([parts[0], parts[5]], [0, 2], 3)
+    out = gap.eval_fused(poses, loss)
+    assert np.all(out[1] == 0.0)
+    assert np.array_equal(out[0], parts[0].eval_fused(poses[0:1], loss)[0]) and np.array_equal(out[2], parts[5].eval_fused(poses[2:3], loss)[0])
+    with pytest.raises(capi.RandtError):
+        gpu_ctx.problem_concat([parts[1], parts[0]], [1, 0], 3)
+    with pytest.raises(capi.RandtError):
+        gpu_ctx.problem_concat([joint], [0], 1)
+    for q in parts + [joint, ref, gap] + f_maps:
+        q.close()
