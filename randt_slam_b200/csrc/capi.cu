@@ -203,6 +203,14 @@ int pinned_reserve(randt_ctx* ctx, uint32_t** buf, size_t* cap, size_t words) {
 // tile list, balanced schedule, record table and per-segment bookkeeping from the host offsets of a problem.  The host computes the
 // tile assignment only (schedule.hpp build_schedule_core, vectors reused between calls); everything the device needs goes up in ONE
 // copy from a pinned block, and the chunk lists of both plans are written by a kernel.
+// Resident warps the K3 schedule is built for.  RANDT_K3_MAX_WARPS (diagnostic, read per problem) lowers it, so that a small problem gives
+// every warp a long chunk list (tests walk the descriptor queue through several refills that way).
+uint32_t k3_warp_budget() {
+  const char* e = getenv("RANDT_K3_MAX_WARPS");
+  if (e) { const long v = strtol(e, nullptr, 10); if (v >= 1 && v < (long)kK3MaxWarps) return (uint32_t)v; }
+  return (uint32_t)kK3MaxWarps;
+}
+
 int finish_problem(randt_ctx* ctx, randt_problem* p, bool records_ready = false) {
   static const bool trace = getenv("RANDT_DEBUG_TIMING") != nullptr;
   auto t_prev = std::chrono::steady_clock::now();
@@ -214,7 +222,7 @@ int finish_problem(randt_ctx* ctx, randt_problem* p, bool records_ready = false)
   };
   Schedule& sch = ctx->sched;
   const uint32_t S = p->S;
-  build_schedule_core(p->h_duo_off.data(), S, (uint32_t)kK3MaxWarps, sch);     // schedule.hpp: tiles, LPT assignment, record layout, chunk ranges
+  build_schedule_core(p->h_duo_off.data(), S, k3_warp_budget(), sch);     // schedule.hpp: tiles, LPT assignment, record layout, chunk ranges
   const uint32_t W = sch.n_warps, T = (uint32_t)sch.tiles.size();
   lap("schedule");
   p->n_warps = W; p->n_tiles = T;

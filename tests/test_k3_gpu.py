@@ -279,6 +279,37 @@ def test_fused_ragged_segments_cover_every_chunk_shape(oracle, gpu_ctx, k):
         assert np.max(np.abs(r[a:b] - ro) / ro) < TOL and rowwise(J[a:b], Jo) < 1e-8
 
 
+def test_a_warp_walks_its_descriptor_queue_through_several_refills(oracle, gpu_ctx, monkeypatch):
+    """ADVICE (round 1): a warp that owns more than 64 chunks refills its 2 x 32-entry descriptor queue while chunks are in flight.  With
+    the schedule built for 4 warps (RANDT_K3_MAX_WARPS) every warp owns ~170 chunks (five refills): FUSED and EMIT must equal the
+    default schedule's results bit for bit (a segment's sums depend on its own tiles only) and the oracle to tolerance."""
+    rng = np.random.default_rng(77)
+    sizes = [500] * 20 + [37, 1, 700, 64, 500, 500, 33, 500] + [500] * 14
+    n_m = sum(sizes)
+    cm = H.random_cells(rng, n_m, extent=6.0); cf = H.random_cells(rng, 900, extent=6.0)
+    im = np.repeat(np.arange(n_m, dtype=np.uint32), 2); jf = rng.integers(0, 900, 2 * n_m).astype(np.uint32)
+    seg = np.concatenate([[0], 2 * np.cumsum(sizes)]).astype(np.uint32)
+    S = len(sizes)
+    poses = np.stack([synth.pose_to_se2(*rng.uniform(-0.3, 0.3, 3)) for _ in range(S)])
+    loss = capi.make_loss(capi.LOSS_BARRON, 1.5, -2.0, 1.4, 0.02)
+    ref = gpu_ctx.problem_create(cm, cf, im, jf, seg)
+    monkeypatch.setenv("RANDT_K3_MAX_WARPS", "4")
+    few = gpu_ctx.problem_create(cm, cf, im, jf, seg)
+    monkeypatch.delenv("RANDT_K3_MAX_WARPS")
+    sch = few.schedule()
+    assert sch["n_warps"] == 4 and ref.schedule()["n_warps"] > 4
+    assert np.min(np.diff(sch["woff_a"])) > 128 and np.min(np.diff(sch["woff_b"])) > 128        # > 2 queues' worth of chunks per warp
+    a = few.eval_fused(poses, loss); b = ref.eval_fused(poses, loss)
+    assert np.array_equal(a, b)
+    ra, Ja = few.eval_emit(poses); rb, Jb = ref.eval_emit(poses)
+    assert np.array_equal(ra, rb) and np.array_equal(Ja, Jb)
+    out = capi.unpack_fused(a)
+    fo, _ = oracle.fused_batch(0, cm, cf, im, jf, seg, poses, (loss.kind, loss.scale, loss.alpha, loss.mu, loss.weight))
+    for s_ in range(S):
+        assert H.rel_err(out["H"][s_], fo["H"][s_]) < 1e-9 and H.rel_err(out["g"][s_], fo["g"][s_]) < 1e-9
+    few.close(); ref.close()
+
+
 def test_fused_one_very_long_segment(oracle, gpu_ctx):
     """a single segment of 300 k pairs: ~590 tiles folded by the ticket/partial path"""
     rng = np.random.default_rng(5)
