@@ -317,4 +317,29 @@ int orc_window_solve(const float* cells_m, const float* cells_f, const uint32_t*
   return R.status;
 }
 
+// One host factor of the window problem as ceres sees it: residuals and the AMBIENT Jacobian over the 2 x 10 parameter slots of its two
+// states (slot of state side s: 10 s + pose 0-3 | pos 0-1, rot 2 | lin_vel 4-5 | rot_vel 6 | lin_acc 7-8 | imu_bias 9), every parameter
+// free.  kind 0: MotionModelFactorSE2 / MotionModelFactor (8 residuals), kind 1: RotationalResidualSE2 / RotationalResidual (2).
+// states: a14, b14 as in orc_window_solve.  Returns the number of residuals; jac is [nres][20] row-major.
+int orc_factor_block(int kind, int manifold, const double* a14, const double* b14, const double* sqrtI64, double imu_rot, double weight_imu,
+                     double weight_bias, double* residuals, double* jac) {
+  typedef Jet<20> J;
+  auto load = [&](const double* s, int base, StateT<J>& S, J& bias) {
+    for (int i = 0; i < 4; ++i) S.pose[i] = manifold ? J(s[i], base + i) : J(s[i]);
+    S.pos[0] = manifold ? J(s[4]) : J(s[4], base + 0); S.pos[1] = manifold ? J(s[5]) : J(s[5], base + 1); S.rot = manifold ? J(s[6]) : J(s[6], base + 2);
+    S.vel[0] = J(s[7], base + 4); S.vel[1] = J(s[8], base + 5); S.omega = J(s[9], base + 6);
+    S.acc[0] = J(s[10], base + 7); S.acc[1] = J(s[11], base + 8);
+    bias = J(s[12], base + 9);
+  };
+  StateT<J> A, B; J ba, bb;
+  load(a14, 0, A, ba); load(b14, 10, B, bb);
+  const double dt = b14[13] - a14[13];
+  J res[8];
+  int n = 8;
+  if (kind == 0) { if (manifold) motion_factor_se2(A, B, dt, sqrtI64, res); else motion_factor_vec(A, B, dt, sqrtI64, res); }
+  else { n = 2; imu_factor(manifold != 0, A, B, ba, bb, imu_rot, weight_imu, dt, weight_bias, res); }
+  for (int r = 0; r < n; ++r) { residuals[r] = res[r].a; for (int c = 0; c < 20; ++c) jac[r * 20 + c] = res[r].v[c]; }
+  return n;
+}
+
 }  // extern "C"

@@ -96,6 +96,7 @@ def _sig(L):
     L.orc_se2_plus_jacobian.restype = None; L.orc_se2_plus_jacobian.argtypes = [pd, pd]
     L.orc_set_tolerances.restype = None; L.orc_set_tolerances.argtypes = [d, d, d]
     L.orc_window_evaluate.restype = i; L.orc_window_evaluate.argtypes = [pf, pf, pu, pu, pu, i, pd, pd, pd, i, d, d, pd, pd, pd, pd]
+    L.orc_factor_block.restype = i; L.orc_factor_block.argtypes = [i, i, pd, pd, pd, d, d, d, pd, pd]
     L.orc_window_solve.restype = i; L.orc_window_solve.argtypes = [pf, pf, pu, pu, pu, i, pd, pd, pd, sz, pd, pd]
 
 
@@ -366,3 +367,12 @@ def window_solve(states14, params80, trans, cells_m, cells_f, im, jf, seg_off, n
             lib().orc_set_tolerances(C.c_double(0.0), C.c_double(0.0), C.c_double(0.0))
     keys = ("status", "rejected", "gnc_solves", "total_iterations", "final_cost", "mu_first", "max_residual", "n_tangent")
     return st, t, dict(zip(keys, out.tolist()))
+
+
+def factor_block(kind, manifold, a14, b14, sqrtI64, imu_rot=0.0, weight_imu=0.0, weight_bias=0.0):
+    """one motion-model (kind 0) or IMU (kind 1) factor between two states: residuals [n] and the ambient Jacobian [n, 20] over the
+    parameter slots 10 * side + (pose 0-3 | pos 0-1, rot 2 | lin_vel 4-5 | rot_vel 6 | lin_acc 7-8 | imu_bias 9)"""
+    res = np.zeros(8); jac = np.zeros((8, 20))
+    n = lib().orc_factor_block(int(kind), int(bool(manifold)), _p(_f64(a14), C.c_double), _p(_f64(b14), C.c_double), _p(_f64(sqrtI64), C.c_double),
+                               float(imu_rot), float(weight_imu), float(weight_bias), _p(res, C.c_double), _p(jac, C.c_double))
+    return res[:n].copy(), jac[:n].copy()

@@ -60,6 +60,48 @@ def main():
             [f.write(r17(c) + "\n") for c in g["cells_m"]]; [f.write(r17(c) + "\n") for c in g["cells_f"]]
             f.write(" ".join(str(i) for i in g["pair_m"]) + "\n" + " ".join(str(i) for i in g["pair_f"]) + "\n" + r17(g["pose0"]) + "\n")
     print(txt, os.path.getsize(txt), "bytes")
+    window_inputs(rng)
+
+
+def window_inputs(rng):
+    """seeded state pairs for the host factors of estimateTransformCeres' window problem (gen_window_fixtures.cpp): poses near each other
+    along a drive (small and large rotation differences, identical stamps for the 0.2 s clamp, a rotation difference exactly 0 for the
+    series branches of SE2::log / exp), velocities, accelerations, IMU biases"""
+    import math
+    sqrtI = 0.3 * np.diag([1.0, 1.0, 10.0, 1.0, 3.0, 0.1, 20.0, 60.0])
+    sqrtI[0, 3] = 0.05; sqrtI[4, 1] = -0.02            # off-diagonal entries: applyOnTheLeft is a full matrix product
+    cases = []
+    for i in range(24):
+        th = rng.uniform(-3.0, 3.0); x, y = rng.uniform(-20, 20, 2)
+        v = rng.normal([4.0, 0.2], [1.5, 0.5]); om = rng.normal(0.1, 0.2); acc = rng.normal(0, 0.5, 2)
+        dt = [0.25, 0.2486, 0.0, 0.05, 0.4][i % 5]
+        d = rng.normal(0, [0.3, 0.3, 0.05])
+        if i == 3:
+            d[2] = 0.0; om = 0.0                          # pose_pred^-1 * pose_1 with rotation exactly 0, exp() of a screw without rotation
+        if i == 7:
+            d[2] = 2.5                                    # a large rotation residual
+        dte = max(dt, 0.2)
+        th1 = th + om * dte + d[2]; x1 = x + math.cos(th) * v[0] * dte - math.sin(th) * v[1] * dte + d[0]; y1 = y + math.sin(th) * v[0] * dte + math.cos(th) * v[1] * dte + d[1]
+        a = [math.cos(th), math.sin(th), x, y, x, y, th, v[0], v[1], om, acc[0], acc[1], rng.normal(0, 0.01), 10.0]
+        b = [math.cos(th1), math.sin(th1), x1, y1, x1, y1, th1, v[0] + rng.normal(0, 0.3), v[1] + rng.normal(0, 0.3), om + rng.normal(0, 0.05),
+             acc[0] + rng.normal(0, 0.1), acc[1] + rng.normal(0, 0.1), rng.normal(0, 0.01), 10.0 + dt]
+        if i == 11:
+            a[0] *= 1.001; a[1] *= 1.001                  # a complex part that is not exactly of unit length (what LM steps leave behind)
+        cases.append(dict(a=a, b=b, imu_rot=float(om * dt + rng.normal(0, 0.01))))
+    doc = dict(note="state14 = cos, sin, tx, ty, pos_x, pos_y, rot, vx, vy, omega, ax, ay, imu_bias, stamp", sqrtI=sqrtI.tolist(), weight_imu=64.0,
+               weight_imu_bias=750.0, cases=cases)
+    out = os.path.join(ROOT, "tests", "golden", "ref_full_window_inputs.json")
+    with open(out, "w") as f:
+        json.dump(doc, f)
+    txt = os.path.join(ROOT, "tests", "golden", "ref_full_window_inputs.txt")
+    r17 = lambda v: " ".join("%.17g" % x for x in v)
+    with open(txt, "w") as f:
+        f.write("sqrtI\n" + "\n".join(r17(row) for row in sqrtI.tolist()) + "\n")
+        f.write("imu_weights %s\n" % r17([doc["weight_imu"], doc["weight_imu_bias"]]))
+        f.write("cases %d\n" % len(cases))
+        for c in cases:
+            f.write("case\n" + r17(c["a"]) + "\n" + r17(c["b"]) + "\n" + r17([c["imu_rot"]]) + "\n")
+    print(txt, os.path.getsize(txt), "bytes")
 
 
 if __name__ == "__main__":

@@ -169,3 +169,123 @@ def test_cuda_matches_full_reference_fixtures(gpu_ctx):
         got["registrations"].append(pair)
         prob.close()
     compare(ref, got, "cuda vs reference")
+
+
+# ---- the host factors of estimateTransformCeres' window problem (oracle/ref_full/gen_window_fixtures.cpp) -------------------------------
+W_INPUTS = os.path.join(ROOT, "tests", "golden", "ref_full_window_inputs.json")
+W_OUTPUTS = os.path.join(ROOT, "tests", "golden", "ref_full_window_outputs.txt")
+W_ORDER = [(0, 1), (0, 0), (1, 1), (1, 0)]      # (kind, manifold): motion SE2, motion vector, imu SE2, imu vector
+
+
+def parse_window_outputs(path):
+    tok = open(path).read().split()
+    pos = 0
+
+    def take(n):
+        nonlocal pos
+        v = tok[pos:pos + n]; pos += n
+        return v
+    assert take(1) == ["cases"]
+    n = int(take(1)[0])
+    cases = []
+    for _ in range(n):
+        blocks = {}
+        for _ in range(4):
+            assert take(1) == ["block"]
+            kind, manifold, nres, ok = (int(x) for x in take(4))
+            rows = np.array(take(21 * nres), np.float64).reshape(nres, 21)
+            blocks[(kind, manifold)] = dict(ok=ok, res=rows[:, 0].copy(), jac=rows[:, 1:].copy())
+        cases.append(blocks)
+    assert pos == len(tok)
+    return cases
+
+
+def oracle_window_outputs(O, doc):
+    sq = np.array(doc["sqrtI"], np.float64).reshape(64)
+    out = []
+    for c in doc["cases"]:
+        blocks = {}
+        for kind, manifold in W_ORDER:
+            r, J = O.factor_block(kind, manifold, c["a"], c["b"], sq, c["imu_rot"], doc["weight_imu"], doc["weight_imu_bias"])
+            blocks[(kind, manifold)] = dict(ok=1, res=r, jac=J)
+        out.append(blocks)
+    return out
+
+
+def write_window_outputs(path, cases):
+    with open(path, "w") as f:
+        f.write("cases %d\n" % len(cases))
+        for blocks in cases:
+            for kind, manifold in W_ORDER:
+                b = blocks[(kind, manifold)]
+                f.write("block %d %d %d %d\n" % (kind, manifold, len(b["res"]), b["ok"]))
+                for r, row in zip(b["res"], b["jac"]):
+                    f.write("%.17g %s\n" % (r, " ".join("%.17g" % x for x in row)))
+
+
+def compare_window(ref, got, what, tol=1e-9):
+    assert len(ref) == len(got)
+    for i, (a, b) in enumerate(zip(ref, got)):
+        for key in W_ORDER:
+            assert a[key]["ok"] == 1, "%s: the reference failed to evaluate case %d block %s" % (what, i, key)
+            sr = max(np.max(np.abs(a[key]["res"])), 1e-12); sj = max(np.max(np.abs(a[key]["jac"])), 1e-12)
+            assert np.max(np.abs(a[key]["res"] - b[key]["res"])) <= tol * sr, (what, i, key)
+            assert np.max(np.abs(a[key]["jac"] - b[key]["jac"])) <= tol * sj, (what, i, key)
+
+
+def tangent_system(blocks, b_pose, manifold, cv, use_imu):
+    """cost, g, H of the two-state window [a, b] from the per-block residuals / ambient Jacobians, in the product's parameter order
+    (a: lin_vel, rot_vel, [lin_acc]; b: pose (through Sophus::Manifold<SE2>'s PlusJacobian), lin_vel, rot_vel, [lin_acc], [imu_bias])"""
+    cols = []                                     # tangent column -> ambient combination
+    def unit(slot):
+        e = np.zeros(20); e[slot] = 1.0; return e
+    cols += [unit(4), unit(5), unit(6)] + ([] if cv else [unit(7), unit(8)])
+    if manifold:
+        c, s = b_pose[0], b_pose[1]
+        Pj = np.array([[0, 0, -s], [0, 0, c], [c, -s, 0], [s, c, 0]], np.float64)
+        for t in range(3):
+            e = np.zeros(20); e[10:14] = Pj[:, t]; cols.append(e)
+    else:
+        cols += [unit(10), unit(11), unit(12)]
+    cols += [unit(14), unit(15), unit(16)] + ([] if cv else [unit(17), unit(18)]) + ([unit(19)] if use_imu else [])
+    T = np.array(cols).T                          # [20, nt]
+    keys = [(0, int(manifold))] + ([(1, int(manifold))] if use_imu else [])
+    res = np.concatenate([blocks[k]["res"] for k in keys]); Jt = np.concatenate([blocks[k]["jac"] @ T for k in keys])
+    return 0.5 * float(res @ res), Jt.T @ res, Jt.T @ Jt
+
+
+def check_host_factors(cases, doc, tol):
+    """the product's host layer (randt_hostapi_window_factors) on every case as a two-state window, against the blocks"""
+    from randt_slam_b200 import hostapi
+    for c, blocks in zip(doc["cases"], cases):
+        for manifold in (True, False):
+            for cv in (True, False):
+                for use_imu in (False, True):
+                    q = hostapi.window_params(manifold=manifold, constant_velocity=cv, use_imu=use_imu, weight_imu=doc["weight_imu"],
+                                              weight_imu_bias=doc["weight_imu_bias"], covariance_scaling_factor=1.0)
+                    q[16:] = np.array(doc["sqrtI"], np.float64).reshape(64)
+                    cost, g, H = hostapi.window_factors(np.array([c["a"], c["b"]]), q, [c["imu_rot"]])
+                    c0, g0, H0 = tangent_system(blocks, c["b"], manifold, cv, use_imu)
+                    assert abs(cost - c0) <= tol * max(c0, 1e-30)
+                    assert np.max(np.abs(g - g0)) <= tol * max(np.max(np.abs(g0)), 1e-30) and np.max(np.abs(H - H0)) <= tol * max(np.max(np.abs(H0)), 1e-30)
+
+
+def test_window_fixture_format_and_comparison_self_check(oracle, tmp_path):
+    doc = json.load(open(W_INPUTS))
+    res = oracle_window_outputs(oracle, doc)
+    p = tmp_path / "stand_in_window_outputs.txt"
+    write_window_outputs(str(p), res)
+    back = parse_window_outputs(str(p))
+    compare_window(back, res, "self-check", tol=1e-15)
+    assert len(back) == 24 and back[0][(0, 1)]["jac"].shape == (8, 20) and back[0][(1, 0)]["jac"].shape == (2, 20)
+    # the vector functors never see the pose block, the SE(2) functors never see pos / rot ... both share the velocity columns
+    assert np.all(back[0][(1, 0)]["jac"][:, [0, 1, 3, 4, 5, 6, 7, 8]] == 0.0)
+    check_host_factors(back, doc, 1e-10)        # (g sums terms of opposite sign: a few 1e-12 of its largest entry)
+
+
+@pytest.mark.skipif(not os.path.exists(W_OUTPUTS), reason="tests/golden/ref_full_window_outputs.txt not generated (needs the reference's Eigen/Ceres/Sophus: oracle/ref_full/README.md)")
+def test_window_factors_match_full_reference_fixtures(oracle):
+    doc = json.load(open(W_INPUTS))
+    ref = parse_window_outputs(W_OUTPUTS)
+    compare_window(ref, oracle_window_outputs(oracle, doc), "oracle vs reference")
+    check_host_factors(ref, doc, 1e-9)
