@@ -93,7 +93,16 @@ enum {
   RANDT_PACKED_G = 10,     /* [4] */
   RANDT_PACKED_COST = 14, RANDT_PACKED_MAXR = 15, RANDT_PACKED_SUMSQ = 16, RANDT_PACKED_N = 17,
   RANDT_PACKED_STRIDE = 18,
-  RANDT_CORE_STRIDE = 15   /* packed == 2: the first 15 entries of the packed record (H upper triangle, g, cost) — what one LM iteration consumes */
+  RANDT_CORE_STRIDE = 15,  /* packed == 2: the first 15 entries of the packed record (H upper triangle, g, cost) — what one LM iteration consumes */
+  /* packed == 3: the normal equations in the functor's own three-dimensional derivative basis, before any chain rule — 80 bytes per
+   * segment, the least a host-side LM iteration needs.  Basis of RANDT_VAR_SE2_INTENSITY: (theta, tx, ty) with theta = atan2(s, c), i.e.
+   * the ambient record is F^T H_b F, F^T g_b with F = [[-s/n2, c/n2, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]], n2 = c^2 + s^2, and the
+   * Sophus::Manifold<SE2> tangent record (ux, uy, theta) is Q^T H_b Q, Q^T g_b with Q = [[0, 0, 1], [c, -s, 0], [s, c, 0]] (unit c, s);
+   * basis of the VEC variants: their parameters (x, y, theta).  Not available for RANDT_VAR_SE2_XY (four-dimensional basis) or want_jac == 0. */
+  RANDT_BASIS_H = 0,       /* [6] upper triangle of the 3x3, row by row: 00 01 02 11 12 22 */
+  RANDT_BASIS_G = 6,       /* [3] */
+  RANDT_BASIS_COST = 9,
+  RANDT_BASIS_STRIDE = 10
 };
 
 typedef struct randt_ctx randt_ctx;
@@ -243,7 +252,8 @@ RANDT_API int randt_eval_fused(randt_ctx* ctx, const randt_problem* p, int varia
  * the kernel of call i (two copy streams, two device slots each way).  The buffers of a call may be read / reused after
  * randt_ctx_sync(), or once call i+2 has left the context's stream; give the calls in flight their own buffers.
  * packed == 1: `out` receives RANDT_PACKED_STRIDE doubles per segment (layout RANDT_PACKED_*) instead of RANDT_FUSED_STRIDE; packed == 2:
- * RANDT_CORE_STRIDE doubles (the packed record without max r, sum r^2, n: the normal equations and the cost, 120 bytes) — the
+ * RANDT_CORE_STRIDE doubles (the packed record without max r, sum r^2, n: the normal equations and the cost, 120 bytes); packed == 3:
+ * RANDT_BASIS_STRIDE doubles (layout RANDT_BASIS_*: the same normal equations before the chain rule to the ambient parameters, 80 bytes) — the
  * copy-out is what bounds a pipelined step, and a quarter of the full record is the mirrored half of H. */
 RANDT_API int randt_eval_fused_async(randt_ctx* ctx, const randt_problem* p, int variant, const double* poses, const randt_loss* loss,
                                      const double* mu_per_seg, int want_jac, int packed, double* out);

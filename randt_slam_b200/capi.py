@@ -18,7 +18,25 @@ FUSED_STRIDE = 24
 FUSED_H, FUSED_G, FUSED_COST, FUSED_MAXR, FUSED_SUMSQ, FUSED_N = 0, 16, 20, 21, 22, 23   # RANDT_FUSED_* of include/randt_gpu.h
 CORE_STRIDE = 15                                                                         # RANDT_CORE_STRIDE: packed == 2 (H upper triangle, g, cost)
 PACKED_STRIDE = 18                                                                       # RANDT_PACKED_*: H upper triangle (10), g (4), cost, max r, sum r^2, n
+BASIS_STRIDE = 10                                                                        # RANDT_BASIS_*: packed == 3 (3x3 upper triangle, g, cost in the functor's basis)
 _PACKED_SRC = [0, 1, 2, 3, 5, 6, 7, 10, 11, 15, 16, 17, 18, 19, 20, 21, 22, 23]
+
+
+def basis_to_core(basis, poses):
+    """[S, 10] basis records of RANDT_VAR_SE2_INTENSITY (packed == 3: derivatives w.r.t. theta = atan2(s, c), tx, ty) + the poses they were
+    evaluated at -> [S, 15] core records (packed == 2: ambient H upper triangle, g, cost): H = F^T H_b F, g = F^T g_b with
+    F = [[-s/n2, c/n2, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]]"""
+    b = np.asarray(basis, np.float64); q = np.asarray(poses, np.float64)
+    S = len(b)
+    n2 = q[:, 0] ** 2 + q[:, 1] ** 2
+    F = np.zeros((S, 3, 4)); F[:, 0, 0] = -q[:, 1] / n2; F[:, 0, 1] = q[:, 0] / n2; F[:, 1, 2] = 1.0; F[:, 2, 3] = 1.0
+    Hb = np.zeros((S, 3, 3))
+    iu = np.triu_indices(3)
+    Hb[:, iu[0], iu[1]] = b[:, 0:6]; Hb[:, iu[1], iu[0]] = b[:, 0:6]
+    H = np.einsum("sia,sij,sjb->sab", F, Hb, F)
+    g = np.einsum("sia,si->sa", F, b[:, 6:9])
+    iu4 = np.triu_indices(4)
+    return np.concatenate([H[:, iu4[0], iu4[1]], g, b[:, 9:10]], axis=1)
 
 
 def pack_fused(full):
@@ -451,7 +469,7 @@ class Problem:
         return out
 
     def eval_fused_async(self, poses, out, loss=None, mu_per_seg=None, want_jac=True, variant=VAR_SE2_INTENSITY, packed=False):
-        """enqueue-only evaluation: `poses`, `mu_per_seg` and `out` ([S, 24], or [S, 18] when packed) are float64 arrays in pinned host
+        """enqueue-only evaluation: `poses`, `mu_per_seg` and `out` ([S, 24]; packed 1: [S, 18], 2: [S, 15], 3: [S, 10]) are float64 arrays in pinned host
         memory (PinnedArray); valid after Context.sync()"""
         for a in (poses, out, mu_per_seg):
             if a is not None and not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous):

@@ -1089,7 +1089,7 @@ int randt_eval_emit(randt_ctx* ctx, const randt_problem* cp, int variant, const 
 namespace {
 int eval_fused_dev_impl(randt_ctx* ctx, const randt_problem* p, int variant, const double* d_poses, const randt_loss* loss,
                         const double* d_mu_per_seg, int want_jac, double* d_out, int packed);
-inline size_t out_stride(int packed) { return packed == 1 ? RANDT_PACKED_STRIDE : (packed == 2 ? RANDT_CORE_STRIDE : RANDT_FUSED_STRIDE); }
+inline size_t out_stride(int packed) { return packed == 1 ? RANDT_PACKED_STRIDE : (packed == 2 ? RANDT_CORE_STRIDE : (packed == 3 ? RANDT_BASIS_STRIDE : RANDT_FUSED_STRIDE)); }
 }
 int randt_eval_fused_dev(randt_ctx* ctx, const randt_problem* p, int variant, const double* d_poses, const randt_loss* loss,
                          const double* d_mu_per_seg, int want_jac, double* d_out) {
@@ -1099,7 +1099,9 @@ namespace {
 int eval_fused_dev_impl(randt_ctx* ctx, const randt_problem* p, int variant, const double* d_poses, const randt_loss* loss,
                         const double* d_mu_per_seg, int want_jac, double* d_out, int packed) {
   if (!ctx || !p || !d_poses || !d_out) return fail(ctx, RANDT_E_INVALID, "randt_eval_fused_dev: null argument");
-  if (packed < 0 || packed > 2) return fail(ctx, RANDT_E_INVALID, "randt_eval_fused: packed must be 0, 1 or 2");
+  if (packed < 0 || packed > 3) return fail(ctx, RANDT_E_INVALID, "randt_eval_fused: packed must be 0 .. 3");
+  if (packed == 3 && (variant == RANDT_VAR_SE2_XY || !want_jac))
+    return fail(ctx, RANDT_E_INVALID, "randt_eval_fused: the basis record (packed == 3) needs a three-dimensional basis and a Jacobian evaluation");
   if (check_variant(ctx, variant)) return RANDT_E_INVALID;
   LossParams lp;
   if (int rc = make_loss(ctx, loss, &lp)) return rc;
@@ -1207,7 +1209,7 @@ int randt_eval_fused_async(randt_ctx* ctx, const randt_problem* cp, int variant,
   CK(cudaStreamWaitEvent(ctx->stream, r.ev_in[slot], 0));
   // Records go to a device slot and leave on a third stream: a DMA copy moves the 192 S bytes at the full PCIe rate while the next
   // call's kernel runs (stores from the kernel straight into mapped host memory, as the blocking call does, reach ~3/4 of that rate).
-  if (packed < 0 || packed > 2) return fail(ctx, RANDT_E_INVALID, "randt_eval_fused_async: packed must be 0, 1 or 2");
+  if (packed < 0 || packed > 3) return fail(ctx, RANDT_E_INVALID, "randt_eval_fused_async: packed must be 0 .. 3");
   const size_t n_out = (size_t)p->S * out_stride(packed);   // K3 writes the layout itself
   CK(cudaStreamWaitEvent(ctx->stream, r.ev_d2h[slot], 0));     // the copy-out of two calls ago has drained this slot
   if (r.oring_cap[slot] < n_out) {

@@ -53,7 +53,7 @@ struct DeviceProblem {
   uint32_t n_chunks;
   const uint32_t* warp_off;  // [n_warps+1]
   uint32_t n_warps;
-  uint32_t out_packed;       // FUSED only: 1 = write RANDT_PACKED_STRIDE-double records (upper triangle of H) instead of RANDT_FUSED_STRIDE, 2 = RANDT_CORE_STRIDE
+  uint32_t out_packed;       // FUSED only: 1 = write RANDT_PACKED_STRIDE-double records (upper triangle of H) instead of RANDT_FUSED_STRIDE, 2 = RANDT_CORE_STRIDE, 3 = RANDT_BASIS_STRIDE (slot totals, no chain rule)
   uint32_t plan_static;      // 1: chunks / warp_off are the problem's immutable schedule; 0: produced by a preceding kernel (solver re-plan)
   const uint32_t* seg_first_tile;  // [S+1]
   uint32_t n_segments;

@@ -413,6 +413,13 @@ __device__ __forceinline__ void write_segment_out_from(double mine, double max_d
 // slot s is owned by lane s * owner_mul (smem_reduce: 2, the partial fold: 1)
 __device__ __forceinline__ void write_segment_out(double mine, double max_dd, double ja, double jb, uint32_t n_pairs, double* __restrict__ out_base,
                                                   uint32_t seg, uint32_t packed, int lane, uint32_t omap, int owner_mul) {
+  if (packed == 3u) {
+    // RANDT_BASIS_*: the slot totals as they are (three-dimensional bases, Jacobian evaluations only: slots 0..5 upper triangle of H in
+    // the kernel's own basis, 6..8 gradient, 9 cost) — no chain-rule factors, 80 bytes per segment
+    const double v = __shfl_sync(kFull, mine, (lane < RANDT_BASIS_STRIDE ? lane : 0) * owner_mul);
+    if (lane < RANDT_BASIS_STRIDE) out_base[(size_t)seg * RANDT_BASIS_STRIDE + lane] = v;
+    return;
+  }
   write_segment_out_from(mine, max_dd, ja, jb, n_pairs, out_base, seg, packed, lane, omap, (int)(omap & 31u) * owner_mul);
 }
 __device__ __forceinline__ void write_segment_out_from(double mine, double max_dd, double ja, double jb, uint32_t n_pairs, double* __restrict__ out_base,

@@ -310,6 +310,47 @@ def test_a_warp_walks_its_descriptor_queue_through_several_refills(oracle, gpu_c
     few.close(); ref.close()
 
 
+def test_basis_record_is_the_normal_equations_before_the_chain_rule(oracle, gpu_ctx):
+    """packed == 3 (RANDT_BASIS_*, 80 B per pose): H_b, g_b, cost in the functor's (theta, tx, ty) basis; expanded with F^T . F it equals
+    the ambient core record (packed == 2) of the same evaluation, projected with Sophus' PlusJacobian it equals the tangent-space system
+    the oracle builds from its ambient sums; ragged segments incl. multi-tile ones (partial fold) and poses off the unit circle"""
+    rng = np.random.default_rng(31)
+    sizes = [40, 1, 300, 33, 700, 64, 5]
+    n_m = sum(sizes)
+    cm = H.random_cells(rng, n_m, extent=6.0); cf = H.random_cells(rng, 500, extent=6.0)
+    im = np.repeat(np.arange(n_m, dtype=np.uint32), 2); jf = rng.integers(0, 500, 2 * n_m).astype(np.uint32)
+    seg = np.concatenate([[0], 2 * np.cumsum(sizes)]).astype(np.uint32)
+    S = len(sizes)
+    poses = np.stack([synth.pose_to_se2(*rng.uniform(-0.3, 0.3, 3)) for _ in range(S)])
+    poses[2, :2] *= 1.003; poses[5, :2] *= 0.998
+    loss = capi.make_loss(capi.LOSS_BARRON, 1.5, -2.0, 1.4, 0.02)
+    prob = gpu_ctx.problem_create(cm, cf, im, jf, seg)
+    hp = capi.PinnedArray((S, 4)); hp.a[...] = poses
+    hb = capi.PinnedArray((S, capi.BASIS_STRIDE)); hc = capi.PinnedArray((S, capi.CORE_STRIDE))
+    prob.eval_fused_async(hp.a, hc.a, loss, packed=2); gpu_ctx.sync()
+    prob.eval_fused_async(hp.a, hb.a, loss, packed=3); gpu_ctx.sync()
+    core = capi.basis_to_core(hb.a, poses)
+    assert np.array_equal(core[:, 14], hc.a[:, 14])                                 # the cost slot travels unchanged
+    scale = np.max(np.abs(hc.a[:, :14]), axis=1, keepdims=True)
+    assert np.max(np.abs(core[:, :14] - hc.a[:, :14]) / scale) < 1e-14
+    # the manifold system: Q^T H_b Q with Q = [[0, 0, 1], [c, -s, 0], [s, c, 0]] for unit (c, s) == PlusJacobian^T H_ambient PlusJacobian
+    fo, _ = oracle.fused_batch(0, cm, cf, im, jf, seg, poses, (loss.kind, loss.scale, loss.alpha, loss.mu, loss.weight))
+    for s_ in (0, 1, 3, 4, 6):
+        c, s = poses[s_, 0], poses[s_, 1]
+        Q = np.array([[0, 0, 1.0], [c, -s, 0], [s, c, 0]]); Pj = np.array([[0, 0, -s], [0, 0, c], [c, -s, 0], [s, c, 0]])
+        Hb = np.zeros((3, 3)); iu = np.triu_indices(3); Hb[iu] = hb.a[s_, :6]; Hb = Hb + Hb.T - np.diag(np.diag(Hb))
+        assert H.rel_err(Q.T @ Hb @ Q, Pj.T @ fo["H"][s_] @ Pj) < 1e-9 and H.rel_err(Q.T @ hb.a[s_, 6:9], Pj.T @ fo["g"][s_]) < 1e-9
+    # not defined for the four-dimensional basis of the 2-D SE(2) functor, nor without a Jacobian evaluation
+    with pytest.raises(capi.RandtError):
+        prob.eval_fused_async(hp.a, hb.a, loss, packed=3, variant=capi.VAR_SE2_XY)
+    with pytest.raises(capi.RandtError):
+        prob.eval_fused_async(hp.a, hb.a, loss, packed=3, want_jac=False)
+    gpu_ctx.sync()
+    for b in (hp, hb, hc):
+        b.close()
+    prob.close()
+
+
 def test_fused_one_very_long_segment(oracle, gpu_ctx):
     """a single segment of 300 k pairs: ~590 tiles folded by the ticket/partial path"""
     rng = np.random.default_rng(5)
