@@ -332,6 +332,12 @@ RANDT_API void randt_hostapi_predict(int se2_model, const double* state12, doubl
  * Returns nt (or a negative error). */
 RANDT_API int randt_hostapi_window_factors(const double* states, uint32_t W, const double* imu, const double* params80, double* cost, double* g,
                                            double* H);
+/* The trust-region loop of the window solve on the host factors alone (no NDT term, no device): minimises the motion-model (+ IMU) cost
+ * over the free parameters of the window states with window::minimize (ceres' Levenberg-Marquardt restated), states in / out.
+ * tolerances3 / max_iterations <= 0: ceres' defaults / 200.  summary4: initial cost, final cost, iterations, termination (0 convergence,
+ * 1 iteration limit, 2 failure).  Returns 0 or a negative error. */
+RANDT_API int randt_hostapi_window_minimize_factors(double* states, uint32_t W, const double* imu, const double* params80, const double* tolerances3,
+                                                    int max_iterations, double* summary4);
 /* Matcher::estimateTransformCeres over scans given as points: fixed scan f is voxelised and moved by fixed_pose4[f] (one fixed map each);
  * window scan w (oldest first, W of them) is voxelised as it is.  states [(W + 1)][14] in / out, trans4 in / out.  params80 [16 + 64]: k,
  * gnc_steps, max_iteration, loss_scale, alpha, divisor, ndt_weight, manifold, constant_velocity, use_imu, weight_imu, weight_imu_bias,

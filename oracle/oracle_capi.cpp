@@ -342,4 +342,31 @@ int orc_factor_block(int kind, int manifold, const double* a14, const double* b1
   return n;
 }
 
+// lm_minimize on the host factors of the window problem alone (no NDT blocks): states in / out; summary4 = initial cost, final cost,
+// iterations, termination
+int orc_window_minimize_factors(double* states, int W, const double* imu, const double* params, int max_iterations, double* summary4) {
+  WindowProblem wp;
+  std::vector<uint32_t> seg_off((size_t)W + 1, 0u);
+  const float no_cell[12] = {0};
+  const uint32_t no_pair = 0;
+  window_fill(wp, no_cell, no_cell, &no_pair, &no_pair, seg_off.data(), W, states, imu, params);
+  LmOptions opt; opt.max_num_iterations = max_iterations > 0 ? max_iterations : 200;
+  if (g_function_tol > 0.0) opt.function_tolerance = g_function_tol;
+  if (g_parameter_tol > 0.0) opt.parameter_tolerance = g_parameter_tol;
+  if (g_gradient_tol > 0.0) opt.gradient_tolerance = g_gradient_tol;
+  std::vector<double> x(wp.n_amb());
+  wp.pack(x.data());
+  Loss none; none.kind = LOSS_NONE;
+  NormalEqProblem prob;
+  prob.n_amb = wp.n_amb(); prob.n_tan = wp.n_tan();
+  prob.eval_full = [&](const double* xx, double* cost, double* g, double* H) { return wp.evaluate(xx, none, cost, g, H); };
+  prob.eval_cost = [&](const double* xx, double* cost) { return wp.evaluate(xx, none, cost, nullptr, nullptr); };
+  prob.plus = [&](const double* xx, const double* d, double* xp) { wp.plus(xx, d, xp); };
+  const LmSummary S = lm_minimize(prob, opt, x.data());
+  wp.unpack(x.data());
+  window_store(wp, states);
+  summary4[0] = S.initial_cost; summary4[1] = S.final_cost; summary4[2] = S.num_iterations; summary4[3] = S.termination;
+  return 0;
+}
+
 }  // extern "C"

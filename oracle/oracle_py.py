@@ -97,6 +97,7 @@ def _sig(L):
     L.orc_set_tolerances.restype = None; L.orc_set_tolerances.argtypes = [d, d, d]
     L.orc_window_evaluate.restype = i; L.orc_window_evaluate.argtypes = [pf, pf, pu, pu, pu, i, pd, pd, pd, i, d, d, pd, pd, pd, pd]
     L.orc_factor_block.restype = i; L.orc_factor_block.argtypes = [i, i, pd, pd, pd, d, d, d, pd, pd]
+    L.orc_window_minimize_factors.restype = i; L.orc_window_minimize_factors.argtypes = [pd, i, pd, pd, i, pd]
     L.orc_window_solve.restype = i; L.orc_window_solve.argtypes = [pf, pf, pu, pu, pu, i, pd, pd, pd, sz, pd, pd]
 
 
@@ -376,3 +377,19 @@ def factor_block(kind, manifold, a14, b14, sqrtI64, imu_rot=0.0, weight_imu=0.0,
     n = lib().orc_factor_block(int(kind), int(bool(manifold)), _p(_f64(a14), C.c_double), _p(_f64(b14), C.c_double), _p(_f64(sqrtI64), C.c_double),
                                float(imu_rot), float(weight_imu), float(weight_bias), _p(res, C.c_double), _p(jac, C.c_double))
     return res[:n].copy(), jac[:n].copy()
+
+
+def window_minimize_factors(states14, params80, imu=None, tolerances=None, max_iterations=0):
+    """lm_oracle.h's minimiser on the motion-model (+ IMU) factors of the window alone -> (states [(W + 1), 14], summary dict)"""
+    st = _f64(states14).reshape(-1, 14).copy()
+    W = len(st) - 1
+    imu_ = _f64(imu if imu is not None else np.zeros(max(W, 1)))
+    out = np.zeros(4)
+    if tolerances is not None:
+        lib().orc_set_tolerances(C.c_double(tolerances[0]), C.c_double(tolerances[1]), C.c_double(tolerances[2]))
+    try:
+        lib().orc_window_minimize_factors(_p(st, C.c_double), W, _p(imu_, C.c_double), _p(_f64(params80), C.c_double), int(max_iterations), _p(out, C.c_double))
+    finally:
+        if tolerances is not None:
+            lib().orc_set_tolerances(C.c_double(0.0), C.c_double(0.0), C.c_double(0.0))
+    return st, dict(initial_cost=out[0], final_cost=out[1], iterations=int(out[2]), termination=int(out[3]))

@@ -909,6 +909,37 @@ int randt_hostapi_window_factors(const double* states, uint32_t W, const double*
   return rc == RANDT_OK ? nt : rc;
 }
 
+int randt_hostapi_window_minimize_factors(double* states, uint32_t W, const double* imu, const double* params80, const double* tolerances3,
+                                          int max_iterations, double* summary4) {
+  return guarded([&] {
+    const randt::NDTMatcherParameters p = matcher_params80(params80);
+    const bool manifold = p.optimize_on_manifold && !p.use_analytic_expressions_for_optimization;
+    std::vector<randt::State> st((size_t)W + 1);
+    std::vector<randt::State*> ptr((size_t)W + 1);
+    for (uint32_t j = 0; j <= W; ++j) { state_from14(states + 14 * (size_t)j, st[j]); ptr[j] = &st[j]; }
+    std::vector<double> zero(W, 0.0);
+    randt::window::JointProblem problem;
+    randt::buildWindowFactors(problem, p, manifold, ptr.data(), (int)W, imu ? imu : zero.data(), p.motion_sqrtI);
+    problem.finalize();
+    randt_solver_options opt;
+    randt_solver_options_default(&opt);
+    if (max_iterations > 0) opt.max_num_iterations = max_iterations;
+    if (tolerances3) {
+      if (tolerances3[0] > 0.0) opt.function_tolerance = tolerances3[0];
+      if (tolerances3[1] > 0.0) opt.parameter_tolerance = tolerances3[1];
+      if (tolerances3[2] > 0.0) opt.gradient_tolerance = tolerances3[2];
+    }
+    std::vector<double> x((size_t)problem.numAmbient());
+    problem.gather(x.data());
+    randt_loss none;
+    none.kind = RANDT_LOSS_NONE; none.scale = 1.0; none.alpha = 2.0; none.mu = 1.0; none.weight = 1.0;
+    const randt::window::MinimizerSummary ms = randt::window::minimize(problem, none, opt, x.data());
+    problem.scatter(x.data());
+    for (uint32_t j = 0; j <= W; ++j) state_to14(st[j], states + 14 * (size_t)j);
+    summary4[0] = ms.initial_cost; summary4[1] = ms.final_cost; summary4[2] = ms.num_iterations; summary4[3] = ms.termination;
+  });
+}
+
 int randt_hostapi_window_solve(int device, const randt_grid_params* gp, const float* const* fixed_pts4, const uint32_t* n_fixed_pts,
                                const double* fixed_pose4, uint32_t n_fixed, const float* const* window_pts4, const uint32_t* n_window_pts, uint32_t W,
                                double* states, const double* imu, const double* params80, const double* tolerances3, double* trans4, double* out10) {

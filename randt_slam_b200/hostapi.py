@@ -20,7 +20,8 @@ def lib():
         L = C.CDLL(LIB_PATH)
         L.randt_hostapi_last_error.restype = C.c_char_p
         for name in ("randt_hostapi_loop_constraints", "randt_hostapi_cost_function", "randt_hostapi_bnb", "randt_hostapi_export", "randt_hostapi_odometry", "randt_hostapi_eval_async_loop", "randt_hostapi_build_schedule",
-                     "randt_hostapi_window_factors", "randt_hostapi_window_solve", "randt_hostapi_window_replay"):
+                     "randt_hostapi_window_factors", "randt_hostapi_window_solve", "randt_hostapi_window_replay",
+                     "randt_hostapi_window_minimize_factors"):
             getattr(L, name).restype = C.c_int
         _lib = L
     return _lib
@@ -194,3 +195,15 @@ def window_replay(gp, scans, stamps, params80, smoothing_steps=3, insertion_step
                                              _pf(poses), _pf(states), _pf(stats), _pf(totals)))
     return poses, states, stats, dict(seconds=totals[0], submap_cells=int(totals[1]), launches=int(totals[2]), keyframes=int(totals[3]),
                                        setup_seconds=totals[4], solve_seconds=totals[5])
+
+
+def window_minimize_factors(states14, params80, imu=None, tolerances=None, max_iterations=0):
+    """window::minimize on the motion-model (+ IMU) factors alone, no device -> (states [(W + 1), 14], summary dict)"""
+    st = np.ascontiguousarray(states14, np.float64).reshape(-1, 14).copy()
+    W = len(st) - 1
+    im = None if imu is None else np.ascontiguousarray(imu, np.float64)
+    tol = None if tolerances is None else np.ascontiguousarray(tolerances, np.float64)
+    out = np.zeros(4)
+    _check(lib().randt_hostapi_window_minimize_factors(_pf(st), C.c_uint32(W), _pf(im) if im is not None else None, _pf(np.ascontiguousarray(params80, np.float64)),
+                                                       _pf(tol) if tol is not None else None, C.c_int(int(max_iterations)), _pf(out)))
+    return st, dict(initial_cost=out[0], final_cost=out[1], iterations=int(out[2]), termination=int(out[3]))

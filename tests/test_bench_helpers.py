@@ -63,3 +63,31 @@ def test_committed_bench_line_keeps_the_contract():
     c = d["cpu_baseline"]
     assert c["kind"] == "port" and c["cores"] >= 1 and d["value"] / c["single_thread_value"] >= 100      # north_star: >= 100x one CPU thread
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+
+
+def test_basis_record_expansion_is_the_chain_rule():
+    """capi.basis_to_core: the 80-byte basis record (H_b, g_b, cost w.r.t. theta = atan2(s, c), tx, ty) -> the ambient core record; checked on
+    a synthetic residual r(c, s, tx, ty) = a . (theta, tx, ty): J_ambient = a F, so H = F^T (a a^T) F and g = F^T a r"""
+    import numpy as np
+    from randt_slam_b200 import capi
+    rng = np.random.default_rng(0)
+    S = 5
+    poses = np.stack([np.array([np.cos(t), np.sin(t), x, y]) * [n, n, 1, 1] for t, x, y, n in zip(rng.uniform(-3, 3, S), rng.normal(0, 5, S), rng.normal(0, 5, S),
+                                                                                                 [1.0, 1.01, 0.97, 1.0, 1.2])])
+    a = rng.normal(0, 1, (S, 3)); r = rng.normal(0, 1, S)
+    basis = np.zeros((S, capi.BASIS_STRIDE))
+    iu = np.triu_indices(3)
+    for s in range(S):
+        basis[s, :6] = np.outer(a[s], a[s])[iu]; basis[s, 6:9] = a[s] * r[s]; basis[s, 9] = 0.5 * r[s] ** 2
+    core = capi.basis_to_core(basis, poses)
+    iu4 = np.triu_indices(4)
+    for s in range(S):
+        c, sn = poses[s, 0], poses[s, 1]
+        n2 = c * c + sn * sn
+        J = np.array([a[s, 0] * (-sn / n2), a[s, 0] * (c / n2), a[s, 1], a[s, 2]])      # d theta / d c = -s / n2, d theta / d s = c / n2
+        assert np.allclose(core[s, :10], np.outer(J, J)[iu4], rtol=1e-13, atol=1e-15)
+        assert np.allclose(core[s, 10:14], J * r[s], rtol=1e-13, atol=1e-15) and core[s, 14] == basis[s, 9]
+    # finite differences of theta = atan2(s, c) confirm the chain-rule row
+    h = 1e-7
+    c, sn = poses[1, 0], poses[1, 1]
+    assert abs((np.arctan2(sn, c + h) - np.arctan2(sn, c - h)) / (2 * h) - (-sn / (c * c + sn * sn))) < 1e-8

@@ -198,3 +198,42 @@ def test_host_factors_equal_the_oracle(oracle, manifold, cv, use_imu):
         assert len(g) == len(go) == 3 + (0 if cv else 2) + W * (6 + (0 if cv else 2) + (1 if use_imu else 0))
         assert abs(cost - co) <= 1e-13 * co
         assert np.max(np.abs(g - go)) <= 1e-12 * np.max(np.abs(go)) and np.max(np.abs(H - Ho)) <= 1e-12 * np.max(np.abs(Ho))
+
+
+@pytest.mark.parametrize("manifold", [True, False])
+@pytest.mark.parametrize("cv", [True, False])
+@pytest.mark.parametrize("use_imu", [False, True])
+def test_trust_region_loop_on_the_host_factors(oracle, manifold, cv, use_imu):
+    """window::minimize (the product's restatement of ceres' Levenberg-Marquardt, randt_slam_b200/host/window_solver.cpp) on the motion /
+    IMU factors alone, no device: same iterates as the oracle's lm_minimize, and where the factors can all be satisfied (constant
+    acceleration, no IMU) the minimum is the known one — a window that follows the motion model, cost 0 under the independent restatement"""
+    rng = np.random.default_rng(300 + 4 * manifold + 2 * cv + use_imu)
+    for W in (1, 3):
+        st = make_states(W, rng)
+        imu = rng.normal(0.03, 0.01, W)
+        q = hostapi.window_params(manifold=manifold, constant_velocity=cv, use_imu=use_imu, weight_imu=64.0, weight_imu_bias=50.0, covariance_scaling_factor=0.3)
+        qo = q.copy(); qo[14] = 0 if manifold else 2
+        s1, i1 = hostapi.window_minimize_factors(st, q, imu)
+        s0, i0 = oracle.window_minimize_factors(st, qo, imu)
+        assert i1["iterations"] == i0["iterations"] and i1["termination"] == i0["termination"] == 0
+        assert np.max(np.abs(s1 - s0)) < 1e-9 and abs(i1["final_cost"] - i0["final_cost"]) <= 1e-9 * max(i0["final_cost"], 1e-12)
+        assert i1["final_cost"] < i1["initial_cost"]
+        assert np.array_equal(s1[0, :7], st[0, :7]) and s1[0, 12] == st[0, 12]          # pose and bias of the oldest state are constant
+        if cv:
+            assert np.array_equal(s1[:, 10:12], st[:, 10:12])                            # acceleration blocks are constant
+        if not use_imu:
+            assert np.array_equal(s1[:, 12], st[:, 12])
+        # the cost the solver reports is the cost of the states it returns, under the independent numpy restatement
+        sq = q[16:].reshape(8, 8)
+        ref = window_cost(s1, sq, manifold, use_imu, imu, 64.0, 50.0)
+        assert abs(ref - i1["final_cost"]) <= 1e-9 * max(ref, 1e-9) + 1e-15
+        if not cv and not use_imu:
+            assert i1["final_cost"] < 1e-12 * i1["initial_cost"]
+
+
+def test_trust_region_loop_stops_at_the_iteration_limit():
+    rng = np.random.default_rng(9)
+    st = make_states(3, rng)
+    q = hostapi.window_params(constant_velocity=False, covariance_scaling_factor=0.3)
+    _, info = hostapi.window_minimize_factors(st, q, tolerances=(1e-30, 1e-30, 1e-30), max_iterations=2)
+    assert info["termination"] == 1 and info["iterations"] == 3      # iteration 0 + two steps (ceres counts iterations.size())
