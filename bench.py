@@ -434,7 +434,10 @@ def run_configs(args, ctx, capi, stream, rank, world, local, barrier):
                 n_o = min(args.window_oracle_scans, n_w)
                 o_poses, o_states, _, dto = W.oracle_window_replay(oracle, p4, scans[:n_o], stamps[:n_o], q)
                 wrec["cpu_baseline"] = {"scans_per_s": (n_o - 1) / dto, "cores": 1, "kind": "port", "sample": "first %d scans of the drive" % n_o,
-                                        "max_abs_pose_difference_vs_device": float(np.max(np.abs(o_poses - poses_w[:n_o])))}
+                                        "max_abs_pose_difference_vs_device": float(np.max(np.abs(o_poses - poses_w[:n_o]))),
+                                        "median_abs_pose_difference_vs_device": float(np.median(np.max(np.abs(o_poses - poses_w[:n_o]), axis=1))),
+                                        "note": "both chains run free at ceres' default tolerances: single solves that creep along a weakly determined valley stop a step "
+                                                "apart (DESIGN.md section 3, Window); with a fixed number of steps the iterates agree to 1e-7 (tests/test_window_gpu.py)"}
             rec["window_odometry"] = wrec
         out["c4"] = rec
     barrier()
