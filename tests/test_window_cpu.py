@@ -237,3 +237,42 @@ def test_trust_region_loop_stops_at_the_iteration_limit():
     q = hostapi.window_params(constant_velocity=False, covariance_scaling_factor=0.3)
     _, info = hostapi.window_minimize_factors(st, q, tolerances=(1e-30, 1e-30, 1e-30), max_iterations=2)
     assert info["termination"] == 1 and info["iterations"] == 3      # iteration 0 + two steps (ceres counts iterations.size())
+
+
+@pytest.mark.parametrize("manifold", [True, False])
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_motion_and_imu_factors_do_not_depend_on_the_frame(manifold, seed):
+    """size-independent property: moving every pose of the window by one rigid motion G (pose_j -> G pose_j; velocities and accelerations
+    are body-frame quantities) changes neither the cost nor — in the solver's right-perturbation tangent coordinates — g and J^T J"""
+    rng = np.random.default_rng(500 + seed)
+    W = 3
+    st = make_states(W, rng)
+    imu = rng.normal(0.02, 0.01, W)
+    G = se2_exp(rng.normal(0, [30.0, 30.0, 1.5]))
+    moved = st.copy()
+    for j in range(W + 1):
+        moved[j, :4] = se2_mul(G, st[j, :4])
+        th = math.atan2(G[1], G[0])
+        moved[j, 4:6] = [G[2] + G[0] * st[j, 4] - G[1] * st[j, 5], G[3] + G[1] * st[j, 4] + G[0] * st[j, 5]]
+        moved[j, 6] = wrap(st[j, 6] + th)
+    for cv in (True, False):
+        q = hostapi.window_params(manifold=manifold, constant_velocity=cv, use_imu=True, weight_imu=64.0, weight_imu_bias=50.0, covariance_scaling_factor=0.3)
+        c0, g0, H0 = hostapi.window_factors(st, q, imu)
+        c1, g1, H1 = hostapi.window_factors(moved, q, imu)
+        assert abs(c1 - c0) <= 1e-9 * c0
+        if manifold:
+            assert np.max(np.abs(g1 - g0)) <= 1e-8 * np.max(np.abs(g0)) and np.max(np.abs(H1 - H0)) <= 1e-8 * np.max(np.abs(H0))
+        else:
+            # additive world-frame position coordinates rotate with G: compare what does not (the cost, and the spectrum of J^T J)
+            assert np.allclose(np.linalg.eigvalsh(H1), np.linalg.eigvalsh(H0), rtol=1e-7, atol=1e-7 * np.max(np.abs(H0)))
+
+
+def test_host_factors_scale_with_the_square_of_the_information_matrix():
+    rng = np.random.default_rng(77)
+    st = make_states(2, rng)
+    q1 = hostapi.window_params(covariance_scaling_factor=0.01)
+    q2 = hostapi.window_params(covariance_scaling_factor=0.03)
+    c1, g1, H1 = hostapi.window_factors(st, q1)
+    c2, g2, H2 = hostapi.window_factors(st, q2)
+    assert abs(c2 - 9.0 * c1) <= 1e-12 * c2
+    assert np.max(np.abs(g2 - 9.0 * g1)) <= 1e-12 * np.max(np.abs(g2)) and np.max(np.abs(H2 - 9.0 * H1)) <= 1e-12 * np.max(np.abs(H2))
