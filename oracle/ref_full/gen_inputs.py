@@ -90,6 +90,7 @@ def window_inputs(rng):
         cases.append(dict(a=a, b=b, imu_rot=float(om * dt + rng.normal(0, 0.01))))
     doc = dict(note="state14 = cos, sin, tx, ty, pos_x, pos_y, rot, vx, vy, omega, ax, ay, imu_bias, stamp", sqrtI=sqrtI.tolist(), weight_imu=64.0,
                weight_imu_bias=750.0, cases=cases)
+    solves = window_solves()      # text file only (the cell tables are float32 values: nine digits round-trip them)
     out = os.path.join(ROOT, "tests", "golden", "ref_full_window_inputs.json")
     with open(out, "w") as f:
         json.dump(doc, f)
@@ -101,7 +102,47 @@ def window_inputs(rng):
         f.write("cases %d\n" % len(cases))
         for c in cases:
             f.write("case\n" + r17(c["a"]) + "\n" + r17(c["b"]) + "\n" + r17([c["imu_rot"]]) + "\n")
+        r9 = lambda v: " ".join("%.9g" % x for x in v)
+        f.write("solves %d\n" % len(solves))
+        for g in solves:
+            f.write("solve %d %d %d %d\n" % (g["W"], len(g["cells_m"]), len(g["cells_f"]), len(g["pair_m"])))
+            f.write("params " + r17(g["params16"]) + "\n")
+            f.write("sqrtI\n" + "\n".join(r17(row) for row in g["sqrtI"]) + "\n")
+            f.write("tolerances " + r17(g["tolerances"]) + "\n")
+            f.write("n_cells %d\n" % g["n_cells"])
+            f.write("states\n" + "\n".join(r17(row) for row in g["states"]) + "\n")
+            f.write("imu " + r17(g["imu"]) + "\n")
+            f.write("cells_m\n" + "\n".join(r9(c) for c in g["cells_m"]) + "\n")
+            f.write("cells_f\n" + "\n".join(r9(c) for c in g["cells_f"]) + "\n")
+            f.write("pair_m " + " ".join(str(i) for i in g["pair_m"]) + "\n")
+            f.write("pair_f " + " ".join(str(i) for i in g["pair_f"]) + "\n")
+            f.write("seg_off " + " ".join(str(i) for i in g["seg_off"]) + "\n")
     print(txt, os.path.getsize(txt), "bytes")
+
+
+def window_solves():
+    """whole window problems for gen_window_fixtures.cpp's "solves" section: the cases of tests/test_window_gpu.py (Oxford as shipped at
+    ceres' default tolerances and with a fixed number of steps; constant acceleration + IMU + two fixed maps; the vector parametrisation)
+    with their NDT pair lists frozen by the oracle's association"""
+    from randt_slam_b200 import hostapi, workloads as W
+    from tests.test_window_gpu import make_case
+    p = P.OXFORD
+    k = p.n_results_nn_lookup
+    out = []
+    for manifold, cv, use_imu, n_fixed, Wn, fixed_steps in ((True, True, False, 1, 3, False), (True, True, False, 1, 3, True), (True, False, True, 2, 3, True),
+                                                           (False, True, True, 1, 2, True)):
+        rng = np.random.default_rng(11 + 7 * Wn + n_fixed)
+        fixed, fixed_se2, window, st = make_case(p, 120, n_fixed, Wn, rng)
+        imu = [0.01 + rng.normal(0, 0.002) for _ in range(Wn)]
+        q = hostapi.window_params(k=k, gnc_steps=p.gnc_steps, loss_scale=p.loss_function_scale, alpha=p.loss_function_convexity,
+                                  divisor=p.gnc_control_parameter_divisor, ndt_weight=p.ndt_weight, manifold=manifold, constant_velocity=cv,
+                                  use_imu=use_imu, weight_imu=64.0, weight_imu_bias=750.0, covariance_scaling_factor=0.01,
+                                  max_iteration=12 if fixed_steps else p.max_iteration)
+        w = W.oracle_window_problem(O, p, fixed, fixed_se2, window, st, k)
+        out.append(dict(W=Wn, params16=q[:16].tolist(), sqrtI=q[16:].reshape(8, 8).tolist(), tolerances=[1e-30] * 3 if fixed_steps else [0.0] * 3,
+                        n_cells=int(w["n_cells"]), states=st.tolist(), imu=imu, cells_m=w["cells_m"].astype(np.float64).tolist(),
+                        cells_f=w["cells_f"].astype(np.float64).tolist(), pair_m=w["im"].tolist(), pair_f=w["jf"].tolist(), seg_off=w["seg_off"].tolist()))
+    return out
 
 
 if __name__ == "__main__":

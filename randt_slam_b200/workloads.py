@@ -348,6 +348,31 @@ def window_odometry_params(hostapi, p, covariance_scaling_factor=0.01, motion_sq
                                  covariance_scaling_factor=covariance_scaling_factor, motion_sqrtI_diag=motion_sqrtI_diag)
 
 
+
+def oracle_window_problem(oracle, p, fixed, fixed_se2, window, st, k):
+    """The NDT blocks of one estimateTransformCeres call on the CPU oracle: every fixed scan voxelised and moved by its pose (one fixed map
+    each), per free window state (st[1:], oldest first) and fixed map the association at the state's own pose (ndt_matcher.cpp:356-359);
+    -> dict(cells_m, cells_f, im, jf, seg_off, n_cells) with one segment per state (tables of the parts back to back)"""
+    va = (p.n_clusters, p.max_range, p.min_points_per_cell, p.size_x, p.size_y, p.resolution, p.max_neighbor_linf_distance)
+    f_tabs = []
+    for pts, T in zip(fixed, fixed_se2):
+        v = oracle.voxelize(pts, *va)
+        f_tabs.append((oracle.transform_cells(v["cells"], *np.asarray(T).astype(np.float32)), v["slot"]))   # transformMap leaves grid_indizes_ alone
+    cells_m, cells_f, im_all, jf_all, seg_off, n_cells = [], [], [], [], [0], 0
+    mb = fb = 0
+    for j in range(1, len(st)):
+        mv = oracle.voxelize(window[j - 1], *va)
+        n_cells += len(mv["cells"])
+        for cells, slot in f_tabs:
+            im, jf = oracle.associate(cells, slot, p.size_x, p.size_y, p.resolution, p.max_neighbor_linf_distance, mv["cells"], st[j, :4], k)
+            im_all.append(im + mb); jf_all.append(jf + fb)
+            cells_m.append(mv["cells"]); cells_f.append(cells)
+            mb += len(mv["cells"]); fb += len(cells)
+        seg_off.append(sum(len(a) for a in im_all))
+    return dict(cells_m=np.concatenate(cells_m), cells_f=np.concatenate(cells_f), im=np.concatenate(im_all).astype(np.uint32),
+                jf=np.concatenate(jf_all).astype(np.uint32), seg_off=np.array(seg_off, np.uint32), n_cells=n_cells)
+
+
 def _se2_exp(u):
     th = u[2]
     if abs(th) < 1e-10:

@@ -41,24 +41,9 @@ def make_case(p, scene, n_fixed, W, rng, perturb=(0.15, 0.15, 0.01)):
 
 def oracle_window(oracle, p, fixed, fixed_se2, window, st, q, trans, imu, tolerances, k):
     """the same blocks on the CPU: per free state, per fixed map, the association at the state's own pose (ndt_matcher.cpp:356-359)"""
-    f_tabs = []
-    for pts, T in zip(fixed, fixed_se2):
-        v = oracle.voxelize(pts, *H.vox_args(p))
-        f_tabs.append((oracle.transform_cells(v["cells"], *T.astype(np.float32)), v["slot"]))   # transformMap leaves grid_indizes_ alone
-    cells_m, cells_f, im_all, jf_all, seg_off, n_cells = [], [], [], [], [0], 0
-    mb = fb = 0
-    for j in range(1, len(st)):
-        mv = oracle.voxelize(window[j - 1], *H.vox_args(p))
-        n_cells += len(mv["cells"])
-        for cells, slot in f_tabs:
-            im, jf = oracle.associate(cells, slot, p.size_x, p.size_y, p.resolution, p.max_neighbor_linf_distance, mv["cells"], st[j, :4], k)
-            im_all.append(im + mb); jf_all.append(jf + fb)
-            cells_m.append(mv["cells"]); cells_f.append(cells)
-            mb += len(mv["cells"]); fb += len(cells)
-        seg_off.append(sum(len(a) for a in im_all))
+    w = W.oracle_window_problem(oracle, p, fixed, fixed_se2, window, st, k)
     qo = q.copy(); qo[14] = 0 if q[7] else 2
-    return oracle.window_solve(st, qo, trans, np.concatenate(cells_m), np.concatenate(cells_f), np.concatenate(im_all).astype(np.uint32),
-                               np.concatenate(jf_all).astype(np.uint32), np.array(seg_off, np.uint32), n_cells, imu=imu, tolerances=tolerances), n_cells
+    return oracle.window_solve(st, qo, trans, w["cells_m"], w["cells_f"], w["im"], w["jf"], w["seg_off"], w["n_cells"], imu=imu, tolerances=tolerances), w["n_cells"]
 
 
 CASES = [
