@@ -42,10 +42,16 @@ def test_round2_bench_line_carries_every_config():
     r = d["registrations"]
     assert r["launches_per_batch"] == 1 and r["failed"] == 0 and r["value"] > 2.5e6
     e = d["e2e"]
-    assert e["d2h_bytes_per_step"] == d["config"]["problems_per_gpu"] * 8 * 15 and e["results_equal_blocking_call"]
+    assert e["d2h_bytes_per_step"] == d["config"]["problems_per_gpu"] * 8 * 10 and e["results_equal_blocking_call"]      # 80-byte basis records
+    assert e["max_rel_difference_vs_blocking_call"] < 1e-13 and e["value"] > 0.9 * d["value"]
+    # the drive through Matcher::estimateTransformCeres (window of three states, motion-model factors)
+    w = c["c4"]["window_odometry"]
+    assert w["scans"] == 1000 and w["rejected_estimates"] == 0 and w["max_position_error_m"] < 1.0
+    assert w["scans_per_s"] > 3 * w["cpu_baseline"]["scans_per_s"] and abs(w["final_speed_m_per_s"] - w["true_speed_m_per_s"]) < 0.1
     # the literal batch gives the same table on 1, 2, 4 and 8 GPUs
     s = json.load(open(os.path.join(ROOT, "profiles", "r02_scaling_1_2_4_8.json")))
     assert len({s[n]["configs_c3"]["table_sha256"] for n in ("1", "2", "4", "8")}) == 1
+    assert all(s[n]["e2e"]["d2h_bytes_per_step"] == 16384 * 80 for n in ("1", "2", "4", "8"))
 
 
 def test_committed_bench_line_keeps_the_contract():
