@@ -589,6 +589,7 @@ void Matcher::solveWindow(SE2d& trans, std::vector<State>& trajectory, const std
     loss.kind = RANDT_LOSS_BARRON; loss.scale = parameters_.loss_function_scale; loss.alpha = parameters_.loss_function_convexity; loss.mu = gnc_mu;
     loss.weight = parameters_.ndt_weight / (double)(n_cells * (size_t)k);
     last = window::minimize(problem, loss, opt, x.data());
+    if (problem.deviceFailed()) throw Error(RANDT_E_CUDA, std::string("estimateTransformCeres: evaluation failed: ") + randt_last_error(ctx_->get()));
     window_summary_.gnc_solves++;
     window_summary_.total_iterations += last.num_iterations;
     gnc_mu /= parameters_.gnc_control_parameter_divisor;

@@ -286,8 +286,10 @@ bool JointProblem::evaluate(const double* x, const randt_loss* loss, bool want_j
     randt_loss none;
     none.kind = RANDT_LOSS_NONE; none.scale = 1.0; none.alpha = 2.0; none.mu = 1.0; none.weight = 1.0;
     // ONE K3 launch: per window state the loss-corrected normal equations of all its residual blocks
-    if (randt_eval_fused(ndt_.ctx, ndt_.problem, ndt_.variant, ndt_.poses, loss ? loss : &none, nullptr, want_jac ? 1 : 0, ndt_.records) != RANDT_OK)
+    if (randt_eval_fused(ndt_.ctx, ndt_.problem, ndt_.variant, ndt_.poses, loss ? loss : &none, nullptr, want_jac ? 1 : 0, ndt_.records) != RANDT_OK) {
+      device_failed_ = true;
       return false;
+    }
     double mr = 0.0;
     for (size_t s = 0; s < S; ++s) {
       const double* rec = &ndt_.records[s * RANDT_FUSED_STRIDE];
@@ -417,6 +419,7 @@ MinimizerSummary minimize(JointProblem& problem, const randt_loss& loss, const r
     // the candidate is evaluated with its Jacobian in the same device launch: an accepted step needs no second evaluation
     double cand_cost = 0.0;
     if (!problem.evaluate(candidate.data(), &loss, true, &cand_cost, g_cand.data(), H_cand.data()) || !std::isfinite(cand_cost)) cand_cost = DBL_MAX;
+    if (problem.deviceFailed()) { summary.termination = 2; break; }     // not a bad step: the device call itself failed
     double step_norm = 0.0;
     for (int i = 0; i < na; ++i) step_norm += (x[i] - candidate[i]) * (x[i] - candidate[i]);
     step_norm = std::sqrt(step_norm);

@@ -71,6 +71,7 @@ class JointProblem {
   bool evaluate(const double* x, const randt_loss* loss, bool want_jac, double* cost, double* g, double* H, double* max_raw = nullptr);
   void evaluateHostFactors(const double* x, bool want_jac, double* cost, double* g, double* H) const;
   int evaluations() const { return n_evals_; }
+  bool deviceFailed() const { return device_failed_; }   // a C-ABI call failed during evaluate (as opposed to a non-finite cost)
   uint32_t ndtBlocks() const { return ndt_blocks_; }
 
  private:
@@ -79,6 +80,7 @@ class JointProblem {
   std::vector<HostFactor> factors_;
   NdtTerm ndt_;
   int n_amb_ = 0, n_tan_ = 0, n_evals_ = 0;
+  bool device_failed_ = false;
   uint32_t ndt_blocks_ = 0;
 };
 
