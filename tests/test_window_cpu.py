@@ -276,3 +276,27 @@ def test_host_factors_scale_with_the_square_of_the_information_matrix():
     c2, g2, H2 = hostapi.window_factors(st, q2)
     assert abs(c2 - 9.0 * c1) <= 1e-12 * c2
     assert np.max(np.abs(g2 - 9.0 * g1)) <= 1e-12 * np.max(np.abs(g2)) and np.max(np.abs(H2 - 9.0 * H1)) <= 1e-12 * np.max(np.abs(H2))
+
+
+@pytest.mark.parametrize("theta", [0.0, 1e-12, 5e-6, 2e-5, 1e-3, 0.7, 3.0])
+def test_se2_log_branches_of_the_motion_factor(oracle, theta):
+    """Sophus' SE2::log switches to a series where cos(theta) - 1 is below 1e-10 in magnitude and otherwise divides by that difference (a
+    cancellation that costs ~1e-6 relative accuracy just outside the switch): the host layer follows it branch for branch — identical to
+    the oracle — and stays within that accuracy of the exact theta/2 cot(theta/2) form on both sides of the switch"""
+    a = np.zeros(14); a[:4] = [math.cos(0.4), math.sin(0.4), 3.0, -1.0]; a[4:7] = [3.0, -1.0, 0.4]; a[7:10] = [2.0, 0.3, 0.0]; a[13] = 0.0
+    pred = se2_mul(a[:4], se2_exp([2.0 * 0.25, 0.3 * 0.25, 0.0]))
+    off = se2_exp([0.31, -0.17, theta])                     # pose_pred^-1 * pose_1
+    b = a.copy(); b[:4] = se2_mul(pred, off); b[4:6] = b[2:4]; b[6] = math.atan2(b[1], b[0]); b[13] = 0.25
+    st = np.array([a, b])
+    q = hostapi.window_params(covariance_scaling_factor=1.0, motion_sqrtI_diag=(1, 1, 1, 1, 1, 1, 1, 1))
+    cost, g, H = hostapi.window_factors(st, q)
+    co, go, Ho, _ = oracle.window_evaluate(st, q)
+    assert cost == co and np.array_equal(g, go) and np.array_equal(H, Ho)
+    # exact: log(off) = (V^-1 t, theta), V^-1 = [[h, theta/2], [-theta/2, h]], h = theta/2 cot(theta/2) (series below 1e-3)
+    h = 1.0 - theta * theta / 12.0 - theta ** 4 / 720.0 if abs(theta) < 1e-3 else (theta / 2.0) / math.tan(theta / 2.0)
+    t = off[2:4]
+    e = np.array([h * t[0] + 0.5 * theta * t[1], -0.5 * theta * t[0] + h * t[1], theta])
+    exact = 0.5 * float(e @ e)
+    in_formula_branch = abs(math.cos(theta) - 1.0) >= 1e-10
+    tol = max(1e-11, 4 * 2.2e-16 / (theta * theta / 2.0)) if in_formula_branch else 1e-11      # cos(theta) - 1 carries one rounding of cos
+    assert abs(cost - exact) <= tol * exact
