@@ -333,3 +333,25 @@ def test_the_oracle_window_solve_ends_in_a_local_minimum_of_the_joint_cost(oracl
     default, _, info_d = oracle.window_solve(g["states"], q, g["states"][-2, :4], *args, g["n_cells"], imu=g["imu"])
     assert 0.0 <= info_d["final_cost"] - c1 <= 1e-4 * c1
     assert 1e-4 < np.max(np.abs(default[:, :4] - tight[:, :4])) < 5e-2
+
+
+def test_the_oracle_window_chain_tracks_a_drive(oracle):
+    """test infrastructure check: LocalFuser::processScan in miniature on the CPU oracle (workloads.oracle_window_replay: predictSE2 ->
+    window solve over three scans with motion-model factors -> delayed keyframe insertion at the smoothed pose) follows a curved 14-scan
+    drive, learns its speed from the motion factors and merges five keyframes — the chain tests/test_window_gpu.py holds the device path to"""
+    from randt_slam_b200 import params as P, workloads as W
+    from tests import helpers as H
+    p = P.OXFORD
+    n = 14
+    truth = np.array([(0.9 * i, 0.015 * i * i, 0.008 * i) for i in range(n)])
+    scans = [H.make_scan(p, 130, tuple(truth[i]), 600 + i) for i in range(n)]
+    stamps = 0.25 * np.arange(n)
+    q = W.window_odometry_params(hostapi, p)
+    poses, states, n_cells, _ = W.oracle_window_replay(oracle, p, scans, stamps, q, 3, 2)
+    est = np.stack([states[:, 2], states[:, 3], np.arctan2(states[:, 1], states[:, 0])], 1)
+    assert np.max(np.abs(est[:, :2] - truth[:, :2])) < 0.15 and np.max(np.abs(est[:, 2] - truth[:, 2])) < 0.01
+    assert abs(np.hypot(states[-1, 7], states[-1, 8]) - 0.9 / 0.25) < 0.8 and n_cells > 100
+    # the estimate returned on arrival and the smoothed state differ (later scans refine the window) but stay close
+    assert 0.0 < np.max(np.abs(poses[1:-1, 2:] - states[1:-1, 2:4])) < 0.1
+    # without the motion factors' help the first prediction is the previous pose: the first solve starts 0.9 m off and still lands
+    assert abs(poses[1, 2] - 0.9) < 0.1
